@@ -1,0 +1,231 @@
+// gca_abi.cu -- the extern "C" surface of libgca.so (see include/gca.h).  Host code only:
+// argument checks, constant derivation (A0) and kernel dispatch by grid shape.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "gca_common.cuh"
+
+namespace gca {
+cudaError_t launch_pack(const gca_params&, const gca_state&, const float*, const float*, const int32_t*,
+                        const int32_t*, const int32_t*, uint8_t*, int32_t*, cudaStream_t);
+cudaError_t launch_unpack(const gca_params&, const gca_state&, float*, float*, int32_t*, cudaStream_t);
+cudaError_t launch_move_modify(const gca_params&, const gca_state&, const int32_t*, cudaStream_t);
+cudaError_t launch_reward_done(const gca_params&, const gca_state&, float*, uint8_t*, int32_t*, cudaStream_t);
+cudaError_t launch_conditional_reset(const gca_params&, const gca_state&, const gca_state&, const float*, float*,
+                                     uint8_t*, cudaStream_t);
+cudaError_t launch_render(const gca_params&, int, const uint8_t*, const uint64_t*, const int32_t*, const uint8_t*,
+                          const int32_t*, const uint8_t*, int, int, uint32_t*, void*, cudaStream_t);
+cudaError_t launch_threefry_bits(const uint32_t*, long long, int, uint32_t*, cudaStream_t);
+cudaError_t launch_threefry_split_part(const uint32_t*, int, uint32_t*, cudaStream_t);
+}  // namespace gca
+
+static thread_local char g_err[256] = "";
+
+static int fail(int code, const char* msg) {
+  std::snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+static int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return GCA_OK;
+  std::snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return GCA_ERR_CUDA;
+}
+static bool is64(const gca_params* p) { return p->H == 64 && p->W == 64; }
+
+extern "C" {
+
+int gca_version(void) { return GCA_VERSION; }
+const char* gca_last_error(void) { return g_err; }
+
+int gca_params_init(gca_params* p, int32_t nrows, int32_t ncols, int32_t K, double speed_move, double speed_act,
+                    double t_any, double t_move, double t_shoot, double p_tree, double p_wind_change,
+                    int32_t rng_mode, const float* winds72) {
+  if (!p) return fail(GCA_ERR_ARG, "gca_params_init: null params");
+  if (nrows < 8 || ncols < 8) return fail(GCA_ERR_UNSUPPORTED, "gca_params_init: grid smaller than 8x8");
+  if (K < 1 || K > GCA_MAX_K) return fail(GCA_ERR_ARG, "gca_params_init: K out of range [1, 8]");
+  if (rng_mode != GCA_RNG_LEGACY && rng_mode != GCA_RNG_PARTITIONABLE)
+    return fail(GCA_ERR_ARG, "gca_params_init: bad rng_mode");
+  std::memset(p, 0, sizeof(*p));
+  p->H = nrows;
+  p->W = ncols;
+  p->K = K;
+  p->rng_mode = rng_mode;
+  // ca_alexandridis_jax.py:57-65 (grid_size = nrows, advanced_bulldozer.py:276-282)
+  const int size = nrows;
+  const int spread = size + size / 2;
+  const double age_min = spread * 1.5, age_max = spread * 1.75;
+  const int R = (int)std::ceil(std::log2((double)size)) - 2;
+  if (R < 1 || R > GCA_MAX_R) return fail(GCA_ERR_UNSUPPORTED, "gca_params_init: burn radius out of range [1, 10]");
+  p->R = R;
+  p->dous_border = (float)(0.0007 * age_max * 0.50);
+  p->dous_inner = (float)(0.006 * age_max * 0.50);
+  // build_burn_kernel (:108-151): 0.065 in total, ring i takes 60 % of what is left
+  double remaining = 0.065;
+  for (int i = 0; i < R; ++i) {
+    const int cells = (2 * i + 3) * (2 * i + 3) - (2 * i + 1) * (2 * i + 1) + (i == 0 ? 1 : 0);
+    double lw;
+    if (i == R - 1) lw = remaining / cells;
+    else { lw = remaining * 0.60 / cells; remaining = remaining * 0.40; }
+    p->ring_w[i + 1] = (float)lw;
+  }
+  p->ring_w[0] = p->ring_w[1];
+  // jax.random.randint(key, shape, fire_age_min, fire_age_max): float bounds truncate
+  const int lo = (int)age_min, hi = (int)age_max;
+  uint32_t span = (uint32_t)(hi - lo);
+  if (hi <= lo) span = 1;
+  uint32_t mult = 65536u % span;
+  mult = (mult * mult) % span;
+  p->age_lo = lo;
+  p->age_span = span;
+  p->age_mult = mult;
+  if (lo <= K) return fail(GCA_ERR_UNSUPPORTED, "gca_params_init: fire_age_min must exceed K");
+  p->day_length = 400;  // advanced_bulldozer.py:733
+  p->p_tree = (float)p_tree;
+  p->p_wind_change = (float)p_wind_change;
+  p->t_any = (float)t_any;
+  // advanced_bulldozer.py:238-246: scale = (nrows + ncols) // 2
+  const int scale = (nrows + ncols) / 2;
+  const double tm = t_move < 0 ? (1.0 / (speed_move * scale)) - t_any : t_move;
+  const double ts = t_shoot < 0 ? (1.0 / (speed_act * scale)) - tm : t_shoot;
+  for (int i = 0; i < 9; ++i) p->t_move[i] = (float)tm;  // every move costs the same (:746-754)
+  for (int i = 0; i < 2; ++i) p->t_shoot[i] = (float)ts;
+  // ca_alexandridis_jax.py:170-173
+  const float pv[6] = {-999.f, (float)-0.1, (float)0.2, (float)0.5, (float)0.8, (float)1.2};
+  const float pd[6] = {-999.f, (float)-0.2, (float)0.2, (float)0.5, (float)0.8, (float)1.2};
+  for (int i = 0; i < 6; ++i) {
+    p->onep_veg[i] = 1.0f + pv[i];
+    p->onep_den[i] = 1.0f + pd[i];
+  }
+  if (winds72) {
+    std::memcpy(p->winds, winds72, sizeof(float) * 72);
+  } else {
+    // init_utils.py:203-245
+    static const int th[8][9] = {
+        {45, 0, 45, 90, 0, 90, 135, 180, 135}, {90, 45, 0, 135, 0, 45, 180, 135, 90},
+        {135, 90, 45, 180, 0, 0, 135, 90, 45}, {180, 135, 90, 135, 0, 45, 90, 45, 0},
+        {135, 180, 135, 90, 0, 90, 45, 0, 45}, {90, 135, 180, 45, 0, 135, 0, 45, 90},
+        {45, 90, 135, 0, 0, 180, 45, 90, 135}, {0, 45, 90, 45, 0, 135, 90, 135, 180}};
+    for (int k = 0; k < 8; ++k)
+      for (int i = 0; i < 9; ++i) {
+        const double t = th[k][i] * (3.14159265358979323846 / 180.0);
+        const double ft = std::exp(10 * 0.131 * (std::cos(t) - 1));
+        p->winds[k * 9 + i] = i == 4 ? 0.0f : (float)(std::exp(0.045 * 10) * ft);
+      }
+  }
+  return GCA_OK;
+}
+
+static int check_state(const gca_params* p, const gca_state* s, const char* who) {
+  if (!p || !s) return fail(GCA_ERR_ARG, who);
+  if (s->N <= 0) return fail(GCA_ERR_ARG, "N must be positive");
+  if (!s->cell || !s->death || !s->doused || !s->tick || !s->key || !s->wind_index)
+    return fail(GCA_ERR_ARG, "state: null cell/death/doused/tick/key/wind_index");
+  return GCA_OK;
+}
+
+int gca_env_step(const gca_params* p, const gca_state* s, const int32_t* actions, const gca_step_out* out,
+                 const gca_inject* inj, const gca_state* snapshot, const float* snapshot_reward, uint32_t flags,
+                 void* stream) {
+  int rc = check_state(p, s, "gca_env_step: null params/state");
+  if (rc) return rc;
+  if (!(flags & GCA_FLAG_CA_ONLY)) {
+    if (!actions || !s->position || !s->time || !s->time_step || !s->is_night)
+      return fail(GCA_ERR_ARG, "gca_env_step: null actions/position/time/time_step/is_night");
+  }
+  if (!(flags & GCA_FLAG_NO_HIDDEN) && !s->hidden) return fail(GCA_ERR_ARG, "gca_env_step: hidden is null");
+  if ((flags & GCA_FLAG_AUTO_RESET) && (!snapshot || !snapshot_reward))
+    return fail(GCA_ERR_ARG, "gca_env_step: auto-reset needs snapshot and snapshot_reward");
+  gca_step_out o;
+  std::memset(&o, 0, sizeof(o));
+  if (out) o = *out;
+  gca_inject j;
+  std::memset(&j, 0, sizeof(j));
+  if (inj) j = *inj;
+  gca_state sn;
+  std::memset(&sn, 0, sizeof(sn));
+  if (snapshot) sn = *snapshot;
+  gca_state st = *s;
+  if (flags & GCA_FLAG_NO_HIDDEN) { st.hidden = nullptr; st.pslope = nullptr; }
+  if (is64(p)) {
+    if (!s->row_min) return fail(GCA_ERR_ARG, "gca_env_step: 64x64 path needs row_min");
+    return check_cuda(gca::launch_env_step64(*p, st, actions, o, j, sn, snapshot_reward, flags, (cudaStream_t)stream),
+                      "env_step64");
+  }
+  return fail(GCA_ERR_UNSUPPORTED, "gca_env_step: only 64x64 grids in this build (tiled path: gca_env_step_tiled)");
+}
+
+int gca_alexandridis_step(const gca_params* p, const gca_state* s, const gca_step_out* out, const gca_inject* inj,
+                          uint32_t flags, void* stream) {
+  return gca_env_step(p, s, nullptr, out, inj, nullptr, nullptr, (flags | GCA_FLAG_CA_ONLY) & ~GCA_FLAG_AUTO_RESET,
+                      stream);
+}
+
+int gca_move_modify(const gca_params* p, const gca_state* s, const int32_t* actions, void* stream) {
+  if (!p || !s || !actions || !s->position || !s->doused) return fail(GCA_ERR_ARG, "gca_move_modify: null argument");
+  return check_cuda(gca::launch_move_modify(*p, *s, actions, (cudaStream_t)stream), "move_modify");
+}
+
+int gca_reward_done(const gca_params* p, const gca_state* s, float* reward, uint8_t* terminated, int32_t* counts,
+                    void* stream) {
+  if (!p || !s || !s->cell) return fail(GCA_ERR_ARG, "gca_reward_done: null argument");
+  return check_cuda(gca::launch_reward_done(*p, *s, reward, terminated, counts, (cudaStream_t)stream), "reward_done");
+}
+
+int gca_conditional_reset(const gca_params* p, const gca_state* s, const gca_state* snapshot,
+                          const float* snapshot_reward, float* reward, uint8_t* terminated, void* stream) {
+  int rc = check_state(p, s, "gca_conditional_reset: null params/state");
+  if (rc) return rc;
+  if (!snapshot || !snapshot_reward || !terminated) return fail(GCA_ERR_ARG, "gca_conditional_reset: null argument");
+  return check_cuda(
+      gca::launch_conditional_reset(*p, *s, *snapshot, snapshot_reward, reward, terminated, (cudaStream_t)stream),
+      "conditional_reset");
+}
+
+int gca_render_rgb(const gca_params* p, int32_t N, const uint8_t* cell, const uint64_t* doused,
+                   const int32_t* position, const uint8_t* night, const int32_t* ext_action,
+                   const uint8_t* env_mask, int32_t enable_extensions, int32_t rgb_u8, uint32_t* scratch,
+                   void* rgb_out, void* stream) {
+  if (!p || N <= 0 || !cell || !doused || !position || !night || !rgb_out)
+    return fail(GCA_ERR_ARG, "gca_render_rgb: null argument");
+  if (enable_extensions && !scratch) return fail(GCA_ERR_ARG, "gca_render_rgb: extensions need a [N] u32 scratch");
+  return check_cuda(gca::launch_render(*p, N, cell, doused, position, night, ext_action, env_mask, enable_extensions,
+                                       rgb_u8, scratch, rgb_out, (cudaStream_t)stream),
+                    "render_rgb");
+}
+
+int gca_pack_state(const gca_params* p, const gca_state* s, const float* true_grid, const float* fire_age,
+                   const int32_t* dousing_count, const int32_t* vegetation, const int32_t* density,
+                   uint8_t* hidden_out, int32_t* err_flag, void* stream) {
+  int rc = check_state(p, s, "gca_pack_state: null params/state");
+  if (rc) return rc;
+  if (!true_grid || !fire_age || !dousing_count) return fail(GCA_ERR_ARG, "gca_pack_state: null input array");
+  if (hidden_out && (!vegetation || !density)) return fail(GCA_ERR_ARG, "gca_pack_state: null vegetation/density");
+  return check_cuda(gca::launch_pack(*p, *s, true_grid, fire_age, dousing_count, vegetation, density, hidden_out,
+                                     err_flag, (cudaStream_t)stream),
+                    "pack_state");
+}
+
+int gca_unpack_state(const gca_params* p, const gca_state* s, float* true_grid, float* fire_age,
+                     int32_t* dousing_count, void* stream) {
+  int rc = check_state(p, s, "gca_unpack_state: null params/state");
+  if (rc) return rc;
+  return check_cuda(gca::launch_unpack(*p, *s, true_grid, fire_age, dousing_count, (cudaStream_t)stream),
+                    "unpack_state");
+}
+
+int gca_threefry_bits(const uint32_t* key2_dev, int64_t n, int32_t rng_mode, uint32_t* out_dev, void* stream) {
+  if (!key2_dev || !out_dev || n <= 0) return fail(GCA_ERR_ARG, "gca_threefry_bits: bad argument");
+  return check_cuda(gca::launch_threefry_bits(key2_dev, (long long)n, rng_mode, out_dev, (cudaStream_t)stream),
+                    "threefry_bits");
+}
+
+int gca_threefry_split(const uint32_t* key2_dev, int32_t num, int32_t rng_mode, uint32_t* out_dev, void* stream) {
+  if (!key2_dev || !out_dev || num <= 0) return fail(GCA_ERR_ARG, "gca_threefry_split: bad argument");
+  if (rng_mode == GCA_RNG_LEGACY)  // split(key, num) = bits(key, 2 num).reshape(num, 2)
+    return check_cuda(gca::launch_threefry_bits(key2_dev, 2ll * num, rng_mode, out_dev, (cudaStream_t)stream),
+                      "threefry_split");
+  return check_cuda(gca::launch_threefry_split_part(key2_dev, num, out_dev, (cudaStream_t)stream), "threefry_split");
+}
+
+}  // extern "C"

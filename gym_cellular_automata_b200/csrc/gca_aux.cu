@@ -1,0 +1,357 @@
+// gca_aux.cu -- boundary kernels around the fused step: reference-layout <-> packed state,
+// stand-alone move/douse, reward/done, conditional_reset, RGB observation, PRNG test hooks.
+// Reference lines are cited per kernel (paths relative to
+// /root/reference/gym_cellular_automata/).
+#include "gca_common.cuh"
+
+namespace gca {
+
+// ---------------------------------------------------------------------------------------------
+// pack / unpack: the float32/int32 context pytree of _initial_context_distribution
+// (forest_fire/bulldozer/advanced_bulldozer.py:690-743) <-> packed state.
+// One warp per grid row segment of 64 columns.
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_state_kernel(gca_params P, gca_state S, const float* __restrict__ grid,
+                                  const float* __restrict__ fire_age, const int32_t* __restrict__ dousing,
+                                  const int32_t* __restrict__ veg, const int32_t* __restrict__ den,
+                                  uint8_t* __restrict__ hidden_out, int32_t* err_flag) {
+  const int H = P.H, W = P.W, WW = (W + 63) >> 6;
+  const int lane = threadIdx.x & 31;
+  const long long seg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nseg = (long long)S.N * H * WW;
+  if (seg >= nseg) return;
+  const int ws = (int)(seg % WW);
+  const long long er = seg / WW;  // e * H + r
+  const int e = (int)(er / H);
+  const uint32_t tick = S.tick[e];
+  uint32_t rowmin = 0xFFFFFFFFu;
+  unsigned long long dmask = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = ws * 64 + h * 32 + lane;
+    bool dbit = false;
+    if (c < W) {
+      const size_t i = (size_t)er * W + c;
+      const float g = grid[i];
+      const int code = g == 2.0f ? 2 : (g == 1.0f ? 1 : 0);
+      if (!(g == 0.0f || g == 1.0f || g == 2.0f) && err_flag) atomicOr(err_flag, 1);
+      S.cell[i] = (uint8_t)code;
+      const float a = fire_age[i];
+      const int ai = (int)a;
+      uint32_t field;
+      if (code == 2) {
+        if (!(a >= 1.0f && a <= 32767.0f && (float)ai == a) && err_flag) atomicOr(err_flag, 2);
+        const uint32_t dabs = tick + (uint32_t)max(ai, 1) - 1u;  // burns out at this tick
+        field = dabs & 0xFFFFu;
+        rowmin = min(rowmin, dabs);
+      } else {
+        if (!(a >= 0.0f && a <= 65535.0f && (float)ai == a) && err_flag) atomicOr(err_flag, 4);
+        field = (uint32_t)min(max(ai, 0), 65535);
+      }
+      S.death[i] = (uint16_t)field;
+      if (hidden_out != nullptr) {
+        const int v = veg[i], d = den[i];
+        if ((v < 0 || v > 7 || d < 0 || d > 7) && err_flag) atomicOr(err_flag, 8);
+        hidden_out[i] = (uint8_t)((v & 7) | ((d & 7) << 3));
+      }
+      const int dc = dousing[i];
+      if (!(dc == 0 || dc == 1) && err_flag) atomicOr(err_flag, 16);
+      dbit = dc != 0;
+    }
+    dmask |= (unsigned long long)__ballot_sync(GCA_FULL, dbit) << (32 * h);
+  }
+  if (lane == 0) S.doused[seg] = dmask;
+  // row_min is only defined (and only used) for single-segment rows, i.e. W <= 64
+  rowmin = __reduce_min_sync(GCA_FULL, rowmin);
+  if (lane == 0 && S.row_min != nullptr && WW == 1) S.row_min[er] = rowmin;
+}
+
+__global__ void unpack_state_kernel(gca_params P, gca_state S, float* __restrict__ grid,
+                                    float* __restrict__ fire_age, int32_t* __restrict__ dousing) {
+  const int H = P.H, W = P.W, WW = (W + 63) >> 6;
+  const size_t n = (size_t)S.N * H * W;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)(i % W);
+  const size_t er = i / W;
+  const int e = (int)(er / H);
+  const int code = S.cell[i];
+  if (grid) grid[i] = (float)code;
+  if (fire_age) {
+    const uint32_t f = S.death[i];
+    fire_age[i] = code == 2 ? (float)(((f - S.tick[e]) & 0xFFFFu) + 1u) : (float)f;
+  }
+  if (dousing) dousing[i] = (int32_t)((S.doused[er * WW + (c >> 6)] >> (c & 63)) & 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// MoveJax / ModifyJax (forest_fire/operators/move_modify_jax.py:39-62,102-114)
+// ---------------------------------------------------------------------------------------------
+__global__ void move_modify_kernel(gca_params P, gca_state S, const int32_t* __restrict__ actions) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= S.N) return;
+  const int WW = (P.W + 63) >> 6;
+  int row = S.position[2 * e], col = S.position[2 * e + 1];
+  move_position(actions[3 * e], P.H, P.W, row, col);
+  S.position[2 * e] = row;
+  S.position[2 * e + 1] = col;
+  if (actions[3 * e + 1] == 1) S.doused[((size_t)e * P.H + row) * WW + (col >> 6)] |= 1ull << (col & 63);
+}
+
+// ---------------------------------------------------------------------------------------------
+// count_cells + _award + _is_done (advanced_bulldozer.py:597-633,941-953): one CTA per env
+// ---------------------------------------------------------------------------------------------
+__global__ void reward_done_kernel(gca_params P, gca_state S, float* reward, uint8_t* terminated, int32_t* counts) {
+  const int e = blockIdx.x;
+  const size_t n = (size_t)P.H * P.W;
+  const uint8_t* g = S.cell + (size_t)e * n;
+  int t = 0, f = 0;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = g[i];
+    t += c == 1;
+    f += c == 2;
+  }
+  __shared__ int st, sf;
+  if (threadIdx.x == 0) { st = 0; sf = 0; }
+  __syncthreads();
+  t = __reduce_add_sync(GCA_FULL, t);
+  f = __reduce_add_sync(GCA_FULL, f);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&st, t); atomicAdd(&sf, f); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (reward) reward[e] = award(st, sf);
+    if (terminated) terminated[e] = sf == 0;
+    if (counts) { counts[2 * e] = st; counts[2 * e + 1] = sf; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conditional_reset (advanced_bulldozer.py:422-518): one CTA per env; envs that are not
+// terminated exit immediately.
+// ---------------------------------------------------------------------------------------------
+__global__ void conditional_reset_kernel(gca_params P, gca_state S, gca_state SNAP, const float* __restrict__ snap_reward,
+                                         float* reward, uint8_t* terminated) {
+  const int e = blockIdx.x;
+  if (!terminated[e]) return;
+  const int H = P.H, W = P.W, WW = (W + 63) >> 6;
+  const size_t n = (size_t)H * W, base = (size_t)e * n;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+    S.cell[base + i] = SNAP.cell[base + i];
+    S.death[base + i] = SNAP.death[base + i];
+  }
+  for (size_t i = threadIdx.x; i < (size_t)H * WW; i += blockDim.x)
+    S.doused[(size_t)e * H * WW + i] = SNAP.doused[(size_t)e * H * WW + i];
+  if (S.row_min != nullptr && SNAP.row_min != nullptr && WW == 1)
+    for (int i = threadIdx.x; i < H; i += blockDim.x) S.row_min[(size_t)e * H + i] = SNAP.row_min[(size_t)e * H + i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    S.key[2 * e] = SNAP.key[2 * e];
+    S.key[2 * e + 1] = SNAP.key[2 * e + 1];
+    S.wind_index[e] = SNAP.wind_index[e];
+    S.position[2 * e] = SNAP.position[2 * e];
+    S.position[2 * e + 1] = SNAP.position[2 * e + 1];
+    S.time[e] = SNAP.time[e];
+    S.tick[e] = SNAP.tick[e];
+    if (S.steps_elapsed) S.steps_elapsed[e] = 0.0f;
+    if (S.reward_accumulated) S.reward_accumulated[e] = 0.0f;
+    if (reward) reward[e] = snap_reward[e];
+    terminated[e] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Observation (advanced_bulldozer.py:988-1101; extension_utils.py:99-195).
+// pass 1 (only with extensions): per-env flags  bit0 any(grid > 0), bit1 any(grid[0,:] > 0),
+//                                               bit2 any(blur > 0), bit3 any(blur[0,:] > 0)
+// pass 2: one thread per cell.
+// blur = round(3 * sum_{3x3, edge padded}(g/3)/9) = (S >= 5) + (S >= 14) with S the integer sum:
+// the mean S/9 is never within 0.05 of a rounding boundary, so float32 rounding cannot matter.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int blur_at(const uint8_t* g, int H, int W, int r, int c) {
+  int s = 0;
+#pragma unroll
+  for (int di = -1; di <= 1; ++di) {
+    const int rr = min(max(r + di, 0), H - 1);
+#pragma unroll
+    for (int dj = -1; dj <= 1; ++dj) {
+      const int cc = min(max(c + dj, 0), W - 1);
+      s += g[(size_t)rr * W + cc];
+    }
+  }
+  return (s >= 5) + (s >= 14);
+}
+
+__global__ void render_flags_kernel(gca_params P, const uint8_t* __restrict__ cell, uint32_t* flags) {
+  const int e = blockIdx.y;
+  const int H = P.H, W = P.W;
+  const size_t n = (size_t)H * W;
+  const uint8_t* g = cell + (size_t)e * n;
+  uint32_t fl = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / W), c = (int)(i % W);
+    if (g[i] > 0) fl |= 1u | (r == 0 ? 2u : 0u);
+    if (blur_at(g, H, W, r, c) > 0) fl |= 4u | (r == 0 ? 8u : 0u);
+  }
+  fl = __reduce_or_sync(GCA_FULL, fl);
+  if ((threadIdx.x & 31) == 0 && fl) atomicOr(&flags[e], fl);
+}
+
+template <bool U8>
+__global__ void render_rgb_kernel(gca_params P, int N, const uint8_t* __restrict__ cell,
+                                  const unsigned long long* __restrict__ doused, const int32_t* __restrict__ position,
+                                  const uint8_t* __restrict__ night, const int32_t* __restrict__ ext_action,
+                                  const uint8_t* __restrict__ env_mask, int enable_ext,
+                                  const uint32_t* __restrict__ flags, void* out) {
+  const int H = P.H, W = P.W, WW = (W + 63) >> 6;
+  const size_t n = (size_t)H * W;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * n) return;
+  const int e = (int)(i / n);
+  if (env_mask != nullptr && env_mask[e] == 0) return;
+  const size_t ci = i % n;
+  const int r = (int)(ci / W), c = (int)(ci % W);
+  const uint8_t* g = cell + (size_t)e * n;
+  int disp = g[ci];
+  if (enable_ext) {
+    // channel 0 = blurred grid; extension channel 0 = raw grid (action bit 0), channel 1 = blurred
+    // grid (bit 1); the display channel index is the FIRST ROW holding a positive extension
+    // value, clamped to 1 (advanced_bulldozer.py:1028-1032).
+    const int ext = ext_action ? ext_action[e] : 0;
+    const uint32_t fl = flags[e];
+    const int blur = blur_at(g, H, W, r, c);
+    if (ext == 1) {        // bits (1,0): ext0 = raw grid, ext1 = 0
+      if (fl & 1u) disp = (fl & 2u) ? disp : 0;
+      else disp = blur;
+    } else if (ext == 2) { // bits (0,1): ext0 = 0, ext1 = blurred grid
+      if (fl & 4u) disp = (fl & 8u) ? 0 : blur;
+      else disp = blur;
+    } else {
+      disp = blur;
+    }
+  }
+  const bool ng = night[e] != 0;
+  float cr, cg, cb;
+  if (!ng) {
+    if (disp == 1) { cr = 169.f; cg = 196.f; cb = 153.f; }       // #A9C499
+    else if (disp == 2) { cr = 230.f; cg = 129.f; cb = 129.f; }  // #E68181
+    else { cr = 221.f; cg = 209.f; cb = 211.f; }                 // #DDD1D3
+  } else {
+    if (disp == 1) { cr = 47.f; cg = 79.f; cb = 79.f; }          // #2F4F4F
+    else if (disp == 2) { cr = 139.f; cg = 0.f; cb = 0.f; }      // #8B0000
+    else { cr = 105.f; cg = 105.f; cb = 105.f; }                 // #696969
+  }
+  const bool ds = (doused[((size_t)e * H + r) * WW + (c >> 6)] >> (c & 63)) & 1ull;
+  if (ds) {  // rgb * (1 - 0.75) + tint * 0.75, float32, tint blue by day / orange by night
+    const float tr = ng ? 255.f : 0.f, tg = ng ? 165.f : 0.f, tb = ng ? 0.f : 200.f;
+    cr = __fadd_rn(__fmul_rn(cr, 0.25f), __fmul_rn(tr, 0.75f));
+    cg = __fadd_rn(__fmul_rn(cg, 0.25f), __fmul_rn(tg, 0.75f));
+    cb = __fadd_rn(__fmul_rn(cb, 0.25f), __fmul_rn(tb, 0.75f));
+  }
+  if (position[2 * e] == r && position[2 * e + 1] == c) { cr = 0.f; cg = 0.f; cb = 0.f; }
+  if (U8) {
+    uint8_t* o = reinterpret_cast<uint8_t*>(out) + i * 3;
+    o[0] = (uint8_t)cr; o[1] = (uint8_t)cg; o[2] = (uint8_t)cb;
+  } else {
+    float* o = reinterpret_cast<float*>(out) + i * 3;
+    o[0] = cr; o[1] = cg; o[2] = cb;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PRNG test hooks
+// ---------------------------------------------------------------------------------------------
+__global__ void threefry_bits_kernel(const uint32_t* __restrict__ key, long long n, int mode, uint32_t* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const TfKey k = tf_key(key[0], key[1]);
+  if (n == 1) { out[0] = bits_scalar(k, mode); return; }
+  if (mode == GCA_RNG_LEGACY) {
+    const long long m = n + (n & 1), half = m / 2;
+    const bool first = i < half;
+    uint32_t c0 = (uint32_t)(first ? i : i - half);
+    uint32_t c1 = (uint32_t)(first ? i + half : i);
+    if ((n & 1) && (first ? i + half : i) == m - 1) c1 = 0u;  // padded counter
+    uint32_t o0, o1;
+    threefry2x32(k, c0, c1, o0, o1);
+    out[i] = first ? o0 : o1;
+  } else {
+    uint32_t o0, o1;
+    threefry2x32(k, (uint32_t)((unsigned long long)i >> 32), (uint32_t)i, o0, o1);
+    out[i] = o0 ^ o1;
+  }
+}
+
+// partitionable split(key, num)[i] = both words of block (0, i)
+__global__ void threefry_split_part_kernel(const uint32_t* __restrict__ key, int num, uint32_t* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num) return;
+  uint32_t o0, o1;
+  threefry2x32(tf_key(key[0], key[1]), 0u, (uint32_t)i, o0, o1);
+  out[2 * i] = o0;
+  out[2 * i + 1] = o1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_pack(const gca_params& p, const gca_state& s, const float* grid, const float* fire_age,
+                        const int32_t* dousing, const int32_t* veg, const int32_t* den, uint8_t* hidden_out,
+                        int32_t* err_flag, cudaStream_t st) {
+  const int WW = (p.W + 63) >> 6;
+  const long long nseg = (long long)s.N * p.H * WW;
+  const int wpb = 8;
+  pack_state_kernel<<<(unsigned)((nseg + wpb - 1) / wpb), wpb * 32, 0, st>>>(p, s, grid, fire_age, dousing, veg, den,
+                                                                           hidden_out, err_flag);
+  return cudaGetLastError();
+}
+cudaError_t launch_unpack(const gca_params& p, const gca_state& s, float* grid, float* fire_age, int32_t* dousing,
+                          cudaStream_t st) {
+  const size_t n = (size_t)s.N * p.H * p.W;
+  unpack_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, s, grid, fire_age, dousing);
+  return cudaGetLastError();
+}
+cudaError_t launch_move_modify(const gca_params& p, const gca_state& s, const int32_t* actions, cudaStream_t st) {
+  move_modify_kernel<<<(s.N + 127) / 128, 128, 0, st>>>(p, s, actions);
+  return cudaGetLastError();
+}
+cudaError_t launch_reward_done(const gca_params& p, const gca_state& s, float* reward, uint8_t* terminated,
+                               int32_t* counts, cudaStream_t st) {
+  reward_done_kernel<<<s.N, 256, 0, st>>>(p, s, reward, terminated, counts);
+  return cudaGetLastError();
+}
+cudaError_t launch_conditional_reset(const gca_params& p, const gca_state& s, const gca_state& snap,
+                                     const float* snap_reward, float* reward, uint8_t* terminated, cudaStream_t st) {
+  conditional_reset_kernel<<<s.N, 256, 0, st>>>(p, s, snap, snap_reward, reward, terminated);
+  return cudaGetLastError();
+}
+cudaError_t launch_render(const gca_params& p, int N, const uint8_t* cell, const uint64_t* doused,
+                          const int32_t* position, const uint8_t* night, const int32_t* ext_action,
+                          const uint8_t* env_mask, int enable_ext, int rgb_u8, uint32_t* flags_scratch, void* out,
+                          cudaStream_t st) {
+  const size_t n = (size_t)N * p.H * p.W;
+  if (enable_ext) {
+    cudaError_t err = cudaMemsetAsync(flags_scratch, 0, sizeof(uint32_t) * N, st);
+    if (err != cudaSuccess) return err;
+    const size_t per = (size_t)p.H * p.W;
+    dim3 grid((unsigned)min((size_t)64, (per + 255) / 256), (unsigned)N);
+    render_flags_kernel<<<grid, 256, 0, st>>>(p, cell, flags_scratch);
+  }
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (rgb_u8)
+    render_rgb_kernel<true><<<blocks, 256, 0, st>>>(p, N, cell, (const unsigned long long*)doused, position, night,
+                                                    ext_action, env_mask, enable_ext, flags_scratch, out);
+  else
+    render_rgb_kernel<false><<<blocks, 256, 0, st>>>(p, N, cell, (const unsigned long long*)doused, position, night,
+                                                     ext_action, env_mask, enable_ext, flags_scratch, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_threefry_split_part(const uint32_t* key, int num, uint32_t* out, cudaStream_t st) {
+  threefry_split_part_kernel<<<(num + 255) / 256, 256, 0, st>>>(key, num, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_threefry_bits(const uint32_t* key, long long n, int mode, uint32_t* out, cudaStream_t st) {
+  threefry_bits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key, n, mode, out);
+  return cudaGetLastError();
+}
+
+}  // namespace gca

@@ -1,0 +1,682 @@
+// gca_step64.cu -- fused environment step for 64x64 grids: ONE WARP PER ENVIRONMENT.
+//
+// Replaces, for a batch of envs, jax.vmap(MDP.update) + _award + _is_done (+ conditional_reset)
+// of /root/reference/gym_cellular_automata/forest_fire/bulldozer/advanced_bulldozer.py:332-518,
+// 1103-1133 and the operators it calls (ca_alexandridis_jax.py:321-460, repeat_ca_jax.py:34-71,
+// move_modify_jax.py:39-157).  Not a translation: the reference materialises (H,W,9,9) gathers and
+// draws 12 random words per cell; this kernel works on bit-boards and draws lazily.
+//
+// Design:
+//  * a 64-cell row is one 64-bit word per mask (tree, fire, doused).  Lane l owns rows 2l, 2l+1 in
+//    registers; vertical halos come from warp shuffles.
+//  * all K CA sub-steps of the env step are applied on-chip (temporal blocking); HBM sees one
+//    coalesced 128-bit read of the u8 grid and sparse in-place writes of the cells that changed.
+//  * front cells (tree with a burning Moore neighbour) are compacted into a shared-memory list;
+//    per front cell the 9x9 fire window is cut out of the bit-board, ring populations give a fast
+//    float32 enclosure [lo, hi] of the burn-probability chain; per (cell, burning direction) one
+//    counter-based threefry2x32 block reproduces exactly the uniform jax.random would have
+//    drawn for that element.  u < lo ignites, u >= hi does not, and the (rare) in-between case is
+//    re-evaluated with the reference's exact row-major float32 summation ("threshold cells").
+//  * fire ages are stored as burn-out ticks, so burning cells need no per-step decrement; a
+//    per-row minimum tells which rows hold a cell that burns out in this step.
+//  * the key chain of jax.random.split is evaluated by lane pairs; clock, move, douse, day/night,
+//    reward (popc + warp reduce), done and the optional auto-reset are fused in the epilogue.
+#include "gca_common.cuh"
+
+namespace gca {
+
+constexpr int S64_WARPS = 4;    // envs per CTA
+constexpr int S64_CAP = 256;    // front cells per pass
+constexpr int S64_PCAP = 512;   // (cell, direction) draws buffered before a flush
+constexpr uint32_t S64_HALF_BURN = 9u * 4096u / 2u;
+constexpr uint32_t S64_HALF_CELL = 4096u / 2u;
+// enclosure half-width of the fast float32 path: |sequential sum - ring-count sum| <= 89 u |sum|
+// (80 adds + 8 flops, u = 2^-24); 2^-16 = 256 u leaves a 2.8x margin.
+#define S64_LO 0.9999847412109375f   /* 1 - 2^-16 */
+#define S64_HI 1.0000152587890625f   /* 1 + 2^-16 */
+
+struct __align__(16) WarpSmem {
+  uint32_t fire32[72 * 4];        // fire rows -4..67, 4 overlapping 32-bit views per row
+  uint32_t dous32[68 * 4];        // doused rows -2..65, same views
+  unsigned long long ign[64];     // ignition accumulator (unpack: tree rows)
+  float base_lo[S64_CAP];         // per front cell: enclosure of (p_h (1+p_veg)) (1+p_den)
+  float base_hi[S64_CAP];         //   (unpack: fire rows, aliased)
+  uint16_t list[S64_CAP];         // front cells of the current pass: (row << 6) | col
+  uint16_t pairs[S64_PCAP];       // (list index << 4) | direction
+  uint32_t sched[GCA_MAX_K][12];  // per sub-step: Sburn[2] Sgrow[2] ak1[2] ak2[2] wind change step pad
+};
+
+// view k of a row covers columns 16k-4 .. 16k+27 (bit b <-> column 16k-4+b)
+__device__ __forceinline__ void store_row_views(uint32_t* dst, unsigned long long x) {
+  uint4 w;
+  w.x = (uint32_t)(x << 4);
+  w.y = (uint32_t)(x >> 12);
+  w.z = (uint32_t)(x >> 28);
+  w.w = (uint32_t)(x >> 44);
+  *reinterpret_cast<uint4*>(dst) = w;
+}
+
+// 16 u8 cells -> 16-bit tree and fire masks (bit i = cell i)
+__device__ __forceinline__ void cells16_to_bits(const uint4& v, uint32_t& t16, uint32_t& f16) {
+  const uint32_t M = 0x00204081u;  // gathers bit 0 of each byte into bits 21..24
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  t16 = 0;
+  f16 = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t tb = w[k] & 0x01010101u;
+    const uint32_t fb = (w[k] >> 1) & 0x01010101u;
+    t16 |= (((tb * M) >> 21) & 0xFu) << (4 * k);
+    f16 |= (((fb * M) >> 21) & 0xFu) << (4 * k);
+  }
+}
+
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
+  const uint32_t lo = __shfl_sync(GCA_FULL, (uint32_t)v, src);
+  const uint32_t hi = __shfl_sync(GCA_FULL, (uint32_t)(v >> 32), src);
+  return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long shfl64_up1(unsigned long long v, int lane) {
+  const uint32_t lo = __shfl_up_sync(GCA_FULL, (uint32_t)v, 1);
+  const uint32_t hi = __shfl_up_sync(GCA_FULL, (uint32_t)(v >> 32), 1);
+  return lane == 0 ? 0ull : (((unsigned long long)hi << 32) | lo);
+}
+__device__ __forceinline__ unsigned long long shfl64_down1(unsigned long long v, int lane) {
+  const uint32_t lo = __shfl_down_sync(GCA_FULL, (uint32_t)v, 1);
+  const uint32_t hi = __shfl_down_sync(GCA_FULL, (uint32_t)(v >> 32), 1);
+  return lane == 31 ? 0ull : (((unsigned long long)hi << 32) | lo);
+}
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(GCA_FULL, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+
+// one threefry block per lane with lane-specific key/counters, words swapped inside the lane pair
+__device__ __forceinline__ void tf_exchange(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t& o0,
+                                            uint32_t& o1, uint32_t& p0, uint32_t& p1) {
+  threefry2x32(tf_key(k0, k1), c0, c1, o0, o1);
+  p0 = __shfl_xor_sync(GCA_FULL, o0, 1);
+  p1 = __shfl_xor_sync(GCA_FULL, o1, 1);
+}
+__device__ __forceinline__ void assemble_split(int mode, uint32_t w, uint32_t o0, uint32_t o1, uint32_t p0,
+                                               uint32_t p1, uint32_t& n0, uint32_t& n1, uint32_t& s0,
+                                               uint32_t& s1) {
+  const uint32_t a0 = w ? p0 : o0, a1 = w ? p1 : o1;
+  const uint32_t b0 = w ? o0 : p0, b1 = w ? o1 : p1;
+  if (mode == GCA_RNG_LEGACY) { n0 = a0; n1 = b0; s0 = a1; s1 = b1; }
+  else { n0 = a0; n1 = a1; s0 = b0; s1 = b1; }
+}
+
+// Key schedule of K successive PartiallyObservableForestFireJax.update calls
+// (ca_alexandridis_jax.py:436-448 and :352-368).  The chain K0 -> K1 -> K2 -> K3 is sequential
+// (3K split levels, every lane pair runs it redundantly -- free in SIMT); pair 2j then derives
+// sub-step j's Sburn / Sgrow / randint keys and pair 2j+1 its wind draws (4 more levels).
+__device__ __noinline__ void key_schedule(WarpSmem& sm, const gca_params& P, const gca_inject& J, int N, int e,
+                                          int lane, uint32_t& key0, uint32_t& key1, int& widx) {
+  const int K = P.K, mode = P.rng_mode;
+  const int pair = lane >> 1;
+  const uint32_t w = lane & 1;
+  uint32_t k0 = key0, k1 = key1;
+  uint32_t c0 = 0, c1 = 0, sw0 = 0, sw1 = 0;
+  for (int j = 0; j < K; ++j) {
+    uint32_t n0, n1, s0, s1;
+    split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K1, S1
+    if (pair == 2 * j) { c0 = s0; c1 = s1; }
+    k0 = n0; k1 = n1;
+    split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K2, Swind
+    if (pair == 2 * j + 1) { sw0 = s0; sw1 = s1; }
+    k0 = n0; k1 = n1;
+    split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K3, Sidx
+    if (pair == 2 * j + 1) { c0 = s0; c1 = s1; }
+    k0 = n0; k1 = n1;
+  }
+  key0 = k0;
+  key1 = k1;
+  const bool burn_role = (pair & 1) == 0;
+  const int j = pair >> 1;
+  const uint32_t sc0 = (mode == GCA_RNG_LEGACY) ? w : 0u;       // split counters of this lane
+  const uint32_t sc1 = (mode == GCA_RNG_LEGACY) ? w + 2u : w;
+  uint32_t o0, o1, p0, p1, n0, n1, s0, s1;
+  // level 1: burn: split(S1) -> Ka, Sburn ; wind: split(Sidx) -> wk1, wk2
+  tf_exchange(c0, c1, sc0, sc1, o0, o1, p0, p1);
+  assemble_split(mode, w, o0, o1, p0, p1, n0, n1, s0, s1);
+  const uint32_t sburn0 = s0, sburn1 = s1;  // (wind role: wk2)
+  uint32_t cur0 = n0, cur1 = n1;            // burn: Ka ; wind: wk1
+  // level 2: burn: split(Ka) -> Kb, Sgrow ; wind: even lane bits(wk1,()), odd lane bits(wk2,())
+  {
+    const uint32_t kk0 = burn_role ? cur0 : (w ? sburn0 : cur0);
+    const uint32_t kk1 = burn_role ? cur1 : (w ? sburn1 : cur1);
+    tf_exchange(kk0, kk1, burn_role ? sc0 : 0u, burn_role ? sc1 : 0u, o0, o1, p0, p1);
+  }
+  assemble_split(mode, w, o0, o1, p0, p1, n0, n1, s0, s1);
+  const uint32_t sgrow0 = s0, sgrow1 = s1;
+  // wind role: hb = even lane's word, lb = odd lane's word
+  const uint32_t my_bits = (mode == GCA_RNG_LEGACY) ? o0 : (o0 ^ o1);
+  const uint32_t pr_bits = (mode == GCA_RNG_LEGACY) ? p0 : (p0 ^ p1);
+  const uint32_t hb = w ? pr_bits : my_bits, lb = w ? my_bits : pr_bits;
+  cur0 = n0; cur1 = n1;  // burn: Kb
+  // level 3: burn: split(Kb) -> Kc, Sage ; wind: bits(Swind, ())
+  tf_exchange(burn_role ? cur0 : sw0, burn_role ? cur1 : sw1, burn_role ? sc0 : 0u, burn_role ? sc1 : 0u,
+              o0, o1, p0, p1);
+  assemble_split(mode, w, o0, o1, p0, p1, n0, n1, s0, s1);
+  const uint32_t uw_bits = (mode == GCA_RNG_LEGACY) ? o0 : (o0 ^ o1);
+  // level 4: burn: split(Sage) -> ak1, ak2
+  tf_exchange(s0, s1, sc0, sc1, o0, o1, p0, p1);
+  uint32_t a10, a11, a20, a21;
+  assemble_split(mode, w, o0, o1, p0, p1, a10, a11, a20, a21);
+  if (j < K && w == 0) {
+    uint32_t* sc = sm.sched[j];
+    if (burn_role) {
+      sc[0] = sburn0; sc[1] = sburn1; sc[2] = sgrow0; sc[3] = sgrow1;
+      sc[4] = a10; sc[5] = a11; sc[6] = a20; sc[7] = a21;
+    } else {
+      float u = bits_to_uniform(uw_bits);
+      int step = randint_from_bits(hb, lb, 1, 7u, 4u);
+      if (J.u_wind) u = J.u_wind[(size_t)j * N + e];
+      if (J.wind_step) step = J.wind_step[(size_t)j * N + e];
+      sc[9] = (u < P.p_wind_change) ? 1u : 0u;
+      sc[10] = (uint32_t)step;
+    }
+  }
+  __syncwarp();
+  int wi = widx;
+  for (int q = 0; q < K; ++q) {
+    if (lane == 0) sm.sched[q][8] = (uint32_t)wi;
+    if (sm.sched[q][9]) wi = (wi + (int)sm.sched[q][10]) % 8;
+  }
+  widx = wi;
+  __syncwarp();
+}
+
+// 9x9 fire window of cell (r, c): rows r-4..r+4 packed 3 per word (9 bits each)
+__device__ __forceinline__ void fire_window(const WarpSmem& sm, int r, int c, uint32_t& A, uint32_t& B,
+                                            uint32_t& C) {
+  const uint32_t* fw = sm.fire32 + r * 4 + (c >> 4);
+  const int o = c & 15;
+  uint32_t wv[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) wv[i] = (fw[i * 4] >> o) & 0x1FFu;
+  A = wv[0] | (wv[1] << 9) | (wv[2] << 18);
+  B = wv[3] | (wv[4] << 9) | (wv[5] << 18);
+  C = wv[6] | (wv[7] << 9) | (wv[8] << 18);
+}
+// 5x5 doused window: rows r-2..r+2, 5 bits each
+__device__ __forceinline__ uint32_t dous_window(const WarpSmem& sm, int r, int c) {
+  const uint32_t* dw = sm.dous32 + r * 4 + (c >> 4);
+  const int o = (c & 15) + 2;
+  uint32_t v = 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) v |= ((dw[i * 4] >> o) & 0x1Fu) << (5 * i);
+  return v;
+}
+
+// Exact (reference-order) value of (heat - dousing) (1+p_veg) (1+p_den) for one cell: row-major
+// sequential float32 sums with the accumulator starting at +0 (oracle/alexandridis.py:_window_sum).
+__device__ __noinline__ float exact_base(const WarpSmem& sm, const gca_params& P, int r, int c, float a, float b) {
+  uint32_t A, B, C;
+  fire_window(sm, r, c, A, B, C);
+  const uint32_t rows3[3] = {A, B, C};
+  float heat = 0.0f;
+  for (int i = 0; i < 9; ++i) {
+    const uint32_t bits = (rows3[i / 3] >> (9 * (i % 3))) & 0x1FFu;
+    const int di = i < 4 ? 4 - i : i - 4;
+    for (int jj = 0; jj < 9; ++jj) {
+      if ((bits >> jj) & 1u) {
+        const int dj = jj < 4 ? 4 - jj : jj - 4;
+        const int ring = di > dj ? di : dj;
+        heat = __fadd_rn(heat, P.ring_w[ring]);
+      }
+    }
+  }
+  const uint32_t dwin = dous_window(sm, r, c);
+  float dous = 0.0f;
+  for (int i = 0; i < 5; ++i)
+    for (int jj = 0; jj < 5; ++jj)
+      if ((dwin >> (5 * i + jj)) & 1u) {
+        const bool inner = i >= 1 && i <= 3 && jj >= 1 && jj <= 3;
+        dous = __fadd_rn(dous, inner ? P.dous_inner : P.dous_border);
+      }
+  const float ph = __fsub_rn(heat, dous);
+  return __fmul_rn(__fmul_rn(ph, a), b);
+}
+
+struct StepCtx {
+  const gca_params* P;
+  const gca_state* S;
+  const gca_inject* J;
+  size_t cell_base;  // e * 4096
+  size_t inj_base;   // (j * N + e) * 4096
+  int lane;
+  float lutreg;      // lane i < 6: onep_veg[i]; 8 <= i < 14: onep_den[i - 8]
+  float windreg;     // lane i < 9: wind matrix entry i of the current sub-step
+  TfKey kburn;
+  uint32_t n_draws, n_thresh;
+};
+
+// Evaluate the buffered (front cell, burning direction) draws and OR the ignitions into sm.ign.
+__device__ __forceinline__ void flush_pairs(WarpSmem& sm, StepCtx& cx, int PT) {
+  __syncwarp();
+  const gca_params& P = *cx.P;
+  const gca_state& S = *cx.S;
+  const int lane = cx.lane, mode = P.rng_mode;
+  uint32_t* ign32 = reinterpret_cast<uint32_t*>(sm.ign);
+  for (int q0 = 0; q0 < PT; q0 += 32) {
+    const int q = q0 + lane;
+    const bool valid = q < PT;
+    const uint32_t ent = valid ? sm.pairs[q] : 0u;
+    const int t = ent >> 4, d = ent & 15;
+    const uint32_t cell = sm.list[t];
+    float u;
+    if (cx.J->u_burn) {
+      u = valid ? cx.J->u_burn[(cx.inj_base + cell) * 9 + d] : 1.0f;
+    } else {
+      u = bits_to_uniform(bits_at(cx.kburn, cell * 9u + (uint32_t)d, S64_HALF_BURN, mode));
+    }
+    const float w = __shfl_sync(GCA_FULL, cx.windreg, d);
+    float s = 1.0f;
+    if (S.pslope != nullptr && valid) s = S.pslope[(cx.cell_base + cell) * 8 + dir_slot(d)];
+    const float plo = __fmul_rn(__fmul_rn(sm.base_lo[t], w), s);
+    const float phi = __fmul_rn(__fmul_rn(sm.base_hi[t], w), s);
+    bool ig = valid && (u < plo);
+    if (valid && !ig && (u < phi)) {
+      // threshold cell: the float32 enclosure cannot decide -> reference-order evaluation
+      const int r = cell >> 6, c = cell & 63;
+      int hid = 3 | (3 << 3);
+      if (S.hidden != nullptr) hid = S.hidden[cx.cell_base + cell];
+      const float a = P.onep_veg[clip15(hid & 7)];
+      const float b = P.onep_den[clip15((hid >> 3) & 7)];
+      const float base = exact_base(sm, P, r, c, a, b);
+      const float p = __fmul_rn(__fmul_rn(base, w), s);
+      ig = u < p;
+      cx.n_thresh++;
+    }
+    if (ig) atomicOr(&ign32[(cell >> 6) * 2 + ((cell >> 5) & 1)], 1u << (cell & 31));
+    cx.n_draws += valid ? 1u : 0u;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(S64_WARPS * 32)
+env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gca_state S,
+                  const int32_t* __restrict__ actions, const __grid_constant__ gca_step_out O,
+                  const __grid_constant__ gca_inject J, const __grid_constant__ gca_state SNAP,
+                  const float* __restrict__ snap_reward, uint32_t flags) {
+  __shared__ WarpSmem smem_all[S64_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * S64_WARPS + warp;
+  const int N = S.N;
+  if (e >= N) return;
+  WarpSmem& sm = smem_all[warp];
+  const int K = P.K, mode = P.rng_mode;
+  const size_t cell_base = (size_t)e * 4096;
+
+  // ---- global loads first (latency overlaps the key schedule) -----------------------------------
+  uint4 cv[8];
+  {
+    const uint4* cptr = reinterpret_cast<const uint4*>(S.cell + cell_base);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cv[i] = cptr[i * 32 + lane];
+  }
+  const ulonglong2 dz = reinterpret_cast<const ulonglong2*>(S.doused + (size_t)e * 64)[lane];
+  uint2 rm = reinterpret_cast<const uint2*>(S.row_min + (size_t)e * 64)[lane];
+  const uint32_t tick0 = S.tick[e];
+  uint32_t key0 = S.key[2 * e], key1 = S.key[2 * e + 1];
+  int widx = S.wind_index[e];
+
+  // ---- shared-memory setup -----------------------------------------------------------------------
+  if (lane < 16) sm.fire32[lane] = 0u; else sm.fire32[272 + lane - 16] = 0u;   // fire rows -4..-1, 64..67
+  if (lane < 8) sm.dous32[lane] = 0u; else if (lane < 16) sm.dous32[264 + lane - 8] = 0u;  // rows -2,-1,64,65
+  store_row_views(sm.dous32 + (2 * lane + 2) * 4, dz.x);
+  store_row_views(sm.dous32 + (2 * lane + 3) * 4, dz.y);
+
+  key_schedule(sm, P, J, N, e, lane, key0, key1, widx);
+
+  // ---- u8 grid -> tree / fire row masks ----------------------------------------------------------
+  {
+    uint16_t* trow = reinterpret_cast<uint16_t*>(sm.ign);
+    uint16_t* frow = reinterpret_cast<uint16_t*>(sm.base_lo);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t t16, f16;
+      cells16_to_bits(cv[i], t16, f16);
+      const int chunk = i * 32 + lane;  // row = chunk >> 2, quarter = chunk & 3
+      trow[chunk] = (uint16_t)t16;
+      frow[chunk] = (uint16_t)f16;
+    }
+  }
+  __syncwarp();
+  unsigned long long t0, t1, f0, f1;
+  {
+    const ulonglong2 tt = reinterpret_cast<const ulonglong2*>(sm.ign)[lane];
+    const ulonglong2 ff = reinterpret_cast<const ulonglong2*>(sm.base_lo)[lane];
+    t0 = tt.x; t1 = tt.y; f0 = ff.x; f1 = ff.y;
+  }
+  __syncwarp();
+  sm.ign[2 * lane] = 0ull;
+  sm.ign[2 * lane + 1] = 0ull;
+  const unsigned long long t0i = t0, t1i = t1, f0i = f0, f1i = f1;
+  store_row_views(sm.fire32 + (2 * lane + 4) * 4, f0);
+  store_row_views(sm.fire32 + (2 * lane + 5) * 4, f1);
+
+  // ---- rows holding a cell that burns out during this env step -----------------------------------
+  unsigned long long die0 = 0, die1 = 0, pl0[3] = {0, 0, 0}, pl1[3] = {0, 0, 0};
+  {
+    uint32_t m0 = __ballot_sync(GCA_FULL, f0 != 0ull && rm.x < tick0 + (uint32_t)K);
+    uint32_t m1 = __ballot_sync(GCA_FULL, f1 != 0ull && rm.y < tick0 + (uint32_t)K);
+    while (m0 | m1) {
+      int src;
+      bool second;
+      if (m0) { src = __ffs(m0) - 1; m0 &= m0 - 1; second = false; }
+      else { src = __ffs(m1) - 1; m1 &= m1 - 1; second = true; }
+      const int row = 2 * src + (second ? 1 : 0);
+      const unsigned long long fr = shfl64(second ? f1 : f0, src);
+      uint16_t* dp = S.death + cell_base + row * 64;
+      const uint32_t da = dp[lane], db = dp[lane + 32];
+      const bool fa = (fr >> lane) & 1ull, fb = (fr >> (lane + 32)) & 1ull;
+      const uint32_t ra = (da - tick0) & 0xFFFFu, rb = (db - tick0) & 0xFFFFu;
+      const bool xa = fa && ra < (uint32_t)K, xb = fb && rb < (uint32_t)K;
+      const unsigned long long dmask =
+          (unsigned long long)__ballot_sync(GCA_FULL, xa) | ((unsigned long long)__ballot_sync(GCA_FULL, xb) << 32);
+      unsigned long long pm[3];
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        pm[b] = (unsigned long long)__ballot_sync(GCA_FULL, xa && ((ra >> b) & 1u)) |
+                ((unsigned long long)__ballot_sync(GCA_FULL, xb && ((rb >> b) & 1u)) << 32);
+      uint32_t v = 0xFFFFFFFFu;
+      if (fa && !xa) v = tick0 + ra;
+      if (fb && !xb) v = min(v, tick0 + rb);
+      const uint32_t newmin = __reduce_min_sync(GCA_FULL, v);
+      if (xa) dp[lane] = 0;        // burnt-out cell: fire_age ends at 0
+      if (xb) dp[lane + 32] = 0;
+      if (lane == src) {
+        if (second) { die1 = dmask; pl1[0] = pm[0]; pl1[1] = pm[1]; pl1[2] = pm[2]; rm.y = newmin; }
+        else { die0 = dmask; pl0[0] = pm[0]; pl0[1] = pm[1]; pl0[2] = pm[2]; rm.x = newmin; }
+      }
+    }
+  }
+  __syncwarp();
+
+  StepCtx cx;
+  cx.P = &P; cx.S = &S; cx.J = &J;
+  cx.cell_base = cell_base;
+  cx.lane = lane;
+  cx.lutreg = lane < 8 ? P.onep_veg[lane] : (lane < 16 ? P.onep_den[lane - 8] : 0.0f);
+  cx.n_draws = 0; cx.n_thresh = 0;
+  uint32_t n_front = 0, n_ign = 0, n_ext = 0;
+  const float w1 = P.ring_w[1], w2 = P.ring_w[2], w3 = P.ring_w[3], w4 = P.ring_w[4];
+
+  // ================================ K CA sub-steps, all on-chip ===================================
+  for (int j = 0; j < K; ++j) {
+    const uint32_t* sc = sm.sched[j];
+    cx.kburn = tf_key(sc[0], sc[1]);
+    cx.inj_base = ((size_t)j * N + e) * 4096;
+    {
+      const int wj = (int)sc[8];
+      cx.windreg = lane < 9 ? P.winds[wj * 9 + lane] : 0.0f;
+    }
+    // front = tree cells with a burning Moore neighbour
+    const unsigned long long fh0 = f0 | (f0 << 1) | (f0 >> 1);
+    const unsigned long long fh1 = f1 | (f1 << 1) | (f1 >> 1);
+    const unsigned long long up = shfl64_up1(fh1, lane);
+    const unsigned long long dn = shfl64_down1(fh0, lane);
+    const unsigned long long fr0 = t0 & (up | fh0 | fh1);
+    const unsigned long long fr1 = t1 & (fh0 | fh1 | dn);
+    const int nf = __popcll(fr0) + __popcll(fr1);
+    const int incl = warp_incl_scan(nf, lane);
+    const int T = __shfl_sync(GCA_FULL, incl, 31);
+    const int excl = incl - nf;
+    n_front += nf;
+
+    for (int pass_base = 0; pass_base < T; pass_base += S64_CAP) {
+      // ---- compact this pass's front cells into sm.list
+      {
+        int idx = excl - pass_base;
+        unsigned long long m = fr0;
+        int rowbits = (2 * lane) << 6;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          while (m) {
+            const int c = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            if (idx >= 0 && idx < S64_CAP) sm.list[idx] = (uint16_t)(rowbits | c);
+            ++idx;
+          }
+          m = fr1;
+          rowbits = (2 * lane + 1) << 6;
+        }
+      }
+      __syncwarp();
+      const int cnt = min(S64_CAP, T - pass_base);
+      int PT = 0;
+      for (int base = 0; base < cnt; base += 32) {
+        if (PT + 256 > S64_PCAP) { flush_pairs(sm, cx, PT); PT = 0; }
+        const int t = base + lane;
+        const bool valid = t < cnt;
+        const uint32_t cell = valid ? sm.list[t] : 0u;
+        const int r = cell >> 6, c = cell & 63;
+        uint32_t A, B, C;
+        fire_window(sm, r, c, A, B, C);
+        // ring populations (Chebyshev rings 1..4 around the centre)
+        const int S1 = __popc(B & 0x00E07038u);
+        const int S2 = __popc(A & (0x07Cu << 18)) + __popc(B & 0x01F0F87Cu) + __popc(C & 0x07Cu);
+        const int S3 = __popc(A & ((0x0FEu << 9) | (0x0FEu << 18))) + __popc(B & 0x03F9FCFEu) +
+                       __popc(C & (0x0FEu | (0x0FEu << 9)));
+        const int S4 = __popc(A) + __popc(B) + __popc(C);
+        const float Hf = fmaf((float)(S4 - S3), w4,
+                              fmaf((float)(S3 - S2), w3, fmaf((float)(S2 - S1), w2, (float)S1 * w1)));
+        uint32_t dirm = ((B >> 3) & 7u) | (((B >> 12) & 7u) << 3) | (((B >> 21) & 7u) << 6);
+        dirm &= ~(1u << 4);
+        const uint32_t dwin = dous_window(sm, r, c);
+        float Dlo = 0.0f, Dhi = 0.0f;
+        if (dwin) {
+          const int ni = __popc(dwin & ((0x0Eu << 5) | (0x0Eu << 10) | (0x0Eu << 15)));
+          const int nb = __popc(dwin) - ni;
+          const float Df = fmaf((float)nb, P.dous_border, (float)ni * P.dous_inner);
+          Dlo = __fmul_rn(Df, S64_LO);
+          Dhi = __fmul_rn(Df, S64_HI);
+        }
+        int hid = 3 | (3 << 3);
+        if (S.hidden != nullptr && valid) hid = S.hidden[cell_base + cell];
+        const float a = __shfl_sync(GCA_FULL, cx.lutreg, clip15(hid & 7));
+        const float b = __shfl_sync(GCA_FULL, cx.lutreg, 8 + clip15((hid >> 3) & 7));
+        const float ph_lo = __fsub_rn(__fmul_rn(Hf, S64_LO), Dhi);
+        const float ph_hi = __fsub_rn(__fmul_rn(Hf, S64_HI), Dlo);
+        const float blo = __fmul_rn(__fmul_rn(ph_lo, a), b);
+        const float bhi = __fmul_rn(__fmul_rn(ph_hi, a), b);
+        if (valid) { sm.base_lo[t] = blo; sm.base_hi[t] = bhi; }
+        const int nd = (valid && bhi > 0.0f) ? __popc(dirm) : 0;
+        const int incl2 = warp_incl_scan(nd, lane);
+        int off = PT + incl2 - nd;
+        uint32_t m = nd ? dirm : 0u;
+        while (m) {
+          const int d = __ffs(m) - 1;
+          m &= m - 1;
+          sm.pairs[off++] = (uint16_t)((t << 4) | d);
+        }
+        PT += __shfl_sync(GCA_FULL, incl2, 31);
+      }
+      flush_pairs(sm, cx, PT);
+    }
+    __syncwarp();
+
+    // ---- apply: ignitions, burn-outs, regrowth ---------------------------------------------------
+    const unsigned long long I0 = sm.ign[2 * lane], I1 = sm.ign[2 * lane + 1];
+    if (I0 | I1) {
+      sm.ign[2 * lane] = 0ull;
+      sm.ign[2 * lane + 1] = 0ull;
+      const TfKey ka1 = tf_key(sc[4], sc[5]), ka2 = tf_key(sc[6], sc[7]);
+      unsigned long long m = I0;
+      int row = 2 * lane;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        while (m) {
+          const int c = __ffsll((long long)m) - 1;
+          m &= m - 1;
+          const uint32_t cell = (uint32_t)(row * 64 + c);
+          int age;
+          if (J.age_new) age = J.age_new[cx.inj_base + cell];
+          else age = randint_from_bits(bits_at(ka1, cell, S64_HALF_CELL, mode), bits_at(ka2, cell, S64_HALF_CELL, mode),
+                                       P.age_lo, P.age_span, P.age_mult);
+          const uint32_t dabs = tick0 + (uint32_t)j + (uint32_t)age;  // burn-out tick
+          S.death[cell_base + cell] = (uint16_t)dabs;
+          if (half == 0) rm.x = min(rm.x, dabs); else rm.y = min(rm.y, dabs);
+        }
+        m = I1;
+        row = 2 * lane + 1;
+      }
+    }
+    unsigned long long ext0 = die0, ext1 = die1;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      ext0 &= ((j >> b) & 1) ? pl0[b] : ~pl0[b];
+      ext1 &= ((j >> b) & 1) ? pl1[b] : ~pl1[b];
+    }
+    unsigned long long g0 = 0, g1 = 0;
+    if (P.p_tree > 0.0f) {
+      // empty -> tree with probability p_tree (0 in the reference env; dense draw per empty cell)
+      const TfKey kg = tf_key(sc[2], sc[3]);
+      unsigned long long m = ~(t0 | f0);
+      int row = 2 * lane;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        while (m) {
+          const int c = __ffsll((long long)m) - 1;
+          m &= m - 1;
+          const uint32_t cell = (uint32_t)(row * 64 + c);
+          float u;
+          if (J.u_grow) u = J.u_grow[cx.inj_base + cell];
+          else u = bits_to_uniform(bits_at(kg, cell, S64_HALF_CELL, mode));
+          if (u < P.p_tree) { if (half == 0) g0 |= 1ull << c; else g1 |= 1ull << c; }
+        }
+        m = ~(t1 | f1);
+        row = 2 * lane + 1;
+      }
+    }
+    n_ign += __popcll(I0) + __popcll(I1);
+    n_ext += __popcll(ext0) + __popcll(ext1);
+    t0 = (t0 & ~I0) | g0;
+    t1 = (t1 & ~I1) | g1;
+    f0 = (f0 & ~ext0) | I0;
+    f1 = (f1 & ~ext1) | I1;
+    if (j + 1 < K) {
+      store_row_views(sm.fire32 + (2 * lane + 4) * 4, f0);
+      store_row_views(sm.fire32 + (2 * lane + 5) * 4, f1);
+    }
+    __syncwarp();
+  }
+
+  // ---- sparse in-place write-back of the cells that changed --------------------------------------
+  {
+    unsigned long long ch = (t0 ^ t0i) | (f0 ^ f0i);
+    unsigned long long tt = t0, ff = f0;
+    int row = 2 * lane;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      while (ch) {
+        const int c = __ffsll((long long)ch) - 1;
+        ch &= ch - 1;
+        const uint8_t code = ((ff >> c) & 1ull) ? 2 : (((tt >> c) & 1ull) ? 1 : 0);
+        S.cell[cell_base + row * 64 + c] = code;
+      }
+      ch = (t1 ^ t1i) | (f1 ^ f1i);
+      tt = t1; ff = f1;
+      row = 2 * lane + 1;
+    }
+  }
+  reinterpret_cast<uint2*>(S.row_min + (size_t)e * 64)[lane] = rm;
+  const int tcount = __reduce_add_sync(GCA_FULL, __popcll(t0) + __popcll(t1));
+  const int fcount = __reduce_add_sync(GCA_FULL, __popcll(f0) + __popcll(f1));
+
+  if (O.stats != nullptr) {
+    const uint32_t a = __reduce_add_sync(GCA_FULL, n_front), b = __reduce_add_sync(GCA_FULL, cx.n_draws);
+    const uint32_t c = __reduce_add_sync(GCA_FULL, n_ign), d = __reduce_add_sync(GCA_FULL, n_ext);
+    const uint32_t t = __reduce_add_sync(GCA_FULL, cx.n_thresh);
+    if (lane == 0) {
+      atomicAdd(&O.stats[0], (unsigned long long)a);
+      atomicAdd(&O.stats[1], (unsigned long long)b);
+      atomicAdd(&O.stats[2], (unsigned long long)c);
+      atomicAdd(&O.stats[3], (unsigned long long)d);
+      if (t) atomicAdd(&O.stats[4], (unsigned long long)t);
+      atomicAdd(&O.stats[5], 1ull);
+    }
+  }
+
+  // ---- per-env scalars: key chain, wind, clock, move, douse, day/night, reward, done -------------
+  const bool ca_only = (flags & GCA_FLAG_CA_ONLY) != 0;
+  const bool done = fcount == 0;
+  if (lane == 0) {
+    S.key[2 * e] = key0;
+    S.key[2 * e + 1] = key1;
+    S.wind_index[e] = widx;
+    S.tick[e] = tick0 + (uint32_t)K;
+    const float rew = award(tcount, fcount);
+    if (!ca_only) {
+      const int a0 = actions[3 * e], a1 = actions[3 * e + 1];
+      const int a0c = min(max(a0, 0), 8), a1c = min(max(a1, 0), 1);
+      // clock (repeat_ca_jax.py:35-41): new = time + ((t_move + t_shoot) + t_any); keep the fraction
+      const float tt = __fadd_rn(__fadd_rn(P.t_move[a0c], P.t_shoot[a1c]), P.t_any);
+      const float nt = __fadd_rn(S.time[e], tt);
+      S.time[e] = __fsub_rn(nt, truncf(nt));
+      int row = S.position[2 * e], col = S.position[2 * e + 1];
+      move_position(a0, 64, 64, row, col);
+      S.position[2 * e] = row;
+      S.position[2 * e + 1] = col;
+      if (a1 == 1) S.doused[(size_t)e * 64 + row] |= 1ull << col;
+      const int ts = S.time_step[e] + 1;
+      S.time_step[e] = ts;
+      int night = S.is_night[e];
+      if (O.obs_night) O.obs_night[e] = (uint8_t)night;
+      if (ts % P.day_length == 0) night = 1 - night;
+      S.is_night[e] = night;
+      if (S.steps_elapsed) S.steps_elapsed[e] = __fadd_rn(S.steps_elapsed[e], 1.0f);
+      if (S.reward_accumulated) S.reward_accumulated[e] = __fadd_rn(S.reward_accumulated[e], rew);
+    }
+    if (O.step_reward) O.step_reward[e] = rew;
+    if (O.terminated) O.terminated[e] = done ? 1 : 0;
+    if (O.counts) { O.counts[2 * e] = tcount; O.counts[2 * e + 1] = fcount; }
+    if (O.reward && !((flags & GCA_FLAG_AUTO_RESET) && done)) O.reward[e] = rew;
+  }
+
+  // ---- fused conditional_reset (advanced_bulldozer.py:422-518) ------------------------------------
+  if ((flags & GCA_FLAG_AUTO_RESET) && done) {
+    __syncwarp();
+    const uint4* sc4 = reinterpret_cast<const uint4*>(SNAP.cell + cell_base);
+    uint4* dc4 = reinterpret_cast<uint4*>(S.cell + cell_base);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dc4[i * 32 + lane] = sc4[i * 32 + lane];
+    const uint4* sd4 = reinterpret_cast<const uint4*>(SNAP.death + cell_base);
+    uint4* dd4 = reinterpret_cast<uint4*>(S.death + cell_base);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dd4[i * 32 + lane] = sd4[i * 32 + lane];
+    reinterpret_cast<ulonglong2*>(S.doused + (size_t)e * 64)[lane] =
+        reinterpret_cast<const ulonglong2*>(SNAP.doused + (size_t)e * 64)[lane];
+    reinterpret_cast<uint2*>(S.row_min + (size_t)e * 64)[lane] =
+        reinterpret_cast<const uint2*>(SNAP.row_min + (size_t)e * 64)[lane];
+    if (lane == 0) {
+      S.key[2 * e] = SNAP.key[2 * e];
+      S.key[2 * e + 1] = SNAP.key[2 * e + 1];
+      S.wind_index[e] = SNAP.wind_index[e];
+      S.position[2 * e] = SNAP.position[2 * e];
+      S.position[2 * e + 1] = SNAP.position[2 * e + 1];
+      S.time[e] = SNAP.time[e];
+      S.tick[e] = SNAP.tick[e];
+      if (S.steps_elapsed) S.steps_elapsed[e] = 0.0f;
+      if (S.reward_accumulated) S.reward_accumulated[e] = 0.0f;
+      if (O.reward) O.reward[e] = snap_reward[e];
+    }
+  }
+}
+
+cudaError_t launch_env_step64(const gca_params& p, const gca_state& s, const int32_t* actions,
+                              const gca_step_out& out, const gca_inject& inj, const gca_state& snap,
+                              const float* snap_reward, uint32_t flags, cudaStream_t st) {
+  const int blocks = (s.N + S64_WARPS - 1) / S64_WARPS;
+  env_step64_kernel<<<blocks, S64_WARPS * 32, 0, st>>>(p, s, actions, out, inj, snap, snap_reward, flags);
+  return cudaGetLastError();
+}
+
+}  // namespace gca

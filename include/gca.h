@@ -1,0 +1,190 @@
+/* gca.h -- C ABI of libgca.so: B200 (sm_100a) kernels for the environment-step hot path of
+ * frasermince/gym-cellular-automata's advanced bulldozer forest-fire environment.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream (as void*).  No
+ * allocation, no hidden global state, no host synchronisation inside a step call; functions
+ * return 0 on success or a negative gca_status and never throw or exit
+ * (gca_last_error() gives the text).  All calls are re-entrant per stream.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/gym_cellular_automata/):
+ *   gca_params_init        PartiallyObservableForestFireJax.__init__  forest_fire/operators/ca_alexandridis_jax.py:54-160
+ *                          + time mappings                             forest_fire/bulldozer/advanced_bulldozer.py:238-246,745-777
+ *   gca_alexandridis_step  PartiallyObservableForestFireJax.update     forest_fire/operators/ca_alexandridis_jax.py:426-460 (vmapped)
+ *   gca_env_step           jax.vmap(MDP.update) + _award + _is_done    forest_fire/bulldozer/advanced_bulldozer.py:332-399,1103-1133
+ *                          (RepeatCAJax.update                         forest_fire/operators/repeat_ca_jax.py:34-71,
+ *                           MoveModifyJax.update                       forest_fire/operators/move_modify_jax.py:148-157)
+ *   gca_move_modify        MoveJax.update / ModifyJax.update           forest_fire/operators/move_modify_jax.py:39-62,102-114
+ *   gca_reward_done        _award / _is_done / count_cells             forest_fire/bulldozer/advanced_bulldozer.py:597-633,941-953
+ *   gca_conditional_reset  conditional_reset                           forest_fire/bulldozer/advanced_bulldozer.py:422-518
+ *   gca_render_rgb         build_observation_on_extensions/grid_to_rgb forest_fire/bulldozer/advanced_bulldozer.py:988-1101
+ *                          + apply_blur/apply_extensions               forest_fire/bulldozer/utils/extension_utils.py:99-195
+ *   gca_pack_state / gca_unpack_state   the float32/int32 context pytree of _initial_context_distribution
+ *                                                                       forest_fire/bulldozer/advanced_bulldozer.py:690-743
+ *   gca_threefry_bits / gca_threefry_split   jax.random.bits / split (third-party jax, unpinned; see oracle/prng.py)
+ */
+#ifndef GCA_H_
+#define GCA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCA_VERSION 100
+#define GCA_MAX_R 10        /* burn kernel radius: ceil(log2(size)) - 2; 10 at 4096 */
+#define GCA_MAX_K 8         /* CA sub-steps fused into one env step */
+
+typedef enum gca_status {
+  GCA_OK = 0,
+  GCA_ERR_ARG = -1,         /* null pointer / bad size / bad enum */
+  GCA_ERR_UNSUPPORTED = -2, /* shape or option not supported by this build */
+  GCA_ERR_CUDA = -3         /* a CUDA runtime call failed; see gca_last_error() */
+} gca_status;
+
+/* jax.random stream layouts */
+#define GCA_RNG_LEGACY 0        /* jax_threefry_partitionable = False (JAX < 0.5 default) */
+#define GCA_RNG_PARTITIONABLE 1 /* jax_threefry_partitionable = True  (JAX >= 0.5 default) */
+
+/* gca_env_step flags */
+#define GCA_FLAG_AUTO_RESET 1u  /* fuse conditional_reset for terminated envs into the step */
+#define GCA_FLAG_NO_HIDDEN 2u   /* hidden layers off: veg = den = 3, slope factor 1 (pslope may be NULL) */
+#define GCA_FLAG_CA_ONLY 4u     /* run only the CA sub-steps (no clock/move/douse/reward bookkeeping) */
+
+/* Constants of one environment family (host POD, passed to kernels by value). */
+typedef struct gca_params {
+  int32_t H, W;             /* grid rows, cols */
+  int32_t R;                /* burn kernel radius */
+  int32_t K;                /* CA sub-steps per env step (1 = reference parity) */
+  int32_t rng_mode;         /* GCA_RNG_* */
+  int32_t age_lo;           /* randint(fire_age_min, fire_age_max): lo, span, mult */
+  uint32_t age_span, age_mult;
+  int32_t day_length;       /* 400 */
+  float p_tree;             /* empty -> tree probability (0 in the reference) */
+  float p_wind_change;      /* 0.06 */
+  float t_any;              /* f32(0.001) */
+  float t_move[9];          /* clock cost of each move action (all equal in the reference) */
+  float t_shoot[2];
+  float onep_veg[8];        /* f32(1) + p_veg[i], i = 0..5 */
+  float onep_den[8];
+  float winds[8 * 9];       /* wind matrix k (3x3 row-major, centre 0), float32 */
+  float dous_border, dous_inner;   /* 5x5 dousing weights: 16 border cells / 9 inner cells */
+  float ring_w[GCA_MAX_R + 1];     /* ring_w[k], k = 1..R: burn-kernel weight of Chebyshev ring k;
+                                      ring_w[0] = centre weight (== ring_w[1]) */
+} gca_params;
+
+/* Packed device-resident state of N independent environments (all pointers device memory).
+ *   cell    u8  [N][H][W]   0 empty / 1 tree / 2 fire
+ *   death   u16 [N][H][W]   fire cell: low 16 bits of the CA tick at which it burns out
+ *                           (fire_age = ((death - tick) & 0xFFFF) + 1); other cells: fire_age itself
+ *   hidden  u8  [N][H][W]   vegetation (bits 0-2) | density (bits 3-5); NULL with GCA_FLAG_NO_HIDDEN
+ *   doused  u64 [N][H][WW]  dousing_count bit-board, WW = ceil(W/64), bit (c & 63) of word c >> 6
+ *   pslope  f32 [N][H][W][8] exp(f32(0.078) * slope) for the 8 neighbours in 3x3 row-major order,
+ *                           centre skipped; NULL = all 1.0
+ *   row_min u32 [N][H]      earliest burn-out tick among the fire cells of a row (0xFFFFFFFF: none);
+ *                           maintained by the 64x64 kernel only
+ *   tick    u32 [N]         CA sub-steps executed since the env was (re)set
+ */
+typedef struct gca_state {
+  int32_t N;
+  int32_t reserved;
+  uint8_t* cell;
+  uint16_t* death;
+  const uint8_t* hidden;
+  uint64_t* doused;
+  const float* pslope;
+  uint32_t* row_min;
+  uint32_t* tick;
+  uint32_t* key;        /* [N][2] raw threefry key data */
+  int32_t* wind_index;  /* [N] 0..7 */
+  int32_t* position;    /* [N][2] (row, col) */
+  float* time;          /* [N] clock accumulator */
+  int32_t* time_step;   /* [N] */
+  int32_t* is_night;    /* [N] */
+  float* steps_elapsed;       /* [N] info bookkeeping (advanced_bulldozer.py:390-391) */
+  float* reward_accumulated;  /* [N] */
+} gca_state;
+
+/* Per-step outputs (device). Any pointer may be NULL to skip that output. */
+typedef struct gca_step_out {
+  float* reward;        /* [N] reward handed to the agent (after auto-reset: _award(restored grid)) */
+  float* step_reward;   /* [N] reward of the transition itself (info["reward"]) */
+  uint8_t* terminated;  /* [N] done flag of the transition (before any auto-reset) */
+  int32_t* counts;      /* [N][2] tree, fire cell counts of the post-step grid */
+  uint8_t* obs_night;   /* [N] is_night value the observation must be rendered with (pre-flip) */
+  unsigned long long* stats; /* [8] += front cells, (cell,dir) draws, ignitions, burn-outs,
+                                       threshold cells (exact re-evaluations), env steps, 0, 0 */
+} gca_step_out;
+
+/* Injected random fields for rule-parity tests (device, each with a leading K axis); NULL = threefry. */
+typedef struct gca_inject {
+  const float* u_burn;      /* [K][N][H][W][9] */
+  const float* u_grow;      /* [K][N][H][W]    */
+  const int32_t* age_new;   /* [K][N][H][W]    */
+  const float* u_wind;      /* [K][N]          */
+  const int32_t* wind_step; /* [K][N]          */
+} gca_inject;
+
+int gca_version(void);
+const char* gca_last_error(void);
+
+/* A0: fill *p for an nrows x ncols env.  winds72 may be NULL (the reference's 8 wind matrices are
+ * generated).  t_move / t_shoot < 0 selects the reference formula from speed_move / speed_act. */
+int gca_params_init(gca_params* p, int32_t nrows, int32_t ncols, int32_t K, double speed_move,
+                    double speed_act, double t_any, double t_move, double t_shoot, double p_tree,
+                    double p_wind_change, int32_t rng_mode, const float* winds72);
+
+/* One full env step for all N envs (clock, K CA sub-steps, move, douse, time_step, day/night,
+ * reward, done, info counters, optional fused auto-reset from `snapshot`).  actions: [N][3] int32
+ * (move 0-8, shoot 0-1, extension id).  snapshot / snapshot_reward are only read with
+ * GCA_FLAG_AUTO_RESET.  State is updated IN PLACE. */
+int gca_env_step(const gca_params* p, const gca_state* s, const int32_t* actions,
+                 const gca_step_out* out, const gca_inject* inj, const gca_state* snapshot,
+                 const float* snapshot_reward, uint32_t flags, void* stream);
+
+/* K CA sub-steps only (PartiallyObservableForestFireJax.update applied K times). */
+int gca_alexandridis_step(const gca_params* p, const gca_state* s, const gca_step_out* out,
+                          const gca_inject* inj, uint32_t flags, void* stream);
+
+/* MoveJax + ModifyJax on positions / dousing bit-board only. */
+int gca_move_modify(const gca_params* p, const gca_state* s, const int32_t* actions, void* stream);
+
+/* count_cells + _award + _is_done on the packed grid. */
+int gca_reward_done(const gca_params* p, const gca_state* s, float* reward, uint8_t* terminated,
+                    int32_t* counts, void* stream);
+
+/* conditional_reset: restore envs with terminated[e] != 0 from `snapshot` (time_step / is_night
+ * kept), zero their info counters, set reward[e] = snapshot_reward[e] and clear terminated[e]. */
+int gca_conditional_reset(const gca_params* p, const gca_state* s, const gca_state* snapshot,
+                          const float* snapshot_reward, float* reward, uint8_t* terminated,
+                          void* stream);
+
+/* Observation: float32 RGB [N][H][W][3] (reference layout) or uint8 RGB when rgb_u8 != 0.
+ * cell: grid to draw; night: [N] is_night to use; ext_action: [N] extension id (0..2) or NULL;
+ * scratch: [N] uint32 device words, required when enable_extensions != 0;
+ * env_mask: [N] or NULL -- when given, only envs with env_mask[e] != 0 are (re)drawn, which is how
+ * conditional_reset re-renders terminated envs without a host round trip. */
+int gca_render_rgb(const gca_params* p, int32_t N, const uint8_t* cell, const uint64_t* doused,
+                   const int32_t* position, const uint8_t* night, const int32_t* ext_action,
+                   const uint8_t* env_mask, int32_t enable_extensions, int32_t rgb_u8,
+                   uint32_t* scratch, void* rgb_out, void* stream);
+
+/* Reference float32/int32 context arrays <-> packed state (device pointers).  fire_age of fire
+ * cells must be an integer in [1, 32767]; vegetation / density in [0, 7].  err_flag (device int32,
+ * may be NULL) is set non-zero if an input violates that. */
+int gca_pack_state(const gca_params* p, const gca_state* s, const float* true_grid,
+                   const float* fire_age, const int32_t* dousing_count, const int32_t* vegetation,
+                   const int32_t* density, uint8_t* hidden_out, int32_t* err_flag, void* stream);
+int gca_unpack_state(const gca_params* p, const gca_state* s, float* true_grid, float* fire_age,
+                     int32_t* dousing_count, void* stream);
+
+/* Test hooks for the in-kernel PRNG: n words of jax.random.bits(key,(n,)) / split(key, num). */
+int gca_threefry_bits(const uint32_t* key2_dev, int64_t n, int32_t rng_mode, uint32_t* out_dev,
+                      void* stream);
+int gca_threefry_split(const uint32_t* key2_dev, int32_t num, int32_t rng_mode, uint32_t* out_dev,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCA_H_ */
