@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the fused environment step (BASELINE.json metric: CA cell-updates/s
+and env-steps/s, 64x64, N envs) on 1..8 B200, with the roofline, the end-to-end figure through
+the host API and the CPU baseline beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one env step (clock + K_sub CA sub-steps + move + douse + reward + done +
+auto-reset) of every env of the batch = ONE launch of env_step64_kernel per GPU.
+Workload = BASELINE.json configs[1]: 64x64 Alexandridis env, 4096 envs per GPU, speed-multiplier 4
+(K_sub = 4 CA sub-steps per env step), hidden layers on, synthetic random hidden layers, random
+actions.  Envs are independent -> sharded across ranks with no data-path collective (weak
+scaling); NCCL only all-gathers the per-env episode statistics.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALGO_BYTES_PER_CELL = 7  # read cell u8 + age u16 + hidden u8, write cell u8 + age u16
+ALGO_BYTES_PER_ENV = 64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=4096)
+    ap.add_argument("--size", type=int, default=64)
+    ap.add_argument("--substeps", type=int, default=4)
+    ap.add_argument("--rng-mode", default="legacy")
+    ap.add_argument("--no-hidden", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-envs", type=int, default=64)
+    ap.add_argument("--cpu-steps", type=int, default=24)
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side (the oracle port): cpu_baseline leg and --impl reference.  The only place bench.py runs
+# anything from oracle/.
+# ------------------------------------------------------------------------------------------------
+def cpu_port_throughput(size, K, n_envs, steps, warmup, mode="legacy", use_hidden=True, seed=0):
+    from oracle import alexandridis as ax
+    from oracle import init_state as oinit
+    from oracle import prng
+    from oracle.c_oracle import COracle
+    m = prng.LEGACY if mode == "legacy" else prng.PARTITIONABLE
+    state, _ = oinit.initial_state(size, size, n_envs, seed=seed, use_hidden=use_hidden, mode=m, hidden="random")
+    E = ax.EnvConstants(size, size, speed_move=0.12 * 4, speed_act=0.03 * 4)
+    co = COracle(E, oinit.get_winds(), K=K, mode=m)
+    rng = np.random.default_rng(seed)
+    threads = COracle.max_threads()
+
+    def act():
+        return np.stack([rng.integers(0, 9, n_envs), rng.integers(0, 2, n_envs), rng.integers(0, 3, n_envs)],
+                        1).astype(np.int32)
+
+    for _ in range(warmup):
+        co.step(state, act(), nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        co.step(state, act(), nthreads=threads)
+    dt = time.perf_counter() - t0
+    env_steps = n_envs * steps / dt
+    return {"cell_updates_per_s": env_steps * size * size * K, "env_steps_per_s": env_steps,
+            "seconds": dt, "threads": threads}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_envs = args.cpu_envs
+    steps = max(1, min(args.steps, args.cpu_steps))
+    warmup = max(1, min(args.warmup, 3))
+    r = cpu_port_throughput(args.size, args.substeps, n_envs, steps, warmup, args.rng_mode, not args.no_hidden,
+                            args.seed)
+    sample = (f"{n_envs} envs x {steps} env steps ({args.substeps} CA sub-steps each) of the {args.size}x{args.size} "
+              f"workload, dense C port of the reference step (oracle/gca_oracle.c), OpenMP over envs")
+    line = {
+        "impl": "reference", "metric": "cell_updates_per_s", "value": r["cell_updates_per_s"],
+        "unit": "cell-updates/s", "env_steps_per_s": r["env_steps_per_s"], "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": r["cell_updates_per_s"], "unit": "cell-updates/s", "cores": r["threads"],
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": r["cell_updates_per_s"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "note": "the reference is JAX-on-CPU and cannot be installed in this image (no jax/jaxlib wheel, no "
+                "network); this arm times the repo's dense C restatement of the same step on all host cores",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"advanced-bulldozer Alexandridis CA {args.size}x{args.size}, {args.envs_per_gpu} envs/GPU, "
+                        f"K={args.substeps} CA sub-steps per env step (speed-multiplier 4), hidden "
+                        f"{'off' if args.no_hidden else 'on (synthetic random layers)'}, random actions, auto-reset on",
+            "envs_per_gpu": args.envs_per_gpu, "grid": [args.size, args.size], "substeps": args.substeps,
+            "rng_mode": args.rng_mode, "l2": "flushed between timed steps (256 MiB write)" if not args.no_flush
+            else "not flushed", "parallelism": f"env-sharded x{args.gpus}, no data-path collective"}
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=3)
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            if len(s) < 7:
+                continue
+            try:
+                sm.append(float(s[0]))
+                mx = float(s[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N, K, size = args.envs_per_gpu, args.substeps, args.size
+
+    env = AdvancedForestFireBulldozerEnv(
+        size, size, key=1 + rank, num_envs=N, speed_move=0.12 * 4, speed_act=0.03 * 4, use_hidden=not args.no_hidden,
+        substeps=K, rng_mode=args.rng_mode, seed=args.seed + rank, hidden="random", obs_mode="none", auto_reset=True,
+        collect_stats=True, device=dev)
+    env.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(args.seed + rank)
+    total = args.warmup + args.steps
+    # synthetic actions for every step, resident in HBM before the timed region
+    acts = torch.stack([torch.randint(0, 9, (total, N), device=dev, generator=gen),
+                        torch.randint(0, 2, (total, N), device=dev, generator=gen),
+                        torch.randint(0, 3, (total, N), device=dev, generator=gen)], dim=-1).to(torch.int32).contiguous()
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    for i in range(args.warmup):
+        env.step_device(acts[i])
+    torch.cuda.synchronize()
+    stats0 = env.stats()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        if flush is not None:
+            flush.fill_(i & 0xFF)  # evict the env state from the 126 MB L2 (outside the timed events)
+        starts[i].record()
+        env.step_device(acts[args.warmup + i])
+        ends[i].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    stats1 = env.stats()
+    # L2-warm variant: back-to-back launches, one event pair
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        env.step_device(acts[args.warmup + i])
+    e1.record()
+    torch.cuda.synchronize()
+    ms_warm = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end to end through the host API: pinned host actions in, reward/terminated out, per step
+    h_act = acts[args.warmup:args.warmup + args.steps].cpu().pin_memory()
+    h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
+    h_term = torch.empty(N, dtype=torch.uint8).pin_memory()
+    d_act = torch.empty((N, 3), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        d_act.copy_(h_act[i], non_blocking=True)
+        out = env.step_device(d_act)
+        h_rew.copy_(out.reward, non_blocking=True)
+        h_term.copy_(out.terminated, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads reward/done every step
+    e2e_s = time.perf_counter() - t0
+
+    # ---- episode statistics all-gather (the only collective of the path)
+    ep = torch.stack([env._state.steps_elapsed, env._state.reward_accumulated], dim=1).contiguous()
+    if world > 1:
+        gathered = torch.empty((world * N, 2), dtype=ep.dtype, device=dev)
+        dist.all_gather_into_tensor(gathered, ep)
+        t = torch.tensor([ms, ms_warm, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_warm, e2e_s = [float(x) for x in t.tolist()]
+    else:
+        gathered = ep
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cells = N * size * size
+    total_envs = N * world
+    env_steps_s = total_envs * args.steps / (ms * 1e-3)
+    cu_s = env_steps_s * size * size * K
+    algo_bytes = ALGO_BYTES_PER_CELL * cells + ALGO_BYTES_PER_ENV * N  # per launch, per GPU
+    launch_s = ms * 1e-3 / args.steps
+    achieved = algo_bytes / launch_s / 1e9
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("env_step64_kernel_bytes_per_launch")
+    except Exception:
+        pass
+    d = (stats1 - stats0).astype(np.float64)
+    sub = max(d[5] * K, 1.0)
+    line = {
+        "metric": "cell_updates_per_s", "value": cu_s, "unit": "cell-updates/s", "env_steps_per_s": env_steps_s,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 bit-boards + f32 + u32 threefry",
+        "data": "synthetic", "config": workload_config(args),
+        "value_l2_warm": total_envs * args.steps / (ms_warm * 1e-3) * size * size * K,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                     "algorithmic_bytes_per_launch": algo_bytes, "launch_us": launch_s * 1e6},
+        "e2e": {"value": total_envs * args.steps / e2e_s * size * size * K, "unit": "cell-updates/s",
+                "env_steps_per_s": total_envs * args.steps / e2e_s,
+                "h2d_bytes_per_step": int(N * 3 * 4), "d2h_bytes_per_step": int(N * 5),
+                "what": "pinned host actions -> H2D -> gca_env_step -> D2H reward+terminated, stream sync every step"},
+        "gpu_launches": args.steps, "clocks": clocks,
+        "workload_stats": {"front_cells_per_env_substep": d[0] / sub, "draws_per_env_substep": d[1] / sub,
+                           "ignitions_per_env_substep": d[2] / sub, "burnouts_per_env_substep": d[3] / sub,
+                           "threshold_cells": int(d[4])},
+        "episode_stats": {"envs": int(gathered.shape[0]), "mean_steps_elapsed": float(gathered[:, 0].mean()),
+                          "mean_reward_accumulated": float(gathered[:, 1].mean())},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_port_throughput(size, K, args.cpu_envs, args.cpu_steps, 2, args.rng_mode, not args.no_hidden, args.seed)
+        line["cpu_baseline"] = {
+            "value": r["cell_updates_per_s"], "unit": "cell-updates/s", "cores": r["threads"], "kind": "port",
+            "sample": f"{args.cpu_envs} envs x {args.cpu_steps} env steps of the same workload, dense C port of the "
+                      f"reference step (oracle/gca_oracle.c), OpenMP over envs, {r['seconds']:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

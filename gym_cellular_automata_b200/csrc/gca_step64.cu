@@ -40,11 +40,25 @@ struct __align__(16) WarpSmem {
   uint32_t dous32[68 * 4];        // doused rows -2..65, same views
   unsigned long long ign[64];     // ignition accumulator (unpack: tree rows)
   float base_lo[S64_CAP];         // per front cell: enclosure of (p_h (1+p_veg)) (1+p_den)
-  float base_hi[S64_CAP];         //   (unpack: fire rows, aliased)
+  float base_hi[S64_CAP];         //   (unpack: fire rows; apply: burn-out ticks of new fires)
   uint16_t list[S64_CAP];         // front cells of the current pass: (row << 6) | col
-  uint16_t pairs[S64_PCAP];       // (list index << 4) | direction
+                                  //   (apply: cells ignited in this sub-step)
+  uint16_t pairs[S64_PCAP];       // (list index << 4) | direction  (list build: front rows)
   uint32_t sched[GCA_MAX_K][12];  // per sub-step: Sburn[2] Sgrow[2] ak1[2] ak2[2] wind change step pad
 };
+
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// x % span with a precomputed magic = 0xFFFFFFFF / span (span < 2^16): quotient estimate is at
+// most 2 too small
+__device__ __forceinline__ uint32_t fastmod(uint32_t x, uint32_t span, uint32_t magic) {
+  uint32_t r = x - __umulhi(x, magic) * span;
+  if (r >= span) r -= span;
+  if (r >= span) r -= span;
+  return r;
+}
 
 // view k of a row covers columns 16k-4 .. 16k+27 (bit b <-> column 16k-4+b)
 __device__ __forceinline__ void store_row_views(uint32_t* dst, unsigned long long x) {
@@ -257,50 +271,108 @@ struct StepCtx {
   uint32_t n_draws, n_thresh;
 };
 
-// Evaluate the buffered (front cell, burning direction) draws and OR the ignitions into sm.ign.
-__device__ __forceinline__ void flush_pairs(WarpSmem& sm, StepCtx& cx, int PT) {
+// Compact the front cells [pass_base, pass_base + CAP) of the row masks fr0 (row 2*lane) and fr1
+// (row 2*lane+1) into sm.list and return the total number of front cells.  The rows are first
+// re-dealt in 16-column pieces (piece p = 4*row + quarter goes to lane p % 32) so that a long
+// horizontal run of front cells -- the top/bottom edge of a burning blob -- is shared by several
+// lanes instead of serialising one.
+__device__ __forceinline__ int build_front_list(WarpSmem& sm, unsigned long long fr0, unsigned long long fr1,
+                                                int lane, int pass_base) {
+  reinterpret_cast<ulonglong2*>(sm.pairs)[lane] = make_ulonglong2(fr0, fr1);
   __syncwarp();
+  const uint16_t* q16 = reinterpret_cast<const uint16_t*>(sm.pairs);
+  uint32_t pc[8];
+  int n = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    pc[k] = q16[lane + 32 * k];
+    n += __popc(pc[k]);
+  }
+  const int incl = warp_incl_scan(n, lane);
+  const int T = __shfl_sync(GCA_FULL, incl, 31);
+  int idx = incl - n - pass_base;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint32_t m = pc[k];
+    const int p = lane + 32 * k;
+    const uint32_t base = ((uint32_t)(p >> 2) << 6) | ((uint32_t)(p & 3) << 4);
+    while (m) {
+      const uint32_t b = __ffs(m) - 1;
+      m &= m - 1;
+      if ((unsigned)idx < (unsigned)S64_CAP) sm.list[idx] = (uint16_t)(base | b);
+      ++idx;
+    }
+  }
+  __syncwarp();
+  return T;
+}
+
+// Touch the hidden byte and the 32-byte slope-factor sector of every listed front cell so that
+// they are in L1/L2 by the time the cell and draw phases ask for them.
+__device__ __forceinline__ void prefetch_front(const WarpSmem& sm, const gca_state& S, size_t cell_base, int cnt,
+                                               int lane) {
+  if (S.hidden == nullptr) return;
+  for (int t = lane; t < cnt; t += 32) {
+    const uint32_t cell = sm.list[t];
+    prefetch_l1(S.hidden + cell_base + cell);
+    if (S.pslope != nullptr) prefetch_l1(S.pslope + (cell_base + cell) * 8);
+  }
+}
+
+// One buffered (front cell, burning direction) draw: returns whether it ignites the cell.
+__device__ __forceinline__ bool eval_pair(const WarpSmem& sm, StepCtx& cx, int q, int PT, uint32_t& cell_out) {
   const gca_params& P = *cx.P;
   const gca_state& S = *cx.S;
-  const int lane = cx.lane, mode = P.rng_mode;
+  const bool valid = q < PT;
+  const uint32_t ent = valid ? sm.pairs[q] : 0u;
+  const int t = ent >> 4, d = ent & 15;
+  const uint32_t cell = sm.list[t];
+  cell_out = cell;
+  float s = 1.0f;
+  if (S.pslope != nullptr && valid) s = S.pslope[(cx.cell_base + cell) * 8 + dir_slot(d)];
+  float u;
+  if (cx.J->u_burn) {
+    u = valid ? cx.J->u_burn[(cx.inj_base + cell) * 9 + d] : 1.0f;
+  } else {
+    u = bits_to_uniform(bits_at(cx.kburn, cell * 9u + (uint32_t)d, S64_HALF_BURN, P.rng_mode));
+  }
+  const float w = __shfl_sync(GCA_FULL, cx.windreg, d);
+  const float plo = __fmul_rn(__fmul_rn(sm.base_lo[t], w), s);
+  const float phi = __fmul_rn(__fmul_rn(sm.base_hi[t], w), s);
+  bool ig = valid && (u < plo);
+  if (valid && !ig && (u < phi)) {
+    // threshold cell: the float32 enclosure cannot decide -> reference-order evaluation
+    const int r = cell >> 6, c = cell & 63;
+    int hid = 3 | (3 << 3);
+    if (S.hidden != nullptr) hid = S.hidden[cx.cell_base + cell];
+    const float a = P.onep_veg[clip15(hid & 7)];
+    const float b = P.onep_den[clip15((hid >> 3) & 7)];
+    const float base = exact_base(sm, P, r, c, a, b);
+    const float p = __fmul_rn(__fmul_rn(base, w), s);
+    ig = u < p;
+    cx.n_thresh++;
+  }
+  cx.n_draws += valid ? 1u : 0u;
+  return ig;
+}
+
+// Evaluate the buffered draws, two per lane per iteration (two independent threefry chains give
+// the ALU pipe instruction-level parallelism), and OR the ignitions into sm.ign.
+__device__ __forceinline__ void flush_pairs(WarpSmem& sm, StepCtx& cx, int PT) {
+  __syncwarp();
   uint32_t* ign32 = reinterpret_cast<uint32_t*>(sm.ign);
-  for (int q0 = 0; q0 < PT; q0 += 32) {
-    const int q = q0 + lane;
-    const bool valid = q < PT;
-    const uint32_t ent = valid ? sm.pairs[q] : 0u;
-    const int t = ent >> 4, d = ent & 15;
-    const uint32_t cell = sm.list[t];
-    float u;
-    if (cx.J->u_burn) {
-      u = valid ? cx.J->u_burn[(cx.inj_base + cell) * 9 + d] : 1.0f;
-    } else {
-      u = bits_to_uniform(bits_at(cx.kburn, cell * 9u + (uint32_t)d, S64_HALF_BURN, mode));
-    }
-    const float w = __shfl_sync(GCA_FULL, cx.windreg, d);
-    float s = 1.0f;
-    if (S.pslope != nullptr && valid) s = S.pslope[(cx.cell_base + cell) * 8 + dir_slot(d)];
-    const float plo = __fmul_rn(__fmul_rn(sm.base_lo[t], w), s);
-    const float phi = __fmul_rn(__fmul_rn(sm.base_hi[t], w), s);
-    bool ig = valid && (u < plo);
-    if (valid && !ig && (u < phi)) {
-      // threshold cell: the float32 enclosure cannot decide -> reference-order evaluation
-      const int r = cell >> 6, c = cell & 63;
-      int hid = 3 | (3 << 3);
-      if (S.hidden != nullptr) hid = S.hidden[cx.cell_base + cell];
-      const float a = P.onep_veg[clip15(hid & 7)];
-      const float b = P.onep_den[clip15((hid >> 3) & 7)];
-      const float base = exact_base(sm, P, r, c, a, b);
-      const float p = __fmul_rn(__fmul_rn(base, w), s);
-      ig = u < p;
-      cx.n_thresh++;
-    }
-    if (ig) atomicOr(&ign32[(cell >> 6) * 2 + ((cell >> 5) & 1)], 1u << (cell & 31));
-    cx.n_draws += valid ? 1u : 0u;
+  for (int q0 = 0; q0 < PT; q0 += 64) {
+    uint32_t ca, cb;
+    const bool ia = eval_pair(sm, cx, q0 + cx.lane, PT, ca);
+    bool ib = false;
+    if (q0 + 32 < PT) ib = eval_pair(sm, cx, q0 + 32 + cx.lane, PT, cb);
+    if (ia) atomicOr(&ign32[(ca >> 6) * 2 + ((ca >> 5) & 1)], 1u << (ca & 31));
+    if (ib) atomicOr(&ign32[(cb >> 6) * 2 + ((cb >> 5) & 1)], 1u << (cb & 31));
   }
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(S64_WARPS * 32)
+__global__ void __launch_bounds__(S64_WARPS * 32, 7)
 env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gca_state S,
                   const int32_t* __restrict__ actions, const __grid_constant__ gca_step_out O,
                   const __grid_constant__ gca_inject J, const __grid_constant__ gca_state SNAP,
@@ -314,29 +386,13 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   const int K = P.K, mode = P.rng_mode;
   const size_t cell_base = (size_t)e * 4096;
 
-  // ---- global loads first (latency overlaps the key schedule) -----------------------------------
-  uint4 cv[8];
+  // ---- coalesced 128-bit read of the u8 grid -> tree / fire row masks ---------------------------
+  unsigned long long t0, t1, f0, f1;
   {
+    uint4 cv[8];
     const uint4* cptr = reinterpret_cast<const uint4*>(S.cell + cell_base);
 #pragma unroll
     for (int i = 0; i < 8; ++i) cv[i] = cptr[i * 32 + lane];
-  }
-  const ulonglong2 dz = reinterpret_cast<const ulonglong2*>(S.doused + (size_t)e * 64)[lane];
-  uint2 rm = reinterpret_cast<const uint2*>(S.row_min + (size_t)e * 64)[lane];
-  const uint32_t tick0 = S.tick[e];
-  uint32_t key0 = S.key[2 * e], key1 = S.key[2 * e + 1];
-  int widx = S.wind_index[e];
-
-  // ---- shared-memory setup -----------------------------------------------------------------------
-  if (lane < 16) sm.fire32[lane] = 0u; else sm.fire32[272 + lane - 16] = 0u;   // fire rows -4..-1, 64..67
-  if (lane < 8) sm.dous32[lane] = 0u; else if (lane < 16) sm.dous32[264 + lane - 8] = 0u;  // rows -2,-1,64,65
-  store_row_views(sm.dous32 + (2 * lane + 2) * 4, dz.x);
-  store_row_views(sm.dous32 + (2 * lane + 3) * 4, dz.y);
-
-  key_schedule(sm, P, J, N, e, lane, key0, key1, widx);
-
-  // ---- u8 grid -> tree / fire row masks ----------------------------------------------------------
-  {
     uint16_t* trow = reinterpret_cast<uint16_t*>(sm.ign);
     uint16_t* frow = reinterpret_cast<uint16_t*>(sm.base_lo);
 #pragma unroll
@@ -348,8 +404,16 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       frow[chunk] = (uint16_t)f16;
     }
   }
+  const ulonglong2 dz = reinterpret_cast<const ulonglong2*>(S.doused + (size_t)e * 64)[lane];
+  uint2 rm = reinterpret_cast<const uint2*>(S.row_min + (size_t)e * 64)[lane];
+  const uint32_t tick0 = S.tick[e];
+  uint32_t key0 = S.key[2 * e], key1 = S.key[2 * e + 1];
+  int widx = S.wind_index[e];
+  if (lane < 16) sm.fire32[lane] = 0u; else sm.fire32[272 + lane - 16] = 0u;   // fire rows -4..-1, 64..67
+  if (lane < 8) sm.dous32[lane] = 0u; else if (lane < 16) sm.dous32[264 + lane - 8] = 0u;  // rows -2,-1,64,65
+  store_row_views(sm.dous32 + (2 * lane + 2) * 4, dz.x);
+  store_row_views(sm.dous32 + (2 * lane + 3) * 4, dz.y);
   __syncwarp();
-  unsigned long long t0, t1, f0, f1;
   {
     const ulonglong2 tt = reinterpret_cast<const ulonglong2*>(sm.ign)[lane];
     const ulonglong2 ff = reinterpret_cast<const ulonglong2*>(sm.base_lo)[lane];
@@ -400,6 +464,20 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   }
   __syncwarp();
 
+  // ---- front of sub-step 0: compact it and start fetching its hidden / slope-factor sectors so
+  //      that their DRAM latency hides behind the key schedule ---------------------------------------
+  unsigned long long fr0, fr1;
+  {
+    const unsigned long long fh0 = f0 | (f0 << 1) | (f0 >> 1);
+    const unsigned long long fh1 = f1 | (f1 << 1) | (f1 >> 1);
+    fr0 = t0 & (shfl64_up1(fh1, lane) | fh0 | fh1);
+    fr1 = t1 & (fh0 | fh1 | shfl64_down1(fh0, lane));
+  }
+  int T = build_front_list(sm, fr0, fr1, lane, 0);
+  prefetch_front(sm, S, cell_base, min(T, S64_CAP), lane);
+
+  key_schedule(sm, P, J, N, e, lane, key0, key1, widx);
+
   StepCtx cx;
   cx.P = &P; cx.S = &S; cx.J = &J;
   cx.cell_base = cell_base;
@@ -408,6 +486,8 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   cx.n_draws = 0; cx.n_thresh = 0;
   uint32_t n_front = 0, n_ign = 0, n_ext = 0;
   const float w1 = P.ring_w[1], w2 = P.ring_w[2], w3 = P.ring_w[3], w4 = P.ring_w[4];
+  const uint32_t age_magic = 0xFFFFFFFFu / P.age_span;
+  const bool any_doused = __ballot_sync(GCA_FULL, (dz.x | dz.y) != 0ull) != 0u;
 
   // ================================ K CA sub-steps, all on-chip ===================================
   for (int j = 0; j < K; ++j) {
@@ -418,38 +498,22 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       const int wj = (int)sc[8];
       cx.windreg = lane < 9 ? P.winds[wj * 9 + lane] : 0.0f;
     }
-    // front = tree cells with a burning Moore neighbour
-    const unsigned long long fh0 = f0 | (f0 << 1) | (f0 >> 1);
-    const unsigned long long fh1 = f1 | (f1 << 1) | (f1 >> 1);
-    const unsigned long long up = shfl64_up1(fh1, lane);
-    const unsigned long long dn = shfl64_down1(fh0, lane);
-    const unsigned long long fr0 = t0 & (up | fh0 | fh1);
-    const unsigned long long fr1 = t1 & (fh0 | fh1 | dn);
-    const int nf = __popcll(fr0) + __popcll(fr1);
-    const int incl = warp_incl_scan(nf, lane);
-    const int T = __shfl_sync(GCA_FULL, incl, 31);
-    const int excl = incl - nf;
-    n_front += nf;
+    if (j > 0) {
+      // front = tree cells with a burning Moore neighbour
+      const unsigned long long fh0 = f0 | (f0 << 1) | (f0 >> 1);
+      const unsigned long long fh1 = f1 | (f1 << 1) | (f1 >> 1);
+      fr0 = t0 & (shfl64_up1(fh1, lane) | fh0 | fh1);
+      fr1 = t1 & (fh0 | fh1 | shfl64_down1(fh0, lane));
+      T = build_front_list(sm, fr0, fr1, lane, 0);
+      prefetch_front(sm, S, cell_base, min(T, S64_CAP), lane);
+    }
+    n_front += (lane == 0) ? (uint32_t)T : 0u;
 
     for (int pass_base = 0; pass_base < T; pass_base += S64_CAP) {
-      // ---- compact this pass's front cells into sm.list
-      {
-        int idx = excl - pass_base;
-        unsigned long long m = fr0;
-        int rowbits = (2 * lane) << 6;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          while (m) {
-            const int c = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            if (idx >= 0 && idx < S64_CAP) sm.list[idx] = (uint16_t)(rowbits | c);
-            ++idx;
-          }
-          m = fr1;
-          rowbits = (2 * lane + 1) << 6;
-        }
+      if (pass_base > 0) {  // more than CAP front cells (dense fires only): next slice of the list
+        build_front_list(sm, fr0, fr1, lane, pass_base);
+        prefetch_front(sm, S, cell_base, min(S64_CAP, T - pass_base), lane);
       }
-      __syncwarp();
       const int cnt = min(S64_CAP, T - pass_base);
       int PT = 0;
       for (int base = 0; base < cnt; base += 32) {
@@ -458,6 +522,8 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         const bool valid = t < cnt;
         const uint32_t cell = valid ? sm.list[t] : 0u;
         const int r = cell >> 6, c = cell & 63;
+        int hid = 3 | (3 << 3);
+        if (S.hidden != nullptr && valid) hid = S.hidden[cell_base + cell];
         uint32_t A, B, C;
         fire_window(sm, r, c, A, B, C);
         // ring populations (Chebyshev rings 1..4 around the centre)
@@ -470,17 +536,17 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
                               fmaf((float)(S3 - S2), w3, fmaf((float)(S2 - S1), w2, (float)S1 * w1)));
         uint32_t dirm = ((B >> 3) & 7u) | (((B >> 12) & 7u) << 3) | (((B >> 21) & 7u) << 6);
         dirm &= ~(1u << 4);
-        const uint32_t dwin = dous_window(sm, r, c);
         float Dlo = 0.0f, Dhi = 0.0f;
-        if (dwin) {
-          const int ni = __popc(dwin & ((0x0Eu << 5) | (0x0Eu << 10) | (0x0Eu << 15)));
-          const int nb = __popc(dwin) - ni;
-          const float Df = fmaf((float)nb, P.dous_border, (float)ni * P.dous_inner);
-          Dlo = __fmul_rn(Df, S64_LO);
-          Dhi = __fmul_rn(Df, S64_HI);
+        if (any_doused) {
+          const uint32_t dwin = dous_window(sm, r, c);
+          if (dwin) {
+            const int ni = __popc(dwin & ((0x0Eu << 5) | (0x0Eu << 10) | (0x0Eu << 15)));
+            const int nb = __popc(dwin) - ni;
+            const float Df = fmaf((float)nb, P.dous_border, (float)ni * P.dous_inner);
+            Dlo = __fmul_rn(Df, S64_LO);
+            Dhi = __fmul_rn(Df, S64_HI);
+          }
         }
-        int hid = 3 | (3 << 3);
-        if (S.hidden != nullptr && valid) hid = S.hidden[cell_base + cell];
         const float a = __shfl_sync(GCA_FULL, cx.lutreg, clip15(hid & 7));
         const float b = __shfl_sync(GCA_FULL, cx.lutreg, 8 + clip15((hid >> 3) & 7));
         const float ph_lo = __fsub_rn(__fmul_rn(Hf, S64_LO), Dhi);
@@ -492,10 +558,11 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         const int incl2 = warp_incl_scan(nd, lane);
         int off = PT + incl2 - nd;
         uint32_t m = nd ? dirm : 0u;
+        const uint32_t tag = (uint32_t)t << 4;
         while (m) {
-          const int d = __ffs(m) - 1;
+          const uint32_t d = __ffs(m) - 1;
           m &= m - 1;
-          sm.pairs[off++] = (uint16_t)((t << 4) | d);
+          sm.pairs[off++] = (uint16_t)(tag | d);
         }
         PT += __shfl_sync(GCA_FULL, incl2, 31);
       }
@@ -503,30 +570,64 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     }
     __syncwarp();
 
-    // ---- apply: ignitions, burn-outs, regrowth ---------------------------------------------------
+    // ---- apply: ignitions (with their fire-age draws), burn-outs, regrowth ------------------------
     const unsigned long long I0 = sm.ign[2 * lane], I1 = sm.ign[2 * lane + 1];
-    if (I0 | I1) {
+    const int ni_l = __popcll(I0) + __popcll(I1);
+    const int incl_i = warp_incl_scan(ni_l, lane);
+    const int NI = __shfl_sync(GCA_FULL, incl_i, 31);
+    if (NI > 0) {
       sm.ign[2 * lane] = 0ull;
       sm.ign[2 * lane + 1] = 0ull;
       const TfKey ka1 = tf_key(sc[4], sc[5]), ka2 = tf_key(sc[6], sc[7]);
-      unsigned long long m = I0;
-      int row = 2 * lane;
+      uint32_t* dt = reinterpret_cast<uint32_t*>(sm.base_lo);  // burn-out tick per listed ignition
+      for (int base = 0; base < NI; base += S64_CAP) {
+        {
+          int idx = incl_i - ni_l - base;
+          unsigned long long m = I0;
+          int rowbits = (2 * lane) << 6;
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        while (m) {
-          const int c = __ffsll((long long)m) - 1;
-          m &= m - 1;
-          const uint32_t cell = (uint32_t)(row * 64 + c);
-          int age;
-          if (J.age_new) age = J.age_new[cx.inj_base + cell];
-          else age = randint_from_bits(bits_at(ka1, cell, S64_HALF_CELL, mode), bits_at(ka2, cell, S64_HALF_CELL, mode),
-                                       P.age_lo, P.age_span, P.age_mult);
-          const uint32_t dabs = tick0 + (uint32_t)j + (uint32_t)age;  // burn-out tick
-          S.death[cell_base + cell] = (uint16_t)dabs;
-          if (half == 0) rm.x = min(rm.x, dabs); else rm.y = min(rm.y, dabs);
+          for (int half = 0; half < 2; ++half) {
+            while (m) {
+              const int c = __ffsll((long long)m) - 1;
+              m &= m - 1;
+              if ((unsigned)idx < (unsigned)S64_CAP) sm.list[idx] = (uint16_t)(rowbits | c);
+              ++idx;
+            }
+            m = I1;
+            rowbits = (2 * lane + 1) << 6;
+          }
         }
-        m = I1;
-        row = 2 * lane + 1;
+        __syncwarp();
+        const int cnt = min(S64_CAP, NI - base);
+        // two lanes per ignition: randint needs two independent words (jax.random.randint)
+        for (int tb = 0; tb < 2 * cnt; tb += 32) {
+          const int task = tb + lane, i = task >> 1;
+          const bool valid = i < cnt;
+          const uint32_t cell = sm.list[valid ? i : 0];
+          uint32_t bits = 0;
+          if (J.age_new == nullptr) bits = bits_at((lane & 1) ? ka2 : ka1, cell, S64_HALF_CELL, mode);
+          const uint32_t other = __shfl_xor_sync(GCA_FULL, bits, 1);
+          if (valid && !(lane & 1)) {
+            int age;
+            if (J.age_new) age = J.age_new[cx.inj_base + cell];
+            else {
+              const uint32_t hm = fastmod(bits, P.age_span, age_magic), lm = fastmod(other, P.age_span, age_magic);
+              age = P.age_lo + (int)fastmod(hm * P.age_mult + lm, P.age_span, age_magic);
+            }
+            const uint32_t dabs = tick0 + (uint32_t)j + (uint32_t)age;  // burn-out tick
+            S.death[cell_base + cell] = (uint16_t)dabs;
+            dt[i] = dabs;
+          }
+        }
+        __syncwarp();
+        {
+          int idx = incl_i - ni_l - base;
+          for (int q = __popcll(I0); q > 0; --q, ++idx)
+            if ((unsigned)idx < (unsigned)S64_CAP) rm.x = min(rm.x, dt[idx]);
+          for (int q = __popcll(I1); q > 0; --q, ++idx)
+            if ((unsigned)idx < (unsigned)S64_CAP) rm.y = min(rm.y, dt[idx]);
+        }
+        __syncwarp();
       }
     }
     unsigned long long ext0 = die0, ext1 = die1;
@@ -556,7 +657,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         row = 2 * lane + 1;
       }
     }
-    n_ign += __popcll(I0) + __popcll(I1);
+    n_ign += ni_l;
     n_ext += __popcll(ext0) + __popcll(ext1);
     t0 = (t0 & ~I0) | g0;
     t1 = (t1 & ~I1) | g1;
