@@ -276,32 +276,39 @@ struct StepCtx {
 // re-dealt in 16-column pieces (piece p = 4*row + quarter goes to lane p % 32) so that a long
 // horizontal run of front cells -- the top/bottom edge of a burning blob -- is shared by several
 // lanes instead of serialising one.
-__device__ __forceinline__ int build_front_list(WarpSmem& sm, unsigned long long fr0, unsigned long long fr1,
-                                                int lane, int pass_base) {
+__device__ __noinline__ int build_front_list(WarpSmem& sm, unsigned long long fr0, unsigned long long fr1,
+                                             int lane, int pass_base) {
   reinterpret_cast<ulonglong2*>(sm.pairs)[lane] = make_ulonglong2(fr0, fr1);
   __syncwarp();
   const uint16_t* q16 = reinterpret_cast<const uint16_t*>(sm.pairs);
-  uint32_t pc[8];
-  int n = 0;
+  // this lane's 8 pieces as two 64-bit words: bit 16*k + b of word h <-> piece (4h + k), column bit b
+  unsigned long long w[2];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    pc[k] = q16[lane + 32 * k];
-    n += __popc(pc[k]);
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t lo = (uint32_t)q16[lane + 32 * (4 * h)] | ((uint32_t)q16[lane + 32 * (4 * h + 1)] << 16);
+    const uint32_t hi = (uint32_t)q16[lane + 32 * (4 * h + 2)] | ((uint32_t)q16[lane + 32 * (4 * h + 3)] << 16);
+    w[h] = ((unsigned long long)hi << 32) | lo;
   }
+  const int n = __popcll(w[0]) + __popcll(w[1]);
   const int incl = warp_incl_scan(n, lane);
   const int T = __shfl_sync(GCA_FULL, incl, 31);
   int idx = incl - n - pass_base;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    uint32_t m = pc[k];
-    const int p = lane + 32 * k;
-    const uint32_t base = ((uint32_t)(p >> 2) << 6) | ((uint32_t)(p & 3) << 4);
+  // piece p = lane + 32 q  ->  row (lane >> 2) + 8 q, columns 16 (lane & 3) ..
+  const uint32_t lane_base = ((uint32_t)(lane >> 2) << 6) | ((uint32_t)(lane & 3) << 4);
+  unsigned long long m = w[0];
+  uint32_t word_base = lane_base;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
     while (m) {
-      const uint32_t b = __ffs(m) - 1;
+      const uint32_t b = (uint32_t)__ffsll((long long)m) - 1u;
       m &= m - 1;
-      if ((unsigned)idx < (unsigned)S64_CAP) sm.list[idx] = (uint16_t)(base | b);
+      // piece within the word = b >> 4 -> 8 rows further down per piece
+      const uint32_t cell = word_base + ((b >> 4) << 9) + (b & 15u);
+      if ((unsigned)idx < (unsigned)S64_CAP) sm.list[idx] = (uint16_t)cell;
       ++idx;
     }
+    m = w[1];
+    word_base = lane_base + (4u << 9);
   }
   __syncwarp();
   return T;
@@ -358,7 +365,7 @@ __device__ __forceinline__ bool eval_pair(const WarpSmem& sm, StepCtx& cx, int q
 
 // Evaluate the buffered draws, two per lane per iteration (two independent threefry chains give
 // the ALU pipe instruction-level parallelism), and OR the ignitions into sm.ign.
-__device__ __forceinline__ void flush_pairs(WarpSmem& sm, StepCtx& cx, int PT) {
+__device__ __noinline__ void flush_pairs(WarpSmem& sm, StepCtx& cx, int PT) {
   __syncwarp();
   uint32_t* ign32 = reinterpret_cast<uint32_t*>(sm.ign);
   for (int q0 = 0; q0 < PT; q0 += 64) {
@@ -422,7 +429,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   __syncwarp();
   sm.ign[2 * lane] = 0ull;
   sm.ign[2 * lane + 1] = 0ull;
-  const unsigned long long t0i = t0, t1i = t1, f0i = f0, f1i = f1;
+  unsigned long long ch0 = 0ull, ch1 = 0ull;  // cells whose state changed during this env step
   store_row_views(sm.fire32 + (2 * lane + 4) * 4, f0);
   store_row_views(sm.fire32 + (2 * lane + 5) * 4, f1);
 
@@ -557,12 +564,12 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         const int nd = (valid && bhi > 0.0f) ? __popc(dirm) : 0;
         const int incl2 = warp_incl_scan(nd, lane);
         int off = PT + incl2 - nd;
-        uint32_t m = nd ? dirm : 0u;
+        const uint32_t em = nd ? dirm : 0u;
         const uint32_t tag = (uint32_t)t << 4;
-        while (m) {
-          const uint32_t d = __ffs(m) - 1;
-          m &= m - 1;
-          sm.pairs[off++] = (uint16_t)(tag | d);
+#pragma unroll
+        for (uint32_t d = 0; d < 9; ++d) {
+          if (d == 4) continue;
+          if (em & (1u << d)) sm.pairs[off++] = (uint16_t)(tag | d);
         }
         PT += __shfl_sync(GCA_FULL, incl2, 31);
       }
@@ -659,6 +666,8 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     }
     n_ign += ni_l;
     n_ext += __popcll(ext0) + __popcll(ext1);
+    ch0 |= I0 | ext0 | g0;
+    ch1 |= I1 | ext1 | g1;
     t0 = (t0 & ~I0) | g0;
     t1 = (t1 & ~I1) | g1;
     f0 = (f0 & ~ext0) | I0;
@@ -672,7 +681,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
 
   // ---- sparse in-place write-back of the cells that changed --------------------------------------
   {
-    unsigned long long ch = (t0 ^ t0i) | (f0 ^ f0i);
+    unsigned long long ch = ch0;
     unsigned long long tt = t0, ff = f0;
     int row = 2 * lane;
 #pragma unroll 1
@@ -683,7 +692,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         const uint8_t code = ((ff >> c) & 1ull) ? 2 : (((tt >> c) & 1ull) ? 1 : 0);
         S.cell[cell_base + row * 64 + c] = code;
       }
-      ch = (t1 ^ t1i) | (f1 ^ f1i);
+      ch = ch1;
       tt = t1; ff = f1;
       row = 2 * lane + 1;
     }
