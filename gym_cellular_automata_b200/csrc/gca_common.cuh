@@ -49,6 +49,24 @@ __device__ __forceinline__ void threefry2x32(const TfKey& k, uint32_t x0, uint32
   o1 = x1;
 }
 
+// Out-of-line copy for the places that are not throughput critical (key schedule, fire-age draws,
+// regrowth): keeps the kernel's hot code inside the instruction cache.
+static __device__ __noinline__ void threefry2x32_ni(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t& o0,
+                                             uint32_t& o1) {
+  threefry2x32(tf_key(k0, k1), x0, x1, o0, o1);
+}
+
+__device__ __forceinline__ uint32_t bits_at_ni(const TfKey& k, uint32_t idx, uint32_t half, int mode) {
+  uint32_t o0, o1;
+  if (mode == GCA_RNG_LEGACY) {
+    const bool first = idx < half;
+    threefry2x32_ni(k.k0, k.k1, first ? idx : idx - half, first ? idx + half : idx, o0, o1);
+    return first ? o0 : o1;
+  }
+  threefry2x32_ni(k.k0, k.k1, 0u, idx, o0, o1);
+  return o0 ^ o1;
+}
+
 // Element `idx` of jax.random.bits(key, (n,)) with n even and half = n / 2.
 //   legacy:        idx <  half -> word 0 of block (idx, idx + half)
 //                  idx >= half -> word 1 of block (idx - half, idx)
@@ -104,10 +122,8 @@ __device__ __forceinline__ void split_thread(uint32_t k0, uint32_t k1, int mode,
 __device__ __forceinline__ void split_pair(uint32_t k0, uint32_t k1, int mode, int lane, uint32_t& n0,
                                            uint32_t& n1, uint32_t& s0, uint32_t& s1) {
   const uint32_t w = lane & 1;
-  const TfKey k = tf_key(k0, k1);
   uint32_t o0, o1;
-  if (mode == GCA_RNG_LEGACY) threefry2x32(k, w, w + 2u, o0, o1);
-  else threefry2x32(k, 0u, w, o0, o1);
+  threefry2x32_ni(k0, k1, mode == GCA_RNG_LEGACY ? w : 0u, mode == GCA_RNG_LEGACY ? w + 2u : w, o0, o1);
   const uint32_t p0 = __shfl_xor_sync(GCA_FULL, o0, 1);
   const uint32_t p1 = __shfl_xor_sync(GCA_FULL, o1, 1);
   const uint32_t a0 = w ? p0 : o0, a1 = w ? p1 : o1;  // block A (even lane)

@@ -112,7 +112,7 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 // one threefry block per lane with lane-specific key/counters, words swapped inside the lane pair
 __device__ __forceinline__ void tf_exchange(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t& o0,
                                             uint32_t& o1, uint32_t& p0, uint32_t& p1) {
-  threefry2x32(tf_key(k0, k1), c0, c1, o0, o1);
+  threefry2x32_ni(k0, k1, c0, c1, o0, o1);
   p0 = __shfl_xor_sync(GCA_FULL, o0, 1);
   p1 = __shfl_xor_sync(GCA_FULL, o1, 1);
 }
@@ -612,7 +612,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
           const bool valid = i < cnt;
           const uint32_t cell = sm.list[valid ? i : 0];
           uint32_t bits = 0;
-          if (J.age_new == nullptr) bits = bits_at((lane & 1) ? ka2 : ka1, cell, S64_HALF_CELL, mode);
+          if (J.age_new == nullptr) bits = bits_at_ni((lane & 1) ? ka2 : ka1, cell, S64_HALF_CELL, mode);
           const uint32_t other = __shfl_xor_sync(GCA_FULL, bits, 1);
           if (valid && !(lane & 1)) {
             int age;
@@ -657,7 +657,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
           const uint32_t cell = (uint32_t)(row * 64 + c);
           float u;
           if (J.u_grow) u = J.u_grow[cx.inj_base + cell];
-          else u = bits_to_uniform(bits_at(kg, cell, S64_HALF_CELL, mode));
+          else u = bits_to_uniform(bits_at_ni(kg, cell, S64_HALF_CELL, mode));
           if (u < P.p_tree) { if (half == 0) g0 |= 1ull << c; else g1 |= 1ull << c; }
         }
         m = ~(t1 | f1);
