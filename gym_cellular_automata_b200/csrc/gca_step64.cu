@@ -41,9 +41,11 @@ struct __align__(16) WarpSmem {
   unsigned long long ign[64];     // ignition accumulator (unpack: tree rows)
   float base_lo[S64_CAP];         // per front cell: enclosure of (p_h (1+p_veg)) (1+p_den)
   float base_hi[S64_CAP];         //   (unpack: fire rows; apply: burn-out ticks of new fires)
-  uint16_t list[S64_CAP];         // front cells of the current pass: (row << 6) | col
-                                  //   (apply: cells ignited in this sub-step)
-  uint16_t pairs[S64_PCAP];       // (list index << 4) | direction  (list build: front rows)
+  uint16_t list[S64_CAP];         // front cells: (row << 6) | col.  Built once per env step and
+                                  //   extended incrementally; stale entries fail the frontbb test
+  uint16_t pairs[S64_PCAP];       // (list index << 4) | direction  (list build: front rows;
+                                  //   apply: cells ignited in this sub-step)
+  unsigned long long frontbb[64]; // front mask of the current sub-step (validates list entries)
   uint32_t sched[GCA_MAX_K][12];  // per sub-step: Sburn[2] Sgrow[2] ak1[2] ak2[2] wind change step pad
 };
 
@@ -258,19 +260,6 @@ __device__ __noinline__ float exact_base(const WarpSmem& sm, const gca_params& P
   return __fmul_rn(__fmul_rn(ph, a), b);
 }
 
-struct StepCtx {
-  const gca_params* P;
-  const gca_state* S;
-  const gca_inject* J;
-  size_t cell_base;  // e * 4096
-  size_t inj_base;   // (j * N + e) * 4096
-  int lane;
-  float lutreg;      // lane i < 6: onep_veg[i]; 8 <= i < 14: onep_den[i - 8]
-  float windreg;     // lane i < 9: wind matrix entry i of the current sub-step
-  TfKey kburn;
-  uint32_t n_draws, n_thresh;
-};
-
 // Compact the front cells [pass_base, pass_base + CAP) of the row masks fr0 (row 2*lane) and fr1
 // (row 2*lane+1) into sm.list and return the total number of front cells.  The rows are first
 // re-dealt in 16-column pieces (piece p = 4*row + quarter goes to lane p % 32) so that a long
@@ -314,12 +303,12 @@ __device__ __noinline__ int build_front_list(WarpSmem& sm, unsigned long long fr
   return T;
 }
 
-// Touch the hidden byte and the 32-byte slope-factor sector of every listed front cell so that
-// they are in L1/L2 by the time the cell and draw phases ask for them.
-__device__ __forceinline__ void prefetch_front(const WarpSmem& sm, const gca_state& S, size_t cell_base, int cnt,
-                                               int lane) {
+// Touch the hidden byte and the 32-byte slope-factor sector of listed front cells [from, to) so
+// that they are in L2 (and, capacity permitting, L1) when the cell and draw phases ask for them.
+__device__ __forceinline__ void prefetch_front(const WarpSmem& sm, const gca_state& S, size_t cell_base, int from,
+                                               int to, int lane) {
   if (S.hidden == nullptr) return;
-  for (int t = lane; t < cnt; t += 32) {
+  for (int t = from + lane; t < to; t += 32) {
     const uint32_t cell = sm.list[t];
     prefetch_l1(S.hidden + cell_base + cell);
     if (S.pslope != nullptr) prefetch_l1(S.pslope + (cell_base + cell) * 8);
@@ -327,23 +316,23 @@ __device__ __forceinline__ void prefetch_front(const WarpSmem& sm, const gca_sta
 }
 
 // One buffered (front cell, burning direction) draw: returns whether it ignites the cell.
-__device__ __forceinline__ bool eval_pair(const WarpSmem& sm, StepCtx& cx, int q, int PT, uint32_t& cell_out) {
-  const gca_params& P = *cx.P;
-  const gca_state& S = *cx.S;
+__device__ __forceinline__ bool eval_pair(const WarpSmem& sm, const gca_params& P, const gca_state& S,
+                                          const gca_inject& J, const TfKey& kburn, float windreg, size_t cell_base,
+                                          size_t inj_base, int q, int PT, uint32_t& cell_out, uint32_t& n_thresh) {
   const bool valid = q < PT;
   const uint32_t ent = valid ? sm.pairs[q] : 0u;
   const int t = ent >> 4, d = ent & 15;
   const uint32_t cell = sm.list[t];
   cell_out = cell;
   float s = 1.0f;
-  if (S.pslope != nullptr && valid) s = S.pslope[(cx.cell_base + cell) * 8 + dir_slot(d)];
+  if (S.pslope != nullptr && valid) s = S.pslope[(cell_base + cell) * 8 + dir_slot(d)];
   float u;
-  if (cx.J->u_burn) {
-    u = valid ? cx.J->u_burn[(cx.inj_base + cell) * 9 + d] : 1.0f;
+  if (J.u_burn) {
+    u = valid ? J.u_burn[(inj_base + cell) * 9 + d] : 1.0f;
   } else {
-    u = bits_to_uniform(bits_at(cx.kburn, cell * 9u + (uint32_t)d, S64_HALF_BURN, P.rng_mode));
+    u = bits_to_uniform(bits_at(kburn, cell * 9u + (uint32_t)d, S64_HALF_BURN, P.rng_mode));
   }
-  const float w = __shfl_sync(GCA_FULL, cx.windreg, d);
+  const float w = __shfl_sync(GCA_FULL, windreg, d);
   const float plo = __fmul_rn(__fmul_rn(sm.base_lo[t], w), s);
   const float phi = __fmul_rn(__fmul_rn(sm.base_hi[t], w), s);
   bool ig = valid && (u < plo);
@@ -351,32 +340,25 @@ __device__ __forceinline__ bool eval_pair(const WarpSmem& sm, StepCtx& cx, int q
     // threshold cell: the float32 enclosure cannot decide -> reference-order evaluation
     const int r = cell >> 6, c = cell & 63;
     int hid = 3 | (3 << 3);
-    if (S.hidden != nullptr) hid = S.hidden[cx.cell_base + cell];
+    if (S.hidden != nullptr) hid = S.hidden[cell_base + cell];
     const float a = P.onep_veg[clip15(hid & 7)];
     const float b = P.onep_den[clip15((hid >> 3) & 7)];
     const float base = exact_base(sm, P, r, c, a, b);
     const float p = __fmul_rn(__fmul_rn(base, w), s);
     ig = u < p;
-    cx.n_thresh++;
+    n_thresh++;
   }
-  cx.n_draws += valid ? 1u : 0u;
   return ig;
 }
 
-// Evaluate the buffered draws, two per lane per iteration (two independent threefry chains give
-// the ALU pipe instruction-level parallelism), and OR the ignitions into sm.ign.
-__device__ __noinline__ void flush_pairs(WarpSmem& sm, StepCtx& cx, int PT) {
-  __syncwarp();
-  uint32_t* ign32 = reinterpret_cast<uint32_t*>(sm.ign);
-  for (int q0 = 0; q0 < PT; q0 += 64) {
-    uint32_t ca, cb;
-    const bool ia = eval_pair(sm, cx, q0 + cx.lane, PT, ca);
-    bool ib = false;
-    if (q0 + 32 < PT) ib = eval_pair(sm, cx, q0 + 32 + cx.lane, PT, cb);
-    if (ia) atomicOr(&ign32[(ca >> 6) * 2 + ((ca >> 5) & 1)], 1u << (ca & 31));
-    if (ib) atomicOr(&ign32[(cb >> 6) * 2 + ((cb >> 5) & 1)], 1u << (cb & 31));
-  }
-  __syncwarp();
+__device__ __forceinline__ void front_masks(unsigned long long t0, unsigned long long t1, unsigned long long f0,
+                                            unsigned long long f1, int lane, unsigned long long& fr0,
+                                            unsigned long long& fr1) {
+  // front = tree cells with a burning Moore neighbour (row halos by warp shuffle)
+  const unsigned long long fh0 = f0 | (f0 << 1) | (f0 >> 1);
+  const unsigned long long fh1 = f1 | (f1 << 1) | (f1 >> 1);
+  fr0 = t0 & (shfl64_up1(fh1, lane) | fh0 | fh1);
+  fr1 = t1 & (fh0 | fh1 | shfl64_down1(fh0, lane));
 }
 
 __global__ void __launch_bounds__(S64_WARPS * 32, 7)
@@ -472,63 +454,90 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   __syncwarp();
 
   // ---- front of sub-step 0: compact it and start fetching its hidden / slope-factor sectors so
-  //      that their DRAM latency hides behind the key schedule ---------------------------------------
+  //      that their DRAM latency hides behind the key schedule.  The list is built ONCE per env
+  //      step; later sub-steps append the cells that joined the front (a handful) and skip the
+  //      entries that left it (ignited / no burning neighbour left) with a front bit-board test.
   unsigned long long fr0, fr1;
-  {
-    const unsigned long long fh0 = f0 | (f0 << 1) | (f0 >> 1);
-    const unsigned long long fh1 = f1 | (f1 << 1) | (f1 >> 1);
-    fr0 = t0 & (shfl64_up1(fh1, lane) | fh0 | fh1);
-    fr1 = t1 & (fh0 | fh1 | shfl64_down1(fh0, lane));
-  }
+  front_masks(t0, t1, f0, f1, lane, fr0, fr1);
   int T = build_front_list(sm, fr0, fr1, lane, 0);
-  prefetch_front(sm, S, cell_base, min(T, S64_CAP), lane);
+  bool dense = T > S64_CAP;  // more front cells than the list holds: rebuild per sub-step, in passes
+  int L = min(T, S64_CAP);
+  prefetch_front(sm, S, cell_base, 0, L, lane);
+  unsigned long long listed0 = fr0, listed1 = fr1;
 
   key_schedule(sm, P, J, N, e, lane, key0, key1, widx);
 
-  StepCtx cx;
-  cx.P = &P; cx.S = &S; cx.J = &J;
-  cx.cell_base = cell_base;
-  cx.lane = lane;
-  cx.lutreg = lane < 8 ? P.onep_veg[lane] : (lane < 16 ? P.onep_den[lane - 8] : 0.0f);
-  cx.n_draws = 0; cx.n_thresh = 0;
-  uint32_t n_front = 0, n_ign = 0, n_ext = 0;
+  const float lutreg = lane < 8 ? P.onep_veg[lane] : (lane < 16 ? P.onep_den[lane - 8] : 0.0f);
+  uint32_t n_draws = 0, n_thresh = 0, n_front = 0, n_ign = 0, n_ext = 0;
   const float w1 = P.ring_w[1], w2 = P.ring_w[2], w3 = P.ring_w[3], w4 = P.ring_w[4];
   const uint32_t age_magic = 0xFFFFFFFFu / P.age_span;
   const bool any_doused = __ballot_sync(GCA_FULL, (dz.x | dz.y) != 0ull) != 0u;
+  const uint32_t* front32 = reinterpret_cast<const uint32_t*>(sm.frontbb);
+  uint32_t* ign32 = reinterpret_cast<uint32_t*>(sm.ign);
 
   // ================================ K CA sub-steps, all on-chip ===================================
   for (int j = 0; j < K; ++j) {
     const uint32_t* sc = sm.sched[j];
-    cx.kburn = tf_key(sc[0], sc[1]);
-    cx.inj_base = ((size_t)j * N + e) * 4096;
-    {
-      const int wj = (int)sc[8];
-      cx.windreg = lane < 9 ? P.winds[wj * 9 + lane] : 0.0f;
-    }
+    const TfKey kburn = tf_key(sc[0], sc[1]);
+    const size_t inj_base = ((size_t)j * N + e) * 4096;
+    const float windreg = lane < 9 ? P.winds[(int)sc[8] * 9 + lane] : 0.0f;
     if (j > 0) {
-      // front = tree cells with a burning Moore neighbour
-      const unsigned long long fh0 = f0 | (f0 << 1) | (f0 >> 1);
-      const unsigned long long fh1 = f1 | (f1 << 1) | (f1 >> 1);
-      fr0 = t0 & (shfl64_up1(fh1, lane) | fh0 | fh1);
-      fr1 = t1 & (fh0 | fh1 | shfl64_down1(fh0, lane));
-      T = build_front_list(sm, fr0, fr1, lane, 0);
-      prefetch_front(sm, S, cell_base, min(T, S64_CAP), lane);
-    }
-    n_front += (lane == 0) ? (uint32_t)T : 0u;
-
-    for (int pass_base = 0; pass_base < T; pass_base += S64_CAP) {
-      if (pass_base > 0) {  // more than CAP front cells (dense fires only): next slice of the list
-        build_front_list(sm, fr0, fr1, lane, pass_base);
-        prefetch_front(sm, S, cell_base, min(S64_CAP, T - pass_base), lane);
+      front_masks(t0, t1, f0, f1, lane, fr0, fr1);
+      if (!dense) {
+        const unsigned long long nw0 = fr0 & ~listed0, nw1 = fr1 & ~listed1;
+        const int nn = __popcll(nw0) + __popcll(nw1);
+        const int incl_n = warp_incl_scan(nn, lane);
+        const int tot_n = __shfl_sync(GCA_FULL, incl_n, 31);
+        if (L + tot_n > S64_CAP) {
+          dense = true;
+        } else if (tot_n > 0) {
+          int idx = L + incl_n - nn;
+          unsigned long long m = nw0;
+          int rowbits = (2 * lane) << 6;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            while (m) {
+              const uint32_t cell = (uint32_t)(rowbits | (__ffsll((long long)m) - 1));
+              m &= m - 1;
+              sm.list[idx++] = (uint16_t)cell;
+              if (S.hidden != nullptr) {
+                prefetch_l1(S.hidden + cell_base + cell);
+                if (S.pslope != nullptr) prefetch_l1(S.pslope + (cell_base + cell) * 8);
+              }
+            }
+            m = nw1;
+            rowbits = (2 * lane + 1) << 6;
+          }
+          L += tot_n;
+          listed0 |= nw0;
+          listed1 |= nw1;
+        }
       }
-      const int cnt = min(S64_CAP, T - pass_base);
+      if (dense) {
+        T = build_front_list(sm, fr0, fr1, lane, 0);
+        prefetch_front(sm, S, cell_base, 0, min(T, S64_CAP), lane);
+      }
+    }
+    sm.frontbb[2 * lane] = fr0;
+    sm.frontbb[2 * lane + 1] = fr1;
+    n_front += (uint32_t)(__popcll(fr0) + __popcll(fr1));
+    __syncwarp();
+
+    const int total = dense ? T : L;
+    for (int pass_base = 0; pass_base < total; pass_base += S64_CAP) {
+      if (pass_base > 0) {  // dense fires only: next slice of the list
+        build_front_list(sm, fr0, fr1, lane, pass_base);
+        prefetch_front(sm, S, cell_base, 0, min(S64_CAP, total - pass_base), lane);
+      }
+      const int cnt = min(S64_CAP, total - pass_base);
       int PT = 0;
       for (int base = 0; base < cnt; base += 32) {
-        if (PT + 256 > S64_PCAP) { flush_pairs(sm, cx, PT); PT = 0; }
         const int t = base + lane;
-        const bool valid = t < cnt;
-        const uint32_t cell = valid ? sm.list[t] : 0u;
+        const bool inrange = t < cnt;
+        const uint32_t cell = inrange ? sm.list[t] : 0u;
         const int r = cell >> 6, c = cell & 63;
+        // still a front cell in this sub-step?
+        const bool valid = inrange && ((front32[cell >> 5] >> (cell & 31)) & 1u);
         int hid = 3 | (3 << 3);
         if (S.hidden != nullptr && valid) hid = S.hidden[cell_base + cell];
         uint32_t A, B, C;
@@ -554,8 +563,8 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
             Dhi = __fmul_rn(Df, S64_HI);
           }
         }
-        const float a = __shfl_sync(GCA_FULL, cx.lutreg, clip15(hid & 7));
-        const float b = __shfl_sync(GCA_FULL, cx.lutreg, 8 + clip15((hid >> 3) & 7));
+        const float a = __shfl_sync(GCA_FULL, lutreg, clip15(hid & 7));
+        const float b = __shfl_sync(GCA_FULL, lutreg, 8 + clip15((hid >> 3) & 7));
         const float ph_lo = __fsub_rn(__fmul_rn(Hf, S64_LO), Dhi);
         const float ph_hi = __fsub_rn(__fmul_rn(Hf, S64_HI), Dlo);
         const float blo = __fmul_rn(__fmul_rn(ph_lo, a), b);
@@ -572,8 +581,25 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
           if (em & (1u << d)) sm.pairs[off++] = (uint16_t)(tag | d);
         }
         PT += __shfl_sync(GCA_FULL, incl2, 31);
+
+        // ---- draw phase (single call site): when the buffer could overflow next round, or at the
+        //      end of the pass.  Two draws per lane per iteration = two independent threefry chains.
+        if (PT + 256 > S64_PCAP || base + 32 >= cnt) {
+          __syncwarp();
+          for (int q0 = 0; q0 < PT; q0 += 64) {
+            uint32_t ca, cb = 0;
+            const bool ia = eval_pair(sm, P, S, J, kburn, windreg, cell_base, inj_base, q0 + lane, PT, ca, n_thresh);
+            bool ib = false;
+            if (q0 + 32 < PT)
+              ib = eval_pair(sm, P, S, J, kburn, windreg, cell_base, inj_base, q0 + 32 + lane, PT, cb, n_thresh);
+            if (ia) atomicOr(&ign32[ca >> 5], 1u << (ca & 31));
+            if (ib) atomicOr(&ign32[cb >> 5], 1u << (cb & 31));
+          }
+          n_draws += (lane == 0) ? (uint32_t)PT : 0u;
+          PT = 0;
+          __syncwarp();
+        }
       }
-      flush_pairs(sm, cx, PT);
     }
     __syncwarp();
 
@@ -597,7 +623,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
             while (m) {
               const int c = __ffsll((long long)m) - 1;
               m &= m - 1;
-              if ((unsigned)idx < (unsigned)S64_CAP) sm.list[idx] = (uint16_t)(rowbits | c);
+              if ((unsigned)idx < (unsigned)S64_CAP) sm.pairs[idx] = (uint16_t)(rowbits | c);
               ++idx;
             }
             m = I1;
@@ -610,13 +636,13 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         for (int tb = 0; tb < 2 * cnt; tb += 32) {
           const int task = tb + lane, i = task >> 1;
           const bool valid = i < cnt;
-          const uint32_t cell = sm.list[valid ? i : 0];
+          const uint32_t cell = sm.pairs[valid ? i : 0];
           uint32_t bits = 0;
           if (J.age_new == nullptr) bits = bits_at_ni((lane & 1) ? ka2 : ka1, cell, S64_HALF_CELL, mode);
           const uint32_t other = __shfl_xor_sync(GCA_FULL, bits, 1);
           if (valid && !(lane & 1)) {
             int age;
-            if (J.age_new) age = J.age_new[cx.inj_base + cell];
+            if (J.age_new) age = J.age_new[inj_base + cell];
             else {
               const uint32_t hm = fastmod(bits, P.age_span, age_magic), lm = fastmod(other, P.age_span, age_magic);
               age = P.age_lo + (int)fastmod(hm * P.age_mult + lm, P.age_span, age_magic);
@@ -656,7 +682,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
           m &= m - 1;
           const uint32_t cell = (uint32_t)(row * 64 + c);
           float u;
-          if (J.u_grow) u = J.u_grow[cx.inj_base + cell];
+          if (J.u_grow) u = J.u_grow[inj_base + cell];
           else u = bits_to_uniform(bits_at_ni(kg, cell, S64_HALF_CELL, mode));
           if (u < P.p_tree) { if (half == 0) g0 |= 1ull << c; else g1 |= 1ull << c; }
         }
@@ -702,9 +728,9 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   const int fcount = __reduce_add_sync(GCA_FULL, __popcll(f0) + __popcll(f1));
 
   if (O.stats != nullptr) {
-    const uint32_t a = __reduce_add_sync(GCA_FULL, n_front), b = __reduce_add_sync(GCA_FULL, cx.n_draws);
+    const uint32_t a = __reduce_add_sync(GCA_FULL, n_front), b = __reduce_add_sync(GCA_FULL, n_draws);
     const uint32_t c = __reduce_add_sync(GCA_FULL, n_ign), d = __reduce_add_sync(GCA_FULL, n_ext);
-    const uint32_t t = __reduce_add_sync(GCA_FULL, cx.n_thresh);
+    const uint32_t t = __reduce_add_sync(GCA_FULL, n_thresh);
     if (lane == 0) {
       atomicAdd(&O.stats[0], (unsigned long long)a);
       atomicAdd(&O.stats[1], (unsigned long long)b);
