@@ -20,7 +20,7 @@ HEADERS = ("gca_common.cuh", os.path.join("..", "..", "include", "gca.h"))
 GCA_MAX_R = 10
 GCA_MAX_K = 8
 RNG_LEGACY, RNG_PARTITIONABLE = 0, 1
-FLAG_AUTO_RESET, FLAG_NO_HIDDEN, FLAG_CA_ONLY = 1, 2, 4
+FLAG_AUTO_RESET, FLAG_NO_HIDDEN, FLAG_CA_ONLY, FLAG_NO_TMA = 1, 2, 4, 8
 
 
 class GcaError(RuntimeError):
@@ -49,6 +49,7 @@ class GcaState(C.Structure):
         ("wind_index", C.c_void_p), ("position", C.c_void_p), ("time", C.c_void_p),
         ("time_step", C.c_void_p), ("is_night", C.c_void_p),
         ("steps_elapsed", C.c_void_p), ("reward_accumulated", C.c_void_p),
+        ("scratch_cell", C.c_void_p), ("scratch_u32", C.c_void_p),
     ]
 
 

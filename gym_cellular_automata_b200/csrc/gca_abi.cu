@@ -18,6 +18,10 @@ cudaError_t launch_render(const gca_params&, int, const uint8_t*, const uint64_t
                           const int32_t*, const uint8_t*, int, int, uint32_t*, void*, cudaStream_t);
 cudaError_t launch_threefry_bits(const uint32_t*, long long, int, uint32_t*, cudaStream_t);
 cudaError_t launch_threefry_split_part(const uint32_t*, int, uint32_t*, cudaStream_t);
+cudaError_t launch_tiled_env_step(const gca_params&, const gca_state&, const int32_t*, const gca_step_out&,
+                                  const gca_inject&, uint32_t, uint8_t*, uint32_t*, int32_t*, int, cudaStream_t);
+cudaError_t launch_auto_reset(const gca_params&, const gca_state&, const gca_state&, const float*, float*,
+                              const uint8_t*, cudaStream_t);
 }  // namespace gca
 
 static thread_local char g_err[256] = "";
@@ -152,7 +156,21 @@ int gca_env_step(const gca_params* p, const gca_state* s, const int32_t* actions
     return check_cuda(gca::launch_env_step64(*p, st, actions, o, j, sn, snapshot_reward, flags, (cudaStream_t)stream),
                       "env_step64");
   }
-  return fail(GCA_ERR_UNSUPPORTED, "gca_env_step: only 64x64 grids in this build (tiled path: gca_env_step_tiled)");
+  // any other grid: tiled path, one launch per CA sub-step
+  if (((long long)p->H * p->W) & 1) return fail(GCA_ERR_UNSUPPORTED, "gca_env_step: H*W must be even");
+  if (!s->scratch_cell || !s->scratch_u32)
+    return fail(GCA_ERR_ARG, "gca_env_step: grids other than 64x64 need scratch_cell and scratch_u32");
+  rc = check_cuda(gca::launch_tiled_env_step(*p, st, actions, o, j, flags, s->scratch_cell, s->scratch_u32,
+                                             reinterpret_cast<int32_t*>(s->scratch_u32) + 12 * (size_t)s->N,
+                                             (flags & GCA_FLAG_NO_TMA) ? 0 : 1, (cudaStream_t)stream),
+                  "env_step_tiled");
+  if (rc) return rc;
+  if (flags & GCA_FLAG_AUTO_RESET) {
+    if (!o.terminated) return fail(GCA_ERR_ARG, "gca_env_step: auto-reset on the tiled path needs out->terminated");
+    return check_cuda(gca::launch_auto_reset(*p, st, sn, snapshot_reward, o.reward, o.terminated, (cudaStream_t)stream),
+                      "auto_reset");
+  }
+  return GCA_OK;
 }
 
 int gca_alexandridis_step(const gca_params* p, const gca_state* s, const gca_step_out* out, const gca_inject* inj,

@@ -130,7 +130,7 @@ __global__ void reward_done_kernel(gca_params P, gca_state S, float* reward, uin
 // terminated exit immediately.
 // ---------------------------------------------------------------------------------------------
 __global__ void conditional_reset_kernel(gca_params P, gca_state S, gca_state SNAP, const float* __restrict__ snap_reward,
-                                         float* reward, uint8_t* terminated) {
+                                         float* reward, uint8_t* terminated, int clear_flag) {
   const int e = blockIdx.x;
   if (!terminated[e]) return;
   const int H = P.H, W = P.W, WW = (W + 63) >> 6;
@@ -155,7 +155,7 @@ __global__ void conditional_reset_kernel(gca_params P, gca_state S, gca_state SN
     if (S.steps_elapsed) S.steps_elapsed[e] = 0.0f;
     if (S.reward_accumulated) S.reward_accumulated[e] = 0.0f;
     if (reward) reward[e] = snap_reward[e];
-    terminated[e] = 0;
+    if (clear_flag) terminated[e] = 0;
   }
 }
 
@@ -321,7 +321,13 @@ cudaError_t launch_reward_done(const gca_params& p, const gca_state& s, float* r
 }
 cudaError_t launch_conditional_reset(const gca_params& p, const gca_state& s, const gca_state& snap,
                                      const float* snap_reward, float* reward, uint8_t* terminated, cudaStream_t st) {
-  conditional_reset_kernel<<<s.N, 256, 0, st>>>(p, s, snap, snap_reward, reward, terminated);
+  conditional_reset_kernel<<<s.N, 256, 0, st>>>(p, s, snap, snap_reward, reward, terminated, 1);
+  return cudaGetLastError();
+}
+// fused auto-reset of the tiled path: same restore, but `terminated` keeps the transition's done flag
+cudaError_t launch_auto_reset(const gca_params& p, const gca_state& s, const gca_state& snap, const float* snap_reward,
+                              float* reward, const uint8_t* terminated, cudaStream_t st) {
+  conditional_reset_kernel<<<s.N, 256, 0, st>>>(p, s, snap, snap_reward, reward, const_cast<uint8_t*>(terminated), 0);
   return cudaGetLastError();
 }
 cudaError_t launch_render(const gca_params& p, int N, const uint8_t* cell, const uint64_t* doused,

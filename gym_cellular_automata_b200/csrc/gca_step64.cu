@@ -361,7 +361,10 @@ __device__ __forceinline__ void front_masks(unsigned long long t0, unsigned long
   fr1 = t1 & (fh0 | fh1 | shfl64_down1(fh0, lane));
 }
 
-__global__ void __launch_bounds__(S64_WARPS * 32, 7)
+#ifndef S64_MINB
+#define S64_MINB 7
+#endif
+__global__ void __launch_bounds__(S64_WARPS * 32, S64_MINB)
 env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gca_state S,
                   const int32_t* __restrict__ actions, const __grid_constant__ gca_step_out O,
                   const __grid_constant__ gca_inject J, const __grid_constant__ gca_state SNAP,

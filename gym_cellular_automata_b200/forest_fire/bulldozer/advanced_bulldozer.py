@@ -110,7 +110,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                  middle_fire: bool = False, enable_extensions: bool = False, *, device="cuda", substeps: int = 1,
                  rng_mode: str = "legacy", seed: Optional[int] = None, hidden: str = "reference",
                  obs_mode: str = "rgb_f32", auto_reset: bool = False, ca_p_tree: float = 0.0,
-                 p_wind_change: float = 0.06, collect_stats: bool = False, **kwargs):
+                 p_wind_change: float = 0.06, collect_stats: bool = False, use_tma: bool = True, **kwargs):
         super().__init__(nrows, ncols, **kwargs)
         if not torch.cuda.is_available():
             raise _lib.GcaError("AdvancedForestFireBulldozerEnv needs a CUDA device (sm_100a); there is no CPU path")
@@ -170,6 +170,8 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         self._t_act_move = float(self._params.t_move[0])
         self._t_act_shoot = float(self._params.t_shoot[0])
         self._flags = 0 if use_hidden else _lib.FLAG_NO_HIDDEN
+        if not use_tma:
+            self._flags |= _lib.FLAG_NO_TMA
 
         self._set_spaces()
         self.ca = PartiallyObservableForestFireCUDA(nrows, self._empty, self._tree, self._fire, params=self._params,

@@ -76,10 +76,13 @@ class PackedState:
         self.is_night = torch.zeros(N, dtype=torch.int32, device=d)
         self.steps_elapsed = torch.zeros(N, dtype=torch.float32, device=d)
         self.reward_accumulated = torch.zeros(N, dtype=torch.float32, device=d)
+        tiled = not (H == 64 and W == 64)
+        self.scratch_cell = torch.zeros((N, H, W), dtype=torch.uint8, device=d) if tiled else None
+        self.scratch_u32 = torch.zeros((N, 14), dtype=torch.int32, device=d) if tiled else None
         self._c = None
 
     _FIELDS = ("cell", "death", "hidden", "doused", "pslope", "row_min", "tick", "key", "wind_index", "position",
-               "time", "time_step", "is_night", "steps_elapsed", "reward_accumulated")
+               "time", "time_step", "is_night", "steps_elapsed", "reward_accumulated", "scratch_cell", "scratch_u32")
 
     def cstruct(self) -> GcaState:
         if self._c is None:
@@ -99,7 +102,7 @@ class PackedState:
             t = getattr(self, f)
             if t is None:
                 setattr(o, f, None)
-            elif share_static and f in ("hidden", "pslope"):
+            elif share_static and f in ("hidden", "pslope", "scratch_cell", "scratch_u32"):
                 setattr(o, f, t)
             else:
                 setattr(o, f, t.clone())
@@ -109,7 +112,7 @@ class PackedState:
     def copy_from(self, other: "PackedState") -> None:
         for f in self._FIELDS:
             t, s = getattr(self, f), getattr(other, f)
-            if t is not None and s is not None and t.data_ptr() != s.data_ptr():
+            if t is not None and s is not None and t.data_ptr() != s.data_ptr() and not f.startswith("scratch"):
                 t.copy_(s)
 
     # ---- reference layout <-> packed ------------------------------------------------------------

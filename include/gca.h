@@ -50,6 +50,7 @@ typedef enum gca_status {
 #define GCA_FLAG_AUTO_RESET 1u  /* fuse conditional_reset for terminated envs into the step */
 #define GCA_FLAG_NO_HIDDEN 2u   /* hidden layers off: veg = den = 3, slope factor 1 (pslope may be NULL) */
 #define GCA_FLAG_CA_ONLY 4u     /* run only the CA sub-steps (no clock/move/douse/reward bookkeeping) */
+#define GCA_FLAG_NO_TMA 8u      /* tiled path: stage tiles with plain loads instead of TMA */
 
 /* Constants of one environment family (host POD, passed to kernels by value). */
 typedef struct gca_params {
@@ -82,7 +83,7 @@ typedef struct gca_params {
  *   pslope  f32 [N][H][W][8] exp(f32(0.078) * slope) for the 8 neighbours in 3x3 row-major order,
  *                           centre skipped; NULL = all 1.0
  *   row_min u32 [N][H]      earliest burn-out tick among the fire cells of a row (0xFFFFFFFF: none);
- *                           maintained by the 64x64 kernel only
+ *                           maintained and needed by the 64x64 kernel only
  *   tick    u32 [N]         CA sub-steps executed since the env was (re)set
  */
 typedef struct gca_state {
@@ -103,6 +104,9 @@ typedef struct gca_state {
   int32_t* is_night;    /* [N] */
   float* steps_elapsed;       /* [N] info bookkeeping (advanced_bulldozer.py:390-391) */
   float* reward_accumulated;  /* [N] */
+  /* scratch of the tiled path (grids other than 64x64); may be NULL for 64x64 */
+  uint8_t* scratch_cell;      /* [N][H][W] second grid buffer (tiles read one, write the other) */
+  uint32_t* scratch_u32;      /* [N][14]: per-env sub-step key schedule (12) + tree/fire counts (2) */
 } gca_state;
 
 /* Per-step outputs (device). Any pointer may be NULL to skip that output. */

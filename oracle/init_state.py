@@ -113,7 +113,7 @@ def get_slope(altitude):
 
 
 def initial_state(nrows, ncols, num_envs, seed=0, jax_seed=1, use_hidden=True, mode=prng.LEGACY,
-                  p_tree=0.90, p_empty=0.10, middle_fire=False, hidden="reference"):
+                  p_tree=0.90, p_empty=0.10, middle_fire=False, hidden="reference", slope_fn=None):
     """Initial (state, info) in the reference's pytree layout (advanced_bulldozer.py:650-743,
     401-420), NumPy arrays with the reference's dtypes.
 
@@ -136,7 +136,9 @@ def initial_state(nrows, ncols, num_envs, seed=0, jax_seed=1, use_hidden=True, m
         density = np.full((num_envs, nrows, ncols), 3, dtype=int)
         vegetation = np.full((num_envs, nrows, ncols), 3, dtype=int)
         altitude = np.zeros((num_envs, nrows, ncols))
-    slope = get_slope(np.asarray(altitude, dtype=np.float64)).astype(F32)
+    # slope_fn: tests of very large grids pass a vectorised equivalent of get_slope (checked against
+    # this literal one on small grids) because the per-cell Python loop is O(N H W)
+    slope = (slope_fn or get_slope)(np.asarray(altitude, dtype=np.float64)).astype(F32)
     # grid: iid empty/tree, two fire seeds (:650-688)
     grid = gen.choice(np.array([EMPTY, TREE, FIRE]), size=(num_envs, nrows, ncols),
                       p=[p_empty, p_tree, 0.0]).astype(F32)

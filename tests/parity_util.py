@@ -22,18 +22,30 @@ MODES = {"legacy": prng.LEGACY, "partitionable": prng.PARTITIONABLE}
 
 
 def make_pair(N=8, size=64, K=1, mode="legacy", use_hidden=True, seed=0, hidden="reference", p_tree=0.0,
-              speed_mult=4.0, jax_seed=1, collect_stats=True, obs_mode="none", enable_extensions=False):
-    state, info = oinit.initial_state(size, size, N, seed=seed, jax_seed=jax_seed, use_hidden=use_hidden,
-                                      mode=MODES[mode], hidden=hidden)
-    E = ax.EnvConstants(size, size, speed_move=0.12 * speed_mult, speed_act=0.03 * speed_mult, p_tree_ca=p_tree)
+              speed_mult=4.0, jax_seed=1, collect_stats=True, obs_mode="none", enable_extensions=False,
+              ncols=None, scatter_fire=0.0, use_tma=True, fast_slope=False):
+    nrows, ncols = size, (ncols or size)
+    slope_fn = None
+    if fast_slope:
+        from gym_cellular_automata_b200.forest_fire.bulldozer.utils.init_utils import get_slope as slope_fn
+    state, info = oinit.initial_state(nrows, ncols, N, seed=seed, jax_seed=jax_seed, use_hidden=use_hidden,
+                                      mode=MODES[mode], hidden=hidden, slope_fn=slope_fn)
+    if scatter_fire > 0:
+        # richer start than the two seed cells: random burning cells with random remaining ages
+        rs = np.random.default_rng(seed + 1000)
+        ctx = state["per_env_context"]
+        m = rs.random(ctx["true_grid"].shape) < scatter_fire
+        ctx["true_grid"][m] = 2.0
+        ctx["fire_age"][m] = rs.integers(1, 40, size=int(m.sum())).astype(np.float32)
+    E = ax.EnvConstants(nrows, ncols, speed_move=0.12 * speed_mult, speed_act=0.03 * speed_mult, p_tree_ca=p_tree)
     winds = oinit.get_winds()
     state["shared_context"] = E.shared_context(winds)
     co = COracle(E, winds, K=K, mode=MODES[mode])
-    env = AdvancedForestFireBulldozerEnv(size, size, key=jax_seed, num_envs=N, speed_move=0.12 * speed_mult,
+    env = AdvancedForestFireBulldozerEnv(nrows, ncols, key=jax_seed, num_envs=N, speed_move=0.12 * speed_mult,
                                          speed_act=0.03 * speed_mult, use_hidden=use_hidden, substeps=K,
                                          rng_mode=mode, seed=seed, hidden="random" if use_hidden else "reference",
                                          obs_mode=obs_mode, ca_p_tree=p_tree, collect_stats=collect_stats,
-                                         enable_extensions=enable_extensions)
+                                         enable_extensions=enable_extensions, use_tma=use_tma)
     sync(env, state, as_snapshot=True)
     return env, co, E, state, info
 

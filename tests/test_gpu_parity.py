@@ -95,3 +95,34 @@ def test_dousing_heavy(cuda_device):
     sync(env, state, as_snapshot=True)
     nbad, reports, stats = lockstep(env, co, state, 300, np.random.default_rng(4), shoot_p=1.0)
     assert nbad == 0, _fmt(reports)
+
+
+@pytest.mark.parametrize("nrows,ncols,K,tma,N", [(32, 32, 2, True, 4), (128, 128, 1, True, 2), (256, 256, 1, True, 2),
+                                                 (256, 256, 2, False, 1), (72, 40, 1, True, 3), (96, 80, 3, True, 2)])
+def test_tiled_parity(cuda_device, nrows, ncols, K, tma, N):
+    """Grids other than 64x64 go through the tiled kernel (TMA staging when W % 16 == 0, plain
+    loads otherwise / on request): same bit-exact contract against the oracle."""
+    from parity_util import make_pair, lockstep
+    env, co, E, state, info = make_pair(N=N, size=nrows, ncols=ncols, K=K, mode="legacy", use_hidden=True, seed=5,
+                                        hidden="random", scatter_fire=0.01, use_tma=tma, fast_slope=True)
+    nbad, reports, stats = lockstep(env, co, state, 40, np.random.default_rng(6))
+    assert nbad == 0, _fmt(reports)
+    assert stats[1] > 0 and stats[2] > 0 and stats[3] > 0
+
+
+def test_tiled_partitionable_hidden_off(cuda_device):
+    from parity_util import make_pair, lockstep
+    env, co, E, state, info = make_pair(N=2, size=128, K=2, mode="partitionable", use_hidden=False, seed=8,
+                                        scatter_fire=0.01, p_tree=0.001)
+    nbad, reports, stats = lockstep(env, co, state, 30, np.random.default_rng(7))
+    assert nbad == 0, _fmt(reports)
+
+
+def test_large_single_grid_4096(cuda_device):
+    """BASELINE config 4: one 4096x4096 grid (R = 10, 21x21 heat window), two env steps."""
+    from parity_util import make_pair, lockstep
+    env, co, E, state, info = make_pair(N=1, size=4096, K=1, mode="legacy", use_hidden=True, seed=2, hidden="random",
+                                        scatter_fire=0.002, fast_slope=True)
+    nbad, reports, stats = lockstep(env, co, state, 2, np.random.default_rng(1))
+    assert nbad == 0, _fmt(reports)
+    assert stats[1] > 1000
