@@ -18,6 +18,7 @@
 // Reference lines as in gca_step64.cu.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cstdlib>
 
 #include "gca_common.cuh"
 
@@ -25,7 +26,9 @@ namespace gca {
 
 constexpr int T_TH = 32, T_TW = 64, T_THREADS = 256;
 constexpr int T_MAXR = GCA_MAX_R;
-constexpr int T_PITCH_MAX = 96;                       // 64 + 2*10 rounded up to a multiple of 16
+constexpr int T_HC = 16;                              // column halo: TMA needs the box start 16-byte aligned,
+                                                      // so the left halo is always 16 columns (>= R)
+constexpr int T_PITCH_MAX = T_TW + 2 * T_HC;          // 96
 constexpr int T_ROWS_MAX = T_TH + 2 * T_MAXR;         // 52
 #define T_LO 0.9998779296875f  /* 1 - 2^-13: (2R+1)^2 <= 441 terms -> |err| <= 441 u |sum| */
 #define T_HI 1.0001220703125f  /* 1 + 2^-13 */
@@ -129,10 +132,11 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       const uint32_t bytes = (uint32_t)(rows * pitch);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-      // box (pitch, rows, 1) at (c0 - R, r0 - R, e); negative / beyond-edge coordinates are zero-filled
+      // box (pitch, rows, 1) at (c0 - 16, r0 - R, e); negative / beyond-edge coordinates are zero-filled.
+      // The innermost start coordinate must keep the global address 16-byte aligned.
       asm volatile(
           "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-          ::"r"(smem_u32(sm.tile)), "l"(&tmap), "r"(c0 - R), "r"(r0 - R), "r"(e), "r"(bar)
+          ::"r"(smem_u32(sm.tile)), "l"(&tmap), "r"(c0 - T_HC), "r"(r0 - R), "r"(e), "r"(bar)
           : "memory");
     }
     __syncthreads();
@@ -150,7 +154,7 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
   } else {
     for (int i = tid; i < rows * pitch; i += T_THREADS) {
       const int lr = i / pitch, lc = i % pitch;
-      const int gr = r0 - R + lr, gc = c0 - R + lc;
+      const int gr = r0 - R + lr, gc = c0 - T_HC + lc;
       uint8_t v = 0;
       if (gr >= 0 && gr < H && gc >= 0 && gc < W) v = cell_in[env_off + (size_t)gr * W + gc];
       sm.tile[i] = v;
@@ -168,7 +172,7 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
   for (int k = 0; k < T_TH / 4; ++k) {
     const int lr = rg + 4 * k;
     const int gr = r0 + lr, gc = c0 + lc;
-    const uint8_t* ctr = sm.tile + (lr + R) * pitch + (lc + R);
+    const uint8_t* ctr = sm.tile + (lr + R) * pitch + (lc + T_HC);
     bool front = false;
     if (gr < H && gc < W && ctr[0] == 1) {
       front = ctr[-pitch - 1] == 2 || ctr[-pitch] == 2 || ctr[-pitch + 1] == 2 || ctr[-1] == 2 || ctr[1] == 2 ||
@@ -194,7 +198,7 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
     const int lr = sm.list[i] >> 6, lcc = sm.list[i] & 63;
     const int gr = r0 + lr, gc = c0 + lcc;
     const size_t gcell = (size_t)gr * W + gc;
-    const uint8_t* ctr = sm.tile + (lr + R) * pitch + (lcc + R);
+    const uint8_t* ctr = sm.tile + (lr + R) * pitch + (lcc + T_HC);
     // heat: any summation order is inside the enclosure
     float Hf = 0.0f;
     for (int di = 0; di < win; ++di) {
@@ -267,7 +271,7 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
     const int gr = r0 + lr, gc = c0 + lc;
     if (gr >= H || gc >= W) continue;
     const size_t gcell = (size_t)gr * W + gc;
-    const int old = sm.tile[(lr + R) * pitch + (lc + R)];
+    const int old = sm.tile[(lr + R) * pitch + (lc + T_HC)];
     int nw = old;
     if (old == 1 && sm.ignite[lr * T_TW + lc]) {
       nw = 2;
@@ -393,7 +397,7 @@ cudaError_t launch_tiled_env_step(const gca_params& p, const gca_state& s, const
                                   const gca_step_out& out, const gca_inject& inj, uint32_t flags, uint8_t* scratch_cell,
                                   uint32_t* scratch_sched, int32_t* scratch_counts, int use_tma, cudaStream_t st) {
   const int N = s.N, H = p.H, W = p.W, R = p.R;
-  const int pitch = ((T_TW + 2 * R) + 15) & ~15;
+  const int pitch = T_PITCH_MAX;
   const int rows = T_TH + 2 * R;
   dim3 grid((W + T_TW - 1) / T_TW, (H + T_TH - 1) / T_TH, N);
   uint8_t* cur = s.cell;

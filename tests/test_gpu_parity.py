@@ -126,3 +126,180 @@ def test_large_single_grid_4096(cuda_device):
     nbad, reports, stats = lockstep(env, co, state, 2, np.random.default_rng(1))
     assert nbad == 0, _fmt(reports)
     assert stats[1] > 1000
+
+
+# ---------------------------------------------------------------------------------------------
+# observation, reset, API surface
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("enable_ext", [False, True])
+def test_observation_parity(cuda_device, enable_ext):
+    """RGB observation of stateless_step == oracle build_observation (new grid / position, old
+    dousing marks and day/night, extension-channel quirk), float32, bit for bit."""
+    from oracle import alexandridis as ax
+    from parity_util import make_pair, random_actions
+    N = 6
+    env, co, E, state, info = make_pair(N=N, K=1, mode="legacy", use_hidden=True, seed=4, obs_mode="rgb_f32",
+                                        enable_extensions=enable_ext)
+    rng = np.random.default_rng(12)
+    # make the day/night flip and some dousing visible
+    state["per_env_context"]["time_step"][:] = np.array([398, 399, 400, 1, 799, 5], dtype=np.int32)
+    state["per_env_context"]["is_night"][:] = np.array([0, 0, 1, 1, 1, 0], dtype=np.int32)
+    state["per_env_context"]["dousing_count"][:, 5:9, 50:60] = 1
+    state["per_env_context"]["true_grid"][3, 0, :] = 0.0  # first row empty: exercises the channel-index quirk
+    from parity_util import sync
+    sync(env, state, as_snapshot=True)
+    o_info = {k: np.zeros(N, np.float32) for k in ("steps_elapsed", "reward_accumulated")}
+    for step in range(12):
+        act = random_actions(rng, N)
+        rgb_o, state, reward, term, trunc, o_info = ax.stateless_step(E, act, state, o_info, K=1,
+                                                                      enable_extensions=enable_ext)
+        obs, r, t, tr, inf = env.stateless_step(act)
+        rgb = obs[0].cpu().numpy()
+        assert rgb.dtype == np.float32 and rgb.shape == (N, 64, 64, 3)
+        assert np.array_equal(rgb, rgb_o), f"step {step}: {np.argwhere(rgb != rgb_o)[:4]}"
+        assert np.array_equal(r.cpu().numpy(), reward)
+        assert np.array_equal(inf["steps_elapsed"].cpu().numpy(), o_info["steps_elapsed"])
+        assert np.array_equal(inf["reward_accumulated"].cpu().numpy(), o_info["reward_accumulated"])
+        ctx = obs[1]["per_env_context"]
+        assert np.array_equal(ctx["true_grid"].cpu().numpy(), state["per_env_context"]["true_grid"])
+        assert np.array_equal(ctx["fire_age"].cpu().numpy(), state["per_env_context"]["fire_age"])
+        assert np.array_equal(ctx["is_night"].cpu().numpy(), state["per_env_context"]["is_night"])
+
+
+def test_conditional_reset_parity(cuda_device):
+    """stateless_step + conditional_reset against the oracle across episode ends: restored grid /
+    keys / position / clock, kept time_step / is_night, zeroed info counters, recomputed reward,
+    cleared terminated, re-rendered observation of the reset envs."""
+    import copy
+    from oracle import alexandridis as ax
+    from parity_util import make_pair, random_actions, sync
+    N = 6
+    env, co, E, state, info = make_pair(N=N, K=4, mode="legacy", use_hidden=True, seed=9, obs_mode="rgb_f32")
+    # short episodes: fires about to burn out in some envs
+    ctx = state["per_env_context"]
+    ctx["fire_age"][ctx["true_grid"] == 2] = np.float32(3)
+    ctx["true_grid"][0:3, 40:56, 8:24] = np.where(ctx["true_grid"][0:3, 40:56, 8:24] == 1, 0, ctx["true_grid"][0:3, 40:56, 8:24])
+    sync(env, state, as_snapshot=True)
+    initial = copy.deepcopy(state)
+    o_info = {k: np.zeros(N, np.float32) for k in ("steps_elapsed", "reward_accumulated")}
+    rng = np.random.default_rng(3)
+    n_resets = 0
+    for step in range(10):
+        act = random_actions(rng, N)
+        rgb_o, state, reward, term, trunc, o_info = ax.stateless_step(E, act, state, o_info, K=4)
+        tup = env.stateless_step(act)
+        assert np.array_equal(tup[2].cpu().numpy(), term), step
+        n_resets += int(term.sum())
+        rgb_o, state, reward, term2, o_info = ax.conditional_reset(E, rgb_o, state, reward, term, o_info, act, initial)
+        obs, r, t, tr, inf = env.conditional_reset(tup, act)
+        assert not t.any() and not term2.any()
+        assert np.array_equal(r.cpu().numpy(), reward), step
+        assert np.array_equal(obs[0].cpu().numpy(), rgb_o), step
+        c = obs[1]["per_env_context"]
+        for k in ("true_grid", "fire_age", "dousing_count", "wind_index", "key", "is_night", "time_step"):
+            assert np.array_equal(c[k].cpu().numpy(), state["per_env_context"][k]), (step, k)
+        assert np.array_equal(obs[1]["position"].cpu().numpy(), state["position"])
+        assert np.array_equal(obs[1]["time"].cpu().numpy(), state["time"])
+        assert np.array_equal(inf["steps_elapsed"].cpu().numpy(), o_info["steps_elapsed"])
+    assert n_resets > 0, "no episode ended: the reset path was not exercised"
+
+
+def test_fused_auto_reset_matches_two_call_path(cuda_device):
+    """GCA_FLAG_AUTO_RESET inside the step kernel == stateless_step followed by conditional_reset."""
+    from parity_util import make_pair, random_actions, sync, read_cuda_state
+    N = 8
+    envs = []
+    for fused in (False, True):
+        env, co, E, state, info = make_pair(N=N, K=4, mode="legacy", use_hidden=True, seed=9)
+        ctx = state["per_env_context"]
+        ctx["fire_age"][ctx["true_grid"] == 2] = np.float32(2)
+        sync(env, state, as_snapshot=True)
+        envs.append(env)
+    rng = np.random.default_rng(5)
+    seen_done = 0
+    for step in range(12):
+        act = random_actions(rng, N)
+        a = torch.as_tensor(act, device="cuda")
+        tup = envs[0].stateless_step(act)
+        seen_done += int(tup[2].sum())
+        tup = envs[0].conditional_reset(tup, act)
+        out = envs[1].step_device(a, auto_reset=True)
+        s0, s1 = read_cuda_state(envs[0]), read_cuda_state(envs[1])
+        for k in s0:
+            assert np.array_equal(s0[k], s1[k]), (step, k)
+        assert np.array_equal(tup[1].cpu().numpy(), out.reward.cpu().numpy())
+    assert seen_done > 0
+
+
+def test_operator_level_api(cuda_device):
+    """The reference's operator call signatures (batched): CA update, RepeatCA clock, Move, Modify,
+    MoveModify, MDP.update."""
+    from oracle import alexandridis as ax, init_state as oinit, prng
+    from parity_util import make_pair, random_actions
+    N = 4
+    env, co, E, state, info = make_pair(N=N, K=1, mode="legacy", use_hidden=True, seed=6)
+    ctx = {k: v.copy() for k, v in state["per_env_context"].items()}
+    shared = state["shared_context"]
+    # CA operator
+    g_o, c_o = ax.ca_update(E.ca, ctx["true_grid"], ctx, shared, prng.LEGACY)
+    g, c, sh = env.ca(ctx["true_grid"], None, ctx, shared)
+    assert np.array_equal(g.cpu().numpy(), g_o)
+    assert np.array_equal(c["fire_age"].cpu().numpy(), c_o["fire_age"])
+    assert np.array_equal(c["key"].cpu().numpy(), c_o["key"])
+    assert np.array_equal(c["wind_index"].cpu().numpy(), c_o["wind_index"])
+    # Move / Modify
+    rng = np.random.default_rng(0)
+    pos = np.stack([rng.integers(0, 64, 50), rng.integers(0, 64, 50)], 1).astype(np.int32)
+    pos[:8] = [[0, 0], [0, 63], [63, 0], [63, 63], [0, 5], [5, 0], [63, 7], [7, 63]]
+    for a0 in range(9):
+        _, new = env.move(np.zeros((50, 64, 64), np.float32), np.full(50, a0), pos)
+        assert np.array_equal(new.cpu().numpy(), ax.move(pos, np.full(50, a0), 64, 64)), a0
+    dc = np.zeros((N, 64, 64), np.int32)
+    p4 = pos[:N]
+    _, _, pe = env.modify(np.zeros((N, 64, 64), np.float32), np.array([1, 0, 1, 1]), p4, {"dousing_count": dc})
+    assert np.array_equal(pe["dousing_count"].cpu().numpy(), ax.modify(dc, np.array([1, 0, 1, 1]), p4))
+    # RepeatCA clock
+    acts = random_actions(rng, N)
+    a0 = torch.as_tensor(acts[:, 0], device="cuda")
+    a1 = torch.as_tensor(acts[:, 1], device="cuda")
+    t_in = np.array([0.0, 0.5, 0.95, 0.999], dtype=np.float32)
+    g2, (c2, frac) = env.repeater(ctx["true_grid"], (a0, a1), ctx, shared, torch.as_tensor(t_in, device="cuda"))
+    t_o = (t_in + ((E.movement_timings[acts[:, 0]] + E.shooting_timings[acts[:, 1]]) + E.t_any_f32)).astype(np.float32)
+    assert np.array_equal(frac.cpu().numpy(), np.modf(t_o)[0].astype(np.float32))
+    assert np.array_equal(g2.cpu().numpy(), g_o)
+    # MDP.update
+    a4 = ax.full_actions(acts)
+    (rgb_o, grid_o), (nctx, npos, ntime) = ax.mdp_update(E, ctx["true_grid"], a4, ctx, shared, state["position"],
+                                                         state["time"], K=1, render_obs=False)
+    (rgb, grid, _), (pe, position, time) = env.MDP(ctx["true_grid"], a4, ctx, shared, state["position"], state["time"])
+    assert np.array_equal(grid.cpu().numpy(), grid_o)
+    assert np.array_equal(position.cpu().numpy(), npos) and np.array_equal(time.cpu().numpy(), ntime)
+    assert np.array_equal(pe["dousing_count"].cpu().numpy(), nctx["dousing_count"])
+
+
+def test_env_api_surface(cuda_device):
+    """reset / spaces / info keys a jax_ppo-style caller touches (reference agents/jax_ppo.py:708-735,790-791)."""
+    from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv
+    env = AdvancedForestFireBulldozerEnv(64, 64, key=1, num_envs=4, seed=0, enable_extensions=True)
+    obs, info = env.reset()
+    rgb, context = obs
+    assert rgb.shape == (4, 64, 64, 3) and rgb.dtype == torch.float32
+    assert set(info) == {"TimeLimit.truncated", "terminated", "steps_elapsed", "reward_accumulated", "reward"}
+    assert env.action_space.nvec[0].tolist() == [9, 2]
+    assert env.total_action_space.shape[-1] == 3 and env.extension_choices == [(2, 1)]
+    grid_space, context_space = env.observation_space
+    assert grid_space.shape == (4, 64, 64, 3)
+    sample = env.observation_space.sample()
+    assert sample[0].shape == (4, 64, 64, 3) and "per_env_context" in sample[1]
+    for k in env.per_env_context_keys:
+        assert k in context["per_env_context"], k
+    a = env.total_action_space.sample()
+    obs, reward, terminated, truncated, info = env.stateless_step(a, obs, info)
+    assert reward.shape == (4,) and terminated.dtype == torch.bool and not truncated.any()
+    assert float(info["steps_elapsed"][0]) == 1.0
+    c = env.count_cells()
+    assert int(c[0] + c[1] + c[2]) == 4 * 64 * 64
+    # initial fire seeds and bulldozer position (advanced_bulldozer.py:673-700)
+    g = context["per_env_context"]["true_grid"].cpu().numpy()
+    assert (g[:, 48, 16] == 2).all() and (g[:, 48, 15] == 2).all() and (g == 2).sum() == 8
+    assert context["position"].cpu().numpy().tolist() == [[9, 54]] * 4
