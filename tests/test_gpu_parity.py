@@ -293,13 +293,15 @@ def test_env_api_surface(cuda_device):
     assert sample[0].shape == (4, 64, 64, 3) and "per_env_context" in sample[1]
     for k in env.per_env_context_keys:
         assert k in context["per_env_context"], k
+    # initial fire seeds and bulldozer position (advanced_bulldozer.py:673-700)
+    g = context["per_env_context"]["true_grid"].cpu().numpy()
+    assert (g[:, 48, 16] == 2).all() and (g[:, 48, 15] == 2).all() and (g == 2).sum() == 8
+    assert context["position"].cpu().numpy().tolist() == [[9, 54]] * 4
     a = env.total_action_space.sample()
     obs, reward, terminated, truncated, info = env.stateless_step(a, obs, info)
     assert reward.shape == (4,) and terminated.dtype == torch.bool and not truncated.any()
     assert float(info["steps_elapsed"][0]) == 1.0
     c = env.count_cells()
     assert int(c[0] + c[1] + c[2]) == 4 * 64 * 64
-    # initial fire seeds and bulldozer position (advanced_bulldozer.py:673-700)
-    g = context["per_env_context"]["true_grid"].cpu().numpy()
-    assert (g[:, 48, 16] == 2).all() and (g[:, 48, 15] == 2).all() and (g == 2).sum() == 8
-    assert context["position"].cpu().numpy().tolist() == [[9, 54]] * 4
+    with pytest.raises(RuntimeError):  # the lazily unpacked arrays of an OLD observation are refused
+        context["per_env_context"]["fire_age"]
