@@ -8,6 +8,7 @@ needs the built library and a GPU."""
 from .ca_env import CAEnv
 from .grid_space import GridSpace
 from .operator import Operator
+from . import spaces
 
 __version__ = "0.1.0"
-__all__ = ["CAEnv", "GridSpace", "Operator"]
+__all__ = ["CAEnv", "GridSpace", "Operator", "spaces"]

@@ -110,7 +110,8 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                  middle_fire: bool = False, enable_extensions: bool = False, *, device="cuda", substeps: int = 1,
                  rng_mode: str = "legacy", seed: Optional[int] = None, hidden: str = "reference",
                  obs_mode: str = "rgb_f32", auto_reset: bool = False, ca_p_tree: float = 0.0,
-                 p_wind_change: float = 0.06, collect_stats: bool = False, use_tma: bool = True, **kwargs):
+                 p_wind_change: float = 0.06, collect_stats: bool = False, use_tma: bool = True,
+                 env_offset: int = 0, total_envs: Optional[int] = None, **kwargs):
         super().__init__(nrows, ncols, **kwargs)
         if not torch.cuda.is_available():
             raise _lib.GcaError("AdvancedForestFireBulldozerEnv needs a CUDA device (sm_100a); there is no CPU path")
@@ -126,6 +127,11 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         self.obs_mode = obs_mode
         self.auto_reset = bool(auto_reset)
         self.num_envs = int(num_envs)
+        # multi-GPU sharding: this instance holds envs [env_offset, env_offset + num_envs) of a batch of
+        # total_envs; per-env keys come from ONE split over the whole batch, so they do not depend on
+        # how many ranks share it
+        self.env_offset = int(env_offset)
+        self.total_envs = int(total_envs) if total_envs is not None else self.env_offset + self.num_envs
         self.title = "ForestFireBulldozer" + str(nrows) + "x" + str(ncols)
         self._host_rng = np.random.RandomState(seed) if seed is not None else np.random
         self.np_random = np.random.default_rng(seed)
@@ -293,7 +299,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
             self._pos_bull = [(int(H * 0.15), int(W * 0.85)) for _ in range(N)]
         elif isinstance(self._pos_bull[0], (int, np.integer)):
             self._pos_bull = [tuple(self._pos_bull)] * N
-        keys = split_keys(self.starting_key, N, self.rng_mode)
+        keys = split_keys(self.starting_key, self.total_envs, self.rng_mode)[self.env_offset:self.env_offset + N]
         wind_index = (self.np_random.integers(0, 8, size=N) if self.use_hidden else np.zeros(N)).astype(np.int32)
         per_env = {
             "wind_index": wind_index,

@@ -305,3 +305,52 @@ def test_env_api_surface(cuda_device):
     assert int(c[0] + c[1] + c[2]) == 4 * 64 * 64
     with pytest.raises(RuntimeError):  # the lazily unpacked arrays of an OLD observation are refused
         context["per_env_context"]["fire_age"]
+
+
+def test_cuda_reproduces_golden_fixtures(cuda_device):
+    """Committed fixtures (tests/golden/make_golden.py, oracle-generated): same seeds -> same final state."""
+    import importlib.util
+    import os
+    from oracle import alexandridis as ax, init_state as oinit
+    from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    gold = np.load(os.path.join(here, "golden", "env_step_golden.npz"))
+    for name, case in mg.CASES.items():
+        mode = "legacy" if case["mode"] == 0 else "partitionable"
+        state, info = oinit.initial_state(64, 64, case["N"], seed=case["seed"], jax_seed=1,
+                                          use_hidden=case["use_hidden"], mode=case["mode"])
+        env = AdvancedForestFireBulldozerEnv(64, 64, key=1, num_envs=case["N"], speed_move=0.48, speed_act=0.12,
+                                             use_hidden=case["use_hidden"], substeps=case["K"], rng_mode=mode,
+                                             seed=0, hidden="random", obs_mode="none")
+        env.set_state(state["per_env_context"], state["position"], state["time"], as_snapshot=True)
+        rewards = []
+        for s in range(case["steps"]):
+            out = env.step_device(torch.as_tensor(mg.actions_for(case, s), device="cuda"))
+            rewards.append(out.step_reward.cpu().numpy().copy())
+        ref = env._state.unpack_to_reference(env._params)
+        assert np.array_equal(ref["true_grid"].cpu().numpy().astype(np.uint8), gold[f"{name}/grid"]), name
+        assert np.array_equal(ref["fire_age"].cpu().numpy().astype(np.uint16), gold[f"{name}/fire_age"]), name
+        assert np.array_equal(np.packbits(ref["dousing_count"].cpu().numpy().astype(np.uint8), axis=-1),
+                              gold[f"{name}/dousing"]), name
+        assert np.array_equal(env._state.key.cpu().numpy(), gold[f"{name}/key"]), name
+        assert np.array_equal(env._state.position.cpu().numpy(), gold[f"{name}/position"]), name
+        assert np.array_equal(env._state.time.cpu().numpy(), gold[f"{name}/time"]), name
+        assert np.array_equal(np.stack(rewards), gold[f"{name}/rewards"]), name
+        assert np.array_equal(env._state.reward_accumulated.cpu().numpy(), gold[f"{name}/reward_accumulated"]), name
+
+
+def test_env_keys_do_not_depend_on_sharding(cuda_device):
+    from oracle import prng
+    from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv
+    kw = dict(use_hidden=False, obs_mode="none", seed=0)
+    whole = AdvancedForestFireBulldozerEnv(64, 64, key=7, num_envs=8, **kw)
+    whole.reset()
+    parts = [AdvancedForestFireBulldozerEnv(64, 64, key=7, num_envs=4, env_offset=o, total_envs=8, **kw) for o in (0, 4)]
+    for p in parts:
+        p.reset()
+    keys = torch.cat([p._state.key for p in parts]).cpu().numpy()
+    assert np.array_equal(whole._state.key.cpu().numpy(), keys)
+    assert np.array_equal(keys, prng.split(prng.key_from_seed(7), 8, prng.LEGACY))

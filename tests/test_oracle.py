@@ -1,0 +1,276 @@
+"""CPU tests of the ORACLE (test infrastructure): PRNG known-answer vectors, NumPy vs C restatement,
+rule-level checks mirroring the reference's own operator tests, golden fixtures."""
+import copy
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from oracle import alexandridis as ax
+from oracle import init_state as oinit
+from oracle import prng
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# ---- PRNG: Random123 KATs and public JAX values ------------------------------
+def test_threefry_random123_known_answers():
+    kat = [((0, 0), (0, 0), (0x6B200159, 0x99BA4EFE)),
+           ((0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0xFFFFFFFF), (0x1CB996FC, 0xBB002BE7)),
+           ((0x13198A2E, 0x03707344), (0x243F6A88, 0x85A308D3), (0xC4923A9C, 0x483DF7A0))]
+    for k, x, y in kat:
+        a, b = prng.threefry2x32(np.uint32(k[0]), np.uint32(k[1]), np.uint32(x[0]), np.uint32(x[1]))
+        assert (int(a), int(b)) == y
+
+
+def test_jax_documented_values_both_layouts():
+    k0 = prng.key_from_seed(0)
+    assert prng.split(k0, 2, prng.LEGACY).tolist() == [[4146024105, 967050713], [2718843009, 1272950319]]
+    assert int(prng.random_bits(k0, 1, prng.LEGACY)[0]) == 1797259609
+    assert prng.uniform(k0, 1, prng.LEGACY)[0] == np.float32(0.41845703)
+    assert prng.split(k0, 2, prng.PARTITIONABLE).tolist() == [[1797259609, 2579123966], [928981903, 3453687069]]
+
+
+@pytest.mark.parametrize("mode", [prng.LEGACY, prng.PARTITIONABLE])
+def test_lazy_element_equals_dense_stream(mode):
+    key = np.array([123, 456], np.uint32)
+    for n in (1, 2, 3, 9, 36864):
+        dense = prng.random_bits(key, n, mode)
+        assert np.array_equal(dense, prng.random_bits_at(key, np.arange(n), n, mode))
+
+
+def test_uniform_and_randint_construction():
+    bits = np.array([0, 511, 512, 0xFFFFFFFF], np.uint32)
+    u = prng.bits_to_uniform(bits)
+    assert u.tolist() == [0.0, 0.0, 2.0 ** -23, 1.0 - 2.0 ** -23]
+    assert prng.randint_params(144.0, 168.0) == (144, 24, 16)      # 64x64
+    assert prng.randint_params(576.0, 672.0) == (576, 96, 64)      # 256x256
+    assert prng.randint_params(9216.0, 10752.0) == (9216, 1536, 1024)
+    assert prng.randint_params(1, 8) == (1, 7, 4)
+    r = prng.randint(np.array([1, 2], np.uint32), 1000, 144.0, 168.0)
+    assert r.min() >= 144 and r.max() < 168 and r.dtype == np.int32
+
+
+# ---- constants (A0) ------------------------------------------------------------------------------------
+def test_ca_constants_table():
+    c = ax.CAConstants(64)
+    assert (c.initial_spread_time, c.radius, c.fire_age_min, c.fire_age_max) == (96, 4, 144.0, 168.0)
+    assert np.allclose(c.ring_weights, [4.3333e-3, 9.75e-4, 2.6e-4, 1.3e-4], rtol=1e-4)
+    assert abs(float(c.burn_kernel.sum(dtype=np.float64)) - 0.065) < 1e-7
+    assert np.isclose(c.dousing_weights[0, 0], 0.0588) and np.isclose(c.dousing_weights[2, 2], 0.504)
+    assert [ax.CAConstants(s).radius for s in (32, 256, 4096)] == [3, 6, 10]
+    E = ax.EnvConstants(64, 64, 0.48, 0.12)
+    t = (E.movement_timings[0] + E.shooting_timings[1]) + E.t_any_f32
+    assert abs(float(t) - 0.13120833) < 1e-7
+
+
+# ---- rule-level checks (the reference's test style: deterministic corner cases) -------------------------
+def _tiny_state(N=2, size=16, seed=0):
+    state, info = oinit.initial_state(size, size, N, seed=seed, use_hidden=True, hidden="random")
+    E = ax.EnvConstants(size, size)
+    state["shared_context"] = E.shared_context(oinit.get_winds())
+    return E, state, info
+
+
+def test_rule_injected_uniforms_extremes():
+    E, state, info = _tiny_state()
+    ctx = state["per_env_context"]
+    N, H, W = ctx["true_grid"].shape
+    zeros = {"u_burn": np.zeros((N, H, W, 3, 3), np.float32), "u_grow": np.ones((N, H, W), np.float32),
+             "age_new": np.full((N, H, W), 7, np.int32), "u_wind": np.ones(N, np.float32),
+             "wind_step": np.ones(N, np.int32)}
+    g, c, dbg = ax.ca_update(E.ca, ctx["true_grid"], ctx, state["shared_context"], inject=zeros, want_debug=True)
+    old = ctx["true_grid"]
+    pad = np.pad(old, ((0, 0), (1, 1), (1, 1)))
+    nb = np.zeros_like(old, dtype=bool)
+    pos_p = np.zeros_like(old, dtype=bool)
+    for i in range(3):
+        for j in range(3):
+            f = pad[:, i:i + H, j:j + W] == 2
+            nb |= f
+            pos_p |= f & (dbg["p"][..., i, j] > 0)
+    # u = 0: every tree with a burning neighbour whose probability is positive ignites, nothing else
+    assert np.array_equal(g == 2, ((old == 1) & pos_p) | ((old == 2) & (ctx["fire_age"] > 1)))
+    assert np.all(c["fire_age"][(g == 2) & (old == 1)] == 7)
+    assert np.array_equal(c["wind_index"], ctx["wind_index"])  # u_wind = 1 -> no wind change
+    ones = dict(zeros, u_burn=np.ones((N, H, W, 3, 3), np.float32))
+    g1, c1 = ax.ca_update(E.ca, old, ctx, state["shared_context"], inject=ones)
+    assert not ((g1 == 2) & (old == 1)).any()                     # u = 1: no ignition at all
+    assert np.array_equal(c1["fire_age"][old == 2], ctx["fire_age"][old == 2] - 1)
+
+
+def test_fire_burns_out_when_age_reaches_one():
+    E, state, info = _tiny_state()
+    ctx = state["per_env_context"]
+    ctx["fire_age"][ctx["true_grid"] == 2] = 1.0
+    inj = {"u_burn": np.ones(ctx["true_grid"].shape + (3, 3), np.float32)}
+    g, c = ax.ca_update(E.ca, ctx["true_grid"], ctx, state["shared_context"], inject=inj)
+    assert not (g == 2).any() and np.all(c["fire_age"][ctx["true_grid"] == 2] == 0)
+    assert ax.is_done(g).all() and np.all(ax.award(g) == 0)
+
+
+def _independent_new_position(action, position, nrows, ncols):
+    # independent boundary oracle, same idea as the reference's test_move_modify.py:132-170
+    r, c = position
+    dr = {0: -1, 1: -1, 2: -1, 3: 0, 4: 0, 5: 0, 6: 1, 7: 1, 8: 1}[action]
+    dc = {0: -1, 1: 0, 2: 1, 3: -1, 4: 0, 5: 1, 6: -1, 7: 0, 8: 1}[action]
+    nr, nc = r + dr, c + dc
+    if nr < 0 or nr >= nrows:
+        nr = r
+    if nc < 0 or nc >= ncols:
+        nc = c
+    return nr, nc
+
+
+def test_move_against_independent_oracle():
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        H, W = rng.integers(2, 9, 2)
+        pos = np.array([[rng.integers(0, H), rng.integers(0, W)]], dtype=np.int32)
+        a = int(rng.integers(0, 9))
+        got = ax.move(pos, np.array([a]), H, W)[0]
+        assert tuple(got) == _independent_new_position(a, tuple(pos[0]), H, W)
+
+
+def test_modify_clock_reward_daynight():
+    dc = np.zeros((2, 8, 8), np.int32)
+    out = ax.modify(dc, np.array([1, 0]), np.array([[3, 4], [1, 1]]))
+    assert out[0, 3, 4] == 1 and out.sum() == 1 and dc.sum() == 0
+    grid = np.zeros((1, 4, 4), np.float32)
+    grid[0, 0, :] = 1
+    grid[0, 1, 0] = 2
+    assert ax.award(grid)[0] == np.float32(-(np.float32(1) / (np.float32(5) + np.float32(1e-8))))
+    assert not ax.is_done(grid)[0] and ax.is_done(np.zeros((1, 4, 4), np.float32))[0]
+    E, state, info = _tiny_state(N=2)
+    state["per_env_context"]["time_step"][:] = [399, 7]
+    act = np.array([[4, 0, 0], [4, 1, 0]])
+    _, ns, _, _, _, ninfo = ax.stateless_step(E, act, state, info, render_obs=False)
+    assert ns["per_env_context"]["is_night"].tolist() == [1, 0]
+    assert ns["per_env_context"]["time_step"].tolist() == [400, 8]
+    assert ns["per_env_context"]["dousing_count"][1].sum() == 1 and ns["per_env_context"]["dousing_count"][0].sum() == 0
+    assert ninfo["steps_elapsed"].tolist() == [1.0, 1.0]
+    assert np.all((ns["time"] >= 0) & (ns["time"] < 1))
+
+
+def test_k_substeps_equals_k_single_updates():
+    # repeats semantics the JAX operator dropped but the NumPy RepeatCA has (reference test_repeat_ca.py:68-90)
+    E, state, info = _tiny_state(N=2, size=16, seed=3)
+    ctx = state["per_env_context"]
+    g, c = ctx["true_grid"], ctx
+    for _ in range(3):
+        g, c = ax.ca_update(E.ca, g, c, state["shared_context"])
+    act = np.array([[4, 0, 0], [4, 0, 0]])
+    _, ns, *_ = ax.stateless_step(E, act, state, info, K=3, render_obs=False)
+    assert np.array_equal(ns["per_env_context"]["true_grid"], g)
+    assert np.array_equal(ns["per_env_context"]["key"], c["key"])
+
+
+def test_observation_quirks():
+    g = np.ones((1, 6, 6), np.float32)
+    g[0, 0, :] = 0
+    g[0, 3, 3] = 2
+    pos = np.array([[5, 5]], np.int32)
+    dc = np.zeros((1, 6, 6), np.int32)
+    dc[0, 2, 2] = 1
+    base = ax.build_observation(g, pos, np.array([[4, 0, 0, 0]]), dc, np.array([0]), False)
+    assert base.dtype == np.float32 and base.shape == (1, 6, 6, 3)
+    assert base[0, 5, 5].tolist() == [0, 0, 0]                       # bulldozer pixel is black
+    assert base[0, 1, 1].tolist() == [0xA9, 0xC4, 0x99] and base[0, 3, 3].tolist() == [0xE6, 0x81, 0x81]
+    assert base[0, 2, 2].tolist() == [0xA9 * 0.25, 0xC4 * 0.25, 0x99 * 0.25 + 150.0]  # doused tree, day tint blue
+    night = ax.build_observation(g, pos, np.array([[4, 0, 0, 0]]), dc, np.array([1]), False)
+    assert night[0, 1, 1].tolist() == [0x2F, 0x4F, 0x4F]
+    # extension bit 0 (raw grid): the first row with a positive entry is row 1 -> channel index 1 (zeros)
+    ext = ax.build_observation(g, pos, np.array([[4, 0, 1, 0]]), dc, np.array([0]), True)
+    assert ext[0, 1, 1].tolist() == [0xDD, 0xD1, 0xD3]
+    g2 = g.copy()
+    g2[0, 0, 0] = 1                                                # now row 0 is positive -> channel 0 = raw grid
+    ext2 = ax.build_observation(g2, pos, np.array([[4, 0, 1, 0]]), dc, np.array([0]), True)
+    assert ext2[0, 1, 1].tolist() == [0xA9, 0xC4, 0x99]
+    assert ax.apply_blur(np.full((1, 4, 4), 2.0, np.float32)).tolist() == np.full((1, 4, 4), 2).tolist()
+
+
+# ---- C restatement == NumPy restatement -------------------------------------------------------------------
+def _c_oracle():
+    from oracle.c_oracle import COracle
+    return COracle
+
+
+@pytest.mark.parametrize("mode,K,size,p_tree", [(prng.LEGACY, 1, 64, 0.0), (prng.PARTITIONABLE, 2, 64, 0.0),
+                                               (prng.LEGACY, 2, 32, 0.01), (prng.LEGACY, 1, 40, 0.0)])
+def test_c_oracle_equals_numpy_oracle(mode, K, size, p_tree):
+    COracle = _c_oracle()
+    N = 2
+    E = ax.EnvConstants(size, size, 0.48, 0.12, p_tree_ca=p_tree)
+    winds = oinit.get_winds()
+    state, info = oinit.initial_state(size, size, N, seed=1, mode=mode, hidden="random")
+    state["shared_context"] = E.shared_context(winds)
+    cst = copy.deepcopy({k: v for k, v in state.items() if k != "shared_context"})
+    co = COracle(E, winds, K=K, mode=mode)
+    rng = np.random.default_rng(0)
+    for step in range(12):
+        act = np.stack([rng.integers(0, 9, N), rng.integers(0, 2, N), rng.integers(0, 3, N)], 1)
+        _, state, reward, term, _, info = ax.stateless_step(E, act, state, info, K=K, mode=mode, render_obs=False)
+        r2, t2, cnt = co.step(cst, act)
+        for k in ("true_grid", "fire_age", "dousing_count", "wind_index", "key", "is_night", "time_step"):
+            assert np.array_equal(state["per_env_context"][k], cst["per_env_context"][k]), (step, k)
+        assert np.array_equal(state["position"], cst["position"]) and np.array_equal(state["time"], cst["time"])
+        assert np.array_equal(reward, r2) and np.array_equal(term, t2)
+
+
+def test_c_oracle_injected_fields():
+    COracle = _c_oracle()
+    N, K, size = 2, 2, 32
+    E = ax.EnvConstants(size, size, 0.48, 0.12, p_tree_ca=0.05)
+    winds = oinit.get_winds()
+    state, info = oinit.initial_state(size, size, N, seed=2, hidden="random")
+    state["shared_context"] = E.shared_context(winds)
+    cst = copy.deepcopy({k: v for k, v in state.items() if k != "shared_context"})
+    co = COracle(E, winds, K=K)
+    rng = np.random.default_rng(1)
+    for step in range(6):
+        inj = {"u_burn": (rng.random((K, N, size, size, 9)) * 0.3).astype(np.float32),
+               "u_grow": rng.random((K, N, size, size)).astype(np.float32),
+               "age_new": rng.integers(3, 9, (K, N, size, size)).astype(np.int32),
+               "u_wind": rng.random((K, N)).astype(np.float32), "wind_step": rng.integers(1, 8, (K, N)).astype(np.int32)}
+        act = np.stack([rng.integers(0, 9, N), rng.integers(0, 2, N), rng.integers(0, 3, N)], 1)
+        inj_list = [{k: (v[j].reshape(N, size, size, 3, 3) if k == "u_burn" else v[j]) for k, v in inj.items()}
+                    for j in range(K)]
+        _, state, reward, term, _, info = ax.stateless_step(E, act, state, info, K=K, inject=inj_list, render_obs=False)
+        r2, t2, cnt = co.step(cst, act, inject=inj)
+        assert np.array_equal(state["per_env_context"]["true_grid"], cst["per_env_context"]["true_grid"]), step
+        assert np.array_equal(state["per_env_context"]["fire_age"], cst["per_env_context"]["fire_age"]), step
+        assert np.array_equal(state["per_env_context"]["wind_index"], cst["per_env_context"]["wind_index"]), step
+
+
+# ---- golden fixtures -------------------------------------------------------------------------------------
+def _golden_module():
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_oracle_reproduces_golden_fixtures():
+    mg = _golden_module()
+    gold = np.load(os.path.join(HERE, "golden", "env_step_golden.npz"))
+    for name, case in mg.CASES.items():
+        out = mg.run_case(case)
+        for k, v in out.items():
+            assert np.array_equal(v, gold[f"{name}/{k}"]), (name, k)
+
+
+def test_c_oracle_reproduces_golden_fixtures():
+    COracle = _c_oracle()
+    mg = _golden_module()
+    gold = np.load(os.path.join(HERE, "golden", "env_step_golden.npz"))
+    for name, case in mg.CASES.items():
+        state, info = oinit.initial_state(64, 64, case["N"], seed=case["seed"], jax_seed=1,
+                                          use_hidden=case["use_hidden"], mode=case["mode"])
+        E = ax.EnvConstants(64, 64, speed_move=0.48, speed_act=0.12)
+        co = COracle(E, oinit.get_winds(), K=case["K"], mode=case["mode"])
+        rewards = [co.step(state, mg.actions_for(case, s))[0] for s in range(case["steps"])]
+        ctx = state["per_env_context"]
+        assert np.array_equal(ctx["true_grid"].astype(np.uint8), gold[f"{name}/grid"]), name
+        assert np.array_equal(ctx["fire_age"].astype(np.uint16), gold[f"{name}/fire_age"]), name
+        assert np.array_equal(ctx["key"], gold[f"{name}/key"]) and np.array_equal(np.stack(rewards), gold[f"{name}/rewards"])
