@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cpu-envs", type=int, default=64)
     ap.add_argument("--cpu-steps", type=int, default=24)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--balance-every", type=int, default=8,
+                    help="re-deal envs to warps every this many steps by last step's cost (0 = off)")
     return ap.parse_args()
 
 
@@ -175,7 +177,7 @@ def run_ours(args):
     env = AdvancedForestFireBulldozerEnv(
         size, size, key=1 + rank, num_envs=N, speed_move=0.12 * 4, speed_act=0.03 * 4, use_hidden=not args.no_hidden,
         substeps=K, rng_mode=args.rng_mode, seed=args.seed + rank, hidden="random", obs_mode="none", auto_reset=True,
-        collect_stats=True, device=dev)
+        collect_stats=True, device=dev, balance_every=args.balance_every)
     env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(args.seed + rank)

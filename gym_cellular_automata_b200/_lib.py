@@ -50,6 +50,7 @@ class GcaState(C.Structure):
         ("time_step", C.c_void_p), ("is_night", C.c_void_p),
         ("steps_elapsed", C.c_void_p), ("reward_accumulated", C.c_void_p),
         ("scratch_cell", C.c_void_p), ("scratch_u32", C.c_void_p),
+        ("work", C.c_void_p), ("order", C.c_void_p),
     ]
 
 
@@ -122,6 +123,7 @@ def load():
                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gca_pack_state.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState)] + [C.c_void_p] * 8
     lib.gca_unpack_state.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState)] + [C.c_void_p] * 4
+    lib.gca_balance_order.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gca_threefry_bits.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     lib.gca_threefry_split.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     _lib = lib
@@ -131,7 +133,7 @@ def load():
 # every symbol include/gca.h declares (tests check the library exports all of them)
 EXPORTS = ("gca_version", "gca_last_error", "gca_params_init", "gca_env_step", "gca_alexandridis_step",
            "gca_move_modify", "gca_reward_done", "gca_conditional_reset", "gca_render_rgb", "gca_pack_state",
-           "gca_unpack_state", "gca_threefry_bits", "gca_threefry_split")
+           "gca_unpack_state", "gca_balance_order", "gca_threefry_bits", "gca_threefry_split")
 
 
 def check(rc: int, what: str = "") -> None:

@@ -18,6 +18,7 @@ cudaError_t launch_render(const gca_params&, int, const uint8_t*, const uint64_t
                           const int32_t*, const uint8_t*, int, int, uint32_t*, void*, cudaStream_t);
 cudaError_t launch_threefry_bits(const uint32_t*, long long, int, uint32_t*, cudaStream_t);
 cudaError_t launch_threefry_split_part(const uint32_t*, int, uint32_t*, cudaStream_t);
+cudaError_t launch_balance_order(int, const uint32_t*, int32_t*, cudaStream_t);
 cudaError_t launch_tiled_env_step(const gca_params&, const gca_state&, const int32_t*, const gca_step_out&,
                                   const gca_inject&, uint32_t, uint8_t*, uint32_t*, int32_t*, int, cudaStream_t);
 cudaError_t launch_auto_reset(const gca_params&, const gca_state&, const gca_state&, const float*, float*,
@@ -230,6 +231,11 @@ int gca_unpack_state(const gca_params* p, const gca_state* s, float* true_grid, 
   if (rc) return rc;
   return check_cuda(gca::launch_unpack(*p, *s, true_grid, fire_age, dousing_count, (cudaStream_t)stream),
                     "unpack_state");
+}
+
+int gca_balance_order(int32_t N, const uint32_t* work, int32_t* order, void* stream) {
+  if (N <= 0 || !work || !order) return fail(GCA_ERR_ARG, "gca_balance_order: bad argument");
+  return check_cuda(gca::launch_balance_order(N, work, order, (cudaStream_t)stream), "balance_order");
 }
 
 int gca_threefry_bits(const uint32_t* key2_dev, int64_t n, int32_t rng_mode, uint32_t* out_dev, void* stream) {

@@ -258,6 +258,52 @@ __global__ void render_rgb_kernel(gca_params P, int N, const uint8_t* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// Load balancing of the warp-per-env kernel.  One CTA sorts a chunk of up to 8192 (work, env) keys
+// (bitonic, shared memory) in descending order and deals the sorted envs to CTA slots wave by wave:
+// the first wave of a launch places CTA b on SM (b mod 148), so giving every run of 148 consecutive
+// CTAs envs of adjacent rank -- in alternating direction -- hands each SM (and each of its four
+// schedulers, which take warp w of every CTA) the same mix of heavy and light envs.
+// ---------------------------------------------------------------------------------------------
+constexpr int BAL_CHUNK = 8192;
+constexpr int BAL_WAVE = 148;
+__global__ void __launch_bounds__(1024) balance_order_kernel(int N, const uint32_t* __restrict__ work, int32_t* order) {
+  extern __shared__ unsigned long long keys[];
+  const int base = blockIdx.x * BAL_CHUNK;
+  const int n = min(BAL_CHUNK, N - base);
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (int i = threadIdx.x; i < np2; i += blockDim.x)
+    keys[i] = i < n ? (((unsigned long long)work[base + i] << 32) | (uint32_t)i) : 0ull;  // padding sorts last
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        const int p = i ^ j;
+        if (p > i) {
+          const bool desc = (i & k) == 0;
+          const unsigned long long a = keys[i], b = keys[p];
+          if (desc ? a < b : a > b) { keys[i] = b; keys[p] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  // keys[0..n) hold the chunk's envs by decreasing work (pad keys are 0 and sort behind real keys
+  // only if work > 0 or idx > 0; real entries are re-identified by counting)
+  const int full = n >> 2;  // CTAs with all four warps in range; a trailing partial CTA keeps its ranks
+  for (int s = threadIdx.x; s < n; s += blockDim.x) {
+    const int b = s >> 2, w = s & 3;  // CTA slot inside the chunk, warp
+    int rank = s;
+    if (b < full) {
+      const int wave = b / BAL_WAVE, pos = b % BAL_WAVE;
+      const int in_wave = min(BAL_WAVE, full - wave * BAL_WAVE);
+      const int q = (wave & 1) ? (in_wave - 1 - pos) : pos;
+      rank = 4 * (wave * BAL_WAVE + q) + w;
+    }
+    order[base + s] = base + (int)(keys[rank] & 0xFFFFFFFFull);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // PRNG test hooks
 // ---------------------------------------------------------------------------------------------
 __global__ void threefry_bits_kernel(const uint32_t* __restrict__ key, long long n, int mode, uint32_t* out) {
@@ -349,6 +395,16 @@ cudaError_t launch_render(const gca_params& p, int N, const uint8_t* cell, const
   else
     render_rgb_kernel<false><<<blocks, 256, 0, st>>>(p, N, cell, (const unsigned long long*)doused, position, night,
                                                      ext_action, env_mask, enable_ext, flags_scratch, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_balance_order(int N, const uint32_t* work, int32_t* order, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(balance_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BAL_CHUNK * 8);
+    attr_set = true;
+  }
+  const int chunks = (N + BAL_CHUNK - 1) / BAL_CHUNK;
+  balance_order_kernel<<<chunks, 1024, BAL_CHUNK * 8, st>>>(N, work, order);
   return cudaGetLastError();
 }
 cudaError_t launch_threefry_split_part(const uint32_t* key, int num, uint32_t* out, cudaStream_t st) {

@@ -138,6 +138,7 @@ __device__ __noinline__ void key_schedule(WarpSmem& sm, const gca_params& P, con
   const uint32_t w = lane & 1;
   uint32_t k0 = key0, k1 = key1;
   uint32_t c0 = 0, c1 = 0, sw0 = 0, sw1 = 0;
+#pragma unroll 1
   for (int j = 0; j < K; ++j) {
     uint32_t n0, n1, s0, s1;
     split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K1, S1
@@ -351,6 +352,30 @@ __device__ __forceinline__ bool eval_pair(const WarpSmem& sm, const gca_params& 
   return ig;
 }
 
+// empty -> tree with probability p_tree (0 in the reference env, so this is a cold path): a dense
+// draw per empty cell of the two rows this lane owns.
+__device__ __noinline__ void regrow_rows(const gca_params& P, const gca_inject& J, const TfKey kg, size_t inj_base,
+                                         int lane, unsigned long long e0, unsigned long long e1,
+                                         unsigned long long& g0, unsigned long long& g1) {
+  unsigned long long m = e0;
+  int row = 2 * lane;
+  for (int half = 0; half < 2; ++half) {
+    unsigned long long g = 0;
+    while (m) {
+      const int c = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      const uint32_t cell = (uint32_t)(row * 64 + c);
+      float u;
+      if (J.u_grow) u = J.u_grow[inj_base + cell];
+      else u = bits_to_uniform(bits_at_ni(kg, cell, S64_HALF_CELL, P.rng_mode));
+      if (u < P.p_tree) g |= 1ull << c;
+    }
+    if (half == 0) g0 = g; else g1 = g;
+    m = e1;
+    row = 2 * lane + 1;
+  }
+}
+
 __device__ __forceinline__ void front_masks(unsigned long long t0, unsigned long long t1, unsigned long long f0,
                                             unsigned long long f1, int lane, unsigned long long& fr0,
                                             unsigned long long& fr1) {
@@ -371,9 +396,11 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
                   const float* __restrict__ snap_reward, uint32_t flags) {
   __shared__ WarpSmem smem_all[S64_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * S64_WARPS + warp;
+  const int slot = blockIdx.x * S64_WARPS + warp;
   const int N = S.N;
-  if (e >= N) return;
+  if (slot >= N) return;
+  // optional load-balancing indirection (gca_balance_order): which env this warp steps
+  const int e = S.order != nullptr ? S.order[slot] : slot;
   WarpSmem& sm = smem_all[warp];
   const int K = P.K, mode = P.rng_mode;
   const size_t cell_base = (size_t)e * 4096;
@@ -472,6 +499,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
 
   const float lutreg = lane < 8 ? P.onep_veg[lane] : (lane < 16 ? P.onep_den[lane - 8] : 0.0f);
   uint32_t n_draws = 0, n_thresh = 0, n_front = 0, n_ign = 0, n_ext = 0;
+  uint32_t work = 0;  // warp-uniform cost estimate of this env step (front cells and draws)
   const float w1 = P.ring_w[1], w2 = P.ring_w[2], w3 = P.ring_w[3], w4 = P.ring_w[4];
   const uint32_t age_magic = 0xFFFFFFFFu / P.age_span;
   const bool any_doused = __ballot_sync(GCA_FULL, (dz.x | dz.y) != 0ull) != 0u;
@@ -527,6 +555,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     __syncwarp();
 
     const int total = dense ? T : L;
+    work += 2u * (uint32_t)total;
     for (int pass_base = 0; pass_base < total; pass_base += S64_CAP) {
       if (pass_base > 0) {  // dense fires only: next slice of the list
         build_front_list(sm, fr0, fr1, lane, pass_base);
@@ -599,6 +628,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
             if (ib) atomicOr(&ign32[cb >> 5], 1u << (cb & 31));
           }
           n_draws += (lane == 0) ? (uint32_t)PT : 0u;
+          work += (uint32_t)PT;
           PT = 0;
           __syncwarp();
         }
@@ -673,26 +703,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       ext1 &= ((j >> b) & 1) ? pl1[b] : ~pl1[b];
     }
     unsigned long long g0 = 0, g1 = 0;
-    if (P.p_tree > 0.0f) {
-      // empty -> tree with probability p_tree (0 in the reference env; dense draw per empty cell)
-      const TfKey kg = tf_key(sc[2], sc[3]);
-      unsigned long long m = ~(t0 | f0);
-      int row = 2 * lane;
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        while (m) {
-          const int c = __ffsll((long long)m) - 1;
-          m &= m - 1;
-          const uint32_t cell = (uint32_t)(row * 64 + c);
-          float u;
-          if (J.u_grow) u = J.u_grow[inj_base + cell];
-          else u = bits_to_uniform(bits_at_ni(kg, cell, S64_HALF_CELL, mode));
-          if (u < P.p_tree) { if (half == 0) g0 |= 1ull << c; else g1 |= 1ull << c; }
-        }
-        m = ~(t1 | f1);
-        row = 2 * lane + 1;
-      }
-    }
+    if (P.p_tree > 0.0f) regrow_rows(P, J, tf_key(sc[2], sc[3]), inj_base, lane, ~(t0 | f0), ~(t1 | f1), g0, g1);
     n_ign += ni_l;
     n_ext += __popcll(ext0) + __popcll(ext1);
     ch0 |= I0 | ext0 | g0;
@@ -751,6 +762,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     S.key[2 * e] = key0;
     S.key[2 * e + 1] = key1;
     S.wind_index[e] = widx;
+    if (S.work != nullptr) S.work[e] = work;
     S.tick[e] = tick0 + (uint32_t)K;
     const float rew = award(tcount, fcount);
     if (!ca_only) {

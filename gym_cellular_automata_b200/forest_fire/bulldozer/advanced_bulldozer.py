@@ -111,7 +111,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                  rng_mode: str = "legacy", seed: Optional[int] = None, hidden: str = "reference",
                  obs_mode: str = "rgb_f32", auto_reset: bool = False, ca_p_tree: float = 0.0,
                  p_wind_change: float = 0.06, collect_stats: bool = False, use_tma: bool = True,
-                 env_offset: int = 0, total_envs: Optional[int] = None, **kwargs):
+                 env_offset: int = 0, total_envs: Optional[int] = None, balance_every: int = 0, **kwargs):
         super().__init__(nrows, ncols, **kwargs)
         if not torch.cuda.is_available():
             raise _lib.GcaError("AdvancedForestFireBulldozerEnv needs a CUDA device (sm_100a); there is no CPU path")
@@ -126,6 +126,9 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         self.substeps = int(substeps)
         self.obs_mode = obs_mode
         self.auto_reset = bool(auto_reset)
+        # 64x64 kernel: re-deal envs to warps every `balance_every` steps by last step's cost (0 = off)
+        self.balance_every = int(balance_every)
+        self._steps_since_balance = 0
         self.num_envs = int(num_envs)
         # multi-GPU sharding: this instance holds envs [env_offset, env_offset + num_envs) of a batch of
         # total_envs; per-env keys come from ONE split over the whole batch, so they do not depend on
@@ -430,6 +433,14 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         flags = self._flags
         if self.auto_reset if auto_reset is None else auto_reset:
             flags |= _lib.FLAG_AUTO_RESET
+        if self.balance_every and self._state.work is not None:
+            if self._state.order is None:
+                self._state.enable_balancing()
+                self._version_structs += 1
+            self._steps_since_balance += 1
+            if self._steps_since_balance >= self.balance_every:
+                self._state.rebalance()
+                self._steps_since_balance = 0
         if inject is None:
             # hot path: every struct pointer is cached; only the action pointer and the stream vary
             fa = self._fast_args

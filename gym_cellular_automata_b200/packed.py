@@ -79,10 +79,12 @@ class PackedState:
         tiled = not (H == 64 and W == 64)
         self.scratch_cell = torch.zeros((N, H, W), dtype=torch.uint8, device=d) if tiled else None
         self.scratch_u32 = torch.zeros((N, 14), dtype=torch.int32, device=d) if tiled else None
+        self.work = None if tiled else torch.zeros(N, dtype=torch.int32, device=d)
+        self.order = None   # set by enable_balancing()
         self._c = None
 
     _FIELDS = ("cell", "death", "hidden", "doused", "pslope", "row_min", "tick", "key", "wind_index", "position",
-               "time", "time_step", "is_night", "steps_elapsed", "reward_accumulated", "scratch_cell", "scratch_u32")
+               "time", "time_step", "is_night", "steps_elapsed", "reward_accumulated", "scratch_cell", "scratch_u32", "work", "order")
 
     def cstruct(self) -> GcaState:
         if self._c is None:
@@ -102,7 +104,7 @@ class PackedState:
             t = getattr(self, f)
             if t is None:
                 setattr(o, f, None)
-            elif share_static and f in ("hidden", "pslope", "scratch_cell", "scratch_u32"):
+            elif share_static and f in ("hidden", "pslope", "scratch_cell", "scratch_u32", "work", "order"):
                 setattr(o, f, t)
             else:
                 setattr(o, f, t.clone())
@@ -112,8 +114,19 @@ class PackedState:
     def copy_from(self, other: "PackedState") -> None:
         for f in self._FIELDS:
             t, s = getattr(self, f), getattr(other, f)
-            if t is not None and s is not None and t.data_ptr() != s.data_ptr() and not f.startswith("scratch"):
+            if t is not None and s is not None and t.data_ptr() != s.data_ptr() and not f.startswith("scratch") and f not in ("work", "order"):
                 t.copy_(s)
+
+    def enable_balancing(self) -> None:
+        """Allocate the warp-slot -> env permutation (identity until rebalance() is called)."""
+        if self.order is None and self.work is not None:
+            self.order = torch.arange(self.N, dtype=torch.int32, device=self.device)
+            self._c = None
+
+    def rebalance(self) -> None:
+        if self.order is not None:
+            check(load().gca_balance_order(self.N, ptr(self.work), ptr(self.order), current_stream()),
+                  "gca_balance_order")
 
     # ---- reference layout <-> packed ------------------------------------------------------------
     def pack_from_reference(self, params: GcaParams, ctx: Dict[str, torch.Tensor], position=None, time=None,

@@ -107,6 +107,10 @@ typedef struct gca_state {
   /* scratch of the tiled path (grids other than 64x64); may be NULL for 64x64 */
   uint8_t* scratch_cell;      /* [N][H][W] second grid buffer (tiles read one, write the other) */
   uint32_t* scratch_u32;      /* [N][14]: per-env sub-step key schedule (12) + tree/fire counts (2) */
+  /* optional load balancing of the 64x64 kernel (one warp per env, so an env step costs what its
+   * fire front costs): the kernel writes work[e]; gca_balance_order turns it into order[] */
+  uint32_t* work;             /* [N] cost estimate of the last env step, or NULL */
+  const int32_t* order;       /* [N] env index handled by warp slot i (a permutation), or NULL */
 } gca_state;
 
 /* Per-step outputs (device). Any pointer may be NULL to skip that output. */
@@ -181,6 +185,11 @@ int gca_pack_state(const gca_params* p, const gca_state* s, const float* true_gr
                    const int32_t* density, uint8_t* hidden_out, int32_t* err_flag, void* stream);
 int gca_unpack_state(const gca_params* p, const gca_state* s, float* true_grid, float* fire_age,
                      int32_t* dousing_count, void* stream);
+
+/* Deal the envs to warp slots so that every SM (and scheduler) gets the same share of heavy and
+ * light envs: sort by work[] (descending) and distribute round-robin over waves of 148 CTAs in
+ * alternating direction.  order and work are [N] device arrays; call it every few steps. */
+int gca_balance_order(int32_t N, const uint32_t* work, int32_t* order, void* stream);
 
 /* Test hooks for the in-kernel PRNG: n words of jax.random.bits(key,(n,)) / split(key, num). */
 int gca_threefry_bits(const uint32_t* key2_dev, int64_t n, int32_t rng_mode, uint32_t* out_dev,

@@ -354,3 +354,16 @@ def test_env_keys_do_not_depend_on_sharding(cuda_device):
     keys = torch.cat([p._state.key for p in parts]).cpu().numpy()
     assert np.array_equal(whole._state.key.cpu().numpy(), keys)
     assert np.array_equal(keys, prng.split(prng.key_from_seed(7), 8, prng.LEGACY))
+
+
+def test_load_balancing_is_a_permutation_and_changes_nothing(cuda_device):
+    """gca_balance_order only re-deals envs to warps: states stay bit-exact vs the oracle."""
+    from parity_util import make_pair, lockstep
+    env, co, E, state, info = make_pair(N=300, K=2, mode="legacy", use_hidden=False, seed=4)
+    env.balance_every = 3
+    nbad, reports, stats = lockstep(env, co, state, 14, np.random.default_rng(8))
+    assert nbad == 0, _fmt(reports)
+    order = env._state.order.cpu().numpy()
+    assert sorted(order.tolist()) == list(range(300))
+    work = env._state.work.cpu().numpy()
+    assert work.max() > 0
