@@ -289,15 +289,16 @@ __global__ void __launch_bounds__(1024) balance_order_kernel(int N, const uint32
     }
   // keys[0..n) hold the chunk's envs by decreasing work (pad keys are 0 and sort behind real keys
   // only if work > 0 or idx > 0; real entries are re-identified by counting)
-  const int full = n >> 2;  // CTAs with all four warps in range; a trailing partial CTA keeps its ranks
+  constexpr int WPC = GCA_S64_WARPS;  // warps (envs) per CTA of the step kernel
+  const int full = n / WPC;  // CTAs with all warps in range; a trailing partial CTA keeps its ranks
   for (int s = threadIdx.x; s < n; s += blockDim.x) {
-    const int b = s >> 2, w = s & 3;  // CTA slot inside the chunk, warp
+    const int b = s / WPC, w = s % WPC;  // CTA slot inside the chunk, warp
     int rank = s;
     if (b < full) {
       const int wave = b / BAL_WAVE, pos = b % BAL_WAVE;
       const int in_wave = min(BAL_WAVE, full - wave * BAL_WAVE);
       const int q = (wave & 1) ? (in_wave - 1 - pos) : pos;
-      rank = 4 * (wave * BAL_WAVE + q) + w;
+      rank = WPC * (wave * BAL_WAVE + q) + w;
     }
     order[base + s] = base + (int)(keys[rank] & 0xFFFFFFFFull);
   }

@@ -6,6 +6,7 @@
 #include "../../include/gca.h"
 
 #define GCA_FULL 0xFFFFFFFFu
+#define GCA_S64_WARPS 1  /* warps (= envs) per CTA of env_step64_kernel */
 
 namespace gca {
 

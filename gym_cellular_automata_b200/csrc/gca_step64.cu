@@ -25,7 +25,8 @@
 
 namespace gca {
 
-constexpr int S64_WARPS = 4;    // envs per CTA
+constexpr int S64_WARPS = GCA_S64_WARPS;  // envs (warps) per CTA: 1 -> the warp's shared-memory block has a
+                                          // compile-time address (no per-access base arithmetic)
 constexpr int S64_CAP = 256;    // front cells per pass
 constexpr int S64_PCAP = 512;   // (cell, direction) draws buffered before a flush
 constexpr uint32_t S64_HALF_BURN = 9u * 4096u / 2u;
@@ -387,7 +388,7 @@ __device__ __forceinline__ void front_masks(unsigned long long t0, unsigned long
 }
 
 #ifndef S64_MINB
-#define S64_MINB 7
+#define S64_MINB (28 / S64_WARPS)  // 28 warps/SM x 72 registers = the whole register file; 4096 envs = one wave
 #endif
 __global__ void __launch_bounds__(S64_WARPS * 32, S64_MINB)
 env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gca_state S,
@@ -428,6 +429,21 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   const uint32_t tick0 = S.tick[e];
   uint32_t key0 = S.key[2 * e], key1 = S.key[2 * e + 1];
   int widx = S.wind_index[e];
+  if (!(flags & GCA_FLAG_CA_ONLY)) {
+    // the per-env scalars of the epilogue (lane 0, serial): get their lines on the way now
+    const void* pf = nullptr;
+    switch (lane) {
+      case 0: pf = actions + 3 * e; break;
+      case 1: pf = S.time + e; break;
+      case 2: pf = S.position + 2 * e; break;
+      case 3: pf = S.time_step + e; break;
+      case 4: pf = S.is_night + e; break;
+      case 5: pf = S.steps_elapsed ? S.steps_elapsed + e : nullptr; break;
+      case 6: pf = S.reward_accumulated ? S.reward_accumulated + e : nullptr; break;
+      default: break;
+    }
+    if (pf != nullptr) prefetch_l1(pf);
+  }
   if (lane < 16) sm.fire32[lane] = 0u; else sm.fire32[272 + lane - 16] = 0u;   // fire rows -4..-1, 64..67
   if (lane < 8) sm.dous32[lane] = 0u; else if (lane < 16) sm.dous32[264 + lane - 8] = 0u;  // rows -2,-1,64,65
   store_row_views(sm.dous32 + (2 * lane + 2) * 4, dz.x);
@@ -448,8 +464,14 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   // ---- rows holding a cell that burns out during this env step -----------------------------------
   unsigned long long die0 = 0, die1 = 0, pl0[3] = {0, 0, 0}, pl1[3] = {0, 0, 0};
   {
-    uint32_t m0 = __ballot_sync(GCA_FULL, f0 != 0ull && rm.x < tick0 + (uint32_t)K);
-    uint32_t m1 = __ballot_sync(GCA_FULL, f1 != 0ull && rm.y < tick0 + (uint32_t)K);
+    const bool need0 = f0 != 0ull && rm.x < tick0 + (uint32_t)K;
+    const bool need1 = f1 != 0ull && rm.y < tick0 + (uint32_t)K;
+    // each flagged row is one 128-byte line of burn-out ticks: request them all now, the serial
+    // row loop below then hits L1/L2 instead of paying one DRAM round trip per row
+    if (need0) prefetch_l1(S.death + cell_base + (2 * lane) * 64);
+    if (need1) prefetch_l1(S.death + cell_base + (2 * lane + 1) * 64);
+    uint32_t m0 = __ballot_sync(GCA_FULL, need0);
+    uint32_t m1 = __ballot_sync(GCA_FULL, need1);
     while (m0 | m1) {
       int src;
       bool second;
