@@ -153,7 +153,7 @@ int gca_env_step(const gca_params* p, const gca_state* s, const int32_t* actions
   gca_state st = *s;
   if (flags & GCA_FLAG_NO_HIDDEN) { st.hidden = nullptr; st.pslope = nullptr; }
   if (is64(p)) {
-    if (!s->row_min || !s->die_list) return fail(GCA_ERR_ARG, "gca_env_step: 64x64 path needs row_min and die_list");
+    if (!s->row_min) return fail(GCA_ERR_ARG, "gca_env_step: 64x64 path needs row_min");
     return check_cuda(gca::launch_env_step64(*p, st, actions, o, j, sn, snapshot_reward, flags, (cudaStream_t)stream),
                       "env_step64");
   }

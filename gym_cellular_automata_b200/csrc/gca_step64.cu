@@ -46,10 +46,7 @@ struct __align__(16) WarpSmem {
                                   //   extended incrementally; stale entries fail the frontbb test
   uint16_t pairs[S64_PCAP];       // (list index << 4) | direction  (list build: front rows;
                                   //   apply: cells ignited in this sub-step)
-  unsigned long long frontbb[64]; // front mask of the current sub-step (validates list entries;
-                                  //   apply: burn-out mask of the sub-step)
-  int die_count;                  // cells burning out during this env step (listed in S.die_list)
-  int pad_[3];
+  unsigned long long frontbb[64]; // front mask of the current sub-step (validates list entries)
   uint32_t sched[GCA_MAX_K][12];  // per sub-step: Sburn[2] Sgrow[2] ak1[2] ak2[2] wind change step pad
 };
 
@@ -464,16 +461,13 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   store_row_views(sm.fire32 + (2 * lane + 4) * 4, f0);
   store_row_views(sm.fire32 + (2 * lane + 5) * 4, f1);
 
-  // ---- cells that burn out during this env step -------------------------------------------------
-  // row_min flags the rows holding a fire cell whose tick expires within the next K sub-steps; those
-  // rows' burn-out ticks are read (one 128-byte line per row) and the expiring cells are appended to
-  // the env's die list as (cell | sub-step << 12).  Their stored age becomes 0 right away.
-  uint16_t* dl = S.die_list + cell_base;
-  if (lane == 0) sm.die_count = 0;
-  __syncwarp();
+  // ---- rows holding a cell that burns out during this env step -----------------------------------
+  unsigned long long die0 = 0, die1 = 0, pl0[3] = {0, 0, 0}, pl1[3] = {0, 0, 0};
   {
     const bool need0 = f0 != 0ull && rm.x < tick0 + (uint32_t)K;
     const bool need1 = f1 != 0ull && rm.y < tick0 + (uint32_t)K;
+    // each flagged row is one 128-byte line of burn-out ticks: request them all now, the serial
+    // row loop below then hits L1/L2 instead of paying one DRAM round trip per row
     if (need0) prefetch_l1(S.death + cell_base + (2 * lane) * 64);
     if (need1) prefetch_l1(S.death + cell_base + (2 * lane + 1) * 64);
     uint32_t m0 = __ballot_sync(GCA_FULL, need0);
@@ -490,23 +484,26 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       const bool fa = (fr >> lane) & 1ull, fb = (fr >> (lane + 32)) & 1ull;
       const uint32_t ra = (da - tick0) & 0xFFFFu, rb = (db - tick0) & 0xFFFFu;
       const bool xa = fa && ra < (uint32_t)K, xb = fb && rb < (uint32_t)K;
+      const unsigned long long dmask =
+          (unsigned long long)__ballot_sync(GCA_FULL, xa) | ((unsigned long long)__ballot_sync(GCA_FULL, xb) << 32);
+      unsigned long long pm[3];
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        pm[b] = (unsigned long long)__ballot_sync(GCA_FULL, xa && ((ra >> b) & 1u)) |
+                ((unsigned long long)__ballot_sync(GCA_FULL, xb && ((rb >> b) & 1u)) << 32);
       uint32_t v = 0xFFFFFFFFu;
       if (fa && !xa) v = tick0 + ra;
       if (fb && !xb) v = min(v, tick0 + rb);
       const uint32_t newmin = __reduce_min_sync(GCA_FULL, v);
-      if (xa) {
-        dl[atomicAdd(&sm.die_count, 1)] = (uint16_t)((row * 64 + lane) | (ra << 12));
-        dp[lane] = 0;  // burnt-out cell: fire_age ends at 0
+      if (xa) dp[lane] = 0;        // burnt-out cell: fire_age ends at 0
+      if (xb) dp[lane + 32] = 0;
+      if (lane == src) {
+        if (second) { die1 = dmask; pl1[0] = pm[0]; pl1[1] = pm[1]; pl1[2] = pm[2]; rm.y = newmin; }
+        else { die0 = dmask; pl0[0] = pm[0]; pl0[1] = pm[1]; pl0[2] = pm[2]; rm.x = newmin; }
       }
-      if (xb) {
-        dl[atomicAdd(&sm.die_count, 1)] = (uint16_t)((row * 64 + lane + 32) | (rb << 12));
-        dp[lane + 32] = 0;
-      }
-      if (lane == src) { if (second) rm.y = newmin; else rm.x = newmin; }
     }
   }
   __syncwarp();
-  const int n_die = sm.die_count;
 
   // ---- front of sub-step 0: compact it and start fetching its hidden / slope-factor sectors so
   //      that their DRAM latency hides behind the key schedule.  The list is built ONCE per env
@@ -721,20 +718,11 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         __syncwarp();
       }
     }
-    // burn-outs of this sub-step: scatter the die-list entries tagged j into a bit-board
-    unsigned long long ext0 = 0ull, ext1 = 0ull;
-    if (n_die > 0) {
-      sm.frontbb[2 * lane] = 0ull;
-      sm.frontbb[2 * lane + 1] = 0ull;
-      __syncwarp();
-      uint32_t* ext32 = reinterpret_cast<uint32_t*>(sm.frontbb);
-      for (int i = lane; i < n_die; i += 32) {
-        const uint32_t ent = dl[i];
-        if ((int)(ent >> 12) == j) atomicOr(&ext32[(ent & 4095u) >> 5], 1u << (ent & 31u));
-      }
-      __syncwarp();
-      ext0 = sm.frontbb[2 * lane];
-      ext1 = sm.frontbb[2 * lane + 1];
+    unsigned long long ext0 = die0, ext1 = die1;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      ext0 &= ((j >> b) & 1) ? pl0[b] : ~pl0[b];
+      ext1 &= ((j >> b) & 1) ? pl1[b] : ~pl1[b];
     }
     unsigned long long g0 = 0, g1 = 0;
     if (P.p_tree > 0.0f) regrow_rows(P, J, tf_key(sc[2], sc[3]), inj_base, lane, ~(t0 | f0), ~(t1 | f1), g0, g1);
@@ -800,31 +788,25 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     S.tick[e] = tick0 + (uint32_t)K;
     const float rew = award(tcount, fcount);
     if (!ca_only) {
-      // all loads first (they may alias the stores below as far as the compiler knows)
       const int a0 = actions[3 * e], a1 = actions[3 * e + 1];
-      const float t_old = S.time[e];
-      int row = S.position[2 * e], col = S.position[2 * e + 1];
-      const int ts = S.time_step[e] + 1;
-      int night = S.is_night[e];
-      const float se = S.steps_elapsed ? S.steps_elapsed[e] : 0.0f;
-      const float ra = S.reward_accumulated ? S.reward_accumulated[e] : 0.0f;
       const int a0c = min(max(a0, 0), 8), a1c = min(max(a1, 0), 1);
       // clock (repeat_ca_jax.py:35-41): new = time + ((t_move + t_shoot) + t_any); keep the fraction
       const float tt = __fadd_rn(__fadd_rn(P.t_move[a0c], P.t_shoot[a1c]), P.t_any);
-      const float nt = __fadd_rn(t_old, tt);
-      move_position(a0, 64, 64, row, col);
-      unsigned long long drow = 0ull;
-      if (a1 == 1) drow = S.doused[(size_t)e * 64 + row];
+      const float nt = __fadd_rn(S.time[e], tt);
       S.time[e] = __fsub_rn(nt, truncf(nt));
+      int row = S.position[2 * e], col = S.position[2 * e + 1];
+      move_position(a0, 64, 64, row, col);
       S.position[2 * e] = row;
       S.position[2 * e + 1] = col;
-      if (a1 == 1) S.doused[(size_t)e * 64 + row] = drow | (1ull << col);
+      if (a1 == 1) S.doused[(size_t)e * 64 + row] |= 1ull << col;
+      const int ts = S.time_step[e] + 1;
       S.time_step[e] = ts;
+      int night = S.is_night[e];
       if (O.obs_night) O.obs_night[e] = (uint8_t)night;
       if (ts % P.day_length == 0) night = 1 - night;
       S.is_night[e] = night;
-      if (S.steps_elapsed) S.steps_elapsed[e] = __fadd_rn(se, 1.0f);
-      if (S.reward_accumulated) S.reward_accumulated[e] = __fadd_rn(ra, rew);
+      if (S.steps_elapsed) S.steps_elapsed[e] = __fadd_rn(S.steps_elapsed[e], 1.0f);
+      if (S.reward_accumulated) S.reward_accumulated[e] = __fadd_rn(S.reward_accumulated[e], rew);
     }
     if (O.step_reward) O.step_reward[e] = rew;
     if (O.terminated) O.terminated[e] = done ? 1 : 0;

@@ -79,13 +79,12 @@ class PackedState:
         tiled = not (H == 64 and W == 64)
         self.scratch_cell = torch.zeros((N, H, W), dtype=torch.uint8, device=d) if tiled else None
         self.scratch_u32 = torch.zeros((N, 14), dtype=torch.int32, device=d) if tiled else None
-        self.die_list = None if tiled else torch.zeros((N, H * W), dtype=torch.uint16, device=d)
         self.work = None if tiled else torch.zeros(N, dtype=torch.int32, device=d)
         self.order = None   # set by enable_balancing()
         self._c = None
 
     _FIELDS = ("cell", "death", "hidden", "doused", "pslope", "row_min", "tick", "key", "wind_index", "position",
-               "time", "time_step", "is_night", "steps_elapsed", "reward_accumulated", "scratch_cell", "scratch_u32", "die_list", "work", "order")
+               "time", "time_step", "is_night", "steps_elapsed", "reward_accumulated", "scratch_cell", "scratch_u32", "work", "order")
 
     def cstruct(self) -> GcaState:
         if self._c is None:
@@ -105,7 +104,7 @@ class PackedState:
             t = getattr(self, f)
             if t is None:
                 setattr(o, f, None)
-            elif share_static and f in ("hidden", "pslope", "scratch_cell", "scratch_u32", "die_list", "work", "order"):
+            elif share_static and f in ("hidden", "pslope", "scratch_cell", "scratch_u32", "work", "order"):
                 setattr(o, f, t)
             else:
                 setattr(o, f, t.clone())
@@ -115,7 +114,7 @@ class PackedState:
     def copy_from(self, other: "PackedState") -> None:
         for f in self._FIELDS:
             t, s = getattr(self, f), getattr(other, f)
-            if t is not None and s is not None and t.data_ptr() != s.data_ptr() and not f.startswith("scratch") and f not in ("work", "order", "die_list"):
+            if t is not None and s is not None and t.data_ptr() != s.data_ptr() and not f.startswith("scratch") and f not in ("work", "order"):
                 t.copy_(s)
 
     def enable_balancing(self) -> None:

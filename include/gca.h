@@ -109,7 +109,6 @@ typedef struct gca_state {
   uint32_t* scratch_u32;      /* [N][14]: per-env sub-step key schedule (12) + tree/fire counts (2) */
   /* optional load balancing of the 64x64 kernel (one warp per env, so an env step costs what its
    * fire front costs): the kernel writes work[e]; gca_balance_order turns it into order[] */
-  uint16_t* die_list;         /* [N][H*W] scratch of the 64x64 kernel: cells burning out in the current env step */
   uint32_t* work;             /* [N] cost estimate of the last env step, or NULL */
   const int32_t* order;       /* [N] env index handled by warp slot i (a permutation), or NULL */
 } gca_state;
