@@ -788,25 +788,31 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     S.tick[e] = tick0 + (uint32_t)K;
     const float rew = award(tcount, fcount);
     if (!ca_only) {
+      // all loads first (they may alias the stores below as far as the compiler knows)
       const int a0 = actions[3 * e], a1 = actions[3 * e + 1];
+      const float t_old = S.time[e];
+      int row = S.position[2 * e], col = S.position[2 * e + 1];
+      const int ts = S.time_step[e] + 1;
+      int night = S.is_night[e];
+      const float se = S.steps_elapsed ? S.steps_elapsed[e] : 0.0f;
+      const float ra = S.reward_accumulated ? S.reward_accumulated[e] : 0.0f;
       const int a0c = min(max(a0, 0), 8), a1c = min(max(a1, 0), 1);
       // clock (repeat_ca_jax.py:35-41): new = time + ((t_move + t_shoot) + t_any); keep the fraction
       const float tt = __fadd_rn(__fadd_rn(P.t_move[a0c], P.t_shoot[a1c]), P.t_any);
-      const float nt = __fadd_rn(S.time[e], tt);
-      S.time[e] = __fsub_rn(nt, truncf(nt));
-      int row = S.position[2 * e], col = S.position[2 * e + 1];
+      const float nt = __fadd_rn(t_old, tt);
       move_position(a0, 64, 64, row, col);
+      unsigned long long drow = 0ull;
+      if (a1 == 1) drow = S.doused[(size_t)e * 64 + row];
+      S.time[e] = __fsub_rn(nt, truncf(nt));
       S.position[2 * e] = row;
       S.position[2 * e + 1] = col;
-      if (a1 == 1) S.doused[(size_t)e * 64 + row] |= 1ull << col;
-      const int ts = S.time_step[e] + 1;
+      if (a1 == 1) S.doused[(size_t)e * 64 + row] = drow | (1ull << col);
       S.time_step[e] = ts;
-      int night = S.is_night[e];
       if (O.obs_night) O.obs_night[e] = (uint8_t)night;
       if (ts % P.day_length == 0) night = 1 - night;
       S.is_night[e] = night;
-      if (S.steps_elapsed) S.steps_elapsed[e] = __fadd_rn(S.steps_elapsed[e], 1.0f);
-      if (S.reward_accumulated) S.reward_accumulated[e] = __fadd_rn(S.reward_accumulated[e], rew);
+      if (S.steps_elapsed) S.steps_elapsed[e] = __fadd_rn(se, 1.0f);
+      if (S.reward_accumulated) S.reward_accumulated[e] = __fadd_rn(ra, rew);
     }
     if (O.step_reward) O.step_reward[e] = rew;
     if (O.terminated) O.terminated[e] = done ? 1 : 0;
