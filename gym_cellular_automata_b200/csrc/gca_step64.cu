@@ -307,32 +307,33 @@ __device__ __noinline__ int build_front_list(WarpSmem& sm, unsigned long long fr
 
 // Touch the hidden byte and the 32-byte slope-factor sector of listed front cells [from, to) so
 // that they are in L2 (and, capacity permitting, L1) when the cell and draw phases ask for them.
-__device__ __forceinline__ void prefetch_front(const WarpSmem& sm, const gca_state& S, size_t cell_base, int from,
-                                               int to, int lane) {
-  if (S.hidden == nullptr) return;
+__device__ __forceinline__ void prefetch_front(const WarpSmem& sm, const uint8_t* hidden, const float* pslope,
+                                               size_t cell_base, int from, int to, int lane) {
+  if (hidden == nullptr) return;
   for (int t = from + lane; t < to; t += 32) {
     const uint32_t cell = sm.list[t];
-    prefetch_l1(S.hidden + cell_base + cell);
-    if (S.pslope != nullptr) prefetch_l1(S.pslope + (cell_base + cell) * 8);
+    prefetch_l1(hidden + cell_base + cell);
+    if (pslope != nullptr) prefetch_l1(pslope + (cell_base + cell) * 8);
   }
 }
 
 // One buffered (front cell, burning direction) draw: returns whether it ignites the cell.
-__device__ __forceinline__ bool eval_pair(const WarpSmem& sm, const gca_params& P, const gca_state& S,
-                                          const gca_inject& J, const TfKey& kburn, float windreg, size_t cell_base,
-                                          size_t inj_base, int q, int PT, uint32_t& cell_out, uint32_t& n_thresh) {
+__device__ __forceinline__ bool eval_pair(const WarpSmem& sm, const gca_params& P, const uint8_t* hidden,
+                                          const float* pslope, const float* j_u_burn, int mode, const TfKey& kburn,
+                                          float windreg, size_t cell_base, size_t inj_base, int q, int PT,
+                                          uint32_t& cell_out, uint32_t& n_thresh) {
   const bool valid = q < PT;
   const uint32_t ent = valid ? sm.pairs[q] : 0u;
   const int t = ent >> 4, d = ent & 15;
   const uint32_t cell = sm.list[t];
   cell_out = cell;
   float s = 1.0f;
-  if (S.pslope != nullptr && valid) s = S.pslope[(cell_base + cell) * 8 + dir_slot(d)];
+  if (pslope != nullptr && valid) s = pslope[(cell_base + cell) * 8 + dir_slot(d)];
   float u;
-  if (J.u_burn) {
-    u = valid ? J.u_burn[(inj_base + cell) * 9 + d] : 1.0f;
+  if (j_u_burn) {
+    u = valid ? j_u_burn[(inj_base + cell) * 9 + d] : 1.0f;
   } else {
-    u = bits_to_uniform(bits_at(kburn, cell * 9u + (uint32_t)d, S64_HALF_BURN, P.rng_mode));
+    u = bits_to_uniform(bits_at(kburn, cell * 9u + (uint32_t)d, S64_HALF_BURN, mode));
   }
   const float w = __shfl_sync(GCA_FULL, windreg, d);
   const float plo = __fmul_rn(__fmul_rn(sm.base_lo[t], w), s);
@@ -342,7 +343,7 @@ __device__ __forceinline__ bool eval_pair(const WarpSmem& sm, const gca_params& 
     // threshold cell: the float32 enclosure cannot decide -> reference-order evaluation
     const int r = cell >> 6, c = cell & 63;
     int hid = 3 | (3 << 3);
-    if (S.hidden != nullptr) hid = S.hidden[cell_base + cell];
+    if (hidden != nullptr) hid = hidden[cell_base + cell];
     const float a = P.onep_veg[clip15(hid & 7)];
     const float b = P.onep_den[clip15((hid >> 3) & 7)];
     const float base = exact_base(sm, P, r, c, a, b);
@@ -390,6 +391,10 @@ __device__ __forceinline__ void front_masks(unsigned long long t0, unsigned long
 #ifndef S64_MINB
 #define S64_MINB (28 / S64_WARPS)  // 28 warps/SM x 72 registers = the whole register file; 4096 envs = one wave
 #endif
+// MODE: GCA_RNG_* or -1 (read P.rng_mode); HP: 0 = no hidden layers, 1 = hidden + slope table present,
+// -1 = test the pointers at run time; INJ: injected random fields may be present.  The launcher picks
+// a fully specialised instance for the production cases and the generic one otherwise.
+template <int MODE, int HP, bool INJ>
 __global__ void __launch_bounds__(S64_WARPS * 32, S64_MINB)
 env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gca_state S,
                   const int32_t* __restrict__ actions, const __grid_constant__ gca_step_out O,
@@ -403,8 +408,13 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   // optional load-balancing indirection (gca_balance_order): which env this warp steps
   const int e = S.order != nullptr ? S.order[slot] : slot;
   WarpSmem& sm = smem_all[warp];
-  const int K = P.K, mode = P.rng_mode;
+  const int K = P.K, mode = MODE < 0 ? P.rng_mode : MODE;
   const size_t cell_base = (size_t)e * 4096;
+  const uint8_t* const hidden = HP == 0 ? nullptr : S.hidden;
+  const float* const pslope = HP == 0 ? nullptr : S.pslope;
+  if (HP == 1) { __builtin_assume(hidden != nullptr); __builtin_assume(pslope != nullptr); }
+  const float* const j_u_burn = INJ ? J.u_burn : nullptr;
+  const int32_t* const j_age_new = INJ ? J.age_new : nullptr;
 
   // ---- coalesced 128-bit read of the u8 grid -> tree / fire row masks ---------------------------
   unsigned long long t0, t1, f0, f1;
@@ -514,7 +524,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   int T = build_front_list(sm, fr0, fr1, lane, 0);
   bool dense = T > S64_CAP;  // more front cells than the list holds: rebuild per sub-step, in passes
   int L = min(T, S64_CAP);
-  prefetch_front(sm, S, cell_base, 0, L, lane);
+  prefetch_front(sm, hidden, pslope, cell_base, 0, L, lane);
   unsigned long long listed0 = fr0, listed1 = fr1;
 
   key_schedule(sm, P, J, N, e, lane, key0, key1, widx);
@@ -553,9 +563,9 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
               const uint32_t cell = (uint32_t)(rowbits | (__ffsll((long long)m) - 1));
               m &= m - 1;
               sm.list[idx++] = (uint16_t)cell;
-              if (S.hidden != nullptr) {
-                prefetch_l1(S.hidden + cell_base + cell);
-                if (S.pslope != nullptr) prefetch_l1(S.pslope + (cell_base + cell) * 8);
+              if (hidden != nullptr) {
+                prefetch_l1(hidden + cell_base + cell);
+                if (pslope != nullptr) prefetch_l1(pslope + (cell_base + cell) * 8);
               }
             }
             m = nw1;
@@ -568,7 +578,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       }
       if (dense) {
         T = build_front_list(sm, fr0, fr1, lane, 0);
-        prefetch_front(sm, S, cell_base, 0, min(T, S64_CAP), lane);
+        prefetch_front(sm, hidden, pslope, cell_base, 0, min(T, S64_CAP), lane);
       }
     }
     sm.frontbb[2 * lane] = fr0;
@@ -581,7 +591,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     for (int pass_base = 0; pass_base < total; pass_base += S64_CAP) {
       if (pass_base > 0) {  // dense fires only: next slice of the list
         build_front_list(sm, fr0, fr1, lane, pass_base);
-        prefetch_front(sm, S, cell_base, 0, min(S64_CAP, total - pass_base), lane);
+        prefetch_front(sm, hidden, pslope, cell_base, 0, min(S64_CAP, total - pass_base), lane);
       }
       const int cnt = min(S64_CAP, total - pass_base);
       int PT = 0;
@@ -593,7 +603,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         // still a front cell in this sub-step?
         const bool valid = inrange && ((front32[cell >> 5] >> (cell & 31)) & 1u);
         int hid = 3 | (3 << 3);
-        if (S.hidden != nullptr && valid) hid = S.hidden[cell_base + cell];
+        if (hidden != nullptr && valid) hid = hidden[cell_base + cell];
         uint32_t A, B, C;
         fire_window(sm, r, c, A, B, C);
         // ring populations (Chebyshev rings 1..4 around the centre)
@@ -642,10 +652,12 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
           __syncwarp();
           for (int q0 = 0; q0 < PT; q0 += 64) {
             uint32_t ca, cb = 0;
-            const bool ia = eval_pair(sm, P, S, J, kburn, windreg, cell_base, inj_base, q0 + lane, PT, ca, n_thresh);
+            const bool ia = eval_pair(sm, P, hidden, pslope, j_u_burn, mode, kburn, windreg, cell_base, inj_base,
+                                      q0 + lane, PT, ca, n_thresh);
             bool ib = false;
             if (q0 + 32 < PT)
-              ib = eval_pair(sm, P, S, J, kburn, windreg, cell_base, inj_base, q0 + 32 + lane, PT, cb, n_thresh);
+              ib = eval_pair(sm, P, hidden, pslope, j_u_burn, mode, kburn, windreg, cell_base, inj_base,
+                             q0 + 32 + lane, PT, cb, n_thresh);
             if (ia) atomicOr(&ign32[ca >> 5], 1u << (ca & 31));
             if (ib) atomicOr(&ign32[cb >> 5], 1u << (cb & 31));
           }
@@ -693,11 +705,11 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
           const bool valid = i < cnt;
           const uint32_t cell = sm.pairs[valid ? i : 0];
           uint32_t bits = 0;
-          if (J.age_new == nullptr) bits = bits_at_ni((lane & 1) ? ka2 : ka1, cell, S64_HALF_CELL, mode);
+          if (j_age_new == nullptr) bits = bits_at_ni((lane & 1) ? ka2 : ka1, cell, S64_HALF_CELL, mode);
           const uint32_t other = __shfl_xor_sync(GCA_FULL, bits, 1);
           if (valid && !(lane & 1)) {
             int age;
-            if (J.age_new) age = J.age_new[inj_base + cell];
+            if (j_age_new) age = j_age_new[inj_base + cell];
             else {
               const uint32_t hm = fastmod(bits, P.age_span, age_magic), lm = fastmod(other, P.age_span, age_magic);
               age = P.age_lo + (int)fastmod(hm * P.age_mult + lm, P.age_span, age_magic);
@@ -854,7 +866,14 @@ cudaError_t launch_env_step64(const gca_params& p, const gca_state& s, const int
                               const gca_step_out& out, const gca_inject& inj, const gca_state& snap,
                               const float* snap_reward, uint32_t flags, cudaStream_t st) {
   const int blocks = (s.N + S64_WARPS - 1) / S64_WARPS;
-  env_step64_kernel<<<blocks, S64_WARPS * 32, 0, st>>>(p, s, actions, out, inj, snap, snap_reward, flags);
+  const dim3 g(blocks), b(S64_WARPS * 32);
+  const bool injected = inj.u_burn || inj.u_grow || inj.age_new || inj.u_wind || inj.wind_step;
+  const int hp = (!s.hidden && !s.pslope) ? 0 : ((s.hidden && s.pslope) ? 1 : -1);
+#define GCA_LAUNCH64(M, H, I) env_step64_kernel<M, H, I><<<g, b, 0, st>>>(p, s, actions, out, inj, snap, snap_reward, flags)
+  if (injected || hp < 0) GCA_LAUNCH64(-1, -1, true);
+  else if (p.rng_mode == GCA_RNG_LEGACY) { if (hp) GCA_LAUNCH64(GCA_RNG_LEGACY, 1, false); else GCA_LAUNCH64(GCA_RNG_LEGACY, 0, false); }
+  else { if (hp) GCA_LAUNCH64(GCA_RNG_PARTITIONABLE, 1, false); else GCA_LAUNCH64(GCA_RNG_PARTITIONABLE, 0, false); }
+#undef GCA_LAUNCH64
   return cudaGetLastError();
 }
 
