@@ -19,6 +19,12 @@ cudaError_t launch_render(const gca_params&, int, const uint8_t*, const uint64_t
 cudaError_t launch_threefry_bits(const uint32_t*, long long, int, uint32_t*, cudaStream_t);
 cudaError_t launch_threefry_split_part(const uint32_t*, int, uint32_t*, cudaStream_t);
 cudaError_t launch_balance_order(int, const uint32_t*, int32_t*, cudaStream_t);
+cudaError_t launch_windy_step(int, int, int, unsigned long long*, unsigned long long*, int32_t*, double*, const int32_t*,
+                              const double*, const double*, int, double, double, double, double*, uint8_t*, int32_t*,
+                              int32_t*, cudaStream_t);
+cudaError_t launch_windy_pack(int, int, int, const uint8_t*, unsigned long long*, unsigned long long*, cudaStream_t);
+cudaError_t launch_windy_unpack(int, int, int, const unsigned long long*, const unsigned long long*, uint8_t*,
+                                cudaStream_t);
 cudaError_t launch_tiled_env_step(const gca_params&, const gca_state&, const int32_t*, const gca_step_out&,
                                   const gca_inject&, uint32_t, uint8_t*, uint32_t*, int32_t*, int, cudaStream_t);
 cudaError_t launch_auto_reset(const gca_params&, const gca_state&, const gca_state&, const float*, float*,
@@ -236,6 +242,36 @@ int gca_unpack_state(const gca_params* p, const gca_state* s, float* true_grid, 
 int gca_balance_order(int32_t N, const uint32_t* work, int32_t* order, void* stream) {
   if (N <= 0 || !work || !order) return fail(GCA_ERR_ARG, "gca_balance_order: bad argument");
   return check_cuda(gca::launch_balance_order(N, work, order, (cudaStream_t)stream), "balance_order");
+}
+
+int gca_windy_env_step(int32_t N, int32_t H, int32_t W, uint64_t* tree_bb, uint64_t* fire_bb, int32_t* position,
+                       double* time, const int32_t* actions, const double* wind9, const double* rolls,
+                       int32_t rmax, double t_move, double t_shoot, double t_any, double* reward,
+                       uint8_t* terminated, int32_t* counts, int32_t* repeats_out, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || !tree_bb || !fire_bb || !position || !time || !actions || !wind9)
+    return fail(GCA_ERR_ARG, "gca_windy_env_step: null/bad argument");
+  if (rmax < 0 || (rmax > 0 && !rolls)) return fail(GCA_ERR_ARG, "gca_windy_env_step: rolls missing");
+  if ((size_t)3 * H * ((W + 63) / 64) * 8 > 200 * 1024)
+    return fail(GCA_ERR_UNSUPPORTED, "gca_windy_env_step: grid does not fit shared memory (max ~512x512)");
+  return check_cuda(gca::launch_windy_step(N, H, W, (unsigned long long*)tree_bb, (unsigned long long*)fire_bb, position,
+                                           time, actions, wind9, rolls, rmax, t_move, t_shoot, t_any, reward,
+                                           terminated, counts, repeats_out, (cudaStream_t)stream),
+                    "windy_env_step");
+}
+
+int gca_windy_pack(int32_t N, int32_t H, int32_t W, const uint8_t* cell, uint64_t* tree_bb, uint64_t* fire_bb,
+                   void* stream) {
+  if (N <= 0 || !cell || !tree_bb || !fire_bb) return fail(GCA_ERR_ARG, "gca_windy_pack: bad argument");
+  return check_cuda(gca::launch_windy_pack(N, H, W, cell, (unsigned long long*)tree_bb, (unsigned long long*)fire_bb,
+                                           (cudaStream_t)stream), "windy_pack");
+}
+
+int gca_windy_unpack(int32_t N, int32_t H, int32_t W, const uint64_t* tree_bb, const uint64_t* fire_bb,
+                     uint8_t* cell, void* stream) {
+  if (N <= 0 || !cell || !tree_bb || !fire_bb) return fail(GCA_ERR_ARG, "gca_windy_unpack: bad argument");
+  return check_cuda(gca::launch_windy_unpack(N, H, W, (const unsigned long long*)tree_bb,
+                                             (const unsigned long long*)fire_bb, cell, (cudaStream_t)stream),
+                    "windy_unpack");
 }
 
 int gca_threefry_bits(const uint32_t* key2_dev, int64_t n, int32_t rng_mode, uint32_t* out_dev, void* stream) {

@@ -1,3 +1,4 @@
+from .bulldozer import ForestFireBulldozerEnv
 from .advanced_bulldozer import AdvancedForestFireBulldozerEnv, BatchedAdvancedBulldozerEnv, MDP
 
-__all__ = ["AdvancedForestFireBulldozerEnv", "BatchedAdvancedBulldozerEnv", "MDP"]
+__all__ = ["ForestFireBulldozerEnv", "AdvancedForestFireBulldozerEnv", "BatchedAdvancedBulldozerEnv", "MDP"]

@@ -1,4 +1,5 @@
 from .ca_alexandridis_cuda import PartiallyObservableForestFireCUDA
+from .ca_windy_cuda import WindyForestFireCUDA
 from .move_modify_cuda import ModifyCUDA, MoveCUDA, MoveModifyCUDA
 from .repeat_ca_cuda import RepeatCACUDA
 
@@ -6,6 +7,7 @@ from .repeat_ca_cuda import RepeatCACUDA
 PartiallyObservableForestFireJax = PartiallyObservableForestFireCUDA
 MoveJax, ModifyJax, MoveModifyJax = MoveCUDA, ModifyCUDA, MoveModifyCUDA
 RepeatCAJax = RepeatCACUDA
+WindyForestFire = WindyForestFireCUDA  # v3 rule set (reference operators/ca_windy.py)
 
-__all__ = ["PartiallyObservableForestFireCUDA", "MoveCUDA", "ModifyCUDA", "MoveModifyCUDA", "RepeatCACUDA",
+__all__ = ["WindyForestFireCUDA", "WindyForestFire", "PartiallyObservableForestFireCUDA", "MoveCUDA", "ModifyCUDA", "MoveModifyCUDA", "RepeatCACUDA",
            "PartiallyObservableForestFireJax", "MoveJax", "ModifyJax", "MoveModifyJax", "RepeatCAJax"]

@@ -191,6 +191,24 @@ int gca_unpack_state(const gca_params* p, const gca_state* s, float* true_grid, 
  * alternating direction.  order and work are [N] device arrays; call it every few steps. */
 int gca_balance_order(int32_t N, const uint32_t* work, int32_t* order, void* stream);
 
+/* ---- v3 rule set: WindyForestFire + Move / Modify(cut) / RepeatCA of ForestFireBulldozer256x256-v3 ----
+ * (reference forest_fire/operators/ca_windy.py:41-139, operators/repeat_ca.py:32-45,
+ *  operators/move_modify.py:39-94, bulldozer/bulldozer.py:196-203,393-400).
+ * State: tree / fire bit-boards u64 [N][H][ceil(W/64)], position i32 [N][2], time f64 [N].
+ * actions i32 [N][2] (move 0-8, shoot 0-1); wind f64 [9] (3x3 row-major, shared by all envs);
+ * rolls f64 [N][rmax][9]: the uniform 3x3 roll of each CA update of this step (the reference draws
+ * them from an unseeded generator, so they are an input); an env uses its first `repeats` rolls.
+ * H * ceil(W/64) * 24 bytes of shared memory per env must fit one SM (grids up to ~ 512 x 512). */
+int gca_windy_env_step(int32_t N, int32_t H, int32_t W, uint64_t* tree_bb, uint64_t* fire_bb, int32_t* position,
+                       double* time, const int32_t* actions, const double* wind9, const double* rolls,
+                       int32_t rmax, double t_move, double t_shoot, double t_any, double* reward,
+                       uint8_t* terminated, int32_t* counts, int32_t* repeats_out, void* stream);
+/* u8 cell codes (0 empty, 1 tree, 2 fire = the reference's 0 / 3 / 25) <-> bit-boards */
+int gca_windy_pack(int32_t N, int32_t H, int32_t W, const uint8_t* cell, uint64_t* tree_bb, uint64_t* fire_bb,
+                   void* stream);
+int gca_windy_unpack(int32_t N, int32_t H, int32_t W, const uint64_t* tree_bb, const uint64_t* fire_bb,
+                     uint8_t* cell, void* stream);
+
 /* Test hooks for the in-kernel PRNG: n words of jax.random.bits(key,(n,)) / split(key, num). */
 int gca_threefry_bits(const uint32_t* key2_dev, int64_t n, int32_t rng_mode, uint32_t* out_dev,
                       void* stream);

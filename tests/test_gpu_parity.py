@@ -367,3 +367,59 @@ def test_load_balancing_is_a_permutation_and_changes_nothing(cuda_device):
     assert sorted(order.tolist()) == list(range(300))
     work = env._state.work.cpu().numpy()
     assert work.max() > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# v3 rule set (WindyForestFire + NumPy Move / Modify / RepeatCA semantics)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H,W", [(16, 16), (64, 96), (256, 256), (40, 130)])
+def test_windy_ca_rule_parity(cuda_device, H, W):
+    from oracle import windy
+    from gym_cellular_automata_b200.forest_fire.operators import WindyForestFire
+    rng = np.random.default_rng(H * 7 + W)
+    ca = WindyForestFire()
+    N = 3
+    g = rng.choice([0, 3, 25], size=(N, H, W), p=[0.15, 0.8, 0.05]).astype(np.int64)
+    wind = windy.DEFAULT_WIND
+    for step in range(6):
+        roll = rng.random((N, 3, 3))
+        exp = np.stack([windy.windy_update(g[e], wind, roll[e]) for e in range(N)])
+        got, _ = ca(g, None, wind, roll=roll)
+        assert np.array_equal(got.cpu().numpy(), exp), (step, np.argwhere(got.cpu().numpy() != exp)[:5])
+        g = exp
+    # the reference's deterministic case: wind = 1 -> every burning neighbour propagates
+    got, _ = ca(g[0], None, np.ones((3, 3)), roll=rng.random((1, 3, 3)))
+    assert np.array_equal(got.cpu().numpy(), windy.windy_update(g[0], np.ones((3, 3)), np.zeros((3, 3))))
+
+
+def test_v3_env_step_parity(cuda_device):
+    """Batched v3 env step == the oracle's per-env CAEnv.step: float64 clock with 0, 1 or several CA
+    updates per step, clamped move, tree cut, reward, done."""
+    from oracle import windy
+    from gym_cellular_automata_b200.forest_fire.bulldozer import ForestFireBulldozerEnv
+    N, H, W = 5, 48, 80
+    env = ForestFireBulldozerEnv(H, W, num_envs=N, seed=3, t_move=0.45, t_shoot=0.8, max_repeats=3)
+    obs, info = env.reset()
+    grid = obs[0].cpu().numpy().copy()
+    pos = obs[1][1].cpu().numpy().copy()
+    time = obs[1][2].cpu().numpy().copy()
+    assert (grid == 25).sum() == N and set(np.unique(grid)) <= {0, 3, 25}
+    C = windy.V3Constants(H, W, t_move=0.45, t_shoot=0.8)
+    rng = np.random.default_rng(1)
+    seen = set()
+    for step in range(40):
+        act = np.stack([rng.integers(0, 9, N), rng.integers(0, 2, N)], 1)
+        rolls = rng.random((N, 3, 9))
+        obs, reward, term, trunc, info = env.step(act, rolls=rolls)
+        for e in range(N):
+            g, p, t, r, d, rep = windy.v3_env_step(C, grid[e], pos[e], time[e], act[e], windy.DEFAULT_WIND,
+                                                   rolls[e].reshape(3, 3, 3))
+            grid[e], pos[e], time[e] = g, p, t
+            seen.add(rep)
+            assert int(info["repeats"][e]) == rep
+            rr = float(reward[e])
+            assert (np.isnan(rr) and np.isnan(r)) or rr == r, (step, e, rr, r)
+            assert bool(term[e]) == d
+        assert np.array_equal(obs[0].cpu().numpy(), grid), step
+        assert np.array_equal(obs[1][1].cpu().numpy(), pos) and np.array_equal(obs[1][2].cpu().numpy(), time)
+    assert {0, 1} <= seen and max(seen) >= 2

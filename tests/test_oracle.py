@@ -274,3 +274,44 @@ def test_c_oracle_reproduces_golden_fixtures():
         assert np.array_equal(ctx["true_grid"].astype(np.uint8), gold[f"{name}/grid"]), name
         assert np.array_equal(ctx["fire_age"].astype(np.uint16), gold[f"{name}/fire_age"]), name
         assert np.array_equal(ctx["key"], gold[f"{name}/key"]) and np.array_equal(np.stack(rewards), gold[f"{name}/rewards"])
+
+
+# ---- v3 rule set (WindyForestFire), reference operators/tests/test_ca_windy.py:55-102 ----------------------
+def test_windy_oracle_rules_with_certain_wind():
+    from oracle import windy
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        g = rng.choice([0, 3, 25], size=(5, 6), p=[0.3, 0.5, 0.2]).astype(np.int64)
+        ng = windy.windy_update(g, np.ones((3, 3)), rng.random((3, 3)))
+        pad = np.pad(g, 1)
+        for r in range(5):
+            for c in range(6):
+                nb = pad[r:r + 3, c:c + 3]
+                if g[r, c] == 3:
+                    assert ng[r, c] == (25 if (nb == 25).any() else 3)
+                else:
+                    assert ng[r, c] == 0
+    # a failed direction does not propagate: fire BELOW a tree spreads up with the kernel's "up" entry
+    g = np.zeros((3, 3), np.int64)
+    g[1, 1], g[2, 1] = 3, 25
+    wind = windy.DEFAULT_WIND
+    roll = np.zeros((3, 3))
+    roll[0, 1] = 0.99  # wind[0,1] = 0.64 <= 0.99 -> "up" fails
+    assert windy.windy_update(g, wind, roll)[1, 1] == 3
+    roll[0, 1] = 0.10
+    assert windy.windy_update(g, wind, roll)[1, 1] == 25
+
+
+def test_v3_env_step_oracle_clock_and_cut():
+    from oracle import windy
+    C = windy.V3Constants(8, 8, t_move=0.6, t_shoot=0.7)
+    g = np.full((8, 8), 3, np.int64)
+    g[4, 4] = 25
+    rolls = np.zeros((3, 3, 3))
+    # move + shoot: 0.6 + 0.7 + 0.001 -> one CA update, fraction kept; the tree under the bulldozer is cut
+    ng, pos, t, rew, done, rep = windy.v3_env_step(C, g, np.array([0, 0]), 0.0, (8, 1), windy.DEFAULT_WIND, rolls)
+    assert rep == 1 and abs(t - 0.301) < 1e-12 and tuple(pos) == (1, 1) and ng[1, 1] == 0
+    assert ng[4, 4] == 0 and (ng == 25).sum() == 8 and not done
+    # not moving and not shooting costs only t_any (bulldozer.py:285-286)
+    ng, pos, t, rew, done, rep = windy.v3_env_step(C, g, np.array([0, 0]), 0.0, (4, 0), windy.DEFAULT_WIND, rolls)
+    assert rep == 0 and t == 0.001 and np.array_equal(ng, g)
