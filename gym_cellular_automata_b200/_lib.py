@@ -124,7 +124,7 @@ def load():
     lib.gca_pack_state.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState)] + [C.c_void_p] * 8
     lib.gca_unpack_state.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState)] + [C.c_void_p] * 4
     lib.gca_balance_order.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.gca_windy_env_step.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 8 + [C.c_int32, C.c_double,
+    lib.gca_windy_env_step.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7 + [C.c_int32, C.c_double,
                                       C.c_double, C.c_double] + [C.c_void_p] * 5
     lib.gca_windy_pack.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 4
     lib.gca_windy_unpack.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 4
