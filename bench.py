@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cpu-envs", type=int, default=64)
     ap.add_argument("--cpu-steps", type=int, default=24)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--ruleset", default="alexandridis", choices=["alexandridis", "v3"],
+                    help="v3 = the registered ForestFireBulldozer256x256-v3 rule set (WindyForestFire), an extra line")
     ap.add_argument("--balance-every", type=int, default=8,
                     help="re-deal envs to warps every this many steps by last step's cost (0 = off)")
     return ap.parse_args()
@@ -306,8 +308,53 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_v3(args):
+    """Extra (non-headline) line: the v3 rule set, 256x256 x 1024 envs by default (BASELINE config 3)."""
+    import torch
+    from gym_cellular_automata_b200.forest_fire.bulldozer import ForestFireBulldozerEnv
+    size = args.size if args.size != 64 else 256
+    N = args.envs_per_gpu if args.envs_per_gpu != 4096 else 1024
+    env = ForestFireBulldozerEnv(size, size, num_envs=N, seed=args.seed, max_repeats=2)
+    env.reset()
+    dev = env.device
+    total = args.warmup + args.steps
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(args.seed)
+    acts = torch.stack([torch.randint(0, 9, (total, N), device=dev, generator=gen),
+                        torch.randint(0, 2, (total, N), device=dev, generator=gen)], -1).to(torch.int32)
+    rolls = torch.rand((N, 2, 9), dtype=torch.float64, device=dev, generator=gen)
+    from gym_cellular_automata_b200._lib import check, current_stream, load, ptr
+    st = env._state
+
+    def step(i):
+        check(load().gca_windy_env_step(N, size, size, ptr(st.tree), ptr(st.fire), ptr(st.position), ptr(st.time),
+                                        ptr(acts[i]), ptr(env._wind_dev), ptr(rolls), 2, float(env._t_act_move),
+                                        float(env._t_act_shoot), float(env._t_env_any), ptr(env._reward),
+                                        ptr(env._term), ptr(env._counts), ptr(env._repeats), current_stream()))
+    reps = 0
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+        reps += env._repeats
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    ca_updates = int(torch.as_tensor(reps).sum())
+    print(json.dumps({"metric": "env_steps_per_s", "value": N * args.steps / (ms * 1e-3), "unit": "env-steps/s",
+                      "ruleset": "v3 WindyForestFire", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": ms / args.steps, "ca_updates": ca_updates,
+                      "cell_updates_per_s": ca_updates * size * size / (ms * 1e-3), "data": "synthetic",
+                      "config": {"workload": f"v3 rule set {size}x{size}, {N} envs, reference clock (most steps run 0 CA updates)"}}))
+
+
 def main():
     args = parse()
+    if args.ruleset == "v3":
+        return run_v3(args)
     if args.impl == "reference":
         run_reference(args)
     else:
