@@ -13,14 +13,15 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libgca.so")
-SOURCES = ("gca_step64.cu", "gca_tiled.cu", "gca_windy.cu", "gca_aux.cu", "gca_abi.cu")
+# GCA_LIB_PATH selects another build of the same sources (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("GCA_LIB_PATH") or os.path.join(_HERE, "libgca.so")
+SOURCES = ("gca_step64.cu", "gca_step64_warp.cu", "gca_tiled.cu", "gca_windy.cu", "gca_aux.cu", "gca_abi.cu")
 HEADERS = ("gca_common.cuh", os.path.join("..", "..", "include", "gca.h"))
 
 GCA_MAX_R = 10
 GCA_MAX_K = 8
 RNG_LEGACY, RNG_PARTITIONABLE = 0, 1
-FLAG_AUTO_RESET, FLAG_NO_HIDDEN, FLAG_CA_ONLY, FLAG_NO_TMA = 1, 2, 4, 8
+FLAG_AUTO_RESET, FLAG_NO_HIDDEN, FLAG_CA_ONLY, FLAG_NO_TMA, FLAG_WORK_CYCLES = 1, 2, 4, 8, 16
 
 
 class GcaError(RuntimeError):

@@ -2,6 +2,7 @@
 // argument checks, constant derivation (A0) and kernel dispatch by grid shape.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "gca_common.cuh"
@@ -160,6 +161,11 @@ int gca_env_step(const gca_params* p, const gca_state* s, const int32_t* actions
   if (flags & GCA_FLAG_NO_HIDDEN) { st.hidden = nullptr; st.pslope = nullptr; }
   if (is64(p)) {
     if (!s->row_min) return fail(GCA_ERR_ARG, "gca_env_step: 64x64 path needs row_min");
+    // GCA_STEP64_IMPL=warp selects the earlier one-warp-per-env kernel (A/B measurements only)
+    static const bool warp_impl = [] { const char* v = getenv("GCA_STEP64_IMPL"); return v && !strcmp(v, "warp"); }();
+    if (warp_impl)
+      return check_cuda(gca::launch_env_step64_warp(*p, st, actions, o, j, sn, snapshot_reward, flags, (cudaStream_t)stream),
+                        "env_step64_warp");
     return check_cuda(gca::launch_env_step64(*p, st, actions, o, j, sn, snapshot_reward, flags, (cudaStream_t)stream),
                       "env_step64");
   }

@@ -2,6 +2,9 @@
 // stand-alone move/douse, reward/done, conditional_reset, RGB observation, PRNG test hooks.
 // Reference lines are cited per kernel (paths relative to
 // /root/reference/gym_cellular_automata/).
+#include <cstdlib>
+#include <cstring>
+
 #include "gca_common.cuh"
 
 namespace gca {
@@ -258,15 +261,13 @@ __global__ void render_rgb_kernel(gca_params P, int N, const uint8_t* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// Load balancing of the warp-per-env kernel.  One CTA sorts a chunk of up to 8192 (work, env) keys
-// (bitonic, shared memory) in descending order and deals the sorted envs to CTA slots wave by wave:
-// the first wave of a launch places CTA b on SM (b mod 148), so giving every run of 148 consecutive
-// CTAs envs of adjacent rank -- in alternating direction -- hands each SM (and each of its four
-// schedulers, which take warp w of every CTA) the same mix of heavy and light envs.
+// Load balancing of the 64x64 step kernel.  One CTA sorts a chunk of up to 8192 (work, env) keys
+// (bitonic, shared memory) in descending order and deals the sorted envs to the warp slots of the
+// step kernel's CTAs (see the dealing rule below; wpc = envs per CTA of the step kernel).
 // ---------------------------------------------------------------------------------------------
 constexpr int BAL_CHUNK = 8192;
 constexpr int BAL_WAVE = 148;
-__global__ void __launch_bounds__(1024) balance_order_kernel(int N, const uint32_t* __restrict__ work, int32_t* order) {
+__global__ void __launch_bounds__(1024) balance_order_kernel(int N, int wpc, const uint32_t* __restrict__ work, int32_t* order) {
   extern __shared__ unsigned long long keys[];
   const int base = blockIdx.x * BAL_CHUNK;
   const int n = min(BAL_CHUNK, N - base);
@@ -289,16 +290,22 @@ __global__ void __launch_bounds__(1024) balance_order_kernel(int N, const uint32
     }
   // keys[0..n) hold the chunk's envs by decreasing work (pad keys are 0 and sort behind real keys
   // only if work > 0 or idx > 0; real entries are re-identified by counting)
-  constexpr int WPC = GCA_S64_WARPS;  // warps (envs) per CTA of the step kernel
-  const int full = n / WPC;  // CTAs with all warps in range; a trailing partial CTA keeps its ranks
+  // Pooled kernel (E warps = E envs per CTA, the heavy phases shared by the CTA): a CTA costs about the
+  // SUM of its envs' work, so deal the sorted envs like cards -- warp w of CTA b gets rank w*C + b,
+  // every other round in reverse (snake) -- which gives all C full CTAs nearly the same sum.
+  const int full = n / wpc;  // CTAs with all warps in range; a trailing partial CTA keeps its ranks
   for (int s = threadIdx.x; s < n; s += blockDim.x) {
-    const int b = s / WPC, w = s % WPC;  // CTA slot inside the chunk, warp
+    const int b = s / wpc, w = s % wpc;  // CTA slot inside the chunk, warp
     int rank = s;
     if (b < full) {
-      const int wave = b / BAL_WAVE, pos = b % BAL_WAVE;
-      const int in_wave = min(BAL_WAVE, full - wave * BAL_WAVE);
-      const int q = (wave & 1) ? (in_wave - 1 - pos) : pos;
-      rank = WPC * (wave * BAL_WAVE + q) + w;
+      if (wpc > 1) {
+        rank = w * full + ((w & 1) ? (full - 1 - b) : b);
+      } else {
+        const int wave = b / BAL_WAVE, pos = b % BAL_WAVE;
+        const int in_wave = min(BAL_WAVE, full - wave * BAL_WAVE);
+        const int q = (wave & 1) ? (in_wave - 1 - pos) : pos;
+        rank = wave * BAL_WAVE + q;
+      }
     }
     order[base + s] = base + (int)(keys[rank] & 0xFFFFFFFFull);
   }
@@ -405,7 +412,8 @@ cudaError_t launch_balance_order(int N, const uint32_t* work, int32_t* order, cu
     attr_set = true;
   }
   const int chunks = (N + BAL_CHUNK - 1) / BAL_CHUNK;
-  balance_order_kernel<<<chunks, 1024, BAL_CHUNK * 8, st>>>(N, work, order);
+  static const bool warp_impl = [] { const char* v = getenv("GCA_STEP64_IMPL"); return v && !strcmp(v, "warp"); }();
+  balance_order_kernel<<<chunks, 1024, BAL_CHUNK * 8, st>>>(N, warp_impl ? 1 : GCA_S64_WARPS, work, order);
   return cudaGetLastError();
 }
 cudaError_t launch_threefry_split_part(const uint32_t* key, int num, uint32_t* out, cudaStream_t st) {

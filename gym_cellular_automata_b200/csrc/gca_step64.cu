@@ -1,4 +1,7 @@
-// gca_step64.cu -- fused environment step for 64x64 grids: ONE WARP PER ENVIRONMENT.
+// gca_step64.cu -- fused environment step for 64x64 grids: one CTA of E warps steps E environments
+// in lock-step; every warp OWNS one env (its bit-boards live in that warp's registers) and the two
+// heavy phases of each CA sub-step -- per-front-cell burn probability and the per-(cell, direction)
+// threefry draws -- are POOLED over the CTA, so a large fire front is worked on by all E warps.
 //
 // Replaces, for a batch of envs, jax.vmap(MDP.update) + _award + _is_done (+ conditional_reset)
 // of /root/reference/gym_cellular_automata/forest_fire/bulldozer/advanced_bulldozer.py:332-518,
@@ -7,16 +10,21 @@
 // draws 12 random words per cell; this kernel works on bit-boards and draws lazily.
 //
 // Design:
-//  * a 64-cell row is one 64-bit word per mask (tree, fire, doused).  Lane l owns rows 2l, 2l+1 in
-//    registers; vertical halos come from warp shuffles.
+//  * a 64-cell row is one 64-bit word per mask (tree, fire, doused).  Lane l of the owner warp holds
+//    rows 2l, 2l+1 in registers; vertical halos come from warp shuffles.
 //  * all K CA sub-steps of the env step are applied on-chip (temporal blocking); HBM sees one
 //    coalesced 128-bit read of the u8 grid and sparse in-place writes of the cells that changed.
-//  * front cells (tree with a burning Moore neighbour) are compacted into a shared-memory list;
-//    per front cell the 9x9 fire window is cut out of the bit-board, ring populations give a fast
-//    float32 enclosure [lo, hi] of the burn-probability chain; per (cell, burning direction) one
-//    counter-based threefry2x32 block reproduces exactly the uniform jax.random would have
-//    drawn for that element.  u < lo ignites, u >= hi does not, and the (rare) in-between case is
-//    re-evaluated with the reference's exact row-major float32 summation ("threshold cells").
+//  * front cells (tree with a burning Moore neighbour) are compacted into a per-env shared-memory
+//    list (built once per env step, extended incrementally).  Work items of the pooled phase are
+//    32-entry chunks of those lists, handed out by a shared-memory counter to whichever warp is
+//    free: per front cell the 9x9 fire window is cut out of the bit-board, ring populations give an
+//    upper bound of the float32 burn-probability chain; the (cell, burning direction) pairs go to
+//    the warp's private pair buffer, and whenever it holds 64 pairs the warp draws them -- one
+//    counter-based threefry2x32 block per pair reproduces exactly the uniform jax.random would have
+//    drawn for that element.  u >= hi does not ignite, u < hi (1 - 2^-14) ignites, and the (rare)
+//    in-between case is re-evaluated with the reference's exact row-major float32 summation
+//    ("threshold cells").  Before round-1's re-design one warp did all of this for its env alone
+//    and the kernel lasted as long as its heaviest env (gca_step64_warp.cu, kept for A/B runs).
 //  * fire ages are stored as burn-out ticks, so burning cells need no per-step decrement; a
 //    per-row minimum tells which rows hold a cell that burns out in this step.
 //  * the key chain of jax.random.split is evaluated by lane pairs; clock, move, douse, day/night,
@@ -24,30 +32,44 @@
 #include "gca_common.cuh"
 
 namespace gca {
+namespace {
 
-constexpr int S64_WARPS = GCA_S64_WARPS;  // envs (warps) per CTA: 1 -> the warp's shared-memory block has a
-                                          // compile-time address (no per-access base arithmetic)
-constexpr int S64_CAP = 256;    // front cells per pass
-constexpr int S64_PCAP = 512;   // (cell, direction) draws buffered before a flush
+constexpr int S64_E = GCA_S64_WARPS;   // envs (= warps) per CTA
+constexpr int S64_CAP = 256;           // front cells per pass
+constexpr int S64_WP = 320;            // warp-private pair buffer: < 64 carried over + <= 256 of one chunk
 constexpr uint32_t S64_HALF_BURN = 9u * 4096u / 2u;
 constexpr uint32_t S64_HALF_CELL = 4096u / 2u;
-// enclosure half-width of the fast float32 path: |sequential sum - ring-count sum| <= 89 u |sum|
-// (80 adds + 8 flops, u = 2^-24); 2^-16 = 256 u leaves a 2.8x margin.
+// enclosure of the fast float32 path: |sequential sum - ring-count sum| <= 89 u |sum|
+// (80 adds + 8 flops, u = 2^-24); 2^-16 = 256 u leaves a 2.8x margin.  The upper bound hi is
+// chain(H (1 + 2^-16)); chain(H (1 - 2^-16)) >= hi (1 - 2^-15 (1 + 2^-6)) > hi (1 - 2^-14), so
+// u < hi (1 - 2^-14) decides "ignites" without storing a second bound per cell.
 #define S64_LO 0.9999847412109375f   /* 1 - 2^-16 */
 #define S64_HI 1.0000152587890625f   /* 1 + 2^-16 */
+#define S64_SURE 0.99993896484375f   /* 1 - 2^-14 */
 
-struct __align__(16) WarpSmem {
-  uint32_t fire32[72 * 4];        // fire rows -4..67, 4 overlapping 32-bit views per row
-  uint32_t dous32[68 * 4];        // doused rows -2..65, same views
-  unsigned long long ign[64];     // ignition accumulator (unpack: tree rows)
-  float base_lo[S64_CAP];         // per front cell: enclosure of (p_h (1+p_veg)) (1+p_den)
-  float base_hi[S64_CAP];         //   (unpack: fire rows; apply: burn-out ticks of new fires)
-  uint16_t list[S64_CAP];         // front cells: (row << 6) | col.  Built once per env step and
-                                  //   extended incrementally; stale entries fail the frontbb test
-  uint16_t pairs[S64_PCAP];       // (list index << 4) | direction  (list build: front rows;
-                                  //   apply: cells ignited in this sub-step)
-  unsigned long long frontbb[64]; // front mask of the current sub-step (validates list entries)
-  uint32_t sched[GCA_MAX_K][12];  // per sub-step: Sburn[2] Sgrow[2] ak1[2] ak2[2] wind change step pad
+struct __align__(16) EnvSmem {
+  uint32_t fire32[72 * 4];          // fire rows -4..67, 4 overlapping 32-bit views per row
+  uint32_t dous32[68 * 4];          // doused rows -2..65, same views
+  unsigned long long ign[64];       // ignition accumulator of the sub-step (unpack: tree rows)
+  unsigned long long burn[64][4];   // rows with burn-outs in this env step: mask, sub-step bit planes 0..2
+  unsigned long long listed[64];    // cells that are (or were) on the front list
+  float base[S64_CAP];              // per listed cell: upper bound of (p_h (1+p_veg)) (1+p_den); negative =
+                                    //   dousing nearby, no cheap lower bound (unpack: fire rows; apply: ticks)
+  uint16_t list[S64_CAP];           // front cells: (row << 6) | col
+  uint32_t sched[GCA_MAX_K][12];    // per sub-step: Sburn[2] Sgrow[2] ak1[2] ak2[2] wind change step pad
+  uint4 hot;                        // current sub-step: Sburn k0, k1, k0^k1^C ; env index
+  float wind[12];                   // current sub-step: wind matrix (9 used)
+  int cnt;                          // list entries of the current pass
+  uint32_t dous_even, dous_odd;     // bit l: some doused cell within 2 rows of row 2l / 2l+1
+  uint32_t npairs;                  // draws of this env step (cost estimate)
+};
+
+struct __align__(16) CtaSmem {
+  EnvSmem env[S64_E];
+  uint16_t pairs[S64_E][S64_WP];    // (env slot << 12) | (list index << 4) | direction
+  int nch[16];                      // chunks of each env in the current pass
+  int next;                         // work-item counter of the pooled phase
+  int pad[3];
 };
 
 __device__ __forceinline__ void prefetch_l1(const void* p) {
@@ -132,7 +154,7 @@ __device__ __forceinline__ void assemble_split(int mode, uint32_t w, uint32_t o0
 // (ca_alexandridis_jax.py:436-448 and :352-368).  The chain K0 -> K1 -> K2 -> K3 is sequential
 // (3K split levels, every lane pair runs it redundantly -- free in SIMT); pair 2j then derives
 // sub-step j's Sburn / Sgrow / randint keys and pair 2j+1 its wind draws (4 more levels).
-__device__ __noinline__ void key_schedule(WarpSmem& sm, const gca_params& P, const gca_inject& J, int N, int e,
+__device__ __noinline__ void key_schedule(EnvSmem& sm, const gca_params& P, const gca_inject& J, int N, int e,
                                           int lane, uint32_t& key0, uint32_t& key1, int& widx) {
   const int K = P.K, mode = P.rng_mode;
   const int pair = lane >> 1;
@@ -211,7 +233,7 @@ __device__ __noinline__ void key_schedule(WarpSmem& sm, const gca_params& P, con
 }
 
 // 9x9 fire window of cell (r, c): rows r-4..r+4 packed 3 per word (9 bits each)
-__device__ __forceinline__ void fire_window(const WarpSmem& sm, int r, int c, uint32_t& A, uint32_t& B,
+__device__ __forceinline__ void fire_window(const EnvSmem& sm, int r, int c, uint32_t& A, uint32_t& B,
                                             uint32_t& C) {
   const uint32_t* fw = sm.fire32 + r * 4 + (c >> 4);
   const int o = c & 15;
@@ -223,7 +245,7 @@ __device__ __forceinline__ void fire_window(const WarpSmem& sm, int r, int c, ui
   C = wv[6] | (wv[7] << 9) | (wv[8] << 18);
 }
 // 5x5 doused window: rows r-2..r+2, 5 bits each
-__device__ __forceinline__ uint32_t dous_window(const WarpSmem& sm, int r, int c) {
+__device__ __forceinline__ uint32_t dous_window(const EnvSmem& sm, int r, int c) {
   const uint32_t* dw = sm.dous32 + r * 4 + (c >> 4);
   const int o = (c & 15) + 2;
   uint32_t v = 0;
@@ -234,7 +256,7 @@ __device__ __forceinline__ uint32_t dous_window(const WarpSmem& sm, int r, int c
 
 // Exact (reference-order) value of (heat - dousing) (1+p_veg) (1+p_den) for one cell: row-major
 // sequential float32 sums with the accumulator starting at +0 (oracle/alexandridis.py:_window_sum).
-__device__ __noinline__ float exact_base(const WarpSmem& sm, const gca_params& P, int r, int c, float a, float b) {
+__device__ __noinline__ float exact_base(const EnvSmem& sm, const gca_params& P, int r, int c, float a, float b) {
   uint32_t A, B, C;
   fire_window(sm, r, c, A, B, C);
   const uint32_t rows3[3] = {A, B, C};
@@ -266,12 +288,12 @@ __device__ __noinline__ float exact_base(const WarpSmem& sm, const gca_params& P
 // (row 2*lane+1) into sm.list and return the total number of front cells.  The rows are first
 // re-dealt in 16-column pieces (piece p = 4*row + quarter goes to lane p % 32) so that a long
 // horizontal run of front cells -- the top/bottom edge of a burning blob -- is shared by several
-// lanes instead of serialising one.
-__device__ __noinline__ int build_front_list(WarpSmem& sm, unsigned long long fr0, unsigned long long fr1,
-                                             int lane, int pass_base) {
-  reinterpret_cast<ulonglong2*>(sm.pairs)[lane] = make_ulonglong2(fr0, fr1);
+// lanes instead of serialising one.  `scratch` = 512 bytes private to the warp.
+__device__ __noinline__ int build_front_list(EnvSmem& sm, uint16_t* scratch, unsigned long long fr0,
+                                             unsigned long long fr1, int lane, int pass_base) {
+  reinterpret_cast<ulonglong2*>(scratch)[lane] = make_ulonglong2(fr0, fr1);
   __syncwarp();
-  const uint16_t* q16 = reinterpret_cast<const uint16_t*>(sm.pairs);
+  const uint16_t* q16 = scratch;
   // this lane's 8 pieces as two 64-bit words: bit 16*k + b of word h <-> piece (4h + k), column bit b
   unsigned long long w[2];
 #pragma unroll
@@ -307,7 +329,7 @@ __device__ __noinline__ int build_front_list(WarpSmem& sm, unsigned long long fr
 
 // Touch the hidden byte and the 32-byte slope-factor sector of listed front cells [from, to) so
 // that they are in L2 (and, capacity permitting, L1) when the cell and draw phases ask for them.
-__device__ __forceinline__ void prefetch_front(const WarpSmem& sm, const uint8_t* hidden, const float* pslope,
+__device__ __forceinline__ void prefetch_front(const EnvSmem& sm, const uint8_t* hidden, const float* pslope,
                                                size_t cell_base, int from, int to, int lane) {
   if (hidden == nullptr) return;
   for (int t = from + lane; t < to; t += 32) {
@@ -317,41 +339,45 @@ __device__ __forceinline__ void prefetch_front(const WarpSmem& sm, const uint8_t
   }
 }
 
-// One buffered (front cell, burning direction) draw: returns whether it ignites the cell.
-__device__ __forceinline__ bool eval_pair(const WarpSmem& sm, const gca_params& P, const uint8_t* hidden,
-                                          const float* pslope, const float* j_u_burn, int mode, const TfKey& kburn,
-                                          float windreg, size_t cell_base, size_t inj_base, int q, int PT,
-                                          uint32_t& cell_out, uint32_t& n_thresh) {
-  const bool valid = q < PT;
-  const uint32_t ent = valid ? sm.pairs[q] : 0u;
-  const int t = ent >> 4, d = ent & 15;
-  const uint32_t cell = sm.list[t];
-  cell_out = cell;
+// One buffered (front cell, burning direction) draw of ANY env of the CTA; ignitions are or-ed into
+// that env's accumulator.
+__device__ __forceinline__ void eval_pair(CtaSmem& cs, const gca_params& P, const uint8_t* hidden,
+                                          const float* pslope, const float* j_u_burn, int mode, size_t inj_stride,
+                                          int j, uint32_t ent, bool valid, uint32_t& n_thresh) {
+  EnvSmem& es = cs.env[ent >> 12];
+  const int t = (ent >> 4) & 255, d = ent & 15;
+  const uint32_t cell = es.list[t];
+  const uint4 hot = es.hot;
+  const size_t cell_base = (size_t)hot.w * 4096;
   float s = 1.0f;
   if (pslope != nullptr && valid) s = pslope[(cell_base + cell) * 8 + dir_slot(d)];
   float u;
   if (j_u_burn) {
-    u = valid ? j_u_burn[(inj_base + cell) * 9 + d] : 1.0f;
+    u = valid ? j_u_burn[((size_t)j * inj_stride + cell_base + cell) * 9 + d] : 1.0f;
   } else {
-    u = bits_to_uniform(bits_at(kburn, cell * 9u + (uint32_t)d, S64_HALF_BURN, mode));
+    TfKey kb;
+    kb.k0 = hot.x; kb.k1 = hot.y; kb.k2 = hot.z;
+    u = bits_to_uniform(bits_at(kb, cell * 9u + (uint32_t)d, S64_HALF_BURN, mode));
   }
-  const float w = __shfl_sync(GCA_FULL, windreg, d);
-  const float plo = __fmul_rn(__fmul_rn(sm.base_lo[t], w), s);
-  const float phi = __fmul_rn(__fmul_rn(sm.base_hi[t], w), s);
-  bool ig = valid && (u < plo);
-  if (valid && !ig && (u < phi)) {
-    // threshold cell: the float32 enclosure cannot decide -> reference-order evaluation
-    const int r = cell >> 6, c = cell & 63;
-    int hid = 3 | (3 << 3);
-    if (hidden != nullptr) hid = hidden[cell_base + cell];
-    const float a = P.onep_veg[clip15(hid & 7)];
-    const float b = P.onep_den[clip15((hid >> 3) & 7)];
-    const float base = exact_base(sm, P, r, c, a, b);
-    const float p = __fmul_rn(__fmul_rn(base, w), s);
-    ig = u < p;
-    n_thresh++;
+  const float bs = es.base[t];
+  const float w = es.wind[d];
+  const float phi = __fmul_rn(__fmul_rn(fabsf(bs), w), s);
+  if (valid && u < phi) {
+    bool ig = bs > 0.0f && u < __fmul_rn(phi, S64_SURE);
+    if (!ig) {
+      // threshold cell: the float32 enclosure cannot decide -> reference-order evaluation
+      const int r = cell >> 6, c = cell & 63;
+      int hid = 3 | (3 << 3);
+      if (hidden != nullptr) hid = hidden[cell_base + cell];
+      const float a = P.onep_veg[clip15(hid & 7)];
+      const float b = P.onep_den[clip15((hid >> 3) & 7)];
+      const float base = exact_base(es, P, r, c, a, b);
+      const float p = __fmul_rn(__fmul_rn(base, w), s);
+      ig = u < p;
+      n_thresh++;
+    }
+    if (ig) atomicOr(reinterpret_cast<uint32_t*>(es.ign) + (cell >> 5), 1u << (cell & 31));
   }
-  return ig;
 }
 
 // empty -> tree with probability p_tree (0 in the reference env, so this is a cold path): a dense
@@ -389,25 +415,28 @@ __device__ __forceinline__ void front_masks(unsigned long long t0, unsigned long
 }
 
 #ifndef S64_MINB
-#define S64_MINB (28 / S64_WARPS)  // 28 warps/SM x 72 registers = the whole register file; 4096 envs = one wave
+#define S64_MINB (28 / S64_E)  // 28 warps/SM x 72 registers = the whole register file; 4096 envs = one wave
 #endif
 // MODE: GCA_RNG_* or -1 (read P.rng_mode); HP: 0 = no hidden layers, 1 = hidden + slope table present,
 // -1 = test the pointers at run time; INJ: injected random fields may be present.  The launcher picks
 // a fully specialised instance for the production cases and the generic one otherwise.
 template <int MODE, int HP, bool INJ>
-__global__ void __launch_bounds__(S64_WARPS * 32, S64_MINB)
+__global__ void __launch_bounds__(S64_E * 32, S64_MINB)
 env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gca_state S,
                   const int32_t* __restrict__ actions, const __grid_constant__ gca_step_out O,
                   const __grid_constant__ gca_inject J, const __grid_constant__ gca_state SNAP,
                   const float* __restrict__ snap_reward, uint32_t flags) {
-  __shared__ WarpSmem smem_all[S64_WARPS];
+  extern __shared__ __align__(16) unsigned char s64_smem_raw[];
+  CtaSmem& cs = *reinterpret_cast<CtaSmem*>(s64_smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot = blockIdx.x * S64_WARPS + warp;
+  const long long clk0 = clock64();
+  const int slot = blockIdx.x * S64_E + warp;
   const int N = S.N;
-  if (slot >= N) return;
-  // optional load-balancing indirection (gca_balance_order): which env this warp steps
-  const int e = S.order != nullptr ? S.order[slot] : slot;
-  WarpSmem& sm = smem_all[warp];
+  const bool active = slot < N;   // a warp without an env still joins the barriers and the pooled work
+  // optional load-balancing indirection (gca_balance_order): which env this warp owns
+  const int e = active ? (S.order != nullptr ? S.order[slot] : slot) : 0;
+  EnvSmem& sm = cs.env[warp];
+  uint16_t* const wp = cs.pairs[warp];
   const int K = P.K, mode = MODE < 0 ? P.rng_mode : MODE;
   const size_t cell_base = (size_t)e * 4096;
   const uint8_t* const hidden = HP == 0 ? nullptr : S.hidden;
@@ -416,341 +445,426 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   const float* const j_u_burn = INJ ? J.u_burn : nullptr;
   const int32_t* const j_age_new = INJ ? J.age_new : nullptr;
 
-  // ---- coalesced 128-bit read of the u8 grid -> tree / fire row masks ---------------------------
-  unsigned long long t0, t1, f0, f1;
-  {
-    uint4 cv[8];
-    const uint4* cptr = reinterpret_cast<const uint4*>(S.cell + cell_base);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) cv[i] = cptr[i * 32 + lane];
-    uint16_t* trow = reinterpret_cast<uint16_t*>(sm.ign);
-    uint16_t* frow = reinterpret_cast<uint16_t*>(sm.base_lo);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      uint32_t t16, f16;
-      cells16_to_bits(cv[i], t16, f16);
-      const int chunk = i * 32 + lane;  // row = chunk >> 2, quarter = chunk & 3
-      trow[chunk] = (uint16_t)t16;
-      frow[chunk] = (uint16_t)f16;
-    }
-  }
-  const ulonglong2 dz = reinterpret_cast<const ulonglong2*>(S.doused + (size_t)e * 64)[lane];
-  uint2 rm = reinterpret_cast<const uint2*>(S.row_min + (size_t)e * 64)[lane];
-  const uint32_t tick0 = S.tick[e];
-  uint32_t key0 = S.key[2 * e], key1 = S.key[2 * e + 1];
-  int widx = S.wind_index[e];
-  if (!(flags & GCA_FLAG_CA_ONLY)) {
-    // the per-env scalars of the epilogue (lane 0, serial): get their lines on the way now
-    const void* pf = nullptr;
-    switch (lane) {
-      case 0: pf = actions + 3 * e; break;
-      case 1: pf = S.time + e; break;
-      case 2: pf = S.position + 2 * e; break;
-      case 3: pf = S.time_step + e; break;
-      case 4: pf = S.is_night + e; break;
-      case 5: pf = S.steps_elapsed ? S.steps_elapsed + e : nullptr; break;
-      case 6: pf = S.reward_accumulated ? S.reward_accumulated + e : nullptr; break;
-      default: break;
-    }
-    if (pf != nullptr) prefetch_l1(pf);
-  }
-  if (lane < 16) sm.fire32[lane] = 0u; else sm.fire32[272 + lane - 16] = 0u;   // fire rows -4..-1, 64..67
-  if (lane < 8) sm.dous32[lane] = 0u; else if (lane < 16) sm.dous32[264 + lane - 8] = 0u;  // rows -2,-1,64,65
-  store_row_views(sm.dous32 + (2 * lane + 2) * 4, dz.x);
-  store_row_views(sm.dous32 + (2 * lane + 3) * 4, dz.y);
-  __syncwarp();
-  {
-    const ulonglong2 tt = reinterpret_cast<const ulonglong2*>(sm.ign)[lane];
-    const ulonglong2 ff = reinterpret_cast<const ulonglong2*>(sm.base_lo)[lane];
-    t0 = tt.x; t1 = tt.y; f0 = ff.x; f1 = ff.y;
-  }
-  __syncwarp();
-  sm.ign[2 * lane] = 0ull;
-  sm.ign[2 * lane + 1] = 0ull;
+  unsigned long long t0 = 0, t1 = 0, f0 = 0, f1 = 0;
   unsigned long long ch0 = 0ull, ch1 = 0ull;  // cells whose state changed during this env step
-  store_row_views(sm.fire32 + (2 * lane + 4) * 4, f0);
-  store_row_views(sm.fire32 + (2 * lane + 5) * 4, f1);
+  uint2 rm = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+  uint32_t tick0 = 0, key0 = 0, key1 = 0;
+  int widx = 0;
+  uint32_t burnrows = 0;  // bit 0 / 1: row 2*lane / 2*lane+1 has burn-outs in this env step (sm.burn valid)
+  int T = 0, L = 0;
+  bool dense = false;
+  uint32_t n_draws = 0, n_thresh = 0, n_front = 0, n_ign = 0, n_ext = 0;
+  uint32_t work = 0;  // warp-uniform cost estimate of this env step (front cells; draws are added at the end)
 
-  // ---- rows holding a cell that burns out during this env step -----------------------------------
-  unsigned long long die0 = 0, die1 = 0, pl0[3] = {0, 0, 0}, pl1[3] = {0, 0, 0};
-  {
-    const bool need0 = f0 != 0ull && rm.x < tick0 + (uint32_t)K;
-    const bool need1 = f1 != 0ull && rm.y < tick0 + (uint32_t)K;
-    // each flagged row is one 128-byte line of burn-out ticks: request them all now, the serial
-    // row loop below then hits L1/L2 instead of paying one DRAM round trip per row
-    if (need0) prefetch_l1(S.death + cell_base + (2 * lane) * 64);
-    if (need1) prefetch_l1(S.death + cell_base + (2 * lane + 1) * 64);
-    uint32_t m0 = __ballot_sync(GCA_FULL, need0);
-    uint32_t m1 = __ballot_sync(GCA_FULL, need1);
-    while (m0 | m1) {
-      int src;
-      bool second;
-      if (m0) { src = __ffs(m0) - 1; m0 &= m0 - 1; second = false; }
-      else { src = __ffs(m1) - 1; m1 &= m1 - 1; second = true; }
-      const int row = 2 * src + (second ? 1 : 0);
-      const unsigned long long fr = shfl64(second ? f1 : f0, src);
-      uint16_t* dp = S.death + cell_base + row * 64;
-      const uint32_t da = dp[lane], db = dp[lane + 32];
-      const bool fa = (fr >> lane) & 1ull, fb = (fr >> (lane + 32)) & 1ull;
-      const uint32_t ra = (da - tick0) & 0xFFFFu, rb = (db - tick0) & 0xFFFFu;
-      const bool xa = fa && ra < (uint32_t)K, xb = fb && rb < (uint32_t)K;
-      const unsigned long long dmask =
-          (unsigned long long)__ballot_sync(GCA_FULL, xa) | ((unsigned long long)__ballot_sync(GCA_FULL, xb) << 32);
-      unsigned long long pm[3];
+  if (active) {
+    // ---- coalesced 128-bit read of the u8 grid -> tree / fire row masks -------------------------
+    {
+      uint4 cv[8];
+      const uint4* cptr = reinterpret_cast<const uint4*>(S.cell + cell_base);
 #pragma unroll
-      for (int b = 0; b < 3; ++b)
-        pm[b] = (unsigned long long)__ballot_sync(GCA_FULL, xa && ((ra >> b) & 1u)) |
-                ((unsigned long long)__ballot_sync(GCA_FULL, xb && ((rb >> b) & 1u)) << 32);
-      uint32_t v = 0xFFFFFFFFu;
-      if (fa && !xa) v = tick0 + ra;
-      if (fb && !xb) v = min(v, tick0 + rb);
-      const uint32_t newmin = __reduce_min_sync(GCA_FULL, v);
-      if (xa) dp[lane] = 0;        // burnt-out cell: fire_age ends at 0
-      if (xb) dp[lane + 32] = 0;
-      if (lane == src) {
-        if (second) { die1 = dmask; pl1[0] = pm[0]; pl1[1] = pm[1]; pl1[2] = pm[2]; rm.y = newmin; }
-        else { die0 = dmask; pl0[0] = pm[0]; pl0[1] = pm[1]; pl0[2] = pm[2]; rm.x = newmin; }
+      for (int i = 0; i < 8; ++i) cv[i] = cptr[i * 32 + lane];
+      uint16_t* trow = reinterpret_cast<uint16_t*>(sm.ign);
+      uint16_t* frow = reinterpret_cast<uint16_t*>(sm.base);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint32_t t16, f16;
+        cells16_to_bits(cv[i], t16, f16);
+        const int chunk = i * 32 + lane;  // row = chunk >> 2, quarter = chunk & 3
+        trow[chunk] = (uint16_t)t16;
+        frow[chunk] = (uint16_t)f16;
       }
     }
+    const ulonglong2 dz = reinterpret_cast<const ulonglong2*>(S.doused + (size_t)e * 64)[lane];
+    rm = reinterpret_cast<const uint2*>(S.row_min + (size_t)e * 64)[lane];
+    tick0 = S.tick[e];
+    key0 = S.key[2 * e];
+    key1 = S.key[2 * e + 1];
+    widx = S.wind_index[e];
+    if (!(flags & GCA_FLAG_CA_ONLY)) {
+      // the per-env scalars of the epilogue (lane 0, serial): get their lines on the way now
+      const void* pf = nullptr;
+      switch (lane) {
+        case 0: pf = actions + 3 * e; break;
+        case 1: pf = S.time + e; break;
+        case 2: pf = S.position + 2 * e; break;
+        case 3: pf = S.time_step + e; break;
+        case 4: pf = S.is_night + e; break;
+        case 5: pf = S.steps_elapsed ? S.steps_elapsed + e : nullptr; break;
+        case 6: pf = S.reward_accumulated ? S.reward_accumulated + e : nullptr; break;
+        default: break;
+      }
+      if (pf != nullptr) prefetch_l1(pf);
+    }
+    if (lane < 16) sm.fire32[lane] = 0u; else sm.fire32[272 + lane - 16] = 0u;   // fire rows -4..-1, 64..67
+    if (lane < 8) sm.dous32[lane] = 0u; else if (lane < 16) sm.dous32[264 + lane - 8] = 0u;  // rows -2,-1,64,65
+    store_row_views(sm.dous32 + (2 * lane + 2) * 4, dz.x);
+    store_row_views(sm.dous32 + (2 * lane + 3) * 4, dz.y);
+    {
+      // which rows have a doused cell within the 5x5 dousing window's reach (2 rows up / down)
+      const uint32_t ev = __ballot_sync(GCA_FULL, dz.x != 0ull), od = __ballot_sync(GCA_FULL, dz.y != 0ull);
+      if (lane == 0) {
+        sm.dous_even = ev | (ev << 1) | (ev >> 1) | od | (od << 1);
+        sm.dous_odd = od | (od << 1) | (od >> 1) | ev | (ev >> 1);
+        sm.npairs = 0u;
+      }
+    }
+    __syncwarp();
+    {
+      const ulonglong2 tt = reinterpret_cast<const ulonglong2*>(sm.ign)[lane];
+      const ulonglong2 ff = reinterpret_cast<const ulonglong2*>(sm.base)[lane];
+      t0 = tt.x; t1 = tt.y; f0 = ff.x; f1 = ff.y;
+    }
+    __syncwarp();
+    sm.ign[2 * lane] = 0ull;
+    sm.ign[2 * lane + 1] = 0ull;
+    store_row_views(sm.fire32 + (2 * lane + 4) * 4, f0);
+    store_row_views(sm.fire32 + (2 * lane + 5) * 4, f1);
+
+    // ---- rows holding a cell that burns out during this env step ---------------------------------
+    {
+      const bool need0 = f0 != 0ull && rm.x < tick0 + (uint32_t)K;
+      const bool need1 = f1 != 0ull && rm.y < tick0 + (uint32_t)K;
+      burnrows = (need0 ? 1u : 0u) | (need1 ? 2u : 0u);
+      // each flagged row is one 128-byte line of burn-out ticks: request them all now, the serial
+      // row loop below then hits L1/L2 instead of paying one DRAM round trip per row
+      if (need0) prefetch_l1(S.death + cell_base + (2 * lane) * 64);
+      if (need1) prefetch_l1(S.death + cell_base + (2 * lane + 1) * 64);
+      uint32_t m0 = __ballot_sync(GCA_FULL, need0);
+      uint32_t m1 = __ballot_sync(GCA_FULL, need1);
+      while (m0 | m1) {
+        int src;
+        bool second;
+        if (m0) { src = __ffs(m0) - 1; m0 &= m0 - 1; second = false; }
+        else { src = __ffs(m1) - 1; m1 &= m1 - 1; second = true; }
+        const int row = 2 * src + (second ? 1 : 0);
+        const unsigned long long fr = shfl64(second ? f1 : f0, src);
+        uint16_t* dp = S.death + cell_base + row * 64;
+        const uint32_t da = dp[lane], db = dp[lane + 32];
+        const bool fa = (fr >> lane) & 1ull, fb = (fr >> (lane + 32)) & 1ull;
+        const uint32_t ra = (da - tick0) & 0xFFFFu, rb = (db - tick0) & 0xFFFFu;
+        const bool xa = fa && ra < (uint32_t)K, xb = fb && rb < (uint32_t)K;
+        const unsigned long long dmask =
+            (unsigned long long)__ballot_sync(GCA_FULL, xa) | ((unsigned long long)__ballot_sync(GCA_FULL, xb) << 32);
+        unsigned long long pm[3];
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+          pm[b] = (unsigned long long)__ballot_sync(GCA_FULL, xa && ((ra >> b) & 1u)) |
+                  ((unsigned long long)__ballot_sync(GCA_FULL, xb && ((rb >> b) & 1u)) << 32);
+        uint32_t v = 0xFFFFFFFFu;
+        if (fa && !xa) v = tick0 + ra;
+        if (fb && !xb) v = min(v, tick0 + rb);
+        const uint32_t newmin = __reduce_min_sync(GCA_FULL, v);
+        if (xa) dp[lane] = 0;        // burnt-out cell: fire_age ends at 0
+        if (xb) dp[lane + 32] = 0;
+        if (lane == 0) {
+          reinterpret_cast<ulonglong2*>(sm.burn[row])[0] = make_ulonglong2(dmask, pm[0]);
+          reinterpret_cast<ulonglong2*>(sm.burn[row])[1] = make_ulonglong2(pm[1], pm[2]);
+        }
+        if (lane == src) {
+          if (second) rm.y = newmin; else rm.x = newmin;
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- front of sub-step 0: compact it and start fetching its hidden / slope-factor sectors so
+    //      that their DRAM latency hides behind the key schedule.  The list is built ONCE per env
+    //      step; later sub-steps append the cells that joined the front (a handful); entries that
+    //      left it (ignited / no burning neighbour left) are recognised from their fire window.
+    {
+      unsigned long long fr0, fr1;
+      front_masks(t0, t1, f0, f1, lane, fr0, fr1);
+      T = build_front_list(sm, wp, fr0, fr1, lane, 0);
+      dense = T > S64_CAP;  // more front cells than the list holds: rebuild per sub-step, in passes
+      L = min(T, S64_CAP);
+      prefetch_front(sm, hidden, pslope, cell_base, 0, L, lane);
+      sm.listed[2 * lane] = fr0;
+      sm.listed[2 * lane + 1] = fr1;
+      n_front += (uint32_t)(__popcll(fr0) + __popcll(fr1));
+    }
+    key_schedule(sm, P, J, N, e, lane, key0, key1, widx);
+    if (lane == 0) {
+      S.key[2 * e] = key0;
+      S.key[2 * e + 1] = key1;
+      S.wind_index[e] = widx;
+    }
   }
-  __syncwarp();
-
-  // ---- front of sub-step 0: compact it and start fetching its hidden / slope-factor sectors so
-  //      that their DRAM latency hides behind the key schedule.  The list is built ONCE per env
-  //      step; later sub-steps append the cells that joined the front (a handful) and skip the
-  //      entries that left it (ignited / no burning neighbour left) with a front bit-board test.
-  unsigned long long fr0, fr1;
-  front_masks(t0, t1, f0, f1, lane, fr0, fr1);
-  int T = build_front_list(sm, fr0, fr1, lane, 0);
-  bool dense = T > S64_CAP;  // more front cells than the list holds: rebuild per sub-step, in passes
-  int L = min(T, S64_CAP);
-  prefetch_front(sm, hidden, pslope, cell_base, 0, L, lane);
-  unsigned long long listed0 = fr0, listed1 = fr1;
-
-  key_schedule(sm, P, J, N, e, lane, key0, key1, widx);
 
   const float lutreg = lane < 8 ? P.onep_veg[lane] : (lane < 16 ? P.onep_den[lane - 8] : 0.0f);
-  uint32_t n_draws = 0, n_thresh = 0, n_front = 0, n_ign = 0, n_ext = 0;
-  uint32_t work = 0;  // warp-uniform cost estimate of this env step (front cells and draws)
   const float w1 = P.ring_w[1], w2 = P.ring_w[2], w3 = P.ring_w[3], w4 = P.ring_w[4];
   const uint32_t age_magic = 0xFFFFFFFFu / P.age_span;
-  const bool any_doused = __ballot_sync(GCA_FULL, (dz.x | dz.y) != 0ull) != 0u;
-  const uint32_t* front32 = reinterpret_cast<const uint32_t*>(sm.frontbb);
-  uint32_t* ign32 = reinterpret_cast<uint32_t*>(sm.ign);
 
   // ================================ K CA sub-steps, all on-chip ===================================
   for (int j = 0; j < K; ++j) {
-    const uint32_t* sc = sm.sched[j];
-    const TfKey kburn = tf_key(sc[0], sc[1]);
-    const size_t inj_base = ((size_t)j * N + e) * 4096;
-    const float windreg = lane < 9 ? P.winds[(int)sc[8] * 9 + lane] : 0.0f;
-    if (j > 0) {
-      front_masks(t0, t1, f0, f1, lane, fr0, fr1);
-      if (!dense) {
-        const unsigned long long nw0 = fr0 & ~listed0, nw1 = fr1 & ~listed1;
-        const int nn = __popcll(nw0) + __popcll(nw1);
-        const int incl_n = warp_incl_scan(nn, lane);
-        const int tot_n = __shfl_sync(GCA_FULL, incl_n, 31);
-        if (L + tot_n > S64_CAP) {
-          dense = true;
-        } else if (tot_n > 0) {
-          int idx = L + incl_n - nn;
-          unsigned long long m = nw0;
-          int rowbits = (2 * lane) << 6;
+    if (active) {
+      const uint32_t* sc = sm.sched[j];
+      if (j > 0) {
+        unsigned long long fr0, fr1;
+        front_masks(t0, t1, f0, f1, lane, fr0, fr1);
+        n_front += (uint32_t)(__popcll(fr0) + __popcll(fr1));
+        if (!dense) {
+          const unsigned long long listed0 = sm.listed[2 * lane], listed1 = sm.listed[2 * lane + 1];
+          const unsigned long long nw0 = fr0 & ~listed0, nw1 = fr1 & ~listed1;
+          const int nn = __popcll(nw0) + __popcll(nw1);
+          const int incl_n = warp_incl_scan(nn, lane);
+          const int tot_n = __shfl_sync(GCA_FULL, incl_n, 31);
+          if (L + tot_n > S64_CAP) {
+            dense = true;
+          } else if (tot_n > 0) {
+            int idx = L + incl_n - nn;
+            unsigned long long m = nw0;
+            int rowbits = (2 * lane) << 6;
 #pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
-            while (m) {
-              const uint32_t cell = (uint32_t)(rowbits | (__ffsll((long long)m) - 1));
-              m &= m - 1;
-              sm.list[idx++] = (uint16_t)cell;
-              if (hidden != nullptr) {
-                prefetch_l1(hidden + cell_base + cell);
-                if (pslope != nullptr) prefetch_l1(pslope + (cell_base + cell) * 8);
+            for (int half = 0; half < 2; ++half) {
+              while (m) {
+                const uint32_t cell = (uint32_t)(rowbits | (__ffsll((long long)m) - 1));
+                m &= m - 1;
+                sm.list[idx++] = (uint16_t)cell;
+                if (hidden != nullptr) {
+                  prefetch_l1(hidden + cell_base + cell);
+                  if (pslope != nullptr) prefetch_l1(pslope + (cell_base + cell) * 8);
+                }
+              }
+              m = nw1;
+              rowbits = (2 * lane + 1) << 6;
+            }
+            L += tot_n;
+            if (nn) {
+              sm.listed[2 * lane] = listed0 | nw0;
+              sm.listed[2 * lane + 1] = listed1 | nw1;
+            }
+          }
+        }
+        if (dense) {
+          T = build_front_list(sm, wp, fr0, fr1, lane, 0);
+          prefetch_front(sm, hidden, pslope, cell_base, 0, min(T, S64_CAP), lane);
+        }
+      }
+      if (lane == 0) sm.hot = make_uint4(sc[0], sc[1], sc[0] ^ sc[1] ^ 0x1BD11BDAu, (uint32_t)e);
+      if (lane < 9) sm.wind[lane] = P.winds[(int)sc[8] * 9 + lane];
+    }
+    const int total = active ? (dense ? T : L) : 0;
+    work += 2u * (uint32_t)total;
+
+    for (int pass = 0;; ++pass) {
+      if (active) {
+        if (pass > 0 && total > pass * S64_CAP) {  // dense fires only: next slice of the list
+          unsigned long long fr0, fr1;
+          front_masks(t0, t1, f0, f1, lane, fr0, fr1);
+          build_front_list(sm, wp, fr0, fr1, lane, pass * S64_CAP);
+          prefetch_front(sm, hidden, pslope, cell_base, 0, min(S64_CAP, total - pass * S64_CAP), lane);
+        }
+      }
+      if (lane == 0) {
+        const int cnt = max(0, min(S64_CAP, total - pass * S64_CAP));
+        sm.cnt = cnt;
+        cs.nch[warp] = (cnt + 31) >> 5;
+        if (warp == 0) cs.next = 0;
+      }
+      __syncthreads();
+
+      // ---------------- pooled phase: work items = 32-entry chunks of every env's front list -------
+      {
+        const int my_n = lane < S64_E ? cs.nch[lane] : 0;
+        int incl = my_n;
+#pragma unroll
+        for (int d = 1; d < S64_E; d <<= 1) {
+          const int o = __shfl_up_sync(GCA_FULL, incl, d);
+          if (lane >= d) incl += o;
+        }
+        const int M = __shfl_sync(GCA_FULL, incl, S64_E - 1);
+        int PT = 0;
+        bool more_items = M > 0;
+#ifdef S64_STATIC_ITEMS
+        int next_item = warp;
+#endif
+        for (;;) {
+          if (PT < 64 && more_items) {
+#ifdef S64_STATIC_ITEMS
+            const int item = next_item;
+            next_item += S64_E;
+#else
+            int item = 0;
+            if (lane == 0) item = atomicAdd(&cs.next, 1);
+            item = __shfl_sync(GCA_FULL, item, 0);
+#endif
+            if (item >= M) { more_items = false; continue; }
+            const int es_slot = __popc(__ballot_sync(GCA_FULL, lane < S64_E && incl <= item));
+            const int chunk = item - __shfl_sync(GCA_FULL, incl - my_n, es_slot);
+            EnvSmem& es = cs.env[es_slot];
+            const int t = chunk * 32 + lane;
+            const bool inrange = t < es.cnt;
+            const uint32_t cell = inrange ? es.list[t] : 0u;
+            const int r = cell >> 6, c = cell & 63;
+            uint32_t A, B, C;
+            fire_window(es, r, c, A, B, C);
+            uint32_t dirm = ((B >> 3) & 7u) | (((B >> 12) & 7u) << 3) | (((B >> 21) & 7u) << 6);
+            // still a front cell in this sub-step?  (a listed tree leaves the front by igniting -- its own
+            // fire bit is then set -- or by losing its last burning neighbour)
+            const bool valid = inrange && !(dirm & 16u) && (dirm & ~16u) != 0u;
+            dirm &= ~16u;
+            int hid = 3 | (3 << 3);
+            if (hidden != nullptr && valid) hid = hidden[(size_t)es.hot.w * 4096 + cell];
+            // ring populations (Chebyshev rings 1..4 around the centre)
+            const int S1 = __popc(B & 0x00E07038u);
+            const int S2 = __popc(A & (0x07Cu << 18)) + __popc(B & 0x01F0F87Cu) + __popc(C & 0x07Cu);
+            const int S3 = __popc(A & ((0x0FEu << 9) | (0x0FEu << 18))) + __popc(B & 0x03F9FCFEu) +
+                           __popc(C & (0x0FEu | (0x0FEu << 9)));
+            const int S4 = __popc(A) + __popc(B) + __popc(C);
+            const float Hf = fmaf((float)(S4 - S3), w4,
+                                  fmaf((float)(S3 - S2), w3, fmaf((float)(S2 - S1), w2, (float)S1 * w1)));
+            float Dlo = 0.0f;
+            bool near_doused = false;
+            if ((((r & 1) ? es.dous_odd : es.dous_even) >> (r >> 1)) & 1u) {
+              const uint32_t dwin = dous_window(es, r, c);
+              if (dwin) {
+                const int ni = __popc(dwin & ((0x0Eu << 5) | (0x0Eu << 10) | (0x0Eu << 15)));
+                const int nb = __popc(dwin) - ni;
+                const float Df = fmaf((float)nb, P.dous_border, (float)ni * P.dous_inner);
+                Dlo = __fmul_rn(Df, S64_LO);
+                near_doused = true;
               }
             }
-            m = nw1;
-            rowbits = (2 * lane + 1) << 6;
-          }
-          L += tot_n;
-          listed0 |= nw0;
-          listed1 |= nw1;
-        }
-      }
-      if (dense) {
-        T = build_front_list(sm, fr0, fr1, lane, 0);
-        prefetch_front(sm, hidden, pslope, cell_base, 0, min(T, S64_CAP), lane);
-      }
-    }
-    sm.frontbb[2 * lane] = fr0;
-    sm.frontbb[2 * lane + 1] = fr1;
-    n_front += (uint32_t)(__popcll(fr0) + __popcll(fr1));
-    __syncwarp();
-
-    const int total = dense ? T : L;
-    work += 2u * (uint32_t)total;
-    for (int pass_base = 0; pass_base < total; pass_base += S64_CAP) {
-      if (pass_base > 0) {  // dense fires only: next slice of the list
-        build_front_list(sm, fr0, fr1, lane, pass_base);
-        prefetch_front(sm, hidden, pslope, cell_base, 0, min(S64_CAP, total - pass_base), lane);
-      }
-      const int cnt = min(S64_CAP, total - pass_base);
-      int PT = 0;
-      for (int base = 0; base < cnt; base += 32) {
-        const int t = base + lane;
-        const bool inrange = t < cnt;
-        const uint32_t cell = inrange ? sm.list[t] : 0u;
-        const int r = cell >> 6, c = cell & 63;
-        // still a front cell in this sub-step?
-        const bool valid = inrange && ((front32[cell >> 5] >> (cell & 31)) & 1u);
-        int hid = 3 | (3 << 3);
-        if (hidden != nullptr && valid) hid = hidden[cell_base + cell];
-        uint32_t A, B, C;
-        fire_window(sm, r, c, A, B, C);
-        // ring populations (Chebyshev rings 1..4 around the centre)
-        const int S1 = __popc(B & 0x00E07038u);
-        const int S2 = __popc(A & (0x07Cu << 18)) + __popc(B & 0x01F0F87Cu) + __popc(C & 0x07Cu);
-        const int S3 = __popc(A & ((0x0FEu << 9) | (0x0FEu << 18))) + __popc(B & 0x03F9FCFEu) +
-                       __popc(C & (0x0FEu | (0x0FEu << 9)));
-        const int S4 = __popc(A) + __popc(B) + __popc(C);
-        const float Hf = fmaf((float)(S4 - S3), w4,
-                              fmaf((float)(S3 - S2), w3, fmaf((float)(S2 - S1), w2, (float)S1 * w1)));
-        uint32_t dirm = ((B >> 3) & 7u) | (((B >> 12) & 7u) << 3) | (((B >> 21) & 7u) << 6);
-        dirm &= ~(1u << 4);
-        float Dlo = 0.0f, Dhi = 0.0f;
-        if (any_doused) {
-          const uint32_t dwin = dous_window(sm, r, c);
-          if (dwin) {
-            const int ni = __popc(dwin & ((0x0Eu << 5) | (0x0Eu << 10) | (0x0Eu << 15)));
-            const int nb = __popc(dwin) - ni;
-            const float Df = fmaf((float)nb, P.dous_border, (float)ni * P.dous_inner);
-            Dlo = __fmul_rn(Df, S64_LO);
-            Dhi = __fmul_rn(Df, S64_HI);
-          }
-        }
-        const float a = __shfl_sync(GCA_FULL, lutreg, clip15(hid & 7));
-        const float b = __shfl_sync(GCA_FULL, lutreg, 8 + clip15((hid >> 3) & 7));
-        const float ph_lo = __fsub_rn(__fmul_rn(Hf, S64_LO), Dhi);
-        const float ph_hi = __fsub_rn(__fmul_rn(Hf, S64_HI), Dlo);
-        const float blo = __fmul_rn(__fmul_rn(ph_lo, a), b);
-        const float bhi = __fmul_rn(__fmul_rn(ph_hi, a), b);
-        if (valid) { sm.base_lo[t] = blo; sm.base_hi[t] = bhi; }
-        const int nd = (valid && bhi > 0.0f) ? __popc(dirm) : 0;
-        const int incl2 = warp_incl_scan(nd, lane);
-        int off = PT + incl2 - nd;
-        const uint32_t em = nd ? dirm : 0u;
-        const uint32_t tag = (uint32_t)t << 4;
+            const float a = __shfl_sync(GCA_FULL, lutreg, clip15(hid & 7));
+            const float b = __shfl_sync(GCA_FULL, lutreg, 8 + clip15((hid >> 3) & 7));
+            const float ph_hi = __fsub_rn(__fmul_rn(Hf, S64_HI), Dlo);
+            const float bhi = __fmul_rn(__fmul_rn(ph_hi, a), b);
+            if (valid) es.base[t] = near_doused ? -bhi : bhi;
+            const int nd = (valid && bhi > 0.0f) ? __popc(dirm) : 0;
+            const int incl2 = warp_incl_scan(nd, lane);
+            int off = PT + incl2 - nd;
+            const uint32_t em = nd ? dirm : 0u;
+            const uint32_t tag = ((uint32_t)es_slot << 12) | ((uint32_t)t << 4);
 #pragma unroll
-        for (uint32_t d = 0; d < 9; ++d) {
-          if (d == 4) continue;
-          if (em & (1u << d)) sm.pairs[off++] = (uint16_t)(tag | d);
-        }
-        PT += __shfl_sync(GCA_FULL, incl2, 31);
-
-        // ---- draw phase (single call site): when the buffer could overflow next round, or at the
-        //      end of the pass.  Two draws per lane per iteration = two independent threefry chains.
-        if (PT + 256 > S64_PCAP || base + 32 >= cnt) {
-          __syncwarp();
-          for (int q0 = 0; q0 < PT; q0 += 64) {
-            uint32_t ca, cb = 0;
-            const bool ia = eval_pair(sm, P, hidden, pslope, j_u_burn, mode, kburn, windreg, cell_base, inj_base,
-                                      q0 + lane, PT, ca, n_thresh);
-            bool ib = false;
-            if (q0 + 32 < PT)
-              ib = eval_pair(sm, P, hidden, pslope, j_u_burn, mode, kburn, windreg, cell_base, inj_base,
-                             q0 + 32 + lane, PT, cb, n_thresh);
-            if (ia) atomicOr(&ign32[ca >> 5], 1u << (ca & 31));
-            if (ib) atomicOr(&ign32[cb >> 5], 1u << (cb & 31));
+            for (uint32_t d = 0; d < 9; ++d) {
+              if (d == 4) continue;
+              if (em & (1u << d)) wp[off++] = (uint16_t)(tag | d);
+            }
+            if (lane == 31 && incl2) atomicAdd(&es.npairs, (uint32_t)incl2);
+            PT += __shfl_sync(GCA_FULL, incl2, 31);
+            __syncwarp();
+            continue;
           }
-          n_draws += (lane == 0) ? (uint32_t)PT : 0u;
-          work += (uint32_t)PT;
-          PT = 0;
+          if (PT == 0) break;
+          // ---- draw up to 64 buffered pairs: two per lane = two independent threefry chains --------
+          const int n = min(PT, 64);
+          PT -= n;
+          n_draws += (lane == 0) ? (uint32_t)n : 0u;
+          const uint16_t* q = wp + PT;
+          const bool va = lane < n, vb = lane + 32 < n;
+          const uint32_t ea = va ? q[lane] : 0u;
+          eval_pair(cs, P, hidden, pslope, j_u_burn, mode, (size_t)N * 4096, j, ea, va, n_thresh);
+          if (n > 32) {
+            const uint32_t eb = vb ? q[lane + 32] : 0u;
+            eval_pair(cs, P, hidden, pslope, j_u_burn, mode, (size_t)N * 4096, j, eb, vb, n_thresh);
+          }
           __syncwarp();
         }
       }
+      const int more = __syncthreads_or(total > (pass + 1) * S64_CAP);
+      if (!more) break;
     }
-    __syncwarp();
 
     // ---- apply: ignitions (with their fire-age draws), burn-outs, regrowth ------------------------
-    const unsigned long long I0 = sm.ign[2 * lane], I1 = sm.ign[2 * lane + 1];
-    const int ni_l = __popcll(I0) + __popcll(I1);
-    const int incl_i = warp_incl_scan(ni_l, lane);
-    const int NI = __shfl_sync(GCA_FULL, incl_i, 31);
-    if (NI > 0) {
-      sm.ign[2 * lane] = 0ull;
-      sm.ign[2 * lane + 1] = 0ull;
-      const TfKey ka1 = tf_key(sc[4], sc[5]), ka2 = tf_key(sc[6], sc[7]);
-      uint32_t* dt = reinterpret_cast<uint32_t*>(sm.base_lo);  // burn-out tick per listed ignition
-      for (int base = 0; base < NI; base += S64_CAP) {
-        {
-          int idx = incl_i - ni_l - base;
-          unsigned long long m = I0;
-          int rowbits = (2 * lane) << 6;
+    if (active) {
+      const uint32_t* sc = sm.sched[j];
+      const size_t inj_base = ((size_t)j * N + e) * 4096;
+      const unsigned long long I0 = sm.ign[2 * lane], I1 = sm.ign[2 * lane + 1];
+      const int ni_l = __popcll(I0) + __popcll(I1);
+      const int incl_i = warp_incl_scan(ni_l, lane);
+      const int NI = __shfl_sync(GCA_FULL, incl_i, 31);
+      if (NI > 0) {
+        sm.ign[2 * lane] = 0ull;
+        sm.ign[2 * lane + 1] = 0ull;
+        const TfKey ka1 = tf_key(sc[4], sc[5]), ka2 = tf_key(sc[6], sc[7]);
+        uint32_t* dt = reinterpret_cast<uint32_t*>(sm.base);  // burn-out tick per listed ignition
+        for (int base = 0; base < NI; base += S64_CAP) {
+          {
+            int idx = incl_i - ni_l - base;
+            unsigned long long m = I0;
+            int rowbits = (2 * lane) << 6;
 #pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
-            while (m) {
-              const int c = __ffsll((long long)m) - 1;
-              m &= m - 1;
-              if ((unsigned)idx < (unsigned)S64_CAP) sm.pairs[idx] = (uint16_t)(rowbits | c);
-              ++idx;
+            for (int half = 0; half < 2; ++half) {
+              while (m) {
+                const int c = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                if ((unsigned)idx < (unsigned)S64_CAP) wp[idx] = (uint16_t)(rowbits | c);
+                ++idx;
+              }
+              m = I1;
+              rowbits = (2 * lane + 1) << 6;
             }
-            m = I1;
-            rowbits = (2 * lane + 1) << 6;
           }
-        }
-        __syncwarp();
-        const int cnt = min(S64_CAP, NI - base);
-        // two lanes per ignition: randint needs two independent words (jax.random.randint)
-        for (int tb = 0; tb < 2 * cnt; tb += 32) {
-          const int task = tb + lane, i = task >> 1;
-          const bool valid = i < cnt;
-          const uint32_t cell = sm.pairs[valid ? i : 0];
-          uint32_t bits = 0;
-          if (j_age_new == nullptr) bits = bits_at_ni((lane & 1) ? ka2 : ka1, cell, S64_HALF_CELL, mode);
-          const uint32_t other = __shfl_xor_sync(GCA_FULL, bits, 1);
-          if (valid && !(lane & 1)) {
-            int age;
-            if (j_age_new) age = j_age_new[inj_base + cell];
-            else {
-              const uint32_t hm = fastmod(bits, P.age_span, age_magic), lm = fastmod(other, P.age_span, age_magic);
-              age = P.age_lo + (int)fastmod(hm * P.age_mult + lm, P.age_span, age_magic);
+          __syncwarp();
+          const int cnt = min(S64_CAP, NI - base);
+          // two lanes per ignition: randint needs two independent words (jax.random.randint)
+          for (int tb = 0; tb < 2 * cnt; tb += 32) {
+            const int task = tb + lane, i = task >> 1;
+            const bool valid = i < cnt;
+            const uint32_t cell = wp[valid ? i : 0];
+            uint32_t bits = 0;
+            if (j_age_new == nullptr) bits = bits_at_ni((lane & 1) ? ka2 : ka1, cell, S64_HALF_CELL, mode);
+            const uint32_t other = __shfl_xor_sync(GCA_FULL, bits, 1);
+            if (valid && !(lane & 1)) {
+              int age;
+              if (j_age_new) age = j_age_new[inj_base + cell];
+              else {
+                const uint32_t hm = fastmod(bits, P.age_span, age_magic), lm = fastmod(other, P.age_span, age_magic);
+                age = P.age_lo + (int)fastmod(hm * P.age_mult + lm, P.age_span, age_magic);
+              }
+              const uint32_t dabs = tick0 + (uint32_t)j + (uint32_t)age;  // burn-out tick
+              S.death[cell_base + cell] = (uint16_t)dabs;
+              dt[i] = dabs;
             }
-            const uint32_t dabs = tick0 + (uint32_t)j + (uint32_t)age;  // burn-out tick
-            S.death[cell_base + cell] = (uint16_t)dabs;
-            dt[i] = dabs;
           }
+          __syncwarp();
+          {
+            int idx = incl_i - ni_l - base;
+            for (int q = __popcll(I0); q > 0; --q, ++idx)
+              if ((unsigned)idx < (unsigned)S64_CAP) rm.x = min(rm.x, dt[idx]);
+            for (int q = __popcll(I1); q > 0; --q, ++idx)
+              if ((unsigned)idx < (unsigned)S64_CAP) rm.y = min(rm.y, dt[idx]);
+          }
+          __syncwarp();
         }
-        __syncwarp();
-        {
-          int idx = incl_i - ni_l - base;
-          for (int q = __popcll(I0); q > 0; --q, ++idx)
-            if ((unsigned)idx < (unsigned)S64_CAP) rm.x = min(rm.x, dt[idx]);
-          for (int q = __popcll(I1); q > 0; --q, ++idx)
-            if ((unsigned)idx < (unsigned)S64_CAP) rm.y = min(rm.y, dt[idx]);
-        }
-        __syncwarp();
+      }
+      unsigned long long ext0 = 0ull, ext1 = 0ull;
+      if (burnrows & 1u) {
+        const ulonglong2 a = reinterpret_cast<const ulonglong2*>(sm.burn[2 * lane])[0];
+        const ulonglong2 b = reinterpret_cast<const ulonglong2*>(sm.burn[2 * lane])[1];
+        ext0 = a.x & ((j & 1) ? a.y : ~a.y) & ((j & 2) ? b.x : ~b.x) & ((j & 4) ? b.y : ~b.y);
+      }
+      if (burnrows & 2u) {
+        const ulonglong2 a = reinterpret_cast<const ulonglong2*>(sm.burn[2 * lane + 1])[0];
+        const ulonglong2 b = reinterpret_cast<const ulonglong2*>(sm.burn[2 * lane + 1])[1];
+        ext1 = a.x & ((j & 1) ? a.y : ~a.y) & ((j & 2) ? b.x : ~b.x) & ((j & 4) ? b.y : ~b.y);
+      }
+      unsigned long long g0 = 0, g1 = 0;
+      if (P.p_tree > 0.0f) regrow_rows(P, J, tf_key(sc[2], sc[3]), inj_base, lane, ~(t0 | f0), ~(t1 | f1), g0, g1);
+      n_ign += ni_l;
+      n_ext += __popcll(ext0) + __popcll(ext1);
+      ch0 |= I0 | ext0 | g0;
+      ch1 |= I1 | ext1 | g1;
+      t0 = (t0 & ~I0) | g0;
+      t1 = (t1 & ~I1) | g1;
+      f0 = (f0 & ~ext0) | I0;
+      f1 = (f1 & ~ext1) | I1;
+      if (j + 1 < K) {
+        store_row_views(sm.fire32 + (2 * lane + 4) * 4, f0);
+        store_row_views(sm.fire32 + (2 * lane + 5) * 4, f1);
+      }
+      __syncwarp();
+    }
+  }
+  if (!active) {
+    if (O.stats != nullptr) {
+      const uint32_t b = __reduce_add_sync(GCA_FULL, n_draws), t = __reduce_add_sync(GCA_FULL, n_thresh);
+      if (lane == 0) {
+        if (b) atomicAdd(&O.stats[1], (unsigned long long)b);
+        if (t) atomicAdd(&O.stats[4], (unsigned long long)t);
       }
     }
-    unsigned long long ext0 = die0, ext1 = die1;
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      ext0 &= ((j >> b) & 1) ? pl0[b] : ~pl0[b];
-      ext1 &= ((j >> b) & 1) ? pl1[b] : ~pl1[b];
-    }
-    unsigned long long g0 = 0, g1 = 0;
-    if (P.p_tree > 0.0f) regrow_rows(P, J, tf_key(sc[2], sc[3]), inj_base, lane, ~(t0 | f0), ~(t1 | f1), g0, g1);
-    n_ign += ni_l;
-    n_ext += __popcll(ext0) + __popcll(ext1);
-    ch0 |= I0 | ext0 | g0;
-    ch1 |= I1 | ext1 | g1;
-    t0 = (t0 & ~I0) | g0;
-    t1 = (t1 & ~I1) | g1;
-    f0 = (f0 & ~ext0) | I0;
-    f1 = (f1 & ~ext1) | I1;
-    if (j + 1 < K) {
-      store_row_views(sm.fire32 + (2 * lane + 4) * 4, f0);
-      store_row_views(sm.fire32 + (2 * lane + 5) * 4, f1);
-    }
-    __syncwarp();
+    return;
   }
 
   // ---- sparse in-place write-back of the cells that changed --------------------------------------
@@ -789,14 +903,12 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     }
   }
 
-  // ---- per-env scalars: key chain, wind, clock, move, douse, day/night, reward, done -------------
+  // ---- per-env scalars: clock, move, douse, day/night, reward, done (key / wind were stored above) --
   const bool ca_only = (flags & GCA_FLAG_CA_ONLY) != 0;
   const bool done = fcount == 0;
   if (lane == 0) {
-    S.key[2 * e] = key0;
-    S.key[2 * e + 1] = key1;
-    S.wind_index[e] = widx;
-    if (S.work != nullptr) S.work[e] = work;
+    if (S.work != nullptr)
+      S.work[e] = (flags & GCA_FLAG_WORK_CYCLES) ? (uint32_t)(clock64() - clk0) : work + sm.npairs;
     S.tick[e] = tick0 + (uint32_t)K;
     const float rew = award(tcount, fcount);
     if (!ca_only) {
@@ -862,19 +974,37 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   }
 }
 
+template <int MODE, int HP, bool INJ>
+cudaError_t launch_instance(const gca_params& p, const gca_state& s, const int32_t* actions, const gca_step_out& out,
+                            const gca_inject& inj, const gca_state& snap, const float* snap_reward, uint32_t flags,
+                            cudaStream_t st) {
+  static bool configured = false;  // per instance; the attribute is per device function
+  auto kern = env_step64_kernel<MODE, HP, INJ>;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
+    if (err != cudaSuccess) return err;
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (err != cudaSuccess) return err;
+    configured = true;
+  }
+  const int blocks = (s.N + S64_E - 1) / S64_E;
+  kern<<<dim3(blocks), dim3(S64_E * 32), sizeof(CtaSmem), st>>>(p, s, actions, out, inj, snap, snap_reward, flags);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
 cudaError_t launch_env_step64(const gca_params& p, const gca_state& s, const int32_t* actions,
                               const gca_step_out& out, const gca_inject& inj, const gca_state& snap,
                               const float* snap_reward, uint32_t flags, cudaStream_t st) {
-  const int blocks = (s.N + S64_WARPS - 1) / S64_WARPS;
-  const dim3 g(blocks), b(S64_WARPS * 32);
   const bool injected = inj.u_burn || inj.u_grow || inj.age_new || inj.u_wind || inj.wind_step;
   const int hp = (!s.hidden && !s.pslope) ? 0 : ((s.hidden && s.pslope) ? 1 : -1);
-#define GCA_LAUNCH64(M, H, I) env_step64_kernel<M, H, I><<<g, b, 0, st>>>(p, s, actions, out, inj, snap, snap_reward, flags)
+#define GCA_LAUNCH64(M, H, I) return launch_instance<M, H, I>(p, s, actions, out, inj, snap, snap_reward, flags, st)
   if (injected || hp < 0) GCA_LAUNCH64(-1, -1, true);
-  else if (p.rng_mode == GCA_RNG_LEGACY) { if (hp) GCA_LAUNCH64(GCA_RNG_LEGACY, 1, false); else GCA_LAUNCH64(GCA_RNG_LEGACY, 0, false); }
-  else { if (hp) GCA_LAUNCH64(GCA_RNG_PARTITIONABLE, 1, false); else GCA_LAUNCH64(GCA_RNG_PARTITIONABLE, 0, false); }
+  if (p.rng_mode == GCA_RNG_LEGACY) { if (hp) GCA_LAUNCH64(GCA_RNG_LEGACY, 1, false); else GCA_LAUNCH64(GCA_RNG_LEGACY, 0, false); }
+  if (hp) GCA_LAUNCH64(GCA_RNG_PARTITIONABLE, 1, false);
+  GCA_LAUNCH64(GCA_RNG_PARTITIONABLE, 0, false);
 #undef GCA_LAUNCH64
-  return cudaGetLastError();
 }
 
 }  // namespace gca

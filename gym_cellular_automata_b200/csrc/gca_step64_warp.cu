@@ -1,0 +1,885 @@
+// gca_step64.cu -- fused environment step for 64x64 grids: ONE WARP PER ENVIRONMENT.
+//
+// Replaces, for a batch of envs, jax.vmap(MDP.update) + _award + _is_done (+ conditional_reset)
+// of /root/reference/gym_cellular_automata/forest_fire/bulldozer/advanced_bulldozer.py:332-518,
+// 1103-1133 and the operators it calls (ca_alexandridis_jax.py:321-460, repeat_ca_jax.py:34-71,
+// move_modify_jax.py:39-157).  Not a translation: the reference materialises (H,W,9,9) gathers and
+// draws 12 random words per cell; this kernel works on bit-boards and draws lazily.
+//
+// Design:
+//  * a 64-cell row is one 64-bit word per mask (tree, fire, doused).  Lane l owns rows 2l, 2l+1 in
+//    registers; vertical halos come from warp shuffles.
+//  * all K CA sub-steps of the env step are applied on-chip (temporal blocking); HBM sees one
+//    coalesced 128-bit read of the u8 grid and sparse in-place writes of the cells that changed.
+//  * front cells (tree with a burning Moore neighbour) are compacted into a shared-memory list;
+//    per front cell the 9x9 fire window is cut out of the bit-board, ring populations give a fast
+//    float32 enclosure [lo, hi] of the burn-probability chain; per (cell, burning direction) one
+//    counter-based threefry2x32 block reproduces exactly the uniform jax.random would have
+//    drawn for that element.  u < lo ignites, u >= hi does not, and the (rare) in-between case is
+//    re-evaluated with the reference's exact row-major float32 summation ("threshold cells").
+//  * fire ages are stored as burn-out ticks, so burning cells need no per-step decrement; a
+//    per-row minimum tells which rows hold a cell that burns out in this step.
+//  * the key chain of jax.random.split is evaluated by lane pairs; clock, move, douse, day/night,
+//    reward (popc + warp reduce), done and the optional auto-reset are fused in the epilogue.
+#include "gca_common.cuh"
+
+namespace gca {
+namespace warpimpl {
+
+constexpr int S64_WARPS = 1;  // envs (warps) per CTA: 1 -> the warp's shared-memory block has a
+                                          // compile-time address (no per-access base arithmetic)
+constexpr int S64_CAP = 256;    // front cells per pass
+constexpr int S64_PCAP = 512;   // (cell, direction) draws buffered before a flush
+constexpr uint32_t S64_HALF_BURN = 9u * 4096u / 2u;
+constexpr uint32_t S64_HALF_CELL = 4096u / 2u;
+// enclosure half-width of the fast float32 path: |sequential sum - ring-count sum| <= 89 u |sum|
+// (80 adds + 8 flops, u = 2^-24); 2^-16 = 256 u leaves a 2.8x margin.
+#define S64_LO 0.9999847412109375f   /* 1 - 2^-16 */
+#define S64_HI 1.0000152587890625f   /* 1 + 2^-16 */
+
+struct __align__(16) WarpSmem {
+  uint32_t fire32[72 * 4];        // fire rows -4..67, 4 overlapping 32-bit views per row
+  uint32_t dous32[68 * 4];        // doused rows -2..65, same views
+  unsigned long long ign[64];     // ignition accumulator (unpack: tree rows)
+  float base_lo[S64_CAP];         // per front cell: enclosure of (p_h (1+p_veg)) (1+p_den)
+  float base_hi[S64_CAP];         //   (unpack: fire rows; apply: burn-out ticks of new fires)
+  uint16_t list[S64_CAP];         // front cells: (row << 6) | col.  Built once per env step and
+                                  //   extended incrementally; stale entries fail the frontbb test
+  uint16_t pairs[S64_PCAP];       // (list index << 4) | direction  (list build: front rows;
+                                  //   apply: cells ignited in this sub-step)
+  unsigned long long frontbb[64]; // front mask of the current sub-step (validates list entries)
+  uint32_t sched[GCA_MAX_K][12];  // per sub-step: Sburn[2] Sgrow[2] ak1[2] ak2[2] wind change step pad
+};
+
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// x % span with a precomputed magic = 0xFFFFFFFF / span (span < 2^16): quotient estimate is at
+// most 2 too small
+__device__ __forceinline__ uint32_t fastmod(uint32_t x, uint32_t span, uint32_t magic) {
+  uint32_t r = x - __umulhi(x, magic) * span;
+  if (r >= span) r -= span;
+  if (r >= span) r -= span;
+  return r;
+}
+
+// view k of a row covers columns 16k-4 .. 16k+27 (bit b <-> column 16k-4+b)
+__device__ __forceinline__ void store_row_views(uint32_t* dst, unsigned long long x) {
+  uint4 w;
+  w.x = (uint32_t)(x << 4);
+  w.y = (uint32_t)(x >> 12);
+  w.z = (uint32_t)(x >> 28);
+  w.w = (uint32_t)(x >> 44);
+  *reinterpret_cast<uint4*>(dst) = w;
+}
+
+// 16 u8 cells -> 16-bit tree and fire masks (bit i = cell i)
+__device__ __forceinline__ void cells16_to_bits(const uint4& v, uint32_t& t16, uint32_t& f16) {
+  const uint32_t M = 0x00204081u;  // gathers bit 0 of each byte into bits 21..24
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  t16 = 0;
+  f16 = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t tb = w[k] & 0x01010101u;
+    const uint32_t fb = (w[k] >> 1) & 0x01010101u;
+    t16 |= (((tb * M) >> 21) & 0xFu) << (4 * k);
+    f16 |= (((fb * M) >> 21) & 0xFu) << (4 * k);
+  }
+}
+
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
+  const uint32_t lo = __shfl_sync(GCA_FULL, (uint32_t)v, src);
+  const uint32_t hi = __shfl_sync(GCA_FULL, (uint32_t)(v >> 32), src);
+  return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long shfl64_up1(unsigned long long v, int lane) {
+  const uint32_t lo = __shfl_up_sync(GCA_FULL, (uint32_t)v, 1);
+  const uint32_t hi = __shfl_up_sync(GCA_FULL, (uint32_t)(v >> 32), 1);
+  return lane == 0 ? 0ull : (((unsigned long long)hi << 32) | lo);
+}
+__device__ __forceinline__ unsigned long long shfl64_down1(unsigned long long v, int lane) {
+  const uint32_t lo = __shfl_down_sync(GCA_FULL, (uint32_t)v, 1);
+  const uint32_t hi = __shfl_down_sync(GCA_FULL, (uint32_t)(v >> 32), 1);
+  return lane == 31 ? 0ull : (((unsigned long long)hi << 32) | lo);
+}
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(GCA_FULL, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+
+// one threefry block per lane with lane-specific key/counters, words swapped inside the lane pair
+__device__ __forceinline__ void tf_exchange(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t& o0,
+                                            uint32_t& o1, uint32_t& p0, uint32_t& p1) {
+  threefry2x32_ni(k0, k1, c0, c1, o0, o1);
+  p0 = __shfl_xor_sync(GCA_FULL, o0, 1);
+  p1 = __shfl_xor_sync(GCA_FULL, o1, 1);
+}
+__device__ __forceinline__ void assemble_split(int mode, uint32_t w, uint32_t o0, uint32_t o1, uint32_t p0,
+                                               uint32_t p1, uint32_t& n0, uint32_t& n1, uint32_t& s0,
+                                               uint32_t& s1) {
+  const uint32_t a0 = w ? p0 : o0, a1 = w ? p1 : o1;
+  const uint32_t b0 = w ? o0 : p0, b1 = w ? o1 : p1;
+  if (mode == GCA_RNG_LEGACY) { n0 = a0; n1 = b0; s0 = a1; s1 = b1; }
+  else { n0 = a0; n1 = a1; s0 = b0; s1 = b1; }
+}
+
+// Key schedule of K successive PartiallyObservableForestFireJax.update calls
+// (ca_alexandridis_jax.py:436-448 and :352-368).  The chain K0 -> K1 -> K2 -> K3 is sequential
+// (3K split levels, every lane pair runs it redundantly -- free in SIMT); pair 2j then derives
+// sub-step j's Sburn / Sgrow / randint keys and pair 2j+1 its wind draws (4 more levels).
+__device__ __noinline__ void key_schedule(WarpSmem& sm, const gca_params& P, const gca_inject& J, int N, int e,
+                                          int lane, uint32_t& key0, uint32_t& key1, int& widx) {
+  const int K = P.K, mode = P.rng_mode;
+  const int pair = lane >> 1;
+  const uint32_t w = lane & 1;
+  uint32_t k0 = key0, k1 = key1;
+  uint32_t c0 = 0, c1 = 0, sw0 = 0, sw1 = 0;
+#pragma unroll 1
+  for (int j = 0; j < K; ++j) {
+    uint32_t n0, n1, s0, s1;
+    split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K1, S1
+    if (pair == 2 * j) { c0 = s0; c1 = s1; }
+    k0 = n0; k1 = n1;
+    split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K2, Swind
+    if (pair == 2 * j + 1) { sw0 = s0; sw1 = s1; }
+    k0 = n0; k1 = n1;
+    split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K3, Sidx
+    if (pair == 2 * j + 1) { c0 = s0; c1 = s1; }
+    k0 = n0; k1 = n1;
+  }
+  key0 = k0;
+  key1 = k1;
+  const bool burn_role = (pair & 1) == 0;
+  const int j = pair >> 1;
+  const uint32_t sc0 = (mode == GCA_RNG_LEGACY) ? w : 0u;       // split counters of this lane
+  const uint32_t sc1 = (mode == GCA_RNG_LEGACY) ? w + 2u : w;
+  uint32_t o0, o1, p0, p1, n0, n1, s0, s1;
+  // level 1: burn: split(S1) -> Ka, Sburn ; wind: split(Sidx) -> wk1, wk2
+  tf_exchange(c0, c1, sc0, sc1, o0, o1, p0, p1);
+  assemble_split(mode, w, o0, o1, p0, p1, n0, n1, s0, s1);
+  const uint32_t sburn0 = s0, sburn1 = s1;  // (wind role: wk2)
+  uint32_t cur0 = n0, cur1 = n1;            // burn: Ka ; wind: wk1
+  // level 2: burn: split(Ka) -> Kb, Sgrow ; wind: even lane bits(wk1,()), odd lane bits(wk2,())
+  {
+    const uint32_t kk0 = burn_role ? cur0 : (w ? sburn0 : cur0);
+    const uint32_t kk1 = burn_role ? cur1 : (w ? sburn1 : cur1);
+    tf_exchange(kk0, kk1, burn_role ? sc0 : 0u, burn_role ? sc1 : 0u, o0, o1, p0, p1);
+  }
+  assemble_split(mode, w, o0, o1, p0, p1, n0, n1, s0, s1);
+  const uint32_t sgrow0 = s0, sgrow1 = s1;
+  // wind role: hb = even lane's word, lb = odd lane's word
+  const uint32_t my_bits = (mode == GCA_RNG_LEGACY) ? o0 : (o0 ^ o1);
+  const uint32_t pr_bits = (mode == GCA_RNG_LEGACY) ? p0 : (p0 ^ p1);
+  const uint32_t hb = w ? pr_bits : my_bits, lb = w ? my_bits : pr_bits;
+  cur0 = n0; cur1 = n1;  // burn: Kb
+  // level 3: burn: split(Kb) -> Kc, Sage ; wind: bits(Swind, ())
+  tf_exchange(burn_role ? cur0 : sw0, burn_role ? cur1 : sw1, burn_role ? sc0 : 0u, burn_role ? sc1 : 0u,
+              o0, o1, p0, p1);
+  assemble_split(mode, w, o0, o1, p0, p1, n0, n1, s0, s1);
+  const uint32_t uw_bits = (mode == GCA_RNG_LEGACY) ? o0 : (o0 ^ o1);
+  // level 4: burn: split(Sage) -> ak1, ak2
+  tf_exchange(s0, s1, sc0, sc1, o0, o1, p0, p1);
+  uint32_t a10, a11, a20, a21;
+  assemble_split(mode, w, o0, o1, p0, p1, a10, a11, a20, a21);
+  if (j < K && w == 0) {
+    uint32_t* sc = sm.sched[j];
+    if (burn_role) {
+      sc[0] = sburn0; sc[1] = sburn1; sc[2] = sgrow0; sc[3] = sgrow1;
+      sc[4] = a10; sc[5] = a11; sc[6] = a20; sc[7] = a21;
+    } else {
+      float u = bits_to_uniform(uw_bits);
+      int step = randint_from_bits(hb, lb, 1, 7u, 4u);
+      if (J.u_wind) u = J.u_wind[(size_t)j * N + e];
+      if (J.wind_step) step = J.wind_step[(size_t)j * N + e];
+      sc[9] = (u < P.p_wind_change) ? 1u : 0u;
+      sc[10] = (uint32_t)step;
+    }
+  }
+  __syncwarp();
+  int wi = widx;
+  for (int q = 0; q < K; ++q) {
+    if (lane == 0) sm.sched[q][8] = (uint32_t)wi;
+    if (sm.sched[q][9]) wi = (wi + (int)sm.sched[q][10]) % 8;
+  }
+  widx = wi;
+  __syncwarp();
+}
+
+// 9x9 fire window of cell (r, c): rows r-4..r+4 packed 3 per word (9 bits each)
+__device__ __forceinline__ void fire_window(const WarpSmem& sm, int r, int c, uint32_t& A, uint32_t& B,
+                                            uint32_t& C) {
+  const uint32_t* fw = sm.fire32 + r * 4 + (c >> 4);
+  const int o = c & 15;
+  uint32_t wv[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) wv[i] = (fw[i * 4] >> o) & 0x1FFu;
+  A = wv[0] | (wv[1] << 9) | (wv[2] << 18);
+  B = wv[3] | (wv[4] << 9) | (wv[5] << 18);
+  C = wv[6] | (wv[7] << 9) | (wv[8] << 18);
+}
+// 5x5 doused window: rows r-2..r+2, 5 bits each
+__device__ __forceinline__ uint32_t dous_window(const WarpSmem& sm, int r, int c) {
+  const uint32_t* dw = sm.dous32 + r * 4 + (c >> 4);
+  const int o = (c & 15) + 2;
+  uint32_t v = 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) v |= ((dw[i * 4] >> o) & 0x1Fu) << (5 * i);
+  return v;
+}
+
+// Exact (reference-order) value of (heat - dousing) (1+p_veg) (1+p_den) for one cell: row-major
+// sequential float32 sums with the accumulator starting at +0 (oracle/alexandridis.py:_window_sum).
+__device__ __noinline__ float exact_base(const WarpSmem& sm, const gca_params& P, int r, int c, float a, float b) {
+  uint32_t A, B, C;
+  fire_window(sm, r, c, A, B, C);
+  const uint32_t rows3[3] = {A, B, C};
+  float heat = 0.0f;
+  for (int i = 0; i < 9; ++i) {
+    const uint32_t bits = (rows3[i / 3] >> (9 * (i % 3))) & 0x1FFu;
+    const int di = i < 4 ? 4 - i : i - 4;
+    for (int jj = 0; jj < 9; ++jj) {
+      if ((bits >> jj) & 1u) {
+        const int dj = jj < 4 ? 4 - jj : jj - 4;
+        const int ring = di > dj ? di : dj;
+        heat = __fadd_rn(heat, P.ring_w[ring]);
+      }
+    }
+  }
+  const uint32_t dwin = dous_window(sm, r, c);
+  float dous = 0.0f;
+  for (int i = 0; i < 5; ++i)
+    for (int jj = 0; jj < 5; ++jj)
+      if ((dwin >> (5 * i + jj)) & 1u) {
+        const bool inner = i >= 1 && i <= 3 && jj >= 1 && jj <= 3;
+        dous = __fadd_rn(dous, inner ? P.dous_inner : P.dous_border);
+      }
+  const float ph = __fsub_rn(heat, dous);
+  return __fmul_rn(__fmul_rn(ph, a), b);
+}
+
+// Compact the front cells [pass_base, pass_base + CAP) of the row masks fr0 (row 2*lane) and fr1
+// (row 2*lane+1) into sm.list and return the total number of front cells.  The rows are first
+// re-dealt in 16-column pieces (piece p = 4*row + quarter goes to lane p % 32) so that a long
+// horizontal run of front cells -- the top/bottom edge of a burning blob -- is shared by several
+// lanes instead of serialising one.
+__device__ __noinline__ int build_front_list(WarpSmem& sm, unsigned long long fr0, unsigned long long fr1,
+                                             int lane, int pass_base) {
+  reinterpret_cast<ulonglong2*>(sm.pairs)[lane] = make_ulonglong2(fr0, fr1);
+  __syncwarp();
+  const uint16_t* q16 = reinterpret_cast<const uint16_t*>(sm.pairs);
+  // this lane's 8 pieces as two 64-bit words: bit 16*k + b of word h <-> piece (4h + k), column bit b
+  unsigned long long w[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t lo = (uint32_t)q16[lane + 32 * (4 * h)] | ((uint32_t)q16[lane + 32 * (4 * h + 1)] << 16);
+    const uint32_t hi = (uint32_t)q16[lane + 32 * (4 * h + 2)] | ((uint32_t)q16[lane + 32 * (4 * h + 3)] << 16);
+    w[h] = ((unsigned long long)hi << 32) | lo;
+  }
+  const int n = __popcll(w[0]) + __popcll(w[1]);
+  const int incl = warp_incl_scan(n, lane);
+  const int T = __shfl_sync(GCA_FULL, incl, 31);
+  int idx = incl - n - pass_base;
+  // piece p = lane + 32 q  ->  row (lane >> 2) + 8 q, columns 16 (lane & 3) ..
+  const uint32_t lane_base = ((uint32_t)(lane >> 2) << 6) | ((uint32_t)(lane & 3) << 4);
+  unsigned long long m = w[0];
+  uint32_t word_base = lane_base;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    while (m) {
+      const uint32_t b = (uint32_t)__ffsll((long long)m) - 1u;
+      m &= m - 1;
+      // piece within the word = b >> 4 -> 8 rows further down per piece
+      const uint32_t cell = word_base + ((b >> 4) << 9) + (b & 15u);
+      if ((unsigned)idx < (unsigned)S64_CAP) sm.list[idx] = (uint16_t)cell;
+      ++idx;
+    }
+    m = w[1];
+    word_base = lane_base + (4u << 9);
+  }
+  __syncwarp();
+  return T;
+}
+
+// Touch the hidden byte and the 32-byte slope-factor sector of listed front cells [from, to) so
+// that they are in L2 (and, capacity permitting, L1) when the cell and draw phases ask for them.
+__device__ __forceinline__ void prefetch_front(const WarpSmem& sm, const uint8_t* hidden, const float* pslope,
+                                               size_t cell_base, int from, int to, int lane) {
+  if (hidden == nullptr) return;
+  for (int t = from + lane; t < to; t += 32) {
+    const uint32_t cell = sm.list[t];
+    prefetch_l1(hidden + cell_base + cell);
+    if (pslope != nullptr) prefetch_l1(pslope + (cell_base + cell) * 8);
+  }
+}
+
+// One buffered (front cell, burning direction) draw: returns whether it ignites the cell.
+__device__ __forceinline__ bool eval_pair(const WarpSmem& sm, const gca_params& P, const uint8_t* hidden,
+                                          const float* pslope, const float* j_u_burn, int mode, const TfKey& kburn,
+                                          float windreg, size_t cell_base, size_t inj_base, int q, int PT,
+                                          uint32_t& cell_out, uint32_t& n_thresh) {
+  const bool valid = q < PT;
+  const uint32_t ent = valid ? sm.pairs[q] : 0u;
+  const int t = ent >> 4, d = ent & 15;
+  const uint32_t cell = sm.list[t];
+  cell_out = cell;
+  float s = 1.0f;
+  if (pslope != nullptr && valid) s = pslope[(cell_base + cell) * 8 + dir_slot(d)];
+  float u;
+  if (j_u_burn) {
+    u = valid ? j_u_burn[(inj_base + cell) * 9 + d] : 1.0f;
+  } else {
+    u = bits_to_uniform(bits_at(kburn, cell * 9u + (uint32_t)d, S64_HALF_BURN, mode));
+  }
+  const float w = __shfl_sync(GCA_FULL, windreg, d);
+  const float plo = __fmul_rn(__fmul_rn(sm.base_lo[t], w), s);
+  const float phi = __fmul_rn(__fmul_rn(sm.base_hi[t], w), s);
+  bool ig = valid && (u < plo);
+  if (valid && !ig && (u < phi)) {
+    // threshold cell: the float32 enclosure cannot decide -> reference-order evaluation
+    const int r = cell >> 6, c = cell & 63;
+    int hid = 3 | (3 << 3);
+    if (hidden != nullptr) hid = hidden[cell_base + cell];
+    const float a = P.onep_veg[clip15(hid & 7)];
+    const float b = P.onep_den[clip15((hid >> 3) & 7)];
+    const float base = exact_base(sm, P, r, c, a, b);
+    const float p = __fmul_rn(__fmul_rn(base, w), s);
+    ig = u < p;
+    n_thresh++;
+  }
+  return ig;
+}
+
+// empty -> tree with probability p_tree (0 in the reference env, so this is a cold path): a dense
+// draw per empty cell of the two rows this lane owns.
+__device__ __noinline__ void regrow_rows(const gca_params& P, const gca_inject& J, const TfKey kg, size_t inj_base,
+                                         int lane, unsigned long long e0, unsigned long long e1,
+                                         unsigned long long& g0, unsigned long long& g1) {
+  unsigned long long m = e0;
+  int row = 2 * lane;
+  for (int half = 0; half < 2; ++half) {
+    unsigned long long g = 0;
+    while (m) {
+      const int c = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      const uint32_t cell = (uint32_t)(row * 64 + c);
+      float u;
+      if (J.u_grow) u = J.u_grow[inj_base + cell];
+      else u = bits_to_uniform(bits_at_ni(kg, cell, S64_HALF_CELL, P.rng_mode));
+      if (u < P.p_tree) g |= 1ull << c;
+    }
+    if (half == 0) g0 = g; else g1 = g;
+    m = e1;
+    row = 2 * lane + 1;
+  }
+}
+
+__device__ __forceinline__ void front_masks(unsigned long long t0, unsigned long long t1, unsigned long long f0,
+                                            unsigned long long f1, int lane, unsigned long long& fr0,
+                                            unsigned long long& fr1) {
+  // front = tree cells with a burning Moore neighbour (row halos by warp shuffle)
+  const unsigned long long fh0 = f0 | (f0 << 1) | (f0 >> 1);
+  const unsigned long long fh1 = f1 | (f1 << 1) | (f1 >> 1);
+  fr0 = t0 & (shfl64_up1(fh1, lane) | fh0 | fh1);
+  fr1 = t1 & (fh0 | fh1 | shfl64_down1(fh0, lane));
+}
+
+#ifndef S64_MINB
+#define S64_MINB (28 / S64_WARPS)  // 28 warps/SM x 72 registers = the whole register file; 4096 envs = one wave
+#endif
+// MODE: GCA_RNG_* or -1 (read P.rng_mode); HP: 0 = no hidden layers, 1 = hidden + slope table present,
+// -1 = test the pointers at run time; INJ: injected random fields may be present.  The launcher picks
+// a fully specialised instance for the production cases and the generic one otherwise.
+template <int MODE, int HP, bool INJ>
+__global__ void __launch_bounds__(S64_WARPS * 32, S64_MINB)
+env_step64_warp_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gca_state S,
+                  const int32_t* __restrict__ actions, const __grid_constant__ gca_step_out O,
+                  const __grid_constant__ gca_inject J, const __grid_constant__ gca_state SNAP,
+                  const float* __restrict__ snap_reward, uint32_t flags) {
+  __shared__ WarpSmem smem_all[S64_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long clk0 = clock64();
+  const int slot = blockIdx.x * S64_WARPS + warp;
+  const int N = S.N;
+  if (slot >= N) return;
+  // optional load-balancing indirection (gca_balance_order): which env this warp steps
+  const int e = S.order != nullptr ? S.order[slot] : slot;
+  WarpSmem& sm = smem_all[warp];
+  const int K = P.K, mode = MODE < 0 ? P.rng_mode : MODE;
+  const size_t cell_base = (size_t)e * 4096;
+  const uint8_t* const hidden = HP == 0 ? nullptr : S.hidden;
+  const float* const pslope = HP == 0 ? nullptr : S.pslope;
+  if (HP == 1) { __builtin_assume(hidden != nullptr); __builtin_assume(pslope != nullptr); }
+  const float* const j_u_burn = INJ ? J.u_burn : nullptr;
+  const int32_t* const j_age_new = INJ ? J.age_new : nullptr;
+
+  // ---- coalesced 128-bit read of the u8 grid -> tree / fire row masks ---------------------------
+  unsigned long long t0, t1, f0, f1;
+  {
+    uint4 cv[8];
+    const uint4* cptr = reinterpret_cast<const uint4*>(S.cell + cell_base);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cv[i] = cptr[i * 32 + lane];
+    uint16_t* trow = reinterpret_cast<uint16_t*>(sm.ign);
+    uint16_t* frow = reinterpret_cast<uint16_t*>(sm.base_lo);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t t16, f16;
+      cells16_to_bits(cv[i], t16, f16);
+      const int chunk = i * 32 + lane;  // row = chunk >> 2, quarter = chunk & 3
+      trow[chunk] = (uint16_t)t16;
+      frow[chunk] = (uint16_t)f16;
+    }
+  }
+  const ulonglong2 dz = reinterpret_cast<const ulonglong2*>(S.doused + (size_t)e * 64)[lane];
+  uint2 rm = reinterpret_cast<const uint2*>(S.row_min + (size_t)e * 64)[lane];
+  const uint32_t tick0 = S.tick[e];
+  uint32_t key0 = S.key[2 * e], key1 = S.key[2 * e + 1];
+  int widx = S.wind_index[e];
+  if (!(flags & GCA_FLAG_CA_ONLY)) {
+    // the per-env scalars of the epilogue (lane 0, serial): get their lines on the way now
+    const void* pf = nullptr;
+    switch (lane) {
+      case 0: pf = actions + 3 * e; break;
+      case 1: pf = S.time + e; break;
+      case 2: pf = S.position + 2 * e; break;
+      case 3: pf = S.time_step + e; break;
+      case 4: pf = S.is_night + e; break;
+      case 5: pf = S.steps_elapsed ? S.steps_elapsed + e : nullptr; break;
+      case 6: pf = S.reward_accumulated ? S.reward_accumulated + e : nullptr; break;
+      default: break;
+    }
+    if (pf != nullptr) prefetch_l1(pf);
+  }
+  if (lane < 16) sm.fire32[lane] = 0u; else sm.fire32[272 + lane - 16] = 0u;   // fire rows -4..-1, 64..67
+  if (lane < 8) sm.dous32[lane] = 0u; else if (lane < 16) sm.dous32[264 + lane - 8] = 0u;  // rows -2,-1,64,65
+  store_row_views(sm.dous32 + (2 * lane + 2) * 4, dz.x);
+  store_row_views(sm.dous32 + (2 * lane + 3) * 4, dz.y);
+  __syncwarp();
+  {
+    const ulonglong2 tt = reinterpret_cast<const ulonglong2*>(sm.ign)[lane];
+    const ulonglong2 ff = reinterpret_cast<const ulonglong2*>(sm.base_lo)[lane];
+    t0 = tt.x; t1 = tt.y; f0 = ff.x; f1 = ff.y;
+  }
+  __syncwarp();
+  sm.ign[2 * lane] = 0ull;
+  sm.ign[2 * lane + 1] = 0ull;
+  unsigned long long ch0 = 0ull, ch1 = 0ull;  // cells whose state changed during this env step
+  store_row_views(sm.fire32 + (2 * lane + 4) * 4, f0);
+  store_row_views(sm.fire32 + (2 * lane + 5) * 4, f1);
+
+  // ---- rows holding a cell that burns out during this env step -----------------------------------
+  unsigned long long die0 = 0, die1 = 0, pl0[3] = {0, 0, 0}, pl1[3] = {0, 0, 0};
+  {
+    const bool need0 = f0 != 0ull && rm.x < tick0 + (uint32_t)K;
+    const bool need1 = f1 != 0ull && rm.y < tick0 + (uint32_t)K;
+    // each flagged row is one 128-byte line of burn-out ticks: request them all now, the serial
+    // row loop below then hits L1/L2 instead of paying one DRAM round trip per row
+    if (need0) prefetch_l1(S.death + cell_base + (2 * lane) * 64);
+    if (need1) prefetch_l1(S.death + cell_base + (2 * lane + 1) * 64);
+    uint32_t m0 = __ballot_sync(GCA_FULL, need0);
+    uint32_t m1 = __ballot_sync(GCA_FULL, need1);
+    while (m0 | m1) {
+      int src;
+      bool second;
+      if (m0) { src = __ffs(m0) - 1; m0 &= m0 - 1; second = false; }
+      else { src = __ffs(m1) - 1; m1 &= m1 - 1; second = true; }
+      const int row = 2 * src + (second ? 1 : 0);
+      const unsigned long long fr = shfl64(second ? f1 : f0, src);
+      uint16_t* dp = S.death + cell_base + row * 64;
+      const uint32_t da = dp[lane], db = dp[lane + 32];
+      const bool fa = (fr >> lane) & 1ull, fb = (fr >> (lane + 32)) & 1ull;
+      const uint32_t ra = (da - tick0) & 0xFFFFu, rb = (db - tick0) & 0xFFFFu;
+      const bool xa = fa && ra < (uint32_t)K, xb = fb && rb < (uint32_t)K;
+      const unsigned long long dmask =
+          (unsigned long long)__ballot_sync(GCA_FULL, xa) | ((unsigned long long)__ballot_sync(GCA_FULL, xb) << 32);
+      unsigned long long pm[3];
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        pm[b] = (unsigned long long)__ballot_sync(GCA_FULL, xa && ((ra >> b) & 1u)) |
+                ((unsigned long long)__ballot_sync(GCA_FULL, xb && ((rb >> b) & 1u)) << 32);
+      uint32_t v = 0xFFFFFFFFu;
+      if (fa && !xa) v = tick0 + ra;
+      if (fb && !xb) v = min(v, tick0 + rb);
+      const uint32_t newmin = __reduce_min_sync(GCA_FULL, v);
+      if (xa) dp[lane] = 0;        // burnt-out cell: fire_age ends at 0
+      if (xb) dp[lane + 32] = 0;
+      if (lane == src) {
+        if (second) { die1 = dmask; pl1[0] = pm[0]; pl1[1] = pm[1]; pl1[2] = pm[2]; rm.y = newmin; }
+        else { die0 = dmask; pl0[0] = pm[0]; pl0[1] = pm[1]; pl0[2] = pm[2]; rm.x = newmin; }
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- front of sub-step 0: compact it and start fetching its hidden / slope-factor sectors so
+  //      that their DRAM latency hides behind the key schedule.  The list is built ONCE per env
+  //      step; later sub-steps append the cells that joined the front (a handful) and skip the
+  //      entries that left it (ignited / no burning neighbour left) with a front bit-board test.
+  unsigned long long fr0, fr1;
+  front_masks(t0, t1, f0, f1, lane, fr0, fr1);
+  int T = build_front_list(sm, fr0, fr1, lane, 0);
+  bool dense = T > S64_CAP;  // more front cells than the list holds: rebuild per sub-step, in passes
+  int L = min(T, S64_CAP);
+  prefetch_front(sm, hidden, pslope, cell_base, 0, L, lane);
+  unsigned long long listed0 = fr0, listed1 = fr1;
+
+  key_schedule(sm, P, J, N, e, lane, key0, key1, widx);
+
+  const float lutreg = lane < 8 ? P.onep_veg[lane] : (lane < 16 ? P.onep_den[lane - 8] : 0.0f);
+  uint32_t n_draws = 0, n_thresh = 0, n_front = 0, n_ign = 0, n_ext = 0;
+  uint32_t work = 0;  // warp-uniform cost estimate of this env step (front cells and draws)
+  const float w1 = P.ring_w[1], w2 = P.ring_w[2], w3 = P.ring_w[3], w4 = P.ring_w[4];
+  const uint32_t age_magic = 0xFFFFFFFFu / P.age_span;
+  const bool any_doused = __ballot_sync(GCA_FULL, (dz.x | dz.y) != 0ull) != 0u;
+  const uint32_t* front32 = reinterpret_cast<const uint32_t*>(sm.frontbb);
+  uint32_t* ign32 = reinterpret_cast<uint32_t*>(sm.ign);
+
+  // ================================ K CA sub-steps, all on-chip ===================================
+  for (int j = 0; j < K; ++j) {
+    const uint32_t* sc = sm.sched[j];
+    const TfKey kburn = tf_key(sc[0], sc[1]);
+    const size_t inj_base = ((size_t)j * N + e) * 4096;
+    const float windreg = lane < 9 ? P.winds[(int)sc[8] * 9 + lane] : 0.0f;
+    if (j > 0) {
+      front_masks(t0, t1, f0, f1, lane, fr0, fr1);
+      if (!dense) {
+        const unsigned long long nw0 = fr0 & ~listed0, nw1 = fr1 & ~listed1;
+        const int nn = __popcll(nw0) + __popcll(nw1);
+        const int incl_n = warp_incl_scan(nn, lane);
+        const int tot_n = __shfl_sync(GCA_FULL, incl_n, 31);
+        if (L + tot_n > S64_CAP) {
+          dense = true;
+        } else if (tot_n > 0) {
+          int idx = L + incl_n - nn;
+          unsigned long long m = nw0;
+          int rowbits = (2 * lane) << 6;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            while (m) {
+              const uint32_t cell = (uint32_t)(rowbits | (__ffsll((long long)m) - 1));
+              m &= m - 1;
+              sm.list[idx++] = (uint16_t)cell;
+              if (hidden != nullptr) {
+                prefetch_l1(hidden + cell_base + cell);
+                if (pslope != nullptr) prefetch_l1(pslope + (cell_base + cell) * 8);
+              }
+            }
+            m = nw1;
+            rowbits = (2 * lane + 1) << 6;
+          }
+          L += tot_n;
+          listed0 |= nw0;
+          listed1 |= nw1;
+        }
+      }
+      if (dense) {
+        T = build_front_list(sm, fr0, fr1, lane, 0);
+        prefetch_front(sm, hidden, pslope, cell_base, 0, min(T, S64_CAP), lane);
+      }
+    }
+    sm.frontbb[2 * lane] = fr0;
+    sm.frontbb[2 * lane + 1] = fr1;
+    n_front += (uint32_t)(__popcll(fr0) + __popcll(fr1));
+    __syncwarp();
+
+    const int total = dense ? T : L;
+    work += 2u * (uint32_t)total;
+    for (int pass_base = 0; pass_base < total; pass_base += S64_CAP) {
+      if (pass_base > 0) {  // dense fires only: next slice of the list
+        build_front_list(sm, fr0, fr1, lane, pass_base);
+        prefetch_front(sm, hidden, pslope, cell_base, 0, min(S64_CAP, total - pass_base), lane);
+      }
+      const int cnt = min(S64_CAP, total - pass_base);
+      int PT = 0;
+      for (int base = 0; base < cnt; base += 32) {
+        const int t = base + lane;
+        const bool inrange = t < cnt;
+        const uint32_t cell = inrange ? sm.list[t] : 0u;
+        const int r = cell >> 6, c = cell & 63;
+        // still a front cell in this sub-step?
+        const bool valid = inrange && ((front32[cell >> 5] >> (cell & 31)) & 1u);
+        int hid = 3 | (3 << 3);
+        if (hidden != nullptr && valid) hid = hidden[cell_base + cell];
+        uint32_t A, B, C;
+        fire_window(sm, r, c, A, B, C);
+        // ring populations (Chebyshev rings 1..4 around the centre)
+        const int S1 = __popc(B & 0x00E07038u);
+        const int S2 = __popc(A & (0x07Cu << 18)) + __popc(B & 0x01F0F87Cu) + __popc(C & 0x07Cu);
+        const int S3 = __popc(A & ((0x0FEu << 9) | (0x0FEu << 18))) + __popc(B & 0x03F9FCFEu) +
+                       __popc(C & (0x0FEu | (0x0FEu << 9)));
+        const int S4 = __popc(A) + __popc(B) + __popc(C);
+        const float Hf = fmaf((float)(S4 - S3), w4,
+                              fmaf((float)(S3 - S2), w3, fmaf((float)(S2 - S1), w2, (float)S1 * w1)));
+        uint32_t dirm = ((B >> 3) & 7u) | (((B >> 12) & 7u) << 3) | (((B >> 21) & 7u) << 6);
+        dirm &= ~(1u << 4);
+        float Dlo = 0.0f, Dhi = 0.0f;
+        if (any_doused) {
+          const uint32_t dwin = dous_window(sm, r, c);
+          if (dwin) {
+            const int ni = __popc(dwin & ((0x0Eu << 5) | (0x0Eu << 10) | (0x0Eu << 15)));
+            const int nb = __popc(dwin) - ni;
+            const float Df = fmaf((float)nb, P.dous_border, (float)ni * P.dous_inner);
+            Dlo = __fmul_rn(Df, S64_LO);
+            Dhi = __fmul_rn(Df, S64_HI);
+          }
+        }
+        const float a = __shfl_sync(GCA_FULL, lutreg, clip15(hid & 7));
+        const float b = __shfl_sync(GCA_FULL, lutreg, 8 + clip15((hid >> 3) & 7));
+        const float ph_lo = __fsub_rn(__fmul_rn(Hf, S64_LO), Dhi);
+        const float ph_hi = __fsub_rn(__fmul_rn(Hf, S64_HI), Dlo);
+        const float blo = __fmul_rn(__fmul_rn(ph_lo, a), b);
+        const float bhi = __fmul_rn(__fmul_rn(ph_hi, a), b);
+        if (valid) { sm.base_lo[t] = blo; sm.base_hi[t] = bhi; }
+        const int nd = (valid && bhi > 0.0f) ? __popc(dirm) : 0;
+        const int incl2 = warp_incl_scan(nd, lane);
+        int off = PT + incl2 - nd;
+        const uint32_t em = nd ? dirm : 0u;
+        const uint32_t tag = (uint32_t)t << 4;
+#pragma unroll
+        for (uint32_t d = 0; d < 9; ++d) {
+          if (d == 4) continue;
+          if (em & (1u << d)) sm.pairs[off++] = (uint16_t)(tag | d);
+        }
+        PT += __shfl_sync(GCA_FULL, incl2, 31);
+
+        // ---- draw phase (single call site): when the buffer could overflow next round, or at the
+        //      end of the pass.  Two draws per lane per iteration = two independent threefry chains.
+        if (PT + 256 > S64_PCAP || base + 32 >= cnt) {
+          __syncwarp();
+          for (int q0 = 0; q0 < PT; q0 += 64) {
+            uint32_t ca, cb = 0;
+            const bool ia = eval_pair(sm, P, hidden, pslope, j_u_burn, mode, kburn, windreg, cell_base, inj_base,
+                                      q0 + lane, PT, ca, n_thresh);
+            bool ib = false;
+            if (q0 + 32 < PT)
+              ib = eval_pair(sm, P, hidden, pslope, j_u_burn, mode, kburn, windreg, cell_base, inj_base,
+                             q0 + 32 + lane, PT, cb, n_thresh);
+            if (ia) atomicOr(&ign32[ca >> 5], 1u << (ca & 31));
+            if (ib) atomicOr(&ign32[cb >> 5], 1u << (cb & 31));
+          }
+          n_draws += (lane == 0) ? (uint32_t)PT : 0u;
+          work += (uint32_t)PT;
+          PT = 0;
+          __syncwarp();
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- apply: ignitions (with their fire-age draws), burn-outs, regrowth ------------------------
+    const unsigned long long I0 = sm.ign[2 * lane], I1 = sm.ign[2 * lane + 1];
+    const int ni_l = __popcll(I0) + __popcll(I1);
+    const int incl_i = warp_incl_scan(ni_l, lane);
+    const int NI = __shfl_sync(GCA_FULL, incl_i, 31);
+    if (NI > 0) {
+      sm.ign[2 * lane] = 0ull;
+      sm.ign[2 * lane + 1] = 0ull;
+      const TfKey ka1 = tf_key(sc[4], sc[5]), ka2 = tf_key(sc[6], sc[7]);
+      uint32_t* dt = reinterpret_cast<uint32_t*>(sm.base_lo);  // burn-out tick per listed ignition
+      for (int base = 0; base < NI; base += S64_CAP) {
+        {
+          int idx = incl_i - ni_l - base;
+          unsigned long long m = I0;
+          int rowbits = (2 * lane) << 6;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            while (m) {
+              const int c = __ffsll((long long)m) - 1;
+              m &= m - 1;
+              if ((unsigned)idx < (unsigned)S64_CAP) sm.pairs[idx] = (uint16_t)(rowbits | c);
+              ++idx;
+            }
+            m = I1;
+            rowbits = (2 * lane + 1) << 6;
+          }
+        }
+        __syncwarp();
+        const int cnt = min(S64_CAP, NI - base);
+        // two lanes per ignition: randint needs two independent words (jax.random.randint)
+        for (int tb = 0; tb < 2 * cnt; tb += 32) {
+          const int task = tb + lane, i = task >> 1;
+          const bool valid = i < cnt;
+          const uint32_t cell = sm.pairs[valid ? i : 0];
+          uint32_t bits = 0;
+          if (j_age_new == nullptr) bits = bits_at_ni((lane & 1) ? ka2 : ka1, cell, S64_HALF_CELL, mode);
+          const uint32_t other = __shfl_xor_sync(GCA_FULL, bits, 1);
+          if (valid && !(lane & 1)) {
+            int age;
+            if (j_age_new) age = j_age_new[inj_base + cell];
+            else {
+              const uint32_t hm = fastmod(bits, P.age_span, age_magic), lm = fastmod(other, P.age_span, age_magic);
+              age = P.age_lo + (int)fastmod(hm * P.age_mult + lm, P.age_span, age_magic);
+            }
+            const uint32_t dabs = tick0 + (uint32_t)j + (uint32_t)age;  // burn-out tick
+            S.death[cell_base + cell] = (uint16_t)dabs;
+            dt[i] = dabs;
+          }
+        }
+        __syncwarp();
+        {
+          int idx = incl_i - ni_l - base;
+          for (int q = __popcll(I0); q > 0; --q, ++idx)
+            if ((unsigned)idx < (unsigned)S64_CAP) rm.x = min(rm.x, dt[idx]);
+          for (int q = __popcll(I1); q > 0; --q, ++idx)
+            if ((unsigned)idx < (unsigned)S64_CAP) rm.y = min(rm.y, dt[idx]);
+        }
+        __syncwarp();
+      }
+    }
+    unsigned long long ext0 = die0, ext1 = die1;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      ext0 &= ((j >> b) & 1) ? pl0[b] : ~pl0[b];
+      ext1 &= ((j >> b) & 1) ? pl1[b] : ~pl1[b];
+    }
+    unsigned long long g0 = 0, g1 = 0;
+    if (P.p_tree > 0.0f) regrow_rows(P, J, tf_key(sc[2], sc[3]), inj_base, lane, ~(t0 | f0), ~(t1 | f1), g0, g1);
+    n_ign += ni_l;
+    n_ext += __popcll(ext0) + __popcll(ext1);
+    ch0 |= I0 | ext0 | g0;
+    ch1 |= I1 | ext1 | g1;
+    t0 = (t0 & ~I0) | g0;
+    t1 = (t1 & ~I1) | g1;
+    f0 = (f0 & ~ext0) | I0;
+    f1 = (f1 & ~ext1) | I1;
+    if (j + 1 < K) {
+      store_row_views(sm.fire32 + (2 * lane + 4) * 4, f0);
+      store_row_views(sm.fire32 + (2 * lane + 5) * 4, f1);
+    }
+    __syncwarp();
+  }
+
+  // ---- sparse in-place write-back of the cells that changed --------------------------------------
+  {
+    unsigned long long ch = ch0;
+    unsigned long long tt = t0, ff = f0;
+    int row = 2 * lane;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      while (ch) {
+        const int c = __ffsll((long long)ch) - 1;
+        ch &= ch - 1;
+        const uint8_t code = ((ff >> c) & 1ull) ? 2 : (((tt >> c) & 1ull) ? 1 : 0);
+        S.cell[cell_base + row * 64 + c] = code;
+      }
+      ch = ch1;
+      tt = t1; ff = f1;
+      row = 2 * lane + 1;
+    }
+  }
+  reinterpret_cast<uint2*>(S.row_min + (size_t)e * 64)[lane] = rm;
+  const int tcount = __reduce_add_sync(GCA_FULL, __popcll(t0) + __popcll(t1));
+  const int fcount = __reduce_add_sync(GCA_FULL, __popcll(f0) + __popcll(f1));
+
+  if (O.stats != nullptr) {
+    const uint32_t a = __reduce_add_sync(GCA_FULL, n_front), b = __reduce_add_sync(GCA_FULL, n_draws);
+    const uint32_t c = __reduce_add_sync(GCA_FULL, n_ign), d = __reduce_add_sync(GCA_FULL, n_ext);
+    const uint32_t t = __reduce_add_sync(GCA_FULL, n_thresh);
+    if (lane == 0) {
+      atomicAdd(&O.stats[0], (unsigned long long)a);
+      atomicAdd(&O.stats[1], (unsigned long long)b);
+      atomicAdd(&O.stats[2], (unsigned long long)c);
+      atomicAdd(&O.stats[3], (unsigned long long)d);
+      if (t) atomicAdd(&O.stats[4], (unsigned long long)t);
+      atomicAdd(&O.stats[5], 1ull);
+    }
+  }
+
+  // ---- per-env scalars: key chain, wind, clock, move, douse, day/night, reward, done -------------
+  const bool ca_only = (flags & GCA_FLAG_CA_ONLY) != 0;
+  const bool done = fcount == 0;
+  if (lane == 0) {
+    S.key[2 * e] = key0;
+    S.key[2 * e + 1] = key1;
+    S.wind_index[e] = widx;
+    if (S.work != nullptr) S.work[e] = (flags & GCA_FLAG_WORK_CYCLES) ? (uint32_t)(clock64() - clk0) : work;
+    S.tick[e] = tick0 + (uint32_t)K;
+    const float rew = award(tcount, fcount);
+    if (!ca_only) {
+      // all loads first (they may alias the stores below as far as the compiler knows)
+      const int a0 = actions[3 * e], a1 = actions[3 * e + 1];
+      const float t_old = S.time[e];
+      int row = S.position[2 * e], col = S.position[2 * e + 1];
+      const int ts = S.time_step[e] + 1;
+      int night = S.is_night[e];
+      const float se = S.steps_elapsed ? S.steps_elapsed[e] : 0.0f;
+      const float ra = S.reward_accumulated ? S.reward_accumulated[e] : 0.0f;
+      const int a0c = min(max(a0, 0), 8), a1c = min(max(a1, 0), 1);
+      // clock (repeat_ca_jax.py:35-41): new = time + ((t_move + t_shoot) + t_any); keep the fraction
+      const float tt = __fadd_rn(__fadd_rn(P.t_move[a0c], P.t_shoot[a1c]), P.t_any);
+      const float nt = __fadd_rn(t_old, tt);
+      move_position(a0, 64, 64, row, col);
+      unsigned long long drow = 0ull;
+      if (a1 == 1) drow = S.doused[(size_t)e * 64 + row];
+      S.time[e] = __fsub_rn(nt, truncf(nt));
+      S.position[2 * e] = row;
+      S.position[2 * e + 1] = col;
+      if (a1 == 1) S.doused[(size_t)e * 64 + row] = drow | (1ull << col);
+      S.time_step[e] = ts;
+      if (O.obs_night) O.obs_night[e] = (uint8_t)night;
+      if (ts % P.day_length == 0) night = 1 - night;
+      S.is_night[e] = night;
+      if (S.steps_elapsed) S.steps_elapsed[e] = __fadd_rn(se, 1.0f);
+      if (S.reward_accumulated) S.reward_accumulated[e] = __fadd_rn(ra, rew);
+    }
+    if (O.step_reward) O.step_reward[e] = rew;
+    if (O.terminated) O.terminated[e] = done ? 1 : 0;
+    if (O.counts) { O.counts[2 * e] = tcount; O.counts[2 * e + 1] = fcount; }
+    if (O.reward && !((flags & GCA_FLAG_AUTO_RESET) && done)) O.reward[e] = rew;
+  }
+
+  // ---- fused conditional_reset (advanced_bulldozer.py:422-518) ------------------------------------
+  if ((flags & GCA_FLAG_AUTO_RESET) && done) {
+    __syncwarp();
+    const uint4* sc4 = reinterpret_cast<const uint4*>(SNAP.cell + cell_base);
+    uint4* dc4 = reinterpret_cast<uint4*>(S.cell + cell_base);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dc4[i * 32 + lane] = sc4[i * 32 + lane];
+    const uint4* sd4 = reinterpret_cast<const uint4*>(SNAP.death + cell_base);
+    uint4* dd4 = reinterpret_cast<uint4*>(S.death + cell_base);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dd4[i * 32 + lane] = sd4[i * 32 + lane];
+    reinterpret_cast<ulonglong2*>(S.doused + (size_t)e * 64)[lane] =
+        reinterpret_cast<const ulonglong2*>(SNAP.doused + (size_t)e * 64)[lane];
+    reinterpret_cast<uint2*>(S.row_min + (size_t)e * 64)[lane] =
+        reinterpret_cast<const uint2*>(SNAP.row_min + (size_t)e * 64)[lane];
+    if (lane == 0) {
+      S.key[2 * e] = SNAP.key[2 * e];
+      S.key[2 * e + 1] = SNAP.key[2 * e + 1];
+      S.wind_index[e] = SNAP.wind_index[e];
+      S.position[2 * e] = SNAP.position[2 * e];
+      S.position[2 * e + 1] = SNAP.position[2 * e + 1];
+      S.time[e] = SNAP.time[e];
+      S.tick[e] = SNAP.tick[e];
+      if (S.steps_elapsed) S.steps_elapsed[e] = 0.0f;
+      if (S.reward_accumulated) S.reward_accumulated[e] = 0.0f;
+      if (O.reward) O.reward[e] = snap_reward[e];
+    }
+  }
+}
+
+}  // namespace warpimpl
+using namespace warpimpl;
+
+cudaError_t launch_env_step64_warp(const gca_params& p, const gca_state& s, const int32_t* actions,
+                              const gca_step_out& out, const gca_inject& inj, const gca_state& snap,
+                              const float* snap_reward, uint32_t flags, cudaStream_t st) {
+  const int blocks = (s.N + S64_WARPS - 1) / S64_WARPS;
+  const dim3 g(blocks), b(S64_WARPS * 32);
+  const bool injected = inj.u_burn || inj.u_grow || inj.age_new || inj.u_wind || inj.wind_step;
+  const int hp = (!s.hidden && !s.pslope) ? 0 : ((s.hidden && s.pslope) ? 1 : -1);
+#define GCA_LAUNCH64(M, H, I) env_step64_warp_kernel<M, H, I><<<g, b, 0, st>>>(p, s, actions, out, inj, snap, snap_reward, flags)
+  if (injected || hp < 0) GCA_LAUNCH64(-1, -1, true);
+  else if (p.rng_mode == GCA_RNG_LEGACY) { if (hp) GCA_LAUNCH64(GCA_RNG_LEGACY, 1, false); else GCA_LAUNCH64(GCA_RNG_LEGACY, 0, false); }
+  else { if (hp) GCA_LAUNCH64(GCA_RNG_PARTITIONABLE, 1, false); else GCA_LAUNCH64(GCA_RNG_PARTITIONABLE, 0, false); }
+#undef GCA_LAUNCH64
+  return cudaGetLastError();
+}
+
+}  // namespace gca

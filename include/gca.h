@@ -51,6 +51,7 @@ typedef enum gca_status {
 #define GCA_FLAG_NO_HIDDEN 2u   /* hidden layers off: veg = den = 3, slope factor 1 (pslope may be NULL) */
 #define GCA_FLAG_CA_ONLY 4u     /* run only the CA sub-steps (no clock/move/douse/reward bookkeeping) */
 #define GCA_FLAG_NO_TMA 8u      /* tiled path: stage tiles with plain loads instead of TMA */
+#define GCA_FLAG_WORK_CYCLES 16u /* diagnostics: work[e] receives the elapsed SM clock cycles of env e's step instead of the cost estimate */
 
 /* Constants of one environment family (host POD, passed to kernels by value). */
 typedef struct gca_params {
