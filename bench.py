@@ -46,8 +46,8 @@ def parse():
     ap.add_argument("--no-hidden", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-envs", type=int, default=64)
-    ap.add_argument("--cpu-steps", type=int, default=24)
+    ap.add_argument("--cpu-envs", type=int, default=256, help="envs of the CPU sample (cpu_baseline leg and --impl reference)")
+    ap.add_argument("--cpu-steps", type=int, default=160, help="env steps of the cpu_baseline sample (about 10-20 s of host work)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--ruleset", default="alexandridis", choices=["alexandridis", "v3"],
                     help="v3 = the registered ForestFireBulldozer256x256-v3 rule set (WindyForestFire), an extra line")
@@ -91,13 +91,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # every step of this arm is a bounded sample of the workload: cpu_envs envs instead of envs_per_gpu,
+    # the requested --steps / --warmup are honoured as given
     n_envs = args.cpu_envs
-    steps = max(1, min(args.steps, args.cpu_steps))
-    warmup = max(1, min(args.warmup, 3))
+    steps = max(1, args.steps)
+    warmup = max(0, args.warmup)
     r = cpu_port_throughput(args.size, args.substeps, n_envs, steps, warmup, args.rng_mode, not args.no_hidden,
                             args.seed)
-    sample = (f"{n_envs} envs x {steps} env steps ({args.substeps} CA sub-steps each) of the {args.size}x{args.size} "
-              f"workload, dense C port of the reference step (oracle/gca_oracle.c), OpenMP over envs")
+    sample = (f"each step = {n_envs} envs (of the workload's {args.envs_per_gpu}) x 1 env step ({args.substeps} CA sub-steps) "
+              f"of the {args.size}x{args.size} workload; dense C port of the reference step (oracle/gca_oracle.c), "
+              f"OpenMP over envs on {r['threads']} host threads")
     line = {
         "impl": "reference", "metric": "cell_updates_per_s", "value": r["cell_updates_per_s"],
         "unit": "cell-updates/s", "env_steps_per_s": r["env_steps_per_s"], "n_gpus": args.gpus,
@@ -194,6 +197,7 @@ def run_ours(args):
         env.step_device(acts[i])
     torch.cuda.synchronize()
     stats0 = env.stats()
+    launches0 = env.kernel_launches
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -213,6 +217,7 @@ def run_ours(args):
         dist.barrier()
     ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
     stats1 = env.stats()
+    launches = env.kernel_launches - launches0  # env_step64_kernel per step + the re-balancing sort every few steps
     # L2-warm variant: back-to-back launches, one event pair
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -221,7 +226,6 @@ def run_ours(args):
     e1.record()
     torch.cuda.synchronize()
     ms_warm = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sampler else None
 
     # ---- end to end through the host API: pinned host actions in, reward/terminated out, per step
     h_act = acts[args.warmup:args.warmup + args.steps].cpu().pin_memory()
@@ -239,6 +243,7 @@ def run_ours(args):
         h_term.copy_(out.terminated, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads reward/done every step
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None  # sampled over the timed loops above (device-timed, L2-warm, end-to-end)
 
     # ---- episode statistics all-gather (the only collective of the path)
     ep = torch.stack([env._state.steps_elapsed, env._state.reward_accumulated], dim=1).contiguous()
@@ -290,7 +295,7 @@ def run_ours(args):
                 "env_steps_per_s": total_envs * args.steps / e2e_s,
                 "h2d_bytes_per_step": int(N * 3 * 4), "d2h_bytes_per_step": int(N * 5),
                 "what": "pinned host actions -> H2D -> gca_env_step -> D2H reward+terminated, stream sync every step"},
-        "gpu_launches": args.steps, "clocks": clocks,
+        "gpu_launches": launches, "clocks": clocks,
         "workload_stats": {"front_cells_per_env_substep": d[0] / sub, "draws_per_env_substep": d[1] / sub,
                            "ignitions_per_env_substep": d[2] / sub, "burnouts_per_env_substep": d[3] / sub,
                            "threshold_cells": int(d[4])},

@@ -60,6 +60,16 @@ class GcaStepOut(C.Structure):
                 ("counts", C.c_void_p), ("obs_night", C.c_void_p), ("stats", C.c_void_p)]
 
 
+_EPISODE_FIELDS = ("episode_returns", "episode_lengths", "returned_episode_returns", "returned_episode_lengths",
+                   "amount_finished", "recent_returns", "recent_lengths", "recent_idx", "current_day_correct",
+                   "current_night_correct", "current_day_steps", "current_night_steps", "recent_day_correct",
+                   "recent_night_correct", "recent_day_steps", "recent_night_steps")
+
+
+class GcaEpisodeStats(C.Structure):
+    _fields_ = [(f, C.c_void_p) for f in _EPISODE_FIELDS]
+
+
 class GcaInject(C.Structure):
     _fields_ = [("u_burn", C.c_void_p), ("u_grow", C.c_void_p), ("age_new", C.c_void_p),
                 ("u_wind", C.c_void_p), ("wind_step", C.c_void_p)]
@@ -125,6 +135,7 @@ def load():
     lib.gca_pack_state.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState)] + [C.c_void_p] * 8
     lib.gca_unpack_state.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState)] + [C.c_void_p] * 4
     lib.gca_balance_order.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gca_episode_stats_update.argtypes = [C.c_int32, C.POINTER(GcaEpisodeStats)] + [C.c_void_p] * 6
     lib.gca_windy_env_step.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7 + [C.c_int32, C.c_double,
                                       C.c_double, C.c_double] + [C.c_void_p] * 5
     lib.gca_windy_pack.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 4
@@ -138,7 +149,7 @@ def load():
 # every symbol include/gca.h declares (tests check the library exports all of them)
 EXPORTS = ("gca_version", "gca_last_error", "gca_params_init", "gca_env_step", "gca_alexandridis_step",
            "gca_move_modify", "gca_reward_done", "gca_conditional_reset", "gca_render_rgb", "gca_pack_state",
-           "gca_unpack_state", "gca_balance_order", "gca_windy_env_step", "gca_windy_pack", "gca_windy_unpack",
+           "gca_unpack_state", "gca_balance_order", "gca_episode_stats_update", "gca_windy_env_step", "gca_windy_pack", "gca_windy_unpack",
            "gca_threefry_bits", "gca_threefry_split")
 
 

@@ -20,6 +20,8 @@ cudaError_t launch_render(const gca_params&, int, const uint8_t*, const uint64_t
 cudaError_t launch_threefry_bits(const uint32_t*, long long, int, uint32_t*, cudaStream_t);
 cudaError_t launch_threefry_split_part(const uint32_t*, int, uint32_t*, cudaStream_t);
 cudaError_t launch_balance_order(int, const uint32_t*, int32_t*, cudaStream_t);
+cudaError_t launch_episode_stats(int, const gca_episode_stats&, const float*, const uint8_t*, const uint8_t*,
+                                 const uint8_t*, const int32_t*, cudaStream_t);
 cudaError_t launch_windy_step(int, int, int, unsigned long long*, unsigned long long*, int32_t*, double*, const int32_t*,
                               const double*, const double*, int, double, double, double, double*, uint8_t*, int32_t*,
                               int32_t*, cudaStream_t);
@@ -243,6 +245,18 @@ int gca_unpack_state(const gca_params* p, const gca_state* s, float* true_grid, 
   if (rc) return rc;
   return check_cuda(gca::launch_unpack(*p, *s, true_grid, fire_age, dousing_count, (cudaStream_t)stream),
                     "unpack_state");
+}
+
+int gca_episode_stats_update(int32_t N, const gca_episode_stats* st, const float* step_reward,
+                             const uint8_t* terminated, const uint8_t* truncated, const uint8_t* obs_night,
+                             const int32_t* actions, void* stream) {
+  if (N <= 0 || !st || !step_reward || !terminated || !actions)
+    return fail(GCA_ERR_ARG, "gca_episode_stats_update: null argument");
+  const void* const* fields = reinterpret_cast<const void* const*>(st);
+  for (size_t i = 0; i < sizeof(gca_episode_stats) / sizeof(void*); ++i)
+    if (!fields[i]) return fail(GCA_ERR_ARG, "gca_episode_stats_update: every gca_episode_stats pointer must be set");
+  return check_cuda(gca::launch_episode_stats(N, *st, step_reward, terminated, truncated, obs_night, actions,
+                                              (cudaStream_t)stream), "episode_stats");
 }
 
 int gca_balance_order(int32_t N, const uint32_t* work, int32_t* order, void* stream) {

@@ -312,6 +312,81 @@ __global__ void __launch_bounds__(1024) balance_order_kernel(int N, int wpc, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// Episode statistics of the rollout loop (agents/jax_ppo.py:504-655), one CTA for all envs: thread t
+// owns the contiguous env range [t*C, (t+1)*C), so a block scan of the per-thread finished counts
+// gives every finished env its rank in env order -- the order the reference's serial scan visits.
+// Only the last 10 ranks survive in the ring, and they land on distinct slots.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) episode_stats_kernel(int N, const __grid_constant__ gca_episode_stats E,
+                                                             const float* __restrict__ step_reward,
+                                                             const uint8_t* __restrict__ terminated,
+                                                             const uint8_t* __restrict__ truncated,
+                                                             const uint8_t* __restrict__ obs_night,
+                                                             const int32_t* __restrict__ actions) {
+  __shared__ int s_cnt[1024];
+  __shared__ int s_term[32];
+  const int tid = threadIdx.x;
+  const int C = (N + 1023) / 1024;
+  const int lo = min(N, tid * C), hi = min(N, lo + C);
+  int nfin = 0, nterm = 0;
+  for (int i = lo; i < hi; ++i) {
+    const float new_ret = __fadd_rn(E.episode_returns[i], step_reward[i]);
+    const int new_len = E.episode_lengths[i] + 1;
+    const int night = obs_night ? (int)obs_night[i] : 0;
+    const int ext = actions[3 * i + 2];
+    E.current_day_correct[i] += (1 - night) * (ext == 2 ? 1 : 0);
+    E.current_night_correct[i] += night * (ext == 1 ? 1 : 0);
+    E.current_day_steps[i] += 1 - night;
+    E.current_night_steps[i] += night;
+    const int term = terminated[i], trunc = truncated ? truncated[i] : 0;
+    const bool fin = (term + trunc) != 0;
+    nterm += term;
+    nfin += fin ? 1 : 0;
+    // (new) * (1 - terminated) * (1 - truncated)
+    E.episode_returns[i] = __fmul_rn(__fmul_rn(new_ret, (float)(1 - term)), (float)(1 - trunc));
+    E.episode_lengths[i] = new_len * (1 - term) * (1 - trunc);
+    if (fin) {
+      E.returned_episode_returns[i] = new_ret;
+      E.returned_episode_lengths[i] = new_len;
+    }
+  }
+  s_cnt[tid] = nfin;
+  const int wsum = __reduce_add_sync(0xFFFFFFFFu, nterm);
+  if ((tid & 31) == 0) s_term[tid >> 5] = wsum;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {  // inclusive Hillis-Steele scan
+    const int v = tid >= d ? s_cnt[tid - d] : 0;
+    __syncthreads();
+    s_cnt[tid] += v;
+    __syncthreads();
+  }
+  const int F = s_cnt[1023];
+  const int idx0 = E.recent_idx[0];
+  int rank = s_cnt[tid] - nfin;
+  __syncthreads();
+  for (int i = lo; i < hi; ++i) {
+    const int term = terminated[i], trunc = truncated ? truncated[i] : 0;
+    if ((term + trunc) == 0) continue;
+    if (rank >= F - GCA_RECENT) {
+      const int slot = (idx0 + rank) % GCA_RECENT;
+      E.recent_returns[slot] = E.returned_episode_returns[i];
+      E.recent_lengths[slot] = E.returned_episode_lengths[i];
+      E.recent_day_correct[slot] = E.current_day_correct[i];
+      E.recent_night_correct[slot] = E.current_night_correct[i];
+      E.recent_day_steps[slot] = E.current_day_steps[i];
+      E.recent_night_steps[slot] = E.current_night_steps[i];
+    }
+    ++rank;
+  }
+  if (tid == 0) {
+    int t = 0;
+    for (int w = 0; w < 32; ++w) t += s_term[w];
+    E.amount_finished[0] += t;
+    E.recent_idx[0] = (idx0 + F) % GCA_RECENT;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // PRNG test hooks
 // ---------------------------------------------------------------------------------------------
 __global__ void threefry_bits_kernel(const uint32_t* __restrict__ key, long long n, int mode, uint32_t* out) {
@@ -403,6 +478,12 @@ cudaError_t launch_render(const gca_params& p, int N, const uint8_t* cell, const
   else
     render_rgb_kernel<false><<<blocks, 256, 0, st>>>(p, N, cell, (const unsigned long long*)doused, position, night,
                                                      ext_action, env_mask, enable_ext, flags_scratch, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_episode_stats(int N, const gca_episode_stats& e, const float* step_reward, const uint8_t* terminated,
+                                 const uint8_t* truncated, const uint8_t* obs_night, const int32_t* actions,
+                                 cudaStream_t st) {
+  episode_stats_kernel<<<1, 1024, 0, st>>>(N, e, step_reward, terminated, truncated, obs_night, actions);
   return cudaGetLastError();
 }
 cudaError_t launch_balance_order(int N, const uint32_t* work, int32_t* order, cudaStream_t st) {

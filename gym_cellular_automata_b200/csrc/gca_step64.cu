@@ -29,6 +29,8 @@
 //    per-row minimum tells which rows hold a cell that burns out in this step.
 //  * the key chain of jax.random.split is evaluated by lane pairs; clock, move, douse, day/night,
 //    reward (popc + warp reduce), done and the optional auto-reset are fused in the epilogue.
+#include <cstddef>
+
 #include "gca_common.cuh"
 
 namespace gca {
@@ -50,19 +52,26 @@ constexpr uint32_t S64_HALF_CELL = 4096u / 2u;
 struct __align__(16) EnvSmem {
   uint32_t fire32[72 * 4];          // fire rows -4..67, 4 overlapping 32-bit views per row
   uint32_t dous32[68 * 4];          // doused rows -2..65, same views
-  unsigned long long ign[64];       // ignition accumulator of the sub-step (unpack: tree rows)
+  unsigned long long ign[64];       // ignition accumulator of the sub-step (prologue: landing zone of the doused rows)
+  // ---- the next four arrays (4096 bytes) double as the landing zone of the env's u8 grid (bulk copy) ----
   unsigned long long burn[64][4];   // rows with burn-outs in this env step: mask, sub-step bit planes 0..2
   unsigned long long listed[64];    // cells that are (or were) on the front list
   float base[S64_CAP];              // per listed cell: upper bound of (p_h (1+p_veg)) (1+p_den); negative =
-                                    //   dousing nearby, no cheap lower bound (unpack: fire rows; apply: ticks)
+                                    //   dousing nearby, no cheap lower bound (apply: burn-out ticks)
   uint16_t list[S64_CAP];           // front cells: (row << 6) | col
+  // ---------------------------------------------------------------------------------------------------------
   uint32_t sched[GCA_MAX_K][12];    // per sub-step: Sburn[2] Sgrow[2] ak1[2] ak2[2] wind change step pad
   uint4 hot;                        // current sub-step: Sburn k0, k1, k0^k1^C ; env index
   float wind[12];                   // current sub-step: wind matrix (9 used)
   int cnt;                          // list entries of the current pass
   uint32_t dous_even, dous_odd;     // bit l: some doused cell within 2 rows of row 2l / 2l+1
   uint32_t npairs;                  // draws of this env step (cost estimate)
+  unsigned long long mbar;          // completion barrier of the prologue's bulk copies
+  unsigned long long pad;
 };
+static_assert(offsetof(EnvSmem, list) + sizeof(uint16_t) * S64_CAP - offsetof(EnvSmem, burn) == 4096,
+              "burn/listed/base/list must be 4096 contiguous bytes (landing zone of the u8 grid)");
+static_assert(offsetof(EnvSmem, burn) % 16 == 0 && offsetof(EnvSmem, ign) % 16 == 0, "bulk copies need 16-byte alignment");
 
 struct __align__(16) CtaSmem {
   EnvSmem env[S64_E];
@@ -71,6 +80,22 @@ struct __align__(16) CtaSmem {
   int next;                         // work-item counter of the pooled phase
   int pad[3];
 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 1-D bulk copy global -> shared by the TMA unit (16-byte aligned, size a multiple of 16), completion on mbar
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+  }
+}
 
 __device__ __forceinline__ void prefetch_l1(const void* p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
@@ -151,31 +176,43 @@ __device__ __forceinline__ void assemble_split(int mode, uint32_t w, uint32_t o0
 }
 
 // Key schedule of K successive PartiallyObservableForestFireJax.update calls
-// (ca_alexandridis_jax.py:436-448 and :352-368).  The chain K0 -> K1 -> K2 -> K3 is sequential
-// (3K split levels, every lane pair runs it redundantly -- free in SIMT); pair 2j then derives
-// sub-step j's Sburn / Sgrow / randint keys and pair 2j+1 its wind draws (4 more levels).
-__device__ __noinline__ void key_schedule(EnvSmem& sm, const gca_params& P, const gca_inject& J, int N, int e,
-                                          int lane, uint32_t& key0, uint32_t& key1, int& widx) {
+// (ca_alexandridis_jax.py:436-448 and :352-368), in two parts so that each can overlap one of the
+// prologue's memory bursts.  key_chain: K0 -> K1 -> K2 -> K3 is sequential (3K split levels, every
+// lane pair runs it redundantly -- free in SIMT); pair 2j keeps sub-step j's S1 and pair 2j+1 its
+// Swind / Sidx.  key_sides: pair 2j derives Sburn / Sgrow / the randint keys of sub-step j and pair
+// 2j+1 its wind draws (4 more levels), then the wind index is threaded through the sub-steps.
+struct KeySides {
+  uint32_t c0, c1, sw0, sw1;
+};
+__device__ __noinline__ KeySides key_chain(const gca_params& P, int lane, uint32_t& key0, uint32_t& key1) {
   const int K = P.K, mode = P.rng_mode;
   const int pair = lane >> 1;
-  const uint32_t w = lane & 1;
   uint32_t k0 = key0, k1 = key1;
-  uint32_t c0 = 0, c1 = 0, sw0 = 0, sw1 = 0;
+  KeySides r;
+  r.c0 = r.c1 = r.sw0 = r.sw1 = 0u;
 #pragma unroll 1
   for (int j = 0; j < K; ++j) {
     uint32_t n0, n1, s0, s1;
     split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K1, S1
-    if (pair == 2 * j) { c0 = s0; c1 = s1; }
+    if (pair == 2 * j) { r.c0 = s0; r.c1 = s1; }
     k0 = n0; k1 = n1;
     split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K2, Swind
-    if (pair == 2 * j + 1) { sw0 = s0; sw1 = s1; }
+    if (pair == 2 * j + 1) { r.sw0 = s0; r.sw1 = s1; }
     k0 = n0; k1 = n1;
     split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K3, Sidx
-    if (pair == 2 * j + 1) { c0 = s0; c1 = s1; }
+    if (pair == 2 * j + 1) { r.c0 = s0; r.c1 = s1; }
     k0 = n0; k1 = n1;
   }
   key0 = k0;
   key1 = k1;
+  return r;
+}
+__device__ __noinline__ void key_sides(EnvSmem& sm, const gca_params& P, const gca_inject& J, int N, int e,
+                                       int lane, const KeySides ks, int& widx) {
+  const int K = P.K, mode = P.rng_mode;
+  const int pair = lane >> 1;
+  const uint32_t w = lane & 1;
+  const uint32_t c0 = ks.c0, c1 = ks.c1, sw0 = ks.sw0, sw1 = ks.sw1;
   const bool burn_role = (pair & 1) == 0;
   const int j = pair >> 1;
   const uint32_t sc0 = (mode == GCA_RNG_LEGACY) ? w : 0u;       // split counters of this lane
@@ -414,6 +451,14 @@ __device__ __forceinline__ void front_masks(unsigned long long t0, unsigned long
   fr1 = t1 & (fh0 | fh1 | shfl64_down1(fh0, lane));
 }
 
+// S64_TRACE (diagnostic builds only): per-env phase timestamps (SM clock, relative to the warp's start) go to
+// O.stats[8 + 16 e ...]; the caller must have allocated stats with 8 + 24 N words.
+#ifdef S64_TRACE
+#define S64_STAMP(k) do { if (active && lane == 0 && O.stats) O.stats[8 + 24 * (size_t)e + (k)] = (unsigned long long)(clock64() - clk0); } while (0)
+#else
+#define S64_STAMP(k) do { } while (0)
+#endif
+
 #ifndef S64_MINB
 #define S64_MINB (28 / S64_E)  // 28 warps/SM x 72 registers = the whole register file; 4096 envs = one wave
 #endif
@@ -457,28 +502,23 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   uint32_t work = 0;  // warp-uniform cost estimate of this env step (front cells; draws are added at the end)
 
   if (active) {
-    // ---- coalesced 128-bit read of the u8 grid -> tree / fire row masks -------------------------
-    {
-      uint4 cv[8];
-      const uint4* cptr = reinterpret_cast<const uint4*>(S.cell + cell_base);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) cv[i] = cptr[i * 32 + lane];
-      uint16_t* trow = reinterpret_cast<uint16_t*>(sm.ign);
-      uint16_t* frow = reinterpret_cast<uint16_t*>(sm.base);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint32_t t16, f16;
-        cells16_to_bits(cv[i], t16, f16);
-        const int chunk = i * 32 + lane;  // row = chunk >> 2, quarter = chunk & 3
-        trow[chunk] = (uint16_t)t16;
-        frow[chunk] = (uint16_t)f16;
-      }
-    }
-    const ulonglong2 dz = reinterpret_cast<const ulonglong2*>(S.doused + (size_t)e * 64)[lane];
-    rm = reinterpret_cast<const uint2*>(S.row_min + (size_t)e * 64)[lane];
-    tick0 = S.tick[e];
-    key0 = S.key[2 * e];
+    // ---- the env's u8 grid (4 KB), doused rows and row minima: three bulk copies into shared memory,
+    //      in flight while this warp walks the key chain ----------------------------------------------
+    const uint32_t mbar = smem_u32(&sm.mbar);
+    key0 = S.key[2 * e];  // ahead of the bulk copies: the key chain below starts as soon as it is here
     key1 = S.key[2 * e + 1];
+    S64_STAMP(16);
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(4096u + 512u + 256u) : "memory");
+      bulk_g2s(sm.burn, S.cell + cell_base, 4096u, mbar);
+      bulk_g2s(sm.ign, S.doused + (size_t)e * 64, 512u, mbar);
+      bulk_g2s(wp, S.row_min + (size_t)e * 64, 256u, mbar);
+    }
+    __syncwarp();
+    S64_STAMP(17);
+    tick0 = S.tick[e];
     widx = S.wind_index[e];
     if (!(flags & GCA_FLAG_CA_ONLY)) {
       // the per-env scalars of the epilogue (lane 0, serial): get their lines on the way now
@@ -497,6 +537,33 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     }
     if (lane < 16) sm.fire32[lane] = 0u; else sm.fire32[272 + lane - 16] = 0u;   // fire rows -4..-1, 64..67
     if (lane < 8) sm.dous32[lane] = 0u; else if (lane < 16) sm.dous32[264 + lane - 8] = 0u;  // rows -2,-1,64,65
+    S64_STAMP(0);
+    const KeySides ks = key_chain(P, lane, key0, key1);  // ~3K dependent threefry blocks while the grid streams in
+    if (lane == 0) {
+      S.key[2 * e] = key0;
+      S.key[2 * e + 1] = key1;
+    }
+    S64_STAMP(19);
+    mbar_wait(mbar, 0u);
+    const ulonglong2 dz = reinterpret_cast<const ulonglong2*>(sm.ign)[lane];
+    rm = reinterpret_cast<const uint2*>(wp)[lane];
+    {
+      // lane l owns rows 2l, 2l+1 = 128 contiguous bytes of the landing zone; the 16-byte pieces are read
+      // in a rotated order so that the 8 lanes of a quarter-warp hit 8 different bank groups
+      const uint4* cz = reinterpret_cast<const uint4*>(sm.burn) + lane * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int pc = (i + lane) & 7;
+        uint32_t t16, f16;
+        cells16_to_bits(cz[pc], t16, f16);
+        const int sh = 16 * (pc & 3);
+        const unsigned long long tb = (unsigned long long)t16 << sh, fb = (unsigned long long)f16 << sh;
+        if (pc < 4) { t0 |= tb; f0 |= fb; } else { t1 |= tb; f1 |= fb; }
+      }
+    }
+    __syncwarp();  // the landing zones are free from here on
+    sm.ign[2 * lane] = 0ull;
+    sm.ign[2 * lane + 1] = 0ull;
     store_row_views(sm.dous32 + (2 * lane + 2) * 4, dz.x);
     store_row_views(sm.dous32 + (2 * lane + 3) * 4, dz.y);
     {
@@ -508,86 +575,131 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         sm.npairs = 0u;
       }
     }
-    __syncwarp();
-    {
-      const ulonglong2 tt = reinterpret_cast<const ulonglong2*>(sm.ign)[lane];
-      const ulonglong2 ff = reinterpret_cast<const ulonglong2*>(sm.base)[lane];
-      t0 = tt.x; t1 = tt.y; f0 = ff.x; f1 = ff.y;
-    }
-    __syncwarp();
-    sm.ign[2 * lane] = 0ull;
-    sm.ign[2 * lane + 1] = 0ull;
     store_row_views(sm.fire32 + (2 * lane + 4) * 4, f0);
     store_row_views(sm.fire32 + (2 * lane + 5) * 4, f1);
 
-    // ---- rows holding a cell that burns out during this env step ---------------------------------
-    {
-      const bool need0 = f0 != 0ull && rm.x < tick0 + (uint32_t)K;
-      const bool need1 = f1 != 0ull && rm.y < tick0 + (uint32_t)K;
-      burnrows = (need0 ? 1u : 0u) | (need1 ? 2u : 0u);
-      // each flagged row is one 128-byte line of burn-out ticks: request them all now, the serial
-      // row loop below then hits L1/L2 instead of paying one DRAM round trip per row
-      if (need0) prefetch_l1(S.death + cell_base + (2 * lane) * 64);
-      if (need1) prefetch_l1(S.death + cell_base + (2 * lane + 1) * 64);
-      uint32_t m0 = __ballot_sync(GCA_FULL, need0);
-      uint32_t m1 = __ballot_sync(GCA_FULL, need1);
-      while (m0 | m1) {
-        int src;
-        bool second;
-        if (m0) { src = __ffs(m0) - 1; m0 &= m0 - 1; second = false; }
-        else { src = __ffs(m1) - 1; m1 &= m1 - 1; second = true; }
-        const int row = 2 * src + (second ? 1 : 0);
-        const unsigned long long fr = shfl64(second ? f1 : f0, src);
-        uint16_t* dp = S.death + cell_base + row * 64;
-        const uint32_t da = dp[lane], db = dp[lane + 32];
-        const bool fa = (fr >> lane) & 1ull, fb = (fr >> (lane + 32)) & 1ull;
-        const uint32_t ra = (da - tick0) & 0xFFFFu, rb = (db - tick0) & 0xFFFFu;
-        const bool xa = fa && ra < (uint32_t)K, xb = fb && rb < (uint32_t)K;
-        const unsigned long long dmask =
-            (unsigned long long)__ballot_sync(GCA_FULL, xa) | ((unsigned long long)__ballot_sync(GCA_FULL, xb) << 32);
-        unsigned long long pm[3];
-#pragma unroll
-        for (int b = 0; b < 3; ++b)
-          pm[b] = (unsigned long long)__ballot_sync(GCA_FULL, xa && ((ra >> b) & 1u)) |
-                  ((unsigned long long)__ballot_sync(GCA_FULL, xb && ((rb >> b) & 1u)) << 32);
-        uint32_t v = 0xFFFFFFFFu;
-        if (fa && !xa) v = tick0 + ra;
-        if (fb && !xb) v = min(v, tick0 + rb);
-        const uint32_t newmin = __reduce_min_sync(GCA_FULL, v);
-        if (xa) dp[lane] = 0;        // burnt-out cell: fire_age ends at 0
-        if (xb) dp[lane + 32] = 0;
-        if (lane == 0) {
-          reinterpret_cast<ulonglong2*>(sm.burn[row])[0] = make_ulonglong2(dmask, pm[0]);
-          reinterpret_cast<ulonglong2*>(sm.burn[row])[1] = make_ulonglong2(pm[1], pm[2]);
-        }
-        if (lane == src) {
-          if (second) rm.y = newmin; else rm.x = newmin;
-        }
-      }
-    }
-    __syncwarp();
+    // ---- rows holding a cell that burns out during this env step: request their burn-out ticks now ----
+    const bool need0 = f0 != 0ull && rm.x < tick0 + (uint32_t)K;
+    const bool need1 = f1 != 0ull && rm.y < tick0 + (uint32_t)K;
+    burnrows = (need0 ? 1u : 0u) | (need1 ? 2u : 0u);
+    if (need0) prefetch_l1(S.death + cell_base + (2 * lane) * 64);
+    if (need1) prefetch_l1(S.death + cell_base + (2 * lane + 1) * 64);
 
-    // ---- front of sub-step 0: compact it and start fetching its hidden / slope-factor sectors so
-    //      that their DRAM latency hides behind the key schedule.  The list is built ONCE per env
-    //      step; later sub-steps append the cells that joined the front (a handful); entries that
-    //      left it (ignited / no burning neighbour left) are recognised from their fire window.
+    // ---- front of sub-step 0: compact it and start fetching its hidden / slope-factor sectors.  The
+    //      list is built ONCE per env step; later sub-steps append the cells that joined the front (a
+    //      handful); entries that left it (ignited / no burning neighbour left) are recognised from
+    //      their fire window.
+    __syncwarp();
     {
       unsigned long long fr0, fr1;
       front_masks(t0, t1, f0, f1, lane, fr0, fr1);
       T = build_front_list(sm, wp, fr0, fr1, lane, 0);
       dense = T > S64_CAP;  // more front cells than the list holds: rebuild per sub-step, in passes
       L = min(T, S64_CAP);
-      prefetch_front(sm, hidden, pslope, cell_base, 0, L, lane);
       sm.listed[2 * lane] = fr0;
       sm.listed[2 * lane + 1] = fr1;
       n_front += (uint32_t)(__popcll(fr0) + __popcll(fr1));
     }
-    key_schedule(sm, P, J, N, e, lane, key0, key1, widx);
-    if (lane == 0) {
-      S.key[2 * e] = key0;
-      S.key[2 * e + 1] = key1;
-      S.wind_index[e] = widx;
+    S64_STAMP(1);
+
+    // ---- burn-out scan, four flagged rows per round: lane group g = lane / 8 takes one row, each of its
+    //      lanes 8 cells (one 128-bit load); the next round's load is issued before this round is processed
+    {
+      uint32_t* const tmp_rm = reinterpret_cast<uint32_t*>(wp);  // new row minimum of scanned rows
+      const int g = lane >> 3, li = lane & 7;
+      // bit s: row 2s, bit 32 + s: row 2s + 1
+      unsigned long long M = (unsigned long long)__ballot_sync(GCA_FULL, need0) |
+                             ((unsigned long long)__ballot_sync(GCA_FULL, need1) << 32);
+      // take the four lowest flagged rows off M: group g gets the (g+1)-th and requests its 16 bytes
+      auto fetch = [&](bool& have, int& idx, uint4& dv) {
+        unsigned long long mm = M;
+        int pos = -1;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q == g && mm) pos = __ffsll((long long)mm) - 1;
+          mm &= mm - 1;
+        }
+        M = mm;
+        have = pos >= 0;
+        idx = have ? pos : 0;
+        const int row = 2 * (idx & 31) + (idx >> 5);
+        dv = make_uint4(0u, 0u, 0u, 0u);
+        if (have) dv = *reinterpret_cast<const uint4*>(S.death + cell_base + row * 64 + 8 * li);
+      };
+      bool cur_any = M != 0ull, have;
+      int idx;
+      uint4 dv;
+      fetch(have, idx, dv);
+#pragma unroll 1
+      while (cur_any) {
+        const bool nxt_any = M != 0ull;
+        bool have_n = false;
+        int idx_n = 0;
+        uint4 dv_n = make_uint4(0u, 0u, 0u, 0u);
+        if (nxt_any) fetch(have_n, idx_n, dv_n);
+        const int row = 2 * (idx & 31) + (idx >> 5);
+        // (both rows of the source lane are fetched: the groups of one round may want different parities)
+        const unsigned long long fe = shfl64(f0, idx & 31), fo = shfl64(f1, idx & 31);
+        const unsigned long long frow = (idx >> 5) ? fo : fe;
+        const uint32_t fb = (uint32_t)(frow >> (8 * li)) & 0xFFu;  // fire bits of this lane's 8 cells
+        uint32_t w[4] = {dv.x, dv.y, dv.z, dv.w};
+        uint32_t die8 = 0, p0 = 0, p1 = 0, p2 = 0, vmin = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t d = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+          const uint32_t r = (d - tick0) & 0xFFFFu;
+          const bool f = have && ((fb >> k) & 1u);
+          const bool x = f && r < (uint32_t)K;
+          if (x) {
+            die8 |= 1u << k;
+            p0 |= (r & 1u) << k;
+            p1 |= ((r >> 1) & 1u) << k;
+            p2 |= ((r >> 2) & 1u) << k;
+            w[k >> 1] &= ~(0xFFFFu << (16 * (k & 1)));  // burnt-out cell: fire_age ends at 0
+          } else if (f) {
+            vmin = min(vmin, tick0 + r);
+          }
+        }
+        if (die8)
+          *reinterpret_cast<uint4*>(S.death + cell_base + row * 64 + 8 * li) = make_uint4(w[0], w[1], w[2], w[3]);
+        // the group's first lane collects the 8 packed byte-quadruples (die, plane 0..2) and transposes
+        // them into four 64-bit row masks (redux.sync with per-group masks would be serialised)
+        const uint32_t packed = die8 | (p0 << 8) | (p1 << 16) | (p2 << 24);
+        uint32_t wq[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wq[k] = __shfl_sync(GCA_FULL, packed, (lane & 24) + k);
+        unsigned long long rowm[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          // inner perm: byte 0 = x.byte[q], byte 1 = y.byte[q]; outer perm: bytes a0 a1 b0 b1
+          const uint32_t lo = __byte_perm(__byte_perm(wq[0], wq[1], 0x0040u + q + (q << 4)),
+                                          __byte_perm(wq[2], wq[3], 0x0040u + q + (q << 4)), 0x5410u);
+          const uint32_t hi = __byte_perm(__byte_perm(wq[4], wq[5], 0x0040u + q + (q << 4)),
+                                          __byte_perm(wq[6], wq[7], 0x0040u + q + (q << 4)), 0x5410u);
+          rowm[q] = ((unsigned long long)hi << 32) | lo;
+        }
+        uint32_t newmin = vmin;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) newmin = min(newmin, __shfl_xor_sync(GCA_FULL, newmin, d));
+        if (have && li == 0) {
+          reinterpret_cast<ulonglong2*>(sm.burn[row])[0] = make_ulonglong2(rowm[0], rowm[1]);
+          reinterpret_cast<ulonglong2*>(sm.burn[row])[1] = make_ulonglong2(rowm[2], rowm[3]);
+          tmp_rm[row] = newmin;
+        }
+        have = have_n; idx = idx_n; dv = dv_n; cur_any = nxt_any;
+      }
+      __syncwarp();
+      S64_STAMP(2);
+      if (need0) rm.x = tmp_rm[2 * lane];
+      if (need1) rm.y = tmp_rm[2 * lane + 1];
+      __syncwarp();
     }
+    S64_STAMP(3);
+    // the front cells' hidden / slope-factor sectors: their DRAM latency hides behind the second half of the key schedule
+    prefetch_front(sm, hidden, pslope, cell_base, 0, L, lane);
+    S64_STAMP(18);
+    key_sides(sm, P, J, N, e, lane, ks, widx);
+    if (lane == 0) S.wind_index[e] = widx;
   }
 
   const float lutreg = lane < 8 ? P.onep_veg[lane] : (lane < 16 ? P.onep_den[lane - 8] : 0.0f);
@@ -655,6 +767,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
           prefetch_front(sm, hidden, pslope, cell_base, 0, min(S64_CAP, total - pass * S64_CAP), lane);
         }
       }
+      S64_STAMP(4 + 3 * j);
       if (lane == 0) {
         const int cnt = max(0, min(S64_CAP, total - pass * S64_CAP));
         sm.cnt = cnt;
@@ -761,7 +874,9 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
           __syncwarp();
         }
       }
+      S64_STAMP(5 + 3 * j);
       const int more = __syncthreads_or(total > (pass + 1) * S64_CAP);
+      S64_STAMP(6 + 3 * j);
       if (!more) break;
     }
 

@@ -129,6 +129,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         # 64x64 kernel: re-deal envs to warps every `balance_every` steps by last step's cost (0 = off)
         self.balance_every = int(balance_every)
         self._steps_since_balance = 0
+        self.kernel_launches = 0  # kernels of libgca launched by the step path (step + re-balancing)
         self.num_envs = int(num_envs)
         # multi-GPU sharding: this instance holds envs [env_offset, env_offset + num_envs) of a batch of
         # total_envs; per-env keys come from ONE split over the whole batch, so they do not depend on
@@ -441,6 +442,8 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
             if self._steps_since_balance >= self.balance_every:
                 self._state.rebalance()
                 self._steps_since_balance = 0
+                self.kernel_launches += 1
+        self.kernel_launches += 1 if self._state.work is not None else 2 * self.substeps + 1
         if inject is None:
             # hot path: every struct pointer is cached; only the action pointer and the stream vary
             fa = self._fast_args

@@ -20,6 +20,7 @@
  *                          + apply_blur/apply_extensions               forest_fire/bulldozer/utils/extension_utils.py:99-195
  *   gca_pack_state / gca_unpack_state   the float32/int32 context pytree of _initial_context_distribution
  *                                                                       forest_fire/bulldozer/advanced_bulldozer.py:690-743
+ *   gca_episode_stats_update  step_env_wrapped's statistics         agents/jax_ppo.py:504-655
  *   gca_threefry_bits / gca_threefry_split   jax.random.bits / split (third-party jax, unpinned; see oracle/prng.py)
  */
 #ifndef GCA_H_
@@ -191,6 +192,42 @@ int gca_unpack_state(const gca_params* p, const gca_state* s, float* true_grid, 
  * light envs: sort by work[] (descending) and distribute round-robin over waves of 148 CTAs in
  * alternating direction.  order and work are [N] device arrays; call it every few steps. */
 int gca_balance_order(int32_t N, const uint32_t* work, int32_t* order, void* stream);
+
+/* ---- rollout-side episode statistics (the caller of the hot path) ----------------------------------------
+ * One call = the statistics part of step_env_wrapped (agents/jax_ppo.py:504-655) for all N envs, to be
+ * issued after gca_env_step and before any conditional reset is observed by the caller:
+ *   episode_returns += step_reward; episode_lengths += 1; day/night extension-correctness counters
+ *   (jax_ppo.py:524-541; they are never cleared, like the reference); finished = terminated + truncated;
+ *   returned_episode_* latch the totals of finished envs; episode_* are zeroed for them;
+ *   amount_finished += sum(terminated); the 10-entry ring buffers receive the finished envs in env
+ *   order starting at recent_idx (jax_ppo.py:543-621, a serial lax.scan there; here a block scan), and
+ *   recent_idx = (recent_idx + #finished) % 10.
+ * All pointers are device memory; per-env arrays have N entries, ring arrays 10, scalars 1. */
+#define GCA_RECENT 10
+typedef struct gca_episode_stats {
+  float* episode_returns;            /* [N] */
+  int32_t* episode_lengths;          /* [N] */
+  float* returned_episode_returns;   /* [N] */
+  int32_t* returned_episode_lengths; /* [N] */
+  int32_t* amount_finished;          /* [1] */
+  float* recent_returns;             /* [10] */
+  int32_t* recent_lengths;           /* [10] */
+  int32_t* recent_idx;               /* [1] */
+  int32_t* current_day_correct;      /* [N] */
+  int32_t* current_night_correct;    /* [N] */
+  int32_t* current_day_steps;        /* [N] */
+  int32_t* current_night_steps;      /* [N] */
+  int32_t* recent_day_correct;       /* [10] */
+  int32_t* recent_night_correct;     /* [10] */
+  int32_t* recent_day_steps;         /* [10] */
+  int32_t* recent_night_steps;       /* [10] */
+} gca_episode_stats;
+/* step_reward: info["reward"] of the transition (gca_step_out.step_reward); terminated: gca_step_out.terminated;
+ * truncated: [N] or NULL (all zero); obs_night: is_night of the observation the action was chosen on
+ * (gca_step_out.obs_night); actions: [N][3], the extension id is actions[.][2]. */
+int gca_episode_stats_update(int32_t N, const gca_episode_stats* st, const float* step_reward,
+                             const uint8_t* terminated, const uint8_t* truncated, const uint8_t* obs_night,
+                             const int32_t* actions, void* stream);
 
 /* ---- v3 rule set: WindyForestFire + Move / Modify(cut) / RepeatCA of ForestFireBulldozer256x256-v3 ----
  * (reference forest_fire/operators/ca_windy.py:41-139, operators/repeat_ca.py:32-45,

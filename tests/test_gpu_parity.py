@@ -423,3 +423,54 @@ def test_v3_env_step_parity(cuda_device):
         assert np.array_equal(obs[0].cpu().numpy(), grid), step
         assert np.array_equal(obs[1][1].cpu().numpy(), pos) and np.array_equal(obs[1][2].cpu().numpy(), time)
     assert {0, 1} <= seen and max(seen) >= 2
+
+
+# ---------------------------------------------------------------------------------------------
+# rollout-side episode statistics (agents/jax_ppo.py:504-655)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [5, 300, 4099])
+def test_episode_statistics_parity(cuda_device, N):
+    """gca_episode_stats_update against the literal serial-scan restatement, over many steps with bursts
+    of more than 10 simultaneous finishes (ring wrap) and truncations."""
+    from gym_cellular_automata_b200.rollout_stats import EpisodeStatistics
+    from oracle import rollout
+    rng = np.random.default_rng(N)
+    dev_st = EpisodeStatistics(N, cuda_device)
+    st = rollout.new_stats(N)
+    for step in range(40):
+        p_fin = [0.0, 0.02, 0.5, 1.0][step % 4]
+        actions = rng.integers(0, 3, (N, 3)).astype(np.int32)
+        reward = (-rng.random(N)).astype(np.float32)
+        term = (rng.random(N) < p_fin).astype(np.uint8)
+        trunc = ((rng.random(N) < 0.01) & (term == 0)).astype(np.uint8)
+        night = rng.integers(0, 2, N).astype(np.uint8)
+        st = rollout.update(st, actions, reward, term, trunc, night)
+        dev_st.update(torch.as_tensor(actions, device=cuda_device), torch.as_tensor(reward, device=cuda_device),
+                      torch.as_tensor(term, device=cuda_device), torch.as_tensor(night, device=cuda_device),
+                      torch.as_tensor(trunc, device=cuda_device))
+        for k, v in dev_st.as_dict().items():
+            got = v.cpu().numpy()
+            want = np.asarray(st[k]).reshape(got.shape)
+            assert np.array_equal(got, want), f"step {step}: {k} differs"
+
+
+def test_episode_statistics_with_env(cuda_device):
+    """Driven by the env's own outputs (step_reward / terminated / obs_night), as the rollout loop would."""
+    from gym_cellular_automata_b200.rollout_stats import EpisodeStatistics
+    from oracle import rollout
+    from parity_util import make_pair
+    env, co, E, state, info = make_pair(N=16, K=4, mode="legacy", use_hidden=True, seed=2)
+    env.auto_reset = True
+    dev_st = EpisodeStatistics(16, cuda_device)
+    st = rollout.new_stats(16)
+    rng = np.random.default_rng(3)
+    for step in range(30):
+        a = np.stack([rng.integers(0, 9, 16), rng.integers(0, 2, 16), rng.integers(0, 3, 16)], 1).astype(np.int32)
+        ad = torch.as_tensor(a, device=cuda_device)
+        night_before = env._state.is_night.cpu().numpy().copy()
+        out = env.step_device(ad)
+        dev_st.update(ad, out.step_reward, out.terminated, out.obs_night)
+        st = rollout.update(st, a, out.step_reward.cpu().numpy(), out.terminated.cpu().numpy(), np.zeros(16, np.uint8),
+                            night_before)
+    for k, v in dev_st.as_dict().items():
+        assert np.array_equal(v.cpu().numpy(), np.asarray(st[k]).reshape(v.shape)), k

@@ -315,3 +315,35 @@ def test_v3_env_step_oracle_clock_and_cut():
     # not moving and not shooting costs only t_any (bulldozer.py:285-286)
     ng, pos, t, rew, done, rep = windy.v3_env_step(C, g, np.array([0, 0]), 0.0, (4, 0), windy.DEFAULT_WIND, rolls)
     assert rep == 0 and t == 0.001 and np.array_equal(ng, g)
+
+
+# ---- rollout statistics (agents/jax_ppo.py:504-655) ---------------------------------------------------
+def test_rollout_stats_ring_buffer_semantics():
+    """Hand-worked case of update_recent_stats: finished envs enter the ring in env order from recent_idx,
+    wrap modulo 10 (later ones overwrite), counters are latched and the running totals are cleared."""
+    from oracle import rollout
+    N = 14
+    st = rollout.new_stats(N)
+    st["recent_idx"] = np.int32(7)
+    st["episode_returns"][:] = np.arange(N, dtype=np.float32)
+    st["episode_lengths"][:] = 5
+    actions = np.zeros((N, 3), np.int32)
+    actions[:, 2] = 2
+    term = np.ones(N, np.uint8)
+    term[3] = 0
+    trunc = np.zeros(N, np.uint8)
+    trunc[3] = 1  # truncated counts as finished, not as terminated
+    out = rollout.update(st, actions, np.full(N, -0.5, np.float32), term, trunc, np.zeros(N, np.int32))
+    assert int(out["recent_idx"]) == (7 + N) % 10 and int(out["amount_finished"]) == N - 1
+    # env e has rank e; slot (7 + e) % 10 keeps the LAST writer: ranks 4..13 survive
+    for e in range(4, N):
+        assert out["recent_returns"][(7 + e) % 10] == np.float32(e - 0.5)
+        assert out["recent_lengths"][(7 + e) % 10] == 6
+        assert out["recent_day_correct"][(7 + e) % 10] == 1 and out["recent_day_steps"][(7 + e) % 10] == 1
+    assert not out["episode_returns"].any() and not out["episode_lengths"].any()
+    assert np.array_equal(out["returned_episode_returns"], np.arange(N, dtype=np.float32) - np.float32(0.5))
+    # nothing finished: accumulators run on, the ring stays
+    out2 = rollout.update(out, actions, np.ones(N, np.float32), np.zeros(N, np.uint8), trunc * 0, np.ones(N, np.int32))
+    assert np.array_equal(out2["recent_returns"], out["recent_returns"]) and int(out2["recent_idx"]) == int(out["recent_idx"])
+    assert np.all(out2["episode_returns"] == 1) and np.all(out2["episode_lengths"] == 1)
+    assert np.all(out2["current_night_steps"] == 1) and np.all(out2["current_night_correct"] == 0)

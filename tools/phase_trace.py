@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Diagnostics (needs a -DS64_TRACE build selected with GCA_LIB_PATH): mean per-env phase timestamps of the
+64x64 step kernel, L2-cold (flushed) vs L2-warm.  Not part of the product path."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from gym_cellular_automata_b200 import _lib
+from gym_cellular_automata_b200.packed import StepOutputs
+from gym_cellular_automata_b200._lib import GcaStepOut, ptr
+from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv
+
+N = 4096; K = 4
+dev = torch.device("cuda", 0)
+env = AdvancedForestFireBulldozerEnv(64, 64, key=1, num_envs=N, speed_move=0.48, speed_act=0.12, use_hidden=True,
+                                     substeps=K, rng_mode="legacy", seed=0, hidden="random", obs_mode="none",
+                                     auto_reset=True, collect_stats=True, device=dev, balance_every=8)
+env.reset()
+o = env._out
+o.stats = torch.zeros(8 + 24 * N, dtype=torch.int64, device=dev)
+o._c = GcaStepOut(ptr(o.reward).value, ptr(o.step_reward).value, ptr(o.terminated).value, ptr(o.counts).value,
+                  ptr(o.obs_night).value, ptr(o.stats).value)
+env._version_structs += 1
+gen = torch.Generator(device=dev); gen.manual_seed(0)
+def act():
+    return torch.stack([torch.randint(0, 9, (N,), device=dev, generator=gen), torch.randint(0, 2, (N,), device=dev, generator=gen),
+                        torch.randint(0, 3, (N,), device=dev, generator=gen)], -1).to(torch.int32).contiguous()
+for _ in range(100): env.step_device(act())
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+names = ["setup", "chain+wait+convert+list", "scan", "(rm)"] + sum([[f"s{j} owner-pre", f"s{j} pooled", f"s{j} barrier"] for j in range(K)], [])
+for mode in ("cold", "warm", "cold", "warm"):
+    a = act()
+    if mode == "cold": flush.fill_(1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); env.step_device(a); e1.record(); torch.cuda.synchronize()
+    tr = o.stats[8:].cpu().numpy().reshape(N, 24).astype(np.float64)
+    extra = tr[:, 16:20].mean(0)
+    tr = tr[:, :4 + 3 * K]
+    mean = tr.mean(0); mx = tr.max(0)
+    print("  abs stamps: e known %.1fk, copies issued %.1fk, prefetch_front done %.1fk, key chain done %.1fk" % tuple(extra / 1e3))
+    d = np.diff(np.concatenate([[0], mean]))  # note: the key schedule sits between stamp 3 and "s0 owner-pre"
+    print(mode, f"kernel {e0.elapsed_time(e1)*1e3:.1f} us = {e0.elapsed_time(e1)*1e3*1.965:.0f} kcycles*1e-3")
+    print("  " + "  ".join(f"{n}:{x/1e3:.1f}k" for n, x in zip(names, d)))
+    print("  last stamp mean %.1fk max %.1fk" % (mean[-1] / 1e3, mx[-1] / 1e3))
