@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-envs", type=int, default=256, help="envs of the CPU sample (cpu_baseline leg and --impl reference)")
-    ap.add_argument("--cpu-steps", type=int, default=160, help="env steps of the cpu_baseline sample (about 10-20 s of host work)")
+    ap.add_argument("--cpu-steps", type=int, default=1024, help="env steps of the cpu_baseline sample (about 10-20 s of host work)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--ruleset", default="alexandridis", choices=["alexandridis", "v3"],
                     help="v3 = the registered ForestFireBulldozer256x256-v3 rule set (WindyForestFire), an extra line")
@@ -229,19 +229,14 @@ def run_ours(args):
 
     # ---- end to end through the host API: pinned host actions in, reward/terminated out, per step
     h_act = acts[args.warmup:args.warmup + args.steps].cpu().pin_memory()
-    h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
-    h_term = torch.empty(N, dtype=torch.uint8).pin_memory()
-    d_act = torch.empty((N, 3), dtype=torch.int32, device=dev)
+    h_rew, h_term = env.host_result_buffers()  # pinned
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        d_act.copy_(h_act[i], non_blocking=True)
-        out = env.step_device(d_act)
-        h_rew.copy_(out.reward, non_blocking=True)
-        h_term.copy_(out.terminated, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads reward/done every step
+        # one C call: H2D of this step's actions, the fused step, D2H of reward + terminated, stream sync
+        env.step_host(h_act[i], h_rew, h_term)
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None  # sampled over the timed loops above (device-timed, L2-warm, end-to-end)
 
@@ -294,7 +289,7 @@ def run_ours(args):
         "e2e": {"value": total_envs * args.steps / e2e_s * size * size * K, "unit": "cell-updates/s",
                 "env_steps_per_s": total_envs * args.steps / e2e_s,
                 "h2d_bytes_per_step": int(N * 3 * 4), "d2h_bytes_per_step": int(N * 5),
-                "what": "pinned host actions -> H2D -> gca_env_step -> D2H reward+terminated, stream sync every step"},
+                "what": "gca_env_step_host per step: pinned host actions -> H2D -> fused step -> D2H reward + terminated -> stream sync"},
         "gpu_launches": launches, "clocks": clocks,
         "workload_stats": {"front_cells_per_env_substep": d[0] / sub, "draws_per_env_substep": d[1] / sub,
                            "ignitions_per_env_substep": d[2] / sub, "burnouts_per_env_substep": d[3] / sub,

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 # GCA_LIB_PATH selects another build of the same sources (A/B measurements of kernel variants)
 LIB_PATH = os.environ.get("GCA_LIB_PATH") or os.path.join(_HERE, "libgca.so")
-SOURCES = ("gca_step64.cu", "gca_step64_warp.cu", "gca_tiled.cu", "gca_windy.cu", "gca_aux.cu", "gca_abi.cu")
+SOURCES = ("gca_step64.cu", "gca_tiled.cu", "gca_windy.cu", "gca_aux.cu", "gca_abi.cu")
 HEADERS = ("gca_common.cuh", os.path.join("..", "..", "include", "gca.h"))
 
 GCA_MAX_R = 10
@@ -123,6 +123,9 @@ def load():
                                     C.c_void_p]
     lib.gca_env_step.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState), C.c_void_p, C.POINTER(GcaStepOut),
                                  C.POINTER(GcaInject), C.POINTER(GcaState), C.c_void_p, C.c_uint32, C.c_void_p]
+    lib.gca_env_step_host.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState), C.c_void_p, C.c_void_p,
+                                      C.POINTER(GcaStepOut), C.POINTER(GcaState), C.c_void_p, C.c_uint32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gca_alexandridis_step.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState), C.POINTER(GcaStepOut),
                                           C.POINTER(GcaInject), C.c_uint32, C.c_void_p]
     lib.gca_move_modify.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState), C.c_void_p, C.c_void_p]
@@ -147,7 +150,7 @@ def load():
 
 
 # every symbol include/gca.h declares (tests check the library exports all of them)
-EXPORTS = ("gca_version", "gca_last_error", "gca_params_init", "gca_env_step", "gca_alexandridis_step",
+EXPORTS = ("gca_version", "gca_last_error", "gca_params_init", "gca_env_step", "gca_env_step_host", "gca_alexandridis_step",
            "gca_move_modify", "gca_reward_done", "gca_conditional_reset", "gca_render_rgb", "gca_pack_state",
            "gca_unpack_state", "gca_balance_order", "gca_episode_stats_update", "gca_windy_env_step", "gca_windy_pack", "gca_windy_unpack",
            "gca_threefry_bits", "gca_threefry_split")

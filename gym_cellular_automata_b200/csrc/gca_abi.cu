@@ -163,11 +163,6 @@ int gca_env_step(const gca_params* p, const gca_state* s, const int32_t* actions
   if (flags & GCA_FLAG_NO_HIDDEN) { st.hidden = nullptr; st.pslope = nullptr; }
   if (is64(p)) {
     if (!s->row_min) return fail(GCA_ERR_ARG, "gca_env_step: 64x64 path needs row_min");
-    // GCA_STEP64_IMPL=warp selects the earlier one-warp-per-env kernel (A/B measurements only)
-    static const bool warp_impl = [] { const char* v = getenv("GCA_STEP64_IMPL"); return v && !strcmp(v, "warp"); }();
-    if (warp_impl)
-      return check_cuda(gca::launch_env_step64_warp(*p, st, actions, o, j, sn, snapshot_reward, flags, (cudaStream_t)stream),
-                        "env_step64_warp");
     return check_cuda(gca::launch_env_step64(*p, st, actions, o, j, sn, snapshot_reward, flags, (cudaStream_t)stream),
                       "env_step64");
   }
@@ -186,6 +181,36 @@ int gca_env_step(const gca_params* p, const gca_state* s, const int32_t* actions
                       "auto_reset");
   }
   return GCA_OK;
+}
+
+int gca_env_step_host(const gca_params* p, const gca_state* s, const int32_t* host_actions, int32_t* dev_actions,
+                      const gca_step_out* out, const gca_state* snapshot, const float* snapshot_reward, uint32_t flags,
+                      float* host_reward, uint8_t* host_terminated, void* stream) {
+  if (!p || !s || !host_actions || !dev_actions || !out || !out->reward || !out->terminated || !host_reward ||
+      !host_terminated)
+    return fail(GCA_ERR_ARG, "gca_env_step_host: null argument (out->reward and out->terminated are required)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t N = (size_t)s->N;
+  int rc = check_cuda(cudaMemcpyAsync(dev_actions, host_actions, N * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st),
+                      "env_step_host: actions H2D");
+  if (rc) return rc;
+  rc = gca_env_step(p, s, dev_actions, out, nullptr, snapshot, snapshot_reward, flags, stream);
+  if (rc) return rc;
+  const bool adjacent = out->terminated == reinterpret_cast<const uint8_t*>(out->reward + N) &&
+                        host_terminated == reinterpret_cast<const uint8_t*>(host_reward + N);
+  if (adjacent) {  // [N] f32 + [N] u8 laid out back to back on both sides: one copy
+    rc = check_cuda(cudaMemcpyAsync(host_reward, out->reward, N * 5, cudaMemcpyDeviceToHost, st),
+                    "env_step_host: reward + terminated D2H");
+    if (rc) return rc;
+  } else {
+    rc = check_cuda(cudaMemcpyAsync(host_reward, out->reward, N * sizeof(float), cudaMemcpyDeviceToHost, st),
+                    "env_step_host: reward D2H");
+    if (rc) return rc;
+    rc = check_cuda(cudaMemcpyAsync(host_terminated, out->terminated, N, cudaMemcpyDeviceToHost, st),
+                    "env_step_host: terminated D2H");
+    if (rc) return rc;
+  }
+  return check_cuda(cudaStreamSynchronize(st), "env_step_host: synchronize");
 }
 
 int gca_alexandridis_step(const gca_params* p, const gca_state* s, const gca_step_out* out, const gca_inject* inj,

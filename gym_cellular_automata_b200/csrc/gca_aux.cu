@@ -261,35 +261,62 @@ __global__ void render_rgb_kernel(gca_params P, int N, const uint8_t* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// Load balancing of the 64x64 step kernel.  One CTA sorts a chunk of up to 8192 (work, env) keys
-// (bitonic, shared memory) in descending order and deals the sorted envs to the warp slots of the
-// step kernel's CTAs (see the dealing rule below; wpc = envs per CTA of the step kernel).
+// Load balancing of the 64x64 step kernel.  One CTA orders a chunk of up to 8192 envs by decreasing
+// work with a 1024-bucket counting sort in shared memory (the order inside a bucket is irrelevant:
+// only the step kernel's speed depends on it, never its results) and deals the sorted envs to the
+// warp slots of the step kernel's CTAs (see the dealing rule below; wpc = envs per CTA there).
 // ---------------------------------------------------------------------------------------------
 constexpr int BAL_CHUNK = 8192;
 constexpr int BAL_WAVE = 148;
+constexpr int BAL_BUCKETS = 1024;
 __global__ void __launch_bounds__(1024) balance_order_kernel(int N, int wpc, const uint32_t* __restrict__ work, int32_t* order) {
-  extern __shared__ unsigned long long keys[];
+  extern __shared__ int keys[];            // [BAL_CHUNK] env (chunk-local) by rank
+  __shared__ int hist[BAL_BUCKETS];        // bucket counts, then start offsets (descending buckets)
+  __shared__ uint32_t s_max;
   const int base = blockIdx.x * BAL_CHUNK;
   const int n = min(BAL_CHUNK, N - base);
-  int np2 = 1;
-  while (np2 < n) np2 <<= 1;
-  for (int i = threadIdx.x; i < np2; i += blockDim.x)
-    keys[i] = i < n ? (((unsigned long long)work[base + i] << 32) | (uint32_t)i) : 0ull;  // padding sorts last
+  const int tid = threadIdx.x;
+  hist[tid] = 0;
+  if (tid == 0) s_max = 0u;
   __syncthreads();
-  for (int k = 2; k <= np2; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < np2; i += blockDim.x) {
-        const int p = i ^ j;
-        if (p > i) {
-          const bool desc = (i & k) == 0;
-          const unsigned long long a = keys[i], b = keys[p];
-          if (desc ? a < b : a > b) { keys[i] = b; keys[p] = a; }
-        }
-      }
-      __syncthreads();
+  uint32_t mx = 0;
+  for (int i = tid; i < n; i += blockDim.x) mx = max(mx, work[base + i]);
+  mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+  if ((tid & 31) == 0) atomicMax(&s_max, mx);
+  __syncthreads();
+  const int shift = max(0, 32 - __clz(s_max | 1u) - 10);  // work >> shift < 1024
+  for (int i = tid; i < n; i += blockDim.x) atomicAdd(&hist[BAL_BUCKETS - 1 - (int)(work[base + i] >> shift)], 1);
+  __syncthreads();
+  // exclusive scan of the 1024 counts (bucket 0 = heaviest)
+  {
+    const int c = hist[tid];
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if ((tid & 31) >= d) incl += o;
     }
-  // keys[0..n) hold the chunk's envs by decreasing work (pad keys are 0 and sort behind real keys
-  // only if work > 0 or idx > 0; real entries are re-identified by counting)
+    __shared__ int wsum[32];
+    if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+      int v = wsum[tid];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (tid >= d) v += o;
+      }
+      wsum[tid] = v;
+    }
+    __syncthreads();
+    hist[tid] = incl - c + ((tid >> 5) ? wsum[(tid >> 5) - 1] : 0);
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int rank = atomicAdd(&hist[BAL_BUCKETS - 1 - (int)(work[base + i] >> shift)], 1);
+    keys[rank] = i;
+  }
+  __syncthreads();
   // Pooled kernel (E warps = E envs per CTA, the heavy phases shared by the CTA): a CTA costs about the
   // SUM of its envs' work, so deal the sorted envs like cards -- warp w of CTA b gets rank w*C + b,
   // every other round in reverse (snake) -- which gives all C full CTAs nearly the same sum.
@@ -307,7 +334,7 @@ __global__ void __launch_bounds__(1024) balance_order_kernel(int N, int wpc, con
         rank = wave * BAL_WAVE + q;
       }
     }
-    order[base + s] = base + (int)(keys[rank] & 0xFFFFFFFFull);
+    order[base + s] = base + keys[rank];
   }
 }
 
@@ -489,12 +516,11 @@ cudaError_t launch_episode_stats(int N, const gca_episode_stats& e, const float*
 cudaError_t launch_balance_order(int N, const uint32_t* work, int32_t* order, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(balance_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BAL_CHUNK * 8);
+    cudaFuncSetAttribute(balance_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BAL_CHUNK * 4);
     attr_set = true;
   }
   const int chunks = (N + BAL_CHUNK - 1) / BAL_CHUNK;
-  static const bool warp_impl = [] { const char* v = getenv("GCA_STEP64_IMPL"); return v && !strcmp(v, "warp"); }();
-  balance_order_kernel<<<chunks, 1024, BAL_CHUNK * 8, st>>>(N, warp_impl ? 1 : GCA_S64_WARPS, work, order);
+  balance_order_kernel<<<chunks, 1024, BAL_CHUNK * 4, st>>>(N, GCA_S64_WARPS, work, order);
   return cudaGetLastError();
 }
 cudaError_t launch_threefry_split_part(const uint32_t* key, int num, uint32_t* out, cudaStream_t st) {

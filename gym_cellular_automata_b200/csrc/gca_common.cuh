@@ -7,7 +7,7 @@
 
 #define GCA_FULL 0xFFFFFFFFu
 #ifndef GCA_S64_WARPS
-#define GCA_S64_WARPS 7  /* warps (= envs) per CTA of env_step64_kernel: 4 CTAs x 7 warps x 72 registers fill an SM */
+#define GCA_S64_WARPS 14  /* warps (= envs) per CTA of env_step64_kernel: 2 CTAs x 14 warps x 72 registers fill an SM */
 #endif
 
 namespace gca {
@@ -162,9 +162,6 @@ namespace gca {
 cudaError_t launch_env_step64(const gca_params& p, const gca_state& s, const int32_t* actions,
                               const gca_step_out& out, const gca_inject& inj, const gca_state& snap,
                               const float* snap_reward, uint32_t flags, cudaStream_t st);
-cudaError_t launch_env_step64_warp(const gca_params& p, const gca_state& s, const int32_t* actions,
-                                   const gca_step_out& out, const gca_inject& inj, const gca_state& snap,
-                                   const float* snap_reward, uint32_t flags, cudaStream_t st);
 cudaError_t launch_ca_tiled(const gca_params& p, const gca_state& s, const gca_step_out& out,
                             const gca_inject& inj, uint32_t flags, int substep, uint8_t* cell_out,
                             uint32_t* sched, cudaStream_t st);

@@ -23,8 +23,8 @@
 //    counter-based threefry2x32 block per pair reproduces exactly the uniform jax.random would have
 //    drawn for that element.  u >= hi does not ignite, u < hi (1 - 2^-14) ignites, and the (rare)
 //    in-between case is re-evaluated with the reference's exact row-major float32 summation
-//    ("threshold cells").  Before round-1's re-design one warp did all of this for its env alone
-//    and the kernel lasted as long as its heaviest env (gca_step64_warp.cu, kept for A/B runs).
+//    ("threshold cells").  (The first design gave every env to one warp alone; the kernel then lasted
+//    as long as its heaviest env)
 //  * fire ages are stored as burn-out ticks, so burning cells need no per-step decrement; a
 //    per-row minimum tells which rows hold a cell that burns out in this step.
 //  * the key chain of jax.random.split is evaluated by lane pairs; clock, move, douse, day/night,
@@ -38,6 +38,7 @@ namespace {
 
 constexpr int S64_E = GCA_S64_WARPS;   // envs (= warps) per CTA
 constexpr int S64_CAP = 256;           // front cells per pass
+constexpr int S64_CHAIN_WARPS = (S64_E + 15) / 16;  // warps that walk the key chains (16 envs each)
 constexpr int S64_WP = 320;            // warp-private pair buffer: < 64 carried over + <= 256 of one chunk
 constexpr uint32_t S64_HALF_BURN = 9u * 4096u / 2u;
 constexpr uint32_t S64_HALF_CELL = 4096u / 2u;
@@ -71,12 +72,13 @@ struct __align__(16) EnvSmem {
 };
 static_assert(offsetof(EnvSmem, list) + sizeof(uint16_t) * S64_CAP - offsetof(EnvSmem, burn) == 4096,
               "burn/listed/base/list must be 4096 contiguous bytes (landing zone of the u8 grid)");
+static_assert(S64_E >= 1 && S64_E <= 32 && 28 % S64_E == 0, "envs per CTA: a divisor of 28 (28 warps of 72 registers fill an SM)");
 static_assert(offsetof(EnvSmem, burn) % 16 == 0 && offsetof(EnvSmem, ign) % 16 == 0, "bulk copies need 16-byte alignment");
 
 struct __align__(16) CtaSmem {
   EnvSmem env[S64_E];
-  uint16_t pairs[S64_E][S64_WP];    // (env slot << 12) | (list index << 4) | direction
-  int nch[16];                      // chunks of each env in the current pass
+  uint16_t pairs[S64_E][S64_WP];    // (env slot << 11) | (list index << 3) | direction slot (0..7, centre skipped)
+  int nch[32];                      // chunks of each env in the current pass
   int next;                         // work-item counter of the pooled phase
   int pad[3];
 };
@@ -176,45 +178,46 @@ __device__ __forceinline__ void assemble_split(int mode, uint32_t w, uint32_t o0
 }
 
 // Key schedule of K successive PartiallyObservableForestFireJax.update calls
-// (ca_alexandridis_jax.py:436-448 and :352-368), in two parts so that each can overlap one of the
-// prologue's memory bursts.  key_chain: K0 -> K1 -> K2 -> K3 is sequential (3K split levels, every
-// lane pair runs it redundantly -- free in SIMT); pair 2j keeps sub-step j's S1 and pair 2j+1 its
-// Swind / Sidx.  key_sides: pair 2j derives Sburn / Sgrow / the randint keys of sub-step j and pair
-// 2j+1 its wind draws (4 more levels), then the wind index is threaded through the sub-steps.
-struct KeySides {
-  uint32_t c0, c1, sw0, sw1;
-};
-__device__ __noinline__ KeySides key_chain(const gca_params& P, int lane, uint32_t& key0, uint32_t& key1) {
+// (ca_alexandridis_jax.py:436-448 and :352-368), in two parts.  key_chain_pooled: K0 -> K1 -> K2 -> K3 is
+// sequential (3K split levels of 2 threefry blocks), so ONE warp of the CTA walks the chains of all its envs,
+// a lane pair per env, while the other warps unpack their grids.  key_sides (every owner warp, after the
+// front data was requested): pair 2j derives Sburn / Sgrow / the randint keys of sub-step j and pair 2j+1
+// its wind draws (4 more levels), then the wind index is threaded through the sub-steps.
+// One warp walks the chains of up to 16 envs at once: lane pair p holds env p's key, its even lane leaves the
+// side keys in that env's sched rows (S1 -> [0,1], Swind -> [2,3], Sidx -> [4,5]) and the final key in hot.x/y.
+__device__ __noinline__ void key_chain_pooled(EnvSmem& ce, const gca_params& P, int lane, bool wr, uint32_t k0,
+                                              uint32_t k1) {
   const int K = P.K, mode = P.rng_mode;
-  const int pair = lane >> 1;
-  uint32_t k0 = key0, k1 = key1;
-  KeySides r;
-  r.c0 = r.c1 = r.sw0 = r.sw1 = 0u;
 #pragma unroll 1
   for (int j = 0; j < K; ++j) {
+    uint32_t* sc = ce.sched[j];
     uint32_t n0, n1, s0, s1;
     split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K1, S1
-    if (pair == 2 * j) { r.c0 = s0; r.c1 = s1; }
+    if (wr) { sc[0] = s0; sc[1] = s1; }
     k0 = n0; k1 = n1;
     split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K2, Swind
-    if (pair == 2 * j + 1) { r.sw0 = s0; r.sw1 = s1; }
+    if (wr) { sc[2] = s0; sc[3] = s1; }
     k0 = n0; k1 = n1;
     split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K3, Sidx
-    if (pair == 2 * j + 1) { r.c0 = s0; r.c1 = s1; }
+    if (wr) { sc[4] = s0; sc[5] = s1; }
     k0 = n0; k1 = n1;
   }
-  key0 = k0;
-  key1 = k1;
-  return r;
+  if (wr) { ce.hot.x = k0; ce.hot.y = k1; }
 }
 __device__ __noinline__ void key_sides(EnvSmem& sm, const gca_params& P, const gca_inject& J, int N, int e,
-                                       int lane, const KeySides ks, int& widx) {
+                                       int lane, int& widx) {
   const int K = P.K, mode = P.rng_mode;
   const int pair = lane >> 1;
   const uint32_t w = lane & 1;
-  const uint32_t c0 = ks.c0, c1 = ks.c1, sw0 = ks.sw0, sw1 = ks.sw1;
   const bool burn_role = (pair & 1) == 0;
   const int j = pair >> 1;
+  uint32_t c0 = 0, c1 = 0, sw0 = 0, sw1 = 0;  // burn role: S1 ; wind role: Sidx and Swind (left by key_chain_pooled)
+  if (j < K) {
+    const uint32_t* sc = sm.sched[j];
+    if (burn_role) { c0 = sc[0]; c1 = sc[1]; }
+    else { sw0 = sc[2]; sw1 = sc[3]; c0 = sc[4]; c1 = sc[5]; }
+  }
+  __syncwarp();  // every lane has its inputs before the rows are overwritten below
   const uint32_t sc0 = (mode == GCA_RNG_LEGACY) ? w : 0u;       // split counters of this lane
   const uint32_t sc1 = (mode == GCA_RNG_LEGACY) ? w + 2u : w;
   uint32_t o0, o1, p0, p1, n0, n1, s0, s1;
@@ -381,13 +384,13 @@ __device__ __forceinline__ void prefetch_front(const EnvSmem& sm, const uint8_t*
 __device__ __forceinline__ void eval_pair(CtaSmem& cs, const gca_params& P, const uint8_t* hidden,
                                           const float* pslope, const float* j_u_burn, int mode, size_t inj_stride,
                                           int j, uint32_t ent, bool valid, uint32_t& n_thresh) {
-  EnvSmem& es = cs.env[ent >> 12];
-  const int t = (ent >> 4) & 255, d = ent & 15;
+  EnvSmem& es = cs.env[ent >> 11];
+  const int t = (ent >> 3) & 255, ds = ent & 7, d = ds + (ds >> 2);  // direction slot -> 3x3 index (skips 4)
   const uint32_t cell = es.list[t];
   const uint4 hot = es.hot;
   const size_t cell_base = (size_t)hot.w * 4096;
   float s = 1.0f;
-  if (pslope != nullptr && valid) s = pslope[(cell_base + cell) * 8 + dir_slot(d)];
+  if (pslope != nullptr && valid) s = pslope[(cell_base + cell) * 8 + ds];
   float u;
   if (j_u_burn) {
     u = valid ? j_u_burn[((size_t)j * inj_stride + cell_base + cell) * 9 + d] : 1.0f;
@@ -452,15 +455,15 @@ __device__ __forceinline__ void front_masks(unsigned long long t0, unsigned long
 }
 
 // S64_TRACE (diagnostic builds only): per-env phase timestamps (SM clock, relative to the warp's start) go to
-// O.stats[8 + 16 e ...]; the caller must have allocated stats with 8 + 24 N words.
+// O.stats[8 + 16 e ...]; the caller must have allocated stats with 8 + 32 N words.
 #ifdef S64_TRACE
-#define S64_STAMP(k) do { if (active && lane == 0 && O.stats) O.stats[8 + 24 * (size_t)e + (k)] = (unsigned long long)(clock64() - clk0); } while (0)
+#define S64_STAMP(k) do { if (active && lane == 0 && O.stats) O.stats[8 + 32 * (size_t)e + (k)] = (unsigned long long)(clock64() - clk0); } while (0)
 #else
 #define S64_STAMP(k) do { } while (0)
 #endif
 
 #ifndef S64_MINB
-#define S64_MINB (28 / S64_E)  // 28 warps/SM x 72 registers = the whole register file; 4096 envs = one wave
+#define S64_MINB (28 / S64_E)  // 28 warps/SM x 72 registers = the whole register file; 4096 envs = one wave of 148 x 28
 #endif
 // MODE: GCA_RNG_* or -1 (read P.rng_mode); HP: 0 = no hidden layers, 1 = hidden + slope table present,
 // -1 = test the pointers at run time; INJ: injected random fields may be present.  The launcher picks
@@ -537,12 +540,19 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     }
     if (lane < 16) sm.fire32[lane] = 0u; else sm.fire32[272 + lane - 16] = 0u;   // fire rows -4..-1, 64..67
     if (lane < 8) sm.dous32[lane] = 0u; else if (lane < 16) sm.dous32[264 + lane - 8] = 0u;  // rows -2,-1,64,65
+    if (lane == 0) { sm.hot.z = key0; sm.hot.w = key1; }  // for the warp that walks the CTA's key chains
     S64_STAMP(0);
-    const KeySides ks = key_chain(P, lane, key0, key1);  // ~3K dependent threefry blocks while the grid streams in
-    if (lane == 0) {
-      S.key[2 * e] = key0;
-      S.key[2 * e + 1] = key1;
-    }
+  }
+  __syncthreads();
+  if (warp >= S64_E - S64_CHAIN_WARPS) {
+    // ~3K dependent threefry blocks per env, for 16 envs at a time, while the grids stream in
+    const int p = (S64_E - 1 - warp) * 16 + (lane >> 1);
+    const bool pv = p < S64_E;
+    EnvSmem& ce = cs.env[pv ? p : 0];
+    key_chain_pooled(ce, P, lane, pv && !(lane & 1), ce.hot.z, ce.hot.w);
+  }
+  if (active) {
+    const uint32_t mbar = smem_u32(&sm.mbar);
     S64_STAMP(19);
     mbar_wait(mbar, 0u);
     const ulonglong2 dz = reinterpret_cast<const ulonglong2*>(sm.ign)[lane];
@@ -698,8 +708,15 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     // the front cells' hidden / slope-factor sectors: their DRAM latency hides behind the second half of the key schedule
     prefetch_front(sm, hidden, pslope, cell_base, 0, L, lane);
     S64_STAMP(18);
-    key_sides(sm, P, J, N, e, lane, ks, widx);
-    if (lane == 0) S.wind_index[e] = widx;
+  }
+  __syncthreads();  // the key chains are done
+  if (active) {
+    key_sides(sm, P, J, N, e, lane, widx);
+    if (lane == 0) {
+      S.key[2 * e] = sm.hot.x;
+      S.key[2 * e + 1] = sm.hot.y;
+      S.wind_index[e] = widx;
+    }
   }
 
   const float lutreg = lane < 8 ? P.onep_veg[lane] : (lane < 16 ? P.onep_den[lane - 8] : 0.0f);
@@ -847,11 +864,11 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
             const int incl2 = warp_incl_scan(nd, lane);
             int off = PT + incl2 - nd;
             const uint32_t em = nd ? dirm : 0u;
-            const uint32_t tag = ((uint32_t)es_slot << 12) | ((uint32_t)t << 4);
+            const uint32_t tag = ((uint32_t)es_slot << 11) | ((uint32_t)t << 3);
 #pragma unroll
             for (uint32_t d = 0; d < 9; ++d) {
               if (d == 4) continue;
-              if (em & (1u << d)) wp[off++] = (uint16_t)(tag | d);
+              if (em & (1u << d)) wp[off++] = (uint16_t)(tag | (d < 4 ? d : d - 1));
             }
             if (lane == 31 && incl2) atomicAdd(&es.npairs, (uint32_t)incl2);
             PT += __shfl_sync(GCA_FULL, incl2, 31);
@@ -982,6 +999,9 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     return;
   }
 
+#ifdef S64_TRACE
+  const uint32_t trace_rows = __reduce_add_sync(GCA_FULL, __popc(burnrows));  // rows scanned for burn-outs
+#endif
   // ---- sparse in-place write-back of the cells that changed --------------------------------------
   {
     unsigned long long ch = ch0;
@@ -1022,6 +1042,21 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   const bool ca_only = (flags & GCA_FLAG_CA_ONLY) != 0;
   const bool done = fcount == 0;
   if (lane == 0) {
+#ifdef S64_TRACE
+    if (O.stats) {
+      O.stats[8 + 32 * (size_t)e + 20] = work / 2u;
+      O.stats[8 + 32 * (size_t)e + 21] = sm.npairs;
+      O.stats[8 + 32 * (size_t)e + 22] = (unsigned long long)trace_rows;
+      O.stats[8 + 32 * (size_t)e + 23] = (unsigned long long)(clock64() - clk0);
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      O.stats[8 + 32 * (size_t)e + 24] = smid;
+      O.stats[8 + 32 * (size_t)e + 25] = gt;                       // end time, ns
+      O.stats[8 + 32 * (size_t)e + 26] = (unsigned long long)blockIdx.x;
+    }
+#endif
     if (S.work != nullptr)
       S.work[e] = (flags & GCA_FLAG_WORK_CYCLES) ? (uint32_t)(clock64() - clk0) : work + sm.npairs;
     S.tick[e] = tick0 + (uint32_t)K;

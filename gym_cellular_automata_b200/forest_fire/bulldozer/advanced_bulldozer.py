@@ -129,6 +129,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         # 64x64 kernel: re-deal envs to warps every `balance_every` steps by last step's cost (0 = off)
         self.balance_every = int(balance_every)
         self._steps_since_balance = 0
+        self._host_act_dev = None
         self.kernel_launches = 0  # kernels of libgca launched by the step path (step + re-balancing)
         self.num_envs = int(num_envs)
         # multi-GPU sharding: this instance holds envs [env_offset, env_offset + num_envs) of a batch of
@@ -522,6 +523,44 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         """Hot path: one fused launch on the current stream; actions and results stay in HBM."""
         self._launch_step(actions_dev, None, auto_reset)
         return self._out
+
+    def host_result_buffers(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Pinned host (reward, terminated) tensors laid out like the device outputs, for ``step_host``."""
+        N = self.num_envs
+        buf = torch.empty(5 * N, dtype=torch.uint8).pin_memory()
+        return buf[:4 * N].view(torch.float32), buf[4 * N:]
+
+    def step_host(self, actions_host: torch.Tensor, reward_host: torch.Tensor, terminated_host: torch.Tensor) -> None:
+        """The step for a CPU-side rollout loop, one C call (``gca_env_step_host``): ``actions_host`` (N,3)
+        int32, ``reward_host`` (N,) float32 and ``terminated_host`` (N,) uint8 are HOST tensors (pin them);
+        actions are copied in, the fused step runs, reward / terminated are copied out and the stream is
+        synchronised, so the results are valid on return.  State stays on the device."""
+        N = self.num_envs
+        for t, dt, n, name in ((actions_host, torch.int32, 3 * N, "actions_host"), (reward_host, torch.float32, N, "reward_host"),
+                               (terminated_host, torch.uint8, N, "terminated_host")):
+            if t.is_cuda or t.dtype != dt or t.numel() != n or not t.is_contiguous():
+                raise _lib.GcaError(f"{name}: expected a contiguous host tensor of {n} x {dt}")
+        if self._state.work is None:
+            raise _lib.GcaError("step_host is implemented for the fused 64x64 path")
+        if self._host_act_dev is None:
+            self._host_act_dev = torch.empty((N, 3), dtype=torch.int32, device=self.device)
+        flags = self._flags | (_lib.FLAG_AUTO_RESET if self.auto_reset else 0)
+        if self.balance_every:
+            if self._state.order is None:
+                self._state.enable_balancing()
+                self._version_structs += 1
+            self._steps_since_balance += 1
+            if self._steps_since_balance >= self.balance_every:
+                self._state.rebalance()
+                self._steps_since_balance = 0
+                self.kernel_launches += 1
+        self.kernel_launches += 1
+        check(load().gca_env_step_host(C.byref(self._params), C.byref(self._state.cstruct()), actions_host.data_ptr(),
+                                       self._host_act_dev.data_ptr(), C.byref(self._out.cstruct()),
+                                       C.byref(self._snapshot.cstruct()), ptr(self._snap_reward), flags,
+                                       reward_host.data_ptr(), terminated_host.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream), "gca_env_step_host")
+        self._version += 1
 
     # ------------------------------------------------------------------------------------------
     # reference helpers

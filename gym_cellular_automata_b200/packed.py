@@ -38,9 +38,12 @@ class StepOutputs:
     """Per-step device outputs (gca_step_out)."""
 
     def __init__(self, N: int, device, with_stats: bool = False):
-        self.reward = torch.zeros(N, dtype=torch.float32, device=device)
+        # reward and terminated share one allocation ([N] f32 followed by [N] u8) so that a host caller
+        # gets both with a single device-to-host copy (gca_env_step_host)
+        self._rt = torch.zeros(5 * N, dtype=torch.uint8, device=device)
+        self.reward = self._rt[:4 * N].view(torch.float32)
+        self.terminated = self._rt[4 * N:]
         self.step_reward = torch.zeros(N, dtype=torch.float32, device=device)
-        self.terminated = torch.zeros(N, dtype=torch.uint8, device=device)
         self.counts = torch.zeros((N, 2), dtype=torch.int32, device=device)
         self.obs_night = torch.zeros(N, dtype=torch.uint8, device=device)
         self.stats = torch.zeros(8, dtype=torch.int64, device=device) if with_stats else None

@@ -152,6 +152,16 @@ int gca_env_step(const gca_params* p, const gca_state* s, const int32_t* actions
                  const gca_step_out* out, const gca_inject* inj, const gca_state* snapshot,
                  const float* snapshot_reward, uint32_t flags, void* stream);
 
+/* The same step for a caller whose actions and results live in HOST memory (pinned for asynchronous
+ * copies), i.e. the call a CPU-side rollout loop makes once per step: host_actions [N][3] is copied to
+ * the device buffer dev_actions, gca_env_step runs, out->reward and out->terminated (both required) are
+ * copied to host_reward [N] / host_terminated [N] (one copy when, on both sides, terminated starts right
+ * after the N rewards), and the stream is synchronised before returning. */
+int gca_env_step_host(const gca_params* p, const gca_state* s, const int32_t* host_actions,
+                      int32_t* dev_actions, const gca_step_out* out, const gca_state* snapshot,
+                      const float* snapshot_reward, uint32_t flags, float* host_reward,
+                      uint8_t* host_terminated, void* stream);
+
 /* K CA sub-steps only (PartiallyObservableForestFireJax.update applied K times). */
 int gca_alexandridis_step(const gca_params* p, const gca_state* s, const gca_step_out* out,
                           const gca_inject* inj, uint32_t flags, void* stream);

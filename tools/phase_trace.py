@@ -16,7 +16,7 @@ env = AdvancedForestFireBulldozerEnv(64, 64, key=1, num_envs=N, speed_move=0.48,
                                      auto_reset=True, collect_stats=True, device=dev, balance_every=8)
 env.reset()
 o = env._out
-o.stats = torch.zeros(8 + 24 * N, dtype=torch.int64, device=dev)
+o.stats = torch.zeros(8 + 32 * N, dtype=torch.int64, device=dev)
 o._c = GcaStepOut(ptr(o.reward).value, ptr(o.step_reward).value, ptr(o.terminated).value, ptr(o.counts).value,
                   ptr(o.obs_night).value, ptr(o.stats).value)
 env._version_structs += 1
@@ -33,7 +33,41 @@ for mode in ("cold", "warm", "cold", "warm"):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); env.step_device(a); e1.record(); torch.cuda.synchronize()
-    tr = o.stats[8:].cpu().numpy().reshape(N, 24).astype(np.float64)
+    tr = o.stats[8:].cpu().numpy().reshape(N, 32).astype(np.float64)
+    feat = tr[:, 20:24].copy()
+    if mode == "cold":
+        order = env._state.order.cpu().numpy() if env._state.order is not None else np.arange(N)
+        E = 7
+        ncta = N // E
+        byslot = feat[order[:ncta * E]].reshape(ncta, E, 4)
+        T = byslot[:, :, 3].max(1)
+        X = np.stack([np.ones(ncta), byslot[:, :, 0].sum(1), byslot[:, :, 1].sum(1), byslot[:, :, 2].sum(1),
+                      byslot[:, :, 0].max(1), byslot[:, :, 1].max(1)], 1)
+        coef, res, *_ = np.linalg.lstsq(X, T, rcond=None)
+        pred = X @ coef
+        print("  CTA time: mean %.1fk max %.1fk std %.1fk | fit [1, sum entries, sum pairs, sum rows, max entries, max pairs] = %s, residual std %.1fk"
+              % (T.mean() / 1e3, T.max() / 1e3, T.std() / 1e3, np.round(coef, 2).tolist(), (T - pred).std() / 1e3))
+        est = byslot[:, :, 0].sum(1) * 2 + byslot[:, :, 1].sum(1)
+        print("  corr(T, current estimate sum) = %.3f ; estimate sum mean %.0f std %.0f" % (np.corrcoef(T, est)[0, 1], est.mean(), est.std()))
+        full = o.stats[8:].cpu().numpy().reshape(N, 32).astype(np.float64)[order[:ncta * E]].reshape(ncta, E, 32)
+        smid = full[:, 0, 24].astype(int); tend = full[:, :, 25].max(1); tend -= tend.min()
+        cyc = full[:, :, 23].max(1)
+        tstart = tend - cyc / 1.965  # ns
+        print("  CTA start (ns rel.): min %.0f p50 %.0f p90 %.0f max %.0f ; end: p50 %.0f max %.0f" % (
+            tstart.min(), np.percentile(tstart, 50), np.percentile(tstart, 90), tstart.max(), np.percentile(tend, 50), tend.max()))
+        per_sm = {}
+        for c in range(ncta): per_sm.setdefault(smid[c], []).append(cyc[c])
+        nper = np.array([len(v) for v in per_sm.values()]); msm = np.array([np.mean(v) for v in per_sm.values()])
+        ssm = np.array([np.std(v) for v in per_sm.values()])
+        print("  SMs used %d, CTAs/SM min %d max %d ; per-SM mean CTA cycles: min %.1fk max %.1fk std %.1fk ; mean within-SM std %.1fk" % (
+            len(per_sm), nper.min(), nper.max(), msm.min() / 1e3, msm.max() / 1e3, msm.std() / 1e3, ssm.mean() / 1e3))
+        for k in (3, 4):
+            sel = [np.mean(v) for v in per_sm.values() if len(v) == k]
+            if sel: print("   SMs with %d CTAs: %d, mean CTA cycles %.1fk" % (k, len(sel), np.mean(sel) / 1e3))
+        # per-env fit of the env's own finish time
+        Xe = np.stack([np.ones(N), feat[:, 0], feat[:, 1], feat[:, 2]], 1)
+        ce, *_ = np.linalg.lstsq(Xe, feat[:, 3], rcond=None)
+        print("  per-env fit of finish time on [1, entries, pairs, rows]:", np.round(ce, 2).tolist())
     extra = tr[:, 16:20].mean(0)
     tr = tr[:, :4 + 3 * K]
     mean = tr.mean(0); mx = tr.max(0)
