@@ -19,7 +19,7 @@
 //    32-entry chunks of those lists, handed out by a shared-memory counter to whichever warp is
 //    free: per front cell the 9x9 fire window is cut out of the bit-board, ring populations give an
 //    upper bound of the float32 burn-probability chain; the (cell, burning direction) pairs go to
-//    the warp's private pair buffer, and whenever it holds 64 pairs the warp draws them -- one
+//    the warp's private pair buffer, and whenever it holds 32 pairs the warp draws them -- one
 //    counter-based threefry2x32 block per pair reproduces exactly the uniform jax.random would have
 //    drawn for that element.  u >= hi does not ignite, u < hi (1 - 2^-14) ignites, and the (rare)
 //    in-between case is re-evaluated with the reference's exact row-major float32 summation
@@ -39,7 +39,7 @@ namespace {
 constexpr int S64_E = GCA_S64_WARPS;   // envs (= warps) per CTA
 constexpr int S64_CAP = 256;           // front cells per pass
 constexpr int S64_CHAIN_WARPS = (S64_E + 15) / 16;  // warps that walk the key chains (16 envs each)
-constexpr int S64_WP = 320;            // warp-private pair buffer: < 64 carried over + <= 256 of one chunk
+constexpr int S64_WP = 288;            // warp-private pair buffer: < 32 carried over + <= 256 of one chunk
 constexpr uint32_t S64_HALF_BURN = 9u * 4096u / 2u;
 constexpr uint32_t S64_HALF_CELL = 4096u / 2u;
 // enclosure of the fast float32 path: |sequential sum - ring-count sum| <= 89 u |sum|
@@ -379,44 +379,64 @@ __device__ __forceinline__ void prefetch_front(const EnvSmem& sm, const uint8_t*
   }
 }
 
-// One buffered (front cell, burning direction) draw of ANY env of the CTA; ignitions are or-ed into
-// that env's accumulator.
-__device__ __forceinline__ void eval_pair(CtaSmem& cs, const gca_params& P, const uint8_t* hidden,
-                                          const float* pslope, const float* j_u_burn, int mode, size_t inj_stride,
-                                          int j, uint32_t ent, bool valid, uint32_t& n_thresh) {
+// One buffered (front cell, burning direction) draw of ANY env of the CTA, in three steps so that the two
+// draws a lane makes per round share one basic block: pair_load (decode, shared / global loads, upper
+// bound of p, threefry counters), the random word (threefry2x32_x2 or the injected field), pair_finish
+// (compare; ignitions are or-ed into that env's accumulator).
+struct PairCtx {
+  EnvSmem* es;
+  uint32_t cell;    // (row << 6) | col
+  uint32_t ds;      // direction slot 0..7
+  float bs;         // stored bound of the cell (sign = dousing nearby)
+  float w, s;       // wind and slope factors of the direction
+  float phi;        // upper bound of the burn probability
+  TfKey key;        // Sburn of the env's current sub-step
+  uint32_t c0, c1;  // threefry counters of the element; `first` tells which output word it is (legacy layout)
+  bool first;
+};
+__device__ __forceinline__ void pair_load(CtaSmem& cs, const float* pslope, int mode, uint32_t ent, bool valid,
+                                          PairCtx& c) {
   EnvSmem& es = cs.env[ent >> 11];
-  const int t = (ent >> 3) & 255, ds = ent & 7, d = ds + (ds >> 2);  // direction slot -> 3x3 index (skips 4)
-  const uint32_t cell = es.list[t];
+  const int t = (ent >> 3) & 255;
+  c.es = &es;
+  c.ds = ent & 7;
+  const uint32_t d = c.ds + (c.ds >> 2);  // direction slot -> 3x3 index (skips the centre)
+  c.cell = es.list[t];
   const uint4 hot = es.hot;
-  const size_t cell_base = (size_t)hot.w * 4096;
-  float s = 1.0f;
-  if (pslope != nullptr && valid) s = pslope[(cell_base + cell) * 8 + ds];
-  float u;
-  if (j_u_burn) {
-    u = valid ? j_u_burn[((size_t)j * inj_stride + cell_base + cell) * 9 + d] : 1.0f;
+  c.s = 1.0f;
+  if (pslope != nullptr && valid) c.s = pslope[((size_t)hot.w * 4096 + c.cell) * 8 + c.ds];
+  c.bs = es.base[t];
+  c.w = es.wind[d];
+  c.key.k0 = hot.x; c.key.k1 = hot.y; c.key.k2 = hot.z;
+  const uint32_t idx = c.cell * 9u + d;
+  if (mode == GCA_RNG_LEGACY) {
+    c.first = idx < S64_HALF_BURN;
+    c.c0 = c.first ? idx : idx - S64_HALF_BURN;
+    c.c1 = c.c0 + S64_HALF_BURN;
   } else {
-    TfKey kb;
-    kb.k0 = hot.x; kb.k1 = hot.y; kb.k2 = hot.z;
-    u = bits_to_uniform(bits_at(kb, cell * 9u + (uint32_t)d, S64_HALF_BURN, mode));
+    c.first = true;
+    c.c0 = 0u;
+    c.c1 = idx;
   }
-  const float bs = es.base[t];
-  const float w = es.wind[d];
-  const float phi = __fmul_rn(__fmul_rn(fabsf(bs), w), s);
-  if (valid && u < phi) {
-    bool ig = bs > 0.0f && u < __fmul_rn(phi, S64_SURE);
+  c.phi = __fmul_rn(__fmul_rn(fabsf(c.bs), c.w), c.s);
+}
+__device__ __forceinline__ void pair_finish(const gca_params& P, const uint8_t* hidden, const PairCtx& c, bool valid,
+                                            float u, uint32_t env, uint32_t& n_thresh) {
+  if (valid && u < c.phi) {
+    bool ig = c.bs > 0.0f && u < __fmul_rn(c.phi, S64_SURE);
     if (!ig) {
       // threshold cell: the float32 enclosure cannot decide -> reference-order evaluation
-      const int r = cell >> 6, c = cell & 63;
+      const int r = c.cell >> 6, col = c.cell & 63;
       int hid = 3 | (3 << 3);
-      if (hidden != nullptr) hid = hidden[cell_base + cell];
+      if (hidden != nullptr) hid = hidden[(size_t)env * 4096 + c.cell];
       const float a = P.onep_veg[clip15(hid & 7)];
       const float b = P.onep_den[clip15((hid >> 3) & 7)];
-      const float base = exact_base(es, P, r, c, a, b);
-      const float p = __fmul_rn(__fmul_rn(base, w), s);
+      const float base = exact_base(*c.es, P, r, col, a, b);
+      const float p = __fmul_rn(__fmul_rn(base, c.w), c.s);
       ig = u < p;
       n_thresh++;
     }
-    if (ig) atomicOr(reinterpret_cast<uint32_t*>(es.ign) + (cell >> 5), 1u << (cell & 31));
+    if (ig) atomicOr(reinterpret_cast<uint32_t*>(c.es->ign) + (c.cell >> 5), 1u << (c.cell & 31));
   }
 }
 
@@ -809,7 +829,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         int next_item = warp;
 #endif
         for (;;) {
-          if (PT < 64 && more_items) {
+          if (PT < 32 && more_items) {
 #ifdef S64_STATIC_ITEMS
             const int item = next_item;
             next_item += S64_E;
@@ -876,18 +896,25 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
             continue;
           }
           if (PT == 0) break;
-          // ---- draw up to 64 buffered pairs: two per lane = two independent threefry chains --------
-          const int n = min(PT, 64);
+          // ---- draw up to 32 buffered pairs, one per lane.  (Two interleaved draws per lane were measured:
+          //      no gain -- with 7 warps per scheduler this phase is bound by the integer pipe, not by latency --
+          //      and a 64-wide round wastes more lanes when a warp flushes its last pairs.)
+          const int n = min(PT, 32);
           PT -= n;
           n_draws += (lane == 0) ? (uint32_t)n : 0u;
-          const uint16_t* q = wp + PT;
-          const bool va = lane < n, vb = lane + 32 < n;
-          const uint32_t ea = va ? q[lane] : 0u;
-          eval_pair(cs, P, hidden, pslope, j_u_burn, mode, (size_t)N * 4096, j, ea, va, n_thresh);
-          if (n > 32) {
-            const uint32_t eb = vb ? q[lane + 32] : 0u;
-            eval_pair(cs, P, hidden, pslope, j_u_burn, mode, (size_t)N * 4096, j, eb, vb, n_thresh);
+          const bool va = lane < n;
+          PairCtx A;
+          pair_load(cs, pslope, mode, va ? wp[PT + lane] : 0u, va, A);
+          float ua;
+          if (j_u_burn) {
+            const size_t inj0 = (size_t)j * N * 4096;
+            ua = va ? j_u_burn[(inj0 + (size_t)A.es->hot.w * 4096 + A.cell) * 9 + A.ds + (A.ds >> 2)] : 1.0f;
+          } else {
+            uint32_t o0, o1;
+            threefry2x32(A.key, A.c0, A.c1, o0, o1);
+            ua = bits_to_uniform(mode == GCA_RNG_LEGACY ? (A.first ? o0 : o1) : (o0 ^ o1));
           }
+          pair_finish(P, hidden, A, va, ua, A.es->hot.w, n_thresh);
           __syncwarp();
         }
       }
