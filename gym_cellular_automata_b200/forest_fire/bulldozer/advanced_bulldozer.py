@@ -540,12 +540,10 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                                (terminated_host, torch.uint8, N, "terminated_host")):
             if t.is_cuda or t.dtype != dt or t.numel() != n or not t.is_contiguous():
                 raise _lib.GcaError(f"{name}: expected a contiguous host tensor of {n} x {dt}")
-        if self._state.work is None:
-            raise _lib.GcaError("step_host is implemented for the fused 64x64 path")
         if self._host_act_dev is None:
             self._host_act_dev = torch.empty((N, 3), dtype=torch.int32, device=self.device)
         flags = self._flags | (_lib.FLAG_AUTO_RESET if self.auto_reset else 0)
-        if self.balance_every:
+        if self.balance_every and self._state.work is not None:
             if self._state.order is None:
                 self._state.enable_balancing()
                 self._version_structs += 1
@@ -554,7 +552,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                 self._state.rebalance()
                 self._steps_since_balance = 0
                 self.kernel_launches += 1
-        self.kernel_launches += 1
+        self.kernel_launches += 1 if self._state.work is not None else 2 * self.substeps + 1
         check(load().gca_env_step_host(C.byref(self._params), C.byref(self._state.cstruct()), actions_host.data_ptr(),
                                        self._host_act_dev.data_ptr(), C.byref(self._out.cstruct()),
                                        C.byref(self._snapshot.cstruct()), ptr(self._snap_reward), flags,

@@ -26,7 +26,7 @@ def act():
                         torch.randint(0, 3, (N,), device=dev, generator=gen)], -1).to(torch.int32).contiguous()
 for _ in range(100): env.step_device(act())
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-names = ["setup", "chain+wait+convert+list", "scan", "(rm)"] + sum([[f"s{j} owner-pre", f"s{j} pooled", f"s{j} barrier"] for j in range(K)], [])
+names = ["setup+publish key", "barrier+wait+convert+list", "scan", "(rm)"] + sum([[f"s{j} owner-pre", f"s{j} pooled", f"s{j} barrier"] for j in range(K)], [])
 for mode in ("cold", "warm", "cold", "warm"):
     a = act()
     if mode == "cold": flush.fill_(1)
@@ -37,7 +37,7 @@ for mode in ("cold", "warm", "cold", "warm"):
     feat = tr[:, 20:24].copy()
     if mode == "cold":
         order = env._state.order.cpu().numpy() if env._state.order is not None else np.arange(N)
-        E = 7
+        E = int(os.environ.get('E', 14))
         ncta = N // E
         byslot = feat[order[:ncta * E]].reshape(ncta, E, 4)
         T = byslot[:, :, 3].max(1)
