@@ -70,7 +70,12 @@ def cpu_port_throughput(size, K, n_envs, steps, warmup, mode="legacy", use_hidde
     E = ax.EnvConstants(size, size, speed_move=0.12 * 4, speed_act=0.03 * 4)
     co = COracle(E, oinit.get_winds(), K=K, mode=m)
     rng = np.random.default_rng(seed)
-    threads = COracle.max_threads()
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what this arm measures)
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    threads = max(threads, COracle.max_threads())
 
     def act():
         return np.stack([rng.integers(0, 9, n_envs), rng.integers(0, 2, n_envs), rng.integers(0, 3, n_envs)],
@@ -353,12 +358,18 @@ def run_v3(args):
 
 def main():
     args = parse()
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.ruleset == "v3":
-        return run_v3(args)
-    if args.impl == "reference":
+        run_v3(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -51,7 +51,7 @@ class GcaState(C.Structure):
         ("time_step", C.c_void_p), ("is_night", C.c_void_p),
         ("steps_elapsed", C.c_void_p), ("reward_accumulated", C.c_void_p),
         ("scratch_cell", C.c_void_p), ("scratch_u32", C.c_void_p),
-        ("work", C.c_void_p), ("order", C.c_void_p),
+        ("work", C.c_void_p), ("order", C.c_void_p), ("bb", C.c_void_p),
     ]
 
 

@@ -162,7 +162,8 @@ int gca_env_step(const gca_params* p, const gca_state* s, const int32_t* actions
   gca_state st = *s;
   if (flags & GCA_FLAG_NO_HIDDEN) { st.hidden = nullptr; st.pslope = nullptr; }
   if (is64(p)) {
-    if (!s->row_min) return fail(GCA_ERR_ARG, "gca_env_step: 64x64 path needs row_min");
+    if (!s->row_min || !s->bb) return fail(GCA_ERR_ARG, "gca_env_step: 64x64 path needs row_min and bb");
+    if ((flags & GCA_FLAG_AUTO_RESET) && !sn.bb) return fail(GCA_ERR_ARG, "gca_env_step: the snapshot needs bb");
     return check_cuda(gca::launch_env_step64(*p, st, actions, o, j, sn, snapshot_reward, flags, (cudaStream_t)stream),
                       "env_step64");
   }

@@ -28,17 +28,19 @@ __global__ void pack_state_kernel(gca_params P, gca_state S, const float* __rest
   const int e = (int)(er / H);
   const uint32_t tick = S.tick[e];
   uint32_t rowmin = 0xFFFFFFFFu;
-  unsigned long long dmask = 0;
+  unsigned long long dmask = 0, tmask = 0, fmask = 0;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int c = ws * 64 + h * 32 + lane;
     bool dbit = false;
+    int ccode = 0;
     if (c < W) {
       const size_t i = (size_t)er * W + c;
       const float g = grid[i];
       const int code = g == 2.0f ? 2 : (g == 1.0f ? 1 : 0);
       if (!(g == 0.0f || g == 1.0f || g == 2.0f) && err_flag) atomicOr(err_flag, 1);
       S.cell[i] = (uint8_t)code;
+      ccode = code;
       const float a = fire_age[i];
       const int ai = (int)a;
       uint32_t field;
@@ -62,8 +64,11 @@ __global__ void pack_state_kernel(gca_params P, gca_state S, const float* __rest
       dbit = dc != 0;
     }
     dmask |= (unsigned long long)__ballot_sync(GCA_FULL, dbit) << (32 * h);
+    tmask |= (unsigned long long)__ballot_sync(GCA_FULL, ccode == 1) << (32 * h);
+    fmask |= (unsigned long long)__ballot_sync(GCA_FULL, ccode == 2) << (32 * h);
   }
   if (lane == 0) S.doused[seg] = dmask;
+  if (lane == 0 && S.bb != nullptr) { S.bb[2 * seg] = tmask; S.bb[2 * seg + 1] = fmask; }
   // row_min is only defined (and only used) for single-segment rows, i.e. W <= 64
   rowmin = __reduce_min_sync(GCA_FULL, rowmin);
   if (lane == 0 && S.row_min != nullptr && WW == 1) S.row_min[er] = rowmin;
@@ -146,6 +151,9 @@ __global__ void conditional_reset_kernel(gca_params P, gca_state S, gca_state SN
     S.doused[(size_t)e * H * WW + i] = SNAP.doused[(size_t)e * H * WW + i];
   if (S.row_min != nullptr && SNAP.row_min != nullptr && WW == 1)
     for (int i = threadIdx.x; i < H; i += blockDim.x) S.row_min[(size_t)e * H + i] = SNAP.row_min[(size_t)e * H + i];
+  if (S.bb != nullptr && SNAP.bb != nullptr)
+    for (size_t i = threadIdx.x; i < (size_t)H * WW * 2; i += blockDim.x)
+      S.bb[(size_t)e * H * WW * 2 + i] = SNAP.bb[(size_t)e * H * WW * 2 + i];
   __syncthreads();
   if (threadIdx.x == 0) {
     S.key[2 * e] = SNAP.key[2 * e];

@@ -13,7 +13,8 @@
 //  * a 64-cell row is one 64-bit word per mask (tree, fire, doused).  Lane l of the owner warp holds
 //    rows 2l, 2l+1 in registers; vertical halos come from warp shuffles.
 //  * all K CA sub-steps of the env step are applied on-chip (temporal blocking); HBM sees one
-//    coalesced 128-bit read of the u8 grid and sparse in-place writes of the cells that changed.
+//    coalesced read of the env's tree / fire bit-boards (1 KB, the packed twin of the u8 grid) and
+//    sparse in-place writes of the cells (u8 grid) and bit-board rows that changed.
 //  * front cells (tree with a burning Moore neighbour) are compacted into a per-env shared-memory
 //    list (built once per env step, extended incrementally).  Work items of the pooled phase are
 //    32-entry chunks of those lists, handed out by a shared-memory counter to whichever warp is
@@ -53,27 +54,21 @@ constexpr uint32_t S64_HALF_CELL = 4096u / 2u;
 struct __align__(16) EnvSmem {
   uint32_t fire32[72 * 4];          // fire rows -4..67, 4 overlapping 32-bit views per row
   uint32_t dous32[68 * 4];          // doused rows -2..65, same views
-  unsigned long long ign[64];       // ignition accumulator of the sub-step (prologue: landing zone of the doused rows)
-  // ---- the next four arrays (4096 bytes) double as the landing zone of the env's u8 grid (bulk copy) ----
+  unsigned long long ign[64];       // ignition accumulator of the sub-step
   unsigned long long burn[64][4];   // rows with burn-outs in this env step: mask, sub-step bit planes 0..2
   unsigned long long listed[64];    // cells that are (or were) on the front list
   float base[S64_CAP];              // per listed cell: upper bound of (p_h (1+p_veg)) (1+p_den); negative =
                                     //   dousing nearby, no cheap lower bound (apply: burn-out ticks)
   uint16_t list[S64_CAP];           // front cells: (row << 6) | col
-  // ---------------------------------------------------------------------------------------------------------
   uint32_t sched[GCA_MAX_K][12];    // per sub-step: Sburn[2] Sgrow[2] ak1[2] ak2[2] wind change step pad
   uint4 hot;                        // current sub-step: Sburn k0, k1, k0^k1^C ; env index
   float wind[12];                   // current sub-step: wind matrix (9 used)
   int cnt;                          // list entries of the current pass
   uint32_t dous_even, dous_odd;     // bit l: some doused cell within 2 rows of row 2l / 2l+1
   uint32_t npairs;                  // draws of this env step (cost estimate)
-  unsigned long long mbar;          // completion barrier of the prologue's bulk copies
-  unsigned long long pad;
 };
-static_assert(offsetof(EnvSmem, list) + sizeof(uint16_t) * S64_CAP - offsetof(EnvSmem, burn) == 4096,
-              "burn/listed/base/list must be 4096 contiguous bytes (landing zone of the u8 grid)");
 static_assert(S64_E >= 1 && S64_E <= 32 && 28 % S64_E == 0, "envs per CTA: a divisor of 28 (28 warps of 72 registers fill an SM)");
-static_assert(offsetof(EnvSmem, burn) % 16 == 0 && offsetof(EnvSmem, ign) % 16 == 0, "bulk copies need 16-byte alignment");
+static_assert(sizeof(EnvSmem) % 16 == 0 && offsetof(EnvSmem, burn) % 16 == 0 && offsetof(EnvSmem, hot) % 16 == 0, "128-bit shared accesses");
 
 struct __align__(16) CtaSmem {
   EnvSmem env[S64_E];
@@ -82,22 +77,6 @@ struct __align__(16) CtaSmem {
   int next;                         // work-item counter of the pooled phase
   int pad[3];
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// 1-D bulk copy global -> shared by the TMA unit (16-byte aligned, size a multiple of 16), completion on mbar
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint32_t mbar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-  }
-}
 
 __device__ __forceinline__ void prefetch_l1(const void* p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
@@ -120,21 +99,6 @@ __device__ __forceinline__ void store_row_views(uint32_t* dst, unsigned long lon
   w.z = (uint32_t)(x >> 28);
   w.w = (uint32_t)(x >> 44);
   *reinterpret_cast<uint4*>(dst) = w;
-}
-
-// 16 u8 cells -> 16-bit tree and fire masks (bit i = cell i)
-__device__ __forceinline__ void cells16_to_bits(const uint4& v, uint32_t& t16, uint32_t& f16) {
-  const uint32_t M = 0x00204081u;  // gathers bit 0 of each byte into bits 21..24
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-  t16 = 0;
-  f16 = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint32_t tb = w[k] & 0x01010101u;
-    const uint32_t fb = (w[k] >> 1) & 0x01010101u;
-    t16 |= (((tb * M) >> 21) & 0xFu) << (4 * k);
-    f16 |= (((fb * M) >> 21) & 0xFu) << (4 * k);
-  }
 }
 
 __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
@@ -524,22 +488,21 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   uint32_t n_draws = 0, n_thresh = 0, n_front = 0, n_ign = 0, n_ext = 0;
   uint32_t work = 0;  // warp-uniform cost estimate of this env step (front cells; draws are added at the end)
 
+  ulonglong2 dz = make_ulonglong2(0ull, 0ull);
   if (active) {
-    // ---- the env's u8 grid (4 KB), doused rows and row minima: three bulk copies into shared memory,
-    //      in flight while this warp walks the key chain ----------------------------------------------
-    const uint32_t mbar = smem_u32(&sm.mbar);
-    key0 = S.key[2 * e];  // ahead of the bulk copies: the key chain below starts as soon as it is here
+    // ---- everything the step needs from HBM up front: the key (first: the chain warp waits for it), the
+    //      tree / fire bit-boards of the grid (1 KB per env; lane l takes rows 2l, 2l+1), doused rows,
+    //      row minima, scalars --------------------------------------------------------------------------
+    key0 = S.key[2 * e];
     key1 = S.key[2 * e + 1];
     S64_STAMP(16);
-    if (lane == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(4096u + 512u + 256u) : "memory");
-      bulk_g2s(sm.burn, S.cell + cell_base, 4096u, mbar);
-      bulk_g2s(sm.ign, S.doused + (size_t)e * 64, 512u, mbar);
-      bulk_g2s(wp, S.row_min + (size_t)e * 64, 256u, mbar);
+    {
+      const ulonglong2* bbp = reinterpret_cast<const ulonglong2*>(S.bb + (size_t)e * 128);
+      const ulonglong2 r0 = bbp[2 * lane], r1 = bbp[2 * lane + 1];
+      t0 = r0.x; f0 = r0.y; t1 = r1.x; f1 = r1.y;
     }
-    __syncwarp();
+    dz = reinterpret_cast<const ulonglong2*>(S.doused + (size_t)e * 64)[lane];
+    rm = reinterpret_cast<const uint2*>(S.row_min + (size_t)e * 64)[lane];
     S64_STAMP(17);
     tick0 = S.tick[e];
     widx = S.wind_index[e];
@@ -572,26 +535,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     key_chain_pooled(ce, P, lane, pv && !(lane & 1), ce.hot.z, ce.hot.w);
   }
   if (active) {
-    const uint32_t mbar = smem_u32(&sm.mbar);
     S64_STAMP(19);
-    mbar_wait(mbar, 0u);
-    const ulonglong2 dz = reinterpret_cast<const ulonglong2*>(sm.ign)[lane];
-    rm = reinterpret_cast<const uint2*>(wp)[lane];
-    {
-      // lane l owns rows 2l, 2l+1 = 128 contiguous bytes of the landing zone; the 16-byte pieces are read
-      // in a rotated order so that the 8 lanes of a quarter-warp hit 8 different bank groups
-      const uint4* cz = reinterpret_cast<const uint4*>(sm.burn) + lane * 8;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int pc = (i + lane) & 7;
-        uint32_t t16, f16;
-        cells16_to_bits(cz[pc], t16, f16);
-        const int sh = 16 * (pc & 3);
-        const unsigned long long tb = (unsigned long long)t16 << sh, fb = (unsigned long long)f16 << sh;
-        if (pc < 4) { t0 |= tb; f0 |= fb; } else { t1 |= tb; f1 |= fb; }
-      }
-    }
-    __syncwarp();  // the landing zones are free from here on
     sm.ign[2 * lane] = 0ull;
     sm.ign[2 * lane + 1] = 0ull;
     store_row_views(sm.dous32 + (2 * lane + 2) * 4, dz.x);
@@ -1047,6 +991,12 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       row = 2 * lane + 1;
     }
   }
+  {
+    // the bit-board copy of the grid: rows that changed
+    ulonglong2* bbp = reinterpret_cast<ulonglong2*>(S.bb + (size_t)e * 128);
+    if (ch0) bbp[2 * lane] = make_ulonglong2(t0, f0);
+    if (ch1) bbp[2 * lane + 1] = make_ulonglong2(t1, f1);
+  }
   reinterpret_cast<uint2*>(S.row_min + (size_t)e * 64)[lane] = rm;
   const int tcount = __reduce_add_sync(GCA_FULL, __popcll(t0) + __popcll(t1));
   const int fcount = __reduce_add_sync(GCA_FULL, __popcll(f0) + __popcll(f1));
@@ -1136,6 +1086,12 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         reinterpret_cast<const ulonglong2*>(SNAP.doused + (size_t)e * 64)[lane];
     reinterpret_cast<uint2*>(S.row_min + (size_t)e * 64)[lane] =
         reinterpret_cast<const uint2*>(SNAP.row_min + (size_t)e * 64)[lane];
+    {
+      const ulonglong2* sb = reinterpret_cast<const ulonglong2*>(SNAP.bb + (size_t)e * 128);
+      ulonglong2* db = reinterpret_cast<ulonglong2*>(S.bb + (size_t)e * 128);
+      db[2 * lane] = sb[2 * lane];
+      db[2 * lane + 1] = sb[2 * lane + 1];
+    }
     if (lane == 0) {
       S.key[2 * e] = SNAP.key[2 * e];
       S.key[2 * e + 1] = SNAP.key[2 * e + 1];

@@ -130,6 +130,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         self.balance_every = int(balance_every)
         self._steps_since_balance = 0
         self._host_act_dev = None
+        self._host_args = None
         self.kernel_launches = 0  # kernels of libgca launched by the step path (step + re-balancing)
         self.num_envs = int(num_envs)
         # multi-GPU sharding: this instance holds envs [env_offset, env_offset + num_envs) of a batch of
@@ -536,28 +537,38 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         actions are copied in, the fused step runs, reward / terminated are copied out and the stream is
         synchronised, so the results are valid on return.  State stays on the device."""
         N = self.num_envs
-        for t, dt, n, name in ((actions_host, torch.int32, 3 * N, "actions_host"), (reward_host, torch.float32, N, "reward_host"),
-                               (terminated_host, torch.uint8, N, "terminated_host")):
-            if t.is_cuda or t.dtype != dt or t.numel() != n or not t.is_contiguous():
-                raise _lib.GcaError(f"{name}: expected a contiguous host tensor of {n} x {dt}")
-        if self._host_act_dev is None:
-            self._host_act_dev = torch.empty((N, 3), dtype=torch.int32, device=self.device)
+        if (actions_host.is_cuda or actions_host.dtype != torch.int32 or actions_host.numel() != 3 * N
+                or not actions_host.is_contiguous()):
+            raise _lib.GcaError(f"actions_host: expected a contiguous host tensor of {3 * N} x int32")
+        ha = self._host_args
+        if ha is None or ha[0] != (reward_host.data_ptr(), terminated_host.data_ptr(), self._version_structs):
+            for t, dt, name in ((reward_host, torch.float32, "reward_host"), (terminated_host, torch.uint8, "terminated_host")):
+                if t.is_cuda or t.dtype != dt or t.numel() != N or not t.is_contiguous():
+                    raise _lib.GcaError(f"{name}: expected a contiguous host tensor of {N} x {dt}")
+            if self._host_act_dev is None:
+                self._host_act_dev = torch.empty((N, 3), dtype=torch.int32, device=self.device)
+            # every pointer that does not change from step to step, bound once
+            ha = self._host_args = (
+                (reward_host.data_ptr(), terminated_host.data_ptr(), self._version_structs), load().gca_env_step_host,
+                C.byref(self._params), C.byref(self._state.cstruct()), self._host_act_dev.data_ptr(),
+                C.byref(self._out.cstruct()), C.byref(self._snapshot.cstruct()), ptr(self._snap_reward),
+                reward_host.data_ptr(), terminated_host.data_ptr())
         flags = self._flags | (_lib.FLAG_AUTO_RESET if self.auto_reset else 0)
         if self.balance_every and self._state.work is not None:
             if self._state.order is None:
                 self._state.enable_balancing()
                 self._version_structs += 1
+                return self.step_host(actions_host, reward_host, terminated_host)  # re-bind the cached pointers
             self._steps_since_balance += 1
             if self._steps_since_balance >= self.balance_every:
                 self._state.rebalance()
                 self._steps_since_balance = 0
                 self.kernel_launches += 1
         self.kernel_launches += 1 if self._state.work is not None else 2 * self.substeps + 1
-        check(load().gca_env_step_host(C.byref(self._params), C.byref(self._state.cstruct()), actions_host.data_ptr(),
-                                       self._host_act_dev.data_ptr(), C.byref(self._out.cstruct()),
-                                       C.byref(self._snapshot.cstruct()), ptr(self._snap_reward), flags,
-                                       reward_host.data_ptr(), terminated_host.data_ptr(),
-                                       torch.cuda.current_stream().cuda_stream), "gca_env_step_host")
+        rc = ha[1](ha[2], ha[3], actions_host.data_ptr(), ha[4], ha[5], ha[6], ha[7], flags, ha[8], ha[9],
+                   torch.cuda.current_stream().cuda_stream)
+        if rc:
+            check(rc, "gca_env_step_host")
         self._version += 1
 
     # ------------------------------------------------------------------------------------------

@@ -84,10 +84,12 @@ class PackedState:
         self.scratch_u32 = torch.zeros((N, 14), dtype=torch.int32, device=d) if tiled else None
         self.work = None if tiled else torch.zeros(N, dtype=torch.int32, device=d)
         self.order = None   # set by enable_balancing()
+        # tree / fire bit-boards, the grid representation the 64x64 kernel reads (kept in step with `cell`)
+        self.bb = None if tiled else torch.zeros((N, H, self.WW, 2), dtype=torch.int64, device=d)
         self._c = None
 
     _FIELDS = ("cell", "death", "hidden", "doused", "pslope", "row_min", "tick", "key", "wind_index", "position",
-               "time", "time_step", "is_night", "steps_elapsed", "reward_accumulated", "scratch_cell", "scratch_u32", "work", "order")
+               "time", "time_step", "is_night", "steps_elapsed", "reward_accumulated", "scratch_cell", "scratch_u32", "work", "order", "bb")
 
     def cstruct(self) -> GcaState:
         if self._c is None:

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GCA_VERSION 100
+#define GCA_VERSION 101
 #define GCA_MAX_R 10        /* burn kernel radius: ceil(log2(size)) - 2; 10 at 4096 */
 #define GCA_MAX_K 8         /* CA sub-steps fused into one env step */
 
@@ -113,6 +113,11 @@ typedef struct gca_state {
    * fire front costs): the kernel writes work[e]; gca_balance_order turns it into order[] */
   uint32_t* work;             /* [N] cost estimate of the last env step, or NULL */
   const int32_t* order;       /* [N] env index handled by warp slot i (a permutation), or NULL */
+  /* tree / fire bit-boards u64 [N][H][WW][2] (bit (c & 63) of word pair c >> 6: tree, fire), a second
+   * representation of `cell` kept in step with it by gca_pack_state, gca_conditional_reset and the 64x64
+   * step kernel, which reads its grid from here (1 KB per env instead of 4 KB); required for 64x64,
+   * ignored (may be NULL) by the tiled path */
+  uint64_t* bb;
 } gca_state;
 
 /* Per-step outputs (device). Any pointer may be NULL to skip that output. */

@@ -492,3 +492,22 @@ def test_step_host_equals_step_device(cuda_device):
         assert torch.equal(out.reward.cpu(), h_rew) and torch.equal(out.terminated.cpu(), h_term)
     for f in ("cell", "death", "doused", "key", "position", "time", "tick", "wind_index"):
         assert torch.equal(getattr(envs[0]._state, f), getattr(envs[1]._state, f)), f
+
+
+@pytest.mark.parametrize("mixed", [False, True])
+def test_dense_front_multi_pass(cuda_device, mixed):
+    """Hundreds of scattered fires: more than 256 front cells per env, so the 64x64 kernel rebuilds its front
+    list per sub-step and works through it in several passes -- with `mixed`, next to sparse envs of the
+    same CTA (the pass loop is CTA-uniform).  Short remaining ages make burn-outs start at once."""
+    from parity_util import make_pair, lockstep, sync
+    env, co, E, state, info = make_pair(N=20, K=4, mode="legacy", use_hidden=True, seed=17, scatter_fire=0.03)
+    if mixed:
+        _, _, _, plain, _ = make_pair(N=20, K=4, mode="legacy", use_hidden=True, seed=17)
+        for k in ("true_grid", "fire_age"):
+            state["per_env_context"][k][::2] = plain["per_env_context"][k][::2]
+        sync(env, state, as_snapshot=True)
+    front0 = env.stats()[0]
+    nbad, reports, stats = lockstep(env, co, state, 25, np.random.default_rng(12))
+    assert nbad == 0, _fmt(reports)
+    assert stats[0] - front0 > 20 * 256 * (1 if mixed else 2), "the fronts were not dense enough to need several passes"
+    assert stats[3] > 0
