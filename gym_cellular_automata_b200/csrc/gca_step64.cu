@@ -65,7 +65,7 @@ struct __align__(16) EnvSmem {
   float wind[12];                   // current sub-step: wind matrix (9 used)
   int cnt;                          // list entries of the current pass
   uint32_t dous_even, dous_odd;     // bit l: some doused cell within 2 rows of row 2l / 2l+1
-  uint32_t npairs;                  // draws of this env step (cost estimate)
+  uint32_t pad0;
 };
 static_assert(S64_E >= 1 && S64_E <= 32 && 28 % S64_E == 0, "envs per CTA: a divisor of 28 (28 warps of 72 registers fill an SM)");
 static_assert(sizeof(EnvSmem) % 16 == 0 && offsetof(EnvSmem, burn) % 16 == 0 && offsetof(EnvSmem, hot) % 16 == 0, "128-bit shared accesses");
@@ -486,7 +486,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   int T = 0, L = 0;
   bool dense = false;
   uint32_t n_draws = 0, n_thresh = 0, n_front = 0, n_ign = 0, n_ext = 0;
-  uint32_t work = 0;  // warp-uniform cost estimate of this env step (front cells; draws are added at the end)
+  uint32_t work = 0;  // warp-uniform cost estimate of this env step: front-list entries over its sub-steps
 
   ulonglong2 dz = make_ulonglong2(0ull, 0ull);
   if (active) {
@@ -546,7 +546,6 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       if (lane == 0) {
         sm.dous_even = ev | (ev << 1) | (ev >> 1) | od | (od << 1);
         sm.dous_odd = od | (od << 1) | (od >> 1) | ev | (ev >> 1);
-        sm.npairs = 0u;
       }
     }
     store_row_views(sm.fire32 + (2 * lane + 4) * 4, f0);
@@ -615,24 +614,21 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         // (both rows of the source lane are fetched: the groups of one round may want different parities)
         const unsigned long long fe = shfl64(f0, idx & 31), fo = shfl64(f1, idx & 31);
         const unsigned long long frow = (idx >> 5) ? fo : fe;
-        const uint32_t fb = (uint32_t)(frow >> (8 * li)) & 0xFFu;  // fire bits of this lane's 8 cells
+        const uint32_t fb = have ? (uint32_t)(frow >> (8 * li)) & 0xFFu : 0u;  // fire bits of this lane's 8 cells
         uint32_t w[4] = {dv.x, dv.y, dv.z, dv.w};
         uint32_t die8 = 0, p0 = 0, p1 = 0, p2 = 0, vmin = 0xFFFFFFFFu;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 8; ++k) {  // branch-free: selects and masks only
           const uint32_t d = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
           const uint32_t r = (d - tick0) & 0xFFFFu;
-          const bool f = have && ((fb >> k) & 1u);
-          const bool x = f && r < (uint32_t)K;
-          if (x) {
-            die8 |= 1u << k;
-            p0 |= (r & 1u) << k;
-            p1 |= ((r >> 1) & 1u) << k;
-            p2 |= ((r >> 2) & 1u) << k;
-            w[k >> 1] &= ~(0xFFFFu << (16 * (k & 1)));  // burnt-out cell: fire_age ends at 0
-          } else if (f) {
-            vmin = min(vmin, tick0 + r);
-          }
+          const uint32_t f = (fb >> k) & 1u;
+          const uint32_t x = r < (uint32_t)K ? f : 0u;  // burns out during this env step (at sub-step r)
+          die8 |= x << k;
+          p0 |= (x & r) << k;
+          p1 |= (x & (r >> 1)) << k;
+          p2 |= (x & (r >> 2)) << k;
+          w[k >> 1] &= ~((0u - x) & (0xFFFFu << (16 * (k & 1))));  // burnt-out cell: fire_age ends at 0
+          vmin = min(vmin, (f ^ x) ? tick0 + r : 0xFFFFFFFFu);      // fires that keep burning: earliest burn-out
         }
         if (die8)
           *reinterpret_cast<uint4*>(S.death + cell_base + row * 64 + 8 * li) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -737,7 +733,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       if (lane < 9) sm.wind[lane] = P.winds[(int)sc[8] * 9 + lane];
     }
     const int total = active ? (dense ? T : L) : 0;
-    work += 2u * (uint32_t)total;
+    work += (uint32_t)total;
 
     for (int pass = 0;; ++pass) {
       if (active) {
@@ -769,20 +765,15 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         const int M = __shfl_sync(GCA_FULL, incl, S64_E - 1);
         int PT = 0;
         bool more_items = M > 0;
-#ifdef S64_STATIC_ITEMS
-        int next_item = warp;
-#endif
+        // the next work item is requested one item ahead, so the shared-memory atomic's round trip overlaps
+        // with the work on the current item (lane 0 holds the ticket until it is needed)
+        int ticket = 0;
+        if (lane == 0 && more_items) ticket = atomicAdd(&cs.next, 1);
         for (;;) {
           if (PT < 32 && more_items) {
-#ifdef S64_STATIC_ITEMS
-            const int item = next_item;
-            next_item += S64_E;
-#else
-            int item = 0;
-            if (lane == 0) item = atomicAdd(&cs.next, 1);
-            item = __shfl_sync(GCA_FULL, item, 0);
-#endif
+            const int item = __shfl_sync(GCA_FULL, ticket, 0);
             if (item >= M) { more_items = false; continue; }
+            if (lane == 0) ticket = atomicAdd(&cs.next, 1);
             const int es_slot = __popc(__ballot_sync(GCA_FULL, lane < S64_E && incl <= item));
             const int chunk = item - __shfl_sync(GCA_FULL, incl - my_n, es_slot);
             EnvSmem& es = cs.env[es_slot];
@@ -834,7 +825,6 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
               if (d == 4) continue;
               if (em & (1u << d)) wp[off++] = (uint16_t)(tag | (d < 4 ? d : d - 1));
             }
-            if (lane == 31 && incl2) atomicAdd(&es.npairs, (uint32_t)incl2);
             PT += __shfl_sync(GCA_FULL, incl2, 31);
             __syncwarp();
             continue;
@@ -1021,8 +1011,8 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   if (lane == 0) {
 #ifdef S64_TRACE
     if (O.stats) {
-      O.stats[8 + 32 * (size_t)e + 20] = work / 2u;
-      O.stats[8 + 32 * (size_t)e + 21] = sm.npairs;
+      O.stats[8 + 32 * (size_t)e + 20] = work;
+      O.stats[8 + 32 * (size_t)e + 21] = 0;
       O.stats[8 + 32 * (size_t)e + 22] = (unsigned long long)trace_rows;
       O.stats[8 + 32 * (size_t)e + 23] = (unsigned long long)(clock64() - clk0);
       uint32_t smid;
@@ -1035,7 +1025,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     }
 #endif
     if (S.work != nullptr)
-      S.work[e] = (flags & GCA_FLAG_WORK_CYCLES) ? (uint32_t)(clock64() - clk0) : work + sm.npairs;
+      S.work[e] = (flags & GCA_FLAG_WORK_CYCLES) ? (uint32_t)(clock64() - clk0) : work;
     S.tick[e] = tick0 + (uint32_t)K;
     const float rew = award(tcount, fcount);
     if (!ca_only) {

@@ -64,6 +64,8 @@ for mode in ("cold", "warm", "cold", "warm"):
         for k in (3, 4):
             sel = [np.mean(v) for v in per_sm.values() if len(v) == k]
             if sel: print("   SMs with %d CTAs: %d, mean CTA cycles %.1fk" % (k, len(sel), np.mean(sel) / 1e3))
+        print("  per env: list entries/step mean %.0f max %.0f ; pairs mean %.0f max %.0f ; scanned rows mean %.1f p90 %.0f max %.0f" % (
+            feat[:, 0].mean(), feat[:, 0].max(), feat[:, 1].mean(), feat[:, 1].max(), feat[:, 2].mean(), np.percentile(feat[:, 2], 90), feat[:, 2].max()))
         # per-env fit of the env's own finish time
         Xe = np.stack([np.ones(N), feat[:, 0], feat[:, 1], feat[:, 2]], 1)
         ce, *_ = np.linalg.lstsq(Xe, feat[:, 3], rcond=None)
