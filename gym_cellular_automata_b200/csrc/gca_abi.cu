@@ -29,7 +29,7 @@ cudaError_t launch_windy_pack(int, int, int, const uint8_t*, unsigned long long*
 cudaError_t launch_windy_unpack(int, int, int, const unsigned long long*, const unsigned long long*, uint8_t*,
                                 cudaStream_t);
 cudaError_t launch_tiled_env_step(const gca_params&, const gca_state&, const int32_t*, const gca_step_out&,
-                                  const gca_inject&, uint32_t, uint8_t*, uint32_t*, int32_t*, int, cudaStream_t);
+                                  const gca_inject&, uint32_t, uint8_t*, uint32_t*, int32_t*, uint8_t*, int, cudaStream_t);
 cudaError_t launch_auto_reset(const gca_params&, const gca_state&, const gca_state&, const float*, float*,
                               const uint8_t*, cudaStream_t);
 }  // namespace gca
@@ -173,6 +173,7 @@ int gca_env_step(const gca_params* p, const gca_state* s, const int32_t* actions
     return fail(GCA_ERR_ARG, "gca_env_step: grids other than 64x64 need scratch_cell and scratch_u32");
   rc = check_cuda(gca::launch_tiled_env_step(*p, st, actions, o, j, flags, s->scratch_cell, s->scratch_u32,
                                              reinterpret_cast<int32_t*>(s->scratch_u32) + 12 * (size_t)s->N,
+                                             reinterpret_cast<uint8_t*>(s->scratch_u32 + 14 * (size_t)s->N),
                                              (flags & GCA_FLAG_NO_TMA) ? 0 : 1, (cudaStream_t)stream),
                   "env_step_tiled");
   if (rc) return rc;

@@ -11,8 +11,13 @@
 //     processed balanced over the CTA: window sum -> enclosure -> per burning direction one
 //     threefry block addressed by the GLOBAL linear index ((r W + c) 9 + d), so results do not
 //     depend on the tiling;
-//   * cells are written to the other grid buffer (neighbouring tiles still read the old one);
-//     burn-out ticks / ages are updated in place (own cell only);
+//   * only tiles that can change are worked on: a dense, vectorised pass (tile_flags_kernel, 1 byte
+//     per cell read) marks the tiles that hold fire, and a tile is ACTIVE when its 3x3 tile
+//     neighbourhood holds any (R <= 10 < the tile's extent, so nothing further away can ignite it);
+//     the CTAs of the other tiles leave at once -- for a small fire on a 4096^2 grid that is all
+//     but a handful.  Active tiles write their new cells to the scratch grid (neighbouring tiles
+//     still read the old ones) and tile_apply_kernel copies them back, so S.cell is always the
+//     current grid; burn-out ticks / ages are updated in place (own cell only);
 //   * per-env scalars (key chain, wind walk, clock, move, douse, reward, done) live in two tiny
 //     kernels around the K sub-step launches.
 // Reference lines as in gca_step64.cu.
@@ -70,6 +75,78 @@ __global__ void tiled_sched_kernel(gca_params P, gca_state S, gca_inject J, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// tile activity: flags[e][ty][tx] = the tile holds a burning cell; with want_counts the tree / fire
+// cells of the whole grid are counted on the way (the step's reward / done need them once)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) tile_flags_kernel(int H, int W, const uint8_t* __restrict__ cell,
+                                                         uint8_t* __restrict__ tile_flags, int32_t* __restrict__ counts,
+                                                         int want_counts, int all_active) {
+  const int e = blockIdx.z, r0 = blockIdx.y * T_TH, c0 = blockIdx.x * T_TW;
+  const int tid = threadIdx.x;
+  const int r = r0 + (tid >> 2), c = c0 + (tid & 3) * 16;  // 16 cells per thread
+  const uint8_t* src = cell + ((size_t)e * H + r) * W + c;
+  uint32_t fire = 0;
+  int nt = 0, nf = 0;
+  if (r < H && c < W) {
+    if ((W & 15) == 0) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {  // cell codes 0 / 1 / 2: bit 0 = tree, bit 1 = fire
+        fire |= w[k] & 0x02020202u;
+        nt += __popc(w[k] & 0x01010101u);
+        nf += __popc(w[k] & 0x02020202u);
+      }
+    } else {
+      for (int k = 0; k < 16 && c + k < W; ++k) {
+        const int v = src[k];
+        fire |= v == 2;
+        nt += v == 1;
+        nf += v == 2;
+      }
+    }
+  }
+  const int any = __syncthreads_or(fire != 0u) | all_active;
+  if (tid == 0) tile_flags[((size_t)e * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = (uint8_t)(any != 0);
+  if (want_counts) {
+    nt = __reduce_add_sync(GCA_FULL, nt);
+    nf = __reduce_add_sync(GCA_FULL, nf);
+    if ((tid & 31) == 0) {
+      if (nt) atomicAdd(&counts[2 * e], nt);
+      if (nf) atomicAdd(&counts[2 * e + 1], nf);
+    }
+  }
+}
+
+// does the 3x3 tile neighbourhood of this CTA's tile hold fire?  (uniform over the CTA)
+__device__ __forceinline__ bool tile_active(const uint8_t* __restrict__ tile_flags) {
+  const int tx = blockIdx.x, ty = blockIdx.y, TX = gridDim.x, TY = gridDim.y;
+  const uint8_t* f = tile_flags + (size_t)blockIdx.z * TY * TX;
+  bool a = false;
+  if (threadIdx.x < 9) {
+    const int y = ty + (int)threadIdx.x / 3 - 1, x = tx + (int)threadIdx.x % 3 - 1;
+    if (y >= 0 && y < TY && x >= 0 && x < TX) a = f[y * TX + x] != 0;
+  }
+  return __syncthreads_or(a) != 0;
+}
+
+// copies the new cells of the active tiles from the scratch grid back into the grid
+__global__ void __launch_bounds__(128) tile_apply_kernel(int H, int W, const uint8_t* __restrict__ tile_flags,
+                                                         const uint8_t* __restrict__ scratch, uint8_t* __restrict__ cell) {
+  if (!tile_active(tile_flags)) return;
+  const int e = blockIdx.z, r0 = blockIdx.y * T_TH, c0 = blockIdx.x * T_TW;
+  const int tid = threadIdx.x;
+  const int r = r0 + (tid >> 2), c = c0 + (tid & 3) * 16;
+  if (r >= H || c >= W) return;
+  const size_t off = ((size_t)e * H + r) * W + c;
+  if ((W & 15) == 0) {
+    *reinterpret_cast<uint4*>(cell + off) = *reinterpret_cast<const uint4*>(scratch + off);
+  } else {
+    for (int k = 0; k < 16 && c + k < W; ++k) cell[off + k] = scratch[off + k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------------------------
 struct TileSmem {
@@ -107,8 +184,9 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
                 const __grid_constant__ gca_inject J, const __grid_constant__ CUtensorMap tmap,
                 const uint8_t* __restrict__ cell_in, uint8_t* __restrict__ cell_out,
                 const uint32_t* __restrict__ sched, int32_t* __restrict__ counts, unsigned long long* stats,
-                int substep, int pitch) {
+                const uint8_t* __restrict__ tile_flags, int substep, int pitch) {
   __shared__ TileSmem sm;
+  if (!tile_active(tile_flags)) return;  // no fire within reach: nothing in this tile can change
   const int H = P.H, W = P.W, R = P.R, mode = P.rng_mode;
   const int WW = (W + 63) >> 6;
   const int e = blockIdx.z;
@@ -296,8 +374,8 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
       }
     }
     cell_out[env_off + gcell] = (uint8_t)nw;
-    nt += nw == 1;
-    nfire += nw == 2;
+    nt += (nw == 1) - (old == 1);     // change of the env's tree / fire counts (tile_flags_kernel counted
+    nfire += (nw == 2) - (old == 2);  // the grid as it was before this sub-step)
   }
   nt = __reduce_add_sync(GCA_FULL, nt);
   nfire = __reduce_add_sync(GCA_FULL, nfire);
@@ -391,36 +469,37 @@ static bool make_tmap(CUtensorMap* m, const uint8_t* base, int N, int H, int W, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Runs K sub-steps (cell ping-pong between S.cell and scratch_cell) and the epilogue.
-// scratch_cell: [N][H][W] u8; scratch_sched: [N][12] u32; scratch_counts: [N][2] i32.
+// Runs K sub-steps and the epilogue.  Per sub-step: key schedule, tile activity flags (+ cell counts in
+// the last one), the CA kernel on the active tiles (S.cell -> scratch_cell), the copy back.
+// scratch_cell: [N][H][W] u8; scratch_sched: [N][12] u32; scratch_counts: [N][2] i32;
+// tile_flags: [N][ceil(H/32)][ceil(W/64)] u8.
 cudaError_t launch_tiled_env_step(const gca_params& p, const gca_state& s, const int32_t* actions,
                                   const gca_step_out& out, const gca_inject& inj, uint32_t flags, uint8_t* scratch_cell,
-                                  uint32_t* scratch_sched, int32_t* scratch_counts, int use_tma, cudaStream_t st) {
+                                  uint32_t* scratch_sched, int32_t* scratch_counts, uint8_t* tile_flags, int use_tma,
+                                  cudaStream_t st) {
   const int N = s.N, H = p.H, W = p.W, R = p.R;
   const int pitch = T_PITCH_MAX;
   const int rows = T_TH + 2 * R;
   dim3 grid((W + T_TW - 1) / T_TW, (H + T_TH - 1) / T_TH, N);
-  uint8_t* cur = s.cell;
-  uint8_t* nxt = scratch_cell;
   cudaError_t err;
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  const bool tma = use_tma && make_tmap(&tm, s.cell, N, H, W, pitch, rows);
+  // regrowth (p_tree > 0) can change any empty cell: every tile is active then
+  const int all_active = p.p_tree > 0.0f ? 1 : 0;
   for (int j = 0; j < p.K; ++j) {
+    const int last = j == p.K - 1;
     tiled_sched_kernel<<<(N + 127) / 128, 128, 0, st>>>(p, s, inj, j, scratch_sched);
-    if ((err = cudaMemsetAsync(scratch_counts, 0, sizeof(int32_t) * 2 * N, st)) != cudaSuccess) return err;
-    CUtensorMap tm;
-    memset(&tm, 0, sizeof(tm));
-    const bool tma = use_tma && make_tmap(&tm, cur, N, H, W, pitch, rows);
+    if (last && (err = cudaMemsetAsync(scratch_counts, 0, sizeof(int32_t) * 2 * N, st)) != cudaSuccess) return err;
+    tile_flags_kernel<<<grid, 128, 0, st>>>(H, W, s.cell, tile_flags, scratch_counts, last, all_active);
     if (tma)
-      ca_tiled_kernel<true><<<grid, T_THREADS, 0, st>>>(p, s, inj, tm, cur, nxt, scratch_sched, scratch_counts,
-                                                        out.stats, j, pitch);
+      ca_tiled_kernel<true><<<grid, T_THREADS, 0, st>>>(p, s, inj, tm, s.cell, scratch_cell, scratch_sched,
+                                                        scratch_counts, out.stats, tile_flags, j, pitch);
     else
-      ca_tiled_kernel<false><<<grid, T_THREADS, 0, st>>>(p, s, inj, tm, cur, nxt, scratch_sched, scratch_counts,
-                                                         out.stats, j, pitch);
+      ca_tiled_kernel<false><<<grid, T_THREADS, 0, st>>>(p, s, inj, tm, s.cell, scratch_cell, scratch_sched,
+                                                         scratch_counts, out.stats, tile_flags, j, pitch);
+    tile_apply_kernel<<<grid, 128, 0, st>>>(H, W, tile_flags, scratch_cell, s.cell);
     if ((err = cudaGetLastError()) != cudaSuccess) return err;
-    uint8_t* t = cur; cur = nxt; nxt = t;
-  }
-  if (cur != s.cell) {
-    if ((err = cudaMemcpyAsync(s.cell, cur, (size_t)N * H * W, cudaMemcpyDeviceToDevice, st)) != cudaSuccess)
-      return err;
   }
   tiled_finish_kernel<<<(N + 127) / 128, 128, 0, st>>>(p, s, actions, out, scratch_counts, flags);
   return cudaGetLastError();

@@ -108,7 +108,8 @@ typedef struct gca_state {
   float* reward_accumulated;  /* [N] */
   /* scratch of the tiled path (grids other than 64x64); may be NULL for 64x64 */
   uint8_t* scratch_cell;      /* [N][H][W] second grid buffer (tiles read one, write the other) */
-  uint32_t* scratch_u32;      /* [N][14]: per-env sub-step key schedule (12) + tree/fire counts (2) */
+  uint32_t* scratch_u32;      /* N*14 words: per-env sub-step key schedule (12) + tree/fire counts (2), followed by
+                                 N * ceil(H/32) * ceil(W/64) bytes (rounded up to words): tile activity flags */
   /* optional load balancing of the 64x64 kernel (one warp per env, so an env step costs what its
    * fire front costs): the kernel writes work[e]; gca_balance_order turns it into order[] */
   uint32_t* work;             /* [N] cost estimate of the last env step, or NULL */
