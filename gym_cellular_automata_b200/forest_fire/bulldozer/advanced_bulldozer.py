@@ -445,7 +445,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                 self._state.rebalance()
                 self._steps_since_balance = 0
                 self.kernel_launches += 1
-        self.kernel_launches += 1 if self._state.work is not None else 5 * self.substeps + 1
+        self.kernel_launches += 1 if self._state.work is not None else 4 * self.substeps + 1
         if inject is None:
             # hot path: every struct pointer is cached; only the action pointer and the stream vary
             fa = self._fast_args
@@ -564,7 +564,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                 self._state.rebalance()
                 self._steps_since_balance = 0
                 self.kernel_launches += 1
-        self.kernel_launches += 1 if self._state.work is not None else 5 * self.substeps + 1
+        self.kernel_launches += 1 if self._state.work is not None else 4 * self.substeps + 1
         rc = ha[1](ha[2], ha[3], actions_host.data_ptr(), ha[4], ha[5], ha[6], ha[7], flags, ha[8], ha[9],
                    torch.cuda.current_stream().cuda_stream)
         if rc:
