@@ -37,7 +37,8 @@ def test_pack_unpack_roundtrip(cuda_device):
 
 
 @pytest.mark.parametrize("mode,K,hidden", [("legacy", 1, True), ("partitionable", 1, True), ("legacy", 4, True),
-                                           ("partitionable", 4, False), ("legacy", 2, False)])
+                                           ("partitionable", 4, False), ("legacy", 2, False), ("legacy", 3, True),
+                                           ("partitionable", 8, True)])
 def test_env_step_parity(cuda_device, mode, K, hidden):
     """Stream parity: in-kernel threefry, same keys/actions/hidden layers -> identical state after
     every step (grid, fire_age, dousing, wind, key chain, position, clock, reward, done)."""
@@ -511,3 +512,14 @@ def test_dense_front_multi_pass(cuda_device, mixed):
     assert nbad == 0, _fmt(reports)
     assert stats[0] - front0 > 20 * 256 * (1 if mixed else 2), "the fronts were not dense enough to need several passes"
     assert stats[3] > 0
+
+
+@pytest.mark.parametrize("N", [1, 13, 15, 29])
+def test_env_counts_around_the_cta_size(cuda_device, N):
+    """Batch sizes below, at and just past the 14 envs a CTA of the 64x64 kernel steps (warps without an env
+    still join its barriers and pooled work)."""
+    from parity_util import make_pair, lockstep
+    env, co, E, state, info = make_pair(N=N, K=4, mode="legacy", use_hidden=True, seed=23 + N, scatter_fire=0.002)
+    nbad, reports, stats = lockstep(env, co, state, 40, np.random.default_rng(N))
+    assert nbad == 0, _fmt(reports)
+    assert stats[1] > 0
