@@ -133,40 +133,74 @@ def workload_config(args):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of one GPU, sampled in a side thread while the timed loops run: NVML
+    (nvidia_ml_py, one query every 2 ms) when available, else `nvidia-smi` (one query per ~50 ms)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
-        self.index, self.samples, self._halt = index, [], threading.Event()
+        self.index, self.uuid, self._halt = index, uuid, threading.Event()
+        self.sm, self.mx, self.reasons, self.how = [], None, set(), "nvidia-smi"
+        self._nvml = self._handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                for cand in (f"GPU-{uuid}", str(uuid)):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand if isinstance(cand, bytes) else cand.encode())
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml, self._handle, self.how = pynvml, h, "nvml"
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n, h = self._nvml, self._handle
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        for name, bit in self.REASONS:
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        if len(f) >= 7:
+            self.sm.append(float(f[0]))
+            self.mx = float(f[1])
+            for (name, _), v in zip(self.REASONS, f[3:7]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.samples.append([x.strip() for x in out.strip().split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
-                pass
-            self._halt.wait(0.2)
+                if self._nvml is not None:
+                    self._nvml = None  # fall back to nvidia-smi
+            self._halt.wait(0.002 if self._nvml is not None else 0.05)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=3)
-        sm, mx, reasons = [], None, set()
-        for s in self.samples:
-            if len(s) < 7:
-                continue
-            try:
-                sm.append(float(s[0]))
-                mx = float(s[1])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.how}
 
 
 def run_ours(args):
@@ -203,7 +237,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     stats0 = env.stats()
     launches0 = env.kernel_launches
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) if rank == 0 else None
     if sampler:
         sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
