@@ -277,7 +277,10 @@ __global__ void render_rgb_kernel(gca_params P, int N, const uint8_t* __restrict
 constexpr int BAL_CHUNK = 8192;
 constexpr int BAL_WAVE = 148;
 constexpr int BAL_BUCKETS = 1024;
-__global__ void __launch_bounds__(1024) balance_order_kernel(int N, int wpc, const uint32_t* __restrict__ work, int32_t* order) {
+#ifndef GCA_BALANCE_SKEW_DEFAULT
+#define GCA_BALANCE_SKEW_DEFAULT GCA_S64_WARPS  /* measured on B200: 88.2 us (0), 85.1 (8), 83.5 (11), 83.3 (14) per step */
+#endif
+__global__ void __launch_bounds__(1024) balance_order_kernel(int N, int wpc, int skew, const uint32_t* __restrict__ work, int32_t* order) {
   extern __shared__ int keys[];            // [BAL_CHUNK] env (chunk-local) by rank
   __shared__ int hist[BAL_BUCKETS];        // bucket counts, then start offsets (descending buckets)
   __shared__ uint32_t s_max;
@@ -326,20 +329,34 @@ __global__ void __launch_bounds__(1024) balance_order_kernel(int N, int wpc, con
   }
   __syncthreads();
   // Pooled kernel (E warps = E envs per CTA, the heavy phases shared by the CTA): a CTA costs about the
-  // SUM of its envs' work, so deal the sorted envs like cards -- warp w of CTA b gets rank w*C + b,
-  // every other round in reverse (snake) -- which gives all C full CTAs nearly the same sum.
-  const int full = n / wpc;  // CTAs with all warps in range; a trailing partial CTA keeps its ranks
+  // SUM of its envs' work, so the sorted envs are dealt like cards, every other round in reverse (snake).
+  // With up to two CTAs per SM (C <= 2 G full CTAs, G = 148 SMs) the bins of the deal are the SMs: the block
+  // scheduler puts CTA b and CTA b + G on the same SM, and the warp scheduler favours the one launched
+  // first (measured: 160 k against 205 k cycles for equal work), so the first CTA of a pair takes the
+  // heaviest `skew` rounds of the bin and then every other one (skew = 0: equal sums; default: the heavier
+  // half), the second the rest.
+  // A trailing partial CTA keeps the lightest ranks.
+  const int full = n / wpc;  // CTAs with all warps in range
+  const int G = BAL_WAVE;
+  const int P = full - G;    // CTA pairs (b, b + G), b < P; CTAs P..G-1 have an SM to themselves
   for (int s = threadIdx.x; s < n; s += blockDim.x) {
     const int b = s / wpc, w = s % wpc;  // CTA slot inside the chunk, warp
     int rank = s;
     if (b < full) {
-      if (wpc > 1) {
-        rank = w * full + ((w & 1) ? (full - 1 - b) : b);
-      } else {
+      if (wpc == 1) {
         const int wave = b / BAL_WAVE, pos = b % BAL_WAVE;
         const int in_wave = min(BAL_WAVE, full - wave * BAL_WAVE);
         const int q = (wave & 1) ? (in_wave - 1 - pos) : pos;
         rank = wave * BAL_WAVE + q;
+      } else if (P <= 0 || P > G) {
+        rank = w * full + ((w & 1) ? (full - 1 - b) : b);  // one CTA per SM, or more than two waves
+      } else {
+        int bin, round;
+        if (b < P) { bin = b; round = w < skew ? w : skew + 2 * (w - skew); }
+        else if (b >= G) { bin = b - G; round = w < wpc - skew ? skew + 1 + 2 * w : wpc + w; }
+        else { bin = b; round = w; }
+        if (round < wpc) rank = round * G + ((round & 1) ? (G - 1 - bin) : bin);
+        else rank = wpc * G + (round - wpc) * P + ((round & 1) ? (P - 1 - bin) : bin);
       }
     }
     order[base + s] = base + keys[rank];
@@ -528,7 +545,13 @@ cudaError_t launch_balance_order(int N, const uint32_t* work, int32_t* order, cu
     attr_set = true;
   }
   const int chunks = (N + BAL_CHUNK - 1) / BAL_CHUNK;
-  balance_order_kernel<<<chunks, 1024, BAL_CHUNK * 4, st>>>(N, GCA_S64_WARPS, work, order);
+  // GCA_BALANCE_SKEW (0 .. envs per CTA) overrides how much heavier the first CTA of an SM is made
+  static const int skew = [] {
+    const char* v = getenv("GCA_BALANCE_SKEW");
+    const int k = v ? atoi(v) : GCA_BALANCE_SKEW_DEFAULT;
+    return k < 0 ? 0 : (k > GCA_S64_WARPS ? GCA_S64_WARPS : k);
+  }();
+  balance_order_kernel<<<chunks, 1024, BAL_CHUNK * 4, st>>>(N, GCA_S64_WARPS, skew, work, order);
   return cudaGetLastError();
 }
 cudaError_t launch_threefry_split_part(const uint32_t* key, int num, uint32_t* out, cudaStream_t st) {

@@ -61,6 +61,8 @@ for mode in ("cold", "warm", "cold", "warm"):
         ssm = np.array([np.std(v) for v in per_sm.values()])
         print("  SMs used %d, CTAs/SM min %d max %d ; per-SM mean CTA cycles: min %.1fk max %.1fk std %.1fk ; mean within-SM std %.1fk" % (
             len(per_sm), nper.min(), nper.max(), msm.min() / 1e3, msm.max() / 1e3, msm.std() / 1e3, ssm.mean() / 1e3))
+        bidx = full[:, 0, 26].astype(int)
+        print("   CTA cycles by launch order: blockIdx < 148: %.1fk ; >= 148: %.1fk" % (cyc[bidx < 148].mean() / 1e3, cyc[bidx >= 148].mean() / 1e3))
         for k in (3, 4):
             sel = [np.mean(v) for v in per_sm.values() if len(v) == k]
             if sel: print("   SMs with %d CTAs: %d, mean CTA cycles %.1fk" % (k, len(sel), np.mean(sel) / 1e3))
