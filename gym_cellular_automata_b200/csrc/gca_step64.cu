@@ -40,6 +40,7 @@ namespace {
 constexpr int S64_E = GCA_S64_WARPS;   // envs (= warps) per CTA
 constexpr int S64_CAP = 256;           // front cells per pass
 constexpr int S64_CHAIN_WARPS = (S64_E + 15) / 16;  // warps that walk the key chains (16 envs each)
+constexpr int S64_IGN_CAP = 160;       // deferred fire-age draws buffered per env (flushed early when full)
 constexpr int S64_WP = 288;            // warp-private pair buffer: < 32 carried over + <= 256 of one chunk
 constexpr uint32_t S64_HALF_BURN = 9u * 4096u / 2u;
 constexpr uint32_t S64_HALF_CELL = 4096u / 2u;
@@ -60,12 +61,14 @@ struct __align__(16) EnvSmem {
   float base[S64_CAP];              // per listed cell: upper bound of (p_h (1+p_veg)) (1+p_den); negative =
                                     //   dousing nearby, no cheap lower bound (apply: burn-out ticks)
   uint16_t list[S64_CAP];           // front cells: (row << 6) | col
+  uint16_t ignlist[S64_IGN_CAP];    // cells ignited so far in this env step: (sub-step << 12) | cell; their fire-age
+                                    //   draws are made in one batch at the end of the step (flush_ages)
   uint32_t sched[GCA_MAX_K][12];    // per sub-step: Sburn[2] Sgrow[2] ak1[2] ak2[2] wind change step pad
   uint4 hot;                        // current sub-step: Sburn k0, k1, k0^k1^C ; env index
   float wind[12];                   // current sub-step: wind matrix (9 used)
   int cnt;                          // list entries of the current pass
   uint32_t dous_even, dous_odd;     // bit l: some doused cell within 2 rows of row 2l / 2l+1
-  uint32_t pad0;
+  int nign;                         // entries on ignlist
 };
 static_assert(S64_E >= 1 && S64_E <= 32 && 28 % S64_E == 0, "envs per CTA: a divisor of 28 (28 warps of 72 registers fill an SM)");
 static_assert(sizeof(EnvSmem) % 16 == 0 && offsetof(EnvSmem, burn) % 16 == 0 && offsetof(EnvSmem, hot) % 16 == 0, "128-bit shared accesses");
@@ -428,6 +431,44 @@ __device__ __noinline__ void regrow_rows(const gca_params& P, const gca_inject& 
   }
 }
 
+// Fire ages of the n cells on sm.ignlist (ca_alexandridis_jax.py:367-370,394-398): two lanes per ignition --
+// jax.random.randint needs two independent words -- with the randint keys of the sub-step the cell ignited
+// in; the burn-out tick goes to S.death and, through a row-minimum scratch, into the owners' row minima.
+// Nothing inside the env step reads these ticks (ages are >= 144 CA updates), so all sub-steps' ignitions
+// are drawn in one batch.  `rowmin` = 64 words private to the warp.
+__device__ __noinline__ void flush_ages(const EnvSmem& sm, const gca_params& P, const gca_state& S,
+                                        const int32_t* j_age_new, int mode, int N, int e, int n, uint32_t tick0,
+                                        uint32_t* rowmin, int lane) {
+  const size_t cell_base = (size_t)e * 4096;
+  const uint32_t age_magic = 0xFFFFFFFFu / P.age_span;
+  rowmin[2 * lane] = 0xFFFFFFFFu;
+  rowmin[2 * lane + 1] = 0xFFFFFFFFu;
+  __syncwarp();
+  for (int tb = 0; tb < 2 * n; tb += 32) {
+    const int task = tb + lane, i = task >> 1;
+    const bool valid = i < n;
+    const uint32_t ent = sm.ignlist[valid ? i : 0];
+    const uint32_t cell = ent & 0xFFFu, jj = ent >> 12;
+    const uint32_t* sc = sm.sched[jj];
+    uint32_t bits = 0;
+    if (j_age_new == nullptr)
+      bits = bits_at_ni((lane & 1) ? tf_key(sc[6], sc[7]) : tf_key(sc[4], sc[5]), cell, S64_HALF_CELL, mode);
+    const uint32_t other = __shfl_xor_sync(GCA_FULL, bits, 1);
+    if (valid && !(lane & 1)) {
+      int age;
+      if (j_age_new) age = j_age_new[((size_t)jj * N + e) * 4096 + cell];
+      else {
+        const uint32_t hm = fastmod(bits, P.age_span, age_magic), lm = fastmod(other, P.age_span, age_magic);
+        age = P.age_lo + (int)fastmod(hm * P.age_mult + lm, P.age_span, age_magic);
+      }
+      const uint32_t dabs = tick0 + jj + (uint32_t)age;  // burn-out tick
+      S.death[cell_base + cell] = (uint16_t)dabs;
+      atomicMin(&rowmin[cell >> 6], dabs);
+    }
+  }
+  __syncwarp();  // the caller folds rowmin[2 lane], rowmin[2 lane + 1] into its row minima
+}
+
 __device__ __forceinline__ void front_masks(unsigned long long t0, unsigned long long t1, unsigned long long f0,
                                             unsigned long long f1, int lane, unsigned long long& fr0,
                                             unsigned long long& fr1) {
@@ -444,6 +485,14 @@ __device__ __forceinline__ void front_masks(unsigned long long t0, unsigned long
 #define S64_STAMP(k) do { if (active && lane == 0 && O.stats) O.stats[8 + 32 * (size_t)e + (k)] = (unsigned long long)(clock64() - clk0); } while (0)
 #else
 #define S64_STAMP(k) do { } while (0)
+#endif
+// S64_ACC(k): add the cycles since the last S64_ACC / S64_MARK of this warp to trace slot k
+#ifdef S64_TRACE
+#define S64_MARK() do { trace_t = clock64(); } while (0)
+#define S64_ACC(k) do { const long long now_ = clock64(); if (active && lane == 0 && O.stats) O.stats[8 + 32 * (size_t)e + (k)] += (unsigned long long)(now_ - trace_t); trace_t = now_; } while (0)
+#else
+#define S64_MARK() do { } while (0)
+#define S64_ACC(k) do { } while (0)
 #endif
 
 #ifndef S64_MINB
@@ -462,6 +511,9 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   CtaSmem& cs = *reinterpret_cast<CtaSmem*>(s64_smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long clk0 = clock64();
+#ifdef S64_TRACE
+  long long trace_t = clk0;
+#endif
   const int slot = blockIdx.x * S64_E + warp;
   const int N = S.N;
   const bool active = slot < N;   // a warp without an env still joins the barriers and the pooled work
@@ -546,6 +598,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       if (lane == 0) {
         sm.dous_even = ev | (ev << 1) | (ev >> 1) | od | (od << 1);
         sm.dous_odd = od | (od << 1) | (od >> 1) | ev | (ev >> 1);
+        sm.nign = 0;
       }
     }
     store_row_views(sm.fire32 + (2 * lane + 4) * 4, f0);
@@ -681,7 +734,6 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
 
   const float lutreg = lane < 8 ? P.onep_veg[lane] : (lane < 16 ? P.onep_den[lane - 8] : 0.0f);
   const float w1 = P.ring_w[1], w2 = P.ring_w[2], w3 = P.ring_w[3], w4 = P.ring_w[4];
-  const uint32_t age_magic = 0xFFFFFFFFu / P.age_span;
 
   // ================================ K CA sub-steps, all on-chip ===================================
   for (int j = 0; j < K; ++j) {
@@ -729,6 +781,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
           prefetch_front(sm, hidden, pslope, cell_base, 0, min(T, S64_CAP), lane);
         }
       }
+      if (j > 0) S64_ACC(29);
       if (lane == 0) sm.hot = make_uint4(sc[0], sc[1], sc[0] ^ sc[1] ^ 0x1BD11BDAu, (uint32_t)e);
       if (lane < 9) sm.wind[lane] = P.winds[(int)sc[8] * 9 + lane];
     }
@@ -855,6 +908,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       S64_STAMP(5 + 3 * j);
       const int more = __syncthreads_or(total > (pass + 1) * S64_CAP);
       S64_STAMP(6 + 3 * j);
+      S64_MARK();
       if (!more) break;
     }
 
@@ -869,58 +923,40 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       if (NI > 0) {
         sm.ign[2 * lane] = 0ull;
         sm.ign[2 * lane + 1] = 0ull;
-        const TfKey ka1 = tf_key(sc[4], sc[5]), ka2 = tf_key(sc[6], sc[7]);
-        uint32_t* dt = reinterpret_cast<uint32_t*>(sm.base);  // burn-out tick per listed ignition
-        for (int base = 0; base < NI; base += S64_CAP) {
-          {
-            int idx = incl_i - ni_l - base;
-            unsigned long long m = I0;
-            int rowbits = (2 * lane) << 6;
+        // remember the ignited cells with their sub-step; the age draws are deferred to flush_ages
+        int nign = sm.nign;
+        int taken = 0;
+        while (taken < NI) {
+          const int take = min(S64_IGN_CAP - nign, NI - taken);
+          int pos = nign + incl_i - ni_l - taken;  // list position of this lane's first ignition
+          unsigned long long m = I0;
+          uint32_t tag = ((uint32_t)j << 12) | ((uint32_t)(2 * lane) << 6);
 #pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-              while (m) {
-                const int c = __ffsll((long long)m) - 1;
-                m &= m - 1;
-                if ((unsigned)idx < (unsigned)S64_CAP) wp[idx] = (uint16_t)(rowbits | c);
-                ++idx;
-              }
-              m = I1;
-              rowbits = (2 * lane + 1) << 6;
+          for (int half = 0; half < 2; ++half) {
+            while (m) {
+              const uint32_t c = (uint32_t)__ffsll((long long)m) - 1u;
+              m &= m - 1;
+              if (pos >= nign && pos < nign + take) sm.ignlist[pos] = (uint16_t)(tag | c);
+              ++pos;
             }
+            m = I1;
+            tag += 64u;
           }
-          __syncwarp();
-          const int cnt = min(S64_CAP, NI - base);
-          // two lanes per ignition: randint needs two independent words (jax.random.randint)
-          for (int tb = 0; tb < 2 * cnt; tb += 32) {
-            const int task = tb + lane, i = task >> 1;
-            const bool valid = i < cnt;
-            const uint32_t cell = wp[valid ? i : 0];
-            uint32_t bits = 0;
-            if (j_age_new == nullptr) bits = bits_at_ni((lane & 1) ? ka2 : ka1, cell, S64_HALF_CELL, mode);
-            const uint32_t other = __shfl_xor_sync(GCA_FULL, bits, 1);
-            if (valid && !(lane & 1)) {
-              int age;
-              if (j_age_new) age = j_age_new[inj_base + cell];
-              else {
-                const uint32_t hm = fastmod(bits, P.age_span, age_magic), lm = fastmod(other, P.age_span, age_magic);
-                age = P.age_lo + (int)fastmod(hm * P.age_mult + lm, P.age_span, age_magic);
-              }
-              const uint32_t dabs = tick0 + (uint32_t)j + (uint32_t)age;  // burn-out tick
-              S.death[cell_base + cell] = (uint16_t)dabs;
-              dt[i] = dabs;
-            }
+          nign += take;
+          taken += take;
+          if (taken < NI) {  // the list is full (hundreds of ignitions in one env step): draw what it holds
+            __syncwarp();
+            flush_ages(sm, P, S, j_age_new, mode, N, e, nign, tick0, reinterpret_cast<uint32_t*>(wp), lane);
+            rm.x = min(rm.x, reinterpret_cast<const uint32_t*>(wp)[2 * lane]);
+            rm.y = min(rm.y, reinterpret_cast<const uint32_t*>(wp)[2 * lane + 1]);
+            __syncwarp();
+            nign = 0;
           }
-          __syncwarp();
-          {
-            int idx = incl_i - ni_l - base;
-            for (int q = __popcll(I0); q > 0; --q, ++idx)
-              if ((unsigned)idx < (unsigned)S64_CAP) rm.x = min(rm.x, dt[idx]);
-            for (int q = __popcll(I1); q > 0; --q, ++idx)
-              if ((unsigned)idx < (unsigned)S64_CAP) rm.y = min(rm.y, dt[idx]);
-          }
-          __syncwarp();
         }
+        __syncwarp();
+        if (lane == 0) sm.nign = nign;
       }
+      S64_ACC(27);
       unsigned long long ext0 = 0ull, ext1 = 0ull;
       if (burnrows & 1u) {
         const ulonglong2 a = reinterpret_cast<const ulonglong2*>(sm.burn[2 * lane])[0];
@@ -947,7 +983,14 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         store_row_views(sm.fire32 + (2 * lane + 5) * 4, f1);
       }
       __syncwarp();
+      S64_ACC(28);
     }
+  }
+  if (active && sm.nign > 0) {
+    __syncwarp();
+    flush_ages(sm, P, S, j_age_new, mode, N, e, sm.nign, tick0, reinterpret_cast<uint32_t*>(wp), lane);
+    rm.x = min(rm.x, reinterpret_cast<const uint32_t*>(wp)[2 * lane]);
+    rm.y = min(rm.y, reinterpret_cast<const uint32_t*>(wp)[2 * lane + 1]);
   }
   if (!active) {
     if (O.stats != nullptr) {

@@ -523,3 +523,25 @@ def test_env_counts_around_the_cta_size(cuda_device, N):
     nbad, reports, stats = lockstep(env, co, state, 40, np.random.default_rng(N))
     assert nbad == 0, _fmt(reports)
     assert stats[1] > 0
+
+
+@pytest.mark.parametrize("inject_ages", [False, True])
+def test_ignition_burst_overflows_deferred_age_list(cuda_device, inject_ages):
+    """Every draw ignites (injected u_burn = 0): hundreds of ignitions per env step, more than the 64x64 kernel
+    buffers for its end-of-step batch of fire-age draws, so the early-flush path runs (with the in-kernel
+    randint, or with injected ages)."""
+    from parity_util import make_pair, lockstep
+    N, K = 5, 4
+    env, co, E, state, info = make_pair(N=N, K=K, mode="legacy", use_hidden=True, seed=31)
+    rng = np.random.default_rng(5)
+
+    def inject(step):
+        d = {"u_burn": np.zeros((K, N, 64, 64, 9), np.float32)}
+        if inject_ages:
+            d["age_new"] = rng.integers(150, 160, (K, N, 64, 64)).astype(np.int32)
+        return d
+
+    ign0 = env.stats()[2]
+    nbad, reports, stats = lockstep(env, co, state, 8, np.random.default_rng(1), inject_fn=inject)
+    assert nbad == 0, _fmt(reports)
+    assert (stats[2] - ign0) / (8 * N) > 200, "not enough ignitions per env step to overflow the deferred list"

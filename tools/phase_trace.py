@@ -30,6 +30,7 @@ names = ["setup+publish key", "barrier+wait+convert+list", "scan", "(rm)"] + sum
 for mode in ("cold", "warm", "cold", "warm"):
     a = act()
     if mode == "cold": flush.fill_(1)
+    o.stats.zero_()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); env.step_device(a); e1.record(); torch.cuda.synchronize()
@@ -72,6 +73,8 @@ for mode in ("cold", "warm", "cold", "warm"):
         Xe = np.stack([np.ones(N), feat[:, 0], feat[:, 1], feat[:, 2]], 1)
         ce, *_ = np.linalg.lstsq(Xe, feat[:, 3], rcond=None)
         print("  per-env fit of finish time on [1, entries, pairs, rows]:", np.round(ce, 2).tolist())
+    acc = o.stats[8:].cpu().numpy().reshape(N, 32)[:, 27:30].astype(np.float64).mean(0) / K
+    print("  owner phases per sub-step (mean): ignition list + age draws %.1fk, burn-outs + state + views %.1fk, front masks + list extension %.1fk" % tuple(acc / 1e3))
     extra = tr[:, 16:20].mean(0)
     tr = tr[:, :4 + 3 * K]
     mean = tr.mean(0); mx = tr.max(0)
