@@ -532,7 +532,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   unsigned long long t0 = 0, t1 = 0, f0 = 0, f1 = 0;
   unsigned long long ch0 = 0ull, ch1 = 0ull;  // cells whose state changed during this env step
   uint2 rm = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-  uint32_t tick0 = 0, key0 = 0, key1 = 0;
+  uint32_t tick0 = 0;
   int widx = 0;
   uint32_t burnrows = 0;  // bit 0 / 1: row 2*lane / 2*lane+1 has burn-outs in this env step (sm.burn valid)
   int T = 0, L = 0;
@@ -542,11 +542,9 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
 
   ulonglong2 dz = make_ulonglong2(0ull, 0ull);
   if (active) {
-    // ---- everything the step needs from HBM up front: the key (first: the chain warp waits for it), the
+    // ---- everything the step needs from HBM up front (the key is fetched by the warp that walks the chains): the
     //      tree / fire bit-boards of the grid (1 KB per env; lane l takes rows 2l, 2l+1), doused rows,
     //      row minima, scalars --------------------------------------------------------------------------
-    key0 = S.key[2 * e];
-    key1 = S.key[2 * e + 1];
     S64_STAMP(16);
     {
       const ulonglong2* bbp = reinterpret_cast<const ulonglong2*>(S.bb + (size_t)e * 128);
@@ -575,16 +573,21 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     }
     if (lane < 16) sm.fire32[lane] = 0u; else sm.fire32[272 + lane - 16] = 0u;   // fire rows -4..-1, 64..67
     if (lane < 8) sm.dous32[lane] = 0u; else if (lane < 16) sm.dous32[264 + lane - 8] = 0u;  // rows -2,-1,64,65
-    if (lane == 0) { sm.hot.z = key0; sm.hot.w = key1; }  // for the warp that walks the CTA's key chains
     S64_STAMP(0);
   }
-  __syncthreads();
   if (warp >= S64_E - S64_CHAIN_WARPS) {
-    // ~3K dependent threefry blocks per env, for 16 envs at a time, while the grids stream in
+    // ~3K dependent threefry blocks per env, for 16 envs at a time, while the grids stream in: lane pair p
+    // fetches the key of the env in slot p itself (no barrier in front of the chain)
     const int p = (S64_E - 1 - warp) * 16 + (lane >> 1);
-    const bool pv = p < S64_E;
-    EnvSmem& ce = cs.env[pv ? p : 0];
-    key_chain_pooled(ce, P, lane, pv && !(lane & 1), ce.hot.z, ce.hot.w);
+    const int pslot = blockIdx.x * S64_E + p;
+    const bool pv = p < S64_E && pslot < N;
+    uint32_t ck0 = 0, ck1 = 0;
+    if (pv) {
+      const int pe = S.order != nullptr ? S.order[pslot] : pslot;
+      ck0 = S.key[2 * pe];
+      ck1 = S.key[2 * pe + 1];
+    }
+    key_chain_pooled(cs.env[pv ? p : 0], P, lane, pv && !(lane & 1), ck0, ck1);
   }
   if (active) {
     S64_STAMP(19);
