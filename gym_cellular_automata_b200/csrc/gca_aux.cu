@@ -278,9 +278,9 @@ constexpr int BAL_CHUNK = 8192;
 constexpr int BAL_WAVE = 148;
 constexpr int BAL_BUCKETS = 1024;
 #ifndef GCA_BALANCE_SKEW_DEFAULT
-#define GCA_BALANCE_SKEW_DEFAULT GCA_S64_WARPS  /* measured on B200: 88.2 us (0), 85.1 (8), 83.5 (11), 83.3 (14) per step */
+#define GCA_BALANCE_SKEW_DEFAULT (GCA_S64_GROUPS == 1 ? GCA_S64_WARPS : 0)  /* measured on B200: 88.2 us (0), 85.1 (8), 83.5 (11), 83.3 (14) per step */
 #endif
-__global__ void __launch_bounds__(1024) balance_order_kernel(int N, int wpc, int skew, const uint32_t* __restrict__ work, int32_t* order) {
+__global__ void __launch_bounds__(1024) balance_order_kernel(int N, int wpc, int groups, int skew, const uint32_t* __restrict__ work, int32_t* order) {
   extern __shared__ int keys[];            // [BAL_CHUNK] env (chunk-local) by rank
   __shared__ int hist[BAL_BUCKETS];        // bucket counts, then start offsets (descending buckets)
   __shared__ uint32_t s_max;
@@ -348,6 +348,12 @@ __global__ void __launch_bounds__(1024) balance_order_kernel(int N, int wpc, int
         const int in_wave = min(BAL_WAVE, full - wave * BAL_WAVE);
         const int q = (wave & 1) ? (in_wave - 1 - pos) : pos;
         rank = wave * BAL_WAVE + q;
+      } else if (groups == 2) {
+        // one CTA per SM holding two lock-step groups: the bin is the CTA, its two groups split the rounds like
+        // the two CTAs of an SM above (skew = 0: equal sums)
+        const int ge = wpc / 2, g = w / ge, wg = w % ge;
+        const int round = g == 0 ? (wg < skew ? wg : skew + 2 * (wg - skew)) : (wg < ge - skew ? skew + 1 + 2 * wg : ge + wg);
+        rank = round * full + ((round & 1) ? (full - 1 - b) : b);
       } else if (P <= 0 || P > G) {
         rank = w * full + ((w & 1) ? (full - 1 - b) : b);  // one CTA per SM, or more than two waves
       } else {
@@ -549,9 +555,10 @@ cudaError_t launch_balance_order(int N, const uint32_t* work, int32_t* order, cu
   static const int skew = [] {
     const char* v = getenv("GCA_BALANCE_SKEW");
     const int k = v ? atoi(v) : GCA_BALANCE_SKEW_DEFAULT;
-    return k < 0 ? 0 : (k > GCA_S64_WARPS ? GCA_S64_WARPS : k);
+    const int cap = GCA_S64_WARPS / GCA_S64_GROUPS;
+    return k < 0 ? 0 : (k > cap ? cap : k);
   }();
-  balance_order_kernel<<<chunks, 1024, BAL_CHUNK * 4, st>>>(N, GCA_S64_WARPS, skew, work, order);
+  balance_order_kernel<<<chunks, 1024, BAL_CHUNK * 4, st>>>(N, GCA_S64_WARPS, GCA_S64_GROUPS, skew, work, order);
   return cudaGetLastError();
 }
 cudaError_t launch_threefry_split_part(const uint32_t* key, int num, uint32_t* out, cudaStream_t st) {

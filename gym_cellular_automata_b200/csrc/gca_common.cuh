@@ -6,6 +6,9 @@
 #include "../../include/gca.h"
 
 #define GCA_FULL 0xFFFFFFFFu
+#ifndef GCA_S64_GROUPS
+#define GCA_S64_GROUPS 1  /* independent lock-step groups inside a CTA of env_step64_kernel (own named barrier each) */
+#endif
 #ifndef GCA_S64_WARPS
 #define GCA_S64_WARPS 14  /* warps (= envs) per CTA of env_step64_kernel: 2 CTAs x 14 warps x 72 registers fill an SM */
 #endif

@@ -39,6 +39,9 @@ namespace {
 
 constexpr int S64_E = GCA_S64_WARPS;   // envs (= warps) per CTA
 constexpr int S64_CAP = 256;           // front cells per pass
+constexpr int S64_G = GCA_S64_GROUPS;  // independent lock-step groups inside a CTA (own barriers, own work-item counter)
+constexpr int S64_GE = S64_E / S64_G;  // envs (= warps) per group
+static_assert(S64_E % S64_G == 0 && S64_G >= 1 && S64_G <= 4, "groups must divide the CTA");
 constexpr int S64_CHAIN_WARPS = (S64_E + 15) / 16;  // warps that walk the key chains (16 envs each)
 constexpr int S64_IGN_CAP = 160;       // deferred fire-age draws buffered per env (flushed early when full)
 constexpr int S64_WP = 288;            // warp-private pair buffer: < 32 carried over + <= 256 of one chunk
@@ -77,9 +80,22 @@ struct __align__(16) CtaSmem {
   EnvSmem env[S64_E];
   uint16_t pairs[S64_E][S64_WP];    // (env slot << 11) | (list index << 3) | direction slot (0..7, centre skipped)
   int nch[32];                      // chunks of each env in the current pass
-  int next;                         // work-item counter of the pooled phase
-  int pad[3];
+  int next[4];                      // work-item counter of the pooled phase, per group
 };
+
+// barriers of one lock-step group (named barrier 1 + group, S64_GE warps); a single group uses barrier 0
+__device__ __forceinline__ void group_sync(int group) {
+  if (S64_G == 1) { __syncthreads(); return; }
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(S64_GE * 32) : "memory");
+}
+__device__ __forceinline__ int group_sync_or(int group, bool pred) {
+  if (S64_G == 1) return __syncthreads_or(pred);
+  int r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %3, 0;\n\tbar.red.or.pred q, %1, %2, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+      : "=r"(r) : "r"(group + 1), "r"(S64_GE * 32), "r"((uint32_t)pred) : "memory");
+  return r;
+}
 
 __device__ __forceinline__ void prefetch_l1(const void* p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
@@ -496,7 +512,7 @@ __device__ __forceinline__ void front_masks(unsigned long long t0, unsigned long
 #endif
 
 #ifndef S64_MINB
-#define S64_MINB (28 / S64_E)  // 28 warps/SM x 72 registers = the whole register file; 4096 envs = one wave of 148 x 28
+#define S64_MINB (28 / S64_E > 0 ? 28 / S64_E : 1)  // 28 warps/SM x 72 registers = the whole register file; 4096 envs = one wave of 148 x 28
 #endif
 // MODE: GCA_RNG_* or -1 (read P.rng_mode); HP: 0 = no hidden layers, 1 = hidden + slope table present,
 // -1 = test the pointers at run time; INJ: injected random fields may be present.  The launcher picks
@@ -514,6 +530,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
 #ifdef S64_TRACE
   long long trace_t = clk0;
 #endif
+  const int group = warp / S64_GE, gwarp = warp % S64_GE;  // lock-step group of this warp, index inside it
   const int slot = blockIdx.x * S64_E + warp;
   const int N = S.N;
   const bool active = slot < N;   // a warp without an env still joins the barriers and the pooled work
@@ -805,33 +822,34 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         const int cnt = max(0, min(S64_CAP, total - pass * S64_CAP));
         sm.cnt = cnt;
         cs.nch[warp] = (cnt + 31) >> 5;
-        if (warp == 0) cs.next = 0;
+        if (gwarp == 0) cs.next[group] = 0;
       }
-      __syncthreads();
+      group_sync(group);
 
       // ---------------- pooled phase: work items = 32-entry chunks of every env's front list -------
       {
-        const int my_n = lane < S64_E ? cs.nch[lane] : 0;
+        const int my_n = lane < S64_GE ? cs.nch[group * S64_GE + lane] : 0;
         int incl = my_n;
 #pragma unroll
-        for (int d = 1; d < S64_E; d <<= 1) {
+        for (int d = 1; d < S64_GE; d <<= 1) {
           const int o = __shfl_up_sync(GCA_FULL, incl, d);
           if (lane >= d) incl += o;
         }
-        const int M = __shfl_sync(GCA_FULL, incl, S64_E - 1);
+        const int M = __shfl_sync(GCA_FULL, incl, S64_GE - 1);
         int PT = 0;
         bool more_items = M > 0;
         // the next work item is requested one item ahead, so the shared-memory atomic's round trip overlaps
         // with the work on the current item (lane 0 holds the ticket until it is needed)
         int ticket = 0;
-        if (lane == 0 && more_items) ticket = atomicAdd(&cs.next, 1);
+        if (lane == 0 && more_items) ticket = atomicAdd(&cs.next[group], 1);
         for (;;) {
           if (PT < 32 && more_items) {
             const int item = __shfl_sync(GCA_FULL, ticket, 0);
             if (item >= M) { more_items = false; continue; }
-            if (lane == 0) ticket = atomicAdd(&cs.next, 1);
-            const int es_slot = __popc(__ballot_sync(GCA_FULL, lane < S64_E && incl <= item));
-            const int chunk = item - __shfl_sync(GCA_FULL, incl - my_n, es_slot);
+            if (lane == 0) ticket = atomicAdd(&cs.next[group], 1);
+            const int gslot = __popc(__ballot_sync(GCA_FULL, lane < S64_GE && incl <= item));
+            const int chunk = item - __shfl_sync(GCA_FULL, incl - my_n, gslot);
+            const int es_slot = group * S64_GE + gslot;
             EnvSmem& es = cs.env[es_slot];
             const int t = chunk * 32 + lane;
             const bool inrange = t < es.cnt;
@@ -909,7 +927,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         }
       }
       S64_STAMP(5 + 3 * j);
-      const int more = __syncthreads_or(total > (pass + 1) * S64_CAP);
+      const int more = group_sync_or(group, total > (pass + 1) * S64_CAP);
       S64_STAMP(6 + 3 * j);
       S64_MARK();
       if (!more) break;

@@ -62,6 +62,9 @@ for mode in ("cold", "warm", "cold", "warm"):
         ssm = np.array([np.std(v) for v in per_sm.values()])
         print("  SMs used %d, CTAs/SM min %d max %d ; per-SM mean CTA cycles: min %.1fk max %.1fk std %.1fk ; mean within-SM std %.1fk" % (
             len(per_sm), nper.min(), nper.max(), msm.min() / 1e3, msm.max() / 1e3, msm.std() / 1e3, ssm.mean() / 1e3))
+        if E == 28:
+            fin = full[:, :, 23]
+            print("   finish cycles by lock-step group: warps 0-13: %.1fk ; warps 14-27: %.1fk" % (fin[:, :14].max(1).mean() / 1e3, fin[:, 14:].max(1).mean() / 1e3))
         bidx = full[:, 0, 26].astype(int)
         print("   CTA cycles by launch order: blockIdx < 148: %.1fk ; >= 148: %.1fk" % (cyc[bidx < 148].mean() / 1e3, cyc[bidx >= 148].mean() / 1e3))
         for k in (3, 4):
