@@ -165,7 +165,4 @@ namespace gca {
 cudaError_t launch_env_step64(const gca_params& p, const gca_state& s, const int32_t* actions,
                               const gca_step_out& out, const gca_inject& inj, const gca_state& snap,
                               const float* snap_reward, uint32_t flags, cudaStream_t st);
-cudaError_t launch_ca_tiled(const gca_params& p, const gca_state& s, const gca_step_out& out,
-                            const gca_inject& inj, uint32_t flags, int substep, uint8_t* cell_out,
-                            uint32_t* sched, cudaStream_t st);
 }  // namespace gca
