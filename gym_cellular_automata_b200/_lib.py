@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 # GCA_LIB_PATH selects another build of the same sources (A/B measurements of kernel variants)
 LIB_PATH = os.environ.get("GCA_LIB_PATH") or os.path.join(_HERE, "libgca.so")
-SOURCES = ("gca_step64.cu", "gca_tiled.cu", "gca_windy.cu", "gca_aux.cu", "gca_abi.cu")
+SOURCES = ("gca_step64.cu", "gca_hidden.cu", "gca_tiled.cu", "gca_windy.cu", "gca_aux.cu", "gca_abi.cu")
 HEADERS = ("gca_common.cuh", os.path.join("..", "..", "include", "gca.h"))
 
 GCA_MAX_R = 10
@@ -138,6 +138,7 @@ def load():
     lib.gca_pack_state.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState)] + [C.c_void_p] * 8
     lib.gca_unpack_state.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState)] + [C.c_void_p] * 4
     lib.gca_balance_order.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gca_generate_hidden.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32] + [C.c_void_p] * 7
     lib.gca_episode_stats_update.argtypes = [C.c_int32, C.POINTER(GcaEpisodeStats)] + [C.c_void_p] * 6
     lib.gca_windy_env_step.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7 + [C.c_int32, C.c_double,
                                       C.c_double, C.c_double] + [C.c_void_p] * 5
@@ -152,7 +153,7 @@ def load():
 # every symbol include/gca.h declares (tests check the library exports all of them)
 EXPORTS = ("gca_version", "gca_last_error", "gca_params_init", "gca_env_step", "gca_env_step_host", "gca_alexandridis_step",
            "gca_move_modify", "gca_reward_done", "gca_conditional_reset", "gca_render_rgb", "gca_pack_state",
-           "gca_unpack_state", "gca_balance_order", "gca_episode_stats_update", "gca_windy_env_step", "gca_windy_pack", "gca_windy_unpack",
+           "gca_unpack_state", "gca_balance_order", "gca_generate_hidden", "gca_episode_stats_update", "gca_windy_env_step", "gca_windy_pack", "gca_windy_unpack",
            "gca_threefry_bits", "gca_threefry_split")
 
 

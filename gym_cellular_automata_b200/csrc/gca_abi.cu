@@ -20,6 +20,8 @@ cudaError_t launch_render(const gca_params&, int, const uint8_t*, const uint64_t
 cudaError_t launch_threefry_bits(const uint32_t*, long long, int, uint32_t*, cudaStream_t);
 cudaError_t launch_threefry_split_part(const uint32_t*, int, uint32_t*, cudaStream_t);
 cudaError_t launch_balance_order(int, const uint32_t*, int32_t*, cudaStream_t);
+cudaError_t launch_generate_hidden(int, int, int, unsigned long long, int, int32_t*, int32_t*, float*, double*, float*,
+                                   float*, cudaStream_t);
 cudaError_t launch_episode_stats(int, const gca_episode_stats&, const float*, const uint8_t*, const uint8_t*,
                                  const uint8_t*, const int32_t*, cudaStream_t);
 cudaError_t launch_windy_step(int, int, int, unsigned long long*, unsigned long long*, int32_t*, double*, const int32_t*,
@@ -272,6 +274,17 @@ int gca_unpack_state(const gca_params* p, const gca_state* s, float* true_grid, 
   if (rc) return rc;
   return check_cuda(gca::launch_unpack(*p, *s, true_grid, fire_age, dousing_count, (cudaStream_t)stream),
                     "unpack_state");
+}
+
+int gca_generate_hidden(int32_t N, int32_t H, int32_t W, uint64_t seed, int32_t env_offset, int32_t* vegetation,
+                        int32_t* density, float* altitude, double* altitude_f64, float* slope9, float* pslope9,
+                        void* stream) {
+  if (N <= 0 || !vegetation || !density || !altitude || !altitude_f64 || !pslope9)
+    return fail(GCA_ERR_ARG, "gca_generate_hidden: null argument");
+  if (H < 16 || W < 16 || (long long)H * W > 0x7FFFFFFFll || env_offset < 0)
+    return fail(GCA_ERR_UNSUPPORTED, "gca_generate_hidden: grids from 16 x 16 up to 2^31 cells, env_offset >= 0");
+  return check_cuda(gca::launch_generate_hidden(N, H, W, (unsigned long long)seed, env_offset, vegetation, density, altitude,
+                                                altitude_f64, slope9, pslope9, (cudaStream_t)stream), "generate_hidden");
 }
 
 int gca_episode_stats_update(int32_t N, const gca_episode_stats* st, const float* step_reward,

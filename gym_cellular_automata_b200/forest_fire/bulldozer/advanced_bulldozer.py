@@ -160,7 +160,13 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         winds = get_winds(use_hidden)
         self._winds = winds.astype(np.float32)
         N = self.num_envs
-        if use_hidden and hidden == "reference":
+        self._pslope_dev = None
+        if use_hidden and hidden == "device":
+            # layers generated on the GPU (gca_generate_hidden): same layer models, counter-based random numbers that
+            # depend only on (seed, global env index); everything stays a device tensor
+            density, vegetation, altitude, self._slope, self._pslope_dev = self._generate_hidden_device(
+                nrows, ncols, N, int(seed or 0), int(env_offset))
+        elif use_hidden and hidden == "reference":
             density = init_density(nrows, ncols, N, self._host_rng)
             vegetation = init_vegetation(nrows, ncols, N, self._host_rng)
             altitude = init_altitude(nrows, ncols, N, self._host_rng)
@@ -172,10 +178,13 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
             density = init_density_same(nrows, ncols, N)
             vegetation = init_vegetation_same(nrows, ncols, N)
             altitude = init_altitude_same(nrows, ncols, N)
-        self._density = np.asarray(density).astype(np.int32)
-        self._vegitation = np.asarray(vegetation).astype(np.int32)
-        self._altitude = np.asarray(altitude).astype(np.float32)
-        self._slope = get_slope(np.asarray(altitude, dtype=np.float64)).astype(np.float32) if use_hidden else None
+        if self._pslope_dev is None:
+            self._density = np.asarray(density).astype(np.int32)
+            self._vegitation = np.asarray(vegetation).astype(np.int32)
+            self._altitude = np.asarray(altitude).astype(np.float32)
+            self._slope = get_slope(np.asarray(altitude, dtype=np.float64)).astype(np.float32) if use_hidden else None
+        else:
+            self._density, self._vegitation, self._altitude = density, vegetation, altitude
 
         self._params = make_params(nrows, ncols, self.substeps, speed_move, speed_act, t_any, t_move, t_shoot,
                                    self._p_tree, self._p_wind_change, rng_mode, self._winds[:, 0])
@@ -313,6 +322,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
             "vegetation": self._vegitation,
             "altitude": self._altitude,
             "slope": self._slope if self._slope is not None else np.zeros((N, H, W, 3, 3), dtype=np.float32),
+            **({"pslope": self._pslope_dev} if self._pslope_dev is not None else {}),
             "fire_age": fire_age,
             "key": keys,
             "is_night": np.zeros(N, dtype=np.int32),
@@ -324,6 +334,18 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                   "p_wind_change": np.float32(self._p_wind_change), "day_length": 400}
         return {"per_env_context": per_env, "shared_context": shared,
                 "position": np.array(self._pos_bull, dtype=np.int32), "time": np.zeros(N, dtype=np.float32)}
+
+    def _generate_hidden_device(self, H, W, N, seed, env_offset):
+        d = self.device
+        veg = torch.empty((N, H, W), dtype=torch.int32, device=d)
+        den = torch.empty((N, H, W), dtype=torch.int32, device=d)
+        alt = torch.empty((N, H, W), dtype=torch.float32, device=d)
+        alt64 = torch.empty((N, H, W), dtype=torch.float64, device=d)
+        slope = torch.empty((N, H, W, 3, 3), dtype=torch.float32, device=d)
+        pslope = torch.empty((N, H, W, 3, 3), dtype=torch.float32, device=d)
+        check(load().gca_generate_hidden(N, H, W, seed, env_offset, ptr(veg), ptr(den), ptr(alt), ptr(alt64), ptr(slope),
+                                         ptr(pslope), current_stream()), "gca_generate_hidden")
+        return den, veg, alt, slope, pslope
 
     def _ensure_initial(self):
         if self._init_grid5 is None:
@@ -343,7 +365,10 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
             self._state = PackedState(N, H, W, self.device, use_hidden=self.use_hidden)
         ctx = dict(per_env_context)
         if self.use_hidden and "pslope" not in ctx and "slope" not in ctx:
-            ctx["slope"] = self._slope
+            if self._pslope_dev is not None:
+                ctx["pslope"] = self._pslope_dev
+            else:
+                ctx["slope"] = self._slope
         self._state.tick.zero_()  # ages are stored as burn-out ticks relative to tick 0
         self._state.pack_from_reference(self._params, ctx, position, time)
         if info is not None:

@@ -20,6 +20,7 @@
  *                          + apply_blur/apply_extensions               forest_fire/bulldozer/utils/extension_utils.py:99-195
  *   gca_pack_state / gca_unpack_state   the float32/int32 context pytree of _initial_context_distribution
  *                                                                       forest_fire/bulldozer/advanced_bulldozer.py:690-743
+ *   gca_generate_hidden    init_vegetation / init_density / init_altitude / get_slope   forest_fire/bulldozer/utils/init_utils.py:10-116,166-200
  *   gca_episode_stats_update  step_env_wrapped's statistics         agents/jax_ppo.py:504-655
  *   gca_threefry_bits / gca_threefry_split   jax.random.bits / split (third-party jax, unpinned; see oracle/prng.py)
  */
@@ -208,6 +209,17 @@ int gca_unpack_state(const gca_params* p, const gca_state* s, float* true_grid, 
  * light envs: sort by work[] (descending) and distribute round-robin over waves of 148 CTAs in
  * alternating direction.  order and work are [N] device arrays; call it every few steps. */
 int gca_balance_order(int32_t N, const uint32_t* work, int32_t* order, void* stream);
+
+/* ---- device-side generation of the hidden layers (inputs of the path) ------------------------------------
+ * vegetation / density [N][H][W] i32 (random rectangles of type 1..5 over a 1..3 background), altitude [N][H][W]
+ * f32 (noise + cosine hills + ramps, / 10), slope9 [N][H][W][3][3] f32 (degrees, centre 0, border cells flat;
+ * may be NULL) and pslope9 = exp(f32(0.078) * slope) in the same layout -- the layer models of
+ * forest_fire/bulldozer/utils/init_utils.py:10-116,166-200 and ca_alexandridis_jax.py:199-200, drawn from a
+ * counter-based generator: env e of the call gets the layers of global env (env_offset + e) under `seed`,
+ * whatever the batch size or sharding.  altitude_f64 is scratch, [N][H][W] doubles.  H, W >= 16. */
+int gca_generate_hidden(int32_t N, int32_t H, int32_t W, uint64_t seed, int32_t env_offset, int32_t* vegetation,
+                        int32_t* density, float* altitude, double* altitude_f64, float* slope9, float* pslope9,
+                        void* stream);
 
 /* ---- rollout-side episode statistics (the caller of the hot path) ----------------------------------------
  * One call = the statistics part of step_env_wrapped (agents/jax_ppo.py:504-655) for all N envs, to be

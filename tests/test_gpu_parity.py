@@ -545,3 +545,75 @@ def test_ignition_burst_overflows_deferred_age_list(cuda_device, inject_ages):
     nbad, reports, stats = lockstep(env, co, state, 8, np.random.default_rng(1), inject_fn=inject)
     assert nbad == 0, _fmt(reports)
     assert (stats[2] - ign0) / (8 * N) > 200, "not enough ignitions per env step to overflow the deferred list"
+
+
+# ---------------------------------------------------------------------------------------------
+# device-side hidden-layer generation (init_utils.py:10-116,166-200)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H,W", [(64, 64), (32, 80), (256, 256)])
+def test_generate_hidden_matches_numpy_mirror(cuda_device, H, W):
+    """gca_generate_hidden against oracle/hidden_device.py: vegetation / density bit for bit, altitude to 1e-12,
+    slope and slope factor to float32 rounding; and an env's layers do not depend on batch size or offset."""
+    from gym_cellular_automata_b200._lib import check, current_stream, load, ptr
+    from gym_cellular_automata_b200.forest_fire.bulldozer.utils.init_utils import p_slope_table
+    from oracle import hidden_device as hd
+    seed, N, off = 0xABCDEF0123, 5, 3
+
+    def gen(n, offset):
+        t = dict(veg=torch.empty((n, H, W), dtype=torch.int32, device=cuda_device),
+                 den=torch.empty((n, H, W), dtype=torch.int32, device=cuda_device),
+                 alt=torch.empty((n, H, W), dtype=torch.float32, device=cuda_device),
+                 alt64=torch.empty((n, H, W), dtype=torch.float64, device=cuda_device),
+                 slope=torch.empty((n, H, W, 3, 3), dtype=torch.float32, device=cuda_device),
+                 pslope=torch.empty((n, H, W, 3, 3), dtype=torch.float32, device=cuda_device))
+        check(load().gca_generate_hidden(n, H, W, seed, offset, ptr(t["veg"]), ptr(t["den"]), ptr(t["alt"]), ptr(t["alt64"]),
+                                         ptr(t["slope"]), ptr(t["pslope"]), current_stream()), "gca_generate_hidden")
+        return {k: v.cpu().numpy() for k, v in t.items()}
+
+    g = gen(N, off)
+    for e in (0, N - 1):
+        assert np.array_equal(g["veg"][e], hd.patches(H, W, seed, off + e, hd.VEG_RECT, hd.VEG_FILL))
+        assert np.array_equal(g["den"][e], hd.patches(H, W, seed, off + e, hd.DEN_RECT, hd.DEN_FILL))
+        alt = hd.altitude(H, W, seed, off + e)
+        assert np.allclose(g["alt64"][e], alt, rtol=0, atol=1e-12)
+        assert np.array_equal(g["alt"][e], g["alt64"][e].astype(np.float32))
+        s = hd.slope(g["alt64"][e])
+        assert np.allclose(g["slope"][e], s, rtol=3e-7, atol=1e-6)
+        assert np.allclose(g["pslope"][e], p_slope_table(g["slope"][e]), rtol=3e-7, atol=0)
+    one = gen(1, off + 2)
+    for k in ("veg", "den", "alt64", "slope", "pslope"):
+        assert np.array_equal(one[k][0], g[k][2]), k
+
+
+def test_env_with_device_generated_layers(cuda_device):
+    """hidden="device": the env steps on layers it generated on the GPU, and the oracle -- fed the very same
+    layers and slope-factor table, read back from the device -- stays bit-exact."""
+    from oracle import alexandridis as ax
+    from oracle import init_state as oinit
+    from oracle import prng
+    from oracle.c_oracle import COracle
+    from parity_util import lockstep, sync
+    N, K = 6, 4
+    env = AdvancedForestFireBulldozerEnv_(64, 64, key=1, num_envs=N, speed_move=0.48, speed_act=0.12, use_hidden=True,
+                                          substeps=K, rng_mode="legacy", seed=5, hidden="device", obs_mode="none",
+                                          collect_stats=True)
+    state, info = oinit.initial_state(64, 64, N, seed=5, jax_seed=1, use_hidden=True, mode=prng.LEGACY, hidden="random")
+    ctx = state["per_env_context"]
+    ctx["vegetation"] = env._vegitation.cpu().numpy()
+    ctx["density"] = env._density.cpu().numpy()
+    ctx["altitude"] = env._altitude.cpu().numpy()
+    ctx["slope"] = env._slope.cpu().numpy()
+    ctx["pslope"] = env._pslope_dev.cpu().numpy()
+    E = ax.EnvConstants(64, 64, speed_move=0.48, speed_act=0.12)
+    winds = oinit.get_winds()
+    state["shared_context"] = E.shared_context(winds)
+    co = COracle(E, winds, K=K, mode=prng.LEGACY)
+    sync(env, state, as_snapshot=True)
+    nbad, reports, stats = lockstep(env, co, state, 40, np.random.default_rng(2))
+    assert nbad == 0, _fmt(reports)
+    assert stats[1] > 0
+
+
+def AdvancedForestFireBulldozerEnv_(*a, **k):
+    from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv
+    return AdvancedForestFireBulldozerEnv(*a, **k)

@@ -347,3 +347,27 @@ def test_rollout_stats_ring_buffer_semantics():
     assert np.array_equal(out2["recent_returns"], out["recent_returns"]) and int(out2["recent_idx"]) == int(out["recent_idx"])
     assert np.all(out2["episode_returns"] == 1) and np.all(out2["episode_lengths"] == 1)
     assert np.all(out2["current_night_steps"] == 1) and np.all(out2["current_night_correct"] == 0)
+
+
+# ---- device-side hidden-layer generator: the NumPy mirror keeps the reference's layer models ------------------
+def test_hidden_device_mirror_layer_models():
+    """oracle/hidden_device.py (what gca_generate_hidden is checked against): value ranges and structure of
+    init_utils.py:10-116, and its slope equals the package's get_slope on the same altitude."""
+    from oracle import hidden_device as hd
+    from gym_cellular_automata_b200.forest_fire.bulldozer.utils.init_utils import get_slope
+    H, W, seed = 64, 48, 0x1234567890AB
+    for env in (0, 5, 70000):
+        veg = hd.patches(H, W, seed, env, hd.VEG_RECT, hd.VEG_FILL)
+        den = hd.patches(H, W, seed, env, hd.DEN_RECT, hd.DEN_FILL)
+        assert veg.min() >= 1 and veg.max() <= 5 and den.min() >= 1 and den.max() <= 5
+        assert not np.array_equal(veg, den)
+        # types 4 and 5 only come from rectangles: they form at most 7 axis-aligned blocks, so few rows change
+        assert (veg >= 4).sum() == 0 or np.unique(np.nonzero(veg >= 4)[0]).size <= H
+        alt = hd.altitude(H, W, seed, env)
+        assert alt.min() >= 0.0 and alt.max() <= (5 + 9 * 6 + 7 * 4) / 10
+        s = hd.slope(alt)
+        assert np.array_equal(s, get_slope(alt[None])[0].astype(np.float32))
+        assert not s[0].any() and not s[-1].any() and not s[:, 0].any() and not s[:, -1].any() and not s[:, :, 1, 1].any()
+    # an env's layers depend on (seed, env) only
+    assert np.array_equal(hd.patches(H, W, seed, 5, 1, 2), hd.patches(H, W, seed, 5, 1, 2))
+    assert not np.array_equal(hd.patches(H, W, seed, 5, 1, 2), hd.patches(H, W, seed + 1, 5, 1, 2))
