@@ -252,3 +252,23 @@ def test_env_sharding_and_stats_allgather_gloo():
             assert g["episode_returns"][e] == -1.0 * (e + 1) and g["episode_lengths"][e] == 1
         else:
             assert g["episode_returns"][e] == -4.0 * (e + 1) and g["returned_episode_lengths"][e] == 0
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exactly one JSON line on stdout
+    with the keys of the bench contract, honouring --steps / --warmup, and no GPU needed."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1", "--cpu-envs", "4"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1
+    assert d["metric"] == "cell_updates_per_s" and d["unit"] == "cell-updates/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"]
