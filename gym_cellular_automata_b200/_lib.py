@@ -21,7 +21,8 @@ HEADERS = ("gca_common.cuh", os.path.join("..", "..", "include", "gca.h"))
 GCA_MAX_R = 10
 GCA_MAX_K = 8
 RNG_LEGACY, RNG_PARTITIONABLE = 0, 1
-FLAG_AUTO_RESET, FLAG_NO_HIDDEN, FLAG_CA_ONLY, FLAG_NO_TMA, FLAG_WORK_CYCLES = 1, 2, 4, 8, 16
+FLAG_AUTO_RESET, FLAG_NO_HIDDEN, FLAG_CA_ONLY, FLAG_NO_TMA, FLAG_WORK_CYCLES, FLAG_HOST_COPY = 1, 2, 4, 8, 16, 96
+FLAG_HOST_COPY_IN, FLAG_HOST_COPY_OUT = 32, 64
 
 
 class GcaError(RuntimeError):
@@ -57,7 +58,8 @@ class GcaState(C.Structure):
 
 class GcaStepOut(C.Structure):
     _fields_ = [("reward", C.c_void_p), ("step_reward", C.c_void_p), ("terminated", C.c_void_p),
-                ("counts", C.c_void_p), ("obs_night", C.c_void_p), ("stats", C.c_void_p)]
+                ("counts", C.c_void_p), ("obs_night", C.c_void_p), ("stats", C.c_void_p),
+                ("host_reward", C.c_void_p), ("host_terminated", C.c_void_p)]
 
 
 _EPISODE_FIELDS = ("episode_returns", "episode_lengths", "returned_episode_returns", "returned_episode_lengths",

@@ -187,6 +187,25 @@ int gca_env_step(const gca_params* p, const gca_state* s, const int32_t* actions
   return GCA_OK;
 }
 
+// Device-visible alias of [host, host + bytes) when that range is pinned host memory mapped into the device's
+// address space (cudaHostAlloc / cudaHostRegister under unified addressing); false for pageable memory.
+static bool mapped_device_pointer(const void* host, size_t bytes, void** dev) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return false;
+  cudaPointerAttributes b;  // the last byte must belong to a pinned range as well
+  if (cudaPointerGetAttributes(&b, static_cast<const char*>(host) + bytes - 1) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (b.type != cudaMemoryTypeHost || b.devicePointer == nullptr) return false;
+  *dev = a.devicePointer;
+  return true;
+}
+
 int gca_env_step_host(const gca_params* p, const gca_state* s, const int32_t* host_actions, int32_t* dev_actions,
                       const gca_step_out* out, const gca_state* snapshot, const float* snapshot_reward, uint32_t flags,
                       float* host_reward, uint8_t* host_terminated, void* stream) {
@@ -195,24 +214,43 @@ int gca_env_step_host(const gca_params* p, const gca_state* s, const int32_t* ho
     return fail(GCA_ERR_ARG, "gca_env_step_host: null argument (out->reward and out->terminated are required)");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t N = (size_t)s->N;
-  int rc = check_cuda(cudaMemcpyAsync(dev_actions, host_actions, N * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st),
-                      "env_step_host: actions H2D");
+  // transport per direction: the kernel itself over the bus (pinned, device-visible buffers; 64x64 kernel), else
+  // the copy engine
+  void *da = nullptr, *dr = nullptr, *dt = nullptr;
+  const bool in_mapped = !(flags & GCA_FLAG_HOST_COPY_IN) && is64(p) &&
+                         mapped_device_pointer(host_actions, N * 3 * sizeof(int32_t), &da);
+  const bool out_mapped = !(flags & GCA_FLAG_HOST_COPY_OUT) && is64(p) &&
+                          mapped_device_pointer(host_reward, N * sizeof(float), &dr) &&
+                          mapped_device_pointer(host_terminated, N, &dt);
+  int rc;
+  if (!in_mapped) {
+    rc = check_cuda(cudaMemcpyAsync(dev_actions, host_actions, N * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st),
+                    "env_step_host: actions H2D");
+    if (rc) return rc;
+  }
+  gca_step_out o = *out;
+  if (out_mapped) {
+    o.host_reward = static_cast<float*>(dr);
+    o.host_terminated = static_cast<uint8_t*>(dt);
+  }
+  rc = gca_env_step(p, s, in_mapped ? static_cast<const int32_t*>(da) : dev_actions, &o, nullptr, snapshot,
+                    snapshot_reward, flags, stream);
   if (rc) return rc;
-  rc = gca_env_step(p, s, dev_actions, out, nullptr, snapshot, snapshot_reward, flags, stream);
-  if (rc) return rc;
-  const bool adjacent = out->terminated == reinterpret_cast<const uint8_t*>(out->reward + N) &&
-                        host_terminated == reinterpret_cast<const uint8_t*>(host_reward + N);
-  if (adjacent) {  // [N] f32 + [N] u8 laid out back to back on both sides: one copy
-    rc = check_cuda(cudaMemcpyAsync(host_reward, out->reward, N * 5, cudaMemcpyDeviceToHost, st),
-                    "env_step_host: reward + terminated D2H");
-    if (rc) return rc;
-  } else {
-    rc = check_cuda(cudaMemcpyAsync(host_reward, out->reward, N * sizeof(float), cudaMemcpyDeviceToHost, st),
-                    "env_step_host: reward D2H");
-    if (rc) return rc;
-    rc = check_cuda(cudaMemcpyAsync(host_terminated, out->terminated, N, cudaMemcpyDeviceToHost, st),
-                    "env_step_host: terminated D2H");
-    if (rc) return rc;
+  if (!out_mapped) {
+    const bool adjacent = out->terminated == reinterpret_cast<const uint8_t*>(out->reward + N) &&
+                          host_terminated == reinterpret_cast<const uint8_t*>(host_reward + N);
+    if (adjacent) {  // [N] f32 + [N] u8 laid out back to back on both sides: one copy
+      rc = check_cuda(cudaMemcpyAsync(host_reward, out->reward, N * 5, cudaMemcpyDeviceToHost, st),
+                      "env_step_host: reward + terminated D2H");
+      if (rc) return rc;
+    } else {
+      rc = check_cuda(cudaMemcpyAsync(host_reward, out->reward, N * sizeof(float), cudaMemcpyDeviceToHost, st),
+                      "env_step_host: reward D2H");
+      if (rc) return rc;
+      rc = check_cuda(cudaMemcpyAsync(host_terminated, out->terminated, N, cudaMemcpyDeviceToHost, st),
+                      "env_step_host: terminated D2H");
+      if (rc) return rc;
+    }
   }
   return check_cuda(cudaStreamSynchronize(st), "env_step_host: synchronize");
 }

@@ -575,9 +575,15 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     widx = S.wind_index[e];
     if (!(flags & GCA_FLAG_CA_ONLY)) {
       // the per-env scalars of the epilogue (lane 0, serial): get their lines on the way now
+      // the action triple goes to the three spare words behind the wind matrix with asynchronous copies: when
+      // `actions` is mapped host memory (gca_env_step_host, zero-copy) the bus round trip hides behind the step
+      if (lane < 3) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.wind[9 + lane]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(actions + 3 * (size_t)e + lane) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
       const void* pf = nullptr;
       switch (lane) {
-        case 0: pf = actions + 3 * e; break;
         case 1: pf = S.time + e; break;
         case 2: pf = S.position + 2 * e; break;
         case 3: pf = S.time_step + e; break;
@@ -1072,6 +1078,10 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   // ---- per-env scalars: clock, move, douse, day/night, reward, done (key / wind were stored above) --
   const bool ca_only = (flags & GCA_FLAG_CA_ONLY) != 0;
   const bool done = fcount == 0;
+  if (!ca_only) {
+    asm volatile("cp.async.wait_all;" ::: "memory");   // the action words (lanes 0..2 copied them)
+    __syncwarp();
+  }
   if (lane == 0) {
 #ifdef S64_TRACE
     if (O.stats) {
@@ -1094,7 +1104,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     const float rew = award(tcount, fcount);
     if (!ca_only) {
       // all loads first (they may alias the stores below as far as the compiler knows)
-      const int a0 = actions[3 * e], a1 = actions[3 * e + 1];
+      const int a0 = __float_as_int(sm.wind[9]), a1 = __float_as_int(sm.wind[10]);
       const float t_old = S.time[e];
       int row = S.position[2 * e], col = S.position[2 * e + 1];
       const int ts = S.time_step[e] + 1;
@@ -1121,8 +1131,12 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     }
     if (O.step_reward) O.step_reward[e] = rew;
     if (O.terminated) O.terminated[e] = done ? 1 : 0;
+    if (O.host_terminated) O.host_terminated[e] = done ? 1 : 0;
     if (O.counts) { O.counts[2 * e] = tcount; O.counts[2 * e + 1] = fcount; }
-    if (O.reward && !((flags & GCA_FLAG_AUTO_RESET) && done)) O.reward[e] = rew;
+    if (!((flags & GCA_FLAG_AUTO_RESET) && done)) {
+      if (O.reward) O.reward[e] = rew;
+      if (O.host_reward) O.host_reward[e] = rew;
+    }
   }
 
   // ---- fused conditional_reset (advanced_bulldozer.py:422-518) ------------------------------------
@@ -1156,7 +1170,9 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       S.tick[e] = SNAP.tick[e];
       if (S.steps_elapsed) S.steps_elapsed[e] = 0.0f;
       if (S.reward_accumulated) S.reward_accumulated[e] = 0.0f;
-      if (O.reward) O.reward[e] = snap_reward[e];
+      const float sr = snap_reward[e];
+      if (O.reward) O.reward[e] = sr;
+      if (O.host_reward) O.host_reward[e] = sr;
     }
   }
 }

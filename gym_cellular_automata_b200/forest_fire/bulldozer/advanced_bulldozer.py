@@ -556,11 +556,15 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         buf = torch.empty(5 * N, dtype=torch.uint8).pin_memory()
         return buf[:4 * N].view(torch.float32), buf[4 * N:]
 
-    def step_host(self, actions_host: torch.Tensor, reward_host: torch.Tensor, terminated_host: torch.Tensor) -> None:
+    def step_host(self, actions_host: torch.Tensor, reward_host: torch.Tensor, terminated_host: torch.Tensor,
+                  staged: bool = False) -> None:
         """The step for a CPU-side rollout loop, one C call (``gca_env_step_host``): ``actions_host`` (N,3)
-        int32, ``reward_host`` (N,) float32 and ``terminated_host`` (N,) uint8 are HOST tensors (pin them);
-        actions are copied in, the fused step runs, reward / terminated are copied out and the stream is
-        synchronised, so the results are valid on return.  State stays on the device."""
+        int32, ``reward_host`` (N,) float32 and ``terminated_host`` (N,) uint8 are HOST tensors.  When all
+        three are pinned (``pin_memory()``) and the grid is 64x64 the step kernel reads the actions and stores
+        reward / terminated over the bus itself (zero-copy: one launch, no copy engine); otherwise -- or with
+        ``staged=True`` -- actions are copied in, the fused step runs, reward / terminated are copied out
+        (``staged`` may also be ``FLAG_HOST_COPY_IN`` or ``FLAG_HOST_COPY_OUT`` to stage one direction only).
+        The stream is synchronised, so the results are valid on return.  State stays on the device."""
         N = self.num_envs
         if (actions_host.is_cuda or actions_host.dtype != torch.int32 or actions_host.numel() != 3 * N
                 or not actions_host.is_contiguous()):
@@ -578,12 +582,12 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                 C.byref(self._params), C.byref(self._state.cstruct()), self._host_act_dev.data_ptr(),
                 C.byref(self._out.cstruct()), C.byref(self._snapshot.cstruct()), ptr(self._snap_reward),
                 reward_host.data_ptr(), terminated_host.data_ptr())
-        flags = self._flags | (_lib.FLAG_AUTO_RESET if self.auto_reset else 0)
+        flags = self._flags | (_lib.FLAG_AUTO_RESET if self.auto_reset else 0) | (_lib.FLAG_HOST_COPY if staged is True else int(staged))
         if self.balance_every and self._state.work is not None:
             if self._state.order is None:
                 self._state.enable_balancing()
                 self._version_structs += 1
-                return self.step_host(actions_host, reward_host, terminated_host)  # re-bind the cached pointers
+                return self.step_host(actions_host, reward_host, terminated_host, staged)  # re-bind the cached pointers
             self._steps_since_balance += 1
             if self._steps_since_balance >= self.balance_every:
                 self._state.rebalance()

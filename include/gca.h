@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GCA_VERSION 101
+#define GCA_VERSION 102
 #define GCA_MAX_R 10        /* burn kernel radius: ceil(log2(size)) - 2; 10 at 4096 */
 #define GCA_MAX_K 8         /* CA sub-steps fused into one env step */
 
@@ -53,6 +53,9 @@ typedef enum gca_status {
 #define GCA_FLAG_NO_HIDDEN 2u   /* hidden layers off: veg = den = 3, slope factor 1 (pslope may be NULL) */
 #define GCA_FLAG_CA_ONLY 4u     /* run only the CA sub-steps (no clock/move/douse/reward bookkeeping) */
 #define GCA_FLAG_NO_TMA 8u      /* tiled path: stage tiles with plain loads instead of TMA */
+#define GCA_FLAG_HOST_COPY_IN 32u   /* gca_env_step_host: stage the actions through cudaMemcpyAsync even when mapped */
+#define GCA_FLAG_HOST_COPY_OUT 64u  /* gca_env_step_host: copy reward / terminated out with cudaMemcpyAsync even when mapped */
+#define GCA_FLAG_HOST_COPY 96u      /* both */
 #define GCA_FLAG_WORK_CYCLES 16u /* diagnostics: work[e] receives the elapsed SM clock cycles of env e's step instead of the cost estimate */
 
 /* Constants of one environment family (host POD, passed to kernels by value). */
@@ -131,6 +134,8 @@ typedef struct gca_step_out {
   uint8_t* obs_night;   /* [N] is_night value the observation must be rendered with (pre-flip) */
   unsigned long long* stats; /* [8] += front cells, (cell,dir) draws, ignitions, burn-outs,
                                        threshold cells (exact re-evaluations), env steps, 0, 0 */
+  float* host_reward;       /* optional [N] mirror of `reward` in MAPPED pinned host memory (device-visible */
+  uint8_t* host_terminated; /* address): the 64x64 step kernel stores both there as well; NULL = off      */
 } gca_step_out;
 
 /* Injected random fields for rule-parity tests (device, each with a leading K axis); NULL = threefry. */
@@ -159,11 +164,16 @@ int gca_env_step(const gca_params* p, const gca_state* s, const int32_t* actions
                  const gca_step_out* out, const gca_inject* inj, const gca_state* snapshot,
                  const float* snapshot_reward, uint32_t flags, void* stream);
 
-/* The same step for a caller whose actions and results live in HOST memory (pinned for asynchronous
- * copies), i.e. the call a CPU-side rollout loop makes once per step: host_actions [N][3] is copied to
- * the device buffer dev_actions, gca_env_step runs, out->reward and out->terminated (both required) are
- * copied to host_reward [N] / host_terminated [N] (one copy when, on both sides, terminated starts right
- * after the N rewards), and the stream is synchronised before returning. */
+/* The same step for a caller whose actions and results live in HOST memory, i.e. the call a CPU-side
+ * rollout loop makes once per step; the results are valid on return (the stream is synchronised).
+ * Two transports, chosen per call and per direction from the buffers themselves (cudaPointerGetAttributes):
+ *  - zero-copy (64x64 grids, host buffer pinned and mapped into the device address space, e.g.
+ *    cudaHostAlloc / torch's pin_memory()): the step kernel reads host_actions [N][3] over the bus
+ *    itself (dev_actions is not touched) / stores reward and terminated to host_reward [N] and
+ *    host_terminated [N] next to its device outputs -- no copy engine in the step;
+ *  - staged (any other case, or GCA_FLAG_HOST_COPY_IN / _OUT): host_actions is copied to the device
+ *    buffer dev_actions before gca_env_step / out->reward and out->terminated (both required) are copied
+ *    out after it (one copy when, on both sides, terminated starts right after the N rewards). */
 int gca_env_step_host(const gca_params* p, const gca_state* s, const int32_t* host_actions,
                       int32_t* dev_actions, const gca_step_out* out, const gca_state* snapshot,
                       const float* snapshot_reward, uint32_t flags, float* host_reward,

@@ -477,20 +477,26 @@ def test_episode_statistics_with_env(cuda_device):
         assert np.array_equal(v.cpu().numpy(), np.asarray(st[k]).reshape(v.shape)), k
 
 
-def test_step_host_equals_step_device(cuda_device):
-    """gca_env_step_host (host buffers in / out, copies inside) gives the states and results of the device call."""
+@pytest.mark.parametrize("transport", ["zero_copy", "staged", "pageable"])
+def test_step_host_equals_step_device(cuda_device, transport):
+    """gca_env_step_host (host buffers in / out) gives the states and results of the device call, on each of its
+    transports: pinned buffers read / written by the kernel itself (zero-copy), pinned buffers staged through the
+    copy engine (GCA_FLAG_HOST_COPY), and pageable buffers (falls back to staging by itself).  Envs terminate and
+    are auto-reset inside the run (reward of the restored grid goes to the host mirror as well)."""
     from parity_util import make_pair
     envs = [make_pair(N=33, K=4, mode="legacy", use_hidden=True, seed=6)[0] for _ in range(2)]
     for env in envs:
         env.auto_reset = True
     rng = np.random.default_rng(1)
-    h_rew = torch.empty(33, dtype=torch.float32).pin_memory()
-    h_term = torch.empty(33, dtype=torch.uint8).pin_memory()
+    pin = (lambda t: t.pin_memory()) if transport != "pageable" else (lambda t: t)
+    h_rew = pin(torch.full((33,), -7.0, dtype=torch.float32))
+    h_term = pin(torch.full((33,), 9, dtype=torch.uint8))
     for step in range(25):
         a = torch.as_tensor(np.stack([rng.integers(0, 9, 33), rng.integers(0, 2, 33), rng.integers(0, 3, 33)], 1).astype(np.int32))
         out = envs[0].step_device(a.to(cuda_device))
-        envs[1].step_host(a.pin_memory(), h_rew, h_term)
+        envs[1].step_host(pin(a), h_rew, h_term, staged=(transport == "staged"))
         assert torch.equal(out.reward.cpu(), h_rew) and torch.equal(out.terminated.cpu(), h_term)
+        assert torch.equal(envs[1]._out.reward.cpu(), h_rew) and torch.equal(envs[1]._out.terminated.cpu(), h_term)
     for f in ("cell", "death", "doused", "key", "position", "time", "tick", "wind_index"):
         assert torch.equal(getattr(envs[0]._state, f), getattr(envs[1]._state, f)), f
 

@@ -25,7 +25,7 @@ def test_abi_exports_every_declared_symbol(lib):
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.gca_version() == 101
+    assert lib.gca_version() == 102
 
 
 def test_abi_struct_sizes_match_header(tmp_path):

@@ -22,7 +22,9 @@ def timed(f, n=steps):
     for i in range(n): f(i)
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e6
 st = torch.cuda.current_stream()
-print("step_host (H2D + step + D2H + sync)        : %.1f us" % timed(lambda i: env.step_host(h_act[i], h_rew, h_term)))
+print("step_host zero-copy (mapped pinned buffers): %.1f us" % timed(lambda i: env.step_host(h_act[i], h_rew, h_term)))
+print("step_host staged (H2D + step + D2H + sync) : %.1f us" % timed(lambda i: env.step_host(h_act[i], h_rew, h_term, staged=True)))
+print("step_host zero-copy again                  : %.1f us" % timed(lambda i: env.step_host(h_act[i], h_rew, h_term)))
 print("step_device + stream sync (no copies)      : %.1f us" % timed(lambda i: (env.step_device(acts[100 + steps + i]), st.synchronize())))
 print("step_device back to back (no sync)         : %.1f us" % timed(lambda i: env.step_device(acts[100 + 2 * steps + i])))
 d_act = torch.empty((N, 3), dtype=torch.int32, device=dev)
