@@ -1,0 +1,187 @@
+"""Generates tests/golden/reference_shim_golden.npz by executing the REFERENCE'S OWN SOURCE.
+
+The reference env (``/root/reference/gym_cellular_automata/forest_fire/bulldozer/advanced_bulldozer.py`` and the
+operator files it composes) is imported where it lies and run on CPU under ``oracle/ref_shim`` -- NumPy stand-ins
+for the jax / flax / gymnasium names it touches (none of them is installable in this image).  The loop below is the
+reference's rollout loop (``agents/jax_ppo.py``: ``stateless_step`` then ``conditional_reset``); every state
+component after every step is recorded.  ``tests/test_oracle.py`` replays the oracle, ``tests/test_gpu_parity.py``
+the CUDA path, on the recorded start states and actions and demand identical results.
+
+What the vectors pin and what they cannot: see ``oracle/ref_shim/__init__.py`` (all reference Python on the path;
+not jax.random's bit stream -- delegated to oracle/prng.py, pinned by known answers -- nor XLA's float32 summation
+order).  jit semantics: ``initial_state`` is evaluated once per env instance (a jitted function bakes the sample it
+saw at trace time); the subclass below does just that and nothing else.
+
+Run (only here, /root/reference is needed):  python tests/golden/make_reference_golden.py
+"""
+import hashlib
+import os
+import random
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import prng, ref_shim  # noqa: E402
+from oracle.ref_shim import jax_shim  # noqa: E402
+
+CASES = {
+    # name: grid size, envs, steps, stream layout, hidden layers, extensions, seed, start-state recipe
+    "ref64_legacy_ext": dict(size=64, N=3, steps=36, mode=prng.LEGACY, use_hidden=True, ext=True, seed=11,
+                             scatter=0.02, dying_env=0, p_tree_ca=0.0),
+    "ref32_nohidden_regrow": dict(size=32, N=4, steps=48, mode=prng.LEGACY, use_hidden=False, ext=False, seed=12,
+                                  scatter=0.03, dying_env=1, p_tree_ca=0.01),
+    "ref64_partitionable": dict(size=64, N=2, steps=12, mode=prng.PARTITIONABLE, use_hidden=True, ext=False, seed=13,
+                                scatter=0.02, dying_env=None, p_tree_ca=0.0),
+}
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def actions_for(case, step):
+    rng = np.random.default_rng(7000 * case["seed"] + step)
+    N = case["N"]
+    return np.stack([rng.integers(0, 9, N), rng.integers(0, 2, N), rng.integers(0, 3, N)], 1).astype(np.int32)
+
+
+def u16(a, name):
+    a = np.asarray(a)
+    assert np.all(a == np.round(a)) and a.min() >= 0 and a.max() < 65536, name
+    return a.astype(np.uint16)
+
+
+def record(ctx_all):
+    ctx = ctx_all["per_env_context"]
+    return {
+        "grid": np.asarray(ctx["true_grid"]).astype(np.uint8),
+        "fire_age": u16(ctx["fire_age"], "fire_age"),
+        "dousing": np.packbits(np.asarray(ctx["dousing_count"]).astype(np.uint8), axis=-1),
+        "key": np.asarray(ctx["key"]).astype(np.uint32),
+        "wind_index": np.asarray(ctx["wind_index"]).astype(np.int32),
+        "time_step": np.asarray(ctx["time_step"]).astype(np.int32),
+        "is_night": np.asarray(ctx["is_night"]).astype(np.int32),
+        "position": np.asarray(ctx_all["position"]).astype(np.int32),
+        "time": np.asarray(ctx_all["time"]).astype(np.float32),
+    }
+
+
+def run_case(name, case, ab, jnp):
+    jax_shim.set_rng_mode(case["mode"])
+    np.random.seed(case["seed"])
+    random.seed(case["seed"])
+    jax = sys.modules["jax"]
+
+    class TraceOnce(ab.AdvancedForestFireBulldozerEnv):
+        """initial_state evaluated once, as under jax.jit (the traced sample becomes a constant)."""
+        _baked = None
+
+        @property
+        def initial_state(self):
+            if self._baked is None:
+                self._baked = ab.AdvancedForestFireBulldozerEnv.initial_state.fget(self)
+            grid, c = self._baked
+            return grid, {"per_env_context": dict(c["per_env_context"]), "shared_context": dict(c["shared_context"]),
+                          "position": c["position"], "time": c["time"]}
+
+    captured = []  # the float64 altitude get_slope is called with (the env keeps only a float32 copy)
+    orig_get_slope = ab.get_slope
+    ab.get_slope = lambda alt, *a, **k: (captured.append(np.array(alt, dtype=np.float64)), orig_get_slope(alt, *a, **k))[1]
+    key = jax.random.split(jax.random.PRNGKey(1))[0]  # scripts/run:554-555
+    S, N = case["size"], case["N"]
+    env = TraceOnce(S, S, key=key, num_envs=N, speed_move=0.48, speed_act=0.12, use_hidden=case["use_hidden"],
+                    enable_extensions=case["ext"])
+    ab.get_slope = orig_get_slope
+    obs, info = env.reset()
+    rgb, ctx_all = obs
+    out = {}
+    snap = record(ctx_all)
+    pec = ctx_all["per_env_context"]
+    out["altitude"] = np.asarray(pec["altitude"]).astype(np.float32)
+    out["altitude64"] = captured[0]
+    assert np.array_equal(captured[0].astype(np.float32), out["altitude"])
+    out["vegetation"] = np.asarray(pec["vegetation"]).astype(np.uint8)
+    out["density"] = np.asarray(pec["density"]).astype(np.uint8)
+    out["slope_sha256"] = np.array(sha(np.asarray(pec["slope"]).astype(np.float32)))
+    out["slope_sample"] = np.asarray(pec["slope"]).astype(np.float32)[0, 5:9, 5:9]
+    out["winds"] = np.asarray(ctx_all["shared_context"]["winds"]).astype(np.float32)
+    sc = ctx_all["shared_context"]
+    if case["p_tree_ca"]:
+        sc["p_tree"] = jnp.array(case["p_tree_ca"], dtype=jnp.float32)  # the CA's regrowth probability (default 0)
+    out["shared_scalars"] = np.array([float(sc["p_fire"]), float(sc["p_tree"]), float(sc["p_wind_change"]),
+                                      float(sc["day_length"])], dtype=np.float64)
+    for k, v in snap.items():
+        out["snapshot/" + k] = v
+    # ---- a richer start than two seed cells: scattered fires with short remaining ages; one env about to end
+    rs = np.random.default_rng(case["seed"] + 500)
+    grid = np.asarray(pec["true_grid"]).copy()
+    age = np.asarray(pec["fire_age"]).copy()
+    m = rs.random(grid.shape) < case["scatter"]
+    grid[m] = 2.0
+    age[m] = rs.integers(1, 30, size=int(m.sum())).astype(np.float32)
+    d = case["dying_env"]
+    if d is not None:  # a lone pair of cells that burns out at once: terminated -> conditional_reset
+        grid[d][grid[d] == 2.0] = 1.0
+        r, c = 3 * S // 4, S // 4
+        grid[d, r - 2:r + 3, c - 3:c + 3] = 0.0
+        grid[d, r, c] = grid[d, r, c - 1] = 2.0
+        age[d, r, c], age[d, r, c - 1] = 2.0, 3.0
+    pec["true_grid"] = jnp.asarray(grid.astype(np.float32))
+    pec["fire_age"] = jnp.asarray(age.astype(np.float32))
+    pec["time_step"] = jnp.asarray(np.full(N, 396, dtype=np.int32))  # day/night flips at time_step 400
+    for k, v in record(ctx_all).items():
+        out["start/" + k] = v
+    steps = case["steps"]
+    acts = np.stack([actions_for(case, s) for s in range(steps)])
+    out["actions"] = acts
+    rec = {}
+    n_term = 0
+    t0 = time.time()
+    for s in range(steps):
+        a = jnp.asarray(acts[s])
+        step_tuple = env.stateless_step(a, obs, info)
+        pre_rgb = np.asarray(step_tuple[0][0]).astype(np.float32)
+        pre = {"step_reward": np.asarray(step_tuple[1]).astype(np.float32),
+               "terminated": np.asarray(step_tuple[2]).astype(np.uint8),
+               "pre_rgb_sha256": np.array(sha(pre_rgb))}
+        n_term += int(pre["terminated"].sum())
+        obs, reward, terminated, truncated, info = env.conditional_reset(step_tuple, a)
+        post = record(obs[1])
+        post["reward"] = np.asarray(reward).astype(np.float32)
+        post["terminated_after_reset"] = np.asarray(terminated).astype(np.uint8)
+        post["steps_elapsed"] = np.asarray(info["steps_elapsed"]).astype(np.float32)
+        post["reward_accumulated"] = np.asarray(info["reward_accumulated"]).astype(np.float32)
+        post["rgb_sha256"] = np.array(sha(np.asarray(obs[0]).astype(np.float32)))
+        for k, v in {**pre, **post}.items():
+            rec.setdefault(k, []).append(v)
+    out["last_rgb"] = np.asarray(obs[0]).astype(np.float32)
+    for k, v in rec.items():
+        out["steps/" + k] = np.stack(v)
+    g = out["steps/grid"]
+    print(f"{name}: {steps} steps x {N} envs in {time.time() - t0:.1f} s; terminations {n_term}; "
+          f"cells changed per step {np.mean((g[1:] != g[:-1]).sum(axis=(1, 2, 3))):.1f}; "
+          f"burning at end {int((g[-1] == 2).sum())}; doused {int(np.unpackbits(out['steps/dousing'][-1]).sum())}")
+    return out
+
+
+if __name__ == "__main__":
+    assert ref_shim.available(), "the reference tree is needed to generate these vectors"
+    jax = ref_shim.install(prng.LEGACY)
+    ab = ref_shim.load("forest_fire.bulldozer.advanced_bulldozer")
+    out = {}
+    import contextlib
+    import io
+    for name, case in CASES.items():
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):  # the reference constructor prints its slope histogram
+            res = run_case(name, case, ab, jax.numpy)
+        print(buf.getvalue().strip().splitlines()[-1])
+        for k, v in res.items():
+            out[f"{name}/{k}"] = v
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_shim_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")

@@ -343,6 +343,58 @@ def test_cuda_reproduces_golden_fixtures(cuda_device):
         assert np.array_equal(env._state.reward_accumulated.cpu().numpy(), gold[f"{name}/reward_accumulated"]), name
 
 
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("name", ["ref64_legacy_ext", "ref32_nohidden_regrow", "ref64_partitionable"])
+def test_cuda_reproduces_reference_source_golden(cuda_device, name, fused):
+    """The CUDA path against vectors recorded from the reference's OWN source (run under oracle/ref_shim,
+    tests/golden/make_reference_golden.py): the reference's rollout loop -- stateless_step, then conditional_reset --
+    through the mirrored env API, every state component and every float32 observation pixel of every step
+    (fused=False); and the hot path proper, the fused step kernel with GCA_FLAG_AUTO_RESET (fused=True), on the
+    state after each step.  64x64 cases run env_step64_kernel, the 32x32 case the tiled kernels."""
+    import ref_golden_util as R
+    from parity_util import read_cuda_state
+    from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv
+    fx = R.load_case(name)
+    c = R.CASES[name]
+    E, start, info, snap, slope = R.oracle_states(fx)
+    N, H, W = fx["start/grid"].shape
+    env = AdvancedForestFireBulldozerEnv(H, W, key=1, num_envs=N, speed_move=0.48, speed_act=0.12,
+                                         use_hidden=c["use_hidden"], substeps=1,
+                                         rng_mode="legacy" if c["mode"] == 0 else "partitionable", seed=0,
+                                         hidden="random" if c["use_hidden"] else "reference",
+                                         obs_mode="none" if fused else "rgb_f32", enable_extensions=c["ext"],
+                                         ca_p_tree=float(fx["shared_scalars"][1]), auto_reset=fused)
+    env.set_state(snap["per_env_context"], snap["position"], snap["time"], as_snapshot=True)
+    env.set_state(start["per_env_context"], start["position"], start["time"], as_snapshot=False, info=info)
+    bad = []
+    for s in range(fx["actions"].shape[0]):
+        a = torch.as_tensor(fx["actions"][s], device=cuda_device)
+        if fused:
+            out = env.step_device(a)
+            reward, step_reward, term = out.reward, out.step_reward, out.terminated
+            steps_elapsed, reward_acc = env._state.steps_elapsed, env._state.reward_accumulated
+        else:
+            step_tuple = env.stateless_step(a)
+            step_reward, term = step_tuple[4]["reward"], step_tuple[2]
+            if R.sha(step_tuple[0][0].cpu().numpy().astype(np.float32)) != str(fx["steps/pre_rgb_sha256"][s]):
+                bad.append(f"{name} step {s}: observation before conditional_reset differs")
+            obs, reward, term_after, _, ninfo = env.conditional_reset(step_tuple, a)
+            steps_elapsed, reward_acc = ninfo["steps_elapsed"], ninfo["reward_accumulated"]
+            assert not term_after.any()
+            if R.sha(obs[0].cpu().numpy().astype(np.float32)) != str(fx["steps/rgb_sha256"][s]):
+                bad.append(f"{name} step {s}: observation differs")
+        st = read_cuda_state(env)
+        got = {"grid": st["true_grid"].astype(np.uint8), "fire_age": st["fire_age"].astype(np.uint16),
+               "dousing": np.packbits(st["dousing_count"].astype(np.uint8), axis=-1), "key": st["key"],
+               "wind_index": st["wind_index"].astype(np.int32), "time_step": st["time_step"].astype(np.int32),
+               "is_night": st["is_night"].astype(np.int32), "position": st["position"].astype(np.int32),
+               "time": st["time"].astype(np.float32), "step_reward": step_reward.cpu().numpy(),
+               "terminated": term.cpu().numpy().astype(np.uint8), "reward": reward.cpu().numpy(),
+               "steps_elapsed": steps_elapsed.cpu().numpy(), "reward_accumulated": reward_acc.cpu().numpy()}
+        bad += R.compare_step(fx, s, got, name)
+    assert not bad, "\n".join(bad[:20])
+
+
 def test_env_keys_do_not_depend_on_sharding(cuda_device):
     from oracle import prng
     from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv

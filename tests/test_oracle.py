@@ -3,6 +3,7 @@ rule-level checks mirroring the reference's own operator tests, golden fixtures.
 import copy
 import importlib.util
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -371,3 +372,54 @@ def test_hidden_device_mirror_layer_models():
     # an env's layers depend on (seed, env) only
     assert np.array_equal(hd.patches(H, W, seed, 5, 1, 2), hd.patches(H, W, seed, 5, 1, 2))
     assert not np.array_equal(hd.patches(H, W, seed, 5, 1, 2), hd.patches(H, W, seed + 1, 5, 1, 2))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# the reference's OWN source, executed under oracle/ref_shim (NumPy stand-ins for jax / flax / gymnasium)
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["ref64_legacy_ext", "ref32_nohidden_regrow", "ref64_partitionable"])
+def test_oracle_reproduces_reference_source_golden(name):
+    """tests/golden/reference_shim_golden.npz was recorded from the reference's advanced_bulldozer.py / operator
+    files themselves (tests/golden/make_reference_golden.py): rollouts of stateless_step + conditional_reset with
+    burn-outs, dousing, wind changes, a day/night flip, regrowth, a termination and its reset, extensions on / off,
+    both jax.random stream layouts.  The oracle must reproduce every state component and every observation pixel
+    of every step; get_slope and get_winds must reproduce the reference's tables."""
+    import ref_golden_util as R
+    fx = R.load_case(name)
+    c = R.CASES[name]
+    bad = R.replay_oracle(fx, c["mode"], c["ext"], name)
+    assert not bad, "\n".join(bad[:20])
+    if name != "ref64_partitionable":
+        assert fx["steps/terminated"].sum() >= 1, "the fixture should hold a termination"
+    assert (fx["steps/is_night"] == 1).any() and fx["steps/dousing"].any()
+
+
+def test_reference_source_runs_live_under_the_shim():
+    """Where the reference tree exists (this container, not the GPU box): import its env through the shim, run a
+    short 16x16 rollout and replay the oracle on it -- the generator of the fixtures above, exercised end to end."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("no reference tree here")
+    import contextlib
+    import importlib.util
+    import io
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_reference_golden",
+                                                  os.path.join(here, "golden", "make_reference_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    import ref_golden_util as R
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k.split(".")[0] in ("jax", "flax", "gymnasium", "gym_cellular_automata")}
+    try:
+        jax = ref_shim.install(prng.LEGACY)
+        ab = ref_shim.load("forest_fire.bulldozer.advanced_bulldozer")
+        case = dict(size=16, N=2, steps=6, mode=prng.LEGACY, use_hidden=True, ext=True, seed=21, scatter=0.04,
+                    dying_env=1, p_tree_ca=0.0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            fx = mg.run_case("live16", case, ab, jax.numpy)
+        bad = R.replay_oracle(fx, prng.LEGACY, True, "live16")
+        assert not bad, "\n".join(bad[:20])
+    finally:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("jax", "flax", "gymnasium", "gym_cellular_automata")]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
