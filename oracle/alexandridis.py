@@ -6,10 +6,16 @@ may import this module.  It is deliberately DENSE and literal (every cell draws 
 random words, every neighbourhood is materialised), i.e. it follows the reference's data
 flow, not the lazy/bit-board formulation of the CUDA kernels it checks.
 
-Parity status: **parity unpinned** at operator level -- the reference's tests hold no
-golden values for this path and JAX cannot be installed here.  The PRNG
-layer is pinned to public known-answer vectors (oracle/prng.py); float32 reduction order
-(row-major, accumulator from +0) and ``exp`` (NumPy float32) are stated assumptions.
+Parity status: **pinned to the reference's own Python source** -- advanced_bulldozer.py and the operator
+files are imported from /root/reference and executed under ``oracle/ref_shim`` (NumPy stand-ins for the
+jax / flax / gymnasium names they touch; jax itself cannot be installed here); the rollouts recorded that
+way (tests/golden/make_reference_golden.py -> tests/golden/reference_shim_golden.npz: stateless_step +
+conditional_reset, observations included) are reproduced bit for bit by this module
+(tests/test_oracle.py::test_oracle_reproduces_reference_source_golden).  **Still unpinned** (no jax / XLA
+here, and the reference's tests hold no golden values): the bit stream of
+``jax.random`` -- pinned only to public known-answer vectors (oracle/prng.py) -- and XLA's float32
+evaluation details; reduction order (row-major, accumulator from +0) and ``exp`` (NumPy float32) are
+stated assumptions, shared by the shim.
 
 All paths below are relative to /root/reference/gym_cellular_automata/.
 

@@ -5,8 +5,9 @@
  * may load this library.  It is the fast twin of oracle/alexandridis.py (same dense,
  * literal data flow: every cell draws its 12 random words, every window is summed in
  * row-major order in float32) and is itself checked against that NumPy restatement in
- * tests/test_oracle_c.py.  Parity status: PRNG pinned to Random123 / public JAX vectors;
- * operator level "parity unpinned" (the reference has no golden values, JAX not installable).
+ * tests/test_oracle.py.  Parity status: PRNG pinned to Random123 / public JAX vectors; the NumPy twin is
+ * pinned to rollouts of the reference's own Python source run under oracle/ref_shim (jax itself is not
+ * installable; XLA's float32 summation order and jax.random's bits beyond the known answers stay unpinned).
  *
  * Reference lines (relative to /root/reference/gym_cellular_automata/):
  *   forest_fire/operators/ca_alexandridis_jax.py:164-206,321-460   CA update

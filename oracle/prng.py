@@ -23,8 +23,10 @@ file restates the published algorithm of ``jax._src.prng`` / ``jax._src.random``
 * ``uniform`` float32 in [0,1): (bits >> 9) * 2**-23 exactly.
 * ``randint`` int32: two draws and the multiply-mod construction of ``_randint``.
 
-Parity status: PRNG layer pinned to public known-answer vectors; the reference's own tests
-hold no random golden values -> operator-level parity is "unpinned".
+Parity status: PRNG layer pinned to public known-answer vectors only (jax cannot run here and the
+reference's own tests hold no random golden values).  The operators that consume
+these numbers are pinned to the reference's own source through oracle/ref_shim, which delegates
+``jax.random`` to this module.
 """
 from __future__ import annotations
 

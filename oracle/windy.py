@@ -6,6 +6,9 @@ operators/move_modify.py:9-134, operators/repeat_ca.py:10-45 and bulldozer/bulld
 Literal: the CA goes through scipy.signal.convolve2d and the three break points exactly like
 the reference.  The reference draws its 3x3 roll from a freshly constructed gymnasium Box
 (unseeded), so only RULE parity is possible: rolls are always passed in.
+Parity status: pinned to the reference's own v3 operator source, executed through oracle/ref_shim's gymnasium
+stand-in with recorded rolls (tests/golden/make_reference_golden.py run_v3,
+tests/test_oracle.py::test_v3_oracle_reproduces_reference_source_golden).
 """
 from __future__ import annotations
 

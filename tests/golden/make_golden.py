@@ -1,8 +1,8 @@
 """Generates tests/golden/env_step_golden.npz from the NumPy oracle (oracle/alexandridis.py).
 
-The reference itself cannot be run in this image (no jax / flax / gymnasium), so
-these are ORACLE-generated vectors: they pin the oracle (NumPy and C) and the CUDA path against
-regressions, they do not add evidence about the reference beyond what the oracle's header states.
+These are ORACLE-generated vectors (K = 1, 2, 4 sub-steps, long runs): they pin the oracle (NumPy and C)
+and the CUDA path against regressions.  The vectors recorded from the reference's own source are
+tests/golden/reference_shim_golden.npz (make_reference_golden.py).
 Run:  python tests/golden/make_golden.py
 """
 import os

@@ -168,6 +168,93 @@ def run_case(name, case, ab, jnp):
     return out
 
 
+def run_v3(ref_shim_mod, N=4, H=32, W=48, steps=40, seed=31):
+    """The registered v3 rule set: the reference's ForestFireBulldozerEnv (bulldozer/bulldozer.py, NumPy
+    WindyForestFire / Move / Modify / RepeatCA) is single-env; N independent instances are stepped with recorded
+    actions.  Its only random draw per CA update, ``spaces.Box(0, 1, (3, 3)).sample()`` (ca_windy.py:53-60), is fed
+    from a seeded stream and recorded."""
+    import types
+    from oracle.ref_shim import gymnasium_shim
+    ops = sys.modules["gym_cellular_automata.forest_fire.operators"]
+    for mod, names in (("ca_windy", ("WindyForestFire",)), ("move_modify", ("Move", "Modify", "MoveModify")),
+                       ("repeat_ca", ("RepeatCA",))):
+        m = ref_shim_mod.load("forest_fire.operators." + mod)
+        for n in names:
+            setattr(ops, n, getattr(m, n))
+    rname = "gym_cellular_automata.forest_fire.bulldozer.utils.render"
+    if rname not in sys.modules:
+        r = types.ModuleType(rname)
+        r.render = None
+        sys.modules[rname] = r
+    bd = ref_shim_mod.load("forest_fire.bulldozer.bulldozer")
+    rng = np.random.default_rng(seed)
+    consumed = []
+    orig_sample = gymnasium_shim.Box.sample
+
+    def sample(self):
+        if self.shape == (3, 3):
+            roll = rng.random((3, 3))
+            consumed.append(roll)
+            return roll
+        return orig_sample(self)
+    gymnasium_shim.Box.sample = sample
+    try:
+        envs = [bd.ForestFireBulldozerEnv(nrows=H, ncols=W, t_move=0.45, t_shoot=0.8) for _ in range(N)]
+        first = [e.reset()[0] for e in envs]
+        consumed.clear()
+        out = {"grid0": np.stack([np.asarray(o[0]) for o in first]).astype(np.uint8),
+               "position0": np.stack([np.asarray(o[1][1]) for o in first]).astype(np.int32),
+               "time0": np.array([float(o[1][2]) for o in first], dtype=np.float64),
+               "wind": np.asarray(first[0][1][0]["wind"], dtype=np.float64),
+               "t_move_shoot_any": np.array([0.45, 0.8, 0.001])}
+        acts = np.stack([rng.integers(0, 9, (steps, N)), rng.integers(0, 2, (steps, N))], -1).astype(np.int32)
+        out["actions"] = acts
+        rolls = np.zeros((steps, N, 3, 3, 3))
+        rec = {k: [] for k in ("grid", "position", "time", "reward", "terminated", "repeats")}
+        for s in range(steps):
+            row = {k: [] for k in rec}
+            for e, env in enumerate(envs):
+                consumed.clear()
+                if env.done:  # the reference refuses to step a finished env; keep it frozen
+                    g, (cp, pos, t) = env.state
+                    rew, term = np.nan, True
+                else:
+                    # CAEnv.step's sequence (ca_env.py:27-48) -- MDP transition, done check, reward -- with ONE
+                    # repair: the env's context carries {"wind": array} where WindyForestFire.update compares the
+                    # array itself (bulldozer.py:270 vs ca_windy.py:65: TypeError as shipped, SURVEY F9), so the
+                    # MDP operator is handed the array
+                    g0, (cp, pos0, t0) = env.state
+                    wind = cp["wind"] if isinstance(cp, dict) else cp
+                    g, (cp, pos, t) = env.MDP(g0, acts[s, e], (wind, pos0, t0))
+                    env.state = env.grid, env.context = g, (cp, pos, t)
+                    env._is_done()
+                    try:
+                        rew = env._award()
+                    except ZeroDivisionError:
+                        rew = np.nan
+                    term = env.done
+                assert len(consumed) <= 3
+                for k, roll in enumerate(consumed):
+                    rolls[s, e, k] = roll
+                row["grid"].append(np.asarray(g).astype(np.uint8))
+                row["position"].append(np.asarray(pos).astype(np.int32))
+                row["time"].append(float(t))
+                row["reward"].append(float(rew))
+                row["terminated"].append(bool(term))
+                row["repeats"].append(len(consumed))
+            for k in rec:
+                rec[k].append(np.stack([np.asarray(v) for v in row[k]]))
+        out["rolls"] = rolls
+        out["frozen"] = np.stack([np.array([False] * N)] + [r.astype(bool) for r in rec["terminated"][:-1]])
+        for k, v in rec.items():
+            out["steps/" + k] = np.stack(v)
+        print(f"v3: {steps} steps x {N} envs of {H}x{W}; repeats seen {sorted(set(out['steps/repeats'].ravel().tolist()))}; "
+              f"burning at end {int((out['steps/grid'][-1] == 25).sum())}")
+        return out
+    finally:
+        gymnasium_shim.Box.sample = orig_sample
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "the reference tree is needed to generate these vectors"
     jax = ref_shim.install(prng.LEGACY)
@@ -182,6 +269,8 @@ if __name__ == "__main__":
         print(buf.getvalue().strip().splitlines()[-1])
         for k, v in res.items():
             out[f"{name}/{k}"] = v
+    for k, v in run_v3(ref_shim).items():
+        out[f"v3_32x48/{k}"] = v
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_shim_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

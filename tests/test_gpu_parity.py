@@ -529,6 +529,29 @@ def test_episode_statistics_with_env(cuda_device):
         assert np.array_equal(v.cpu().numpy(), np.asarray(st[k]).reshape(v.shape)), k
 
 
+def test_v3_cuda_reproduces_reference_source_golden(cuda_device):
+    """The batched CUDA v3 env against vectors recorded from the reference's own v3 operators
+    (tests/golden/make_reference_golden.py run_v3): grid, position, float64 clock, reward, done, CA-update count."""
+    import ref_golden_util as R
+    from gym_cellular_automata_b200.forest_fire.bulldozer import ForestFireBulldozerEnv
+    fx = R.load_case("v3_32x48")
+    N, H, W = fx["grid0"].shape
+    tm, ts, ta = [float(x) for x in fx["t_move_shoot_any"]]
+    assert not fx["frozen"].any(), "the fixture has no finished env (a finished reference env stops stepping)"
+    env = ForestFireBulldozerEnv(H, W, num_envs=N, seed=0, t_move=tm, t_shoot=ts, t_any=ta, max_repeats=3)
+    env.reset()
+    env.set_state(fx["grid0"].astype(np.int64), fx["position0"], fx["time0"])
+    for s in range(fx["actions"].shape[0]):
+        obs, reward, term, trunc, info = env.step(fx["actions"][s], rolls=fx["rolls"][s].reshape(N, 3, 9))
+        assert np.array_equal(obs[0].cpu().numpy(), fx["steps/grid"][s]), s
+        assert np.array_equal(obs[1][1].cpu().numpy(), fx["steps/position"][s]), s
+        assert np.array_equal(obs[1][2].cpu().numpy(), fx["steps/time"][s]), s
+        assert np.array_equal(reward.cpu().numpy(), fx["steps/reward"][s], equal_nan=True), s
+        assert np.array_equal(term.cpu().numpy(), fx["steps/terminated"][s].astype(bool)), s
+        assert np.array_equal(np.asarray(info["repeats"].cpu() if torch.is_tensor(info["repeats"]) else info["repeats"]),
+                              fx["steps/repeats"][s]), s
+
+
 @pytest.mark.parametrize("transport", ["zero_copy", "staged", "pageable"])
 def test_step_host_equals_step_device(cuda_device, transport):
     """gca_env_step_host (host buffers in / out) gives the states and results of the device call, on each of its

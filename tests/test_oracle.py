@@ -394,6 +394,33 @@ def test_oracle_reproduces_reference_source_golden(name):
     assert (fx["steps/is_night"] == 1).any() and fx["steps/dousing"].any()
 
 
+def test_v3_oracle_reproduces_reference_source_golden():
+    """v3 rule set: the reference's own WindyForestFire / Move / Modify / RepeatCA / MDP operators (NumPy + scipy,
+    run through the gymnasium stand-in) stepped for 40 steps on 4 grids of 32x48 with recorded wind rolls; the
+    oracle's v3_env_step must give the same grid, position, clock, reward, done flag and CA-update count."""
+    import ref_golden_util as R
+    from oracle import windy
+    fx = R.load_case("v3_32x48")
+    N, H, W = fx["grid0"].shape
+    tm, ts, ta = fx["t_move_shoot_any"]
+    C = windy.V3Constants(H, W, t_any=float(ta), t_move=float(tm), t_shoot=float(ts))
+    assert np.array_equal(fx["wind"], windy.DEFAULT_WIND)
+    grid, pos, time = fx["grid0"].astype(np.int64), fx["position0"].copy(), fx["time0"].copy()
+    for s in range(fx["actions"].shape[0]):
+        for e in range(N):
+            if fx["frozen"][s, e]:
+                continue
+            g, p, t, r, d, rep = windy.v3_env_step(C, grid[e], pos[e], time[e], fx["actions"][s, e], fx["wind"],
+                                                   fx["rolls"][s, e])
+            grid[e], pos[e], time[e] = g, p, t
+            assert np.array_equal(g, fx["steps/grid"][s, e]), (s, e)
+            assert np.array_equal(p, fx["steps/position"][s, e]) and t == fx["steps/time"][s, e], (s, e)
+            want = fx["steps/reward"][s, e]
+            assert r == want or (np.isnan(r) and np.isnan(want)), (s, e)
+            assert d == bool(fx["steps/terminated"][s, e]) and rep == int(fx["steps/repeats"][s, e]), (s, e)
+    assert {0, 1, 2} <= set(fx["steps/repeats"].ravel().tolist())
+
+
 def test_reference_source_runs_live_under_the_shim():
     """Where the reference tree exists (this container, not the GPU box): import its env through the shim, run a
     short 16x16 rollout and replay the oracle on it -- the generator of the fixtures above, exercised end to end."""
