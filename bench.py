@@ -282,10 +282,6 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    if sampler:
-        # NVML queries take driver locks that the per-step launch + synchronize of this loop then waits on (measured:
-        # +20 us per step at the 2 ms period): the wall-clocked loop is sampled every 10 ms instead
-        sampler.period = float(os.environ.get("GCA_BENCH_E2E_SAMPLER_PERIOD", "0.01"))
     t0 = time.perf_counter()
     for i in range(args.steps):
         # one C call per step: the kernel reads this step's actions from the pinned host buffer and stores reward +

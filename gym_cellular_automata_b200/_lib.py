@@ -165,11 +165,12 @@ def check(rc: int, what: str = "") -> None:
         raise GcaError(f"{what or 'libgca'} failed (status {rc}): {msg}")
 
 
-def ptr(t, dtype=None, numel=None, name="tensor"):
-    """Raw device address of a contiguous CUDA tensor (None -> NULL)."""
+def ptr(t, dtype=None, numel=None, name="tensor", allow_pinned=False):
+    """Raw device address of a contiguous CUDA tensor (None -> NULL).  ``allow_pinned``: a pinned host tensor is
+    accepted as well -- its pages are mapped into the device's address space, a kernel reads them over the bus."""
     if t is None:
         return None
-    if not t.is_cuda:
+    if not t.is_cuda and not (allow_pinned and t.is_pinned()):
         raise GcaError(f"{name}: expected a CUDA tensor (libgca has no CPU path)")
     if not t.is_contiguous():
         raise GcaError(f"{name}: tensor must be contiguous")

@@ -46,7 +46,8 @@ class EpisodeStatistics:
                obs_night: torch.Tensor, truncated: torch.Tensor | None = None) -> "EpisodeStatistics":
         """One rollout step: ``actions`` (N,3) int32, ``step_reward`` = info["reward"] (N,) float32,
         ``terminated`` / ``truncated`` (N,) uint8 (or bool), ``obs_night`` (N,) uint8 = is_night of the
-        observation the actions were chosen on.  Call it after the env step, on the same stream."""
+        observation the actions were chosen on.  Call it after the env step, on the same stream.  ``actions`` may be
+        the pinned host tensor handed to ``env.step_host`` (read in place, no copy)."""
         def u8(t):
             return None if t is None else (t.view(torch.uint8) if t.dtype == torch.bool else t)
         terminated, truncated, obs_night = u8(terminated), u8(truncated), u8(obs_night)
@@ -54,7 +55,7 @@ class EpisodeStatistics:
         check(load().gca_episode_stats_update(
             N, C.byref(self._c), ptr(step_reward, torch.float32, N, "step_reward"),
             ptr(terminated, torch.uint8, N, "terminated"), ptr(truncated, torch.uint8, N, "truncated"),
-            ptr(obs_night, torch.uint8, N, "obs_night"), ptr(actions, torch.int32, 3 * N, "actions"),
+            ptr(obs_night, torch.uint8, N, "obs_night"), ptr(actions, torch.int32, 3 * N, "actions", allow_pinned=True),
             current_stream()), "gca_episode_stats_update")
         return self
 

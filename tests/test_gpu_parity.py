@@ -521,8 +521,17 @@ def test_episode_statistics_with_env(cuda_device):
         a = np.stack([rng.integers(0, 9, 16), rng.integers(0, 2, 16), rng.integers(0, 3, 16)], 1).astype(np.int32)
         ad = torch.as_tensor(a, device=cuda_device)
         night_before = env._state.is_night.cpu().numpy().copy()
-        out = env.step_device(ad)
-        dev_st.update(ad, out.step_reward, out.terminated, out.obs_night)
+        if step % 2:
+            out = env.step_device(ad)
+            dev_st.update(ad, out.step_reward, out.terminated, out.obs_night)
+        else:  # host rollout loop: pinned actions, read in place by the step kernel and by the statistics kernel
+            if step == 0:
+                h_rew, h_term = env.host_result_buffers()
+            ah = torch.as_tensor(a).pin_memory()
+            env.step_host(ah, h_rew, h_term)
+            out = env._out
+            dev_st.update(ah, out.step_reward, out.terminated, out.obs_night)
+            torch.cuda.synchronize()  # ah is dropped at the end of the iteration
         st = rollout.update(st, a, out.step_reward.cpu().numpy(), out.terminated.cpu().numpy(), np.zeros(16, np.uint8),
                             night_before)
     for k, v in dev_st.as_dict().items():
