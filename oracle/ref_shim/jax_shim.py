@@ -129,6 +129,16 @@ def _fori_loop(lo, hi, body, init):
     return v
 
 
+def _scan(f, init, xs=None, length=None):
+    n = int(length) if xs is None else int(np.asarray(_first_leaf(xs)).shape[0])
+    carry, ys = init, []
+    for i in range(n):
+        x = None if xs is None else _tree_map(lambda a: jnp.asarray(a)[i], xs)
+        carry, y = f(carry, x)
+        ys.append(y)
+    return carry, (None if not ys or ys[0] is None else _tree_stack(ys))
+
+
 def _cond(pred, true_fun, false_fun, *operands):
     return true_fun(*operands) if bool(np.asarray(pred)) else false_fun(*operands)
 
@@ -192,6 +202,7 @@ def build_module():
     lax.dynamic_slice = _dynamic_slice
     lax.fori_loop = _fori_loop
     lax.cond = _cond
+    lax.scan = _scan
     lax.switch = _switch
     jax.lax = lax
     random = types.ModuleType("jax.random")

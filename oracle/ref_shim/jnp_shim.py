@@ -194,6 +194,7 @@ logical_not = _wrap(np.logical_not)
 abs = _wrap(np.abs)  # noqa: A001
 floor = _wrap(np.floor)
 mod = _wrap(np.mod)
+append = _wrap(np.append)
 
 
 def modf(x):

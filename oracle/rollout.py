@@ -1,7 +1,9 @@
 """TEST INFRASTRUCTURE (CPU oracle) -- literal NumPy restatement of the statistics half of
 ``step_env_wrapped`` in /root/reference/gym_cellular_automata/agents/jax_ppo.py:504-655, including
 the serial per-env scan of ``update_recent_stats`` (:543-621).  Only tests / smoke / bench may import it.
-Parity unpinned at this level: the reference's tests hold no fixture for it and JAX cannot run here."""
+Parity status: pinned to the reference's own source -- ``step_env_wrapped`` and ``EpisodeStatistics`` are cut out of
+jax_ppo.py by ``ast`` and executed under oracle/ref_shim (tests/golden/make_reference_golden.py run_rollout_stats);
+tests/test_oracle.py::test_rollout_stats_oracle_reproduces_reference_source_golden replays the recorded steps."""
 import numpy as np
 
 RECENT = 10

@@ -255,22 +255,89 @@ def run_v3(ref_shim_mod, N=4, H=32, W=48, steps=40, seed=31):
         gymnasium_shim.Box.sample = orig_sample
 
 
+def run_rollout_stats(N=37, steps=40, seed=41):
+    """The statistics half of the PPO rollout step: ``step_env_wrapped`` is a closure inside
+    agents/jax_ppo.py:run_rollout_loop (the module itself needs flax.linen / optax / orbax / tensorboard), so its
+    source and the EpisodeStatistics dataclass are cut out of the reference file by ``ast`` at run time and executed
+    under the shim against a stand-in env whose stateless_step / conditional_reset hand back prepared tuples
+    (bursts of more than 10 simultaneous finishes, truncations, day and night)."""
+    import ast
+    import types
+    path = os.path.join(ref_shim.REFERENCE_ROOT, "gym_cellular_automata", "agents", "jax_ppo.py")
+    tree = ast.parse(open(path).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "EpisodeStatistics")
+    loop = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "run_rollout_loop")
+    fn = next(n for n in ast.walk(loop) if isinstance(n, ast.FunctionDef) and n.name == "step_env_wrapped")
+    jax = sys.modules["jax"]
+    jnp = jax.numpy
+    env = types.SimpleNamespace()
+    ns = {"jax": jax, "jnp": jnp, "flax": sys.modules["flax"], "env": env, "IS_FIRE_FIGHTER": True}
+    exec(compile(ast.Module(body=[cls, fn], type_ignores=[]), path, "exec"), ns)
+    Stats, step_env_wrapped = ns["EpisodeStatistics"], ns["step_env_wrapped"]
+    z = lambda n, dt: jnp.zeros(n, dtype=dt)  # noqa: E731  (initial values: jax_ppo.py:486-501)
+    st = Stats(episode_returns=z(N, jnp.float32), episode_lengths=z(N, jnp.int32),
+               returned_episode_returns=z(N, jnp.float32), returned_episode_lengths=z(N, jnp.int32),
+               recent_returns=z(10, jnp.float32), recent_lengths=z(10, jnp.int32),
+               recent_idx=jnp.array(0, dtype=jnp.int32),
+               current_day_correct=z(N, jnp.int32), current_night_correct=z(N, jnp.int32),
+               current_day_steps=z(N, jnp.int32), current_night_steps=z(N, jnp.int32),
+               recent_day_correct=z(10, jnp.int32), recent_night_correct=z(10, jnp.int32),
+               recent_day_steps=z(10, jnp.int32), recent_night_steps=z(10, jnp.int32))
+    rng = np.random.default_rng(seed)
+    fields = [f for f in Stats.__dataclass_fields__]
+    rec = {k: [] for k in ["actions", "reward", "terminated", "truncated", "is_night"] + ["out/" + f for f in fields]}
+    for s in range(steps):
+        p_fin = [0.0, 0.02, 0.5, 1.0][s % 4]
+        actions = rng.integers(0, 3, (N, 3)).astype(np.int32)
+        reward = (-rng.random(N)).astype(np.float32)
+        term = rng.random(N) < p_fin
+        trunc = (rng.random(N) < 0.02) & ~term
+        night = rng.integers(0, 2, N).astype(np.int32)
+        obs = (None, {"per_env_context": {"is_night": jnp.asarray(night)}})
+        info = {"reward": jnp.asarray(reward), "terminated": jnp.asarray(term), "TimeLimit.truncated": jnp.asarray(trunc)}
+        step_tuple = (obs, jnp.asarray(reward), jnp.asarray(term), jnp.asarray(trunc), info)
+        env.stateless_step = lambda a, o, i, _t=step_tuple: _t
+        env.conditional_reset = lambda t, a: t
+        st, _ = step_env_wrapped(st, jnp.asarray(actions), obs, info)
+        for k, v in (("actions", actions), ("reward", reward), ("terminated", term.astype(np.uint8)),
+                     ("truncated", trunc.astype(np.uint8)), ("is_night", night.astype(np.uint8))):
+            rec[k].append(v)
+        for f in fields:
+            rec["out/" + f].append(np.asarray(getattr(st, f)))
+    out = {k: np.stack(v) for k, v in rec.items()}
+    print(f"rollout stats: {steps} steps x {N} envs; finished {int(out['out/amount_finished'][-1])}")
+    return out
+
+
 if __name__ == "__main__":
+    # usage: make_reference_golden.py [--only name[,name...]]   (names: the CASES keys, v3_32x48, rollout_stats);
+    # with --only the other sections of the existing file are kept as they are
     assert ref_shim.available(), "the reference tree is needed to generate these vectors"
-    jax = ref_shim.install(prng.LEGACY)
-    ab = ref_shim.load("forest_fire.bulldozer.advanced_bulldozer")
-    out = {}
     import contextlib
     import io
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_shim_golden.npz")
+    only = set(sys.argv[sys.argv.index("--only") + 1].split(",")) if "--only" in sys.argv else None
+    out = {}
+    if only is not None:
+        old = np.load(path)
+        out = {k: old[k] for k in old.files if k.split("/")[0] not in only}
+    jax = ref_shim.install(prng.LEGACY)
+    ab = ref_shim.load("forest_fire.bulldozer.advanced_bulldozer")
     for name, case in CASES.items():
+        if only is not None and name not in only:
+            continue
         buf = io.StringIO()
         with contextlib.redirect_stdout(buf):  # the reference constructor prints its slope histogram
             res = run_case(name, case, ab, jax.numpy)
         print(buf.getvalue().strip().splitlines()[-1])
         for k, v in res.items():
             out[f"{name}/{k}"] = v
-    for k, v in run_v3(ref_shim).items():
-        out[f"v3_32x48/{k}"] = v
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_shim_golden.npz")
+    jax_shim.set_rng_mode(prng.LEGACY)
+    if only is None or "v3_32x48" in only:
+        for k, v in run_v3(ref_shim).items():
+            out[f"v3_32x48/{k}"] = v
+    if only is None or "rollout_stats" in only:
+        for k, v in run_rollout_stats().items():
+            out[f"rollout_stats/{k}"] = v
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

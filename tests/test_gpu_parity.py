@@ -507,6 +507,23 @@ def test_episode_statistics_parity(cuda_device, N):
             assert np.array_equal(got, want), f"step {step}: {k} differs"
 
 
+def test_episode_statistics_reproduce_reference_source_golden(cuda_device):
+    """gca_episode_stats_update against vectors recorded from the reference's own step_env_wrapped source
+    (tests/golden/make_reference_golden.py run_rollout_stats)."""
+    import ref_golden_util as R
+    from gym_cellular_automata_b200.rollout_stats import EpisodeStatistics
+    fx = R.load_case("rollout_stats")
+    steps, N = fx["actions"].shape[:2]
+    dev_st = EpisodeStatistics(N, cuda_device)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=cuda_device)  # noqa: E731
+    for s in range(steps):
+        dev_st.update(t(fx["actions"][s]), t(fx["reward"][s]), t(fx["terminated"][s]), t(fx["is_night"][s]),
+                      t(fx["truncated"][s]))
+        for k, v in dev_st.as_dict().items():
+            got = v.cpu().numpy()
+            assert np.array_equal(got, fx["out/" + k][s].reshape(got.shape)), f"step {s}: {k} differs"
+
+
 def test_episode_statistics_with_env(cuda_device):
     """Driven by the env's own outputs (step_reward / terminated / obs_night), as the rollout loop would."""
     from gym_cellular_automata_b200.rollout_stats import EpisodeStatistics

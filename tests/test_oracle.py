@@ -421,6 +421,24 @@ def test_v3_oracle_reproduces_reference_source_golden():
     assert {0, 1, 2} <= set(fx["steps/repeats"].ravel().tolist())
 
 
+def test_rollout_stats_oracle_reproduces_reference_source_golden():
+    """Episode statistics: vectors recorded from the reference's own ``step_env_wrapped`` / ``EpisodeStatistics``
+    source (cut out of agents/jax_ppo.py by ast and run under the shim, make_reference_golden.run_rollout_stats);
+    every field, value and dtype, after every step."""
+    import ref_golden_util as R
+    from oracle import rollout
+    fx = R.load_case("rollout_stats")
+    steps, N = fx["actions"].shape[:2]
+    st = rollout.new_stats(N)
+    for s in range(steps):
+        st = rollout.update(st, fx["actions"][s], fx["reward"][s], fx["terminated"][s], fx["truncated"][s],
+                            fx["is_night"][s])
+        for k, v in st.items():
+            want = fx["out/" + k][s]
+            assert np.array_equal(np.asarray(v), want) and np.asarray(v).dtype == want.dtype, (s, k)
+    assert int(fx["out/amount_finished"][-1]) > 100 and fx["truncated"].any()
+
+
 def test_reference_source_runs_live_under_the_shim():
     """Where the reference tree exists (this container, not the GPU box): import its env through the shim, run a
     short 16x16 rollout and replay the oracle on it -- the generator of the fixtures above, exercised end to end."""
