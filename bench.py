@@ -243,6 +243,8 @@ def run_ours(args):
     stats0 = env.stats()
     launches0 = env.kernel_launches
     sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) if rank == 0 else None
+    if os.environ.get("GCA_BENCH_NO_SAMPLER"):  # diagnostics only: the JSON line then has no clocks
+        sampler = None
     if sampler:
         sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]

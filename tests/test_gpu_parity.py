@@ -119,6 +119,33 @@ def test_tiled_partitionable_hidden_off(cuda_device):
     assert nbad == 0, _fmt(reports)
 
 
+def test_full_batch_4096_envs_lockstep(cuda_device):
+    """BASELINE config 2 at its full size: 4096 envs of 64x64, K = 4, hidden layers on -- one full wave of 293 CTAs,
+    the load balancer re-dealing the envs to CTA slots every 8 steps -- in lock step with the C oracle (which steps
+    the whole batch in well under a second on the host cores): every state component of every env after every env
+    step.  Scattered fires give each env its own front; size-independent properties are checked on the whole batch
+    as well (counts = populations of the grid, reward = -f/(t+f+1e-8), done = no fire, only legal transitions)."""
+    from parity_util import make_pair, lockstep, read_cuda_state
+    N = 4096
+    env, co, E, state, info = make_pair(N=N, K=4, mode="legacy", use_hidden=True, seed=9, hidden="random",
+                                        scatter_fire=0.004, fast_slope=True)
+    env.balance_every = 8  # as in bench.py
+    before = read_cuda_state(env)["true_grid"].copy()
+    nbad, reports, stats = lockstep(env, co, state, 18, np.random.default_rng(3))
+    assert nbad == 0, _fmt(reports)
+    assert env._state.order is not None and stats[1] > 50 * N, "no balancing / too few draws for a full-size run"
+    g = read_cuda_state(env)["true_grid"]
+    t, f = (g == 1).sum(axis=(1, 2)), (g == 2).sum(axis=(1, 2))
+    counts = env._out.counts.cpu().numpy()
+    assert np.array_equal(counts[:, 0], t) and np.array_equal(counts[:, 1], f)
+    rew = -(f.astype(np.float32) / ((t + f).astype(np.float32) + np.float32(1e-8)))
+    assert np.array_equal(env._out.step_reward.cpu().numpy(), rew.astype(np.float32))
+    assert np.array_equal(env._out.terminated.cpu().numpy().astype(bool), f == 0)
+    # p_tree = 0: empty stays empty, a tree stays or ignites (or has burnt out since), fire never reverts to tree
+    assert not ((before == 0) & (g != 0)).any() and not ((before == 2) & (g == 1)).any()
+    assert len({g[i].tobytes() for i in range(0, N, 16)}) == N // 16, "every env should have its own grid"
+
+
 def test_large_single_grid_4096(cuda_device):
     """BASELINE config 4: one 4096x4096 grid (R = 10, 21x21 heat window), two env steps."""
     from parity_util import make_pair, lockstep
