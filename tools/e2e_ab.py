@@ -26,6 +26,9 @@ def run(name, f, reps=2):
         for i in range(steps): f(env, i, h_rew, h_term)
         torch.cuda.synchronize(); best.append((time.perf_counter() - t0) / steps * 1e6)
     print("%-52s: %s us" % (name, " / ".join("%.1f" % b for b in best)), flush=True)
+if os.environ.get("E2E_AB_QUICK"):
+    run("step_host zero-copy in + out", lambda e, i, r, t: e.step_host(h_act[i], r, t), reps=3)
+    sys.exit(0)
 run("step_device back to back (no sync, no copies)", lambda e, i, r, t: e.step_device(acts[warm + i]))
 run("step_device + stream sync (no copies)", lambda e, i, r, t: (e.step_device(acts[warm + i]), st.synchronize()))
 run("step_host zero-copy in + out", lambda e, i, r, t: e.step_host(h_act[i], r, t))
