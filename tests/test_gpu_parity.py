@@ -146,6 +146,30 @@ def test_full_batch_4096_envs_lockstep(cuda_device):
     assert len({g[i].tobytes() for i in range(0, N, 16)}) == N // 16, "every env should have its own grid"
 
 
+def test_two_waves_8192_envs_lockstep(cuda_device):
+    """BASELINE config 5's per-GPU share (65536 envs over 8 GPUs = 8192 per GPU): 586 CTAs = two waves of the 64x64
+    kernel, two chunks of the balancer.  Ten env steps in lock step with the C oracle, every env."""
+    from parity_util import make_pair, lockstep
+    env, co, E, state, info = make_pair(N=8192, K=4, mode="legacy", use_hidden=True, seed=10, hidden="random",
+                                        scatter_fire=0.004, fast_slope=True)
+    env.balance_every = 4
+    nbad, reports, stats = lockstep(env, co, state, 10, np.random.default_rng(4))
+    assert nbad == 0, _fmt(reports)
+    order = env._state.order.cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange(8192)), "the dealing must be a permutation of the envs"
+
+
+def test_tiled_many_envs_256(cuda_device):
+    """BASELINE config 3's grid (256x256, R = 6) with enough envs for several waves of tile CTAs (96 envs x 32 tiles):
+    three env steps of K = 2 in lock step with the C oracle."""
+    from parity_util import make_pair, lockstep
+    env, co, E, state, info = make_pair(N=96, size=256, K=2, mode="legacy", use_hidden=True, seed=11, hidden="random",
+                                        scatter_fire=0.003, fast_slope=True)
+    nbad, reports, stats = lockstep(env, co, state, 3, np.random.default_rng(5))
+    assert nbad == 0, _fmt(reports)
+    assert stats[1] > 10000
+
+
 def test_large_single_grid_4096(cuda_device):
     """BASELINE config 4: one 4096x4096 grid (R = 10, 21x21 heat window), two env steps."""
     from parity_util import make_pair, lockstep
