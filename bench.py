@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-hidden", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-obs-leg", action="store_true", help="skip the extra device-timed leg with RGB observations")
     ap.add_argument("--cpu-envs", type=int, default=256, help="envs of the CPU sample (cpu_baseline leg and --impl reference)")
     ap.add_argument("--cpu-steps", type=int, default=1024, help="env steps of the cpu_baseline sample (about 10-20 s of host work)")
     ap.add_argument("--seed", type=int, default=0)
@@ -219,10 +220,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     N, K, size = args.envs_per_gpu, args.substeps, args.size
 
-    def make_env():
+    def make_env(obs_mode="none"):
         e = AdvancedForestFireBulldozerEnv(
             size, size, key=1 + rank, num_envs=N, speed_move=0.12 * 4, speed_act=0.03 * 4, use_hidden=not args.no_hidden,
-            substeps=K, rng_mode=args.rng_mode, seed=args.seed + rank, hidden="random", obs_mode="none", auto_reset=True,
+            substeps=K, rng_mode=args.rng_mode, seed=args.seed + rank, hidden="random", obs_mode=obs_mode, auto_reset=True,
             collect_stats=True, device=dev, balance_every=args.balance_every)
         e.reset()
         return e
@@ -292,6 +293,31 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None  # sampled over the timed loops above (device-timed, L2-warm, end-to-end)
 
+    # ---- reported separately: the same env steps with the RGB observation rendered after each step
+    # (one more launch, gca_render_rgb: +3 B/cell written as uint8, +12 B/cell as the reference's float32 layout)
+    with_obs = {}
+    if not args.no_obs_leg:
+        n_obs = min(args.steps, 64)
+        for mode in ("rgb_u8", "rgb_f32"):
+            env_obs = make_env(mode)
+            for i in range(args.warmup):
+                env_obs.step_device(acts[i])
+            torch.cuda.synchronize()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_obs)]
+            for i in range(n_obs):
+                if flush is not None:
+                    flush.fill_(i & 0xFF)
+                ev[i][0].record()
+                env_obs.step_device(acts[args.warmup + i])
+                rgb = env_obs.observe_device(acts[args.warmup + i])
+                ev[i][1].record()
+            torch.cuda.synchronize()
+            ms_obs = sum(a.elapsed_time(b) for a, b in ev)
+            with_obs[mode] = {"us_per_step": ms_obs / n_obs * 1e3, "steps": n_obs,
+                              "cell_updates_per_s_per_gpu": N * n_obs / (ms_obs * 1e-3) * size * size * K,
+                              "obs_bytes_per_step": int(rgb.numel() * rgb.element_size())}
+            del env_obs, rgb
+
     # ---- episode statistics all-gather (the only collective of the path)
     ep = torch.stack([env._state.steps_elapsed, env._state.reward_accumulated], dim=1).contiguous()
     if world > 1:
@@ -342,7 +368,7 @@ def run_ours(args):
                 "env_steps_per_s": total_envs * args.steps / e2e_s,
                 "h2d_bytes_per_step": int(N * 3 * 4), "d2h_bytes_per_step": int(N * 5),
                 "what": "gca_env_step_host per step, host buffers in and out: the fused step kernel reads the pinned host actions (H2D over the bus, zero-copy) and stores reward + terminated to pinned host memory (D2H), then stream sync; same env steps as the device-timed loop (second env, same seeds and warm-up)"},
-        "gpu_launches": launches, "clocks": clocks,
+        "gpu_launches": launches, "clocks": clocks, "with_observation": with_obs,
         "workload_stats": {"front_cells_per_env_substep": d[0] / sub, "draws_per_env_substep": d[1] / sub,
                            "ignitions_per_env_substep": d[2] / sub, "burnouts_per_env_substep": d[3] / sub,
                            "threshold_cells": int(d[4])},

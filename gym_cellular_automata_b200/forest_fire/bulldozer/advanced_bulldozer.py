@@ -550,6 +550,13 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         self._launch_step(actions_dev, None, auto_reset)
         return self._out
 
+    def observe_device(self, actions_dev: torch.Tensor) -> Optional[torch.Tensor]:
+        """The RGB observation ``stateless_step`` would return for the step just made with ``step_device(actions_dev)``
+        (new grid / position, pre-step dousing marks and day/night, extension channel of the actions); one launch
+        of ``gca_render_rgb`` into a fresh (N,H,W,3) buffer of the env's ``obs_mode`` (None for ``"none"``)."""
+        st, out = self._state, self._out
+        return self._render(st.cell, st.doused, st.position, out.obs_night, actions_dev[:, 2].contiguous())
+
     def host_result_buffers(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """Pinned host (reward, terminated) tensors laid out like the device outputs, for ``step_host``."""
         N = self.num_envs
