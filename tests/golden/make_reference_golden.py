@@ -255,6 +255,43 @@ def run_v3(ref_shim_mod, N=4, H=32, W=48, steps=40, seed=31):
         gymnasium_shim.Box.sample = orig_sample
 
 
+def run_operator_edges(ab, jnp, S=16):
+    """Operator level, exhaustive where it is cheap: the reference env's own ``move_modify`` (MoveModifyJax) for
+    every move x shoot action at every cell of the border ring (+ interior cells) of a 16x16 grid, and its
+    ``time_per_action`` / RepeatCAJax clock arithmetic for every action pair at accumulated times around 1."""
+    jax = sys.modules["jax"]
+    key = jax.random.split(jax.random.PRNGKey(1))[0]
+    env = ab.AdvancedForestFireBulldozerEnv(S, S, key=key, num_envs=1, speed_move=0.48, speed_act=0.12, use_hidden=False)
+    cells = [(r, c) for r in range(S) for c in range(S) if r in (0, 1, S - 2, S - 1) or c in (0, 1, S - 2, S - 1)]
+    cells += [(5, 7), (8, 8)]
+    pos_in, act, pos_out, doused = [], [], [], []
+    grid = jnp.zeros((S, S))
+    for (r, c) in cells:
+        for a0 in range(9):
+            for a1 in range(2):
+                pec = {"dousing_count": jnp.zeros((S, S), dtype=jnp.int32)}
+                _, p, pec2 = env.move_modify(grid, (jnp.array(a0), jnp.array(a1)), jnp.array([r, c]), pec)
+                pos_in.append((r, c)); act.append((a0, a1)); pos_out.append(np.asarray(p))
+                d = np.argwhere(np.asarray(pec2["dousing_count"]) != 0)
+                assert len(d) <= 1
+                doused.append(d[0] if len(d) else np.array([-1, -1]))
+    times_in, times_act, frac = [], [], []
+    obs, _ = env.reset()
+    pec0 = {k: v[0] for k, v in obs[1]["per_env_context"].items()}
+    shared = obs[1]["shared_context"]
+    for t_in in (0.0, 0.5, 0.86, 0.8687916, 0.8687917, 0.87, 0.95, 0.999):
+        for a0 in range(9):
+            for a1 in range(2):
+                _, (_, f) = env.repeater(pec0["true_grid"], (jnp.array(a0), jnp.array(a1)), dict(pec0), shared,
+                                         jnp.asarray(np.float32(t_in)))
+                times_in.append(t_in); times_act.append((a0, a1)); frac.append(np.asarray(f, dtype=np.float32))
+    print(f"operator edges: {len(pos_in)} move/douse cases, {len(frac)} clock cases")
+    return {"size": np.array(S), "pos_in": np.array(pos_in, np.int32), "actions": np.array(act, np.int32),
+            "pos_out": np.stack(pos_out).astype(np.int32), "doused": np.stack(doused).astype(np.int32),
+            "clock_time_in": np.array(times_in, np.float32), "clock_actions": np.array(times_act, np.int32),
+            "clock_frac": np.array(frac, np.float32)}
+
+
 def run_rollout_stats(N=37, steps=40, seed=41):
     """The statistics half of the PPO rollout step: ``step_env_wrapped`` is a closure inside
     agents/jax_ppo.py:run_rollout_loop (the module itself needs flax.linen / optax / orbax / tensorboard), so its
@@ -336,6 +373,13 @@ if __name__ == "__main__":
     if only is None or "v3_32x48" in only:
         for k, v in run_v3(ref_shim).items():
             out[f"v3_32x48/{k}"] = v
+    if only is None or "operator_edges" in only:
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            res = run_operator_edges(ab, jax.numpy)
+        print(buf.getvalue().strip().splitlines()[-1])
+        for k, v in res.items():
+            out[f"operator_edges/{k}"] = v
     if only is None or "rollout_stats" in only:
         for k, v in run_rollout_stats().items():
             out[f"rollout_stats/{k}"] = v

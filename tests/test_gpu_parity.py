@@ -329,6 +329,25 @@ def test_operator_level_api(cuda_device):
     assert np.array_equal(pe["dousing_count"].cpu().numpy(), nctx["dousing_count"])
 
 
+def test_move_douse_cuda_reproduces_reference_source_golden(cuda_device):
+    """gca_move_modify (through MoveModifyCUDA) against the reference's own MoveModifyJax: every action at every cell
+    of the two outer rings of a 16x16 grid (tests/golden/make_reference_golden.py run_operator_edges)."""
+    import ref_golden_util as R
+    from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv
+    fx = R.load_case("operator_edges")
+    S, a = int(fx["size"]), fx["actions"]
+    n = len(a)
+    env = AdvancedForestFireBulldozerEnv(64, 64, key=1, num_envs=4, seed=0, use_hidden=False, obs_mode="none")
+    grid = np.zeros((n, S, S), np.float32)
+    pec = {"dousing_count": np.zeros((n, S, S), np.int32)}
+    _, pos, pec = env.move_modify(grid, (a[:, 0], a[:, 1]), fx["pos_in"], pec)
+    assert np.array_equal(pos.cpu().numpy(), fx["pos_out"])
+    want = np.zeros((n, S, S), np.int32)
+    hit = fx["doused"][:, 0] >= 0
+    want[np.nonzero(hit)[0], fx["doused"][hit, 0], fx["doused"][hit, 1]] = 1
+    assert np.array_equal(pec["dousing_count"].cpu().numpy(), want)
+
+
 def test_env_api_surface(cuda_device):
     """reset / spaces / info keys a jax_ppo-style caller touches (reference agents/jax_ppo.py:708-735,790-791)."""
     from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv

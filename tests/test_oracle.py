@@ -421,6 +421,29 @@ def test_v3_oracle_reproduces_reference_source_golden():
     assert {0, 1, 2} <= set(fx["steps/repeats"].ravel().tolist())
 
 
+def test_move_douse_clock_oracle_reproduces_reference_source_golden():
+    """Operator level, exhaustive: the reference env's own MoveModifyJax for every move x shoot action at every cell of
+    the two outer rings of a 16x16 grid (2052 cases), and its RepeatCAJax clock for every action pair at accumulated
+    times on both sides of the wrap (0.8687916 + 0.13120833 is the float32 boundary at speed-multiplier 4)."""
+    import ref_golden_util as R
+    fx = R.load_case("operator_edges")
+    S = int(fx["size"])
+    a = fx["actions"]
+    new = ax.move(fx["pos_in"], a[:, 0], S, S)
+    assert np.array_equal(new, fx["pos_out"])
+    n = len(a)
+    dc = ax.modify(np.zeros((n, S, S), np.int32), a[:, 1], new)
+    want = np.zeros((n, S, S), np.int32)
+    hit = fx["doused"][:, 0] >= 0
+    want[np.nonzero(hit)[0], fx["doused"][hit, 0], fx["doused"][hit, 1]] = 1
+    assert np.array_equal(dc, want) and np.array_equal(hit, a[:, 1] == 1)
+    E = ax.EnvConstants(S, S, speed_move=0.48, speed_act=0.12)
+    ca = fx["clock_actions"]
+    t = (fx["clock_time_in"] + ((E.movement_timings[ca[:, 0]] + E.shooting_timings[ca[:, 1]]) + E.t_any_f32)).astype(np.float32)
+    assert np.array_equal(np.modf(t)[0].astype(np.float32), fx["clock_frac"])
+    assert (np.modf(t)[1] == 0).any() and (np.modf(t)[1] == 1).any(), "both sides of the wrap"
+
+
 def test_rollout_stats_oracle_reproduces_reference_source_golden():
     """Episode statistics: vectors recorded from the reference's own ``step_env_wrapped`` / ``EpisodeStatistics``
     source (cut out of agents/jax_ppo.py by ast and run under the shim, make_reference_golden.run_rollout_stats);
