@@ -195,16 +195,252 @@ __device__ __forceinline__ int blur_at(const uint8_t* g, int H, int W, int r, in
 __global__ void render_flags_kernel(gca_params P, const uint8_t* __restrict__ cell, uint32_t* flags) {
   const int e = blockIdx.y;
   const int H = P.H, W = P.W;
-  const size_t n = (size_t)H * W;
+  const uint32_t n = (uint32_t)H * (uint32_t)W;  // <= 4096 x 4096: 32-bit index arithmetic
   const uint8_t* g = cell + (size_t)e * n;
   uint32_t fl = 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / W), c = (int)(i % W);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int r = (int)(i / (uint32_t)W), c = (int)(i - (uint32_t)r * (uint32_t)W);
     if (g[i] > 0) fl |= 1u | (r == 0 ? 2u : 0u);
     if (blur_at(g, H, W, r, c) > 0) fl |= 4u | (r == 0 ? 8u : 0u);
   }
   fl = __reduce_or_sync(GCA_FULL, fl);
   if ((threadIdx.x & 31) == 0 && fl) atomicOr(&flags[e], fl);
+}
+
+// One pixel: display value, palette, dousing tint, bulldozer -- the float32 arithmetic of grid_to_rgb
+// (advanced_bulldozer.py:1035-1101), shared by both render kernels.
+__device__ __forceinline__ void render_pixel(int disp, bool ng, bool ds, bool dozer, float& cr, float& cg, float& cb) {
+  if (!ng) {
+    if (disp == 1) { cr = 169.f; cg = 196.f; cb = 153.f; }       // #A9C499
+    else if (disp == 2) { cr = 230.f; cg = 129.f; cb = 129.f; }  // #E68181
+    else { cr = 221.f; cg = 209.f; cb = 211.f; }                 // #DDD1D3
+  } else {
+    if (disp == 1) { cr = 47.f; cg = 79.f; cb = 79.f; }          // #2F4F4F
+    else if (disp == 2) { cr = 139.f; cg = 0.f; cb = 0.f; }      // #8B0000
+    else { cr = 105.f; cg = 105.f; cb = 105.f; }                 // #696969
+  }
+  if (ds) {  // rgb * (1 - 0.75) + tint * 0.75, float32, tint blue by day / orange by night
+    const float tr = ng ? 255.f : 0.f, tg = ng ? 165.f : 0.f, tb = ng ? 0.f : 200.f;
+    cr = __fadd_rn(__fmul_rn(cr, 0.25f), __fmul_rn(tr, 0.75f));
+    cg = __fadd_rn(__fmul_rn(cg, 0.25f), __fmul_rn(tg, 0.75f));
+    cb = __fadd_rn(__fmul_rn(cb, 0.25f), __fmul_rn(tb, 0.75f));
+  }
+  if (dozer) { cr = 0.f; cg = 0.f; cb = 0.f; }
+}
+// extension logic of build_observation_on_extensions for one cell (see render_rgb_kernel)
+__device__ __forceinline__ int render_display(int raw, int blur, int ext, uint32_t fl) {
+  if (ext == 1) return (fl & 1u) ? ((fl & 2u) ? raw : 0) : blur;
+  if (ext == 2) return (fl & 4u) ? ((fl & 8u) ? 0 : blur) : blur;
+  return blur;
+}
+
+// Fast path (W % 4 == 0, H W % 16 == 0): a CTA renders 1024 consecutive cells of one env, each thread 4 cells
+// of a row (one 32-bit load of the grid, one 64-bit load of the dousing board), the pixels are staged in shared
+// memory and leave as fully coalesced 128-bit stores -- the observation is write-bound (3 B or 12 B per cell).
+constexpr int RENDER_CELLS = 1024;
+template <bool U8>
+__global__ void __launch_bounds__(256) render_rgb4_kernel(gca_params P, uint32_t chunks, const uint8_t* __restrict__ cell,
+                                                          const unsigned long long* __restrict__ doused,
+                                                          const int32_t* __restrict__ position,
+                                                          const uint8_t* __restrict__ night,
+                                                          const int32_t* __restrict__ ext_action,
+                                                          const uint8_t* __restrict__ env_mask, int enable_ext,
+                                                          const uint32_t* __restrict__ flags, void* out) {
+  extern __shared__ uint4 stage[];  // U8: 3 x 256 32-bit words; float: 3 x 256 float4
+  const uint32_t e = blockIdx.x / chunks, chunk = blockIdx.x - e * chunks;
+  if (env_mask != nullptr && env_mask[e] == 0) return;
+  const int H = P.H, W = P.W, WW = (W + 63) >> 6;
+  const uint32_t n = (uint32_t)H * (uint32_t)W;
+  const uint32_t c0 = chunk * RENDER_CELLS;
+  const uint32_t ci = c0 + threadIdx.x * 4;
+  if (ci < n) {
+    const int r = (int)(ci / (uint32_t)W), c = (int)(ci - (uint32_t)r * (uint32_t)W);
+    const uint8_t* g = cell + (size_t)e * n;
+    const uint32_t four = *reinterpret_cast<const uint32_t*>(g + ci);
+    const bool ng = night[e] != 0;
+    const int pr = position[2 * e], pc = position[2 * e + 1];
+    const unsigned long long dw = doused[((size_t)e * H + r) * WW + (c >> 6)] >> (c & 63);
+    const int ext = (enable_ext && ext_action) ? ext_action[e] : 0;
+    const uint32_t fl = enable_ext ? flags[e] : 0u;
+    float px[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int disp = (int)((four >> (8 * k)) & 255u);
+      if (enable_ext) disp = render_display(disp, blur_at(g, H, W, r, c + k), ext, fl);
+      render_pixel(disp, ng, (dw >> k) & 1ull, pr == r && pc == c + k, px[3 * k], px[3 * k + 1], px[3 * k + 2]);
+    }
+    if (U8) {
+      uint32_t* s32 = reinterpret_cast<uint32_t*>(stage) + threadIdx.x * 3;
+      uint32_t b[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) b[k] = (uint32_t)(uint8_t)px[k];
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        s32[j] = b[4 * j] | (b[4 * j + 1] << 8) | (b[4 * j + 2] << 16) | (b[4 * j + 3] << 24);
+    } else {
+      float4* s4 = reinterpret_cast<float4*>(stage) + threadIdx.x * 3;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) s4[j] = make_float4(px[4 * j], px[4 * j + 1], px[4 * j + 2], px[4 * j + 3]);
+    }
+  }
+  __syncthreads();
+  const uint32_t cells = min((uint32_t)RENDER_CELLS, n - c0);
+  const size_t first = ((size_t)e * n + c0) * 3;  // first output element of the CTA
+  if (U8) {
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + first);
+    for (uint32_t j = threadIdx.x; j < cells * 3 / 16; j += 256) o[j] = stage[j];
+  } else {
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<float*>(out) + first);
+    for (uint32_t j = threadIdx.x; j < cells * 3 / 4; j += 256) o[j] = stage[j];
+  }
+}
+
+// ---- 16 cells per thread (W % 16 == 0): byte-parallel (SWAR) blur, colours from a per-CTA table --------------
+// 16 cells of row r from column c (c % 16 == 0): byte k of word j = cell c + 4 j + k
+__device__ __forceinline__ uint4 load16(const uint8_t* g, int W, int r, int c) {
+  return *reinterpret_cast<const uint4*>(g + (size_t)r * W + c);
+}
+// blur of those 16 cells, one byte each: S = 3x3 edge-padded sum (<= 18, no carries between bytes),
+// blur = (S >= 5) + (S >= 14); `any` receives a non-zero value iff some blur byte is non-zero
+__device__ __forceinline__ uint4 blur16(const uint8_t* g, int H, int W, int r, int c, uint32_t& any) {
+  const int rm = max(r - 1, 0), rp = min(r + 1, H - 1);
+  const uint4 a = load16(g, W, rm, c), b = load16(g, W, r, c), d = load16(g, W, rp, c);
+  uint32_t V[4] = {a.x + b.x + d.x, a.y + b.y + d.y, a.z + b.z + d.z, a.w + b.w + d.w};
+  const int cl = max(c - 1, 0), cr = min(c + 16, W - 1);
+  const uint32_t vl = (uint32_t)g[(size_t)rm * W + cl] + g[(size_t)r * W + cl] + g[(size_t)rp * W + cl];
+  const uint32_t vr = (uint32_t)g[(size_t)rm * W + cr] + g[(size_t)r * W + cr] + g[(size_t)rp * W + cr];
+  uint32_t out[4];
+  uint32_t acc = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t prev = __funnelshift_l(j ? V[j - 1] : (vl << 24), V[j], 8);   // byte k: V of the cell to the left
+    const uint32_t next = __funnelshift_r(V[j], j < 3 ? V[j + 1] : vr, 8);       // byte k: V of the cell to the right
+    const uint32_t S = V[j] + prev + next;
+    const uint32_t t1 = ((S + 0x7B7B7B7Bu) >> 7) & 0x01010101u;  // S >= 5
+    const uint32_t t2 = ((S + 0x72727272u) >> 7) & 0x01010101u;  // S >= 14
+    out[j] = t1 + t2;
+    acc |= t1;
+  }
+  any = acc;
+  return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+__global__ void __launch_bounds__(256) render_flags16_kernel(gca_params P, const uint8_t* __restrict__ cell,
+                                                             uint32_t* flags) {
+  const int e = blockIdx.y;
+  const int H = P.H, W = P.W;
+  const uint32_t n16 = (uint32_t)H * (uint32_t)W / 16u, w16 = (uint32_t)W / 16u;
+  const uint8_t* g = cell + (size_t)e * H * W;
+  uint32_t fl = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) {
+    const int r = (int)(i / w16), c = (int)(i - (uint32_t)r * w16) * 16;
+    const uint4 raw = load16(g, W, r, c);
+    if (raw.x | raw.y | raw.z | raw.w) fl |= 1u | (r == 0 ? 2u : 0u);
+    uint32_t any;
+    blur16(g, H, W, r, c, any);
+    if (any) fl |= 4u | (r == 0 ? 8u : 0u);
+  }
+  fl = __reduce_or_sync(GCA_FULL, fl);
+  if ((threadIdx.x & 31) == 0 && fl) atomicOr(&flags[e], fl);
+}
+
+constexpr int RENDER16_THREADS = 128;
+constexpr int RENDER16_CELLS = RENDER16_THREADS * 16;
+constexpr int RENDER16_F32_STRIDE = 13;  // float4 per thread in the staging buffer (12 + 1 pad: conflict-free stores)
+template <bool U8>
+__global__ void __launch_bounds__(RENDER16_THREADS) render_rgb16_kernel(
+    gca_params P, uint32_t chunks, const uint8_t* __restrict__ cell, const unsigned long long* __restrict__ doused,
+    const int32_t* __restrict__ position, const uint8_t* __restrict__ night, const int32_t* __restrict__ ext_action,
+    const uint8_t* __restrict__ env_mask, int enable_ext, const uint32_t* __restrict__ flags, void* out) {
+  extern __shared__ uint4 stage[];
+  __shared__ float lut_f[8][3];   // [doused * 4 + min(display value, 3)]
+  __shared__ uint32_t lut_u[8];   // the same colours as 0x00BBGGRR
+  const uint32_t e = blockIdx.x / chunks, chunk = blockIdx.x - e * chunks;
+  if (env_mask != nullptr && env_mask[e] == 0) return;
+  const int H = P.H, W = P.W, WW = (W + 63) >> 6;
+  const uint32_t n = (uint32_t)H * (uint32_t)W;
+  const bool ng = night[e] != 0;
+  if (threadIdx.x < 8) {
+    float cr, cg, cb;
+    render_pixel((int)(threadIdx.x & 3u), ng, threadIdx.x >= 4, false, cr, cg, cb);
+    lut_f[threadIdx.x][0] = cr; lut_f[threadIdx.x][1] = cg; lut_f[threadIdx.x][2] = cb;
+    lut_u[threadIdx.x] = (uint32_t)(uint8_t)cr | ((uint32_t)(uint8_t)cg << 8) | ((uint32_t)(uint8_t)cb << 16);
+  }
+  __syncthreads();
+  const uint32_t c0 = chunk * RENDER16_CELLS;
+  const uint32_t ci = c0 + threadIdx.x * 16;
+  if (ci < n) {
+    const int r = (int)(ci / (uint32_t)W), c = (int)(ci - (uint32_t)r * (uint32_t)W);
+    const uint8_t* g = cell + (size_t)e * n;
+    uint4 disp = load16(g, W, r, c);
+    if (enable_ext) {
+      // channel 0 = blurred grid; extension channel 0 = raw grid (action bit 0), channel 1 = blurred grid (bit 1);
+      // the display channel index is the first row holding a positive extension value, clamped to 1
+      const int ext = ext_action ? ext_action[e] : 0;
+      const uint32_t fl = flags[e];
+      int src;  // 0: raw grid, 1: zeros, 2: blurred grid -- the same for every cell of the env
+      if (ext == 1) src = (fl & 1u) ? ((fl & 2u) ? 0 : 1) : 2;
+      else if (ext == 2) src = (fl & 4u) ? ((fl & 8u) ? 1 : 2) : 2;
+      else src = 2;
+      if (src == 2) { uint32_t any; disp = blur16(g, H, W, r, c, any); }
+      else if (src == 1) disp = make_uint4(0u, 0u, 0u, 0u);
+    }
+    const uint32_t dw = (uint32_t)(doused[((size_t)e * H + r) * WW + (c >> 6)] >> (c & 63)) & 0xFFFFu;
+    const uint32_t dv[4] = {disp.x, disp.y, disp.z, disp.w};
+    if (U8) {
+      uint32_t w[12];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          p[k] = lut_u[(((dw >> (4 * q + k)) & 1u) << 2) | min((dv[q] >> (8 * k)) & 255u, 3u)];
+        w[3 * q] = p[0] | (p[1] << 24);
+        w[3 * q + 1] = (p[1] >> 8) | (p[2] << 16);
+        w[3 * q + 2] = (p[2] >> 16) | (p[3] << 8);
+      }
+      uint4* s = stage + threadIdx.x * 3;
+      s[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      s[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      s[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    } else {
+      float* s = reinterpret_cast<float*>(stage + threadIdx.x * RENDER16_F32_STRIDE);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float f[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float* l = lut_f[(((dw >> (4 * q + k)) & 1u) << 2) | min((dv[q] >> (8 * k)) & 255u, 3u)];
+          f[3 * k] = l[0]; f[3 * k + 1] = l[1]; f[3 * k + 2] = l[2];
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          reinterpret_cast<float4*>(s)[3 * q + j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      }
+    }
+    // the bulldozer's pixel is black
+    const int pr = position[2 * e], pk = position[2 * e + 1] - c;
+    if (pr == r && pk >= 0 && pk < 16) {
+      if (U8) {
+        uint8_t* s = reinterpret_cast<uint8_t*>(stage + threadIdx.x * 3) + 3 * pk;
+        s[0] = 0; s[1] = 0; s[2] = 0;
+      } else {
+        float* s = reinterpret_cast<float*>(stage + threadIdx.x * RENDER16_F32_STRIDE) + 3 * pk;
+        s[0] = 0.f; s[1] = 0.f; s[2] = 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t cells = min((uint32_t)RENDER16_CELLS, n - c0);
+  const size_t first = ((size_t)e * n + c0) * 3;  // first output element of the CTA
+  if (U8) {
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + first);
+    for (uint32_t j = threadIdx.x; j < cells * 3 / 16; j += RENDER16_THREADS) o[j] = stage[j];
+  } else {
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<float*>(out) + first);
+    for (uint32_t j = threadIdx.x; j < cells * 3 / 4; j += RENDER16_THREADS)
+      o[j] = stage[(j / 12u) * RENDER16_F32_STRIDE + j % 12u];
+  }
 }
 
 template <bool U8>
@@ -526,8 +762,44 @@ cudaError_t launch_render(const gca_params& p, int N, const uint8_t* cell, const
     cudaError_t err = cudaMemsetAsync(flags_scratch, 0, sizeof(uint32_t) * N, st);
     if (err != cudaSuccess) return err;
     const size_t per = (size_t)p.H * p.W;
-    dim3 grid((unsigned)min((size_t)64, (per + 255) / 256), (unsigned)N);
-    render_flags_kernel<<<grid, 256, 0, st>>>(p, cell, flags_scratch);
+    if (p.W % 16 == 0 && N <= 65535) {
+      dim3 grid((unsigned)min((size_t)64, (per / 16 + 255) / 256), (unsigned)N);
+      render_flags16_kernel<<<grid, 256, 0, st>>>(p, cell, flags_scratch);
+    } else {
+      dim3 grid((unsigned)min((size_t)64, (per + 255) / 256), (unsigned)N);
+      render_flags_kernel<<<grid, 256, 0, st>>>(p, cell, flags_scratch);
+    }
+  }
+  const size_t per_env = (size_t)p.H * p.W;
+  if (p.W % 16 == 0) {
+    const uint32_t chunks = (uint32_t)((per_env + RENDER16_CELLS - 1) / RENDER16_CELLS);
+    const size_t ctas = (size_t)N * chunks;
+    if (ctas <= 0x7FFFFFFFull) {
+      if (rgb_u8)
+        render_rgb16_kernel<true><<<(unsigned)ctas, RENDER16_THREADS, RENDER16_THREADS * 48, st>>>(
+            p, chunks, cell, (const unsigned long long*)doused, position, night, ext_action, env_mask, enable_ext,
+            flags_scratch, out);
+      else
+        render_rgb16_kernel<false><<<(unsigned)ctas, RENDER16_THREADS, RENDER16_THREADS * RENDER16_F32_STRIDE * 16, st>>>(
+            p, chunks, cell, (const unsigned long long*)doused, position, night, ext_action, env_mask, enable_ext,
+            flags_scratch, out);
+      return cudaGetLastError();
+    }
+  }
+  if (p.W % 4 == 0 && per_env % 16 == 0) {
+    const uint32_t chunks = (uint32_t)((per_env + RENDER_CELLS - 1) / RENDER_CELLS);
+    const size_t ctas = (size_t)N * chunks;
+    if (ctas <= 0x7FFFFFFFull) {
+      if (rgb_u8)
+        render_rgb4_kernel<true><<<(unsigned)ctas, 256, 256 * 12, st>>>(p, chunks, cell, (const unsigned long long*)doused,
+                                                                     position, night, ext_action, env_mask, enable_ext,
+                                                                     flags_scratch, out);
+      else
+        render_rgb4_kernel<false><<<(unsigned)ctas, 256, 256 * 48, st>>>(p, chunks, cell,
+                                                                      (const unsigned long long*)doused, position, night,
+                                                                      ext_action, env_mask, enable_ext, flags_scratch, out);
+      return cudaGetLastError();
+    }
   }
   const unsigned blocks = (unsigned)((n + 255) / 256);
   if (rgb_u8)
