@@ -213,6 +213,8 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         self._rgb = None
         self._scratch = torch.zeros(N, dtype=torch.int32, device=self.device)
         self._actions = torch.zeros((N, 3), dtype=torch.int32, device=self.device)
+        self._shared_ctx = None
+        self._false = None
 
     # ------------------------------------------------------------------------------------------
     # clock helpers (advanced_bulldozer.py:745-777)
@@ -399,13 +401,27 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         }
         return static
 
+    def _shared_context(self):
+        """shared_context (advanced_bulldozer.py:724-731): constants, uploaded once (a host-to-device copy per step
+        would synchronise the rollout loop with the device) and handed out like the reference hands its dict through."""
+        if self._shared_ctx is None:
+            self._shared_ctx = {
+                "winds": torch.as_tensor(self._winds, device=self.device),
+                "p_fire": torch.tensor(self._p_fire, dtype=torch.float32, device=self.device),
+                "p_tree": torch.tensor(self._p_tree, dtype=torch.float32, device=self.device),
+                "p_wind_change": torch.tensor(self._p_wind_change, dtype=torch.float32, device=self.device),
+                "day_length": 400}
+        return dict(self._shared_ctx)
+
+    def _all_false(self):
+        """The (N,) all-False tensor of ``truncated`` (never written: shared between steps)."""
+        if self._false is None:
+            self._false = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+        return self._false
+
     def _context_view(self):
         per_env = _LazyPerEnv(self, self._static_context())
-        shared = {"winds": torch.as_tensor(self._winds, device=self.device),
-                  "p_fire": torch.tensor(self._p_fire, dtype=torch.float32, device=self.device),
-                  "p_tree": torch.tensor(self._p_tree, dtype=torch.float32, device=self.device),
-                  "p_wind_change": torch.tensor(self._p_wind_change, dtype=torch.float32, device=self.device),
-                  "day_length": 400}
+        shared = self._shared_context()
         return {"per_env_context": per_env, "shared_context": shared,
                 "position": self._state.position.clone(), "time": self._state.time.clone()}
 
@@ -422,10 +438,11 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                                     ptr(self._scratch), ptr(self._rgb), current_stream()), "gca_render_rgb")
         return self._rgb
 
-    def _info(self):
+    def _info(self, terminated=None):
         st, out = self._state, self._out
-        return {"reward": out.step_reward.clone(), "terminated": out.terminated.bool(),
-                "TimeLimit.truncated": torch.zeros(self.num_envs, dtype=torch.bool, device=self.device),
+        return {"reward": out.step_reward.clone(),
+                "terminated": out.terminated.bool() if terminated is None else terminated,
+                "TimeLimit.truncated": self._all_false(),
                 "steps_elapsed": st.steps_elapsed.clone(), "reward_accumulated": st.reward_accumulated.clone()}
 
     # ------------------------------------------------------------------------------------------
@@ -499,19 +516,22 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         if self._state is None:
             raise RuntimeError("call reset() first")
         a = action if torch.is_tensor(action) else torch.as_tensor(np.asarray(action))
-        self._actions.copy_(a.to(self.device, non_blocking=True).reshape(self.num_envs, -1)[:, :3])
-        self._launch_step(self._actions, inject)
+        if (a.is_cuda and a.dtype == torch.int32 and a.dim() == 2 and a.shape[0] == self.num_envs and a.shape[1] == 3
+                and a.is_contiguous() and a.device == self._actions.device):
+            acts = a  # already what the kernel reads: no staging copy
+        else:
+            self._actions.copy_(a.to(self.device, non_blocking=True).reshape(self.num_envs, -1)[:, :3])
+            acts = self._actions
+        self._launch_step(acts, inject)
         st, out = self._state, self._out
-        ext = self._actions[:, 2].contiguous()
-        rgb = self._render(st.cell, st.doused, st.position, out.obs_night, ext)
+        rgb = None
+        if self.obs_mode != "none":
+            rgb = self._render(st.cell, st.doused, st.position, out.obs_night, acts[:, 2].contiguous())
         reward = out.reward.clone()
         terminated = out.terminated.bool()
-        truncated = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
-        if self.auto_reset:
-            terminated_out = torch.zeros_like(terminated)
-        else:
-            terminated_out = terminated
-        return (rgb, self._context_view()), reward, terminated_out, truncated, self._info()
+        truncated = self._all_false()
+        terminated_out = truncated if self.auto_reset else terminated
+        return (rgb, self._context_view()), reward, terminated_out, truncated, self._info(terminated)
 
     def conditional_reset(self, step_tuple, action, *, seed=None, options=None):
         """conditional_reset (advanced_bulldozer.py:422-518): restore terminated envs from the
@@ -536,7 +556,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         ninfo = dict(info)
         ninfo["steps_elapsed"] = st.steps_elapsed.clone()
         ninfo["reward_accumulated"] = st.reward_accumulated.clone()
-        return (rgb, self._context_view()), new_reward, torch.zeros_like(terminated), truncated, ninfo
+        return (rgb, self._context_view()), new_reward, self._all_false(), truncated, ninfo
 
     # ------------------------------------------------------------------------------------------
     # stateful / fast paths
