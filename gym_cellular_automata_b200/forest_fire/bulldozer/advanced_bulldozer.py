@@ -215,6 +215,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         self._actions = torch.zeros((N, 3), dtype=torch.int32, device=self.device)
         self._shared_ctx = None
         self._false = None
+        self._host_lazy = None
 
     # ------------------------------------------------------------------------------------------
     # clock helpers (advanced_bulldozer.py:745-777)
@@ -362,6 +363,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         """Load an arbitrary reference-layout state (NumPy or torch arrays) into the packed device
         state.  ``pslope`` (N,H,W,3,3) may be given instead of ``slope``."""
         N, H, W = self.num_envs, self.nrows, self.ncols
+        self._host_lazy = None
         if self._state is None:
             self._version_structs += 1
             self._state = PackedState(N, H, W, self.device, use_hidden=self.use_hidden)
@@ -388,17 +390,19 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                                          ptr(self._snap_reward), None, None, current_stream()), "gca_reward_done")
         self._version += 1
 
-    def _static_context(self):
+    def _static_context(self, sc=None):
         d = self.device
-        st = self._state
-        static = {
-            "wind_index": st.wind_index.clone(), "key": st.key.clone(), "is_night": st.is_night.clone(),
-            "time_step": st.time_step.clone(),
-            "density": _HostLazy(self._density, d), "vegetation": _HostLazy(self._vegitation, d),
-            "altitude": _HostLazy(self._altitude, d),
-            "slope": _HostLazy(self._slope if self._slope is not None
-                               else np.zeros((self.num_envs, self.nrows, self.ncols, 3, 3), np.float32), d),
-        }
+        if sc is None:
+            sc = PackedState.carve_scalars(self._state._scalars.clone(), self.num_envs)
+        if self._host_lazy is None:  # static host arrays, uploaded on first use
+            self._host_lazy = {
+                "density": _HostLazy(self._density, d), "vegetation": _HostLazy(self._vegitation, d),
+                "altitude": _HostLazy(self._altitude, d),
+                "slope": _HostLazy(self._slope if self._slope is not None
+                                   else np.zeros((self.num_envs, self.nrows, self.ncols, 3, 3), np.float32), d)}
+        static = {"wind_index": sc["wind_index"], "key": sc["key"], "is_night": sc["is_night"],
+                  "time_step": sc["time_step"]}
+        static.update(self._host_lazy)
         return static
 
     def _shared_context(self):
@@ -419,11 +423,14 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
             self._false = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         return self._false
 
-    def _context_view(self):
-        per_env = _LazyPerEnv(self, self._static_context())
+    def _context_view(self, sc=None):
+        """The context pytree of the current state.  ``sc``: views of ONE snapshot copy of the per-env scalar block
+        (PackedState.carve_scalars) -- what used to be eight small clones per step."""
+        if sc is None:
+            sc = PackedState.carve_scalars(self._state._scalars.clone(), self.num_envs)
+        per_env = _LazyPerEnv(self, self._static_context(sc))
         shared = self._shared_context()
-        return {"per_env_context": per_env, "shared_context": shared,
-                "position": self._state.position.clone(), "time": self._state.time.clone()}
+        return {"per_env_context": per_env, "shared_context": shared, "position": sc["position"], "time": sc["time"]}
 
     def _render(self, cell, doused, position, night_u8, ext_action, env_mask=None):
         if self.obs_mode == "none":
@@ -438,12 +445,13 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                                     ptr(self._scratch), ptr(self._rgb), current_stream()), "gca_render_rgb")
         return self._rgb
 
-    def _info(self, terminated=None):
+    def _info(self, terminated=None, sc=None, oc=None):
         st, out = self._state, self._out
-        return {"reward": out.step_reward.clone(),
+        return {"reward": out.step_reward.clone() if oc is None else oc["step_reward"],
                 "terminated": out.terminated.bool() if terminated is None else terminated,
                 "TimeLimit.truncated": self._all_false(),
-                "steps_elapsed": st.steps_elapsed.clone(), "reward_accumulated": st.reward_accumulated.clone()}
+                "steps_elapsed": st.steps_elapsed.clone() if sc is None else sc["steps_elapsed"],
+                "reward_accumulated": st.reward_accumulated.clone() if sc is None else sc["reward_accumulated"]}
 
     # ------------------------------------------------------------------------------------------
     # functional API
@@ -527,11 +535,14 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         rgb = None
         if self.obs_mode != "none":
             rgb = self._render(st.cell, st.doused, st.position, out.obs_night, acts[:, 2].contiguous())
-        reward = out.reward.clone()
-        terminated = out.terminated.bool()
+        # two snapshot copies (per-env scalars, step outputs); everything handed out is a view of them
+        sc = PackedState.carve_scalars(st._scalars.clone(), self.num_envs)
+        oc = StepOutputs.carve(out._base.clone(), self.num_envs)
+        reward = oc["reward"]
+        terminated = oc["terminated"].bool()
         truncated = self._all_false()
         terminated_out = truncated if self.auto_reset else terminated
-        return (rgb, self._context_view()), reward, terminated_out, truncated, self._info(terminated)
+        return (rgb, self._context_view(sc)), reward, terminated_out, truncated, self._info(terminated, sc, oc)
 
     def conditional_reset(self, step_tuple, action, *, seed=None, options=None):
         """conditional_reset (advanced_bulldozer.py:422-518): restore terminated envs from the
@@ -553,10 +564,11 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                                            C.byref(self._snapshot.cstruct()), ptr(self._snap_reward),
                                            ptr(new_reward), ptr(mask), current_stream()), "gca_conditional_reset")
         self._version += 1
+        sc = PackedState.carve_scalars(st._scalars.clone(), self.num_envs)
         ninfo = dict(info)
-        ninfo["steps_elapsed"] = st.steps_elapsed.clone()
-        ninfo["reward_accumulated"] = st.reward_accumulated.clone()
-        return (rgb, self._context_view()), new_reward, self._all_false(), truncated, ninfo
+        ninfo["steps_elapsed"] = sc["steps_elapsed"]
+        ninfo["reward_accumulated"] = sc["reward_accumulated"]
+        return (rgb, self._context_view(sc)), new_reward, self._all_false(), truncated, ninfo
 
     # ------------------------------------------------------------------------------------------
     # stateful / fast paths

@@ -40,10 +40,11 @@ class StepOutputs:
     def __init__(self, N: int, device, with_stats: bool = False):
         # reward and terminated share one allocation ([N] f32 followed by [N] u8) so that a host caller
         # gets both with a single device-to-host copy (gca_env_step_host)
-        self._rt = torch.zeros(5 * N, dtype=torch.uint8, device=device)
-        self.reward = self._rt[:4 * N].view(torch.float32)
-        self.terminated = self._rt[4 * N:]
-        self.step_reward = torch.zeros(N, dtype=torch.float32, device=device)
+        # ... and step_reward sits in front of them, so that one copy snapshots all three (carve())
+        self.N = N
+        self._base = torch.zeros(9 * N, dtype=torch.uint8, device=device)
+        v = self.carve(self._base, N)
+        self.step_reward, self.reward, self.terminated = v["step_reward"], v["reward"], v["terminated"]
         self.counts = torch.zeros((N, 2), dtype=torch.int32, device=device)
         self.obs_night = torch.zeros(N, dtype=torch.uint8, device=device)
         self.stats = torch.zeros(8, dtype=torch.int64, device=device) if with_stats else None
@@ -53,6 +54,12 @@ class StepOutputs:
 
     def cstruct(self) -> GcaStepOut:
         return self._c
+
+    @staticmethod
+    def carve(base: torch.Tensor, N: int) -> dict:
+        """Views of a (9 N,) uint8 buffer: step_reward (N,) float32 | reward (N,) float32 | terminated (N,) uint8."""
+        f = base.narrow(0, 0, 8 * N).view(torch.float32)
+        return {"step_reward": f.narrow(0, 0, N), "reward": f.narrow(0, N, N), "terminated": base.narrow(0, 8 * N, N)}
 
 
 class PackedState:
@@ -71,14 +78,9 @@ class PackedState:
                        if (use_hidden and with_pslope) else None)
         self.row_min = torch.full((N, H), -1, dtype=torch.int32, device=d)  # 0xFFFFFFFF
         self.tick = torch.zeros(N, dtype=torch.int32, device=d)
-        self.key = torch.zeros((N, 2), dtype=torch.uint32, device=d)
-        self.wind_index = torch.zeros(N, dtype=torch.int32, device=d)
-        self.position = torch.zeros((N, 2), dtype=torch.int32, device=d)
-        self.time = torch.zeros(N, dtype=torch.float32, device=d)
-        self.time_step = torch.ones(N, dtype=torch.int32, device=d)
-        self.is_night = torch.zeros(N, dtype=torch.int32, device=d)
-        self.steps_elapsed = torch.zeros(N, dtype=torch.float32, device=d)
-        self.reward_accumulated = torch.zeros(N, dtype=torch.float32, device=d)
+        # the per-env scalars live in ONE buffer, so that a rollout loop can snapshot them with one copy
+        self._carve_scalars(torch.zeros(self.scalar_words(N), dtype=torch.int32, device=d))
+        self.time_step.fill_(1)
         tiled = not (H == 64 and W == 64)
         self.scratch_cell = torch.zeros((N, H, W), dtype=torch.uint8, device=d) if tiled else None
         # per-env key schedule + counts (14 words each), then one activity byte per 32x64 tile
@@ -89,6 +91,29 @@ class PackedState:
         # tree / fire bit-boards, the grid representation the 64x64 kernel reads (kept in step with `cell`)
         self.bb = None if tiled else torch.zeros((N, H, self.WW, 2), dtype=torch.int64, device=d)
         self._c = None
+
+    SCALARS = ("wind_index", "is_night", "time_step", "position", "key", "time", "steps_elapsed", "reward_accumulated")
+
+    @staticmethod
+    def scalar_words(N: int) -> int:
+        return 10 * ((N + 3) // 4 * 4)
+
+    @staticmethod
+    def carve_scalars(base: torch.Tensor, N: int) -> dict:
+        """Views of a (scalar_words(N),) int32 buffer: wind_index, is_night, time_step (N,) int32, position (N,2) int32,
+        key (N,2) uint32, time, steps_elapsed, reward_accumulated (N,) float32 -- each block 16-byte aligned."""
+        M = (N + 3) // 4 * 4
+        f = base.view(torch.float32)
+        return {"wind_index": base.narrow(0, 0, N), "is_night": base.narrow(0, M, N), "time_step": base.narrow(0, 2 * M, N),
+                "position": base.narrow(0, 3 * M, 2 * N).view(N, 2),
+                "key": base.narrow(0, 5 * M, 2 * N).view(torch.uint32).view(N, 2),
+                "time": f.narrow(0, 7 * M, N), "steps_elapsed": f.narrow(0, 8 * M, N),
+                "reward_accumulated": f.narrow(0, 9 * M, N)}
+
+    def _carve_scalars(self, base: torch.Tensor) -> None:
+        self._scalars = base
+        for k, v in self.carve_scalars(base, self.N).items():
+            setattr(self, k, v)
 
     _FIELDS = ("cell", "death", "hidden", "doused", "pslope", "row_min", "tick", "key", "wind_index", "position",
                "time", "time_step", "is_night", "steps_elapsed", "reward_accumulated", "scratch_cell", "scratch_u32", "work", "order", "bb")
@@ -107,8 +132,11 @@ class PackedState:
         """Deep copy of the dynamic arrays; hidden / pslope are static and shared by default."""
         o = PackedState.__new__(PackedState)
         o.N, o.H, o.W, o.WW, o.device = self.N, self.H, self.W, self.WW, self.device
+        o._carve_scalars(self._scalars.clone())
         for f in self._FIELDS:
             t = getattr(self, f)
+            if f in self.SCALARS:
+                continue
             if t is None:
                 setattr(o, f, None)
             elif share_static and f in ("hidden", "pslope", "scratch_cell", "scratch_u32", "work", "order"):
