@@ -648,14 +648,16 @@ def test_v3_cuda_reproduces_reference_source_golden(cuda_device):
                               fx["steps/repeats"][s]), s
 
 
+@pytest.mark.parametrize("size", [64, 32])
 @pytest.mark.parametrize("transport", ["zero_copy", "staged", "pageable"])
-def test_step_host_equals_step_device(cuda_device, transport):
+def test_step_host_equals_step_device(cuda_device, transport, size):
     """gca_env_step_host (host buffers in / out) gives the states and results of the device call, on each of its
     transports: pinned buffers read / written by the kernel itself (zero-copy), pinned buffers staged through the
     copy engine (GCA_FLAG_HOST_COPY), and pageable buffers (falls back to staging by itself).  Envs terminate and
     are auto-reset inside the run (reward of the restored grid goes to the host mirror as well)."""
     from parity_util import make_pair
-    envs = [make_pair(N=33, K=4, mode="legacy", use_hidden=True, seed=6)[0] for _ in range(2)]
+    # size 32 runs the tiled kernels, whose host entry point always stages (pinned buffers included)
+    envs = [make_pair(N=33, K=4, mode="legacy", use_hidden=True, seed=6, size=size)[0] for _ in range(2)]
     for env in envs:
         env.auto_reset = True
     rng = np.random.default_rng(1)
