@@ -137,6 +137,7 @@ def load():
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gca_render_rgb.argtypes = [C.POINTER(GcaParams), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gca_render_rgb_actions.argtypes = lib.gca_render_rgb.argtypes
     lib.gca_pack_state.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState)] + [C.c_void_p] * 8
     lib.gca_unpack_state.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState)] + [C.c_void_p] * 4
     lib.gca_balance_order.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -153,7 +154,7 @@ def load():
 
 
 # every symbol include/gca.h declares (tests check the library exports all of them)
-EXPORTS = ("gca_version", "gca_last_error", "gca_params_init", "gca_env_step", "gca_env_step_host", "gca_alexandridis_step",
+EXPORTS = ("gca_version", "gca_last_error", "gca_params_init", "gca_env_step", "gca_env_step_host", "gca_alexandridis_step", "gca_render_rgb_actions",
            "gca_move_modify", "gca_reward_done", "gca_conditional_reset", "gca_render_rgb", "gca_pack_state",
            "gca_unpack_state", "gca_balance_order", "gca_generate_hidden", "gca_episode_stats_update", "gca_windy_env_step", "gca_windy_pack", "gca_windy_unpack",
            "gca_threefry_bits", "gca_threefry_split")

@@ -16,7 +16,7 @@ cudaError_t launch_reward_done(const gca_params&, const gca_state&, float*, uint
 cudaError_t launch_conditional_reset(const gca_params&, const gca_state&, const gca_state&, const float*, float*,
                                      uint8_t*, cudaStream_t);
 cudaError_t launch_render(const gca_params&, int, const uint8_t*, const uint64_t*, const int32_t*, const uint8_t*,
-                          const int32_t*, const uint8_t*, int, int, uint32_t*, void*, cudaStream_t);
+                          const int32_t*, int, const uint8_t*, int, int, uint32_t*, void*, cudaStream_t);
 cudaError_t launch_threefry_bits(const uint32_t*, long long, int, uint32_t*, cudaStream_t);
 cudaError_t launch_threefry_split_part(const uint32_t*, int, uint32_t*, cudaStream_t);
 cudaError_t launch_balance_order(int, const uint32_t*, int32_t*, cudaStream_t);
@@ -289,9 +289,22 @@ int gca_render_rgb(const gca_params* p, int32_t N, const uint8_t* cell, const ui
   if (!p || N <= 0 || !cell || !doused || !position || !night || !rgb_out)
     return fail(GCA_ERR_ARG, "gca_render_rgb: null argument");
   if (enable_extensions && !scratch) return fail(GCA_ERR_ARG, "gca_render_rgb: extensions need a [N] u32 scratch");
-  return check_cuda(gca::launch_render(*p, N, cell, doused, position, night, ext_action, env_mask, enable_extensions,
-                                       rgb_u8, scratch, rgb_out, (cudaStream_t)stream),
+  return check_cuda(gca::launch_render(*p, N, cell, doused, position, night, ext_action, 1, env_mask,
+                                       enable_extensions, rgb_u8, scratch, rgb_out, (cudaStream_t)stream),
                     "render_rgb");
+}
+
+int gca_render_rgb_actions(const gca_params* p, int32_t N, const uint8_t* cell, const uint64_t* doused,
+                           const int32_t* position, const uint8_t* night, const int32_t* actions,
+                           const uint8_t* env_mask, int32_t enable_extensions, int32_t rgb_u8, uint32_t* scratch,
+                           void* rgb_out, void* stream) {
+  if (!p || N <= 0 || !cell || !doused || !position || !night || !rgb_out)
+    return fail(GCA_ERR_ARG, "gca_render_rgb_actions: null argument");
+  if (enable_extensions && !scratch)
+    return fail(GCA_ERR_ARG, "gca_render_rgb_actions: extensions need a [N] u32 scratch");
+  return check_cuda(gca::launch_render(*p, N, cell, doused, position, night, actions ? actions + 2 : nullptr, 3, env_mask,
+                                       enable_extensions, rgb_u8, scratch, rgb_out, (cudaStream_t)stream),
+                    "render_rgb_actions");
 }
 
 int gca_pack_state(const gca_params* p, const gca_state* s, const float* true_grid, const float* fire_age,

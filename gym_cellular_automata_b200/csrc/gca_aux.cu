@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) render_rgb4_kernel(gca_params P, uint32_t
                                                           const unsigned long long* __restrict__ doused,
                                                           const int32_t* __restrict__ position,
                                                           const uint8_t* __restrict__ night,
-                                                          const int32_t* __restrict__ ext_action,
+                                                          const int32_t* __restrict__ ext_action, int ext_stride,
                                                           const uint8_t* __restrict__ env_mask, int enable_ext,
                                                           const uint32_t* __restrict__ flags, void* out) {
   extern __shared__ uint4 stage[];  // U8: 3 x 256 32-bit words; float: 3 x 256 float4
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(256) render_rgb4_kernel(gca_params P, uint32_t
     const bool ng = night[e] != 0;
     const int pr = position[2 * e], pc = position[2 * e + 1];
     const unsigned long long dw = doused[((size_t)e * H + r) * WW + (c >> 6)] >> (c & 63);
-    const int ext = (enable_ext && ext_action) ? ext_action[e] : 0;
+    const int ext = (enable_ext && ext_action) ? ext_action[(size_t)e * ext_stride] : 0;
     const uint32_t fl = enable_ext ? flags[e] : 0u;
     float px[12];
 #pragma unroll
@@ -350,7 +350,7 @@ constexpr int RENDER16_F32_STRIDE = 13;  // float4 per thread in the staging buf
 template <bool U8>
 __global__ void __launch_bounds__(RENDER16_THREADS) render_rgb16_kernel(
     gca_params P, uint32_t chunks, const uint8_t* __restrict__ cell, const unsigned long long* __restrict__ doused,
-    const int32_t* __restrict__ position, const uint8_t* __restrict__ night, const int32_t* __restrict__ ext_action,
+    const int32_t* __restrict__ position, const uint8_t* __restrict__ night, const int32_t* __restrict__ ext_action, int ext_stride,
     const uint8_t* __restrict__ env_mask, int enable_ext, const uint32_t* __restrict__ flags, void* out) {
   extern __shared__ uint4 stage[];
   __shared__ float lut_f[8][3];   // [doused * 4 + min(display value, 3)]
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(RENDER16_THREADS) render_rgb16_kernel(
     if (enable_ext) {
       // channel 0 = blurred grid; extension channel 0 = raw grid (action bit 0), channel 1 = blurred grid (bit 1);
       // the display channel index is the first row holding a positive extension value, clamped to 1
-      const int ext = ext_action ? ext_action[e] : 0;
+      const int ext = ext_action ? ext_action[(size_t)e * ext_stride] : 0;
       const uint32_t fl = flags[e];
       int src;  // 0: raw grid, 1: zeros, 2: blurred grid -- the same for every cell of the env
       if (ext == 1) src = (fl & 1u) ? ((fl & 2u) ? 0 : 1) : 2;
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(RENDER16_THREADS) render_rgb16_kernel(
 template <bool U8>
 __global__ void render_rgb_kernel(gca_params P, int N, const uint8_t* __restrict__ cell,
                                   const unsigned long long* __restrict__ doused, const int32_t* __restrict__ position,
-                                  const uint8_t* __restrict__ night, const int32_t* __restrict__ ext_action,
+                                  const uint8_t* __restrict__ night, const int32_t* __restrict__ ext_action, int ext_stride,
                                   const uint8_t* __restrict__ env_mask, int enable_ext,
                                   const uint32_t* __restrict__ flags, void* out) {
   const int H = P.H, W = P.W, WW = (W + 63) >> 6;
@@ -463,7 +463,7 @@ __global__ void render_rgb_kernel(gca_params P, int N, const uint8_t* __restrict
     // channel 0 = blurred grid; extension channel 0 = raw grid (action bit 0), channel 1 = blurred
     // grid (bit 1); the display channel index is the FIRST ROW holding a positive extension
     // value, clamped to 1 (advanced_bulldozer.py:1028-1032).
-    const int ext = ext_action ? ext_action[e] : 0;
+    const int ext = ext_action ? ext_action[(size_t)e * ext_stride] : 0;
     const uint32_t fl = flags[e];
     const int blur = blur_at(g, H, W, r, c);
     if (ext == 1) {        // bits (1,0): ext0 = raw grid, ext1 = 0
@@ -754,7 +754,7 @@ cudaError_t launch_auto_reset(const gca_params& p, const gca_state& s, const gca
   return cudaGetLastError();
 }
 cudaError_t launch_render(const gca_params& p, int N, const uint8_t* cell, const uint64_t* doused,
-                          const int32_t* position, const uint8_t* night, const int32_t* ext_action,
+                          const int32_t* position, const uint8_t* night, const int32_t* ext_action, int ext_stride,
                           const uint8_t* env_mask, int enable_ext, int rgb_u8, uint32_t* flags_scratch, void* out,
                           cudaStream_t st) {
   const size_t n = (size_t)N * p.H * p.W;
@@ -777,11 +777,11 @@ cudaError_t launch_render(const gca_params& p, int N, const uint8_t* cell, const
     if (ctas <= 0x7FFFFFFFull) {
       if (rgb_u8)
         render_rgb16_kernel<true><<<(unsigned)ctas, RENDER16_THREADS, RENDER16_THREADS * 48, st>>>(
-            p, chunks, cell, (const unsigned long long*)doused, position, night, ext_action, env_mask, enable_ext,
+            p, chunks, cell, (const unsigned long long*)doused, position, night, ext_action, ext_stride, env_mask, enable_ext,
             flags_scratch, out);
       else
         render_rgb16_kernel<false><<<(unsigned)ctas, RENDER16_THREADS, RENDER16_THREADS * RENDER16_F32_STRIDE * 16, st>>>(
-            p, chunks, cell, (const unsigned long long*)doused, position, night, ext_action, env_mask, enable_ext,
+            p, chunks, cell, (const unsigned long long*)doused, position, night, ext_action, ext_stride, env_mask, enable_ext,
             flags_scratch, out);
       return cudaGetLastError();
     }
@@ -792,22 +792,22 @@ cudaError_t launch_render(const gca_params& p, int N, const uint8_t* cell, const
     if (ctas <= 0x7FFFFFFFull) {
       if (rgb_u8)
         render_rgb4_kernel<true><<<(unsigned)ctas, 256, 256 * 12, st>>>(p, chunks, cell, (const unsigned long long*)doused,
-                                                                     position, night, ext_action, env_mask, enable_ext,
+                                                                     position, night, ext_action, ext_stride, env_mask, enable_ext,
                                                                      flags_scratch, out);
       else
         render_rgb4_kernel<false><<<(unsigned)ctas, 256, 256 * 48, st>>>(p, chunks, cell,
                                                                       (const unsigned long long*)doused, position, night,
-                                                                      ext_action, env_mask, enable_ext, flags_scratch, out);
+                                                                      ext_action, ext_stride, env_mask, enable_ext, flags_scratch, out);
       return cudaGetLastError();
     }
   }
   const unsigned blocks = (unsigned)((n + 255) / 256);
   if (rgb_u8)
     render_rgb_kernel<true><<<blocks, 256, 0, st>>>(p, N, cell, (const unsigned long long*)doused, position, night,
-                                                    ext_action, env_mask, enable_ext, flags_scratch, out);
+                                                    ext_action, ext_stride, env_mask, enable_ext, flags_scratch, out);
   else
     render_rgb_kernel<false><<<blocks, 256, 0, st>>>(p, N, cell, (const unsigned long long*)doused, position, night,
-                                                     ext_action, env_mask, enable_ext, flags_scratch, out);
+                                                     ext_action, ext_stride, env_mask, enable_ext, flags_scratch, out);
   return cudaGetLastError();
 }
 cudaError_t launch_episode_stats(int N, const gca_episode_stats& e, const float* step_reward, const uint8_t* terminated,

@@ -432,7 +432,9 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         shared = self._shared_context()
         return {"per_env_context": per_env, "shared_context": shared, "position": sc["position"], "time": sc["time"]}
 
-    def _render(self, cell, doused, position, night_u8, ext_action, env_mask=None):
+    def _render(self, cell, doused, position, night_u8, ext_action, env_mask=None, actions=None):
+        """``ext_action``: (N,) int32 extension ids, or ``actions``: the step's (N,3) int32 CUDA action triples (the
+        kernel then reads the third column itself, gca_render_rgb_actions)."""
         if self.obs_mode == "none":
             return None
         N, H, W = self.num_envs, self.nrows, self.ncols
@@ -440,9 +442,15 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         if self._rgb is None or env_mask is None:
             # a fresh buffer per step keeps earlier observations valid (rollout storage keeps them)
             self._rgb = torch.empty((N, H, W, 3), dtype=torch.uint8 if u8 else torch.float32, device=self.device)
-        check(load().gca_render_rgb(C.byref(self._params), N, ptr(cell), ptr(doused), ptr(position), ptr(night_u8),
-                                    ptr(ext_action), ptr(env_mask), int(self.enable_extensions), int(u8),
-                                    ptr(self._scratch), ptr(self._rgb), current_stream()), "gca_render_rgb")
+        if actions is not None:
+            check(load().gca_render_rgb_actions(C.byref(self._params), N, ptr(cell), ptr(doused), ptr(position),
+                                                ptr(night_u8), ptr(actions, torch.int32, 3 * N, "actions"), ptr(env_mask),
+                                                int(self.enable_extensions), int(u8), ptr(self._scratch),
+                                                ptr(self._rgb), current_stream()), "gca_render_rgb_actions")
+        else:
+            check(load().gca_render_rgb(C.byref(self._params), N, ptr(cell), ptr(doused), ptr(position), ptr(night_u8),
+                                        ptr(ext_action), ptr(env_mask), int(self.enable_extensions), int(u8),
+                                        ptr(self._scratch), ptr(self._rgb), current_stream()), "gca_render_rgb")
         return self._rgb
 
     def _info(self, terminated=None, sc=None, oc=None):
@@ -534,7 +542,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         st, out = self._state, self._out
         rgb = None
         if self.obs_mode != "none":
-            rgb = self._render(st.cell, st.doused, st.position, out.obs_night, acts[:, 2].contiguous())
+            rgb = self._render(st.cell, st.doused, st.position, out.obs_night, None, actions=acts)
         # two snapshot copies (per-env scalars, step outputs); everything handed out is a view of them
         sc = PackedState.carve_scalars(st._scalars.clone(), self.num_envs)
         oc = StepOutputs.carve(out._base.clone(), self.num_envs)
@@ -587,7 +595,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         (new grid / position, pre-step dousing marks and day/night, extension channel of the actions); one launch
         of ``gca_render_rgb`` into a fresh (N,H,W,3) buffer of the env's ``obs_mode`` (None for ``"none"``)."""
         st, out = self._state, self._out
-        return self._render(st.cell, st.doused, st.position, out.obs_night, actions_dev[:, 2].contiguous())
+        return self._render(st.cell, st.doused, st.position, out.obs_night, None, actions=actions_dev)
 
     def host_result_buffers(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """Pinned host (reward, terminated) tensors laid out like the device outputs, for ``step_host``."""

@@ -206,6 +206,13 @@ int gca_render_rgb(const gca_params* p, int32_t N, const uint8_t* cell, const ui
                    const uint8_t* env_mask, int32_t enable_extensions, int32_t rgb_u8,
                    uint32_t* scratch, void* rgb_out, void* stream);
 
+/* The same with the extension id taken from the step's action triples: actions [N][3] int32 (move, shoot,
+ * extension id), i.e. the array handed to gca_env_step -- no gather of the third column needed. */
+int gca_render_rgb_actions(const gca_params* p, int32_t N, const uint8_t* cell, const uint64_t* doused,
+                           const int32_t* position, const uint8_t* night, const int32_t* actions,
+                           const uint8_t* env_mask, int32_t enable_extensions, int32_t rgb_u8,
+                           uint32_t* scratch, void* rgb_out, void* stream);
+
 /* Reference float32/int32 context arrays <-> packed state (device pointers).  fire_age of fire
  * cells must be an integer in [1, 32767]; vegetation / density in [0, 7].  err_flag (device int32,
  * may be NULL) is set non-zero if an input violates that. */
