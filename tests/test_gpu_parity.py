@@ -218,6 +218,31 @@ def test_observation_parity(cuda_device, enable_ext):
         assert np.array_equal(ctx["is_night"].cpu().numpy(), state["per_env_context"]["is_night"])
 
 
+@pytest.mark.parametrize("nrows,ncols,mode", [(40, 36, "rgb_f32"), (30, 30, "rgb_f32"), (32, 80, "rgb_u8"), (40, 36, "rgb_u8")])
+def test_observation_other_widths(cuda_device, nrows, ncols, mode):
+    """The three render kernels: 16 cells per thread (width a multiple of 16: 32x80, several chunks per env), 4 cells per
+    thread (40x36) and one cell per thread (30x30), float32 and uint8 pixels, extensions on, against the oracle."""
+    from oracle import alexandridis as ax
+    from parity_util import make_pair, random_actions, sync
+    N = 5
+    env, co, E, state, info = make_pair(N=N, size=nrows, ncols=ncols, K=1, mode="legacy", use_hidden=True, seed=8,
+                                        obs_mode=mode, enable_extensions=True, scatter_fire=0.02)
+    state["per_env_context"]["is_night"][:] = np.array([0, 1, 0, 1, 1], dtype=np.int32)
+    state["per_env_context"]["dousing_count"][:, 3:6, 10:25] = 1
+    state["per_env_context"]["true_grid"][2, 0, :] = 0.0
+    sync(env, state, as_snapshot=True)
+    o_info = {k: np.zeros(N, np.float32) for k in ("steps_elapsed", "reward_accumulated")}
+    rng = np.random.default_rng(2)
+    for step in range(4):
+        act = random_actions(rng, N)
+        rgb_o, state, reward, term, trunc, o_info = ax.stateless_step(E, act, state, o_info, K=1, enable_extensions=True)
+        obs, r, t, tr, inf = env.stateless_step(act)
+        rgb = obs[0].cpu().numpy()
+        want = rgb_o if mode == "rgb_f32" else rgb_o.astype(np.uint8)
+        assert rgb.dtype == want.dtype and rgb.shape == (N, nrows, ncols, 3)
+        assert np.array_equal(rgb, want), f"step {step}: {np.argwhere(rgb != want)[:4]}"
+
+
 def test_conditional_reset_parity(cuda_device):
     """stateless_step + conditional_reset against the oracle across episode ends: restored grid /
     keys / position / clock, kept time_step / is_night, zeroed info counters, recomputed reward,
