@@ -13,15 +13,21 @@
  *   gca_env_step           jax.vmap(MDP.update) + _award + _is_done    forest_fire/bulldozer/advanced_bulldozer.py:332-399,1103-1133
  *                          (RepeatCAJax.update                         forest_fire/operators/repeat_ca_jax.py:34-71,
  *                           MoveModifyJax.update                       forest_fire/operators/move_modify_jax.py:148-157)
+ *   gca_env_step_host      the same transition as a host rollout loop calls it (host actions in, host reward /
+ *                          terminated out: jax.device_get around stateless_step)   agents/jax_ppo.py:1150-1166
  *   gca_move_modify        MoveJax.update / ModifyJax.update           forest_fire/operators/move_modify_jax.py:39-62,102-114
  *   gca_reward_done        _award / _is_done / count_cells             forest_fire/bulldozer/advanced_bulldozer.py:597-633,941-953
  *   gca_conditional_reset  conditional_reset                           forest_fire/bulldozer/advanced_bulldozer.py:422-518
- *   gca_render_rgb         build_observation_on_extensions/grid_to_rgb forest_fire/bulldozer/advanced_bulldozer.py:988-1101
+ *   gca_render_rgb, gca_render_rgb_actions
+ *                          build_observation_on_extensions/grid_to_rgb forest_fire/bulldozer/advanced_bulldozer.py:988-1101
  *                          + apply_blur/apply_extensions               forest_fire/bulldozer/utils/extension_utils.py:99-195
  *   gca_pack_state / gca_unpack_state   the float32/int32 context pytree of _initial_context_distribution
  *                                                                       forest_fire/bulldozer/advanced_bulldozer.py:690-743
  *   gca_generate_hidden    init_vegetation / init_density / init_altitude / get_slope   forest_fire/bulldozer/utils/init_utils.py:10-116,166-200
  *   gca_episode_stats_update  step_env_wrapped's statistics         agents/jax_ppo.py:504-655
+ *   gca_windy_env_step / gca_windy_pack / gca_windy_unpack   v3 rule set: WindyForestFire.update, RepeatCA, Move / Modify,
+ *                          ForestFireBulldozerEnv reward / done        forest_fire/operators/ca_windy.py:41-139, operators/repeat_ca.py:32-45,
+ *                                                                       operators/move_modify.py:39-94, bulldozer/bulldozer.py:196-203,393-400
  *   gca_threefry_bits / gca_threefry_split   jax.random.bits / split (third-party jax, unpinned; see oracle/prng.py)
  */
 #ifndef GCA_H_
