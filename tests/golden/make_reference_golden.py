@@ -292,6 +292,24 @@ def run_operator_edges(ab, jnp, S=16):
             "clock_frac": np.array(frac, np.float32)}
 
 
+CONSTANT_SIZES = (32, 64, 100, 128, 200, 256, 1024, 4096)
+
+
+def run_constants(ref_shim_mod):
+    """A0: what the reference's PartiallyObservableForestFireJax constructor derives from the grid size (heat kernel
+    up to 21x21, dousing weights, fire-age range) for every BASELINE grid size, and the env's clock constants."""
+    m = ref_shim_mod.load("forest_fire.operators.ca_alexandridis_jax")
+    out = {"sizes": np.array(CONSTANT_SIZES, np.int32)}
+    for s in CONSTANT_SIZES:
+        op = m.PartiallyObservableForestFireJax(s, 0, 1, 2)
+        out[f"{s}/burn_kernel"] = np.asarray(op.burn_kernel, dtype=np.float32)[0, 0]
+        out[f"{s}/dousing_weights"] = np.asarray(op.dousing_weights, dtype=np.float32)
+        out[f"{s}/scalars"] = np.array([op.initial_spread_time, op.fire_age_min, op.fire_age_max, op.burn_kernel_radius],
+                                       dtype=np.float64)
+    print(f"constants: sizes {CONSTANT_SIZES}")
+    return out
+
+
 def run_rollout_stats(N=37, steps=40, seed=41):
     """The statistics half of the PPO rollout step: ``step_env_wrapped`` is a closure inside
     agents/jax_ppo.py:run_rollout_loop (the module itself needs flax.linen / optax / orbax / tensorboard), so its
@@ -347,7 +365,7 @@ def run_rollout_stats(N=37, steps=40, seed=41):
 
 
 if __name__ == "__main__":
-    # usage: make_reference_golden.py [--only name[,name...]]   (names: the CASES keys, v3_32x48, rollout_stats);
+    # usage: make_reference_golden.py [--only name[,name...]]   (names: the CASES keys, v3_32x48, operator_edges, constants, rollout_stats);
     # with --only the other sections of the existing file are kept as they are
     assert ref_shim.available(), "the reference tree is needed to generate these vectors"
     import contextlib
@@ -380,6 +398,9 @@ if __name__ == "__main__":
         print(buf.getvalue().strip().splitlines()[-1])
         for k, v in res.items():
             out[f"operator_edges/{k}"] = v
+    if only is None or "constants" in only:
+        for k, v in run_constants(ref_shim).items():
+            out[f"constants/{k}"] = v
     if only is None or "rollout_stats" in only:
         for k, v in run_rollout_stats().items():
             out[f"rollout_stats/{k}"] = v

@@ -444,6 +444,20 @@ def test_move_douse_clock_oracle_reproduces_reference_source_golden():
     assert (np.modf(t)[1] == 0).any() and (np.modf(t)[1] == 1).any(), "both sides of the wrap"
 
 
+def test_ca_constants_reproduce_reference_source_golden():
+    """A0 for every BASELINE grid size (32 ... 4096, R = 3 ... 10): the oracle's CAConstants against what the reference's
+    own constructor derived (heat kernel, dousing weights, fire-age range), bit for bit; gca_params_init is checked
+    against CAConstants in tests/test_host_api.py."""
+    import ref_golden_util as R
+    fx = R.load_case("constants")
+    for s in fx["sizes"].tolist():
+        c = ax.CAConstants(s)
+        assert np.array_equal(c.burn_kernel, fx[f"{s}/burn_kernel"]), s
+        assert np.array_equal(c.dousing_weights, fx[f"{s}/dousing_weights"]), s
+        assert [c.initial_spread_time, c.fire_age_min, c.fire_age_max, c.radius] == fx[f"{s}/scalars"].tolist(), s
+    assert ax.CAConstants(4096).burn_kernel.shape == (21, 21)
+
+
 def test_rollout_stats_oracle_reproduces_reference_source_golden():
     """Episode statistics: vectors recorded from the reference's own ``step_env_wrapped`` / ``EpisodeStatistics``
     source (cut out of agents/jax_ppo.py by ast and run under the shim, make_reference_golden.run_rollout_stats);
@@ -460,6 +474,46 @@ def test_rollout_stats_oracle_reproduces_reference_source_golden():
             want = fx["out/" + k][s]
             assert np.array_equal(np.asarray(v), want) and np.asarray(v).dtype == want.dtype, (s, k)
     assert int(fx["out/amount_finished"][-1]) > 100 and fx["truncated"].any()
+
+
+@pytest.mark.skipif(not os.environ.get("GCA_SHIM_FUZZ"), reason="opt-in: GCA_SHIM_FUZZ=<number of random cases>")
+def test_reference_source_fuzz():
+    """Opt-in sweep (minutes of CPU, needs /root/reference): random configurations -- grid sizes incl. non-powers of
+    two, 1-3 envs, both stream layouts, hidden layers / extensions / regrowth on and off -- each rolled out with the
+    reference's own source under the shim and replayed by the oracle."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("no reference tree here")
+    import contextlib
+    import io
+    from oracle.ref_shim import jax_shim
+    spec = importlib.util.spec_from_file_location("make_reference_golden",
+                                                  os.path.join(HERE, "golden", "make_reference_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    import ref_golden_util as R
+    saved = {k: sys.modules.get(k) for k in list(sys.modules)
+             if k.split(".")[0] in ("jax", "flax", "gymnasium", "gym_cellular_automata")}
+    rng = np.random.default_rng(int(os.environ.get("GCA_SHIM_FUZZ_SEED", "0")))
+    try:
+        jax = ref_shim.install(prng.LEGACY)
+        ab = ref_shim.load("forest_fire.bulldozer.advanced_bulldozer")
+        for i in range(int(os.environ["GCA_SHIM_FUZZ"])):
+            n = int(rng.integers(1, 4))
+            case = dict(size=int(rng.choice([16, 20, 24, 32, 40])), N=n, steps=int(rng.integers(4, 10)),
+                        mode=int(rng.integers(0, 2)), use_hidden=bool(rng.integers(0, 2)), ext=bool(rng.integers(0, 2)),
+                        seed=1000 + i, scatter=float(rng.choice([0.02, 0.05, 0.1])),
+                        dying_env=(int(rng.integers(0, n)) if rng.random() < 0.5 else None),
+                        p_tree_ca=float(rng.choice([0.0, 0.0, 0.03])))
+            with contextlib.redirect_stdout(io.StringIO()):
+                fx = mg.run_case(f"fuzz{i}", case, ab, jax.numpy)
+            bad = R.replay_oracle(fx, case["mode"], case["ext"], f"fuzz{i} {case}")
+            assert not bad, "\n".join(bad[:20])
+    finally:
+        jax_shim.set_rng_mode(prng.LEGACY)
+        for k in [k for k in sys.modules if k.split(".")[0] in ("jax", "flax", "gymnasium", "gym_cellular_automata")]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
 
 
 def test_reference_source_runs_live_under_the_shim():
