@@ -298,25 +298,28 @@ def run_ours(args):
     with_obs = {}
     if not args.no_obs_leg:
         n_obs = min(args.steps, 64)
-        for mode in ("rgb_u8", "rgb_f32"):
-            env_obs = make_env(mode)
-            for i in range(args.warmup):
-                env_obs.step_device(acts[i])
-            torch.cuda.synchronize()
-            # back to back, one event pair (like value_l2_warm): per-step event pairs would count the host's enqueue
-            # latency between the two launches of a step whenever the device runs dry
-            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            o0.record()
-            for i in range(n_obs):
-                env_obs.step_device(acts[args.warmup + i])
-                rgb = env_obs.observe_device(acts[args.warmup + i])
-            o1.record()
-            torch.cuda.synchronize()
-            ms_obs = o0.elapsed_time(o1)
-            with_obs[mode] = {"us_per_step": ms_obs / n_obs * 1e3, "steps": n_obs, "l2": "warm (back-to-back steps)",
-                              "cell_updates_per_s_per_gpu": N * n_obs / (ms_obs * 1e-3) * size * size * K,
-                              "obs_bytes_per_step": int(rgb.numel() * rgb.element_size())}
-            del env_obs, rgb
+        try:
+            for mode in ("rgb_u8", "rgb_f32"):
+                env_obs = make_env(mode)
+                for i in range(args.warmup):
+                    env_obs.step_device(acts[i])
+                torch.cuda.synchronize()
+                # back to back, one event pair (like value_l2_warm): per-step event pairs would count the host's enqueue
+                # latency between the two launches of a step whenever the device runs dry
+                o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                o0.record()
+                for i in range(n_obs):
+                    env_obs.step_device(acts[args.warmup + i])
+                    rgb = env_obs.observe_device(acts[args.warmup + i])
+                o1.record()
+                torch.cuda.synchronize()
+                ms_obs = o0.elapsed_time(o1)
+                with_obs[mode] = {"us_per_step": ms_obs / n_obs * 1e3, "steps": n_obs, "l2": "warm (back-to-back steps)",
+                                  "cell_updates_per_s_per_gpu": N * n_obs / (ms_obs * 1e-3) * size * size * K,
+                                  "obs_bytes_per_step": int(rgb.numel() * rgb.element_size())}
+                del env_obs, rgb
+        except Exception as exc:  # a reported-separately figure must never take the bench line down
+            with_obs = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- episode statistics all-gather (the only collective of the path)
     ep = torch.stack([env._state.steps_elapsed, env._state.reward_accumulated], dim=1).contiguous()
