@@ -1,7 +1,12 @@
-"""GridSpace: a Space of integer lattices (reference gym_cellular_automata/grid_space.py:11-90):
-``n`` or explicit ``values``, optional per-value ``probs``, ``sample``/``contains``/``__eq__``."""
+"""GridSpace -- the space of integer lattices the envs declare for their grids.
+
+Same public surface as the reference type (gym_cellular_automata/grid_space.py:11-90): built from a number of cell
+states ``n`` (states 0..n-1) or from explicit ``values``, optionally with one sampling probability per state;
+``sample()`` draws an iid lattice of ``shape``, ``contains(x)`` checks shape and state set, two spaces are equal when
+shape and states agree."""
 from __future__ import annotations
 
+import math
 from typing import Optional, Sequence
 
 import numpy as np
@@ -10,43 +15,54 @@ from ._config import TYPE_INT
 from .spaces import Space
 
 
+def _cell_states(n, values, dtype) -> np.ndarray:
+    """Sorted unique cell states from either constructor form."""
+    if values is not None:
+        return np.unique(np.asarray(list(values), dtype=dtype))
+    if n is None:
+        raise ValueError("'n' or 'values' must be provided.")
+    if not n > 0:
+        raise AssertionError("'n' must be a positive integer.")
+    return np.arange(int(n), dtype=dtype)
+
+
 class GridSpace(Space):
     def __init__(self, n: Optional[int] = None, values: Optional[Sequence[int]] = None, shape: tuple = tuple(),
                  probs: Optional[Sequence[float]] = None, dtype=TYPE_INT, seed: Optional[int] = None):
+        if not shape:
+            raise AssertionError("Shape must be a non-empty tuple.")
         super().__init__(shape, dtype, seed)
-        assert shape, "Shape must be a non-empty tuple."
-        if values is not None:
-            self._from_values = True
-            self.values = np.unique(np.array(values, dtype=dtype))
-            self.n = len(self.values)
-        elif n is not None:
-            assert n > 0, "'n' must be a positive integer."
-            self._from_values = False
-            self.n = int(n)
-            self.values = np.arange(self.n, dtype=dtype)
-        else:
-            raise ValueError("'n' or 'values' must be provided.")
-        self.probs = np.repeat(1.0, self.n) / self.n if probs is None else probs
-        assert len(self.values) == len(self.probs), "Unique values do NOT MATCH with assigned probabilities."
-        self.size = int(np.prod(self.shape))
+        self._from_values = values is not None
+        self.values = _cell_states(n, values, dtype)
+        self.n = int(self.values.size)
+        self.probs = np.full(self.n, 1.0 / self.n) if probs is None else probs
+        if len(self.probs) != self.n:
+            raise AssertionError("Unique values do NOT MATCH with assigned probabilities.")
+        self.size = math.prod(self.shape)
 
+    # -- gymnasium.Space protocol ---------------------------------------------------------------------
     def sample(self) -> np.ndarray:
-        return self.np_random.choice(a=self.values, size=self.size, p=self.probs).reshape(self.shape)
+        flat = self.np_random.choice(a=self.values, size=self.size, p=self.probs)
+        return flat.reshape(self.shape)
 
     def contains(self, x) -> bool:
-        if isinstance(x, list):
-            x = np.array(x, dtype=self.dtype)
-        x = np.asarray(x)
-        return set(np.unique(x)).issubset(set(self.values)) and self.shape == x.shape
-
-    def __repr__(self):
-        if self._from_values:
-            return f"GridSpace(values={self.values}, shape={self.shape})"
-        return f"GridSpace(n={self.n}, shape={self.shape})"
-
-    def __eq__(self, other):
-        return isinstance(other, GridSpace) and self.shape == other.shape and bool(np.all(self.values == other.values))
+        lattice = np.asarray(x, dtype=self.dtype) if isinstance(x, list) else np.asarray(x)
+        if lattice.shape != self.shape:
+            return False
+        return bool(np.isin(lattice, self.values).all())
 
     @property
     def is_np_flattenable(self):
         return True
+
+    # -- value semantics -------------------------------------------------------------------------------
+    def __eq__(self, other):
+        if not isinstance(other, GridSpace) or self.shape != other.shape:
+            return False
+        return np.array_equal(self.values, other.values)
+
+    __hash__ = None
+
+    def __repr__(self):
+        what = f"values={self.values}" if self._from_values else f"n={self.n}"
+        return f"GridSpace({what}, shape={self.shape})"
