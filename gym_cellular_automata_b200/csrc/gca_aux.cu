@@ -762,12 +762,16 @@ cudaError_t launch_render(const gca_params& p, int N, const uint8_t* cell, const
     cudaError_t err = cudaMemsetAsync(flags_scratch, 0, sizeof(uint32_t) * N, st);
     if (err != cudaSuccess) return err;
     const size_t per = (size_t)p.H * p.W;
-    if (p.W % 16 == 0 && N <= 65535) {
-      dim3 grid((unsigned)min((size_t)64, (per / 16 + 255) / 256), (unsigned)N);
-      render_flags16_kernel<<<grid, 256, 0, st>>>(p, cell, flags_scratch);
-    } else {
-      dim3 grid((unsigned)min((size_t)64, (per + 255) / 256), (unsigned)N);
-      render_flags_kernel<<<grid, 256, 0, st>>>(p, cell, flags_scratch);
+    // blockIdx.y = env: at most 65535 envs per launch
+    for (int e0 = 0; e0 < N; e0 += 65535) {
+      const unsigned ne = (unsigned)min(65535, N - e0);
+      if (p.W % 16 == 0) {
+        dim3 grid((unsigned)min((size_t)64, (per / 16 + 255) / 256), ne);
+        render_flags16_kernel<<<grid, 256, 0, st>>>(p, cell + (size_t)e0 * per, flags_scratch + e0);
+      } else {
+        dim3 grid((unsigned)min((size_t)64, (per + 255) / 256), ne);
+        render_flags_kernel<<<grid, 256, 0, st>>>(p, cell + (size_t)e0 * per, flags_scratch + e0);
+      }
     }
   }
   const size_t per_env = (size_t)p.H * p.W;
