@@ -31,6 +31,12 @@ import numpy as np  # noqa: E402
 
 ALGO_BYTES_PER_CELL = 7  # read cell u8 + age u16 + hidden u8, write cell u8 + age u16
 ALGO_BYTES_PER_ENV = 64
+# Workload phase (SURVEY 8d asks for a developed fire front): every env made by this file is first stepped
+# PREROLL_HORIZON times in SETUP while env group g (e % PREROLL_GROUPS == g) is force-reset at pre-roll step
+# g * PREROLL_HORIZON / PREROLL_GROUPS (gym_cellular_automata_b200/workload.py), so the batch is a stationary
+# mixture of episode phases whatever --steps / --warmup a driver passes.
+PREROLL_HORIZON = 352
+PREROLL_GROUPS = 16
 
 
 def parse():
@@ -52,6 +58,13 @@ def parse():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--ruleset", default="alexandridis", choices=["alexandridis", "v3"],
                     help="v3 = the registered ForestFireBulldozer256x256-v3 rule set (WindyForestFire), an extra line")
+    ap.add_argument("--preroll", type=int, default=PREROLL_HORIZON,
+                    help="setup: env steps of the phase-desynchronising pre-roll (0 = all envs start in phase from reset)")
+    ap.add_argument("--preroll-groups", type=int, default=PREROLL_GROUPS)
+    ap.add_argument("--config5", action="store_true",
+                    help="also time BASELINE config 5's per-GPU share (8192 envs per GPU); on by default at 8 GPUs")
+    ap.add_argument("--long-run", type=int, default=384,
+                    help="extra device-timed steps after the timed window that state the long-run mean (0 = off)")
     ap.add_argument("--balance-every", type=int, default=8,
                     help="re-deal envs to warps every this many steps by last step's cost (0 = off)")
     return ap.parse_args()
@@ -112,7 +125,9 @@ def run_reference(args):
         "unit": "cell-updates/s", "env_steps_per_s": r["env_steps_per_s"], "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
-        "config": workload_config(args),
+        "config": dict(workload_config(args), cpu_sample_envs_per_step=n_envs,
+                       cpu_sample=f"this arm steps {n_envs} envs per step, not {args.envs_per_gpu}: a bounded sample of the "
+                                  "workload (the dense CPU step costs the same for every env and phase)"),
         "cpu_baseline": {"value": r["cell_updates_per_s"], "unit": "cell-updates/s", "cores": r["threads"],
                          "kind": "port", "sample": sample},
         "e2e": {"value": r["cell_updates_per_s"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0,
@@ -128,6 +143,9 @@ def workload_config(args):
                         f"K={args.substeps} CA sub-steps per env step (speed-multiplier 4), hidden "
                         f"{'off' if args.no_hidden else 'on (synthetic random layers)'}, random actions, auto-reset on",
             "envs_per_gpu": args.envs_per_gpu, "grid": [args.size, args.size], "substeps": args.substeps,
+            "phase": (f"stationary mixture: {args.preroll}-step pre-roll in setup, {args.preroll_groups} env groups force-reset "
+                      f"{args.preroll // max(args.preroll_groups, 1)} steps apart (episode ages spread over one episode)"
+                      if args.preroll > 0 else "all envs in phase from reset"),
             "rng_mode": args.rng_mode, "l2": "flushed between timed steps (256 MiB write)" if not args.no_flush
             else "not flushed", "parallelism": f"env-sharded x{args.gpus}, no data-path collective"}
 
@@ -205,102 +223,154 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.how}
 
 
+def pin_rank_to_cores(local, world):
+    """Give every rank of a node its own slice of the host cores (eight synchronous host loops otherwise share
+    whatever cores the scheduler picks).  Returns (previous affinity, cores now used) or (None, None)."""
+    try:
+        prev = sorted(os.sched_getaffinity(0))
+        per = len(prev) // world
+        if world <= 1 or per < 1:
+            return None, None
+        mine = prev[local * per:(local + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return prev, mine
+    except (AttributeError, OSError):
+        return None, None
+
+
+def timed_steps(env, acts, first, n, flush, torch):
+    """n env steps (acts[first + i]) with one CUDA-event pair each, the L2 flushed before every step (outside the
+    events).  Returns the per-step times in microseconds after a synchronize."""
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+    for i in range(n):
+        if flush is not None:
+            flush.fill_(i & 0xFF)  # evict the env state from the 126 MB L2 (outside the timed events)
+        starts[i].record()
+        env.step_device(acts[first + i])
+        ends[i].record()
+    torch.cuda.synchronize()
+    return np.array([s.elapsed_time(e) * 1e3 for s, e in zip(starts, ends)])
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv
+    from gym_cellular_automata_b200.workload import random_actions, stationary_preroll
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    prev_affinity, my_cores = pin_rank_to_cores(local, world)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    N, K, size = args.envs_per_gpu, args.substeps, args.size
+    K, size = args.substeps, args.size
+    ROLLOUT = 128  # steps per rollout of the reference's trainer (agents/args.py:59): cadence of the statistics all-gather
 
-    def make_env(obs_mode="none"):
+    def make_env(n_envs, obs_mode="none"):
         e = AdvancedForestFireBulldozerEnv(
-            size, size, key=1 + rank, num_envs=N, speed_move=0.12 * 4, speed_act=0.03 * 4, use_hidden=not args.no_hidden,
+            size, size, key=1 + rank, num_envs=n_envs, speed_move=0.12 * 4, speed_act=0.03 * 4, use_hidden=not args.no_hidden,
             substeps=K, rng_mode=args.rng_mode, seed=args.seed + rank, hidden="random", obs_mode=obs_mode, auto_reset=True,
             collect_stats=True, device=dev, balance_every=args.balance_every)
         e.reset()
+        if args.preroll > 0:  # SETUP: stationary, phase-desynchronised mixture (not part of --warmup)
+            stationary_preroll(e, args.preroll, args.preroll_groups, seed=args.seed + rank)
         return e
 
-    env = make_env()
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(args.seed + rank)
-    total = args.warmup + args.steps
-    # synthetic actions for every step, resident in HBM before the timed region
-    acts = torch.stack([torch.randint(0, 9, (total, N), device=dev, generator=gen),
-                        torch.randint(0, 2, (total, N), device=dev, generator=gen),
-                        torch.randint(0, 3, (total, N), device=dev, generator=gen)], dim=-1).to(torch.int32).contiguous()
-    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    def gather_episode_info(e):
+        """The path's only collective (reference agents/jax_ppo.py:1330-1343): all-gather of the per-env episode
+        counters the step kernel maintains (info["steps_elapsed"], info["reward_accumulated"])."""
+        ep = torch.stack([e._state.steps_elapsed, e._state.reward_accumulated], dim=1).contiguous()
+        if world == 1:
+            return ep
+        out = torch.empty((world * ep.shape[0], 2), dtype=ep.dtype, device=dev)
+        dist.all_gather_into_tensor(out, ep)
+        return out
 
-    for i in range(args.warmup):
-        env.step_device(acts[i])
-    torch.cuda.synchronize()
-    stats0 = env.stats()
-    launches0 = env.kernel_launches
+    def measure(n_envs, with_long_run):
+        """Device-timed loop, L2-warm loop and the end-to-end loop for one batch size; the same env steps in all three."""
+        env = make_env(n_envs)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(args.seed + rank)
+        n_long = args.long_run if with_long_run else 0
+        total = args.warmup + args.steps + n_long
+        acts = random_actions(total, n_envs, dev, gen)  # resident in HBM before the timed region
+        for i in range(args.warmup):
+            env.step_device(acts[i])
+        torch.cuda.synchronize()
+        stats0 = env.stats()
+        launches0 = env.kernel_launches
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        us = timed_steps(env, acts, args.warmup, args.steps, flush, torch)
+        if world > 1:
+            dist.barrier()
+        stats1 = env.stats()
+        launches = env.kernel_launches - launches0  # env_step64_kernel per step + the re-balancing sort every few steps
+        us_long = timed_steps(env, acts, args.warmup + args.steps, n_long, flush, torch) if n_long else None
+        stats2 = env.stats()
+        # L2-warm variant: back-to-back launches, one event pair (the steps after the ones above)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            env.step_device(acts[args.warmup + i])
+        e1.record()
+        torch.cuda.synchronize()
+        ms_warm = e0.elapsed_time(e1)
+        del env
+        # ---- end to end through the host API: pinned host actions in, reward/terminated out, per step.  The SAME steps
+        # as the device-timed loop: a second env built from the same seeds, same pre-roll, same warm-up steps
+        env_host = make_env(n_envs)
+        for i in range(args.warmup):
+            env_host.step_device(acts[i])
+        h_act = acts[args.warmup:args.warmup + args.steps].cpu().pin_memory()
+        h_rew, h_term = env_host.host_result_buffers()  # pinned
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n_coll = 0
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            # one C call per step: the kernel reads this step's actions from the pinned host buffer and stores reward +
+            # terminated to the pinned host buffers itself (zero-copy transport); results are valid on return
+            env_host.step_host(h_act[i], h_rew, h_term)
+            if (i + 1) % ROLLOUT == 0 or i + 1 == args.steps:  # end of a rollout: the statistics all-gather
+                gathered = gather_episode_info(env_host)
+                n_coll += 1
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        return {"us": us, "us_long": us_long, "ms_warm": ms_warm, "e2e_s": e2e_s, "launches": launches,
+                "d_stats": (stats1 - stats0).astype(np.float64),
+                "d_stats_long": (stats2 - stats1).astype(np.float64) if n_long else None,
+                "gathered": gathered, "collectives": n_coll}
+
+    N = args.envs_per_gpu
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) if rank == 0 else None
     if os.environ.get("GCA_BENCH_NO_SAMPLER"):  # diagnostics only: the JSON line then has no clocks
         sampler = None
     if sampler:
         sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    for i in range(args.steps):
-        if flush is not None:
-            flush.fill_(i & 0xFF)  # evict the env state from the 126 MB L2 (outside the timed events)
-        starts[i].record()
-        env.step_device(acts[args.warmup + i])
-        ends[i].record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    stats1 = env.stats()
-    launches = env.kernel_launches - launches0  # env_step64_kernel per step + the re-balancing sort every few steps
-    # L2-warm variant: back-to-back launches, one event pair
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        env.step_device(acts[args.warmup + i])
-    e1.record()
-    torch.cuda.synchronize()
-    ms_warm = e0.elapsed_time(e1)
-
-    # ---- end to end through the host API: pinned host actions in, reward/terminated out, per step
-    # The SAME steps as the device-timed loop above (the cost of a step grows with the fire fronts, i.e. with the
-    # episode phase): a second env built from the same seeds, brought to the same state by the same warm-up steps
-    env_host = make_env()
-    for i in range(args.warmup):
-        env_host.step_device(acts[i])
-    h_act = acts[args.warmup:args.warmup + args.steps].cpu().pin_memory()
-    h_rew, h_term = env_host.host_result_buffers()  # pinned
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        # one C call per step: the kernel reads this step's actions from the pinned host buffer and stores reward +
-        # terminated to the pinned host buffers itself (zero-copy transport), then the stream is synchronised
-        env_host.step_host(h_act[i], h_rew, h_term)
-    e2e_s = time.perf_counter() - t0
+    m = measure(N, True)
+    # BASELINE config 5 (65 536 envs of 64x64 over 8 GPUs = 8192 per GPU): timed beside the headline at 8 GPUs
+    m5 = measure(8192, False) if (args.config5 or (world == 8 and N != 8192 and size == 64)) else None
     clocks = sampler.stop() if sampler else None  # sampled over the timed loops above (device-timed, L2-warm, end-to-end)
 
-    # ---- reported separately: the same env steps with the RGB observation rendered after each step
-    # (one more launch, gca_render_rgb: +3 B/cell written as uint8, +12 B/cell as the reference's float32 layout)
+    # ---- reported separately (SURVEY 8d): the same env steps with the RGB observation of each step
     with_obs = {}
     if not args.no_obs_leg:
         n_obs = min(args.steps, 64)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(args.seed + rank)
+        acts = random_actions(args.warmup + n_obs, N, dev, gen)
         try:
             for mode in ("rgb_u8", "rgb_f32"):
-                env_obs = make_env(mode)
+                env_obs = make_env(N, mode)
                 for i in range(args.warmup):
                     env_obs.step_device(acts[i])
                 torch.cuda.synchronize()
@@ -321,20 +391,27 @@ def run_ours(args):
         except Exception as exc:  # a reported-separately figure must never take the bench line down
             with_obs = {"error": f"{type(exc).__name__}: {exc}"}
 
-    # ---- episode statistics all-gather (the only collective of the path)
-    ep = torch.stack([env._state.steps_elapsed, env._state.reward_accumulated], dim=1).contiguous()
-    if world > 1:
-        gathered = torch.empty((world * N, 2), dtype=ep.dtype, device=dev)
-        dist.all_gather_into_tensor(gathered, ep)
-        t = torch.tensor([ms, ms_warm, e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_warm, e2e_s = [float(x) for x in t.tolist()]
-    else:
-        gathered = ep
+    def reduce_ranks(mm):
+        """max over ranks of the three timed regions (+ the per-rank values, for attribution)"""
+        mine = torch.tensor([float(mm["us"].sum()) * 1e-3, mm["ms_warm"], mm["e2e_s"]], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [float(x) for x in mine.tolist()], None
+        allr = torch.empty((world, 3), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        a = allr.cpu().numpy()
+        per_rank = {"device_ms_per_step": [float(x) / args.steps for x in a[:, 0]],
+                    "e2e_us_per_step": [float(x) / args.steps * 1e6 for x in a[:, 2]]}
+        return [float(x) for x in a.max(0)], per_rank
+
+    (ms, ms_warm, e2e_s), per_rank = reduce_ranks(m)
+    red5 = reduce_ranks(m5) if m5 is not None else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    def throughput(n_envs, seconds):
+        return n_envs * world * args.steps / seconds * size * size * K
 
     cells = N * size * size
     total_envs = N * world
@@ -350,35 +427,66 @@ def run_ours(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("env_step64_kernel_bytes_per_launch")
+            tj = json.load(f)
+            traffic, traffic_src = tj.get("env_step64_kernel_bytes_per_launch"), tj.get("source")
     except Exception:
         pass
-    d = (stats1 - stats0).astype(np.float64)
-    sub = max(d[5] * K, 1.0)
+
+    def wl(d):
+        sub = max(d[5] * K, 1.0)
+        return {"front_cells_per_env_substep": d[0] / sub, "draws_per_env_substep": d[1] / sub,
+                "ignitions_per_env_substep": d[2] / sub, "burnouts_per_env_substep": d[3] / sub,
+                "threshold_cells": int(d[4])}
+
+    us = m["us"]
+    step_us = {"mean": float(us.mean()), "min": float(us.min()), "median": float(np.median(us)), "max": float(us.max()),
+               "series": [round(float(x), 2) for x in us[:64]]}
+    workload_stats = wl(m["d_stats"])
+    if m["us_long"] is not None and len(m["us_long"]):
+        lr = float(m["us_long"].mean())
+        workload_stats["long_run"] = dict(wl(m["d_stats_long"]), steps=int(len(m["us_long"])), us_per_step=lr,
+                                          timed_window_over_long_run=float(us.mean()) / lr,
+                                          what="the steps right after the timed window, same timing method: the "
+                                               "stationary mean the timed window must agree with (+-10 %)")
+    gathered = m["gathered"]
     line = {
         "metric": "cell_updates_per_s", "value": cu_s, "unit": "cell-updates/s", "env_steps_per_s": env_steps_s,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 bit-boards + f32 + u32 threefry",
         "data": "synthetic", "config": workload_config(args),
-        "value_l2_warm": total_envs * args.steps / (ms_warm * 1e-3) * size * size * K,
+        "value_l2_warm": throughput(N, ms_warm * 1e-3),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                      "algorithmic_bytes_per_launch": algo_bytes, "launch_us": launch_s * 1e6},
-        "e2e": {"value": total_envs * args.steps / e2e_s * size * size * K, "unit": "cell-updates/s",
+        "e2e": {"value": throughput(N, e2e_s), "unit": "cell-updates/s",
                 "env_steps_per_s": total_envs * args.steps / e2e_s,
                 "h2d_bytes_per_step": int(N * 3 * 4), "d2h_bytes_per_step": int(N * 5),
-                "what": "gca_env_step_host per step, host buffers in and out: the fused step kernel reads the pinned host actions (H2D over the bus, zero-copy) and stores reward + terminated to pinned host memory (D2H), then stream sync; same env steps as the device-timed loop (second env, same seeds and warm-up)"},
-        "gpu_launches": launches, "clocks": clocks, "with_observation": with_obs,
-        "workload_stats": {"front_cells_per_env_substep": d[0] / sub, "draws_per_env_substep": d[1] / sub,
-                           "ignitions_per_env_substep": d[2] / sub, "burnouts_per_env_substep": d[3] / sub,
-                           "threshold_cells": int(d[4])},
+                "collectives_in_timed_region": m["collectives"],
+                "what": "gca_env_step_host per step, host buffers in and out: the fused step kernel reads the pinned host actions (H2D over the bus, zero-copy) and stores reward + terminated to pinned host memory (D2H), results valid on return; the all-gather of the per-env episode counters runs inside this loop every 128 steps (one rollout) and at its end; same env steps as the device-timed loop (second env, same seeds, pre-roll and warm-up)"},
+        "gpu_launches": m["launches"], "clocks": clocks, "step_us": step_us, "with_observation": with_obs,
+        "workload_stats": workload_stats,
         "episode_stats": {"envs": int(gathered.shape[0]), "mean_steps_elapsed": float(gathered[:, 0].mean()),
                           "mean_reward_accumulated": float(gathered[:, 1].mean())},
     }
+    if per_rank is not None:
+        line["per_rank"] = dict(per_rank, host_cores_per_rank=len(my_cores) if my_cores else None)
+    if m5 is not None:
+        (ms5, ms5_warm, e2e5_s), per_rank5 = red5
+        line["config5"] = {"workload": f"BASELINE config 5: {8192 * world} envs of {size}x{size}, 8192 per GPU, same pre-roll",
+                           "value": throughput(8192, ms5 * 1e-3), "ms_per_step": ms5 / args.steps,
+                           "env_steps_per_s": 8192 * world * args.steps / (ms5 * 1e-3),
+                           "e2e": {"value": throughput(8192, e2e5_s), "env_steps_per_s": 8192 * world * args.steps / e2e5_s,
+                                   "collectives_in_timed_region": m5["collectives"]},
+                           "roofline_frac": (ALGO_BYTES_PER_CELL * 8192 * size * size + ALGO_BYTES_PER_ENV * 8192)
+                           / (ms5 * 1e-3 / args.steps) / 1e9 / peak,
+                           "workload_stats": wl(m5["d_stats"]), "per_rank": per_rank5}
     if not args.no_cpu_baseline and world == 1:
+        if prev_affinity:
+            os.sched_setaffinity(0, prev_affinity)
         r = cpu_port_throughput(size, K, args.cpu_envs, args.cpu_steps, 2, args.rng_mode, not args.no_hidden, args.seed)
         line["cpu_baseline"] = {
             "value": r["cell_updates_per_s"], "unit": "cell-updates/s", "cores": r["threads"], "kind": "port",
@@ -434,6 +542,8 @@ def run_v3(args):
 
 def main():
     args = parse()
+    if args.size != 64 and args.preroll == PREROLL_HORIZON:
+        args.preroll = 0  # the pre-roll horizon is one 64x64 episode; other grids start from reset unless told otherwise
     # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner ...) goes to stderr
     sys.stdout.flush()
     real_stdout = os.dup(1)

@@ -57,12 +57,10 @@ constexpr uint32_t S64_HALF_CELL = 4096u / 2u;
 
 struct __align__(16) EnvSmem {
   uint32_t fire32[72 * 4];          // fire rows -4..67, 4 overlapping 32-bit views per row
-  uint32_t dous32[68 * 4];          // doused rows -2..65, same views
+  unsigned long long dous64[68];    // doused rows -2..65 (sparse: the 5x5 window is cut out of the 64-bit rows)
   unsigned long long ign[64];       // ignition accumulator of the sub-step
   unsigned long long burn[64][4];   // rows with burn-outs in this env step: mask, sub-step bit planes 0..2
   unsigned long long listed[64];    // cells that are (or were) on the front list
-  float base[S64_CAP];              // per listed cell: upper bound of (p_h (1+p_veg)) (1+p_den); negative =
-                                    //   dousing nearby, no cheap lower bound (apply: burn-out ticks)
   uint16_t list[S64_CAP];           // front cells: (row << 6) | col
   uint16_t ignlist[S64_IGN_CAP];    // cells ignited so far in this env step: (sub-step << 12) | cell; their fire-age
                                     //   draws are made in one batch at the end of the step (flush_ages)
@@ -72,13 +70,21 @@ struct __align__(16) EnvSmem {
   int cnt;                          // list entries of the current pass
   uint32_t dous_even, dous_odd;     // bit l: some doused cell within 2 rows of row 2l / 2l+1
   int nign;                         // entries on ignlist
+  int chain_done;                   // set (release) by the chain warp when sched rows 0..5 / hot.x, hot.y of this env are written
+  uint32_t tick0;                   // CA tick at the start of this env step (scan items)
+  int nscan;                        // rows whose burn-out ticks must be scanned in this env step: their indices are the
+                                    //   first nscan BYTES of ignlist (which holds no ignitions before apply(0))
+  int pad_;
 };
 static_assert(S64_E >= 1 && S64_E <= 32 && 28 % S64_E == 0, "envs per CTA: a divisor of 28 (28 warps of 72 registers fill an SM)");
 static_assert(sizeof(EnvSmem) % 16 == 0 && offsetof(EnvSmem, burn) % 16 == 0 && offsetof(EnvSmem, hot) % 16 == 0, "128-bit shared accesses");
 
 struct __align__(16) CtaSmem {
   EnvSmem env[S64_E];
-  uint16_t pairs[S64_E][S64_WP];    // (env slot << 11) | (list index << 3) | direction slot (0..7, centre skipped)
+  // warp-private buffer of (front cell, burning direction) draws waiting for a full round, of ANY env of the CTA:
+  uint32_t pairs[S64_E][S64_WP];    // upper bound of the cell's (p_h (1+p_veg)) (1+p_den) (float32 bits rounded UP to a multiple
+                                    //   of 32 ulp) | env slot in the 5 low bits; sign bit: dousing nearby (no cheap lower bound)
+  uint16_t pidx[S64_E][S64_WP];     // (cell << 4) | direction 0..8: the pair is compared with element cell * 9 + direction of uniform(Sburn, (H,W,3,3))
   int nch[32];                      // chunks of each env in the current pass
   int next[4];                      // work-item counter of the pooled phase, per group
 };
@@ -95,6 +101,22 @@ __device__ __forceinline__ int group_sync_or(int group, bool pred) {
       "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %3, 0;\n\tbar.red.or.pred q, %1, %2, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
       : "=r"(r) : "r"(group + 1), "r"(S64_GE * 32), "r"((uint32_t)pred) : "memory");
   return r;
+}
+
+// atomicAdd on a shared-memory int by ONE lane: the CUDA builtin compiles to the warp-aggregated pattern (vote, leader
+// election, popc, shuffle: ~14 instructions); the plain instruction is what is wanted here
+__device__ __forceinline__ int smem_add_ret(int* p, int v) {
+  int old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void smem_st_release(int* p, int v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int smem_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
 }
 
 __device__ __forceinline__ void prefetch_l1(const void* p) {
@@ -185,7 +207,10 @@ __device__ __noinline__ void key_chain_pooled(EnvSmem& ce, const gca_params& P, 
     if (wr) { sc[4] = s0; sc[5] = s1; }
     k0 = n0; k1 = n1;
   }
-  if (wr) { ce.hot.x = k0; ce.hot.y = k1; }
+  if (wr) {
+    ce.hot.x = k0; ce.hot.y = k1;
+    smem_st_release(&ce.chain_done, 1);  // the owner warp of this env waits for it before key_sides
+  }
 }
 __device__ __noinline__ void key_sides(EnvSmem& sm, const gca_params& P, const gca_inject& J, int N, int e,
                                        int lane, int& widx) {
@@ -267,13 +292,15 @@ __device__ __forceinline__ void fire_window(const EnvSmem& sm, int r, int c, uin
   B = wv[3] | (wv[4] << 9) | (wv[5] << 18);
   C = wv[6] | (wv[7] << 9) | (wv[8] << 18);
 }
-// 5x5 doused window: rows r-2..r+2, 5 bits each
+// 5x5 doused window: rows r-2..r+2, 5 bits each (columns c-2..c+2; outside the grid = 0)
 __device__ __forceinline__ uint32_t dous_window(const EnvSmem& sm, int r, int c) {
-  const uint32_t* dw = sm.dous32 + r * 4 + (c >> 4);
-  const int o = (c & 15) + 2;
   uint32_t v = 0;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) v |= ((dw[i * 4] >> o) & 0x1Fu) << (5 * i);
+  for (int i = 0; i < 5; ++i) {
+    const unsigned long long row = sm.dous64[r + i];  // index r - 2 + i + 2
+    const uint32_t bits = (uint32_t)(c >= 2 ? (row >> (c - 2)) : (row << (2 - c))) & 0x1Fu;
+    v |= bits << (5 * i);
+  }
   return v;
 }
 
@@ -362,65 +389,26 @@ __device__ __forceinline__ void prefetch_front(const EnvSmem& sm, const uint8_t*
   }
 }
 
-// One buffered (front cell, burning direction) draw of ANY env of the CTA, in three steps so that the two
-// draws a lane makes per round share one basic block: pair_load (decode, shared / global loads, upper
-// bound of p, threefry counters), the random word (threefry2x32_x2 or the injected field), pair_finish
-// (compare; ignitions are or-ed into that env's accumulator).
-struct PairCtx {
-  EnvSmem* es;
-  uint32_t cell;    // (row << 6) | col
-  uint32_t ds;      // direction slot 0..7
-  float bs;         // stored bound of the cell (sign = dousing nearby)
-  float w, s;       // wind and slope factors of the direction
-  float phi;        // upper bound of the burn probability
-  TfKey key;        // Sburn of the env's current sub-step
-  uint32_t c0, c1;  // threefry counters of the element; `first` tells which output word it is (legacy layout)
-  bool first;
-};
-__device__ __forceinline__ void pair_load(CtaSmem& cs, const float* pslope, int mode, uint32_t ent, bool valid,
-                                          PairCtx& c) {
-  EnvSmem& es = cs.env[ent >> 11];
-  const int t = (ent >> 3) & 255;
-  c.es = &es;
-  c.ds = ent & 7;
-  const uint32_t d = c.ds + (c.ds >> 2);  // direction slot -> 3x3 index (skips the centre)
-  c.cell = es.list[t];
-  const uint4 hot = es.hot;
-  c.s = 1.0f;
-  if (pslope != nullptr && valid) c.s = pslope[((size_t)hot.w * 4096 + c.cell) * 8 + c.ds];
-  c.bs = es.base[t];
-  c.w = es.wind[d];
-  c.key.k0 = hot.x; c.key.k1 = hot.y; c.key.k2 = hot.z;
-  const uint32_t idx = c.cell * 9u + d;
-  if (mode == GCA_RNG_LEGACY) {
-    c.first = idx < S64_HALF_BURN;
-    c.c0 = c.first ? idx : idx - S64_HALF_BURN;
-    c.c1 = c.c0 + S64_HALF_BURN;
-  } else {
-    c.first = true;
-    c.c0 = 0u;
-    c.c1 = idx;
+// A buffered (front cell, burning direction) draw whose uniform fell below the stored upper bound of its burn
+// probability (~2 % of the draws): u < hi (1 - 2^-14) ignites for sure; anything in between -- or any hit next to doused
+// cells -- is re-evaluated with the reference's exact summation order ("threshold cells").  Ignitions are or-ed into the
+// env's accumulator.
+__device__ __forceinline__ void pair_hit(const gca_params& P, const uint8_t* hidden, EnvSmem& es, uint32_t ent,
+                                         uint32_t cell, float w, float sl, float phi, float u, uint32_t& n_thresh) {
+  bool ig = !(ent >> 31) && u < __fmul_rn(phi, S64_SURE);
+  if (!ig) {
+    // threshold cell: the float32 enclosure cannot decide -> reference-order evaluation
+    const int r = cell >> 6, col = cell & 63;
+    int hid = 3 | (3 << 3);
+    if (hidden != nullptr) hid = hidden[(size_t)es.hot.w * 4096 + cell];
+    const float a = P.onep_veg[clip15(hid & 7)];
+    const float b = P.onep_den[clip15((hid >> 3) & 7)];
+    const float base = exact_base(es, P, r, col, a, b);
+    const float p = __fmul_rn(__fmul_rn(base, w), sl);
+    ig = u < p;
+    n_thresh++;
   }
-  c.phi = __fmul_rn(__fmul_rn(fabsf(c.bs), c.w), c.s);
-}
-__device__ __forceinline__ void pair_finish(const gca_params& P, const uint8_t* hidden, const PairCtx& c, bool valid,
-                                            float u, uint32_t env, uint32_t& n_thresh) {
-  if (valid && u < c.phi) {
-    bool ig = c.bs > 0.0f && u < __fmul_rn(c.phi, S64_SURE);
-    if (!ig) {
-      // threshold cell: the float32 enclosure cannot decide -> reference-order evaluation
-      const int r = c.cell >> 6, col = c.cell & 63;
-      int hid = 3 | (3 << 3);
-      if (hidden != nullptr) hid = hidden[(size_t)env * 4096 + c.cell];
-      const float a = P.onep_veg[clip15(hid & 7)];
-      const float b = P.onep_den[clip15((hid >> 3) & 7)];
-      const float base = exact_base(*c.es, P, r, col, a, b);
-      const float p = __fmul_rn(__fmul_rn(base, c.w), c.s);
-      ig = u < p;
-      n_thresh++;
-    }
-    if (ig) atomicOr(reinterpret_cast<uint32_t*>(c.es->ign) + (c.cell >> 5), 1u << (c.cell & 31));
-  }
+  if (ig) atomicOr(reinterpret_cast<uint32_t*>(es.ign) + (cell >> 5), 1u << (cell & 31));
 }
 
 // empty -> tree with probability p_tree (0 in the reference env, so this is a cold path): a dense
@@ -495,6 +483,66 @@ __device__ __forceinline__ void front_masks(unsigned long long t0, unsigned long
   fr1 = t1 & (fh0 | fh1 | shfl64_down1(fh0, lane));
 }
 
+// One round of the burn-out scan of env `es` (pooled work item of sub-step 0): rows rowlist[4 q .. 4 q + 3] -- lane
+// group g = lane / 8 takes one row, each of its lanes 8 cells (one 128-bit load of their burn-out ticks).  Cells that
+// burn out during this env step get their tick cleared (fire_age ends at 0), the row's masks (which cells, bit planes of
+// the sub-step) are parked in es.burn[row] for the owner's apply phases, and the row's new minimum goes to S.row_min
+// (L2: the owner re-reads it after the phase's closing barrier).
+__device__ __noinline__ void scan_round(EnvSmem& es, const gca_state& S, int q, int K, int lane) {
+  const int g = lane >> 3, li = lane & 7;
+  const int nrows = es.nscan;
+  const uint32_t tick0 = es.tick0;
+  const size_t e = es.hot.w;
+  const int ri = 4 * q + g;
+  const bool have = ri < nrows;
+  const int row = have ? (int)reinterpret_cast<const uint8_t*>(es.ignlist)[ri] : 0;
+  uint16_t* const drow = S.death + e * 4096 + row * 64 + 8 * li;
+  uint4 dv = make_uint4(0u, 0u, 0u, 0u);
+  if (have) dv = *reinterpret_cast<const uint4*>(drow);
+  // fire bits of this lane's 8 cells: view k of a row starts at column 16 k - 4
+  const uint32_t fb = have ? (es.fire32[(row + 4) * 4 + (li >> 1)] >> (8 * (li & 1) + 4)) & 0xFFu : 0u;
+  uint32_t w[4] = {dv.x, dv.y, dv.z, dv.w};
+  uint32_t die8 = 0, p0 = 0, p1 = 0, p2 = 0, vmin = 0xFFFFFFFFu;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {  // branch-free: selects and masks only
+    const uint32_t d = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+    const uint32_t r = (d - tick0) & 0xFFFFu;
+    const uint32_t f = (fb >> k) & 1u;
+    const uint32_t x = r < (uint32_t)K ? f : 0u;  // burns out during this env step (at sub-step r)
+    die8 |= x << k;
+    p0 |= (x & r) << k;
+    p1 |= (x & (r >> 1)) << k;
+    p2 |= (x & (r >> 2)) << k;
+    w[k >> 1] &= ~((0u - x) & (0xFFFFu << (16 * (k & 1))));  // burnt-out cell: fire_age ends at 0
+    vmin = min(vmin, (f ^ x) ? tick0 + r : 0xFFFFFFFFu);      // fires that keep burning: earliest burn-out
+  }
+  if (die8) *reinterpret_cast<uint4*>(drow) = make_uint4(w[0], w[1], w[2], w[3]);
+  // the group's first lane collects the 8 packed byte-quadruples (die, plane 0..2) and transposes them into four
+  // 64-bit row masks
+  const uint32_t packed = die8 | (p0 << 8) | (p1 << 16) | (p2 << 24);
+  uint32_t wq[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) wq[k] = __shfl_sync(GCA_FULL, packed, (lane & 24) + k);
+  unsigned long long rowm[4];
+#pragma unroll
+  for (int qq = 0; qq < 4; ++qq) {
+    // inner perm: byte 0 = x.byte[qq], byte 1 = y.byte[qq]; outer perm: bytes a0 a1 b0 b1
+    const uint32_t lo = __byte_perm(__byte_perm(wq[0], wq[1], 0x0040u + qq + (qq << 4)),
+                                    __byte_perm(wq[2], wq[3], 0x0040u + qq + (qq << 4)), 0x5410u);
+    const uint32_t hi = __byte_perm(__byte_perm(wq[4], wq[5], 0x0040u + qq + (qq << 4)),
+                                    __byte_perm(wq[6], wq[7], 0x0040u + qq + (qq << 4)), 0x5410u);
+    rowm[qq] = ((unsigned long long)hi << 32) | lo;
+  }
+  uint32_t newmin = vmin;
+#pragma unroll
+  for (int d = 1; d < 8; d <<= 1) newmin = min(newmin, __shfl_xor_sync(GCA_FULL, newmin, d));
+  if (have && li == 0) {
+    reinterpret_cast<ulonglong2*>(es.burn[row])[0] = make_ulonglong2(rowm[0], rowm[1]);
+    reinterpret_cast<ulonglong2*>(es.burn[row])[1] = make_ulonglong2(rowm[2], rowm[3]);
+    __stcg(S.row_min + e * 64 + row, newmin);
+  }
+}
+
 // S64_TRACE (diagnostic builds only): per-env phase timestamps (SM clock, relative to the warp's start) go to
 // O.stats[8 + 16 e ...]; the caller must have allocated stats with 8 + 32 N words.
 #ifdef S64_TRACE
@@ -537,7 +585,11 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   // optional load-balancing indirection (gca_balance_order): which env this warp owns
   const int e = active ? (S.order != nullptr ? S.order[slot] : slot) : 0;
   EnvSmem& sm = cs.env[warp];
-  uint16_t* const wp = cs.pairs[warp];
+  uint32_t* const wp32 = cs.pairs[warp];  // warp-private pair buffer (and scratch of the owner phases)
+  uint16_t* const wpi = cs.pidx[warp];
+  uint16_t* const wp = reinterpret_cast<uint16_t*>(wp32);
+  if (lane == 0) sm.chain_done = 0;
+  __syncthreads();  // (every warp is here within a few cycles of the launch) the flags are clear before a chain warp can set one
   const int K = P.K, mode = MODE < 0 ? P.rng_mode : MODE;
   const size_t cell_base = (size_t)e * 4096;
   const uint8_t* const hidden = HP == 0 ? nullptr : S.hidden;
@@ -595,7 +647,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       if (pf != nullptr) prefetch_l1(pf);
     }
     if (lane < 16) sm.fire32[lane] = 0u; else sm.fire32[272 + lane - 16] = 0u;   // fire rows -4..-1, 64..67
-    if (lane < 8) sm.dous32[lane] = 0u; else if (lane < 16) sm.dous32[264 + lane - 8] = 0u;  // rows -2,-1,64,65
+    if (lane < 2) sm.dous64[lane] = 0ull; else if (lane < 4) sm.dous64[64 + lane] = 0ull;  // rows -2,-1,64,65
     S64_STAMP(0);
   }
   if (warp >= S64_E - S64_CHAIN_WARPS) {
@@ -616,8 +668,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     S64_STAMP(19);
     sm.ign[2 * lane] = 0ull;
     sm.ign[2 * lane + 1] = 0ull;
-    store_row_views(sm.dous32 + (2 * lane + 2) * 4, dz.x);
-    store_row_views(sm.dous32 + (2 * lane + 3) * 4, dz.y);
+    reinterpret_cast<ulonglong2*>(sm.dous64 + 2)[lane] = dz;  // rows 2 lane, 2 lane + 1
     {
       // which rows have a doused cell within the 5x5 dousing window's reach (2 rows up / down)
       const uint32_t ev = __ballot_sync(GCA_FULL, dz.x != 0ull), od = __ballot_sync(GCA_FULL, dz.y != 0ull);
@@ -654,102 +705,27 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     }
     S64_STAMP(1);
 
-    // ---- burn-out scan, four flagged rows per round: lane group g = lane / 8 takes one row, each of its
-    //      lanes 8 cells (one 128-bit load); the next round's load is issued before this round is processed
+    // ---- rows to scan for burn-outs: the scan itself is POOLED work of sub-step 0 (scan items next to the front-cell
+    //      chunks: every warp of the CTA takes rounds of four rows of whichever env), so an env with many burning
+    //      rows does not hold its owner -- and with it the CTA's first barrier -- back.  The owner only lists the rows.
     {
-      uint32_t* const tmp_rm = reinterpret_cast<uint32_t*>(wp);  // new row minimum of scanned rows
-      const int g = lane >> 3, li = lane & 7;
-      // bit s: row 2s, bit 32 + s: row 2s + 1
-      unsigned long long M = (unsigned long long)__ballot_sync(GCA_FULL, need0) |
-                             ((unsigned long long)__ballot_sync(GCA_FULL, need1) << 32);
-      // take the four lowest flagged rows off M: group g gets the (g+1)-th and requests its 16 bytes
-      auto fetch = [&](bool& have, int& idx, uint4& dv) {
-        unsigned long long mm = M;
-        int pos = -1;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (q == g && mm) pos = __ffsll((long long)mm) - 1;
-          mm &= mm - 1;
-        }
-        M = mm;
-        have = pos >= 0;
-        idx = have ? pos : 0;
-        const int row = 2 * (idx & 31) + (idx >> 5);
-        dv = make_uint4(0u, 0u, 0u, 0u);
-        if (have) dv = *reinterpret_cast<const uint4*>(S.death + cell_base + row * 64 + 8 * li);
-      };
-      bool cur_any = M != 0ull, have;
-      int idx;
-      uint4 dv;
-      fetch(have, idx, dv);
-#pragma unroll 1
-      while (cur_any) {
-        const bool nxt_any = M != 0ull;
-        bool have_n = false;
-        int idx_n = 0;
-        uint4 dv_n = make_uint4(0u, 0u, 0u, 0u);
-        if (nxt_any) fetch(have_n, idx_n, dv_n);
-        const int row = 2 * (idx & 31) + (idx >> 5);
-        // (both rows of the source lane are fetched: the groups of one round may want different parities)
-        const unsigned long long fe = shfl64(f0, idx & 31), fo = shfl64(f1, idx & 31);
-        const unsigned long long frow = (idx >> 5) ? fo : fe;
-        const uint32_t fb = have ? (uint32_t)(frow >> (8 * li)) & 0xFFu : 0u;  // fire bits of this lane's 8 cells
-        uint32_t w[4] = {dv.x, dv.y, dv.z, dv.w};
-        uint32_t die8 = 0, p0 = 0, p1 = 0, p2 = 0, vmin = 0xFFFFFFFFu;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {  // branch-free: selects and masks only
-          const uint32_t d = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-          const uint32_t r = (d - tick0) & 0xFFFFu;
-          const uint32_t f = (fb >> k) & 1u;
-          const uint32_t x = r < (uint32_t)K ? f : 0u;  // burns out during this env step (at sub-step r)
-          die8 |= x << k;
-          p0 |= (x & r) << k;
-          p1 |= (x & (r >> 1)) << k;
-          p2 |= (x & (r >> 2)) << k;
-          w[k >> 1] &= ~((0u - x) & (0xFFFFu << (16 * (k & 1))));  // burnt-out cell: fire_age ends at 0
-          vmin = min(vmin, (f ^ x) ? tick0 + r : 0xFFFFFFFFu);      // fires that keep burning: earliest burn-out
-        }
-        if (die8)
-          *reinterpret_cast<uint4*>(S.death + cell_base + row * 64 + 8 * li) = make_uint4(w[0], w[1], w[2], w[3]);
-        // the group's first lane collects the 8 packed byte-quadruples (die, plane 0..2) and transposes
-        // them into four 64-bit row masks (redux.sync with per-group masks would be serialised)
-        const uint32_t packed = die8 | (p0 << 8) | (p1 << 16) | (p2 << 24);
-        uint32_t wq[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) wq[k] = __shfl_sync(GCA_FULL, packed, (lane & 24) + k);
-        unsigned long long rowm[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          // inner perm: byte 0 = x.byte[q], byte 1 = y.byte[q]; outer perm: bytes a0 a1 b0 b1
-          const uint32_t lo = __byte_perm(__byte_perm(wq[0], wq[1], 0x0040u + q + (q << 4)),
-                                          __byte_perm(wq[2], wq[3], 0x0040u + q + (q << 4)), 0x5410u);
-          const uint32_t hi = __byte_perm(__byte_perm(wq[4], wq[5], 0x0040u + q + (q << 4)),
-                                          __byte_perm(wq[6], wq[7], 0x0040u + q + (q << 4)), 0x5410u);
-          rowm[q] = ((unsigned long long)hi << 32) | lo;
-        }
-        uint32_t newmin = vmin;
-#pragma unroll
-        for (int d = 1; d < 8; d <<= 1) newmin = min(newmin, __shfl_xor_sync(GCA_FULL, newmin, d));
-        if (have && li == 0) {
-          reinterpret_cast<ulonglong2*>(sm.burn[row])[0] = make_ulonglong2(rowm[0], rowm[1]);
-          reinterpret_cast<ulonglong2*>(sm.burn[row])[1] = make_ulonglong2(rowm[2], rowm[3]);
-          tmp_rm[row] = newmin;
-        }
-        have = have_n; idx = idx_n; dv = dv_n; cur_any = nxt_any;
-      }
-      __syncwarp();
-      S64_STAMP(2);
-      if (need0) rm.x = tmp_rm[2 * lane];
-      if (need1) rm.y = tmp_rm[2 * lane + 1];
-      __syncwarp();
+      const uint32_t Me = __ballot_sync(GCA_FULL, need0), Mo = __ballot_sync(GCA_FULL, need1);
+      const uint32_t lt = (1u << lane) - 1u;
+      uint8_t* const rowlist = reinterpret_cast<uint8_t*>(sm.ignlist);
+      if (need0) rowlist[__popc(Me & lt)] = (uint8_t)(2 * lane);
+      if (need1) rowlist[__popc(Me) + __popc(Mo & lt)] = (uint8_t)(2 * lane + 1);
+      if (lane == 0) { sm.nscan = __popc(Me) + __popc(Mo); sm.tick0 = tick0; }
     }
+    S64_STAMP(2);
     S64_STAMP(3);
     // the front cells' hidden / slope-factor sectors: their DRAM latency hides behind the second half of the key schedule
     prefetch_front(sm, hidden, pslope, cell_base, 0, L, lane);
     S64_STAMP(18);
   }
-  __syncthreads();  // the key chains are done
   if (active) {
+    // the chain warp finished this env's key chain long ago (it runs while the grids stream in); no CTA barrier
+    while (smem_ld_acquire(&sm.chain_done) == 0) __nanosleep(40);
+    __syncwarp();
     key_sides(sm, P, J, N, e, lane, widx);
     if (lane == 0) {
       S.key[2 * e] = sm.hot.x;
@@ -827,14 +803,18 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       if (lane == 0) {
         const int cnt = max(0, min(S64_CAP, total - pass * S64_CAP));
         sm.cnt = cnt;
-        cs.nch[warp] = (cnt + 31) >> 5;
+        // work items of this env: its 32-entry chunks, then (first pass of sub-step 0) its burn-out scan rounds of 4 rows
+        const int nsc = (active && j == 0 && pass == 0) ? (sm.nscan + 3) >> 2 : 0;
+        cs.nch[warp] = ((cnt + 31) >> 5) | (nsc << 16);
         if (gwarp == 0) cs.next[group] = 0;
       }
       group_sync(group);
 
       // ---------------- pooled phase: work items = 32-entry chunks of every env's front list -------
       {
-        const int my_n = lane < S64_GE ? cs.nch[group * S64_GE + lane] : 0;
+        const int my_pk = lane < S64_GE ? cs.nch[group * S64_GE + lane] : 0;
+        const int my_nc = my_pk & 0xFFFF;              // cell chunks of env slot `lane`
+        const int my_n = my_nc + (my_pk >> 16);        // + its scan rounds
         int incl = my_n;
 #pragma unroll
         for (int d = 1; d < S64_GE; d <<= 1) {
@@ -847,20 +827,31 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         // the next work item is requested one item ahead, so the shared-memory atomic's round trip overlaps
         // with the work on the current item (lane 0 holds the ticket until it is needed)
         int ticket = 0;
-        if (lane == 0 && more_items) ticket = atomicAdd(&cs.next[group], 1);
+        if (lane == 0 && more_items) ticket = smem_add_ret(&cs.next[group], 1);
         for (;;) {
           if (PT < 32 && more_items) {
             const int item = __shfl_sync(GCA_FULL, ticket, 0);
             if (item >= M) { more_items = false; continue; }
-            if (lane == 0) ticket = atomicAdd(&cs.next[group], 1);
+            if (lane == 0) ticket = smem_add_ret(&cs.next[group], 1);
             const int gslot = __popc(__ballot_sync(GCA_FULL, lane < S64_GE && incl <= item));
             const int chunk = item - __shfl_sync(GCA_FULL, incl - my_n, gslot);
             const int es_slot = group * S64_GE + gslot;
             EnvSmem& es = cs.env[es_slot];
+            const int nc_env = __shfl_sync(GCA_FULL, my_nc, gslot);
+            if (chunk >= nc_env) {
+              S64_MARK();
+              scan_round(es, S, chunk - nc_env, K, lane);
+              S64_ACC(30);
+              continue;
+            }
+            S64_MARK();
             const int t = chunk * 32 + lane;
             const bool inrange = t < es.cnt;
             const uint32_t cell = inrange ? es.list[t] : 0u;
             const int r = cell >> 6, c = cell & 63;
+            // the hidden byte is requested first: its (L2) latency hides behind the window work
+            int hid = 3 | (3 << 3);
+            if (hidden != nullptr && inrange) hid = hidden[(size_t)es.hot.w * 4096 + cell];
             uint32_t A, B, C;
             fire_window(es, r, c, A, B, C);
             uint32_t dirm = ((B >> 3) & 7u) | (((B >> 12) & 7u) << 3) | (((B >> 21) & 7u) << 6);
@@ -868,8 +859,6 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
             // fire bit is then set -- or by losing its last burning neighbour)
             const bool valid = inrange && !(dirm & 16u) && (dirm & ~16u) != 0u;
             dirm &= ~16u;
-            int hid = 3 | (3 << 3);
-            if (hidden != nullptr && valid) hid = hidden[(size_t)es.hot.w * 4096 + cell];
             // ring populations (Chebyshev rings 1..4 around the centre)
             const int S1 = __popc(B & 0x00E07038u);
             const int S2 = __popc(A & (0x07Cu << 18)) + __popc(B & 0x01F0F87Cu) + __popc(C & 0x07Cu);
@@ -894,41 +883,66 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
             const float b = __shfl_sync(GCA_FULL, lutreg, 8 + clip15((hid >> 3) & 7));
             const float ph_hi = __fsub_rn(__fmul_rn(Hf, S64_HI), Dlo);
             const float bhi = __fmul_rn(__fmul_rn(ph_hi, a), b);
-            if (valid) es.base[t] = near_doused ? -bhi : bhi;
             const int nd = (valid && bhi > 0.0f) ? __popc(dirm) : 0;
             const int incl2 = warp_incl_scan(nd, lane);
             int off = PT + incl2 - nd;
             const uint32_t em = nd ? dirm : 0u;
-            const uint32_t tag = ((uint32_t)es_slot << 11) | ((uint32_t)t << 3);
+            // one record per (cell, burning direction): the cell's bound bhi rounded UP to a multiple of 32 ulp (2^-18
+            // relative: inside the enclosure's margin) to make room for the env slot, sign bit = "dousing nearby";
+            // and (cell << 4) | direction
+            const uint32_t rec = ((__float_as_uint(bhi) + 31u) & 0x7FFFFFE0u) | (uint32_t)es_slot | (near_doused ? 0x80000000u : 0u);
+            const uint32_t c16 = cell << 4;
 #pragma unroll
             for (uint32_t d = 0; d < 9; ++d) {
               if (d == 4) continue;
-              if (em & (1u << d)) wp[off++] = (uint16_t)(tag | (d < 4 ? d : d - 1));
+              if (em & (1u << d)) {
+                wp32[off] = rec;
+                wpi[off] = (uint16_t)(c16 | d);
+                ++off;
+              }
             }
             PT += __shfl_sync(GCA_FULL, incl2, 31);
             __syncwarp();
+            S64_ACC(31);
             continue;
           }
           if (PT == 0) break;
-          // ---- draw up to 32 buffered pairs, one per lane.  (Two interleaved draws per lane were measured:
-          //      no gain -- with 7 warps per scheduler this phase is bound by the integer pipe, not by latency --
-          //      and a 64-wide round wastes more lanes when a warp flushes its last pairs.)
+          // ---- draw up to 32 buffered pairs, one per lane: the record holds everything but the env's key.  (Two
+          //      interleaved draws per lane were measured at the time the phase was bound by the integer pipe: no gain.)
           const int n = min(PT, 32);
           PT -= n;
           n_draws += (lane == 0) ? (uint32_t)n : 0u;
           const bool va = lane < n;
-          PairCtx A;
-          pair_load(cs, pslope, mode, va ? wp[PT + lane] : 0u, va, A);
+          const uint32_t ent = va ? wp32[PT + lane] : 0u;
+          const uint32_t pk = va ? wpi[PT + lane] : 0u;
+          EnvSmem& des = cs.env[ent & 31u];
+          const uint4 hot = des.hot;
+          const uint32_t cell = pk >> 4, d = pk & 15u;
+          const uint32_t idx = cell * 9u + d;
+          // direction's wind and slope factors: the global load's latency hides behind the threefry block
+          float sl = 1.0f;
+          if (pslope != nullptr && va) sl = pslope[((size_t)hot.w * 4096 + cell) * 8 + d - (d > 4u ? 1u : 0u)];
+          const float wd = des.wind[d];
           float ua;
           if (j_u_burn) {
             const size_t inj0 = (size_t)j * N * 4096;
-            ua = va ? j_u_burn[(inj0 + (size_t)A.es->hot.w * 4096 + A.cell) * 9 + A.ds + (A.ds >> 2)] : 1.0f;
+            ua = va ? j_u_burn[(inj0 + (size_t)hot.w * 4096) * 9 + idx] : 1.0f;
           } else {
             uint32_t o0, o1;
-            threefry2x32(A.key, A.c0, A.c1, o0, o1);
-            ua = bits_to_uniform(mode == GCA_RNG_LEGACY ? (A.first ? o0 : o1) : (o0 ^ o1));
+            TfKey key;
+            key.k0 = hot.x; key.k1 = hot.y; key.k2 = hot.z;
+            if (mode == GCA_RNG_LEGACY) {
+              const bool first = idx < S64_HALF_BURN;
+              const uint32_t c0 = first ? idx : idx - S64_HALF_BURN;
+              threefry2x32(key, c0, c0 + S64_HALF_BURN, o0, o1);
+              ua = bits_to_uniform(first ? o0 : o1);
+            } else {
+              threefry2x32(key, 0u, idx, o0, o1);
+              ua = bits_to_uniform(o0 ^ o1);
+            }
           }
-          pair_finish(P, hidden, A, va, ua, A.es->hot.w, n_thresh);
+          const float phi = __fmul_rn(__fmul_rn(__uint_as_float(ent & 0x7FFFFFE0u), wd), sl);
+          if (va && ua < phi) pair_hit(P, hidden, des, ent, cell, wd, sl, phi, ua, n_thresh);
           __syncwarp();
         }
       }
@@ -984,6 +998,10 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         if (lane == 0) sm.nign = nign;
       }
       S64_ACC(27);
+      if (j == 0) {  // the scan rounds of the pooled phase left the scanned rows' new minima in S.row_min
+        if (burnrows & 1u) rm.x = __ldcg(S.row_min + (size_t)e * 64 + 2 * lane);
+        if (burnrows & 2u) rm.y = __ldcg(S.row_min + (size_t)e * 64 + 2 * lane + 1);
+      }
       unsigned long long ext0 = 0ull, ext1 = 0ull;
       if (burnrows & 1u) {
         const ulonglong2 a = reinterpret_cast<const ulonglong2*>(sm.burn[2 * lane])[0];

@@ -24,6 +24,9 @@ gen = torch.Generator(device=dev); gen.manual_seed(0)
 def act():
     return torch.stack([torch.randint(0, 9, (N,), device=dev, generator=gen), torch.randint(0, 2, (N,), device=dev, generator=gen),
                         torch.randint(0, 3, (N,), device=dev, generator=gen)], -1).to(torch.int32).contiguous()
+if os.environ.get('PREROLL'):
+    from gym_cellular_automata_b200.workload import stationary_preroll
+    stationary_preroll(env, int(os.environ['PREROLL']), 32)
 for _ in range(100): env.step_device(act())
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 names = ["setup+publish key", "barrier+wait+convert+list", "scan", "(rm)"] + sum([[f"s{j} owner-pre", f"s{j} pooled", f"s{j} barrier"] for j in range(K)], [])
@@ -78,6 +81,8 @@ for mode in ("cold", "warm", "cold", "warm"):
         print("  per-env fit of finish time on [1, entries, pairs, rows]:", np.round(ce, 2).tolist())
     acc = o.stats[8:].cpu().numpy().reshape(N, 32)[:, 27:30].astype(np.float64).mean(0) / K
     print("  owner phases per sub-step (mean): ignition list + age draws %.1fk, burn-outs + state + views %.1fk, front masks + list extension %.1fk" % tuple(acc / 1e3))
+    pool = o.stats[8:].cpu().numpy().reshape(N, 32)[:, 30:32].astype(np.float64).mean(0)
+    print("  pooled work per warp and env step (mean): scan rounds %.1fk, cell chunks %.1fk cycles" % tuple(pool / 1e3))
     extra = tr[:, 16:20].mean(0)
     tr = tr[:, :4 + 3 * K]
     mean = tr.mean(0); mx = tr.max(0)
