@@ -35,8 +35,8 @@ ALGO_BYTES_PER_ENV = 64
 # PREROLL_HORIZON times in SETUP while env group g (e % PREROLL_GROUPS == g) is force-reset at pre-roll step
 # g * PREROLL_HORIZON / PREROLL_GROUPS (gym_cellular_automata_b200/workload.py), so the batch is a stationary
 # mixture of episode phases whatever --steps / --warmup a driver passes.
-PREROLL_HORIZON = 352
-PREROLL_GROUPS = 16
+PREROLL_HORIZON = 512
+PREROLL_GROUPS = 32
 
 
 def parse():
@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--rng-mode", default="legacy")
     ap.add_argument("--no-hidden", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--flush-mode", default="write+read", choices=["write", "write+read"],
+                    help="L2 flush between timed steps: a 256 MiB write, or the write followed by a 256 MiB read sweep (clean L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-obs-leg", action="store_true", help="skip the extra device-timed leg with RGB observations")
     ap.add_argument("--cpu-envs", type=int, default=256, help="envs of the CPU sample (cpu_baseline leg and --impl reference)")
@@ -146,7 +148,7 @@ def workload_config(args):
             "phase": (f"stationary mixture: {args.preroll}-step pre-roll in setup, {args.preroll_groups} env groups force-reset "
                       f"{args.preroll // max(args.preroll_groups, 1)} steps apart (episode ages spread over one episode)"
                       if args.preroll > 0 else "all envs in phase from reset"),
-            "rng_mode": args.rng_mode, "l2": "flushed between timed steps (256 MiB write)" if not args.no_flush
+            "rng_mode": args.rng_mode, "l2": (f"flushed between timed steps (256 MiB write{', then a 256 MiB read sweep: cold and clean' if args.flush_mode == 'write+read' else ''})") if not args.no_flush
             else "not flushed", "parallelism": f"env-sharded x{args.gpus}, no data-path collective"}
 
 
@@ -238,6 +240,19 @@ def pin_rank_to_cores(local, world):
         return None, None
 
 
+FLUSH_MODE = "write+read"
+
+
+def flush_l2(flush, i, torch):
+    """Evict everything from the 126 MB L2 between timed steps: write a 256 MiB buffer (the env state is displaced, its
+    dirty lines written back), then -- mode "write+read" -- sweep a second 256 MiB buffer with reads so that the L2 ends up
+    holding CLEAN lines: the timed kernel then misses in L2 on every access (cold), but does not also pay for the
+    write-back of the flush buffer's own 126 MB of dirty lines, which is traffic of the measurement, not of the path."""
+    flush[0].fill_(i & 0xFF)
+    if FLUSH_MODE == "write+read":
+        flush[2][0] = flush[1].view(torch.int64).max()  # full read sweep (no L2-sized write)
+
+
 def timed_steps(env, acts, first, n, flush, torch):
     """n env steps (acts[first + i]) with one CUDA-event pair each, the L2 flushed before every step (outside the
     events).  Returns the per-step times in microseconds after a synchronize."""
@@ -245,7 +260,7 @@ def timed_steps(env, acts, first, n, flush, torch):
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
     for i in range(n):
         if flush is not None:
-            flush.fill_(i & 0xFF)  # evict the env state from the 126 MB L2 (outside the timed events)
+            flush_l2(flush, i, torch)  # evict the env state from the 126 MB L2 (outside the timed events)
         starts[i].record()
         env.step_device(acts[first + i])
         ends[i].record()
@@ -271,11 +286,12 @@ def run_ours(args):
     K, size = args.substeps, args.size
     ROLLOUT = 128  # steps per rollout of the reference's trainer (agents/args.py:59): cadence of the statistics all-gather
 
-    def make_env(n_envs, obs_mode="none"):
+    def make_env(n_envs, obs_mode="none", env_offset=0, total=None):
         e = AdvancedForestFireBulldozerEnv(
             size, size, key=1 + rank, num_envs=n_envs, speed_move=0.12 * 4, speed_act=0.03 * 4, use_hidden=not args.no_hidden,
-            substeps=K, rng_mode=args.rng_mode, seed=args.seed + rank, hidden="random", obs_mode=obs_mode, auto_reset=True,
-            collect_stats=True, device=dev, balance_every=args.balance_every)
+            substeps=K, rng_mode=args.rng_mode, seed=args.seed + rank + 1000 * env_offset, hidden="random", obs_mode=obs_mode,
+            auto_reset=True, collect_stats=True, device=dev, balance_every=args.balance_every, env_offset=env_offset,
+            total_envs=total)
         e.reset()
         if args.preroll > 0:  # SETUP: stationary, phase-desynchronised mixture (not part of --warmup)
             stationary_preroll(e, args.preroll, args.preroll_groups, seed=args.seed + rank)
@@ -323,8 +339,9 @@ def run_ours(args):
         torch.cuda.synchronize()
         ms_warm = e0.elapsed_time(e1)
         del env
-        # ---- end to end through the host API: pinned host actions in, reward/terminated out, per step.  The SAME steps
-        # as the device-timed loop: a second env built from the same seeds, same pre-roll, same warm-up steps
+        # ---- end to end through the host API: pinned host actions in, reward/terminated out, per step.
+        # (1) synchronous: ONE C call per step for the whole batch, results valid on return.  The SAME steps as the
+        # device-timed loop: a second env built from the same seeds, same pre-roll, same warm-up steps
         env_host = make_env(n_envs)
         for i in range(args.warmup):
             env_host.step_device(acts[i])
@@ -336,21 +353,62 @@ def run_ours(args):
         n_coll = 0
         t0 = time.perf_counter()
         for i in range(args.steps):
-            # one C call per step: the kernel reads this step's actions from the pinned host buffer and stores reward +
-            # terminated to the pinned host buffers itself (zero-copy transport); results are valid on return
+            # the kernel reads this step's actions from the pinned host buffer and stores reward + terminated to the
+            # pinned host buffers itself (zero-copy transport); the host polls the completion word of the launch
             env_host.step_host(h_act[i], h_rew, h_term)
             if (i + 1) % ROLLOUT == 0 or i + 1 == args.steps:  # end of a rollout: the statistics all-gather
                 gathered = gather_episode_info(env_host)
                 n_coll += 1
         torch.cuda.synchronize()
+        e2e_sync_s = time.perf_counter() - t0
+        del env_host
+        # (2) two env groups (EnvPool style): the batch is two half-size envs on two CUDA streams; the host handles the
+        # results of one group while the other group steps (step_host(wait=False) / step_host_wait()).  Every step of
+        # every group still takes its actions from pinned host memory and delivers reward + terminated to the host.
+        half = n_envs // 2
+        groups = [make_env(half, env_offset=0, total=n_envs), make_env(n_envs - half, env_offset=half, total=n_envs)]
+        streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        g_act = [h_act[:, :half].contiguous().pin_memory(), h_act[:, half:].contiguous().pin_memory()]
+        g_buf = [g.host_result_buffers() for g in groups]
+        for g in range(2):
+            for i in range(args.warmup):
+                groups[g].step_device(acts[i][:half] if g == 0 else acts[i][half:])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n_coll2 = 0
+        sink = 0.0
+        t0 = time.perf_counter()
+        for g in range(2):
+            with torch.cuda.stream(streams[g]):
+                groups[g].step_host(g_act[g][0], g_buf[g][0], g_buf[g][1], wait=False)
+        for i in range(args.steps):
+            for g in range(2):
+                groups[g].step_host_wait()          # this group's reward / terminated are in host memory now
+                sink += float(g_buf[g][0][0])       # (the host reads them)
+                if i + 1 < args.steps:
+                    with torch.cuda.stream(streams[g]):
+                        groups[g].step_host(g_act[g][i + 1], g_buf[g][0], g_buf[g][1], wait=False)
+            if (i + 1) % ROLLOUT == 0 or i + 1 == args.steps:
+                for g in range(2):
+                    with torch.cuda.stream(streams[g]):
+                        gather_episode_info(groups[g])
+                n_coll2 += 1
+        torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-        return {"us": us, "us_long": us_long, "ms_warm": ms_warm, "e2e_s": e2e_s, "launches": launches,
+        del groups
+        return {"us": us, "us_long": us_long, "ms_warm": ms_warm, "e2e_s": e2e_s, "e2e_sync_s": e2e_sync_s,
+                "launches": launches, "collectives2": n_coll2,
                 "d_stats": (stats1 - stats0).astype(np.float64),
                 "d_stats_long": (stats2 - stats1).astype(np.float64) if n_long else None,
                 "gathered": gathered, "collectives": n_coll}
 
     N = args.envs_per_gpu
-    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    global FLUSH_MODE
+    FLUSH_MODE = args.flush_mode
+    flush = None if args.no_flush else (torch.empty(256 << 20, dtype=torch.uint8, device=dev),
+                                        torch.zeros(256 << 20, dtype=torch.uint8, device=dev),
+                                        torch.zeros(1, dtype=torch.int64, device=dev))
     sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) if rank == 0 else None
     if os.environ.get("GCA_BENCH_NO_SAMPLER"):  # diagnostics only: the JSON line then has no clocks
         sampler = None
@@ -393,17 +451,19 @@ def run_ours(args):
 
     def reduce_ranks(mm):
         """max over ranks of the three timed regions (+ the per-rank values, for attribution)"""
-        mine = torch.tensor([float(mm["us"].sum()) * 1e-3, mm["ms_warm"], mm["e2e_s"]], dtype=torch.float64, device=dev)
+        mine = torch.tensor([float(mm["us"].sum()) * 1e-3, mm["ms_warm"], mm["e2e_s"], mm["e2e_sync_s"]], dtype=torch.float64,
+                            device=dev)
         if world == 1:
             return [float(x) for x in mine.tolist()], None
-        allr = torch.empty((world, 3), dtype=torch.float64, device=dev)
+        allr = torch.empty((world, 4), dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(allr, mine)
         a = allr.cpu().numpy()
         per_rank = {"device_ms_per_step": [float(x) / args.steps for x in a[:, 0]],
-                    "e2e_us_per_step": [float(x) / args.steps * 1e6 for x in a[:, 2]]}
+                    "e2e_us_per_step": [float(x) / args.steps * 1e6 for x in a[:, 2]],
+                    "e2e_sync_us_per_step": [float(x) / args.steps * 1e6 for x in a[:, 3]]}
         return [float(x) for x in a.max(0)], per_rank
 
-    (ms, ms_warm, e2e_s), per_rank = reduce_ranks(m)
+    (ms, ms_warm, e2e_s, e2e_sync_s), per_rank = reduce_ranks(m)
     red5 = reduce_ranks(m5) if m5 is not None else None
     if rank != 0:
         if world > 1:
@@ -462,11 +522,14 @@ def run_ours(args):
                      "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                      "algorithmic_bytes_per_launch": algo_bytes, "launch_us": launch_s * 1e6},
-        "e2e": {"value": throughput(N, e2e_s), "unit": "cell-updates/s",
-                "env_steps_per_s": total_envs * args.steps / e2e_s,
+        "e2e": {"value": throughput(N, e2e_sync_s), "unit": "cell-updates/s",
+                "env_steps_per_s": total_envs * args.steps / e2e_sync_s,
                 "h2d_bytes_per_step": int(N * 3 * 4), "d2h_bytes_per_step": int(N * 5),
-                "collectives_in_timed_region": m["collectives"],
-                "what": "gca_env_step_host per step, host buffers in and out: the fused step kernel reads the pinned host actions (H2D over the bus, zero-copy) and stores reward + terminated to pinned host memory (D2H), results valid on return; the all-gather of the per-env episode counters runs inside this loop every 128 steps (one rollout) and at its end; same env steps as the device-timed loop (second env, same seeds, pre-roll and warm-up)"},
+                "collectives_in_timed_region": m["collectives"], "us_per_step": e2e_sync_s / args.steps * 1e6,
+                "what": "one synchronous gca_env_step_host call per step for the whole batch, host buffers in and out: the fused step kernel reads the pinned host actions (H2D over the bus, zero-copy), the warp whose env ends last copies reward + terminated of all envs to pinned host memory in one burst (D2H) and stores the completion word the host polls -- results valid on return; the all-gather of the per-env episode counters runs inside this loop every 128 steps (one rollout) and at its end; same env steps as the device-timed loop (second env, same seeds, pre-roll and warm-up; L2 not flushed in this loop)",
+                "two_group_async": {"value": throughput(N, e2e_s), "us_per_step": e2e_s / args.steps * 1e6,
+                                    "collectives_in_timed_region": m["collectives2"],
+                                    "what": "the same traffic with the batch split into two env groups of N/2 on two CUDA streams (EnvPool style: GCA_FLAG_HOST_ASYNC + gca_host_wait, the host handles one group's results while the other steps); not the headline: a half-size launch lasts almost as long as a full one (the step is latency-bound per CTA), so splitting the batch does not pay on one GPU"}},
         "gpu_launches": m["launches"], "clocks": clocks, "step_us": step_us, "with_observation": with_obs,
         "workload_stats": workload_stats,
         "episode_stats": {"envs": int(gathered.shape[0]), "mean_steps_elapsed": float(gathered[:, 0].mean()),
@@ -475,12 +538,13 @@ def run_ours(args):
     if per_rank is not None:
         line["per_rank"] = dict(per_rank, host_cores_per_rank=len(my_cores) if my_cores else None)
     if m5 is not None:
-        (ms5, ms5_warm, e2e5_s), per_rank5 = red5
+        (ms5, ms5_warm, e2e5_s, e2e5_sync_s), per_rank5 = red5
         line["config5"] = {"workload": f"BASELINE config 5: {8192 * world} envs of {size}x{size}, 8192 per GPU, same pre-roll",
                            "value": throughput(8192, ms5 * 1e-3), "ms_per_step": ms5 / args.steps,
                            "env_steps_per_s": 8192 * world * args.steps / (ms5 * 1e-3),
-                           "e2e": {"value": throughput(8192, e2e5_s), "env_steps_per_s": 8192 * world * args.steps / e2e5_s,
-                                   "collectives_in_timed_region": m5["collectives"]},
+                           "e2e": {"value": throughput(8192, e2e5_sync_s), "env_steps_per_s": 8192 * world * args.steps / e2e5_sync_s,
+                                   "collectives_in_timed_region": m5["collectives"],
+                                   "two_group_async_value": throughput(8192, e2e5_s)},
                            "roofline_frac": (ALGO_BYTES_PER_CELL * 8192 * size * size + ALGO_BYTES_PER_ENV * 8192)
                            / (ms5 * 1e-3 / args.steps) / 1e9 / peak,
                            "workload_stats": wl(m5["d_stats"]), "per_rank": per_rank5}

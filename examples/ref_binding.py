@@ -1,22 +1,3 @@
-# INTEGRATION — binding `libgca.so` from the reference
-
-The reference (frasermince/gym-cellular-automata) is Python; the drop-in boundary is the C ABI of
-`include/gca.h`.  A maintainer who wants the reference's `AdvancedForestFireBulldozerEnv` to step on
-a B200 replaces the body of `stateless_step` (reference
-`gym_cellular_automata/forest_fire/bulldozer/advanced_bulldozer.py:332-399`) with one call into the
-library.  The stub below is everything the reference side needs; `gym_cellular_automata_b200/_lib.py`
-and `packed.py` are the production version of the same binding.
-
-## 1. ctypes stub (reference side)
-
-The file below is `examples/ref_binding.py`, included verbatim (`tools/sync_integration.py` rewrites this block;
-`tests/test_host_api.py::test_integration_md_shows_the_tested_binding` fails when they differ).  Its structures are
-checked field by field against `include/gca.h` (`test_abi_struct_sizes_match_header`), and
-`tests/test_gpu_parity.py::test_reference_side_stub_steps_an_env` steps 64x64 envs through this file alone --
-nothing of `gym_cellular_automata_b200` imported -- in lock step with the oracle.
-
-<!-- ref_binding:begin -->
-```python
 """Reference-side binding of libgca.so -- the stub a maintainer of frasermince/gym-cellular-automata would add as
 ``gym_cellular_automata/forest_fire/bulldozer/_gca.py`` to step ``AdvancedForestFireBulldozerEnv`` on a B200.
 
@@ -189,81 +170,3 @@ class RefSideEnv:
         check(self.lib, self.lib.gca_unpack_state(C.byref(self.params), C.byref(self.state.struct), g.data_ptr(),
                                                   a.data_ptr(), d.data_ptr(), self.stream()))
         return {"true_grid": g, "fire_age": a, "dousing_count": d}
-```
-<!-- ref_binding:end -->
-
-With JAX arrays the device pointers come from `jax.dlpack` / `unsafe_buffer_pointer()`, with torch
-from `tensor.data_ptr()`; `stream` is the raw `cudaStream_t`.  `conditional_reset`
-(reference `advanced_bulldozer.py:422-518`) maps to `gca_conditional_reset` (or to
-`GCA_FLAG_AUTO_RESET` inside the step).  `gca_unpack_state` gives back the reference's float32
-`true_grid` / `fire_age` / int32 `dousing_count` whenever the caller wants to look at them.
-
-## 2. Entry points and the reference interface each replaces
-
-| C symbol | reference interface (file:line) |
-|---|---|
-| `gca_params_init` | `PartiallyObservableForestFireJax.__init__` `forest_fire/operators/ca_alexandridis_jax.py:54-160`; clock mapping `forest_fire/bulldozer/advanced_bulldozer.py:238-246,745-777` |
-| `gca_alexandridis_step` | `PartiallyObservableForestFireJax.update` `ca_alexandridis_jax.py:426-460` under `jax.vmap` |
-| `gca_env_step` | `jax.vmap(MDP.update)` + `_award` + `_is_done` + info bookkeeping `advanced_bulldozer.py:332-399,1103-1133`; `RepeatCAJax.update` `forest_fire/operators/repeat_ca_jax.py:34-71`; `MoveModifyJax.update` `forest_fire/operators/move_modify_jax.py:148-157` |
-| `gca_env_step_host`, `gca_host_wait` | the same call as a CPU-side rollout loop makes it: host actions in, host reward / terminated out, the transfers and the completion wait inside (pinned buffers: read / written by the step kernel itself, zero-copy, and the env that ends last stores a completion word the host polls; pageable ones: staged with `cudaMemcpyAsync` + stream synchronisation) — what `jax.device_get` around `stateless_step` is in `agents/jax_ppo.py:1150-1166`.  With `GCA_FLAG_HOST_ASYNC` the call returns after the launch and `gca_host_wait` completes it: a rollout loop with two env groups handles one group's results while the other steps |
-| `gca_move_modify` | `MoveJax.update`, `ModifyJax.update` `move_modify_jax.py:39-62,102-114` |
-| `gca_reward_done` | `_award`, `_is_done`, `count_cells` `advanced_bulldozer.py:597-633,941-953` |
-| `gca_conditional_reset` | `conditional_reset` `advanced_bulldozer.py:422-518` |
-| `gca_render_rgb`, `gca_render_rgb_actions` (extension id read from the step's action triples) | `build_observation_on_extensions`, `grid_to_rgb_with_extensions`, `grid_to_rgb` `advanced_bulldozer.py:988-1101`; `apply_blur`, `apply_extensions` `forest_fire/bulldozer/utils/extension_utils.py:99-195` |
-| `gca_pack_state`, `gca_unpack_state` | the context pytree of `_initial_context_distribution` `advanced_bulldozer.py:690-743` |
-| `gca_generate_hidden` | `init_vegetation`, `init_density`, `init_altitude`, `get_slope` `forest_fire/bulldozer/utils/init_utils.py:10-116,166-200` and the slope factor of `ca_alexandridis_jax.py:199-200` (same layer models; counter-based random numbers instead of Python's unseeded generator) |
-| `gca_episode_stats_update` | the statistics half of `step_env_wrapped` (`EpisodeStatistics`, ring buffers of finished episodes) `agents/jax_ppo.py:380-398,486-501,504-655` |
-| `gca_balance_order` | — (scheduling aid of the 64×64 kernel: deals envs to CTA slots by last step's cost) |
-| `gca_windy_env_step`, `gca_windy_pack`, `gca_windy_unpack` | v3 rule set: `WindyForestFire.update` `forest_fire/operators/ca_windy.py:41-139`, `RepeatCA` `operators/repeat_ca.py:32-45`, `Move`/`Modify` `operators/move_modify.py:39-94`, `ForestFireBulldozerEnv` reward / done `bulldozer/bulldozer.py:196-203,393-400` |
-| `gca_threefry_bits`, `gca_threefry_split` | `jax.random.bits`, `jax.random.split` (third-party, unpinned) |
-| `gca_version`, `gca_last_error` | — |
-
-## 3. Using the repo's own host layer instead
-
-```python
-from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv
-env = AdvancedForestFireBulldozerEnv(64, 64, key=1, num_envs=4096, speed_move=0.12 * 4, speed_act=0.03 * 4,
-                                     use_hidden=True, enable_extensions=True, substeps=1)   # same kwargs as the reference
-obs, info = env.reset()
-obs, reward, terminated, truncated, info = env.stateless_step(env.total_action_space.sample(), obs, info)
-step_tuple = env.conditional_reset((obs, reward, terminated, truncated, info), action)
-```
-
-`from gym_cellular_automata_b200.forest_fire.operators import PartiallyObservableForestFireJax,
-RepeatCAJax, MoveJax, ModifyJax, MoveModifyJax` keeps the reference's import names.
-
-A rollout loop that keeps everything on the device: `out = env.step_device(actions)` (int32 CUDA tensor (N,3); `out.reward`,
-`out.terminated`, `out.step_reward`, `out.counts` are views of buffers the next step overwrites) and, when pixels are
-needed, `rgb = env.observe_device(actions)` — the observation `stateless_step` would have returned, in the env's
-`obs_mode` (`"rgb_f32"`: the reference's float32 layout, `"rgb_u8"`: the same pixels as bytes).
-
-A rollout loop that keeps its actions on the host and wants the reference's episode statistics:
-
-```python
-from gym_cellular_automata_b200.rollout_stats import EpisodeStatistics
-stats = EpisodeStatistics(env.num_envs, env.device)          # jax_ppo.py:486-501
-h_rew, h_term = env.host_result_buffers()                     # pinned
-env.step_host(h_actions, h_rew, h_term)                       # one C call: fused step (+ auto-reset) reading the pinned
-                                                              # actions / storing reward + terminated over the bus, sync
-stats.update(h_actions, env._out.step_reward, env._out.terminated, env._out.obs_night)   # pinned actions read in place
-```
-
-## 4. Checking a change against the reference itself
-
-The parity vectors of `tests/golden/reference_shim_golden.npz` come from the reference's own files
-(`forest_fire/bulldozer/advanced_bulldozer.py`, the three `*_jax.py` operators, the v3 NumPy operators and the
-statistics closure of `agents/jax_ppo.py`), executed where they lie under `oracle/ref_shim` — NumPy stand-ins for
-the `jax` / `flax.struct` / `gymnasium` names they use, so no jax install is needed:
-
-```
-python tests/golden/make_reference_golden.py                 # every section (about 3 minutes of CPU)
-python tests/golden/make_reference_golden.py --only rollout_stats,v3_32x48
-python -m pytest tests -q -m "not gpu" -k reference_source   # the oracle against the vectors (+ a live 16x16 run)
-python -m pytest tests -q -m gpu -k reference_source         # the CUDA path against the same vectors
-```
-
-A maintainer with a real jax install can point `jax`'s own `stateless_step` at the recorded start states and
-actions (the arrays `start/*`, `snapshot/*`, `actions`, `altitude64`, `vegetation`, `density` of each case) and
-compare with `steps/*`: that closes the two things the shim cannot see — `jax.random`'s bit stream (restated in
-`oracle/prng.py`, pinned by known-answer vectors) and XLA's float32 summation order (only the counted
-threshold cells, ≈ 1 per 10⁶ draws, can depend on it).

@@ -23,6 +23,9 @@ GCA_MAX_K = 8
 RNG_LEGACY, RNG_PARTITIONABLE = 0, 1
 FLAG_AUTO_RESET, FLAG_NO_HIDDEN, FLAG_CA_ONLY, FLAG_NO_TMA, FLAG_WORK_CYCLES, FLAG_HOST_COPY = 1, 2, 4, 8, 16, 96
 FLAG_HOST_COPY_IN, FLAG_HOST_COPY_OUT = 32, 64
+FLAG_HOST_ASYNC = 128
+FLAG_HOST_MAPPED = 256
+GCA_VERSION = 103  # include/gca.h: the ctypes structures below mirror that version of the header
 
 
 class GcaError(RuntimeError):
@@ -59,7 +62,9 @@ class GcaState(C.Structure):
 class GcaStepOut(C.Structure):
     _fields_ = [("reward", C.c_void_p), ("step_reward", C.c_void_p), ("terminated", C.c_void_p),
                 ("counts", C.c_void_p), ("obs_night", C.c_void_p), ("stats", C.c_void_p),
-                ("host_reward", C.c_void_p), ("host_terminated", C.c_void_p)]
+                ("host_reward", C.c_void_p), ("host_terminated", C.c_void_p),
+                ("host_done", C.c_void_p), ("done_counter", C.c_void_p), ("done_token", C.c_uint32),
+                ("reserved_", C.c_uint32)]
 
 
 _EPISODE_FIELDS = ("episode_returns", "episode_lengths", "returned_episode_returns", "returned_episode_lengths",
@@ -114,11 +119,18 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise GcaError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(nvcc, sm_100a).  There is no CPU fallback.")
+    if not os.environ.get("GCA_LIB_PATH") and _needs_build():
+        raise GcaError(f"{LIB_PATH} is older than its sources (csrc/*.cu, include/gca.h): rebuild it with "
+                       "`python -c 'import __graft_entry__ as g; g.build()'` -- a stale binary would be bound with "
+                       "the wrong structure layouts")
     lib = C.CDLL(LIB_PATH)
     lib.gca_version.restype = C.c_int
+    if lib.gca_version() != GCA_VERSION and not os.environ.get("GCA_SKIP_VERSION_CHECK"):  # (A/B runs against older builds)
+        raise GcaError(f"{LIB_PATH} reports gca_version {lib.gca_version()}, this binding was written for {GCA_VERSION}: "
+                       "rebuild the library (structure layouts may differ)")
     lib.gca_last_error.restype = C.c_char_p
     for name in EXPORTS:
-        if name not in ("gca_version", "gca_last_error"):
+        if name not in ("gca_version", "gca_last_error") and hasattr(lib, name):
             getattr(lib, name).restype = C.c_int
     lib.gca_params_init.argtypes = [C.POINTER(GcaParams), C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double,
                                     C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32,
@@ -128,6 +140,8 @@ def load():
     lib.gca_env_step_host.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState), C.c_void_p, C.c_void_p,
                                       C.POINTER(GcaStepOut), C.POINTER(GcaState), C.c_void_p, C.c_uint32,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
+    if hasattr(lib, "gca_host_wait"):
+        lib.gca_host_wait.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_void_p]
     lib.gca_alexandridis_step.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState), C.POINTER(GcaStepOut),
                                           C.POINTER(GcaInject), C.c_uint32, C.c_void_p]
     lib.gca_move_modify.argtypes = [C.POINTER(GcaParams), C.POINTER(GcaState), C.c_void_p, C.c_void_p]
@@ -154,7 +168,7 @@ def load():
 
 
 # every symbol include/gca.h declares (tests check the library exports all of them)
-EXPORTS = ("gca_version", "gca_last_error", "gca_params_init", "gca_env_step", "gca_env_step_host", "gca_alexandridis_step", "gca_render_rgb_actions",
+EXPORTS = ("gca_version", "gca_last_error", "gca_params_init", "gca_env_step", "gca_env_step_host", "gca_host_wait", "gca_alexandridis_step", "gca_render_rgb_actions",
            "gca_move_modify", "gca_reward_done", "gca_conditional_reset", "gca_render_rgb", "gca_pack_state",
            "gca_unpack_state", "gca_balance_order", "gca_generate_hidden", "gca_episode_stats_update", "gca_windy_env_step", "gca_windy_pack", "gca_windy_unpack",
            "gca_threefry_bits", "gca_threefry_split")

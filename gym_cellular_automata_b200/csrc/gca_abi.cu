@@ -1,5 +1,7 @@
 // gca_abi.cu -- the extern "C" surface of libgca.so (see include/gca.h).  Host code only:
 // argument checks, constant derivation (A0) and kernel dispatch by grid shape.
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -140,9 +142,20 @@ static int check_state(const gca_params* p, const gca_state* s, const char* who)
   return GCA_OK;
 }
 
+static int env_step_impl(const gca_params* p, const gca_state* s, const int32_t* actions, const gca_step_out* out,
+                         const gca_inject* inj, const gca_state* snapshot, const float* snapshot_reward, uint32_t flags,
+                         void* stream, bool completion_word);
+
 int gca_env_step(const gca_params* p, const gca_state* s, const int32_t* actions, const gca_step_out* out,
                  const gca_inject* inj, const gca_state* snapshot, const float* snapshot_reward, uint32_t flags,
                  void* stream) {
+  // device-resident callers order their work by the stream: no completion word, whatever the struct holds
+  return env_step_impl(p, s, actions, out, inj, snapshot, snapshot_reward, flags, stream, false);
+}
+
+static int env_step_impl(const gca_params* p, const gca_state* s, const int32_t* actions, const gca_step_out* out,
+                         const gca_inject* inj, const gca_state* snapshot, const float* snapshot_reward, uint32_t flags,
+                         void* stream, bool completion_word) {
   int rc = check_state(p, s, "gca_env_step: null params/state");
   if (rc) return rc;
   if (!(flags & GCA_FLAG_CA_ONLY)) {
@@ -155,6 +168,7 @@ int gca_env_step(const gca_params* p, const gca_state* s, const int32_t* actions
   gca_step_out o;
   std::memset(&o, 0, sizeof(o));
   if (out) o = *out;
+  if (!completion_word) o.host_done = nullptr;
   gca_inject j;
   std::memset(&j, 0, sizeof(j));
   if (inj) j = *inj;
@@ -216,12 +230,23 @@ int gca_env_step_host(const gca_params* p, const gca_state* s, const int32_t* ho
   const size_t N = (size_t)s->N;
   // transport per direction: the kernel itself over the bus (pinned, device-visible buffers; 64x64 kernel), else
   // the copy engine
-  void *da = nullptr, *dr = nullptr, *dt = nullptr;
-  const bool in_mapped = !(flags & GCA_FLAG_HOST_COPY_IN) && is64(p) &&
-                         mapped_device_pointer(host_actions, N * 3 * sizeof(int32_t), &da);
-  const bool out_mapped = !(flags & GCA_FLAG_HOST_COPY_OUT) && is64(p) &&
-                          mapped_device_pointer(host_reward, N * sizeof(float), &dr) &&
-                          mapped_device_pointer(host_terminated, N, &dt);
+  void *da = nullptr, *dr = nullptr, *dt = nullptr, *dw = nullptr;
+  bool in_mapped, out_mapped, word_mapped = false;
+  if ((flags & GCA_FLAG_HOST_MAPPED) && is64(p)) {
+    // the caller vouches for cudaHostAlloc'ed buffers: under unified addressing their device address is the host address
+    da = const_cast<int32_t*>(host_actions); dr = host_reward; dt = host_terminated; dw = out->host_done;
+    in_mapped = !(flags & GCA_FLAG_HOST_COPY_IN);
+    out_mapped = !(flags & GCA_FLAG_HOST_COPY_OUT);
+    word_mapped = out->host_done != nullptr;
+  } else {
+    in_mapped = !(flags & GCA_FLAG_HOST_COPY_IN) && is64(p) &&
+                mapped_device_pointer(host_actions, N * 3 * sizeof(int32_t), &da);
+    out_mapped = !(flags & GCA_FLAG_HOST_COPY_OUT) && is64(p) &&
+                 mapped_device_pointer(host_reward, N * sizeof(float), &dr) &&
+                 mapped_device_pointer(host_terminated, N, &dt);
+    if (out_mapped && out->host_done && out->done_counter)
+      word_mapped = mapped_device_pointer(out->host_done, sizeof(uint32_t), &dw);
+  }
   int rc;
   if (!in_mapped) {
     rc = check_cuda(cudaMemcpyAsync(dev_actions, host_actions, N * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st),
@@ -229,12 +254,18 @@ int gca_env_step_host(const gca_params* p, const gca_state* s, const int32_t* ho
     if (rc) return rc;
   }
   gca_step_out o = *out;
+  bool use_word = false;
+  o.host_done = nullptr;
   if (out_mapped) {
     o.host_reward = static_cast<float*>(dr);
     o.host_terminated = static_cast<uint8_t*>(dt);
+    if (word_mapped && out->done_counter) {
+      o.host_done = static_cast<uint32_t*>(dw);  // the kernel needs the device-visible alias of the word
+      use_word = true;
+    }
   }
-  rc = gca_env_step(p, s, in_mapped ? static_cast<const int32_t*>(da) : dev_actions, &o, nullptr, snapshot,
-                    snapshot_reward, flags, stream);
+  rc = env_step_impl(p, s, in_mapped ? static_cast<const int32_t*>(da) : dev_actions, &o, nullptr, snapshot,
+                     snapshot_reward, flags, stream, use_word);
   if (rc) return rc;
   if (!out_mapped) {
     const bool adjacent = out->terminated == reinterpret_cast<const uint8_t*>(out->reward + N) &&
@@ -252,7 +283,31 @@ int gca_env_step_host(const gca_params* p, const gca_state* s, const int32_t* ho
       if (rc) return rc;
     }
   }
-  return check_cuda(cudaStreamSynchronize(st), "env_step_host: synchronize");
+  if (flags & GCA_FLAG_HOST_ASYNC) return GCA_OK;  // the caller waits: gca_host_wait
+  return gca_host_wait(use_word ? out->host_done : nullptr, out->done_token, 30.0, stream);
+}
+
+int gca_host_wait(const uint32_t* host_done, uint32_t token, double timeout_s, void* stream) {
+  if (!host_done) return check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "host_wait: synchronize");
+  const volatile uint32_t* w = host_done;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned spins = 0;; ++spins) {
+    if (*w == token) {
+      std::atomic_thread_fence(std::memory_order_acquire);
+      return GCA_OK;
+    }
+    if ((spins & 0x3FFFu) == 0x3FFFu) {
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (dt > timeout_s) {
+        const cudaError_t e = cudaStreamQuery((cudaStream_t)stream);
+        if (e != cudaSuccess && e != cudaErrorNotReady) return check_cuda(e, "host_wait");
+        return fail(GCA_ERR_CUDA, "gca_host_wait: the completion word did not arrive in time");
+      }
+    }
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
 }
 
 int gca_alexandridis_step(const gca_params* p, const gca_state* s, const gca_step_out* out, const gca_inject* inj,

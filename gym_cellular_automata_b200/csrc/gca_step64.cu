@@ -543,6 +543,32 @@ __device__ __noinline__ void scan_round(EnvSmem& es, const gca_state& S, int q, 
   }
 }
 
+// n 32-bit words from device memory (read through L2: other SMs wrote them) to mapped host memory by one warp: 128-bit
+// accesses, eight loads in flight per lane, so the copy costs a handful of L2 round trips and one PCIe burst
+__device__ __noinline__ void burst_copy_u32(uint32_t* dst, const uint32_t* src, int n, int lane) {
+  if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
+    const int n4 = n >> 2;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int base = 0; base < n4; base += 32 * 8) {
+      uint4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = base + k * 32 + lane;
+        if (i < n4) v[k] = __ldcg(s4 + i);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = base + k * 32 + lane;
+        if (i < n4) d4[i] = v[k];
+      }
+    }
+    for (int i = (n4 << 2) + lane; i < n; i += 32) dst[i] = __ldcg(src + i);
+  } else {
+    for (int i = lane; i < n; i += 32) dst[i] = __ldcg(src + i);
+  }
+}
+
 // S64_TRACE (diagnostic builds only): per-env phase timestamps (SM clock, relative to the warp's start) go to
 // O.stats[8 + 16 e ...]; the caller must have allocated stats with 8 + 32 N words.
 #ifdef S64_TRACE
@@ -1149,11 +1175,11 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     }
     if (O.step_reward) O.step_reward[e] = rew;
     if (O.terminated) O.terminated[e] = done ? 1 : 0;
-    if (O.host_terminated) O.host_terminated[e] = done ? 1 : 0;
+    if (O.host_terminated && !O.host_done) O.host_terminated[e] = done ? 1 : 0;
     if (O.counts) { O.counts[2 * e] = tcount; O.counts[2 * e + 1] = fcount; }
     if (!((flags & GCA_FLAG_AUTO_RESET) && done)) {
       if (O.reward) O.reward[e] = rew;
-      if (O.host_reward) O.host_reward[e] = rew;
+      if (O.host_reward && !O.host_done) O.host_reward[e] = rew;
     }
   }
 
@@ -1190,7 +1216,36 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       if (S.reward_accumulated) S.reward_accumulated[e] = 0.0f;
       const float sr = snap_reward[e];
       if (O.reward) O.reward[e] = sr;
-      if (O.host_reward) O.host_reward[e] = sr;
+      if (O.host_reward && !O.host_done) O.host_reward[e] = sr;
+    }
+  }
+  // ---- completion word (gca_env_step_host): the warp whose env ends last copies the step's results -- reward and
+  //      terminated of ALL envs, from the device outputs -- to the mapped host mirrors in one burst, fences once at
+  //      system scope and stores the token the host polls.  (Every env storing its own 5 bytes to host memory and
+  //      fencing at system scope costs a PCIe round trip per warp on the kernel's tail.)
+  if (O.host_done != nullptr) {
+    uint32_t last = 0;
+    if (lane == 0) {
+      __threadfence();  // release: this env's device outputs
+      last = atomicAdd(O.done_counter, 1u) == (uint32_t)N - 1u ? 1u : 0u;
+    }
+    last = __shfl_sync(GCA_FULL, last, 0);
+    if (last) {
+      __threadfence();  // acquire: the other envs' device outputs
+      if (O.host_reward != nullptr && O.reward != nullptr)
+        burst_copy_u32(reinterpret_cast<uint32_t*>(O.host_reward), reinterpret_cast<const uint32_t*>(O.reward), N, lane);
+      if (O.host_terminated != nullptr && O.terminated != nullptr) {
+        if ((N & 3) == 0 && ((reinterpret_cast<uintptr_t>(O.host_terminated) | reinterpret_cast<uintptr_t>(O.terminated)) & 3) == 0)
+          burst_copy_u32(reinterpret_cast<uint32_t*>(O.host_terminated), reinterpret_cast<const uint32_t*>(O.terminated), N / 4, lane);
+        else
+          for (int i = lane; i < N; i += 32) O.host_terminated[i] = __ldcg(O.terminated + i);
+      }
+      __threadfence_system();
+      __syncwarp();
+      if (lane == 0) {
+        *O.done_counter = 0u;
+        *reinterpret_cast<volatile uint32_t*>(O.host_done) = O.done_token;
+      }
     }
   }
 }

@@ -85,10 +85,41 @@ class _LazyPerEnv(dict):
         raise KeyError(k)
 
     def keys(self):
-        return list(super().keys()) + [k for k in self._LAZY if k not in self]
+        return list(super().keys()) + [k for k in self._LAZY if not super().__contains__(k)]
 
     def __contains__(self, k):
         return super().__contains__(k) or k in self._LAZY
+
+    # the rest of the mapping protocol goes through keys() / __getitem__, so the lazy arrays are part of every
+    # iteration and copy.  (CPython's dict(d) / {**d} read the underlying table directly and still miss them: code of
+    # this package that copies a context uses materialise_context(), below.)
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return len(self.keys())
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def copy(self):
+        return {k: self[k] for k in self.keys()}
+
+
+def materialise_context(per_env_context) -> dict:
+    """A plain dict of a per_env_context, lazily unpacked arrays included (dict(ctx) would drop them) and host-lazy
+    static layers resolved to their arrays."""
+    out = {}
+    for k in per_env_context.keys():
+        v = per_env_context[k]
+        out[k] = v.tensor() if isinstance(v, _HostLazy) else v
+    return out
 
 
 class AdvancedForestFireBulldozerEnv(CAEnv):
@@ -216,6 +247,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         self._shared_ctx = None
         self._false = None
         self._host_lazy = None
+        self._slope_packed = False
 
     # ------------------------------------------------------------------------------------------
     # clock helpers (advanced_bulldozer.py:745-777)
@@ -363,16 +395,22 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         """Load an arbitrary reference-layout state (NumPy or torch arrays) into the packed device
         state.  ``pslope`` (N,H,W,3,3) may be given instead of ``slope``."""
         N, H, W = self.num_envs, self.nrows, self.ncols
-        self._host_lazy = None
         if self._state is None:
             self._version_structs += 1
             self._state = PackedState(N, H, W, self.device, use_hidden=self.use_hidden)
-        ctx = dict(per_env_context)
-        if self.use_hidden and "pslope" not in ctx and "slope" not in ctx:
-            if self._pslope_dev is not None:
-                ctx["pslope"] = self._pslope_dev
-            else:
-                ctx["slope"] = self._slope
+            self._slope_packed = False
+        ctx = materialise_context(per_env_context)
+        if self.use_hidden:
+            own = self._host_lazy.get("slope") if self._host_lazy else None
+            own_t = own._t if isinstance(own, _HostLazy) else own
+            if "pslope" not in ctx and "slope" in ctx and self._slope_packed and own_t is not None and ctx["slope"] is own_t:
+                del ctx["slope"]  # the env's own slope tensor (from a previous observation): its factor table is packed already
+            elif "pslope" not in ctx and "slope" not in ctx and not self._slope_packed:
+                if self._pslope_dev is not None:
+                    ctx["pslope"] = self._pslope_dev
+                else:
+                    ctx["slope"] = self._slope
+            self._slope_packed = True
         self._state.tick.zero_()  # ages are stored as burn-out ticks relative to tick 0
         self._state.pack_from_reference(self._params, ctx, position, time)
         if info is not None:
@@ -395,11 +433,12 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         if sc is None:
             sc = PackedState.carve_scalars(self._state._scalars.clone(), self.num_envs)
         if self._host_lazy is None:  # static host arrays, uploaded on first use
+            def lazy(a):  # device tensors (hidden="device") are handed out as they are
+                return a if torch.is_tensor(a) and a.is_cuda else _HostLazy(a, d)
             self._host_lazy = {
-                "density": _HostLazy(self._density, d), "vegetation": _HostLazy(self._vegitation, d),
-                "altitude": _HostLazy(self._altitude, d),
-                "slope": _HostLazy(self._slope if self._slope is not None
-                                   else np.zeros((self.num_envs, self.nrows, self.ncols, 3, 3), np.float32), d)}
+                "density": lazy(self._density), "vegetation": lazy(self._vegitation), "altitude": lazy(self._altitude),
+                "slope": lazy(self._slope if self._slope is not None
+                              else np.zeros((self.num_envs, self.nrows, self.ncols, 3, 3), np.float32))}
         static = {"wind_index": sc["wind_index"], "key": sc["key"], "is_night": sc["is_night"],
                   "time_step": sc["time_step"]}
         static.update(self._host_lazy)
@@ -604,14 +643,17 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         return buf[:4 * N].view(torch.float32), buf[4 * N:]
 
     def step_host(self, actions_host: torch.Tensor, reward_host: torch.Tensor, terminated_host: torch.Tensor,
-                  staged: bool = False) -> None:
+                  staged: bool = False, wait: bool = True) -> None:
         """The step for a CPU-side rollout loop, one C call (``gca_env_step_host``): ``actions_host`` (N,3)
         int32, ``reward_host`` (N,) float32 and ``terminated_host`` (N,) uint8 are HOST tensors.  When all
         three are pinned (``pin_memory()``) and the grid is 64x64 the step kernel reads the actions and stores
-        reward / terminated over the bus itself (zero-copy: one launch, no copy engine); otherwise -- or with
-        ``staged=True`` -- actions are copied in, the fused step runs, reward / terminated are copied out
-        (``staged`` may also be ``FLAG_HOST_COPY_IN`` or ``FLAG_HOST_COPY_OUT`` to stage one direction only).
-        The stream is synchronised, so the results are valid on return.  State stays on the device."""
+        reward / terminated over the bus itself (zero-copy: one launch, no copy engine) and the env that finishes last
+        stores a completion word the host polls; otherwise -- or with ``staged=True`` -- actions are copied in, the
+        fused step runs, reward / terminated are copied out and the stream is synchronised (``staged`` may also be
+        ``FLAG_HOST_COPY_IN`` or ``FLAG_HOST_COPY_OUT`` to stage one direction only).
+        ``wait=True``: the results are valid on return.  ``wait=False`` returns right after the launch; call
+        ``step_host_wait()`` before reading the buffers -- a rollout loop that owns two env groups (two env objects on
+        two CUDA streams) handles the results of one while the other steps, EnvPool style.  State stays on the device."""
         N = self.num_envs
         if (actions_host.is_cuda or actions_host.dtype != torch.int32 or actions_host.numel() != 3 * N
                 or not actions_host.is_contiguous()):
@@ -628,24 +670,42 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                 (reward_host.data_ptr(), terminated_host.data_ptr(), self._version_structs), load().gca_env_step_host,
                 C.byref(self._params), C.byref(self._state.cstruct()), self._host_act_dev.data_ptr(),
                 C.byref(self._out.cstruct()), C.byref(self._snapshot.cstruct()), ptr(self._snap_reward),
-                reward_host.data_ptr(), terminated_host.data_ptr())
+                reward_host.data_ptr(), terminated_host.data_ptr(),
+                reward_host.is_pinned() and terminated_host.is_pinned() and self._state.work is not None)
         flags = self._flags | (_lib.FLAG_AUTO_RESET if self.auto_reset else 0) | (_lib.FLAG_HOST_COPY if staged is True else int(staged))
+        if not wait:
+            flags |= _lib.FLAG_HOST_ASYNC
+        if ha[10] and actions_host.is_pinned():
+            flags |= _lib.FLAG_HOST_MAPPED  # torch pins with cudaHostAlloc: no per-call pointer queries in the C layer
         if self.balance_every and self._state.work is not None:
             if self._state.order is None:
                 self._state.enable_balancing()
                 self._version_structs += 1
-                return self.step_host(actions_host, reward_host, terminated_host, staged)  # re-bind the cached pointers
+                return self.step_host(actions_host, reward_host, terminated_host, staged, wait)  # re-bind the cached pointers
             self._steps_since_balance += 1
             if self._steps_since_balance >= self.balance_every:
                 self._state.rebalance()
                 self._steps_since_balance = 0
                 self.kernel_launches += 1
         self.kernel_launches += 1 if self._state.work is not None else 4 * self.substeps + 1
-        rc = ha[1](ha[2], ha[3], actions_host.data_ptr(), ha[4], ha[5], ha[6], ha[7], flags, ha[8], ha[9],
-                   torch.cuda.current_stream().cuda_stream)
+        self._out.next_token()
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = ha[1](ha[2], ha[3], actions_host.data_ptr(), ha[4], ha[5], ha[6], ha[7], flags, ha[8], ha[9], stream)
         if rc:
             check(rc, "gca_env_step_host")
         self._version += 1
+        # what step_host_wait() has to wait for: the completion word (zero-copy out on the 64x64 path) or the stream
+        word = (self._state.work is not None and not (flags & _lib.FLAG_HOST_COPY_OUT) and reward_host.is_pinned()
+                and terminated_host.is_pinned())
+        self._host_pending = None if wait else (self._out.host_done.data_ptr() if word else None, self._out.token, stream)
+
+    def step_host_wait(self, timeout_s: float = 30.0) -> None:
+        """Block until the ``step_host(..., wait=False)`` in flight has delivered its results to the host buffers."""
+        pend = getattr(self, "_host_pending", None)
+        if pend is None:
+            return
+        self._host_pending = None
+        check(load().gca_host_wait(pend[0], pend[1], float(timeout_s), pend[2]), "gca_host_wait")
 
     # ------------------------------------------------------------------------------------------
     # reference helpers
@@ -682,7 +742,18 @@ class _HostLazy:
         return self._t
 
     def __array__(self, dtype=None, copy=None):
-        return np.asarray(self._arr, dtype=dtype)
+        a = self._arr.detach().cpu().numpy() if torch.is_tensor(self._arr) else self._arr
+        return np.asarray(a, dtype=dtype)
+
+    def to(self, *args, **kwargs):
+        return self.tensor().to(*args, **kwargs)
+
+    def cpu(self):
+        return self.tensor().cpu()
+
+    @property
+    def dtype(self):
+        return self.tensor().dtype
 
     @property
     def shape(self):
@@ -713,7 +784,7 @@ class MDP(Operator):
 
     def update(self, grid, action, per_env_context, shared_context, position, time):
         env = self.env
-        ctx = dict(per_env_context)
+        ctx = materialise_context(per_env_context)
         ctx["true_grid"] = grid
         env.set_state(ctx, position, time)
         a = action if torch.is_tensor(action) else torch.as_tensor(np.asarray(action))

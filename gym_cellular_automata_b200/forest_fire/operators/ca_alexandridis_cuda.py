@@ -56,7 +56,9 @@ class PartiallyObservableForestFireCUDA(Operator):
         d = self.device
         g = _as_dev(grid, d, torch.float32)
         single = g.dim() == 2
-        ctx = dict(per_env_context)
+        # a plain copy that keeps lazily unpacked / host-lazy entries of the env's own context (dict(ctx) drops them)
+        ctx = {k: (per_env_context[k].tensor() if hasattr(per_env_context[k], "tensor") else per_env_context[k])
+               for k in per_env_context.keys()}
         if single:  # the reference's single-env signature: add the env axis
             g = g[None]
             ctx = {k: (_as_dev(v, d)[None] if k != "key" else _as_dev(v, d).reshape(1, 2)) for k, v in ctx.items()}
@@ -81,7 +83,7 @@ class PartiallyObservableForestFireCUDA(Operator):
                                            None if inj is None else C.byref(inj), flags, current_stream()),
               "gca_alexandridis_step")
         res = st.unpack_to_reference(P, want=("true_grid", "fire_age"))
-        new_ctx = dict(per_env_context)
+        new_ctx = {k: per_env_context[k] for k in per_env_context.keys()}
         new_grid = res["true_grid"]
         new_ctx["fire_age"] = res["fire_age"][0] if single else res["fire_age"]
         new_ctx["wind_index"] = st.wind_index[0] if single else st.wind_index

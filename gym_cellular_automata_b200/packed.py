@@ -48,9 +48,21 @@ class StepOutputs:
         self.counts = torch.zeros((N, 2), dtype=torch.int32, device=device)
         self.obs_night = torch.zeros(N, dtype=torch.uint8, device=device)
         self.stats = torch.zeros(8, dtype=torch.int64, device=device) if with_stats else None
+        # completion word of the host step (gca_env_step_host / gca_host_wait): one word of pinned (mapped) host memory the
+        # step kernel stores the step's token to, and the device word the launch counts its envs in
+        self.done_counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self.host_done = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.token = 0
         self._c = GcaStepOut(ptr(self.reward).value, ptr(self.step_reward).value, ptr(self.terminated).value,
                              ptr(self.counts).value, ptr(self.obs_night).value,
-                             None if self.stats is None else ptr(self.stats).value)
+                             None if self.stats is None else ptr(self.stats).value, None, None,
+                             self.host_done.data_ptr(), ptr(self.done_counter).value, 0, 0)
+
+    def next_token(self) -> int:
+        """A fresh non-zero token for the next host step; written into the struct the C call reads."""
+        self.token = (self.token % 0x7FFFFFFF) + 1
+        self._c.done_token = self.token
+        return self.token
 
     def cstruct(self) -> GcaStepOut:
         return self._c
@@ -182,13 +194,19 @@ class PackedState:
             veg = dev(ctx["vegetation"], torch.int32)
             den = dev(ctx["density"], torch.int32)
             if self.pslope is not None:
+                ps = None
                 if "pslope" in ctx:
                     ps = dev(ctx["pslope"], torch.float32)
-                else:
+                elif "slope" in ctx:
+                    # exp(f32(0.078) slope) is tabulated with NumPy on the host (the oracle's bits, whatever the libm)
                     from .forest_fire.bulldozer.utils.init_utils import p_slope_table
-                    ps = dev(p_slope_table(np.asarray(ctx["slope"])), torch.float32)
-                ps = ps.reshape(self.N, self.H, self.W, 9)
-                self.pslope.copy_(ps[..., [0, 1, 2, 3, 5, 6, 7, 8]])
+                    sl = ctx["slope"]
+                    sl = sl.detach().cpu().numpy() if torch.is_tensor(sl) else np.asarray(sl)
+                    ps = dev(p_slope_table(sl), torch.float32)
+                # neither given: the table already packed stays (set_state of the env's own, unchanged slope)
+                if ps is not None:
+                    ps = ps.reshape(self.N, self.H, self.W, 9)
+                    self.pslope.copy_(ps[..., [0, 1, 2, 3, 5, 6, 7, 8]])
         if "tick" in ctx:
             self.tick.copy_(dev(ctx["tick"], torch.int32))
         err = torch.zeros(1, dtype=torch.int32, device=d)

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define GCA_VERSION 102
+#define GCA_VERSION 103
 #define GCA_MAX_R 10        /* burn kernel radius: ceil(log2(size)) - 2; 10 at 4096 */
 #define GCA_MAX_K 8         /* CA sub-steps fused into one env step */
 
@@ -62,6 +62,10 @@ typedef enum gca_status {
 #define GCA_FLAG_HOST_COPY_IN 32u   /* gca_env_step_host: stage the actions through cudaMemcpyAsync even when mapped */
 #define GCA_FLAG_HOST_COPY_OUT 64u  /* gca_env_step_host: copy reward / terminated out with cudaMemcpyAsync even when mapped */
 #define GCA_FLAG_HOST_COPY 96u      /* both */
+#define GCA_FLAG_HOST_MAPPED 256u    /* gca_env_step_host: the caller guarantees that host_actions, host_reward, host_terminated and
+                                        out->host_done are cudaHostAlloc'ed (pinned, mapped, device address == host address under
+                                        unified addressing, e.g. torch pin_memory()): skips the per-call pointer queries */
+#define GCA_FLAG_HOST_ASYNC 128u     /* gca_env_step_host: return after the launch; the caller waits with gca_host_wait */
 #define GCA_FLAG_WORK_CYCLES 16u /* diagnostics: work[e] receives the elapsed SM clock cycles of env e's step instead of the cost estimate */
 
 /* Constants of one environment family (host POD, passed to kernels by value). */
@@ -142,6 +146,14 @@ typedef struct gca_step_out {
                                        threshold cells (exact re-evaluations), env steps, 0, 0 */
   float* host_reward;       /* optional [N] mirror of `reward` in MAPPED pinned host memory (device-visible */
   uint8_t* host_terminated; /* address): the 64x64 step kernel stores both there as well; NULL = off      */
+  /* completion word (64x64 kernel, optional): the env whose step ends last stores done_token to *host_done (one
+   * word of MAPPED pinned host memory, device-visible address) after every host mirror of the launch is visible
+   * to the host -- a host thread polls it (gca_host_wait) instead of synchronising the stream.  done_counter is
+   * one zero-initialised device word the launch counts its envs in (it is back to zero when the word is stored). */
+  uint32_t* host_done;
+  uint32_t* done_counter;
+  uint32_t done_token;
+  uint32_t reserved_;
 } gca_step_out;
 
 /* Injected random fields for rule-parity tests (device, each with a leading K axis); NULL = threefry. */
@@ -184,6 +196,13 @@ int gca_env_step_host(const gca_params* p, const gca_state* s, const int32_t* ho
                       int32_t* dev_actions, const gca_step_out* out, const gca_state* snapshot,
                       const float* snapshot_reward, uint32_t flags, float* host_reward,
                       uint8_t* host_terminated, void* stream);
+
+/* Completion of a gca_env_step_host call made with GCA_FLAG_HOST_ASYNC (an EnvPool-style rollout loop steps one
+ * group of envs while it handles the results of another): when the call used the completion word
+ * (out->host_done / done_counter set, zero-copy transport out) poll host_done -- the HOST address of that word --
+ * until it holds `token`; otherwise (host_done NULL) synchronise `stream`.  Returns GCA_ERR_CUDA if the word has
+ * not arrived after timeout_s seconds (the stream's error state is then reported by gca_last_error). */
+int gca_host_wait(const uint32_t* host_done, uint32_t token, double timeout_s, void* stream);
 
 /* K CA sub-steps only (PartiallyObservableForestFireJax.update applied K times). */
 int gca_alexandridis_step(const gca_params* p, const gca_state* s, const gca_step_out* out,

@@ -821,3 +821,119 @@ def test_env_with_device_generated_layers(cuda_device):
 def AdvancedForestFireBulldozerEnv_(*a, **k):
     from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv
     return AdvancedForestFireBulldozerEnv(*a, **k)
+
+
+def test_reference_side_stub_steps_an_env(cuda_device):
+    """The binding INTEGRATION.md shows (examples/ref_binding.py: ctypes + include/gca.h only, nothing of the package
+    imported) packs a reference-layout state, steps 64x64 envs with the fused kernel and unpacks them again -- in lock
+    step with the oracle, auto-reset included."""
+    import importlib.util
+    import os
+    from oracle import alexandridis as ax, init_state as oinit, prng
+    from oracle.c_oracle import COracle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("ref_binding", os.path.join(root, "examples", "ref_binding.py"))
+    rb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rb)
+    lib = rb.load()
+    N, K = 12, 2
+    state, _ = oinit.initial_state(64, 64, N, seed=4, jax_seed=9, use_hidden=True, mode=prng.LEGACY, hidden="random")
+    E = ax.EnvConstants(64, 64, speed_move=0.48, speed_act=0.12)
+    winds = oinit.get_winds()
+    state["shared_context"] = E.shared_context(winds)
+    co = COracle(E, winds, K=K, mode=prng.LEGACY)
+    env = rb.RefSideEnv(lib, torch, 64, 64, N, 0.48, 0.12, substeps=K, rng_mode=rb.GCA_RNG_LEGACY, auto_reset=False)
+    ctx = state["per_env_context"]
+    dev = {k: torch.as_tensor(np.ascontiguousarray(ctx[k])).cuda() for k in
+           ("true_grid", "fire_age", "dousing_count", "vegetation", "density", "wind_index", "is_night", "time_step")}
+    dev["vegetation"], dev["density"] = dev["vegetation"].to(torch.int32), dev["density"].to(torch.int32)
+    dev["key"] = torch.as_tensor(np.asarray(ctx["key"]).astype(np.uint32)).cuda()
+    ps = torch.as_tensor(np.asarray(ctx["pslope"], np.float32).reshape(N, 64, 64, 9)[..., [0, 1, 2, 3, 5, 6, 7, 8]].copy()).cuda()
+    env.reset(dev, torch.as_tensor(np.asarray(state["position"], np.int32)).cuda(),
+              torch.as_tensor(np.asarray(state["time"], np.float32)).cuda(), pslope8=ps)
+    rng = np.random.default_rng(0)
+    from parity_util import random_actions
+    for step in range(80):
+        act = random_actions(rng, N)
+        reward, term, counts = co.step(state, act)
+        r, t = env.stateless_step(torch.as_tensor(act).cuda())
+        got = env.context()
+        for k in ("true_grid", "fire_age", "dousing_count"):
+            assert np.array_equal(got[k].cpu().numpy(), np.asarray(ctx[k])), (step, k)
+        assert np.array_equal(env.step_reward.cpu().numpy(), reward), step
+        assert np.array_equal(t.cpu().numpy().astype(bool), term), step
+        assert np.array_equal(env.state.t["key"].cpu().numpy(), np.asarray(ctx["key"])), step
+        assert np.array_equal(env.state.t["position"].cpu().numpy(), np.asarray(state["position"])), step
+    rgb = env.observation(torch.as_tensor(act).cuda())
+    assert rgb.shape == (N, 64, 64, 3) and float(rgb.max()) <= 255.0
+
+
+def test_step_host_async_two_groups_equals_sync(cuda_device):
+    """EnvPool-style loop: two env groups on two CUDA streams, step_host(wait=False) + step_host_wait(), the results of
+    one group handled while the other steps -- same rewards / terminations / states as one synchronous env."""
+    from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv
+    N, K, steps = 64, 4, 40
+
+    def make(n, src=None, sl=None):
+        e = AdvancedForestFireBulldozerEnv(64, 64, key=3, num_envs=n, speed_move=0.48, speed_act=0.12, use_hidden=True,
+                                           substeps=K, seed=5, hidden="random", obs_mode="none", auto_reset=True,
+                                           balance_every=4)
+        e.reset()
+        if src is not None:  # this group = envs `sl` of the whole batch: same grids, layers, keys, winds
+            ic = src.initial_state[1]
+            e.set_state({k: np.asarray(v)[sl] for k, v in ic["per_env_context"].items()}, ic["position"][sl], ic["time"][sl],
+                        as_snapshot=True)
+        return e
+    whole = make(N)
+    rng = np.random.default_rng(1)
+    acts = torch.as_tensor(np.stack([rng.integers(0, 9, (steps, N)), rng.integers(0, 2, (steps, N)),
+                                     rng.integers(0, 3, (steps, N))], -1).astype(np.int32)).pin_memory()
+    hr, ht = whole.host_result_buffers()
+    ref_r, ref_t = [], []
+    for i in range(steps):
+        whole.step_host(acts[i], hr, ht)
+        ref_r.append(hr.clone()); ref_t.append(ht.clone())
+    halves = [make(N // 2, whole, slice(0, N // 2)), make(N // 2, whole, slice(N // 2, N))]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    bufs = [h.host_result_buffers() for h in halves]
+    hacts = [acts[:, :N // 2].contiguous().pin_memory(), acts[:, N // 2:].contiguous().pin_memory()]
+    got_r = [[None] * steps for _ in range(2)]
+    got_t = [[None] * steps for _ in range(2)]
+    for g in range(2):
+        with torch.cuda.stream(streams[g]):
+            halves[g].step_host(hacts[g][0], bufs[g][0], bufs[g][1], wait=False)
+    for i in range(steps):
+        for g in range(2):
+            halves[g].step_host_wait()
+            got_r[g][i], got_t[g][i] = bufs[g][0].clone(), bufs[g][1].clone()
+            if i + 1 < steps:
+                with torch.cuda.stream(streams[g]):
+                    halves[g].step_host(hacts[g][i + 1], bufs[g][0], bufs[g][1], wait=False)
+    torch.cuda.synchronize()
+    for i in range(steps):
+        assert torch.equal(torch.cat([got_r[0][i], got_r[1][i]]), ref_r[i]), i
+        assert torch.equal(torch.cat([got_t[0][i], got_t[1][i]]), ref_t[i]), i
+    assert torch.equal(torch.cat([halves[0]._state.cell, halves[1]._state.cell]), whole._state.cell)
+
+
+def test_env_context_round_trips_through_the_operator_api(cuda_device):
+    """The env's own (lazily unpacked) per_env_context fed back into set_state / MDP / ca / repeater -- the reference's
+    operator call pattern -- keeps its lazy arrays (dict(ctx) would drop true_grid / fire_age / dousing_count)."""
+    from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv
+    for hidden in ("reference", "device"):
+        env = AdvancedForestFireBulldozerEnv(64, 64, key=2, num_envs=4, speed_move=0.48, speed_act=0.12, use_hidden=True,
+                                             seed=1, hidden=hidden, obs_mode="rgb_f32")
+        obs, info = env.reset()
+        ctx = obs[1]
+        pe = ctx["per_env_context"]
+        assert set(dict(pe.items())) >= {"true_grid", "fire_age", "dousing_count", "wind_index", "key"}
+        a = torch.as_tensor(np.array([[4, 1, 0]] * 4, dtype=np.int32)).cuda()
+        (rgb, grid, _), (pe2, pos2, time2) = env.MDP(pe["true_grid"], a, pe, ctx["shared_context"], ctx["position"], ctx["time"])
+        assert rgb.shape == (4, 64, 64, 3) and grid.shape == (4, 64, 64)
+        # the returned context goes straight back in, as does the one of a plain stateless_step
+        env.set_state(pe2, pos2, time2)
+        obs, r, t, tr, info = env.stateless_step(a)
+        env.set_state(obs[1]["per_env_context"], obs[1]["position"], obs[1]["time"])
+        g2, pe3, _ = env.ca(obs[1]["per_env_context"]["true_grid"], a, obs[1]["per_env_context"], obs[1]["shared_context"])
+        assert g2.shape == (4, 64, 64) and "fire_age" in pe3

@@ -25,22 +25,61 @@ def test_abi_exports_every_declared_symbol(lib):
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.gca_version() == 102
+    assert lib.gca_version() == _lib.GCA_VERSION
+
+
+def _header_layout(tmp_path, structs):
+    """sizeof and offsetof of every field of the given {struct name: [field names]} as gcc lays out include/gca.h."""
+    import subprocess
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gca.h"', 'int main(){']
+    for name, fields in structs.items():
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        for f in fields:
+            lines.append(f'printf("{name}.{f} %zu\\n", offsetof({name}, {f}));')
+    lines.append('return 0;}')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    return dict((k, int(v)) for k, v in (ln.split() for ln in subprocess.check_output([str(exe)]).decode().splitlines()))
+
+
+def _ctypes_layout(pairs):
+    out = {}
+    for cname, cls in pairs.items():
+        out[cname] = ctypes.sizeof(cls)
+        for f in cls._fields_:
+            out[f"{cname}.{f[0]}"] = getattr(cls, f[0]).offset
+    return out
 
 
 def test_abi_struct_sizes_match_header(tmp_path):
-    """The ctypes mirrors must have the layout a C compiler gives include/gca.h."""
-    import subprocess
+    """The ctypes mirrors (production binding AND the reference-side stub of examples/ref_binding.py, the file
+    INTEGRATION.md shows) must have, field by field, the layout a C compiler gives include/gca.h."""
+    import importlib.util
     from gym_cellular_automata_b200 import _lib
-    src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gca.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
-                   'sizeof(gca_params),sizeof(gca_state),sizeof(gca_step_out),sizeof(gca_inject),'
-                   'offsetof(gca_params,ring_w),offsetof(gca_state,scratch_u32));return 0;}')
-    exe = tmp_path / "sz"
-    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
-    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
-    assert sizes == [ctypes.sizeof(_lib.GcaParams), ctypes.sizeof(_lib.GcaState), ctypes.sizeof(_lib.GcaStepOut),
-                     ctypes.sizeof(_lib.GcaInject), _lib.GcaParams.ring_w.offset, _lib.GcaState.scratch_u32.offset]
+    spec = importlib.util.spec_from_file_location("ref_binding", os.path.join(ROOT, "examples", "ref_binding.py"))
+    rb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rb)
+    for pairs in ({"gca_params": _lib.GcaParams, "gca_state": _lib.GcaState, "gca_step_out": _lib.GcaStepOut,
+                   "gca_inject": _lib.GcaInject, "gca_episode_stats": _lib.GcaEpisodeStats},
+                  {"gca_params": rb.gca_params, "gca_state": rb.gca_state, "gca_step_out": rb.gca_step_out,
+                   "gca_inject": rb.gca_inject}):
+        want = _header_layout(tmp_path, {n: [f[0] for f in c._fields_] for n, c in pairs.items()})
+        assert _ctypes_layout(pairs) == want
+    # no field of the header may be missing from a mirror: the last field of each struct ends at sizeof
+    hdr = open(os.path.join(ROOT, "include", "gca.h")).read()
+    assert f"#define GCA_VERSION {_lib.GCA_VERSION}" in hdr and rb.GCA_VERSION == _lib.GCA_VERSION
+    for cls in (_lib.GcaState, rb.gca_state, _lib.GcaStepOut, rb.gca_step_out):
+        last = cls._fields_[-1]
+        assert getattr(cls, last[0]).offset + ctypes.sizeof(last[1]) == ctypes.sizeof(cls)
+
+
+def test_integration_md_shows_the_tested_binding():
+    """INTEGRATION.md includes examples/ref_binding.py verbatim (tools/sync_integration.py rewrites the block)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    src = open(os.path.join(ROOT, "examples", "ref_binding.py")).read()
+    assert src.strip() in doc
 
 
 def test_abi_argument_errors_do_not_throw(lib):

@@ -20,6 +20,9 @@ def run(name, f, reps=2):
                                              rng_mode="legacy", seed=0, hidden="random", obs_mode="none", auto_reset=True,
                                              collect_stats=True, device=dev, balance_every=8)
         env.reset()
+        if os.environ.get("PREROLL"):
+            from gym_cellular_automata_b200.workload import stationary_preroll
+            stationary_preroll(env, int(os.environ["PREROLL"]), 32)
         for i in range(warm): env.step_device(acts[i])
         h_rew, h_term = env.host_result_buffers()
         torch.cuda.synchronize(); t0 = time.perf_counter()
