@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--preroll", type=int, default=PREROLL_HORIZON,
                     help="setup: env steps of the phase-desynchronising pre-roll (0 = all envs start in phase from reset)")
     ap.add_argument("--preroll-groups", type=int, default=PREROLL_GROUPS)
+    ap.add_argument("--two-group", action="store_true",
+                    help="also time the end-to-end loop with the batch split into two asynchronous env groups (EnvPool style)")
     ap.add_argument("--config5", action="store_true",
                     help="also time BASELINE config 5's per-GPU share (8192 envs per GPU); on by default at 8 GPUs")
     ap.add_argument("--long-run", type=int, default=384,
@@ -258,6 +260,12 @@ def timed_steps(env, acts, first, n, flush, torch):
     events).  Returns the per-step times in microseconds after a synchronize."""
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+    if flush is not None:
+        # the synchronize() in front of the timed region leaves the GPU idle; the first kernel after an idle gap of a
+        # few milliseconds runs ~50 us slower (measured: 140 us vs 85, tools/first_step_probe.py).  A millisecond of
+        # un-timed flush sweeps (no env step) brings it back to its loaded state and loads torch's kernels.
+        for i in range(16):
+            flush_l2(flush, i, torch)
     for i in range(n):
         if flush is not None:
             flush_l2(flush, i, torch)  # evict the env state from the 126 MB L2 (outside the timed events)
@@ -365,6 +373,12 @@ def run_ours(args):
         # (2) two env groups (EnvPool style): the batch is two half-size envs on two CUDA streams; the host handles the
         # results of one group while the other group steps (step_host(wait=False) / step_host_wait()).  Every step of
         # every group still takes its actions from pinned host memory and delivers reward + terminated to the host.
+        if not args.two_group:
+            return {"us": us, "us_long": us_long, "ms_warm": ms_warm, "e2e_s": float("nan"), "e2e_sync_s": e2e_sync_s,
+                    "launches": launches, "collectives2": 0,
+                    "d_stats": (stats1 - stats0).astype(np.float64),
+                    "d_stats_long": (stats2 - stats1).astype(np.float64) if n_long else None,
+                    "gathered": gathered, "collectives": n_coll}
         half = n_envs // 2
         groups = [make_env(half, env_offset=0, total=n_envs), make_env(n_envs - half, env_offset=half, total=n_envs)]
         streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
@@ -437,12 +451,13 @@ def run_ours(args):
                 o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 o0.record()
                 for i in range(n_obs):
-                    env_obs.step_device(acts[args.warmup + i])
-                    rgb = env_obs.observe_device(acts[args.warmup + i])
+                    # ONE launch: the step kernel's epilogue draws the frame (GCA_FLAG_RENDER)
+                    _, rgb = env_obs.step_observe_device(acts[args.warmup + i])
                 o1.record()
                 torch.cuda.synchronize()
                 ms_obs = o0.elapsed_time(o1)
                 with_obs[mode] = {"us_per_step": ms_obs / n_obs * 1e3, "steps": n_obs, "l2": "warm (back-to-back steps)",
+                                  "launches_per_step": 1 if env_obs._can_fuse_render() else 2,
                                   "cell_updates_per_s_per_gpu": N * n_obs / (ms_obs * 1e-3) * size * size * K,
                                   "obs_bytes_per_step": int(rgb.numel() * rgb.element_size())}
                 del env_obs, rgb
@@ -527,7 +542,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(N * 3 * 4), "d2h_bytes_per_step": int(N * 5),
                 "collectives_in_timed_region": m["collectives"], "us_per_step": e2e_sync_s / args.steps * 1e6,
                 "what": "one synchronous gca_env_step_host call per step for the whole batch, host buffers in and out: the fused step kernel reads the pinned host actions (H2D over the bus, zero-copy), the warp whose env ends last copies reward + terminated of all envs to pinned host memory in one burst (D2H) and stores the completion word the host polls -- results valid on return; the all-gather of the per-env episode counters runs inside this loop every 128 steps (one rollout) and at its end; same env steps as the device-timed loop (second env, same seeds, pre-roll and warm-up; L2 not flushed in this loop)",
-                "two_group_async": {"value": throughput(N, e2e_s), "us_per_step": e2e_s / args.steps * 1e6,
+                "two_group_async": None if not args.two_group else {"value": throughput(N, e2e_s), "us_per_step": e2e_s / args.steps * 1e6,
                                     "collectives_in_timed_region": m["collectives2"],
                                     "what": "the same traffic with the batch split into two env groups of N/2 on two CUDA streams (EnvPool style: GCA_FLAG_HOST_ASYNC + gca_host_wait, the host handles one group's results while the other steps); not the headline: a half-size launch lasts almost as long as a full one (the step is latency-bound per CTA), so splitting the batch does not pay on one GPU"}},
         "gpu_launches": m["launches"], "clocks": clocks, "step_us": step_us, "with_observation": with_obs,
@@ -544,7 +559,7 @@ def run_ours(args):
                            "env_steps_per_s": 8192 * world * args.steps / (ms5 * 1e-3),
                            "e2e": {"value": throughput(8192, e2e5_sync_s), "env_steps_per_s": 8192 * world * args.steps / e2e5_sync_s,
                                    "collectives_in_timed_region": m5["collectives"],
-                                   "two_group_async_value": throughput(8192, e2e5_s)},
+                                   "two_group_async_value": throughput(8192, e2e5_s) if args.two_group else None},
                            "roofline_frac": (ALGO_BYTES_PER_CELL * 8192 * size * size + ALGO_BYTES_PER_ENV * 8192)
                            / (ms5 * 1e-3 / args.steps) / 1e9 / peak,
                            "workload_stats": wl(m5["d_stats"]), "per_rank": per_rank5}

@@ -14,7 +14,7 @@ conditional_reset (advanced_bulldozer.py:422-518, here GCA_FLAG_AUTO_RESET insid
 import ctypes as C
 import os
 
-GCA_VERSION = 103
+GCA_VERSION = 104
 GCA_FLAG_AUTO_RESET, GCA_FLAG_NO_HIDDEN = 1, 2
 GCA_RNG_LEGACY, GCA_RNG_PARTITIONABLE = 0, 1   # jax_threefry_partitionable False / True
 
@@ -38,7 +38,7 @@ class gca_state(C.Structure):                    # device pointers; shapes in in
 class gca_step_out(C.Structure):                 # per-step outputs; any pointer may be NULL
     _fields_ = [(n, C.c_void_p) for n in ("reward", "step_reward", "terminated", "counts", "obs_night", "stats",
                                            "host_reward", "host_terminated", "host_done", "done_counter")] + [
-        ("done_token", C.c_uint32), ("reserved_", C.c_uint32)]
+        ("done_token", C.c_uint32), ("rgb_u8", C.c_uint32), ("rgb", C.c_void_p)]
 
 
 class gca_inject(C.Structure):                   # injected random fields (rule-parity tests); NULL = in-kernel threefry

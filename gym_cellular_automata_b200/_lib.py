@@ -25,7 +25,8 @@ FLAG_AUTO_RESET, FLAG_NO_HIDDEN, FLAG_CA_ONLY, FLAG_NO_TMA, FLAG_WORK_CYCLES, FL
 FLAG_HOST_COPY_IN, FLAG_HOST_COPY_OUT = 32, 64
 FLAG_HOST_ASYNC = 128
 FLAG_HOST_MAPPED = 256
-GCA_VERSION = 103  # include/gca.h: the ctypes structures below mirror that version of the header
+FLAG_RENDER = 512
+GCA_VERSION = 104  # include/gca.h: the ctypes structures below mirror that version of the header
 
 
 class GcaError(RuntimeError):
@@ -64,7 +65,7 @@ class GcaStepOut(C.Structure):
                 ("counts", C.c_void_p), ("obs_night", C.c_void_p), ("stats", C.c_void_p),
                 ("host_reward", C.c_void_p), ("host_terminated", C.c_void_p),
                 ("host_done", C.c_void_p), ("done_counter", C.c_void_p), ("done_token", C.c_uint32),
-                ("reserved_", C.c_uint32)]
+                ("rgb_u8", C.c_uint32), ("rgb", C.c_void_p)]
 
 
 _EPISODE_FIELDS = ("episode_returns", "episode_lengths", "returned_episode_returns", "returned_episode_lengths",
@@ -82,12 +83,31 @@ class GcaInject(C.Structure):
                 ("u_wind", C.c_void_p), ("wind_step", C.c_void_p)]
 
 
+def source_hash() -> str:
+    """16 hex digits over the CUDA sources and headers next to this file: the build id compiled into libgca.so."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in [os.path.join(_CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(_CSRC, x)) for x in HEADERS]:
+        if os.path.exists(d):
+            with open(d, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def _built_id(path: str):
+    """Build id of a libgca.so, read without binding anything else (None: not loadable / no such symbol)."""
+    try:
+        lib = C.CDLL(path)
+        lib.gca_build_id.restype = C.c_char_p
+        return lib.gca_build_id().decode()
+    except (OSError, AttributeError):
+        return None
+
+
 def _needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(_CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(_CSRC, h)) for h in HEADERS]
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+    """The library is missing or was built from other sources than the ones next to it (content hash, not mtimes: a
+    copied tree keeps no useful timestamps)."""
+    return not os.path.exists(LIB_PATH) or _built_id(LIB_PATH) != source_hash()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -96,7 +116,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     srcs = [os.path.join(_CSRC, s) for s in SOURCES if os.path.exists(os.path.join(_CSRC, s))]
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH] + srcs
+           f'-DGCA_BUILD_ID="{source_hash()}"', "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH] + srcs
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -120,7 +140,7 @@ def load():
         raise GcaError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(nvcc, sm_100a).  There is no CPU fallback.")
     if not os.environ.get("GCA_LIB_PATH") and _needs_build():
-        raise GcaError(f"{LIB_PATH} is older than its sources (csrc/*.cu, include/gca.h): rebuild it with "
+        raise GcaError(f"{LIB_PATH} was not built from the sources next to it (csrc/*.cu, include/gca.h): rebuild it with "
                        "`python -c 'import __graft_entry__ as g; g.build()'` -- a stale binary would be bound with "
                        "the wrong structure layouts")
     lib = C.CDLL(LIB_PATH)
@@ -130,7 +150,7 @@ def load():
                        "rebuild the library (structure layouts may differ)")
     lib.gca_last_error.restype = C.c_char_p
     for name in EXPORTS:
-        if name not in ("gca_version", "gca_last_error") and hasattr(lib, name):
+        if name not in ("gca_version", "gca_last_error", "gca_build_id") and hasattr(lib, name):
             getattr(lib, name).restype = C.c_int
     lib.gca_params_init.argtypes = [C.POINTER(GcaParams), C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double,
                                     C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32,
@@ -168,7 +188,7 @@ def load():
 
 
 # every symbol include/gca.h declares (tests check the library exports all of them)
-EXPORTS = ("gca_version", "gca_last_error", "gca_params_init", "gca_env_step", "gca_env_step_host", "gca_host_wait", "gca_alexandridis_step", "gca_render_rgb_actions",
+EXPORTS = ("gca_version", "gca_last_error", "gca_build_id", "gca_params_init", "gca_env_step", "gca_env_step_host", "gca_host_wait", "gca_alexandridis_step", "gca_render_rgb_actions",
            "gca_move_modify", "gca_reward_done", "gca_conditional_reset", "gca_render_rgb", "gca_pack_state",
            "gca_unpack_state", "gca_balance_order", "gca_generate_hidden", "gca_episode_stats_update", "gca_windy_env_step", "gca_windy_pack", "gca_windy_unpack",
            "gca_threefry_bits", "gca_threefry_split")

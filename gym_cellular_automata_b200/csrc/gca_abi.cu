@@ -53,7 +53,11 @@ static bool is64(const gca_params* p) { return p->H == 64 && p->W == 64; }
 
 extern "C" {
 
+#ifndef GCA_BUILD_ID
+#define GCA_BUILD_ID "unknown"
+#endif
 int gca_version(void) { return GCA_VERSION; }
+const char* gca_build_id(void) { return GCA_BUILD_ID; }
 const char* gca_last_error(void) { return g_err; }
 
 int gca_params_init(gca_params* p, int32_t nrows, int32_t ncols, int32_t K, double speed_move, double speed_act,
@@ -177,6 +181,10 @@ static int env_step_impl(const gca_params* p, const gca_state* s, const int32_t*
   if (snapshot) sn = *snapshot;
   gca_state st = *s;
   if (flags & GCA_FLAG_NO_HIDDEN) { st.hidden = nullptr; st.pslope = nullptr; }
+  if (flags & GCA_FLAG_RENDER) {
+    if (!is64(p)) return fail(GCA_ERR_UNSUPPORTED, "gca_env_step: GCA_FLAG_RENDER is a feature of the 64x64 kernel (use gca_render_rgb)");
+    if (!o.rgb || (flags & GCA_FLAG_CA_ONLY)) return fail(GCA_ERR_ARG, "gca_env_step: GCA_FLAG_RENDER needs out->rgb and a full env step");
+  }
   if (is64(p)) {
     if (!s->row_min || !s->bb) return fail(GCA_ERR_ARG, "gca_env_step: 64x64 path needs row_min and bb");
     if ((flags & GCA_FLAG_AUTO_RESET) && !sn.bb) return fail(GCA_ERR_ARG, "gca_env_step: the snapshot needs bb");

@@ -153,6 +153,27 @@ __device__ __forceinline__ void move_position(int a0, int H, int W, int& row, in
   if ((a0 == 2 || a0 == 5 || a0 == 8) && vr) col += 1;
 }
 
+// One pixel: display value, palette, dousing tint, bulldozer -- the float32 arithmetic of grid_to_rgb
+// (advanced_bulldozer.py:1035-1101), shared by both render kernels.
+__device__ __forceinline__ void render_pixel(int disp, bool ng, bool ds, bool dozer, float& cr, float& cg, float& cb) {
+  if (!ng) {
+    if (disp == 1) { cr = 169.f; cg = 196.f; cb = 153.f; }       // #A9C499
+    else if (disp == 2) { cr = 230.f; cg = 129.f; cb = 129.f; }  // #E68181
+    else { cr = 221.f; cg = 209.f; cb = 211.f; }                 // #DDD1D3
+  } else {
+    if (disp == 1) { cr = 47.f; cg = 79.f; cb = 79.f; }          // #2F4F4F
+    else if (disp == 2) { cr = 139.f; cg = 0.f; cb = 0.f; }      // #8B0000
+    else { cr = 105.f; cg = 105.f; cb = 105.f; }                 // #696969
+  }
+  if (ds) {  // rgb * (1 - 0.75) + tint * 0.75, float32, tint blue by day / orange by night
+    const float tr = ng ? 255.f : 0.f, tg = ng ? 165.f : 0.f, tb = ng ? 0.f : 200.f;
+    cr = __fadd_rn(__fmul_rn(cr, 0.25f), __fmul_rn(tr, 0.75f));
+    cg = __fadd_rn(__fmul_rn(cg, 0.25f), __fmul_rn(tg, 0.75f));
+    cb = __fadd_rn(__fmul_rn(cb, 0.25f), __fmul_rn(tb, 0.75f));
+  }
+  if (dozer) { cr = 0.f; cg = 0.f; cb = 0.f; }
+}
+
 __device__ __forceinline__ int clip15(int v) { return v < 1 ? 1 : (v > 5 ? 5 : v); }
 
 // direction index d = i*3+j (0..8, 4 = centre) -> slot in the 8-entry slope-factor table

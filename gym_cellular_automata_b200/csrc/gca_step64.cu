@@ -569,6 +569,174 @@ __device__ __noinline__ void burst_copy_u32(uint32_t* dst, const uint32_t* src, 
   }
 }
 
+// Observation of one env by its owner warp (fused epilogue of the step): grid_to_rgb without extensions
+// (advanced_bulldozer.py:1035-1101) -- palette by day / night, doused cells blended 0.25 rgb + 0.75 tint in float32,
+// bulldozer pixel black -- from the tree / fire rows the lanes hold (lane l: rows 2l, 2l+1) and the doused rows in
+// sm.dous64.  The rows are parked in shared memory (sm.burn / sm.ign: the caller makes sure they are free and clears
+// sm.ign again if the pooled phases still need it).  `scratch`: the warp's pair buffer (>= 320 bytes): colour tables.
+// colour tables of one env in `scratch` (320 bytes): [16] float4 r g b -- entry = doused << 2 | cell state (0 empty,
+// 1 tree, 2 fire, 3 unused), entries 8..15 black (bulldozer) -- then [3][8] bytes: R of entries 0..7, G, B
+__device__ __forceinline__ void render_lut(uint32_t* scratch, uint32_t night, int lane) {
+  float4* lutf = reinterpret_cast<float4*>(scratch);
+  uint8_t* lutb = reinterpret_cast<uint8_t*>(scratch) + 256;
+  if (lane < 16) {
+    float cr = 0.f, cg = 0.f, cb = 0.f;
+    if (lane < 8) render_pixel(lane & 3, night != 0, lane >= 4, false, cr, cg, cb);
+    lutf[lane] = make_float4(cr, cg, cb, 0.f);
+    if (lane < 8) {
+      lutb[lane] = (uint8_t)cr; lutb[8 + lane] = (uint8_t)cg; lutb[16 + lane] = (uint8_t)cb;
+    }
+  }
+}
+
+// The frame was drawn from the grid the step STARTED with (render_env64 in the prologue, so that its stores overlap
+// the CA work); here the pixels of the cells that changed during the step (masks ch0 / ch1 of rows 2 lane, 2 lane + 1)
+// are redrawn from the final rows.  The bulldozer pixel (prow, pcol) stays black.
+template <bool U8>
+__device__ __noinline__ void render_patch64(EnvSmem& sm, uint32_t* scratch, void* rgb, int e, unsigned long long t0,
+                                            unsigned long long t1, unsigned long long f0, unsigned long long f1,
+                                            unsigned long long ch0, unsigned long long ch1, int prow, int pcol,
+                                            uint32_t night, int lane) {
+  if (__ballot_sync(GCA_FULL, (ch0 | ch1) != 0ull) == 0u) return;
+  render_lut(scratch, night, lane);
+  __syncwarp();
+  const float4* lutf = reinterpret_cast<const float4*>(scratch);
+  unsigned long long ch = ch0, tt = t0, ff = f0;
+  int row = 2 * lane;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const unsigned long long dd = sm.dous64[2 + row];
+    while (ch) {
+      const int c = __ffsll((long long)ch) - 1;
+      ch &= ch - 1;
+      if (row == prow && c == pcol) continue;
+      const uint32_t code = (uint32_t)((tt >> c) & 1ull) | ((uint32_t)((ff >> c) & 1ull) << 1) | ((uint32_t)((dd >> c) & 1ull) << 2);
+      const float4 px = lutf[code];
+      const size_t o = ((size_t)e * 4096 + (size_t)row * 64 + c) * 3;
+      if (U8) {
+        uint8_t* p = reinterpret_cast<uint8_t*>(rgb) + o;
+        p[0] = (uint8_t)px.x; p[1] = (uint8_t)px.y; p[2] = (uint8_t)px.z;
+      } else {
+        float* p = reinterpret_cast<float*>(rgb) + o;
+        p[0] = px.x; p[1] = px.y; p[2] = px.z;
+      }
+    }
+    ch = ch1; tt = t1; ff = f1;
+    row = 2 * lane + 1;
+  }
+  __syncwarp();
+}
+
+// bit k of a 16-bit mask -> bit 4 k (one nibble per cell)
+__device__ __forceinline__ unsigned long long spread16(uint32_t v) {
+  unsigned long long x = v;
+  x = (x | (x << 24)) & 0x000000FF000000FFull;
+  x = (x | (x << 12)) & 0x000F000F000F000Full;
+  x = (x | (x << 6)) & 0x0303030303030303ull;
+  x = (x | (x << 3)) & 0x1111111111111111ull;
+  return x;
+}
+
+template <bool U8>
+__device__ __noinline__ void render_env64(EnvSmem& sm, uint32_t* scratch, void* rgb, int e, unsigned long long t0,
+                                          unsigned long long t1, unsigned long long f0, unsigned long long f1, int prow,
+                                          int pcol, uint32_t night, int lane) {
+  unsigned long long* const flat = &sm.burn[0][0];   // 2 KB, free outside [barrier A of sub-step 0, last apply]
+  reinterpret_cast<ulonglong2*>(flat)[lane] = make_ulonglong2(t0, t1);
+  reinterpret_cast<ulonglong2*>(sm.ign)[lane] = make_ulonglong2(f0, f1);
+  render_lut(scratch, night, lane);
+  float4* lutf = reinterpret_cast<float4*>(scratch);
+  uint8_t* lutb = reinterpret_cast<uint8_t*>(scratch) + 256;
+  __syncwarp();
+  const uint16_t* tq = reinterpret_cast<const uint16_t*>(flat);
+  const uint16_t* fq = reinterpret_cast<const uint16_t*>(sm.ign);
+  const uint16_t* dq = reinterpret_cast<const uint16_t*>(sm.dous64 + 2);
+  const int q = lane & 3;
+  uint32_t Rlo = 0, Rhi = 0, Glo = 0, Ghi = 0, Blo = 0, Bhi = 0;
+  if (U8) {
+    const uint2 R = reinterpret_cast<const uint2*>(lutb)[0], G = reinterpret_cast<const uint2*>(lutb)[1],
+                B = reinterpret_cast<const uint2*>(lutb)[2];
+    Rlo = R.x; Rhi = R.y; Glo = G.x; Ghi = G.y; Blo = B.x; Bhi = B.y;
+  }
+  // pixels are staged in shared memory (sm.burn: 2 KB, free by now) so that every global store of the warp covers 512
+  // contiguous bytes: uint8 -- 8 rows (1536 B) per round, a lane renders 16 cells; float32 -- 2 rows (1536 B) per round,
+  // a lane renders 4 cells
+  uint4* const stage = reinterpret_cast<uint4*>(flat + 64);
+  if (U8) {
+    uint4* const out = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(rgb) + (size_t)e * 4096 * 3);
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it) {
+      const int r = 8 * it + (lane >> 2);
+      const uint32_t t16 = tq[r * 4 + q], f16 = fq[r * 4 + q], d16 = dq[r * 4 + q];
+      const int pk = (r == prow && (pcol >> 4) == q) ? (pcol & 15) : -1;  // the bulldozer's cell among this lane's 16
+      uint32_t w[12];
+      // 16 cells -> 16 nibbles: state | doused << 2 (tree and fire are disjoint, fire = 2)
+      const unsigned long long sel64 = spread16(t16) | (spread16(f16) << 1) | (spread16(d16) << 2);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t sel = (uint32_t)(sel64 >> (16 * g)) & 0xFFFFu;
+        const uint32_t R4 = __byte_perm(Rlo, Rhi, sel), G4 = __byte_perm(Glo, Ghi, sel), B4 = __byte_perm(Blo, Bhi, sel);
+        // bytes R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+        const uint32_t rg = __byte_perm(R4, G4, 0x5140u);   // R0 G0 R1 G1
+        const uint32_t rg2 = __byte_perm(R4, G4, 0x7362u);  // R2 G2 R3 G3
+        w[3 * g] = __byte_perm(rg, B4, 0x2410u);            // R0 G0 B0 R1
+        w[3 * g + 1] = __byte_perm(__byte_perm(rg, B4, 0x0053u), rg2, 0x5410u);  // G1 B1 R2 G2
+        w[3 * g + 2] = __byte_perm(rg2, B4, 0x7326u);       // B2 R3 G3 B3
+      }
+      if (pk >= 0) {  // black pixel: bytes 3 pk .. 3 pk + 2 of the 48
+#pragma unroll
+        for (int jw = 0; jw < 12; ++jw) {
+          uint32_t m = 0;
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            const int byte = 4 * jw + bb;
+            if (byte >= 3 * pk && byte < 3 * pk + 3) m |= 0xFFu << (8 * bb);
+          }
+          w[jw] &= ~m;
+        }
+      }
+      stage[3 * lane] = make_uint4(w[0], w[1], w[2], w[3]);
+      stage[3 * lane + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+      stage[3 * lane + 2] = make_uint4(w[8], w[9], w[10], w[11]);
+      __syncwarp();
+      const uint4 a0 = stage[lane], a1 = stage[lane + 32], a2 = stage[lane + 64];
+      out[96 * it + lane] = a0;
+      out[96 * it + 32 + lane] = a1;
+      out[96 * it + 64 + lane] = a2;
+      __syncwarp();
+    }
+  } else {
+    float4* const out = reinterpret_cast<float4*>(reinterpret_cast<float*>(rgb) + (size_t)e * 4096 * 3);
+    float4* const stf = reinterpret_cast<float4*>(stage);
+    const int h = lane >> 4, c4 = lane & 15;  // row of the pair, group of 4 cells
+#pragma unroll 1
+    for (int it = 0; it < 32; ++it) {
+      const int r = 2 * it + h;
+      const int sh = 4 * (c4 & 3);
+      const uint32_t t4 = (uint32_t)tq[r * 4 + (c4 >> 2)] >> sh, f4 = (uint32_t)fq[r * 4 + (c4 >> 2)] >> sh,
+                     d4 = (uint32_t)dq[r * 4 + (c4 >> 2)] >> sh;
+      const int pk = (r == prow && (pcol >> 2) == c4) ? (pcol & 3) : -1;
+      float4 c[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t code = ((t4 >> k) & 1u) | (((f4 >> k) & 1u) << 1) | (((d4 >> k) & 1u) << 2);
+        if (k == pk) code = 8u;
+        c[k] = lutf[code];
+      }
+      stf[3 * lane] = make_float4(c[0].x, c[0].y, c[0].z, c[1].x);
+      stf[3 * lane + 1] = make_float4(c[1].y, c[1].z, c[2].x, c[2].y);
+      stf[3 * lane + 2] = make_float4(c[2].z, c[3].x, c[3].y, c[3].z);
+      __syncwarp();
+      const float4 a0 = stf[lane], a1 = stf[lane + 32], a2 = stf[lane + 64];
+      out[96 * it + lane] = a0;
+      out[96 * it + 32 + lane] = a1;
+      out[96 * it + 64 + lane] = a2;
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+}
+
 // S64_TRACE (diagnostic builds only): per-env phase timestamps (SM clock, relative to the warp's start) go to
 // O.stats[8 + 16 e ...]; the caller must have allocated stats with 8 + 32 N words.
 #ifdef S64_TRACE
@@ -758,6 +926,26 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       S.key[2 * e + 1] = sm.hot.y;
       S.wind_index[e] = widx;
     }
+#ifdef S64_EARLY_RENDER  // measured: uint8 100 us per step against 94 with the frame drawn in the epilogue, float32 127 against 131
+    if ((flags & GCA_FLAG_RENDER) && O.rgb != nullptr) {
+      // the observation is drawn NOW, from the grid the step starts with (the frame's 12 / 48 KB of stores then overlap
+      // the CA work instead of piling up at the end of the launch); the few cells that change are redrawn in the
+      // epilogue.  New position (the action is known), pre-step dousing marks and day/night.
+      uint32_t ri = 0;
+      if (lane == 0) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        int row = S.position[2 * e], col = S.position[2 * e + 1];
+        move_position(__float_as_int(sm.wind[9]), 64, 64, row, col);
+        ri = (uint32_t)row | ((uint32_t)col << 8) | ((uint32_t)(S.is_night[e] != 0) << 16);
+      }
+      ri = __shfl_sync(GCA_FULL, ri, 0);
+      if (O.rgb_u8) render_env64<true>(sm, wp32, O.rgb, e, t0, t1, f0, f1, (int)(ri & 255u), (int)((ri >> 8) & 255u), ri >> 16, lane);
+      else render_env64<false>(sm, wp32, O.rgb, e, t0, t1, f0, f1, (int)(ri & 255u), (int)((ri >> 8) & 255u), ri >> 16, lane);
+      sm.ign[2 * lane] = 0ull;   // (the render parked the fire rows there)
+      sm.ign[2 * lane + 1] = 0ull;
+      __syncwarp();
+    }
+#endif
   }
 
   const float lutreg = lane < 8 ? P.onep_veg[lane] : (lane < 16 ? P.onep_den[lane - 8] : 0.0f);
@@ -1126,6 +1314,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     asm volatile("cp.async.wait_all;" ::: "memory");   // the action words (lanes 0..2 copied them)
     __syncwarp();
   }
+  uint32_t rinfo = 0;  // observation inputs (lane 0): row | col << 8 | night << 16 | "add this step's dousing mark" << 17
   if (lane == 0) {
 #ifdef S64_TRACE
     if (O.stats) {
@@ -1168,7 +1357,13 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       if (a1 == 1) S.doused[(size_t)e * 64 + row] = drow | (1ull << col);
       S.time_step[e] = ts;
       if (O.obs_night) O.obs_night[e] = (uint8_t)night;
+      // the observation shows the NEW position with the PRE-step dousing marks and day/night (advanced_bulldozer.py:1120-1122)
+      rinfo = (uint32_t)row | ((uint32_t)col << 8) | ((uint32_t)night << 16);
       if (ts % P.day_length == 0) night = 1 - night;
+      if ((flags & GCA_FLAG_AUTO_RESET) && done)
+        // ... unless the env resets now: conditional_reset redraws it from the restored grid and position with the
+        // POST-step marks and day/night (:462-487); the mark of this step sits at the position just moved to
+        rinfo = (uint32_t)row | ((uint32_t)col << 8) | ((uint32_t)night << 16) | (a1 == 1 ? 1u << 17 : 0u);
       S.is_night[e] = night;
       if (S.steps_elapsed) S.steps_elapsed[e] = __fadd_rn(se, 1.0f);
       if (S.reward_accumulated) S.reward_accumulated[e] = __fadd_rn(ra, rew);
@@ -1180,6 +1375,35 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     if (!((flags & GCA_FLAG_AUTO_RESET) && done)) {
       if (O.reward) O.reward[e] = rew;
       if (O.host_reward && !O.host_done) O.host_reward[e] = rew;
+    }
+  }
+
+  // ---- observation, fused (GCA_FLAG_RENDER): MDP.grid_to_rgb (advanced_bulldozer.py:1035-1101) from the bit-boards --
+  if ((flags & GCA_FLAG_RENDER) && O.rgb != nullptr) {
+    rinfo = __shfl_sync(GCA_FULL, rinfo, 0);
+    int prow = (int)(rinfo & 255u), pcol = (int)((rinfo >> 8) & 255u);
+    const uint32_t night_obs = (rinfo >> 16) & 1u;
+    unsigned long long rt0 = t0, rt1 = t1, rf0 = f0, rf1 = f1;
+    const bool resets = (flags & GCA_FLAG_AUTO_RESET) && done;
+    if (resets) {
+      // this env resets now: the frame shows the restored grid and position (post-step marks and day/night)
+      const ulonglong2* sb = reinterpret_cast<const ulonglong2*>(SNAP.bb + (size_t)e * 128);
+      const ulonglong2 r0 = sb[2 * lane], r1 = sb[2 * lane + 1];
+      rt0 = r0.x; rf0 = r0.y; rt1 = r1.x; rf1 = r1.y;
+      if (lane == 0 && (rinfo & (1u << 17))) sm.dous64[2 + prow] |= 1ull << pcol;  // this step's mark (pre-restore position)
+      prow = SNAP.position[2 * e];
+      pcol = SNAP.position[2 * e + 1];
+      __syncwarp();
+    }
+#ifdef S64_EARLY_RENDER
+    if (!resets) {  // the prologue drew the frame from the grid the step started with: redraw the cells that changed
+      if (O.rgb_u8) render_patch64<true>(sm, wp32, O.rgb, e, t0, t1, f0, f1, ch0, ch1, prow, pcol, night_obs, lane);
+      else render_patch64<false>(sm, wp32, O.rgb, e, t0, t1, f0, f1, ch0, ch1, prow, pcol, night_obs, lane);
+    } else
+#endif
+    {
+      if (O.rgb_u8) render_env64<true>(sm, wp32, O.rgb, e, rt0, rt1, rf0, rf1, prow, pcol, night_obs, lane);
+      else render_env64<false>(sm, wp32, O.rgb, e, rt0, rt1, rf0, rf1, prow, pcol, night_obs, lane);
     }
   }
 

@@ -529,10 +529,27 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         self._out.terminated.zero_()
         return (rgb, self._context_view()), info
 
-    def _launch_step(self, actions_dev, inject=None, auto_reset=None):
+    def _can_fuse_render(self) -> bool:
+        """The step kernel draws the observation itself (GCA_FLAG_RENDER): 64x64 grids without extensions."""
+        return (self.obs_mode != "none" and not self.enable_extensions and self._state is not None
+                and self._state.work is not None)
+
+    def _new_rgb(self):
+        u8 = self.obs_mode == "rgb_u8"
+        # a fresh buffer per step keeps earlier observations valid (rollout storage keeps them)
+        self._rgb = torch.empty((self.num_envs, self.nrows, self.ncols, 3), dtype=torch.uint8 if u8 else torch.float32,
+                                device=self.device)
+        return self._rgb
+
+    def _launch_step(self, actions_dev, inject=None, auto_reset=None, render=False):
         flags = self._flags
         if self.auto_reset if auto_reset is None else auto_reset:
             flags |= _lib.FLAG_AUTO_RESET
+        if render:
+            flags |= _lib.FLAG_RENDER
+            c = self._out.cstruct()
+            c.rgb = self._new_rgb().data_ptr()
+            c.rgb_u8 = 1 if self.obs_mode == "rgb_u8" else 0
         if self.balance_every and self._state.work is not None:
             if self._state.order is None:
                 self._state.enable_balancing()
@@ -577,10 +594,11 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         else:
             self._actions.copy_(a.to(self.device, non_blocking=True).reshape(self.num_envs, -1)[:, :3])
             acts = self._actions
-        self._launch_step(acts, inject)
+        fused = self._can_fuse_render()
+        self._launch_step(acts, inject, render=fused)
         st, out = self._state, self._out
-        rgb = None
-        if self.obs_mode != "none":
+        rgb = self._rgb if fused else None
+        if self.obs_mode != "none" and not fused:
             rgb = self._render(st.cell, st.doused, st.position, out.obs_night, None, actions=acts)
         # two snapshot copies (per-env scalars, step outputs); everything handed out is a view of them
         sc = PackedState.carve_scalars(st._scalars.clone(), self.num_envs)
@@ -628,6 +646,16 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         """Hot path: one fused launch on the current stream; actions and results stay in HBM."""
         self._launch_step(actions_dev, None, auto_reset)
         return self._out
+
+    def step_observe_device(self, actions_dev: torch.Tensor, auto_reset: Optional[bool] = None):
+        """``step_device`` + the step's RGB observation.  64x64 grids without extensions: ONE launch (the step kernel's
+        epilogue draws the frame from the bit-boards it holds, GCA_FLAG_RENDER); otherwise the step followed by
+        ``gca_render_rgb``.  Returns (outputs, rgb)."""
+        if self._can_fuse_render():
+            self._launch_step(actions_dev, None, auto_reset, render=True)
+            return self._out, self._rgb
+        self._launch_step(actions_dev, None, auto_reset)
+        return self._out, self.observe_device(actions_dev)
 
     def observe_device(self, actions_dev: torch.Tensor) -> Optional[torch.Tensor]:
         """The RGB observation ``stateless_step`` would return for the step just made with ``step_device(actions_dev)``

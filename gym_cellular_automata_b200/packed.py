@@ -56,7 +56,7 @@ class StepOutputs:
         self._c = GcaStepOut(ptr(self.reward).value, ptr(self.step_reward).value, ptr(self.terminated).value,
                              ptr(self.counts).value, ptr(self.obs_night).value,
                              None if self.stats is None else ptr(self.stats).value, None, None,
-                             self.host_done.data_ptr(), ptr(self.done_counter).value, 0, 0)
+                             self.host_done.data_ptr(), ptr(self.done_counter).value, 0, 0, None)
 
     def next_token(self) -> int:
         """A fresh non-zero token for the next host step; written into the struct the C call reads."""

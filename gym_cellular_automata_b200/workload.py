@@ -37,8 +37,9 @@ def force_reset(env, mask_u8: torch.Tensor) -> None:
     env._version += 1
 
 
-def stationary_preroll(env, horizon: int, groups: int, seed: int = 0, chunk: int = 64) -> dict:
-    """Pre-roll ``horizon`` env steps with random actions, force-resetting group g at step g*horizon/groups.
+def stationary_preroll(env, horizon: int, groups: int, seed: int = 0, chunk: int = 64, settle: int = 96) -> dict:
+    """Pre-roll ``horizon`` env steps with random actions, force-resetting group g at step g*horizon/groups, then
+    ``settle`` free-running steps (the last groups' young fires grow in, the load balancer re-deals the envs).
     Returns {"horizon", "groups", "steps"}; the env must have been reset() and use auto_reset."""
     N, dev = env.num_envs, env.device
     gen = torch.Generator(device=dev)
@@ -55,4 +56,11 @@ def stationary_preroll(env, horizon: int, groups: int, seed: int = 0, chunk: int
                 force_reset(env, (gid == t // stride).to(torch.uint8))
             env.step_device(acts[i])
         done += n
-    return {"horizon": horizon, "groups": groups, "steps": done}
+    left = settle
+    while left > 0:
+        n = min(chunk, left)
+        acts = random_actions(n, N, dev, gen)
+        for i in range(n):
+            env.step_device(acts[i])
+        left -= n
+    return {"horizon": horizon, "groups": groups, "steps": done + settle}

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define GCA_VERSION 103
+#define GCA_VERSION 104
 #define GCA_MAX_R 10        /* burn kernel radius: ceil(log2(size)) - 2; 10 at 4096 */
 #define GCA_MAX_K 8         /* CA sub-steps fused into one env step */
 
@@ -62,6 +62,11 @@ typedef enum gca_status {
 #define GCA_FLAG_HOST_COPY_IN 32u   /* gca_env_step_host: stage the actions through cudaMemcpyAsync even when mapped */
 #define GCA_FLAG_HOST_COPY_OUT 64u  /* gca_env_step_host: copy reward / terminated out with cudaMemcpyAsync even when mapped */
 #define GCA_FLAG_HOST_COPY 96u      /* both */
+#define GCA_FLAG_RENDER 512u         /* render the step's observation into out->rgb in the step kernel's epilogue (64x64 grids,
+                                        no extensions): MDP.grid_to_rgb of the NEW grid / position with the PRE-step dousing marks
+                                        and day/night (advanced_bulldozer.py:1103-1133); for an env that auto-resets in this step
+                                        the frame conditional_reset draws (restored grid / position, post-step dousing marks and
+                                        day/night, :462-487).  float32 [N][H][W][3], or uint8 when out->rgb_u8 != 0 */
 #define GCA_FLAG_HOST_MAPPED 256u    /* gca_env_step_host: the caller guarantees that host_actions, host_reward, host_terminated and
                                         out->host_done are cudaHostAlloc'ed (pinned, mapped, device address == host address under
                                         unified addressing, e.g. torch pin_memory()): skips the per-call pointer queries */
@@ -153,7 +158,8 @@ typedef struct gca_step_out {
   uint32_t* host_done;
   uint32_t* done_counter;
   uint32_t done_token;
-  uint32_t reserved_;
+  uint32_t rgb_u8;          /* GCA_FLAG_RENDER: 0 = float32 pixels (the reference's layout), else uint8 */
+  void* rgb;                /* GCA_FLAG_RENDER: [N][H][W][3] observation of this step (device) */
 } gca_step_out;
 
 /* Injected random fields for rule-parity tests (device, each with a leading K axis); NULL = threefry. */
@@ -167,6 +173,9 @@ typedef struct gca_inject {
 
 int gca_version(void);
 const char* gca_last_error(void);
+/* Hash of the sources this binary was built from (gym_cellular_automata_b200/_lib.py passes it to nvcc and refuses a
+ * library whose id differs from the sources next to it); "unknown" for a build that did not set it. */
+const char* gca_build_id(void);
 
 /* A0: fill *p for an nrows x ncols env.  winds72 may be NULL (the reference's 8 wind matrices are
  * generated).  t_move / t_shoot < 0 selects the reference formula from speed_move / speed_act. */

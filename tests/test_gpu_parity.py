@@ -937,3 +937,43 @@ def test_env_context_round_trips_through_the_operator_api(cuda_device):
         env.set_state(obs[1]["per_env_context"], obs[1]["position"], obs[1]["time"])
         g2, pe3, _ = env.ca(obs[1]["per_env_context"]["true_grid"], a, obs[1]["per_env_context"], obs[1]["shared_context"])
         assert g2.shape == (4, 64, 64) and "fire_age" in pe3
+
+
+@pytest.mark.parametrize("mode", ["rgb_f32", "rgb_u8"])
+def test_fused_observation_and_auto_reset_frame(cuda_device, mode):
+    """GCA_FLAG_RENDER (the step kernel draws the frame itself) with the fused auto-reset: every frame equals what
+    stateless_step + conditional_reset of the two-call path return (stand-alone render kernel, pixel-checked against
+    the oracle in test_observation_parity / test_conditional_reset_parity) -- incl. the frames of envs that reset in
+    the step (restored grid / position, post-step dousing marks and day/night)."""
+    from parity_util import make_pair, random_actions, sync
+    from gym_cellular_automata_b200 import _lib
+    N = 10
+    envs = []
+    for fused in (False, True):
+        env, co, E, state, info = make_pair(N=N, K=2, mode="legacy", use_hidden=True, seed=13, obs_mode=mode)
+        ctx = state["per_env_context"]
+        ctx["fire_age"][ctx["true_grid"] == 2] = np.float32(3)   # fires die quickly: envs terminate and reset
+        ctx["time_step"][:] = np.arange(395, 395 + N, dtype=np.int32)  # day/night flips inside the run
+        ctx["dousing_count"][:, 8:12, 50:58] = 1
+        sync(env, state, as_snapshot=True)
+        envs.append(env)
+    two_call, fused_env = envs
+    two_call._can_fuse_render = lambda: False   # force the stand-alone render kernel on the two-call side
+    fused_env.auto_reset = True
+    rng = np.random.default_rng(3)
+    resets = 0
+    for step in range(14):
+        act = random_actions(rng, N, shoot_p=0.8)
+        tup = two_call.stateless_step(act)
+        resets += int(tup[2].sum())
+        tup = two_call.conditional_reset(tup, act)
+        obs, r, t, tr, inf = fused_env.stateless_step(act)
+        assert obs[0].dtype == (torch.uint8 if mode == "rgb_u8" else torch.float32)
+        assert torch.equal(obs[0], tup[0][0]), (step, torch.nonzero(obs[0] != tup[0][0])[:4])
+        assert torch.equal(r, tup[1])
+    assert resets > 0
+    # the device-level call returns the same frame as stateless_step would
+    a = torch.as_tensor(random_actions(rng, N), device="cuda")
+    out, rgb = fused_env.step_observe_device(a)
+    tup = two_call.conditional_reset(two_call.stateless_step(a), a)
+    assert torch.equal(rgb, tup[0][0])
