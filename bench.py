@@ -50,10 +50,14 @@ def parse():
     ap.add_argument("--substeps", type=int, default=4)
     ap.add_argument("--rng-mode", default="legacy")
     ap.add_argument("--no-hidden", action="store_true")
+    ap.add_argument("--hidden", default="random", choices=["random", "device", "reference"],
+                    help="hidden layers: iid synthetic (host NumPy), generated on the device (large grids), reference-like")
+    ap.add_argument("--generic-tiles", action="store_true", help="grids other than 64x64: force the generic tiled kernels")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--flush-mode", default="write+read", choices=["write", "write+read"],
                     help="L2 flush between timed steps: a 256 MiB write, or the write followed by a 256 MiB read sweep (clean L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the BASELINE config 3 / 4 lines (other_configs)")
     ap.add_argument("--no-obs-leg", action="store_true", help="skip the extra device-timed leg with RGB observations")
     ap.add_argument("--cpu-envs", type=int, default=256, help="envs of the CPU sample (cpu_baseline leg and --impl reference)")
     ap.add_argument("--cpu-steps", type=int, default=1024, help="env steps of the cpu_baseline sample (about 10-20 s of host work)")
@@ -276,6 +280,37 @@ def timed_steps(env, acts, first, n, flush, torch):
     return np.array([s.elapsed_time(e) * 1e3 for s, e in zip(starts, ends)])
 
 
+def other_config_line(torch, dev, peak, flush, size, n_envs, use_hidden, K, steps, warmup, label):
+    """One of the BASELINE configurations that are not the headline (config 3: 1024 envs of 256x256, hidden on / off;
+    config 4: one 4096x4096 grid): device-timed env steps with the L2 flushed, from reset + `warmup` steps (young
+    fires), device-generated hidden layers.  Same metric, same 7 B/cell/env-step roofline accounting."""
+    from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv
+    from gym_cellular_automata_b200.workload import random_actions
+    env = AdvancedForestFireBulldozerEnv(size, size, key=7, num_envs=n_envs, speed_move=0.12 * 4, speed_act=0.03 * 4,
+                                         use_hidden=use_hidden, substeps=K, seed=3, hidden="device", obs_mode="none",
+                                         auto_reset=True, collect_stats=True, device=dev)
+    env.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(11)
+    acts = random_actions(warmup + steps, n_envs, dev, gen)
+    for i in range(warmup):
+        env.step_device(acts[i])
+    torch.cuda.synchronize()
+    st0, l0 = env.stats(), env.kernel_launches
+    us = timed_steps(env, acts, warmup, steps, flush, torch)
+    d = (env.stats() - st0).astype(np.float64)
+    sub = max(d[5] * K, 1.0)
+    sec = float(us.mean()) * 1e-6
+    algo = ALGO_BYTES_PER_CELL * n_envs * size * size + ALGO_BYTES_PER_ENV * n_envs
+    return {"workload": label, "grid": [size, size], "envs": n_envs, "substeps": K, "hidden": "on (device-generated layers)" if use_hidden else "off",
+            "value": n_envs * size * size * K / sec, "unit": "cell-updates/s", "env_steps_per_s": n_envs / sec,
+            "us_per_step": sec * 1e6, "steps": steps, "warmup": warmup, "launches_per_step": (env.kernel_launches - l0) / steps,
+            "roofline": {"bound": "hbm", "achieved": algo / sec / 1e9, "peak": peak, "unit": "GB/s", "frac": algo / sec / 1e9 / peak,
+                         "algorithmic_bytes_per_launch": algo},
+            "front_cells_per_env_substep": d[0] / sub, "draws_per_env_substep": d[1] / sub, "threshold_cells": int(d[4]),
+            "phase": f"steps {warmup}..{warmup + steps} after reset (young fires), L2 flushed between steps"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -297,9 +332,9 @@ def run_ours(args):
     def make_env(n_envs, obs_mode="none", env_offset=0, total=None):
         e = AdvancedForestFireBulldozerEnv(
             size, size, key=1 + rank, num_envs=n_envs, speed_move=0.12 * 4, speed_act=0.03 * 4, use_hidden=not args.no_hidden,
-            substeps=K, rng_mode=args.rng_mode, seed=args.seed + rank + 1000 * env_offset, hidden="random", obs_mode=obs_mode,
+            substeps=K, rng_mode=args.rng_mode, seed=args.seed + rank + 1000 * env_offset, hidden=args.hidden, obs_mode=obs_mode,
             auto_reset=True, collect_stats=True, device=dev, balance_every=args.balance_every, env_offset=env_offset,
-            total_envs=total)
+            total_envs=total, generic_tiles=args.generic_tiles)
         e.reset()
         if args.preroll > 0:  # SETUP: stationary, phase-desynchronised mixture (not part of --warmup)
             stationary_preroll(e, args.preroll, args.preroll_groups, seed=args.seed + rank)
@@ -563,6 +598,18 @@ def run_ours(args):
                            "roofline_frac": (ALGO_BYTES_PER_CELL * 8192 * size * size + ALGO_BYTES_PER_ENV * 8192)
                            / (ms5 * 1e-3 / args.steps) / 1e9 / peak,
                            "workload_stats": wl(m5["d_stats"]), "per_rank": per_rank5}
+    if not args.no_other_configs and world == 1 and size == 64:
+        # reported beside the headline, not part of it: BASELINE configs 3 and 4 (parity at full size: tests/test_gpu_parity.py)
+        try:
+            line["other_configs"] = [
+                other_config_line(torch, dev, peak, flush, 256, 1024, True, 4, 24, 40,
+                                  "BASELINE config 3: 1024 envs of 256x256 (R = 6), hidden layers on; whole-grid bit-board kernel, one launch per env step"),
+                other_config_line(torch, dev, peak, flush, 256, 1024, False, 4, 24, 40,
+                                  "BASELINE config 3: 1024 envs of 256x256 (R = 6), hidden layers off"),
+                other_config_line(torch, dev, peak, flush, 4096, 1, True, 4, 16, 24,
+                                  "BASELINE config 4: one 4096x4096 grid (R = 10); generic tiled kernels (TMA-staged tiles, only tiles near fire are worked on)")]
+        except Exception as exc:
+            line["other_configs"] = {"error": f"{type(exc).__name__}: {exc}"}
     if not args.no_cpu_baseline and world == 1:
         if prev_affinity:
             os.sched_setaffinity(0, prev_affinity)

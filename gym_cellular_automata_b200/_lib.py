@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 # GCA_LIB_PATH selects another build of the same sources (A/B measurements of kernel variants)
 LIB_PATH = os.environ.get("GCA_LIB_PATH") or os.path.join(_HERE, "libgca.so")
-SOURCES = ("gca_step64.cu", "gca_hidden.cu", "gca_tiled.cu", "gca_windy.cu", "gca_aux.cu", "gca_abi.cu")
+SOURCES = ("gca_step64.cu", "gca_bb.cu", "gca_hidden.cu", "gca_tiled.cu", "gca_windy.cu", "gca_aux.cu", "gca_abi.cu")
 HEADERS = ("gca_common.cuh", os.path.join("..", "..", "include", "gca.h"))
 
 GCA_MAX_R = 10
@@ -26,6 +26,7 @@ FLAG_HOST_COPY_IN, FLAG_HOST_COPY_OUT = 32, 64
 FLAG_HOST_ASYNC = 128
 FLAG_HOST_MAPPED = 256
 FLAG_RENDER = 512
+FLAG_GENERIC_TILES = 1024
 GCA_VERSION = 104  # include/gca.h: the ctypes structures below mirror that version of the header
 
 

@@ -36,6 +36,9 @@ cudaError_t launch_tiled_env_step(const gca_params&, const gca_state&, const int
                                   const gca_inject&, uint32_t, uint8_t*, uint32_t*, int32_t*, uint8_t*, int, cudaStream_t);
 cudaError_t launch_auto_reset(const gca_params&, const gca_state&, const gca_state&, const float*, float*,
                               const uint8_t*, cudaStream_t);
+bool bb_supported(const gca_params&);
+cudaError_t launch_bb_env_step(const gca_params&, const gca_state&, const int32_t*, const gca_step_out&, const gca_inject&,
+                               uint32_t, cudaStream_t);
 }  // namespace gca
 
 static thread_local char g_err[256] = "";
@@ -191,6 +194,10 @@ static int env_step_impl(const gca_params* p, const gca_state* s, const int32_t*
     return check_cuda(gca::launch_env_step64(*p, st, actions, o, j, sn, snapshot_reward, flags, (cudaStream_t)stream),
                       "env_step64");
   }
+  if (gca::bb_supported(*p) && !(flags & GCA_FLAG_GENERIC_TILES)) {
+    // grids of whole 64-bit words up to 256x256: one launch per env step, the grid as bit-boards in shared memory
+    rc = check_cuda(gca::launch_bb_env_step(*p, st, actions, o, j, flags, (cudaStream_t)stream), "env_step_bb");
+  } else {
   // any other grid: tiled path, one launch per CA sub-step
   if (((long long)p->H * p->W) & 1) return fail(GCA_ERR_UNSUPPORTED, "gca_env_step: H*W must be even");
   if (!s->scratch_cell || !s->scratch_u32)
@@ -200,6 +207,7 @@ static int env_step_impl(const gca_params* p, const gca_state* s, const int32_t*
                                              reinterpret_cast<uint8_t*>(s->scratch_u32 + 14 * (size_t)s->N),
                                              (flags & GCA_FLAG_NO_TMA) ? 0 : 1, (cudaStream_t)stream),
                   "env_step_tiled");
+  }
   if (rc) return rc;
   if (flags & GCA_FLAG_AUTO_RESET) {
     if (!o.terminated) return fail(GCA_ERR_ARG, "gca_env_step: auto-reset on the tiled path needs out->terminated");

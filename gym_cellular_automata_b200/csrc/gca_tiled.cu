@@ -24,6 +24,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cstdlib>
+#include <cstring>
 
 #include "gca_common.cuh"
 
@@ -473,36 +474,142 @@ static bool make_tmap(CUtensorMap* m, const uint8_t* base, int N, int H, int W, 
 // the last one), the CA kernel on the active tiles (S.cell -> scratch_cell), the copy back.
 // scratch_cell: [N][H][W] u8; scratch_sched: [N][12] u32; scratch_counts: [N][2] i32;
 // tile_flags: [N][ceil(H/32)][ceil(W/64)] u8.
-cudaError_t launch_tiled_env_step(const gca_params& p, const gca_state& s, const int32_t* actions,
-                                  const gca_step_out& out, const gca_inject& inj, uint32_t flags, uint8_t* scratch_cell,
-                                  uint32_t* scratch_sched, int32_t* scratch_counts, uint8_t* tile_flags, int use_tma,
-                                  cudaStream_t st) {
+static cudaError_t enqueue_tiled_env_step(const gca_params& p, const gca_state& s, const int32_t* actions,
+                                          const gca_step_out& out, const gca_inject& inj, uint32_t flags,
+                                          uint8_t* scratch_cell, uint32_t* scratch_sched, int32_t* scratch_counts,
+                                          uint8_t* tile_flags, int use_tma, cudaStream_t st) {
   const int N = s.N, H = p.H, W = p.W, R = p.R;
   const int pitch = T_PITCH_MAX;
   const int rows = T_TH + 2 * R;
-  dim3 grid((W + T_TW - 1) / T_TW, (H + T_TH - 1) / T_TH, N);
+  const int TX = (W + T_TW - 1) / T_TW, TY = (H + T_TH - 1) / T_TH;
   cudaError_t err;
-  CUtensorMap tm;
-  memset(&tm, 0, sizeof(tm));
-  const bool tma = use_tma && make_tmap(&tm, s.cell, N, H, W, pitch, rows);
   // regrowth (p_tree > 0) can change any empty cell: every tile is active then
   const int all_active = p.p_tree > 0.0f ? 1 : 0;
   for (int j = 0; j < p.K; ++j) {
     const int last = j == p.K - 1;
     tiled_sched_kernel<<<(N + 127) / 128, 128, 0, st>>>(p, s, inj, j, scratch_sched);
     if (last && (err = cudaMemsetAsync(scratch_counts, 0, sizeof(int32_t) * 2 * N, st)) != cudaSuccess) return err;
-    tile_flags_kernel<<<grid, 128, 0, st>>>(H, W, s.cell, tile_flags, scratch_counts, last, all_active);
-    if (tma)
-      ca_tiled_kernel<true><<<grid, T_THREADS, 0, st>>>(p, s, inj, tm, s.cell, scratch_cell, scratch_sched,
-                                                        scratch_counts, out.stats, tile_flags, j, pitch);
-    else
-      ca_tiled_kernel<false><<<grid, T_THREADS, 0, st>>>(p, s, inj, tm, s.cell, scratch_cell, scratch_sched,
-                                                         scratch_counts, out.stats, tile_flags, j, pitch);
-    tile_apply_kernel<<<grid, 128, 0, st>>>(H, W, tile_flags, scratch_cell, s.cell);
+    // gridDim.z holds the env: at most 65535 envs per launch
+    for (int e0 = 0; e0 < N; e0 += 65535) {
+      const int ne = min(65535, N - e0);
+      dim3 grid(TX, TY, ne);
+      gca_state sv = s;  // the slice's view of the per-env arrays the tile kernels index by blockIdx.z
+      sv.N = ne;
+      const size_t cells = (size_t)e0 * H * W;
+      sv.cell = s.cell + cells;
+      sv.death = s.death + cells;
+      sv.hidden = s.hidden ? s.hidden + cells : nullptr;
+      sv.pslope = s.pslope ? s.pslope + cells * 8 : nullptr;
+      sv.doused = s.doused + (size_t)e0 * H * ((W + 63) >> 6);
+      sv.tick = s.tick + e0;
+      gca_inject jv = inj;  // injected fields are indexed [substep][N][...]: only whole-batch launches may use them
+      if (e0 > 0 || ne < N) {
+        if (inj.u_burn || inj.u_grow || inj.age_new) return cudaErrorInvalidValue;
+      }
+      CUtensorMap tm;
+      memset(&tm, 0, sizeof(tm));
+      const bool tma = use_tma && make_tmap(&tm, sv.cell, ne, H, W, pitch, rows);
+      uint8_t* tf = tile_flags + (size_t)e0 * TX * TY;
+      tile_flags_kernel<<<grid, 128, 0, st>>>(H, W, sv.cell, tf, scratch_counts + 2 * (size_t)e0, last, all_active);
+      if (tma)
+        ca_tiled_kernel<true><<<grid, T_THREADS, 0, st>>>(p, sv, jv, tm, sv.cell, scratch_cell + cells,
+                                                          scratch_sched + (size_t)e0 * SC_N, scratch_counts + 2 * (size_t)e0,
+                                                          out.stats, tf, j, pitch);
+      else
+        ca_tiled_kernel<false><<<grid, T_THREADS, 0, st>>>(p, sv, jv, tm, sv.cell, scratch_cell + cells,
+                                                           scratch_sched + (size_t)e0 * SC_N, scratch_counts + 2 * (size_t)e0,
+                                                           out.stats, tf, j, pitch);
+      tile_apply_kernel<<<grid, 128, 0, st>>>(H, W, tf, scratch_cell + cells, sv.cell);
+    }
     if ((err = cudaGetLastError()) != cudaSuccess) return err;
   }
   tiled_finish_kernel<<<(N + 127) / 128, 128, 0, st>>>(p, s, actions, out, scratch_counts, flags);
   return cudaGetLastError();
+}
+
+// The 4 K + 1 launches of one env step as ONE CUDA graph launch: at 4096x4096 with a small fire nearly every tile
+// exits at once and the step is bound by launch latency (85 us for K = 1).  The graph is captured once per set of
+// buffers (thread-local cache of one entry; a capture stream of its own: the caller's may be the legacy stream, which
+// cannot capture) and replayed with only the action pointer of the last kernel patched.  GCA_TILED_GRAPH=0 disables it.
+namespace {
+struct TiledGraphKey {
+  gca_params p; gca_state s; gca_step_out out; uint32_t flags; const void *a, *b, *c, *d; int use_tma;
+};
+struct TiledGraphCache {
+  bool valid = false, broken = false;
+  TiledGraphKey key;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphNode_t finish = nullptr;
+  cudaStream_t cap = nullptr;
+};
+thread_local TiledGraphCache g_tiled_graph;
+}  // namespace
+
+cudaError_t launch_tiled_env_step(const gca_params& p, const gca_state& s, const int32_t* actions,
+                                  const gca_step_out& out, const gca_inject& inj, uint32_t flags, uint8_t* scratch_cell,
+                                  uint32_t* scratch_sched, int32_t* scratch_counts, uint8_t* tile_flags, int use_tma,
+                                  cudaStream_t st) {
+  static const bool enabled = [] { const char* v = getenv("GCA_TILED_GRAPH"); return !(v && v[0] == '0'); }();
+  TiledGraphCache& G = g_tiled_graph;
+  const bool injected = inj.u_burn || inj.u_grow || inj.age_new || inj.u_wind || inj.wind_step;
+  if (!enabled || G.broken || injected)
+    return enqueue_tiled_env_step(p, s, actions, out, inj, flags, scratch_cell, scratch_sched, scratch_counts, tile_flags,
+                                  use_tma, st);
+  TiledGraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.p = p; key.s = s; key.out = out; key.flags = flags;
+  key.out.done_token = 0; key.out.rgb = nullptr; key.out.rgb_u8 = 0;  // per-step values no tiled kernel reads
+  key.out.host_done = nullptr; key.out.done_counter = nullptr;
+  key.a = scratch_cell; key.b = scratch_sched; key.c = scratch_counts; key.d = tile_flags; key.use_tma = use_tma;
+  auto fallback = [&]() {
+    G.broken = true;
+    cudaGetLastError();
+    return enqueue_tiled_env_step(p, s, actions, out, inj, flags, scratch_cell, scratch_sched, scratch_counts, tile_flags,
+                                  use_tma, st);
+  };
+  if (!G.valid || memcmp(&G.key, &key, sizeof(key)) != 0) {
+    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+    if (G.graph) { cudaGraphDestroy(G.graph); G.graph = nullptr; }
+    G.valid = false;
+    if (!G.cap && cudaStreamCreateWithFlags(&G.cap, cudaStreamNonBlocking) != cudaSuccess) return fallback();
+    if (cudaStreamBeginCapture(G.cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return fallback();
+    const cudaError_t e1 = enqueue_tiled_env_step(p, s, actions, out, inj, flags, scratch_cell, scratch_sched, scratch_counts,
+                                                  tile_flags, use_tma, G.cap);
+    const cudaError_t e2 = cudaStreamEndCapture(G.cap, &G.graph);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || !G.graph) return fallback();
+    size_t nn = 0;
+    if (cudaGraphGetNodes(G.graph, nullptr, &nn) != cudaSuccess || nn == 0) return fallback();
+    cudaGraphNode_t* nodes = new cudaGraphNode_t[nn];
+    cudaGraphGetNodes(G.graph, nodes, &nn);
+    G.finish = nullptr;
+    for (size_t i = 0; i < nn; ++i) {
+      cudaGraphNodeType ty;
+      if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+      cudaKernelNodeParams kp;
+      if (cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess && kp.func == (void*)tiled_finish_kernel) G.finish = nodes[i];
+    }
+    delete[] nodes;
+    if (!G.finish || cudaGraphInstantiate(&G.exec, G.graph, 0) != cudaSuccess) return fallback();
+    G.key = key;
+    G.valid = true;
+  }
+  // patch the one argument that changes from step to step
+  {
+    gca_params pp = p; gca_state ss = s; gca_step_out oo = out;
+    const int32_t* act = actions; const int32_t* cnt = scratch_counts; uint32_t fl = flags;
+    void* args[6] = {&pp, &ss, &act, &oo, &cnt, &fl};
+    cudaKernelNodeParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.func = (void*)tiled_finish_kernel;
+    kp.gridDim = dim3((s.N + 127) / 128);
+    kp.blockDim = dim3(128);
+    kp.sharedMemBytes = 0;
+    kp.kernelParams = args;
+    if (cudaGraphExecKernelNodeSetParams(G.exec, G.finish, &kp) != cudaSuccess) { G.valid = false; return fallback(); }
+  }
+  if (cudaGraphLaunch(G.exec, st) != cudaSuccess) { G.valid = false; return fallback(); }
+  return cudaSuccess;
 }
 
 }  // namespace gca

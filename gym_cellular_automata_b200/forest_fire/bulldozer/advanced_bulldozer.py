@@ -142,7 +142,8 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                  rng_mode: str = "legacy", seed: Optional[int] = None, hidden: str = "reference",
                  obs_mode: str = "rgb_f32", auto_reset: bool = False, ca_p_tree: float = 0.0,
                  p_wind_change: float = 0.06, collect_stats: bool = False, use_tma: bool = True,
-                 env_offset: int = 0, total_envs: Optional[int] = None, balance_every: int = 0, **kwargs):
+                 env_offset: int = 0, total_envs: Optional[int] = None, balance_every: int = 0,
+                 generic_tiles: bool = False, **kwargs):
         super().__init__(nrows, ncols, **kwargs)
         if not torch.cuda.is_available():
             raise _lib.GcaError("AdvancedForestFireBulldozerEnv needs a CUDA device (sm_100a); there is no CPU path")
@@ -224,6 +225,8 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         self._flags = 0 if use_hidden else _lib.FLAG_NO_HIDDEN
         if not use_tma:
             self._flags |= _lib.FLAG_NO_TMA
+        if generic_tiles:  # the tiled kernels even where the whole-grid bit-board kernel applies (tests, A/B runs)
+            self._flags |= _lib.FLAG_GENERIC_TILES
 
         self._set_spaces()
         self.ca = PartiallyObservableForestFireCUDA(nrows, self._empty, self._tree, self._fire, params=self._params,

@@ -67,6 +67,8 @@ typedef enum gca_status {
                                         and day/night (advanced_bulldozer.py:1103-1133); for an env that auto-resets in this step
                                         the frame conditional_reset draws (restored grid / position, post-step dousing marks and
                                         day/night, :462-487).  float32 [N][H][W][3], or uint8 when out->rgb_u8 != 0 */
+#define GCA_FLAG_GENERIC_TILES 1024u /* use the generic tiled kernels (one launch per CA sub-step) even for a grid the whole-grid
+                                        bit-board kernel takes (W % 64 == 0, H, W <= 256): tests / A-B measurements */
 #define GCA_FLAG_HOST_MAPPED 256u    /* gca_env_step_host: the caller guarantees that host_actions, host_reward, host_terminated and
                                         out->host_done are cudaHostAlloc'ed (pinned, mapped, device address == host address under
                                         unified addressing, e.g. torch pin_memory()): skips the per-call pointer queries */

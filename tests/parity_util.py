@@ -23,7 +23,7 @@ MODES = {"legacy": prng.LEGACY, "partitionable": prng.PARTITIONABLE}
 
 def make_pair(N=8, size=64, K=1, mode="legacy", use_hidden=True, seed=0, hidden="reference", p_tree=0.0,
               speed_mult=4.0, jax_seed=1, collect_stats=True, obs_mode="none", enable_extensions=False,
-              ncols=None, scatter_fire=0.0, use_tma=True, fast_slope=False):
+              ncols=None, scatter_fire=0.0, use_tma=True, fast_slope=False, generic_tiles=False):
     nrows, ncols = size, (ncols or size)
     slope_fn = None
     if fast_slope:
@@ -45,7 +45,7 @@ def make_pair(N=8, size=64, K=1, mode="legacy", use_hidden=True, seed=0, hidden=
                                          speed_act=0.03 * speed_mult, use_hidden=use_hidden, substeps=K,
                                          rng_mode=mode, seed=seed, hidden="random" if use_hidden else "reference",
                                          obs_mode=obs_mode, ca_p_tree=p_tree, collect_stats=collect_stats,
-                                         enable_extensions=enable_extensions, use_tma=use_tma)
+                                         enable_extensions=enable_extensions, use_tma=use_tma, generic_tiles=generic_tiles)
     sync(env, state, as_snapshot=True)
     return env, co, E, state, info
 

@@ -101,12 +101,28 @@ def test_dousing_heavy(cuda_device):
 @pytest.mark.parametrize("nrows,ncols,K,tma,N", [(32, 32, 2, True, 4), (128, 128, 1, True, 2), (256, 256, 1, True, 2),
                                                  (256, 256, 2, False, 1), (72, 40, 1, True, 3), (96, 80, 3, True, 2)])
 def test_tiled_parity(cuda_device, nrows, ncols, K, tma, N):
-    """Grids other than 64x64 go through the tiled kernel (TMA staging when W % 16 == 0, plain
+    """Grids other than 64x64 through the generic tiled kernels (TMA staging when W % 16 == 0, plain
     loads otherwise / on request): same bit-exact contract against the oracle."""
     from parity_util import make_pair, lockstep
     env, co, E, state, info = make_pair(N=N, size=nrows, ncols=ncols, K=K, mode="legacy", use_hidden=True, seed=5,
-                                        hidden="random", scatter_fire=0.01, use_tma=tma, fast_slope=True)
+                                        hidden="random", scatter_fire=0.01, use_tma=tma, fast_slope=True, generic_tiles=True)
     nbad, reports, stats = lockstep(env, co, state, 40, np.random.default_rng(6))
+    assert nbad == 0, _fmt(reports)
+    assert stats[1] > 0 and stats[2] > 0 and stats[3] > 0
+
+
+@pytest.mark.parametrize("nrows,ncols,K,N,mode,hidden,p_tree", [
+    (128, 128, 1, 3, "legacy", True, 0.0), (256, 256, 2, 2, "legacy", True, 0.0), (192, 192, 4, 2, "partitionable", True, 0.0),
+    (256, 256, 4, 2, "legacy", False, 0.0), (64, 128, 3, 3, "legacy", True, 0.0), (128, 256, 2, 2, "partitionable", False, 0.001),
+    (256, 64, 8, 2, "legacy", True, 0.0)])
+def test_bitboard_grid_kernel_parity(cuda_device, nrows, ncols, K, N, mode, hidden, p_tree):
+    """Grids of whole 64-bit words up to 256x256 (BASELINE config 3's grid) step with ONE launch per env step: the grid
+    as tree / fire / doused bit-boards in one CTA's shared memory, all K sub-steps on-chip (csrc/gca_bb.cu).  Lock step
+    with the oracle: both stream layouts, hidden layers on / off, regrowth, dousing, non-square grids."""
+    from parity_util import make_pair, lockstep
+    env, co, E, state, info = make_pair(N=N, size=nrows, ncols=ncols, K=K, mode=mode, use_hidden=hidden, seed=5,
+                                        hidden="random", scatter_fire=0.01, fast_slope=True, p_tree=p_tree)
+    nbad, reports, stats = lockstep(env, co, state, 40 // K + 12, np.random.default_rng(6), shoot_p=0.7)
     assert nbad == 0, _fmt(reports)
     assert stats[1] > 0 and stats[2] > 0 and stats[3] > 0
 
@@ -159,23 +175,36 @@ def test_two_waves_8192_envs_lockstep(cuda_device):
     assert np.array_equal(np.sort(order), np.arange(8192)), "the dealing must be a permutation of the envs"
 
 
+@pytest.mark.parametrize("hidden", [True, False])
+def test_config3_full_batch_256(cuda_device, hidden):
+    """BASELINE config 3 at its full size: 1024 envs of 256x256 (R = 6), hidden layers on and off, ten env steps of
+    K = 2 in lock step with the C oracle -- every state component of every env after every step (whole-grid
+    bit-board kernel, one launch per env step)."""
+    from parity_util import make_pair, lockstep
+    env, co, E, state, info = make_pair(N=1024, size=256, K=2, mode="legacy", use_hidden=hidden, seed=11, hidden="random",
+                                        scatter_fire=0.003, fast_slope=True)
+    nbad, reports, stats = lockstep(env, co, state, 10, np.random.default_rng(5))
+    assert nbad == 0, _fmt(reports)
+    assert stats[1] > 1000000 and stats[2] > 1000
+
+
 def test_tiled_many_envs_256(cuda_device):
-    """BASELINE config 3's grid (256x256, R = 6) with enough envs for several waves of tile CTAs (96 envs x 32 tiles):
-    three env steps of K = 2 in lock step with the C oracle."""
+    """The generic tiled kernels on config 3's grid with enough envs for several waves of tile CTAs (96 envs x 32
+    tiles): three env steps of K = 2 in lock step with the C oracle."""
     from parity_util import make_pair, lockstep
     env, co, E, state, info = make_pair(N=96, size=256, K=2, mode="legacy", use_hidden=True, seed=11, hidden="random",
-                                        scatter_fire=0.003, fast_slope=True)
+                                        scatter_fire=0.003, fast_slope=True, generic_tiles=True)
     nbad, reports, stats = lockstep(env, co, state, 3, np.random.default_rng(5))
     assert nbad == 0, _fmt(reports)
     assert stats[1] > 10000
 
 
 def test_large_single_grid_4096(cuda_device):
-    """BASELINE config 4: one 4096x4096 grid (R = 10, 21x21 heat window), two env steps."""
+    """BASELINE config 4: one 4096x4096 grid (R = 10, 21x21 heat window), eight env steps of K = 4 CA sub-steps."""
     from parity_util import make_pair, lockstep
-    env, co, E, state, info = make_pair(N=1, size=4096, K=1, mode="legacy", use_hidden=True, seed=2, hidden="random",
+    env, co, E, state, info = make_pair(N=1, size=4096, K=4, mode="legacy", use_hidden=True, seed=2, hidden="random",
                                         scatter_fire=0.002, fast_slope=True)
-    nbad, reports, stats = lockstep(env, co, state, 2, np.random.default_rng(1))
+    nbad, reports, stats = lockstep(env, co, state, 8, np.random.default_rng(1))
     assert nbad == 0, _fmt(reports)
     assert stats[1] > 1000
 

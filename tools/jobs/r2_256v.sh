@@ -1,0 +1,12 @@
+#!/bin/bash
+for v in "$@"; do
+GCA_LIB_PATH=build/variants/$v.so python bench.py --size 256 --envs-per-gpu 1024 --hidden device --steps 30 --warmup 40 --preroll 0 --no-cpu-baseline --no-obs-leg --no-other-configs --long-run 0 > gpurun_out/t256.json 2> gpurun_out/t256.err
+python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/t256.json"))
+    print("256x256x1024 [$v]: us/step %.1f value %.3e warm %.3e frac %.3f" % (d["ms_per_step"]*1e3, d["value"], d["value_l2_warm"], d["roofline"]["frac"]))
+except Exception as e:
+    print("failed", e); print(open("gpurun_out/t256.err").read()[-1500:])
+PY
+done

@@ -2,7 +2,7 @@
 # A/B of variant libraries on the default bench workload, interleaved twice
 for rep in 1 2; do
 for v in "$@"; do
-  GCA_SKIP_VERSION_CHECK=1 GCA_LIB_PATH=build/variants/$v.so python bench.py --steps 128 --warmup 8 --no-cpu-baseline --no-obs-leg --long-run 0 > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
+  GCA_SKIP_VERSION_CHECK=1 GCA_LIB_PATH=build/variants/$v.so python bench.py --steps 128 --warmup 8 --no-cpu-baseline --no-obs-leg --no-other-configs --long-run 0 > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
   python - <<PY
 import json
 try:

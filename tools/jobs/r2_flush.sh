@@ -1,7 +1,7 @@
 #!/bin/bash
 for rep in 1 2; do
 for m in write write+read; do
-  python bench.py --steps 128 --warmup 8 --no-cpu-baseline --no-obs-leg --long-run 0 --flush-mode $m > gpurun_out/fl_$m.json 2> gpurun_out/fl_$m.err
+  python bench.py --steps 128 --warmup 8 --no-cpu-baseline --no-obs-leg --no-other-configs --long-run 0 --flush-mode $m > gpurun_out/fl_$m.json 2> gpurun_out/fl_$m.err
   python - <<PY
 import json
 try:

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 for s in 0 3 5 7 9 11 14; do
-  GCA_BALANCE_SKEW=$s python bench.py --steps 192 --warmup 16 --preroll 512 --preroll-groups 32 --no-cpu-baseline --no-obs-leg --long-run 0 > gpurun_out/r2_skew_$s.json 2> gpurun_out/r2_skew_$s.err
+  GCA_BALANCE_SKEW=$s python bench.py --steps 192 --warmup 16 --preroll 512 --preroll-groups 32 --no-cpu-baseline --no-obs-leg --no-other-configs --long-run 0 > gpurun_out/r2_skew_$s.json 2> gpurun_out/r2_skew_$s.err
   python - <<PY
 import json
 d=json.load(open("gpurun_out/r2_skew_$s.json"))

@@ -1,7 +1,7 @@
 #!/bin/bash
 # bench the listed variant libraries (build/variants/NAME.so) on the stationary workload
 for v in "$@"; do
-  GCA_LIB_PATH=build/variants/$v.so python bench.py --steps 192 --warmup 16 --preroll 512 --preroll-groups 32 --no-cpu-baseline --no-obs-leg --long-run 0 > gpurun_out/var_$v.json 2> gpurun_out/var_$v.err
+  GCA_LIB_PATH=build/variants/$v.so python bench.py --steps 192 --warmup 16 --preroll 512 --preroll-groups 32 --no-cpu-baseline --no-obs-leg --no-other-configs --long-run 0 > gpurun_out/var_$v.json 2> gpurun_out/var_$v.err
   python - <<PY
 import json
 try:
