@@ -20,40 +20,28 @@ def shard_range(num_envs: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, min(lo + per, num_envs)
 
 
-class EpisodeStatistics:
-    """Per-env running episode statistics with the fields of the reference's EpisodeStatistics
-    (agents/jax_ppo.py:379-398): running returns / lengths and the values of the last finished
-    episode.  Plain tensor ops on (N,) vectors; lives on whatever device the env uses."""
-
-    def __init__(self, num_envs: int, device="cpu"):
-        z = lambda dt: torch.zeros(num_envs, dtype=dt, device=device)  # noqa: E731
-        self.episode_returns = z(torch.float32)
-        self.episode_lengths = z(torch.int32)
-        self.returned_episode_returns = z(torch.float32)
-        self.returned_episode_lengths = z(torch.int32)
-
-    def update(self, reward: torch.Tensor, terminated: torch.Tensor) -> None:
-        done = terminated.bool()
-        ret = self.episode_returns + reward
-        ln = self.episode_lengths + 1
-        self.returned_episode_returns = torch.where(done, ret, self.returned_episode_returns)
-        self.returned_episode_lengths = torch.where(done, ln, self.returned_episode_lengths)
-        self.episode_returns = torch.where(done, torch.zeros_like(ret), ret)
-        self.episode_lengths = torch.where(done, torch.zeros_like(ln), ln)
-
-    def as_dict(self) -> Dict[str, torch.Tensor]:
-        return {k: getattr(self, k) for k in ("episode_returns", "episode_lengths", "returned_episode_returns",
-                                              "returned_episode_lengths")}
-
-
 def gather_episode_stats(stats: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:
-    """All-gather every (N_local,) leaf into a (world * N_local,) tensor ordered by rank, i.e. by
-    global env index.  No-op without an initialised process group."""
+    """All-gather every per-env leaf into a (world * N_local, ...) tensor ordered by rank, i.e. by global env index --
+    the reference's ``gather_stats`` (agents/jax_ppo.py:1330-1343).  The 4-byte (N_local,) leaves (float32 / int32: all
+    fields of ``rollout_stats.EpisodeStatistics`` and the env's info counters) travel in ONE collective, packed as bit
+    patterns; anything else is gathered leaf by leaf.  No-op without an initialised process group."""
     if not (dist.is_available() and dist.is_initialized()):
         return dict(stats)
     world = dist.get_world_size(group)
     out = {}
+    packed = [k for k, v in stats.items() if v.dim() == 1 and v.element_size() == 4]
+    if packed:
+        n = stats[packed[0]].shape[0]
+        packed = [k for k in packed if stats[k].shape[0] == n]
+        send = torch.stack([stats[k].contiguous().view(torch.int32) for k in packed], dim=0).reshape(-1)  # L x n bit patterns
+        recv = torch.empty(world * send.numel(), dtype=torch.int32, device=send.device)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        recv = recv.view(world, len(packed), n)
+        for i, k in enumerate(packed):
+            out[k] = recv[:, i, :].reshape(world * n).view(stats[k].dtype)
     for k, v in stats.items():
+        if k in out:
+            continue
         v = v.contiguous()
         buf = torch.empty((world * v.shape[0],) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
         dist.all_gather_into_tensor(buf, v, group=group)

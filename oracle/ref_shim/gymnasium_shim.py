@@ -8,11 +8,28 @@ import types
 import numpy as np
 
 
+# Reproducible vector generation: the reference never seeds its spaces / env generator, so a stand-in seeded from the
+# OS would make every run of tests/golden/make_reference_golden.py different.  seed_all(s) makes every generator that is
+# created WITHOUT a seed afterwards draw its seed from one stream started at s (creation order is deterministic).
+_SEED_SOURCE = None
+
+
+def seed_all(seed=None):
+    global _SEED_SOURCE
+    _SEED_SOURCE = None if seed is None else np.random.default_rng(seed)
+
+
+def _fresh_rng(seed=None):
+    if seed is None and _SEED_SOURCE is not None:
+        seed = int(_SEED_SOURCE.integers(0, 2 ** 62))
+    return np.random.default_rng(seed)
+
+
 class Space:
     def __init__(self, shape=None, dtype=None, seed=None):
         self._shape = None if shape is None else tuple(shape)
         self.dtype = None if dtype is None else np.dtype(dtype)
-        self._np_random = np.random.default_rng(seed)
+        self._np_random = _fresh_rng(seed)
 
     @property
     def shape(self):
@@ -23,7 +40,7 @@ class Space:
         return self._np_random
 
     def seed(self, seed=None):
-        self._np_random = np.random.default_rng(seed)
+        self._np_random = _fresh_rng(seed)
         return [seed]
 
     def contains(self, x):
@@ -125,7 +142,7 @@ class Env:
     @property
     def np_random(self):
         if not hasattr(self, "_np_random"):
-            self._np_random = np.random.default_rng()
+            self._np_random = _fresh_rng()
         return self._np_random
 
 
@@ -144,7 +161,7 @@ def build_modules():
     g.logger = logger
     utils = types.ModuleType("gymnasium.utils")
     seeding = types.ModuleType("gymnasium.utils.seeding")
-    seeding.np_random = lambda seed=None: (np.random.default_rng(seed), seed)
+    seeding.np_random = lambda seed=None: (_fresh_rng(seed), seed)
     utils.seeding = seeding
     g.utils = utils
     error = types.ModuleType("gymnasium.error")

@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from oracle import prng, ref_shim  # noqa: E402
-from oracle.ref_shim import jax_shim  # noqa: E402
+from oracle.ref_shim import gymnasium_shim, jax_shim  # noqa: E402
 
 CASES = {
     # name: grid size, envs, steps, stream layout, hidden layers, extensions, seed, start-state recipe
@@ -74,6 +74,7 @@ def run_case(name, case, ab, jnp):
     jax_shim.set_rng_mode(case["mode"])
     np.random.seed(case["seed"])
     random.seed(case["seed"])
+    gymnasium_shim.seed_all(case["seed"])  # the spaces' / env's own generators (the reference leaves them unseeded)
     jax = sys.modules["jax"]
 
     class TraceOnce(ab.AdvancedForestFireBulldozerEnv):
@@ -364,18 +365,19 @@ def run_rollout_stats(N=37, steps=40, seed=41):
     return out
 
 
-if __name__ == "__main__":
-    # usage: make_reference_golden.py [--only name[,name...]]   (names: the CASES keys, v3_32x48, operator_edges, constants, rollout_stats);
-    # with --only the other sections of the existing file are kept as they are
+GOLDEN_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_shim_golden.npz")
+
+
+def generate(only=None, keep=None):
+    """All sections (or the names in ``only``) as a dict of arrays; ``keep`` = arrays of an existing file whose
+    sections are not regenerated.  Deterministic: every generator the reference leaves unseeded is seeded from the case
+    seed (np.random / random / the shim's spaces), so a rerun reproduces the committed file array by array."""
     assert ref_shim.available(), "the reference tree is needed to generate these vectors"
     import contextlib
     import io
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_shim_golden.npz")
-    only = set(sys.argv[sys.argv.index("--only") + 1].split(",")) if "--only" in sys.argv else None
     out = {}
-    if only is not None:
-        old = np.load(path)
-        out = {k: old[k] for k in old.files if k.split("/")[0] not in only}
+    if only is not None and keep is not None:
+        out = {k: keep[k] for k in keep.files if k.split("/")[0] not in only}
     jax = ref_shim.install(prng.LEGACY)
     ab = ref_shim.load("forest_fire.bulldozer.advanced_bulldozer")
     for name, case in CASES.items():
@@ -388,6 +390,7 @@ if __name__ == "__main__":
         for k, v in res.items():
             out[f"{name}/{k}"] = v
     jax_shim.set_rng_mode(prng.LEGACY)
+    gymnasium_shim.seed_all(1)
     if only is None or "v3_32x48" in only:
         for k, v in run_v3(ref_shim).items():
             out[f"v3_32x48/{k}"] = v
@@ -404,5 +407,14 @@ if __name__ == "__main__":
     if only is None or "rollout_stats" in only:
         for k, v in run_rollout_stats().items():
             out[f"rollout_stats/{k}"] = v
-    np.savez_compressed(path, **out)
-    print("wrote", path, os.path.getsize(path), "bytes")
+    gymnasium_shim.seed_all(None)
+    return out
+
+
+if __name__ == "__main__":
+    # usage: make_reference_golden.py [--only name[,name...]]   (names: the CASES keys, v3_32x48, operator_edges, constants, rollout_stats);
+    # with --only the other sections of the existing file are kept as they are
+    only = set(sys.argv[sys.argv.index("--only") + 1].split(",")) if "--only" in sys.argv else None
+    out = generate(only, np.load(GOLDEN_PATH) if only is not None else None)
+    np.savez_compressed(GOLDEN_PATH, **out)
+    print("wrote", GOLDEN_PATH, os.path.getsize(GOLDEN_PATH), "bytes")

@@ -251,19 +251,28 @@ def test_host_generators_match_literal_restatement():
 def _gloo_worker(rank, world, port, ret):
     import torch
     import torch.distributed as dist
-    from gym_cellular_automata_b200.distributed import EpisodeStatistics, gather_episode_stats, shard_range
+    from gym_cellular_automata_b200.distributed import gather_episode_stats, shard_range
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
         total = 10
         lo, hi = shard_range(total, rank, world)
         n = hi - lo
-        st = EpisodeStatistics(n)
+        # the per-env statistics of the rollout loop (on a GPU: rollout_stats.EpisodeStatistics, one kernel per step)
+        st = {"episode_returns": torch.zeros(n), "episode_lengths": torch.zeros(n, dtype=torch.int32),
+              "returned_episode_returns": torch.zeros(n), "returned_episode_lengths": torch.zeros(n, dtype=torch.int32)}
         # env e earns reward -(e+1) per step and terminates on step 3 if e is even
         for step in range(4):
             reward = -torch.arange(lo + 1, hi + 1, dtype=torch.float32)
             term = torch.tensor([(e % 2 == 0) and step == 2 for e in range(lo, hi)])
-            st.update(reward, term)
-        g = gather_episode_stats(st.as_dict())
+            ret_, len_ = st["episode_returns"] + reward, st["episode_lengths"] + 1
+            st["returned_episode_returns"] = torch.where(term, ret_, st["returned_episode_returns"])
+            st["returned_episode_lengths"] = torch.where(term, len_, st["returned_episode_lengths"])
+            st["episode_returns"] = torch.where(term, torch.zeros_like(ret_), ret_)
+            st["episode_lengths"] = torch.where(term, torch.zeros_like(len_), len_)
+        st["keys"] = torch.arange(2 * lo, 2 * hi, dtype=torch.int64).reshape(n, 2)   # a leaf that is not 4-byte / 1-D
+        g = gather_episode_stats(st)
+        assert g["keys"].tolist() == [[2 * e, 2 * e + 1] for e in range(total)]
+        del g["keys"]
         ret[rank] = {k: v.tolist() for k, v in g.items()}
     finally:
         dist.destroy_process_group()

@@ -545,3 +545,24 @@ def test_reference_source_runs_live_under_the_shim():
         for k in [k for k in sys.modules if k.split(".")[0] in ("jax", "flax", "gymnasium", "gym_cellular_automata")]:
             del sys.modules[k]
         sys.modules.update({k: v for k, v in saved.items() if v is not None})
+
+
+def test_reference_golden_is_reproducible():
+    """tests/golden/make_reference_golden.py is deterministic: regenerating sections from the reference's source (every
+    generator the reference leaves unseeded is seeded from the case seed) reproduces the committed arrays exactly.
+    Needs /root/reference (skipped on the GPU box)."""
+    import importlib.util
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("the reference tree is not mounted here")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_reference_golden.py")
+    spec = importlib.util.spec_from_file_location("make_reference_golden", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    committed = np.load(mod.GOLDEN_PATH)
+    out = mod.generate(only={"ref64_partitionable", "v3_32x48", "rollout_stats", "constants"})
+    assert len(out) > 50
+    for k, v in out.items():
+        v = np.asarray(v)
+        assert k in committed.files, k
+        assert v.shape == committed[k].shape and np.array_equal(v, committed[k]), k
