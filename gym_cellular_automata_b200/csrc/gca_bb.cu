@@ -23,12 +23,14 @@ namespace {
 
 constexpr int BB_THREADS = 256;
 constexpr int BB_LIST_CAP = 4096;  // front cells the balanced list holds; larger fronts are walked word by word
+constexpr int BB_BURN_CAP = 1024;  // burn-outs of one env step the burn list holds (beyond: per-sub-step scans)
 #define BB_LO 0.9998779296875f     /* 1 - 2^-13: (2R+1)^2 <= 441 terms -> |err| <= 441 u |sum| */
 #define BB_HI 1.0001220703125f     /* 1 + 2^-13 */
 
 struct BbScalars {
   uint32_t sched[GCA_MAX_K][12];  // per sub-step: Sburn[2] Sgrow[2] ak1[2] ak2[2] wind change step pad
   int nfront;
+  int nburn;                      // entries on the burn list (> BB_BURN_CAP: overflow, the list is not used)
   int cnt_tree, cnt_fire;
   unsigned int n_draws, n_ign, n_ext, n_thresh, n_front;
 };
@@ -150,6 +152,7 @@ __device__ void bb_key_schedule(BbScalars& sc, const gca_params& P, const gca_st
 struct BbView {
   unsigned long long *tree, *fire, *dous, *ign;
   uint16_t* list;
+  uint32_t* burn;   // cells that burn out during this env step: (row << 8 | col) << 3 | sub-step
   BbScalars* sc;
 };
 
@@ -265,7 +268,9 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
   v.dous = v.fire + HW;
   v.ign = v.dous + HW;
   v.list = reinterpret_cast<uint16_t*>(v.ign + HW);
-  v.sc = reinterpret_cast<BbScalars*>(v.list + BB_LIST_CAP);
+  v.burn = reinterpret_cast<uint32_t*>(v.list + BB_LIST_CAP);
+  v.sc = reinterpret_cast<BbScalars*>(v.burn + BB_BURN_CAP);
+  const uint32_t inv_ww = (65536u + (uint32_t)WW - 1u) / (uint32_t)WW;  // i / WW = (i * inv_ww) >> 16 for i < 1024
   BbScalars& sc = *v.sc;
   const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const size_t env_off = (size_t)e * H * W;
@@ -274,7 +279,7 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
   const uint32_t half_burn = (uint32_t)((9ull * H * W) >> 1);
 
   if (tid == 0) {
-    sc.cnt_tree = 0; sc.cnt_fire = 0;
+    sc.cnt_tree = 0; sc.cnt_fire = 0; sc.nburn = 0;
     sc.n_draws = 0; sc.n_ign = 0; sc.n_ext = 0; sc.n_thresh = 0; sc.n_front = 0;
   }
   // ---- grid -> bit-boards (warp 0 walks the key chains meanwhile) --------------------------------------------------
@@ -288,6 +293,60 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
     v.ign[i] = 0ull;
   }
   __syncthreads();
+
+  // ---- burn-outs of the whole env step, found ONCE: the burn-out ticks of the words that hold fire are read 64 cells at
+  //      a time; a burning cell whose tick falls inside [tick0, tick0 + K) goes on the burn list with its sub-step and its
+  //      tick is cleared (fire_age ends at 0; nothing reads it before).  A list that overflows is dropped: the sub-steps
+  //      then scan for their own burn-outs.
+  for (int i = tid; i < HW; i += BB_THREADS) {
+    const unsigned long long f_old = v.fire[i];
+    if (!f_old) continue;
+    const int r = (int)(((uint32_t)i * inv_ww) >> 16), w = i - r * WW;
+    uint4* dp = reinterpret_cast<uint4*>(S.death + env_off + (size_t)i * 64);
+    uint4 dv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dv[q] = dp[q];
+    unsigned long long due = 0ull;
+    unsigned long long w0 = 0ull, w1 = 0ull, w2 = 0ull;  // bit planes of the sub-step (K <= 8)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t ww[4] = {dv[q].x, dv[q].y, dv[q].z, dv[q].w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int b = 8 * q + k;
+        const uint32_t d = (ww[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+        const uint32_t rr = (d - tick0) & 0xFFFFu;
+        const unsigned long long hit = (((f_old >> b) & 1ull) && rr < (uint32_t)K) ? 1ull : 0ull;
+        due |= hit << b;
+        w0 |= (hit & (unsigned long long)(rr & 1u)) << b;
+        w1 |= (hit & (unsigned long long)((rr >> 1) & 1u)) << b;
+        w2 |= (hit & (unsigned long long)((rr >> 2) & 1u)) << b;
+      }
+    }
+    if (due) {
+      const int n = __popcll(due);
+      const int base = atomicAdd(&sc.nburn, n);
+      int at = base;
+      unsigned long long m = due;
+      while (m) {
+        const int b = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const uint32_t sub = (uint32_t)((w0 >> b) & 1ull) | ((uint32_t)((w1 >> b) & 1ull) << 1) | ((uint32_t)((w2 >> b) & 1ull) << 2);
+        if (at < BB_BURN_CAP) v.burn[at] = ((((uint32_t)r << 8) | (uint32_t)(w * 64 + b)) << 3) | sub;
+        ++at;
+      }
+    }
+  }
+  __syncthreads();
+  const int nburn = sc.nburn;
+  const bool burn_listed = nburn <= BB_BURN_CAP;
+  if (burn_listed) {
+    // the listed cells' ticks end at 0 (scattered 2-byte stores: a handful per env step)
+    for (int i = tid; i < nburn; i += BB_THREADS) {
+      const uint32_t cellrc = v.burn[i] >> 3;
+      S.death[env_off + (size_t)(cellrc >> 8) * W + (cellrc & 255u)] = 0;
+    }
+  }
 
   uint32_t n_draws = 0, n_thresh = 0, n_ign = 0, n_ext = 0;
   for (int j = 0; j < K; ++j) {
@@ -306,7 +365,7 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
       const int i = tid + q * BB_THREADS;
       fr[q] = 0ull;
       if (i < HW) {
-        const int r = i / WW, w = i - r * WW;
+        const int r = (int)(((uint32_t)i * inv_ww) >> 16), w = i - r * WW;
         unsigned long long dil = 0ull;
 #pragma unroll
         for (int dr = -1; dr <= 1; ++dr) {
@@ -333,7 +392,7 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
         const int i = tid + q * BB_THREADS;
         unsigned long long m = fr[q];
         if (m) {
-          const int r = i / WW, w = i - r * WW;
+          const int r = (int)(((uint32_t)i * inv_ww) >> 16), w = i - r * WW;
           while (m) {
             const int b = __ffsll((long long)m) - 1;
             m &= m - 1;
@@ -352,7 +411,7 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
       for (int q = 0; q < MAXW; ++q) {
         const int i = tid + q * BB_THREADS;
         unsigned long long m = fr[q];
-        const int r = i / WW, w = i - r * WW;
+        const int r = (int)(((uint32_t)i * inv_ww) >> 16), w = i - r * WW;
         while (m) {
           const int b = __ffsll((long long)m) - 1;
           m &= m - 1;
@@ -363,14 +422,26 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
     if (tid == 0) sc.n_front += (unsigned)nfront;
     __syncthreads();
     // ---- apply: ignitions (fire-age draws), burn-outs, regrowth -----------------------------------------------------
+    if (burn_listed) {
+      // this sub-step's burn-outs join the ignition bits in v.ign (ignitions are tree cells, burn-outs fire cells)
+      for (int i = tid; i < nburn; i += BB_THREADS) {
+        const uint32_t ent = v.burn[i];
+        if ((int)(ent & 7u) != j) continue;
+        const uint32_t cellrc = ent >> 3, col = cellrc & 255u;
+        atomicOr(v.ign + (cellrc >> 8) * WW + (col >> 6), 1ull << (col & 63));
+      }
+      __syncthreads();
+    }
     const TfKey ka1 = tf_key(sr[4], sr[5]), ka2 = tf_key(sr[6], sr[7]), kg = tf_key(sr[2], sr[3]);
     for (int i = tid; i < HW; i += BB_THREADS) {
-      const int r = i / WW, w = i - r * WW;
-      const unsigned long long I = v.ign[i];
+      const int r = (int)(((uint32_t)i * inv_ww) >> 16), w = i - r * WW;
       const unsigned long long t_old = v.tree[i], f_old = v.fire[i];
-      unsigned long long ext = 0ull, grow = 0ull;
-      if (f_old) {
-        // burn-out ticks of the word's 64 cells: a burning cell whose tick is due goes out, its age ends at 0
+      const unsigned long long marks = v.ign[i];
+      const unsigned long long I = marks & t_old;
+      unsigned long long ext = marks & f_old, grow = 0ull;
+      if (marks) v.ign[i] = 0ull;
+      if (f_old && !burn_listed) {
+        // (burn list overflow) burn-out ticks of the word's 64 cells: a burning cell whose tick is due goes out
         uint4* dp = reinterpret_cast<uint4*>(S.death + env_off + (size_t)i * 64);
         uint4 dv[8];
 #pragma unroll
@@ -393,7 +464,6 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
         }
       }
       if (I) {
-        v.ign[i] = 0ull;
         unsigned long long m = I;
         while (m) {
           const int b = __ffsll((long long)m) - 1;
@@ -514,7 +584,7 @@ bool bb_supported(const gca_params& p) {
 cudaError_t launch_bb_env_step(const gca_params& p, const gca_state& s, const int32_t* actions, const gca_step_out& out,
                                const gca_inject& inj, uint32_t flags, cudaStream_t st) {
   const int HW = p.H * (p.W >> 6);
-  const size_t smem = (size_t)HW * 8 * 4 + BB_LIST_CAP * sizeof(uint16_t) + sizeof(BbScalars) + 16;
+  const size_t smem = (size_t)HW * 8 * 4 + BB_LIST_CAP * sizeof(uint16_t) + BB_BURN_CAP * sizeof(uint32_t) + sizeof(BbScalars) + 16;
   switch (p.R) {
     case 4: return launch_bb_instance<4>(p, s, actions, out, inj, flags, smem, st);
     case 5: return launch_bb_instance<5>(p, s, actions, out, inj, flags, smem, st);

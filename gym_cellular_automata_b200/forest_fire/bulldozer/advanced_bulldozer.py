@@ -532,6 +532,17 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         self._out.terminated.zero_()
         return (rgb, self._context_view()), info
 
+    def _kernels_per_step(self, auto_reset: bool) -> int:
+        """libgca kernels one env step launches: 64x64 -- the fused kernel; whole-grid bit-board grids (W % 64 == 0, up to
+        256x256) -- one kernel (+ the reset kernel); anything else -- 4 per CA sub-step + the epilogue, replayed as one
+        CUDA graph (+ the reset kernel)."""
+        if self._state.work is not None:
+            return 1
+        H, W, R = self.nrows, self.ncols, int(self._params.R)
+        bb = (W % 64 == 0 and W <= 256 and H <= 256 and H * W <= 65536 and 4 <= R <= 6
+              and not (self._flags & _lib.FLAG_GENERIC_TILES))
+        return (1 if bb else 4 * self.substeps + 1) + (1 if auto_reset else 0)
+
     def _can_fuse_render(self) -> bool:
         """The step kernel draws the observation itself (GCA_FLAG_RENDER): 64x64 grids without extensions."""
         return (self.obs_mode != "none" and not self.enable_extensions and self._state is not None
@@ -562,7 +573,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                 self._state.rebalance()
                 self._steps_since_balance = 0
                 self.kernel_launches += 1
-        self.kernel_launches += 1 if self._state.work is not None else 4 * self.substeps + 1
+        self.kernel_launches += self._kernels_per_step(bool(flags & _lib.FLAG_AUTO_RESET))
         if inject is None:
             # hot path: every struct pointer is cached; only the action pointer and the stream vary
             fa = self._fast_args
@@ -718,7 +729,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                 self._state.rebalance()
                 self._steps_since_balance = 0
                 self.kernel_launches += 1
-        self.kernel_launches += 1 if self._state.work is not None else 4 * self.substeps + 1
+        self.kernel_launches += self._kernels_per_step(self.auto_reset)
         self._out.next_token()
         stream = torch.cuda.current_stream().cuda_stream
         rc = ha[1](ha[2], ha[3], actions_host.data_ptr(), ha[4], ha[5], ha[6], ha[7], flags, ha[8], ha[9], stream)
