@@ -511,8 +511,9 @@ def run_ours(args):
         dist.all_gather_into_tensor(allr, mine)
         a = allr.cpu().numpy()
         per_rank = {"device_ms_per_step": [float(x) / args.steps for x in a[:, 0]],
-                    "e2e_us_per_step": [float(x) / args.steps * 1e6 for x in a[:, 2]],
-                    "e2e_sync_us_per_step": [float(x) / args.steps * 1e6 for x in a[:, 3]]}
+                    "e2e_us_per_step": [float(x) / args.steps * 1e6 for x in a[:, 3]]}
+        if args.two_group:
+            per_rank["e2e_two_group_us_per_step"] = [float(x) / args.steps * 1e6 for x in a[:, 2]]
         return [float(x) for x in a.max(0)], per_rank
 
     (ms, ms_warm, e2e_s, e2e_sync_s), per_rank = reduce_ranks(m)
