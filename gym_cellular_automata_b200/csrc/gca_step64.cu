@@ -918,9 +918,11 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   }
   if (active) {
     // the chain warp finished this env's key chain long ago (it runs while the grids stream in); no CTA barrier
+    S64_MARK();
     while (smem_ld_acquire(&sm.chain_done) == 0) __nanosleep(40);
     __syncwarp();
     key_sides(sm, P, J, N, e, lane, widx);
+    S64_ACC(28);   // trace: wait for the key chain + key sides
     if (lane == 0) {
       S.key[2 * e] = sm.hot.x;
       S.key[2 * e + 1] = sm.hot.y;
@@ -1022,7 +1024,9 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         cs.nch[warp] = ((cnt + 31) >> 5) | (nsc << 16);
         if (gwarp == 0) cs.next[group] = 0;
       }
+      S64_MARK();
       group_sync(group);
+      S64_ACC(27);   // trace: wait at the barrier that opens the pooled phase (summed over the sub-steps)
 
       // ---------------- pooled phase: work items = 32-entry chunks of every env's front list -------
       {
@@ -1242,7 +1246,6 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         store_row_views(sm.fire32 + (2 * lane + 5) * 4, f1);
       }
       __syncwarp();
-      S64_ACC(28);
     }
   }
   if (active && sm.nign > 0) {

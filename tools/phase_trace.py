@@ -80,7 +80,7 @@ for mode in ("cold", "warm", "cold", "warm"):
         ce, *_ = np.linalg.lstsq(Xe, feat[:, 3], rcond=None)
         print("  per-env fit of finish time on [1, entries, pairs, rows]:", np.round(ce, 2).tolist())
     acc = o.stats[8:].cpu().numpy().reshape(N, 32)[:, 27:30].astype(np.float64).mean(0) / K
-    print("  owner phases per sub-step (mean): ignition list + age draws %.1fk, burn-outs + state + views %.1fk, front masks + list extension %.1fk" % tuple(acc / 1e3))
+    print("  per env step (mean): wait at the pooled phases' opening barriers %.1fk, key-chain wait + key sides %.1fk ; per sub-step: front masks + list extension %.1fk" % (acc[0] * K / 1e3, acc[1] * K / 1e3, acc[2] / 1e3))
     pool = o.stats[8:].cpu().numpy().reshape(N, 32)[:, 30:32].astype(np.float64).mean(0)
     print("  pooled work per warp and env step (mean): scan rounds %.1fk, cell chunks %.1fk cycles" % tuple(pool / 1e3))
     extra = tr[:, 16:20].mean(0)
