@@ -610,7 +610,10 @@ def run_ours(args):
                 other_config_line(torch, dev, peak, flush, 256, 1024, False, 4, 24, 40,
                                   "BASELINE config 3: 1024 envs of 256x256 (R = 6), hidden layers off"),
                 other_config_line(torch, dev, peak, flush, 4096, 1, True, 4, 16, 24,
-                                  "BASELINE config 4: one 4096x4096 grid (R = 10); generic tiled kernels (TMA-staged tiles, only tiles near fire are worked on)")]
+                                  "BASELINE config 4: one 4096x4096 grid (R = 10); generic tiled kernels (TMA-staged tiles, only tiles near fire are worked on), one CUDA graph launch per env step"),
+                other_config_line(torch, dev, peak, flush, 64, 4096, True, 1, 24, 200,
+                                  "config 2 at K = 1: ONE CA update per env step, the reference's own RepeatCAJax semantics (repeat_ca_jax.py:61-63)"),
+                v3_line(256, 1024, 64, 16)]
         except Exception as exc:
             line["other_configs"] = {"error": f"{type(exc).__name__}: {exc}"}
     if not args.no_cpu_baseline and world == 1:
@@ -626,18 +629,17 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_v3(args):
-    """Extra (non-headline) line: the v3 rule set, 256x256 x 1024 envs by default (BASELINE config 3)."""
+def v3_line(size, N, steps, warmup, seed=0):
+    """The v3 rule set (WindyForestFire + Move / Modify(cut) / RepeatCA of ForestFireBulldozer256x256-v3), batched: env
+    steps per second with the reference's clock (most steps run 0 CA updates) -- a line beside the headline."""
     import torch
     from gym_cellular_automata_b200.forest_fire.bulldozer import ForestFireBulldozerEnv
-    size = args.size if args.size != 64 else 256
-    N = args.envs_per_gpu if args.envs_per_gpu != 4096 else 1024
-    env = ForestFireBulldozerEnv(size, size, num_envs=N, seed=args.seed, max_repeats=2)
+    env = ForestFireBulldozerEnv(size, size, num_envs=N, seed=seed, max_repeats=2)
     env.reset()
     dev = env.device
-    total = args.warmup + args.steps
+    total = warmup + steps
     gen = torch.Generator(device=dev)
-    gen.manual_seed(args.seed)
+    gen.manual_seed(seed)
     acts = torch.stack([torch.randint(0, 9, (total, N), device=dev, generator=gen),
                         torch.randint(0, 2, (total, N), device=dev, generator=gen)], -1).to(torch.int32)
     rolls = torch.rand((N, 2, 9), dtype=torch.float64, device=dev, generator=gen)
@@ -650,23 +652,31 @@ def run_v3(args):
                                         float(env._t_act_shoot), float(env._t_env_any), ptr(env._reward),
                                         ptr(env._term), ptr(env._counts), ptr(env._repeats), current_stream()))
     reps = 0
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        step(args.warmup + i)
+    for i in range(steps):
+        step(warmup + i)
         reps += env._repeats
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     ca_updates = int(torch.as_tensor(reps).sum())
-    print(json.dumps({"metric": "env_steps_per_s", "value": N * args.steps / (ms * 1e-3), "unit": "env-steps/s",
-                      "ruleset": "v3 WindyForestFire", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-                      "ms_per_step": ms / args.steps, "ca_updates": ca_updates,
-                      "cell_updates_per_s": ca_updates * size * size / (ms * 1e-3), "data": "synthetic",
-                      "config": {"workload": f"v3 rule set {size}x{size}, {N} envs, reference clock (most steps run 0 CA updates)"}}))
+    return {"metric": "env_steps_per_s", "value": N * steps / (ms * 1e-3), "unit": "env-steps/s",
+            "ruleset": "v3 WindyForestFire", "n_gpus": 1, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "us_per_step": ms / steps * 1e3, "ca_updates": ca_updates,
+            "cell_updates_per_s": ca_updates * size * size / (ms * 1e-3), "data": "synthetic",
+            "workload": f"BASELINE config 3, the registered v3 rule set: {N} envs of {size}x{size}, reference clock (most steps run 0 CA updates)",
+            "config": {"workload": f"v3 rule set {size}x{size}, {N} envs, reference clock (most steps run 0 CA updates)"}}
+
+
+def run_v3(args):
+    """Extra (non-headline) line: the v3 rule set, 256x256 x 1024 envs by default (BASELINE config 3)."""
+    size = args.size if args.size != 64 else 256
+    N = args.envs_per_gpu if args.envs_per_gpu != 4096 else 1024
+    print(json.dumps(v3_line(size, N, args.steps, args.warmup, args.seed)))
 
 
 def main():

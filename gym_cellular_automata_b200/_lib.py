@@ -137,13 +137,21 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise GcaError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                       "(nvcc, sm_100a).  There is no CPU fallback.")
+    if not os.path.exists(LIB_PATH) and os.environ.get("GCA_LIB_PATH"):
+        raise GcaError(f"{LIB_PATH} is missing.  There is no CPU fallback.")
     if not os.environ.get("GCA_LIB_PATH") and _needs_build():
-        raise GcaError(f"{LIB_PATH} was not built from the sources next to it (csrc/*.cu, include/gca.h): rebuild it with "
-                       "`python -c 'import __graft_entry__ as g; g.build()'` -- a stale binary would be bound with "
-                       "the wrong structure layouts")
+        # a binary built from other sources would be bound with the wrong structure layouts: rebuild it (nvcc is part
+        # of the image: ~30 s), refuse it when that is not possible
+        try:
+            import fcntl
+            with open(LIB_PATH + ".lock", "w") as lk:   # ranks of one node start together: one of them builds
+                fcntl.flock(lk, fcntl.LOCK_EX)
+                if _needs_build():
+                    sys.stderr.write(f"[gca] {LIB_PATH} was not built from the sources next to it: rebuilding\n")
+                    build_library(force=True)
+        except Exception as exc:
+            raise GcaError(f"{LIB_PATH} was not built from the sources next to it (csrc/*.cu, include/gca.h) and could not "
+                           f"be rebuilt ({exc}); run `python -c 'import __graft_entry__ as g; g.build()'`") from exc
     lib = C.CDLL(LIB_PATH)
     lib.gca_version.restype = C.c_int
     if lib.gca_version() != GCA_VERSION and not os.environ.get("GCA_SKIP_VERSION_CHECK"):  # (A/B runs against older builds)

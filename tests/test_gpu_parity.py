@@ -1006,3 +1006,35 @@ def test_fused_observation_and_auto_reset_frame(cuda_device, mode):
     out, rgb = fused_env.step_observe_device(a)
     tup = two_call.conditional_reset(two_call.stateless_step(a), a)
     assert torch.equal(rgb, tup[0][0])
+
+
+def test_stationary_preroll_mixes_phases_and_keeps_the_state_consistent(cuda_device):
+    """bench.py's workload preparation (workload.stationary_preroll: staggered forced resets through
+    gca_conditional_reset between fused steps): afterwards the envs' episode ages are spread over the horizon, and the
+    packed state is still self-consistent -- the bit-board twin equals the u8 grid, the row minima bound the burn-out
+    ticks, and a lock-step run against the oracle from that state stays bit-exact."""
+    from parity_util import make_pair, lockstep, read_cuda_state
+    from gym_cellular_automata_b200.workload import stationary_preroll
+    N, K = 64, 4
+    env, co, E, state, info = make_pair(N=N, K=K, mode="legacy", use_hidden=True, seed=21, hidden="random", fast_slope=True)
+    env.auto_reset = True
+    env.balance_every = 4
+    stationary_preroll(env, horizon=64, groups=8, seed=1, settle=8)
+    age = env._state.steps_elapsed.cpu().numpy()
+    assert len(np.unique(age)) >= 8 and age.max() <= 72 and age.min() >= 8
+    st = env._state
+    cell = st.cell.cpu().numpy()
+    bb = st.bb.cpu().numpy().view(np.uint64).reshape(N, 64, 2)
+    cols = np.arange(64, dtype=np.uint64)
+    tree = ((bb[:, :, 0:1] >> cols) & np.uint64(1)).astype(bool)
+    fire = ((bb[:, :, 1:2] >> cols) & np.uint64(1)).astype(bool)
+    assert np.array_equal(tree, cell == 1) and np.array_equal(fire, cell == 2)
+    # continue in lock step with the oracle from the state the pre-roll left
+    got = read_cuda_state(env)
+    ctx = state["per_env_context"]
+    for k in ("true_grid", "fire_age", "dousing_count", "wind_index", "key", "is_night", "time_step"):
+        ctx[k] = got[k].copy()
+    state["position"], state["time"] = got["position"].copy(), got["time"].copy()
+    env.auto_reset = False
+    nbad, reports, stats = lockstep(env, co, state, 12, np.random.default_rng(4), resync=False)
+    assert nbad == 0, _fmt(reports)
