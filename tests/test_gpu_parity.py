@@ -127,6 +127,48 @@ def test_bitboard_grid_kernel_parity(cuda_device, nrows, ncols, K, N, mode, hidd
     assert stats[1] > 0 and stats[2] > 0 and stats[3] > 0
 
 
+@pytest.mark.parametrize("generic", [False, True])
+def test_rule_parity_injected_uniforms_128(cuda_device, generic):
+    """Rule parity on a 128x128 grid with identical injected random fields on both sides: the whole-grid bit-board
+    kernel and the generic tiled kernels, with regrowth, dousing bands and short injected fire ages (burn-outs inside
+    the run, exercising the burn list)."""
+    from parity_util import make_pair, lockstep, sync
+    N, K, S = 3, 2, 128
+    env, co, E, state, info = make_pair(N=N, size=S, K=K, mode="legacy", use_hidden=True, seed=7, p_tree=0.002,
+                                        hidden="random", scatter_fire=0.004, fast_slope=True, generic_tiles=generic)
+    state["per_env_context"]["dousing_count"][:, 60:64, :] = 1
+    sync(env, state, as_snapshot=True)
+    rng = np.random.default_rng(9)
+
+    def inject(step):
+        return {"u_burn": (rng.integers(0, 1 << 23, (K, N, S, S, 9)) * 2.0 ** -23).astype(np.float32) * 0.35,
+                "u_grow": (rng.integers(0, 1 << 23, (K, N, S, S)) * 2.0 ** -23).astype(np.float32),
+                "age_new": rng.integers(3, 12, (K, N, S, S)).astype(np.int32),
+                "u_wind": rng.random((K, N)).astype(np.float32),
+                "wind_step": rng.integers(1, 8, (K, N)).astype(np.int32)}
+
+    nbad, reports, stats = lockstep(env, co, state, 24, np.random.default_rng(1), inject_fn=inject)
+    assert nbad == 0, _fmt(reports)
+    assert stats[2] > 0 and stats[3] > 0
+
+
+def test_bitboard_grid_burn_list_overflow(cuda_device):
+    """More than 1024 cells of one env burn out inside one env step (every burning cell is given a remaining age of
+    1..K): the bit-board kernel drops its burn list and scans per sub-step -- still bit-exact."""
+    from parity_util import make_pair, lockstep, sync
+    env, co, E, state, info = make_pair(N=2, size=128, K=4, mode="legacy", use_hidden=True, seed=3, hidden="random",
+                                        scatter_fire=0.12, fast_slope=True)
+    ctx = state["per_env_context"]
+    rs = np.random.default_rng(0)
+    m = ctx["true_grid"] == 2
+    assert m[0].sum() > 1200
+    ctx["fire_age"][m] = rs.integers(1, 5, size=int(m.sum())).astype(np.float32)
+    sync(env, state, as_snapshot=True)
+    nbad, reports, stats = lockstep(env, co, state, 6, np.random.default_rng(2))
+    assert nbad == 0, _fmt(reports)
+    assert stats[3] > 2400
+
+
 def test_tiled_partitionable_hidden_off(cuda_device):
     from parity_util import make_pair, lockstep
     env, co, E, state, info = make_pair(N=2, size=128, K=2, mode="partitionable", use_hidden=False, seed=8,
