@@ -43,6 +43,10 @@ constexpr int S64_G = GCA_S64_GROUPS;  // independent lock-step groups inside a 
 constexpr int S64_GE = S64_E / S64_G;  // envs (= warps) per group
 static_assert(S64_E % S64_G == 0 && S64_G >= 1 && S64_G <= 4, "groups must divide the CTA");
 constexpr int S64_CHAIN_WARPS = (S64_E + 15) / 16;  // warps that walk the key chains (16 envs each)
+// How an owner waits for its env's key chain: a named barrier per owner (ids 1 .. S64_E - 1: the chain warp arrives, the
+// owner syncs -- a hardware wait, no polling) when there are enough barriers and no lock-step groups use them; else a
+// shared-memory flag the owner polls (measured: the polling loop was 4 % of the kernel's instructions).
+constexpr bool S64_CHAIN_BAR = S64_E <= 15 && S64_G == 1;
 constexpr int S64_IGN_CAP = 160;       // deferred fire-age draws buffered per env (flushed early when full)
 constexpr int S64_WP = 288;            // warp-private pair buffer: < 32 carried over + <= 256 of one chunk
 constexpr uint32_t S64_HALF_BURN = 9u * 4096u / 2u;
@@ -209,7 +213,7 @@ __device__ __noinline__ void key_chain_pooled(EnvSmem& ce, const gca_params& P, 
   }
   if (wr) {
     ce.hot.x = k0; ce.hot.y = k1;
-    smem_st_release(&ce.chain_done, 1);  // the owner warp of this env waits for it before key_sides
+    if (!S64_CHAIN_BAR) smem_st_release(&ce.chain_done, 1);  // the owner warp of this env polls it before key_sides
   }
 }
 __device__ __noinline__ void key_sides(EnvSmem& sm, const gca_params& P, const gca_inject& J, int N, int e,
@@ -782,8 +786,10 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   uint32_t* const wp32 = cs.pairs[warp];  // warp-private pair buffer (and scratch of the owner phases)
   uint16_t* const wpi = cs.pidx[warp];
   uint16_t* const wp = reinterpret_cast<uint16_t*>(wp32);
-  if (lane == 0) sm.chain_done = 0;
-  __syncthreads();  // (every warp is here within a few cycles of the launch) the flags are clear before a chain warp can set one
+  if (!S64_CHAIN_BAR) {
+    if (lane == 0) sm.chain_done = 0;
+    __syncthreads();  // (every warp is here within a few cycles of the launch) the flags are clear before a chain warp can set one
+  }
   const int K = P.K, mode = MODE < 0 ? P.rng_mode : MODE;
   const size_t cell_base = (size_t)e * 4096;
   const uint8_t* const hidden = HP == 0 ? nullptr : S.hidden;
@@ -857,6 +863,11 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
       ck1 = S.key[2 * pe + 1];
     }
     key_chain_pooled(cs.env[pv ? p : 0], P, lane, pv && !(lane & 1), ck0, ck1);
+    if (S64_CHAIN_BAR) {
+      // the sched rows / hot.x, hot.y written above are ordered before the arrival (producer side of bar.arrive / bar.sync)
+#pragma unroll
+      for (int w = 0; w < S64_E - 1; ++w) asm volatile("bar.arrive %0, 64;" ::"r"(w + 1) : "memory");
+    }
   }
   if (active) {
     S64_STAMP(19);
@@ -916,11 +927,14 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     prefetch_front(sm, hidden, pslope, cell_base, 0, L, lane);
     S64_STAMP(18);
   }
+  if (S64_CHAIN_BAR && warp < S64_E - 1) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");
   if (active) {
-    // the chain warp finished this env's key chain long ago (it runs while the grids stream in); no CTA barrier
+    // the env's key chain is done (the chain warp walks it while the grids stream in); no CTA-wide barrier
     S64_MARK();
-    while (smem_ld_acquire(&sm.chain_done) == 0) __nanosleep(40);
-    __syncwarp();
+    if (!S64_CHAIN_BAR) {
+      while (smem_ld_acquire(&sm.chain_done) == 0) __nanosleep(40);
+      __syncwarp();
+    }
     key_sides(sm, P, J, N, e, lane, widx);
     S64_ACC(28);   // trace: wait for the key chain + key sides
     if (lane == 0) {
@@ -1044,13 +1058,23 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
         bool more_items = M > 0;
         // the next work item is requested one item ahead, so the shared-memory atomic's round trip overlaps
         // with the work on the current item (lane 0 holds the ticket until it is needed)
+#ifdef S64_STATIC_ITEMS
+        int item_next = gwarp;  // item i goes to warp i mod S64_GE: no shared counter
+#else
         int ticket = 0;
         if (lane == 0 && more_items) ticket = smem_add_ret(&cs.next[group], 1);
+#endif
         for (;;) {
           if (PT < 32 && more_items) {
+#ifdef S64_STATIC_ITEMS
+            const int item = item_next;
+            if (item >= M) { more_items = false; continue; }
+            item_next += S64_GE;
+#else
             const int item = __shfl_sync(GCA_FULL, ticket, 0);
             if (item >= M) { more_items = false; continue; }
             if (lane == 0) ticket = smem_add_ret(&cs.next[group], 1);
+#endif
             const int gslot = __popc(__ballot_sync(GCA_FULL, lane < S64_GE && incl <= item));
             const int chunk = item - __shfl_sync(GCA_FULL, incl - my_n, gslot);
             const int es_slot = group * S64_GE + gslot;
