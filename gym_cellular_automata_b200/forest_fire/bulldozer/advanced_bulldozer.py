@@ -725,21 +725,30 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                 self._version_structs += 1
                 return self.step_host(actions_host, reward_host, terminated_host, staged, wait)  # re-bind the cached pointers
             self._steps_since_balance += 1
-            if self._steps_since_balance >= self.balance_every:
-                self._state.rebalance()
-                self._steps_since_balance = 0
-                self.kernel_launches += 1
+        # the re-dealing of envs to CTA slots is launched AFTER the step (it reads the costs the step leaves and only the
+        # next step needs its result): the host already has this step's results while it runs
+        rebalance = (self.balance_every and self._state.work is not None
+                     and self._steps_since_balance >= self.balance_every)
         self.kernel_launches += self._kernels_per_step(self.auto_reset)
         self._out.next_token()
         stream = torch.cuda.current_stream().cuda_stream
-        rc = ha[1](ha[2], ha[3], actions_host.data_ptr(), ha[4], ha[5], ha[6], ha[7], flags, ha[8], ha[9], stream)
+        rc = ha[1](ha[2], ha[3], actions_host.data_ptr(), ha[4], ha[5], ha[6], ha[7],
+                   flags | (_lib.FLAG_HOST_ASYNC if rebalance else 0), ha[8], ha[9], stream)
         if rc:
             check(rc, "gca_env_step_host")
         self._version += 1
-        # what step_host_wait() has to wait for: the completion word (zero-copy out on the 64x64 path) or the stream
+        # what a wait has to wait for: the completion word (zero-copy out on the 64x64 path) or the stream
         word = (self._state.work is not None and not (flags & _lib.FLAG_HOST_COPY_OUT) and reward_host.is_pinned()
                 and terminated_host.is_pinned())
-        self._host_pending = None if wait else (self._out.host_done.data_ptr() if word else None, self._out.token, stream)
+        self._host_pending = (self._out.host_done.data_ptr() if word else None, self._out.token, stream)
+        if rebalance:
+            self._state.rebalance()
+            self._steps_since_balance = 0
+            self.kernel_launches += 1
+            if wait:
+                self.step_host_wait()
+        if wait:
+            self._host_pending = None
 
     def step_host_wait(self, timeout_s: float = 30.0) -> None:
         """Block until the ``step_host(..., wait=False)`` in flight has delivered its results to the host buffers."""

@@ -1080,3 +1080,20 @@ def test_stationary_preroll_mixes_phases_and_keeps_the_state_consistent(cuda_dev
     env.auto_reset = False
     nbad, reports, stats = lockstep(env, co, state, 12, np.random.default_rng(4), resync=False)
     assert nbad == 0, _fmt(reports)
+
+
+@pytest.mark.parametrize("N", [1, 13, 15, 29])
+def test_fused_observation_env_counts_around_the_cta_size(cuda_device, N):
+    """The fused frame for batches that do not fill the step kernel's 14-env CTAs (idle warp slots), uint8."""
+    from parity_util import make_pair, random_actions
+    envs = []
+    for _ in range(2):
+        env, co, E, state, info = make_pair(N=N, K=1, mode="legacy", use_hidden=True, seed=17, obs_mode="rgb_u8")
+        envs.append(env)
+    envs[0]._can_fuse_render = lambda: False
+    rng = np.random.default_rng(8)
+    for step in range(6):
+        act = random_actions(rng, N, shoot_p=0.9)
+        a = envs[0].stateless_step(act)
+        b = envs[1].stateless_step(act)
+        assert torch.equal(a[0][0], b[0][0]), step
