@@ -1,5 +1,6 @@
+"""Diagnostics: the first kernel after an idle gap runs ~50 us slower -- why bench.py primes the timed region."""
 import sys, os
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 from gym_cellular_automata_b200.forest_fire.bulldozer import AdvancedForestFireBulldozerEnv
