@@ -122,6 +122,21 @@ def materialise_context(per_env_context) -> dict:
     return out
 
 
+def reference_reset_display(grid_sample):
+    """Display grid of the reference's reset() frame (advanced_bulldozer.py:405-409 -> :1021-1033) for the raw
+    (N, H, W, 3 + extensions) initial sample: channel 0 when there are no extension channels; otherwise the
+    reference tests "any entry > 0" per ROW of the (H, W, E) extension block and uses the first such row's index,
+    clamped to E - 1, as the CHANNEL index (the same quirk every step's frame has)."""
+    g = np.asarray(grid_sample)
+    base, ext = g[..., 0], g[..., 3:]
+    if ext.shape[-1] == 0:
+        return base
+    has_row = (ext > 0).any(axis=(2, 3))
+    ch = np.minimum(np.argmax(has_row, axis=1), ext.shape[-1] - 1)
+    chosen = ext[np.arange(g.shape[0]), :, :, ch]
+    return np.where(has_row.any(axis=1)[:, None, None], chosen, base)
+
+
 class AdvancedForestFireBulldozerEnv(CAEnv):
     metadata = {"render_modes": ["human"], "render_mode": "rgb_array"}
 
@@ -143,7 +158,7 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
                  obs_mode: str = "rgb_f32", auto_reset: bool = False, ca_p_tree: float = 0.0,
                  p_wind_change: float = 0.06, collect_stats: bool = False, use_tma: bool = True,
                  env_offset: int = 0, total_envs: Optional[int] = None, balance_every: int = 0,
-                 generic_tiles: bool = False, **kwargs):
+                 generic_tiles: bool = False, reset_obs: str = "true_grid", **kwargs):
         super().__init__(nrows, ncols, **kwargs)
         if not torch.cuda.is_available():
             raise _lib.GcaError("AdvancedForestFireBulldozerEnv needs a CUDA device (sm_100a); there is no CPU path")
@@ -158,6 +173,12 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         self.substeps = int(substeps)
         self.obs_mode = obs_mode
         self.auto_reset = bool(auto_reset)
+        # observation returned by reset(): "true_grid" (channel 0 of the initial sample: what every later step shows) or
+        # "reference" (the reference's own reset frame: grid_to_rgb_with_extensions on the raw multi-channel sample,
+        # advanced_bulldozer.py:405-409 -- with extensions its channels 3.. are independent random grids)
+        if reset_obs not in ("true_grid", "reference"):
+            raise ValueError("reset_obs must be 'true_grid' or 'reference'")
+        self.reset_obs = reset_obs
         # 64x64 kernel: re-deal envs to warps every `balance_every` steps by last step's cost (0 = off)
         self.balance_every = int(balance_every)
         self._steps_since_balance = 0
@@ -518,11 +539,17 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
         ext0 = torch.zeros(N, dtype=torch.int32, device=self.device)
         self._rgb = None
         # the reference renders reset observations with grid_to_rgb_with_extensions on the raw
-        # 5-channel sample (:405-409): channels 3,4 are independent random grids there.  Here the
-        # observation is drawn from the true grid (channel 0), which is what every later step shows.
+        # 5-channel sample (:405-409): channels 3,4 are independent random grids there.  By default the
+        # observation is drawn from the true grid (channel 0), which is what every later step shows;
+        # reset_obs="reference" reproduces the reference's frame (display grid chosen on the host: reset is
+        # not on the hot path).
+        shown = st.cell
+        if self.reset_obs == "reference":
+            disp = reference_reset_display(self._init_grid5)
+            shown = torch.as_tensor(np.ascontiguousarray(disp.astype(np.uint8)), device=self.device)
         enable = self.enable_extensions
         self.enable_extensions = False
-        rgb = self._render(st.cell, st.doused, st.position, zeros_u8, ext0)
+        rgb = self._render(shown, st.doused, st.position, zeros_u8, ext0)
         self.enable_extensions = enable
         info = {"TimeLimit.truncated": torch.zeros(N, dtype=torch.bool, device=self.device),
                 "terminated": torch.zeros(N, dtype=torch.bool, device=self.device),

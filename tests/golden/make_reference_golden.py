@@ -293,6 +293,34 @@ def run_operator_edges(ab, jnp, S=16):
             "clock_frac": np.array(frac, np.float32)}
 
 
+def run_reset_frame(ab, jnp, S=32, N=3, seed=17):
+    """The frame reset() itself returns (advanced_bulldozer.py:401-420): grid_to_rgb_with_extensions applied to the raw
+    multi-channel initial sample -- with extensions enabled its channels 3.. are independent random grids, and the
+    row-index-as-channel-index quirk of :1028-1032 picks which one is shown.  Recorded: the whole sample, the position,
+    the frame, with and without extension channels."""
+    jax = sys.modules["jax"]
+    out = {}
+    for tag, ext in (("ext", True), ("plain", False)):
+        np.random.seed(seed); random.seed(seed); gymnasium_shim.seed_all(seed)
+        key = jax.random.split(jax.random.PRNGKey(1))[0]
+        env = ab.AdvancedForestFireBulldozerEnv(S, S, key=key, num_envs=N, speed_move=0.48, speed_act=0.12,
+                                                use_hidden=False, enable_extensions=ext)
+        grid, ctx = env.initial_state
+        env.__class__.initial_state = property(lambda self, _v=(grid, ctx): _v)  # jit bakes the traced sample
+        try:
+            (rgb, ctx_all), _ = env.reset()
+        finally:
+            env.__class__.initial_state = ab.AdvancedForestFireBulldozerEnv.__dict__["initial_state"]
+        g = np.asarray(grid)
+        assert g.ndim == 4 and np.all(g == np.round(g))
+        out[tag + "/sample"] = g.astype(np.uint8)
+        out[tag + "/position"] = np.asarray(ctx_all["position"]).astype(np.int32)
+        out[tag + "/rgb"] = np.asarray(rgb).astype(np.float32)
+        assert np.array_equal(np.asarray(ctx_all["per_env_context"]["true_grid"]), g[..., 0])
+    print(f"reset frame: {S}x{S}, {N} envs, sample channels {out['ext/sample'].shape[-1]} / {out['plain/sample'].shape[-1]}")
+    return out
+
+
 CONSTANT_SIZES = (32, 64, 100, 128, 200, 256, 1024, 4096)
 
 
@@ -401,6 +429,13 @@ def generate(only=None, keep=None):
         print(buf.getvalue().strip().splitlines()[-1])
         for k, v in res.items():
             out[f"operator_edges/{k}"] = v
+    if only is None or "reset_frame" in only:
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            res = run_reset_frame(ab, jax.numpy)
+        print(buf.getvalue().strip().splitlines()[-1])
+        for k, v in res.items():
+            out[f"reset_frame/{k}"] = v
     if only is None or "constants" in only:
         for k, v in run_constants(ref_shim).items():
             out[f"constants/{k}"] = v
@@ -412,7 +447,7 @@ def generate(only=None, keep=None):
 
 
 if __name__ == "__main__":
-    # usage: make_reference_golden.py [--only name[,name...]]   (names: the CASES keys, v3_32x48, operator_edges, constants, rollout_stats);
+    # usage: make_reference_golden.py [--only name[,name...]]   (names: the CASES keys, v3_32x48, operator_edges, reset_frame, constants, rollout_stats);
     # with --only the other sections of the existing file are kept as they are
     only = set(sys.argv[sys.argv.index("--only") + 1].split(",")) if "--only" in sys.argv else None
     out = generate(only, np.load(GOLDEN_PATH) if only is not None else None)

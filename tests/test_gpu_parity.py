@@ -1,4 +1,6 @@
 """-m gpu: the CUDA hot path (through the C ABI) against the CPU oracle, bit for bit."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -1097,3 +1099,30 @@ def test_fused_observation_env_counts_around_the_cta_size(cuda_device, N):
         a = envs[0].stateless_step(act)
         b = envs[1].stateless_step(act)
         assert torch.equal(a[0][0], b[0][0]), step
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,mode", [("ext", "rgb_f32"), ("plain", "rgb_f32"), ("ext", "rgb_u8")])
+def test_reset_frame_reference_mode(cuda_device, tag, mode):
+    """reset_obs="reference": reset() returns the frame the reference's reset() returns for the same initial sample
+    (reference-source golden, section reset_frame); the default shows the true grid, which every later step shows."""
+    import torch
+    from gym_cellular_automata_b200.forest_fire.bulldozer.advanced_bulldozer import AdvancedForestFireBulldozerEnv
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_shim_golden.npz"))
+    g = z[f"reset_frame/{tag}/sample"].astype(np.float32)
+    pos, rgb = z[f"reset_frame/{tag}/position"], z[f"reset_frame/{tag}/rgb"]
+    N, H, W, _ = g.shape
+    frames = {}
+    for how in ("reference", "true_grid"):
+        env = AdvancedForestFireBulldozerEnv(H, W, key=1, num_envs=N, speed_move=0.48, speed_act=0.12, use_hidden=False,
+                                             enable_extensions=(tag == "ext"), obs_mode=mode, reset_obs=how, seed=3)
+        env._ensure_initial()
+        assert env._init_grid5.shape == g.shape
+        env._init_grid5 = g.copy()
+        env._init_context["per_env_context"]["true_grid"] = np.ascontiguousarray(g[..., 0])
+        env._init_context["position"] = pos.copy()
+        (frame, _ctx), _info = env.reset()
+        frames[how] = frame.cpu().numpy()
+    want = rgb.astype(np.uint8) if mode == "rgb_u8" else rgb
+    assert frames["reference"].dtype == want.dtype and np.array_equal(frames["reference"], want)
+    assert not np.array_equal(frames["true_grid"], want)

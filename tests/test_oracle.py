@@ -560,9 +560,24 @@ def test_reference_golden_is_reproducible():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     committed = np.load(mod.GOLDEN_PATH)
-    out = mod.generate(only={"ref64_partitionable", "v3_32x48", "rollout_stats", "constants"})
+    out = mod.generate(only={"ref64_partitionable", "v3_32x48", "rollout_stats", "constants", "reset_frame"})
     assert len(out) > 50
     for k, v in out.items():
         v = np.asarray(v)
         assert k in committed.files, k
         assert v.shape == committed[k].shape and np.array_equal(v, committed[k]), k
+
+
+@pytest.mark.parametrize("tag", ["ext", "plain"])
+def test_reset_frame_rule_reproduces_reference_source_golden(tag):
+    """The frame the reference's reset() returns (advanced_bulldozer.py:405-409) is grid_to_rgb of the display grid that
+    grid_to_rgb_with_extensions picks out of the raw multi-channel sample -- NOT of channel 0.  The host rule the env
+    uses for reset_obs="reference" plus the oracle's grid_to_rgb reproduce the recorded frame; channel 0 does not."""
+    from gym_cellular_automata_b200.forest_fire.bulldozer.advanced_bulldozer import reference_reset_display
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_shim_golden.npz"))
+    g = z[f"reset_frame/{tag}/sample"].astype(np.float32)
+    pos, rgb = z[f"reset_frame/{tag}/position"], z[f"reset_frame/{tag}/rgb"]
+    N, H, W, _ = g.shape
+    night, dous = np.zeros(N, np.int32), np.zeros((N, H, W), np.int32)
+    assert np.array_equal(ax.grid_to_rgb(reference_reset_display(g), night, dous, pos), rgb)
+    assert not np.array_equal(ax.grid_to_rgb(g[..., 0], night, dous, pos), rgb)
