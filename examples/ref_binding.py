@@ -14,7 +14,7 @@ conditional_reset (advanced_bulldozer.py:422-518, here GCA_FLAG_AUTO_RESET insid
 import ctypes as C
 import os
 
-GCA_VERSION = 104
+GCA_VERSION = 105
 GCA_FLAG_AUTO_RESET, GCA_FLAG_NO_HIDDEN = 1, 2
 GCA_RNG_LEGACY, GCA_RNG_PARTITIONABLE = 0, 1   # jax_threefry_partitionable False / True
 

@@ -27,7 +27,7 @@ FLAG_HOST_ASYNC = 128
 FLAG_HOST_MAPPED = 256
 FLAG_RENDER = 512
 FLAG_GENERIC_TILES = 1024
-GCA_VERSION = 104  # include/gca.h: the ctypes structures below mirror that version of the header
+GCA_VERSION = 105  # include/gca.h: the ctypes structures below mirror that version of the header
 
 
 class GcaError(RuntimeError):

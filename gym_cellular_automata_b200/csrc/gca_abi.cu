@@ -198,13 +198,13 @@ static int env_step_impl(const gca_params* p, const gca_state* s, const int32_t*
     // grids of whole 64-bit words up to 256x256: one launch per env step, the grid as bit-boards in shared memory
     rc = check_cuda(gca::launch_bb_env_step(*p, st, actions, o, j, flags, (cudaStream_t)stream), "env_step_bb");
   } else {
-    // any other grid: generic tiled kernels, 4 per CA sub-step + the epilogue, replayed as one CUDA graph
+    // any other grid: generic tiled kernels (active-tile lists), 2 per CA sub-step + 3, replayed as one CUDA graph
     if (((long long)p->H * p->W) & 1) return fail(GCA_ERR_UNSUPPORTED, "gca_env_step: H*W must be even");
     if (!s->scratch_cell || !s->scratch_u32)
       return fail(GCA_ERR_ARG, "gca_env_step: grids other than 64x64 need scratch_cell and scratch_u32");
     rc = check_cuda(gca::launch_tiled_env_step(*p, st, actions, o, j, flags, s->scratch_cell, s->scratch_u32,
-                                               reinterpret_cast<int32_t*>(s->scratch_u32) + 12 * (size_t)s->N,
-                                               reinterpret_cast<uint8_t*>(s->scratch_u32 + 14 * (size_t)s->N),
+                                               reinterpret_cast<int32_t*>(s->scratch_u32) + 12 * GCA_MAX_K * (size_t)s->N,
+                                               reinterpret_cast<uint8_t*>(s->scratch_u32 + (12 * GCA_MAX_K + 2) * (size_t)s->N),
                                                (flags & GCA_FLAG_NO_TMA) ? 0 : 1, (cudaStream_t)stream),
                     "env_step_tiled");
   }

@@ -156,6 +156,22 @@ __device__ __forceinline__ void split_pair(uint32_t k0, uint32_t k1, int mode, i
   else { n0 = a0; n1 = a1; s0 = b0; s1 = b1; }
 }
 
+// one threefry block per lane with lane-specific key/counters, words swapped inside the lane pair
+__device__ __forceinline__ void tf_exchange(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t& o0,
+                                            uint32_t& o1, uint32_t& p0, uint32_t& p1) {
+  threefry2x32_ni(k0, k1, c0, c1, o0, o1);
+  p0 = __shfl_xor_sync(GCA_FULL, o0, 1);
+  p1 = __shfl_xor_sync(GCA_FULL, o1, 1);
+}
+__device__ __forceinline__ void assemble_split(int mode, uint32_t w, uint32_t o0, uint32_t o1, uint32_t p0,
+                                               uint32_t p1, uint32_t& n0, uint32_t& n1, uint32_t& s0,
+                                               uint32_t& s1) {
+  const uint32_t a0 = w ? p0 : o0, a1 = w ? p1 : o1;
+  const uint32_t b0 = w ? o0 : p0, b1 = w ? o1 : p1;
+  if (mode == GCA_RNG_LEGACY) { n0 = a0; n1 = b0; s0 = a1; s1 = b1; }
+  else { n0 = a0; n1 = a1; s0 = b0; s1 = b1; }
+}
+
 // Reward of _award: -(f / (t + f + 1e-8)) in float32 (advanced_bulldozer.py:627-630)
 __device__ __forceinline__ float award(int t, int f) {
   const float denom = __fadd_rn((float)(t + f), 1e-8f);

@@ -227,22 +227,6 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   return v;
 }
 
-// one threefry block per lane with lane-specific key/counters, words swapped inside the lane pair
-__device__ __forceinline__ void tf_exchange(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t& o0,
-                                            uint32_t& o1, uint32_t& p0, uint32_t& p1) {
-  threefry2x32_ni(k0, k1, c0, c1, o0, o1);
-  p0 = __shfl_xor_sync(GCA_FULL, o0, 1);
-  p1 = __shfl_xor_sync(GCA_FULL, o1, 1);
-}
-__device__ __forceinline__ void assemble_split(int mode, uint32_t w, uint32_t o0, uint32_t o1, uint32_t p0,
-                                               uint32_t p1, uint32_t& n0, uint32_t& n1, uint32_t& s0,
-                                               uint32_t& s1) {
-  const uint32_t a0 = w ? p0 : o0, a1 = w ? p1 : o1;
-  const uint32_t b0 = w ? o0 : p0, b1 = w ? o1 : p1;
-  if (mode == GCA_RNG_LEGACY) { n0 = a0; n1 = b0; s0 = a1; s1 = b1; }
-  else { n0 = a0; n1 = a1; s0 = b0; s1 = b1; }
-}
-
 // Key schedule of K successive PartiallyObservableForestFireJax.update calls
 // (ca_alexandridis_jax.py:436-448 and :352-368), in two parts.  key_chain_pooled: K0 -> K1 -> K2 -> K3 is
 // sequential (3K split levels of 2 threefry blocks), so ONE warp of the CTA walks the chains of all its envs,
@@ -1022,7 +1006,9 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   long long trace_t = clk0;
 #endif
   const int group = s64_group_of(warp), gwarp = s64_index_in_group(warp);  // lock-step group of this warp, index inside it
+#ifdef S64_FAIR
   if (lane == 0) cs.member[group][gwarp] = (uint8_t)warp;  // (read after the group's first barrier)
+#endif
   const int slot = blockIdx.x * S64_E + warp;
   const int N = S.N;
   const bool active = slot < N;   // a warp without an env still joins the barriers and the pooled work
@@ -1728,7 +1714,11 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
 
       // ---------------- pooled phase: work items = 32-entry chunks of every env's front list -------
       {
+#ifdef S64_FAIR
         const int my_slot = lane < S64_GE ? (int)cs.member[group][lane] : 0;  // env slot of the group's lane-th member
+#else
+        const int my_slot = group * S64_GE + lane;  // blocked groups: members are consecutive warps
+#endif
         const int my_pk = lane < S64_GE ? cs.nch[my_slot] : 0;
         const int my_nc = my_pk & 0xFFFF;              // cell chunks of env slot `lane`
         const int my_n = my_nc + (my_pk >> 16);        // + its scan rounds
@@ -1762,7 +1752,11 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
 #endif
             const int gslot = __popc(__ballot_sync(GCA_FULL, lane < S64_GE && incl <= item));
             const int chunk = item - __shfl_sync(GCA_FULL, incl - my_n, gslot);
+#ifdef S64_FAIR
             const int es_slot = __shfl_sync(GCA_FULL, my_slot, gslot);
+#else
+            const int es_slot = group * S64_GE + gslot;
+#endif
             EnvSmem& es = cs.env[es_slot];
             const int nc_env = __shfl_sync(GCA_FULL, my_nc, gslot);
             if (chunk >= nc_env) {

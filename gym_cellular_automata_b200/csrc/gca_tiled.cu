@@ -1,25 +1,26 @@
-// gca_tiled.cu -- environment step for grids of any size (256x256 x 1024 envs, one 4096x4096
-// grid, ...): 2-D tiles with a halo of R cells, ONE CA sub-step per launch.
+// gca_tiled.cu -- environment step for grids of any size (one 4096x4096 grid, odd widths, ...): 2-D tiles of
+// 32 x 64 cells with a halo of R cells, one CA sub-step per tile-kernel launch, the whole env step one CUDA graph.
 //
-// Same rule, same lazy counter-based draws and the same enclosure / exact-fallback logic as the
-// 64x64 kernel (gca_step64.cu); what differs is the decomposition:
-//   * tile of 32 x 64 cells per CTA; tile + halo (R <= 10) of the u8 grid is staged into shared
-//     memory -- by TMA (cp.async.bulk.tensor, 3-D map (W, H, N); out-of-bounds coordinates are
-//     zero-filled, which IS the reference's jnp.pad(constant_values=0) boundary,
-//     ca_alexandridis_jax.py:26) when W % 16 == 0, by plain bounds-checked loads otherwise;
-//   * front cells of the tile are compacted into a shared list (ballot + one atomic per warp) and
-//     processed balanced over the CTA: window sum -> enclosure -> per burning direction one
-//     threefry block addressed by the GLOBAL linear index ((r W + c) 9 + d), so results do not
-//     depend on the tiling;
-//   * only tiles that can change are worked on: a dense, vectorised pass (tile_flags_kernel, 1 byte
-//     per cell read) marks the tiles that hold fire, and a tile is ACTIVE when its 3x3 tile
-//     neighbourhood holds any (R <= 10 < the tile's extent, so nothing further away can ignite it);
-//     the CTAs of the other tiles leave at once -- for a small fire on a 4096^2 grid that is all
-//     but a handful.  Active tiles write their new cells to the scratch grid (neighbouring tiles
-//     still read the old ones) and tile_apply_kernel copies them back, so S.cell is always the
-//     current grid; burn-out ticks / ages are updated in place (own cell only);
-//   * per-env scalars (key chain, wind walk, clock, move, douse, reward, done) live in two tiny
-//     kernels around the K sub-step launches.
+// Same rule, same lazy counter-based draws and the same enclosure / exact-fallback logic as the 64x64 kernel
+// (gca_step64.cu); what differs is the decomposition:
+//   * only tiles that can change are worked on.  Tile activity is a per-tile count of burning cells: counted ONCE per
+//     env step by a dense pass (tile_count_kernel, which also counts the env's tree / fire cells for the reward) and
+//     then maintained by the tile kernel itself (a tile's own CTA knows its new count).  A tile is ACTIVE when its 3x3
+//     tile neighbourhood holds fire (R <= 10 < the tile's extent, so nothing further away can ignite it), or always
+//     when regrowth is on.  Every sub-step works on a compact LIST of the active tiles with small fixed grids whose
+//     CTAs loop over the list (one 4096x4096 grid has 8192 tiles of which a young fire touches a dozen);
+//   * tile + halo of the u8 grid is staged into shared memory -- by TMA (cp.async.bulk.tensor, 3-D map (W, H, N);
+//     out-of-bounds coordinates are zero-filled, which IS the reference's jnp.pad(constant_values=0) boundary,
+//     ca_alexandridis_jax.py:26) when W % 16 == 0, by plain bounds-checked loads otherwise -- and turned into tree /
+//     fire bit rows (warp ballots): front cells are found bit-parallel (a thread per tile row), the (2R+1)^2 heat
+//     window is nested box popcounts of those rows, the doused rows in reach are staged as 64-bit words;
+//   * front cells are processed one per thread: window sum -> enclosure -> per burning direction one threefry block
+//     addressed by the GLOBAL linear index ((r W + c) 9 + d), so results do not depend on the tiling;
+//   * active tiles write their new cells to the scratch grid (neighbouring tiles still read the old ones; only burning
+//     and igniting cells are looked at unless regrowth is on) and tile_apply_list_kernel copies them back -- and builds
+//     the next sub-step's list --, so S.cell is always the current grid; burn-out ticks are updated in place;
+//   * the key schedules of all K sub-steps come from one kernel (a warp per env, lane pairs per split), the per-env
+//     scalars (clock, move, douse, reward, done) from the epilogue kernel.
 // Reference lines as in gca_step64.cu.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -42,122 +43,19 @@ constexpr int T_ROWS_MAX = T_TH + 2 * T_MAXR;         // 52
 // sched[e][*] written by tiled_sched_kernel for the current sub-step
 enum { SC_BURN0 = 0, SC_BURN1, SC_GROW0, SC_GROW1, SC_AK10, SC_AK11, SC_AK20, SC_AK21, SC_WIND, SC_N = 12 };
 
-// ---------------------------------------------------------------------------------------------
-// per-env key schedule of ONE PartiallyObservableForestFireJax.update (thread per env)
-// ---------------------------------------------------------------------------------------------
-__global__ void tiled_sched_kernel(gca_params P, gca_state S, gca_inject J, int substep, uint32_t* sched) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= S.N) return;
-  const int mode = P.rng_mode;
-  uint32_t k0 = S.key[2 * e], k1 = S.key[2 * e + 1];
-  uint32_t K1[2], S1[2], Ka[2], Sb[2], Kb[2], Sg[2], Kc[2], Sa[2], K2[2], Sw[2], K3[2], Si[2], a1[2], a2[2], w1[2],
-      w2[2];
-  split_thread(k0, k1, mode, K1[0], K1[1], S1[0], S1[1]);
-  split_thread(S1[0], S1[1], mode, Ka[0], Ka[1], Sb[0], Sb[1]);
-  split_thread(Ka[0], Ka[1], mode, Kb[0], Kb[1], Sg[0], Sg[1]);
-  split_thread(Kb[0], Kb[1], mode, Kc[0], Kc[1], Sa[0], Sa[1]);
-  split_thread(Sa[0], Sa[1], mode, a1[0], a1[1], a2[0], a2[1]);
-  split_thread(K1[0], K1[1], mode, K2[0], K2[1], Sw[0], Sw[1]);
-  split_thread(K2[0], K2[1], mode, K3[0], K3[1], Si[0], Si[1]);
-  split_thread(Si[0], Si[1], mode, w1[0], w1[1], w2[0], w2[1]);
-  float u = bits_to_uniform(bits_scalar(tf_key(Sw[0], Sw[1]), mode));
-  int step = randint_from_bits(bits_scalar(tf_key(w1[0], w1[1]), mode), bits_scalar(tf_key(w2[0], w2[1]), mode), 1,
-                               7u, 4u);
-  if (J.u_wind) u = J.u_wind[(size_t)substep * S.N + e];
-  if (J.wind_step) step = J.wind_step[(size_t)substep * S.N + e];
-  uint32_t* sc = sched + (size_t)e * SC_N;
-  sc[SC_BURN0] = Sb[0]; sc[SC_BURN1] = Sb[1]; sc[SC_GROW0] = Sg[0]; sc[SC_GROW1] = Sg[1];
-  sc[SC_AK10] = a1[0]; sc[SC_AK11] = a1[1]; sc[SC_AK20] = a2[0]; sc[SC_AK21] = a2[1];
-  const int w = S.wind_index[e];
-  sc[SC_WIND] = (uint32_t)w;  // wind used by THIS sub-step
-  S.wind_index[e] = (u < P.p_wind_change) ? (w + step) % 8 : w;
-  S.key[2 * e] = K3[0];
-  S.key[2 * e + 1] = K3[1];
-}
-
-// ---------------------------------------------------------------------------------------------
-// tile activity: flags[e][ty][tx] = the tile holds a burning cell; with want_counts the tree / fire
-// cells of the whole grid are counted on the way (the step's reward / done need them once)
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) tile_flags_kernel(int H, int W, const uint8_t* __restrict__ cell,
-                                                         uint8_t* __restrict__ tile_flags, int32_t* __restrict__ counts,
-                                                         int want_counts, int all_active) {
-  const int e = blockIdx.z, r0 = blockIdx.y * T_TH, c0 = blockIdx.x * T_TW;
-  const int tid = threadIdx.x;
-  const int r = r0 + (tid >> 2), c = c0 + (tid & 3) * 16;  // 16 cells per thread
-  const uint8_t* src = cell + ((size_t)e * H + r) * W + c;
-  uint32_t fire = 0;
-  int nt = 0, nf = 0;
-  if (r < H && c < W) {
-    if ((W & 15) == 0) {
-      const uint4 v = *reinterpret_cast<const uint4*>(src);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {  // cell codes 0 / 1 / 2: bit 0 = tree, bit 1 = fire
-        fire |= w[k] & 0x02020202u;
-        nt += __popc(w[k] & 0x01010101u);
-        nf += __popc(w[k] & 0x02020202u);
-      }
-    } else {
-      for (int k = 0; k < 16 && c + k < W; ++k) {
-        const int v = src[k];
-        fire |= v == 2;
-        nt += v == 1;
-        nf += v == 2;
-      }
-    }
-  }
-  const int any = __syncthreads_or(fire != 0u) | all_active;
-  if (tid == 0) tile_flags[((size_t)e * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = (uint8_t)(any != 0);
-  if (want_counts) {
-    nt = __reduce_add_sync(GCA_FULL, nt);
-    nf = __reduce_add_sync(GCA_FULL, nf);
-    if ((tid & 31) == 0) {
-      if (nt) atomicAdd(&counts[2 * e], nt);
-      if (nf) atomicAdd(&counts[2 * e + 1], nf);
-    }
-  }
-}
-
-// does the 3x3 tile neighbourhood of this CTA's tile hold fire?  (uniform over the CTA)
-__device__ __forceinline__ bool tile_active(const uint8_t* __restrict__ tile_flags) {
-  const int tx = blockIdx.x, ty = blockIdx.y, TX = gridDim.x, TY = gridDim.y;
-  const uint8_t* f = tile_flags + (size_t)blockIdx.z * TY * TX;
-  bool a = false;
-  if (threadIdx.x < 9) {
-    const int y = ty + (int)threadIdx.x / 3 - 1, x = tx + (int)threadIdx.x % 3 - 1;
-    if (y >= 0 && y < TY && x >= 0 && x < TX) a = f[y * TX + x] != 0;
-  }
-  return __syncthreads_or(a) != 0;
-}
-
-// copies the new cells of the active tiles from the scratch grid back into the grid
-__global__ void __launch_bounds__(128) tile_apply_kernel(int H, int W, const uint8_t* __restrict__ tile_flags,
-                                                         const uint8_t* __restrict__ scratch, uint8_t* __restrict__ cell) {
-  if (!tile_active(tile_flags)) return;
-  const int e = blockIdx.z, r0 = blockIdx.y * T_TH, c0 = blockIdx.x * T_TW;
-  const int tid = threadIdx.x;
-  const int r = r0 + (tid >> 2), c = c0 + (tid & 3) * 16;
-  if (r >= H || c >= W) return;
-  const size_t off = ((size_t)e * H + r) * W + c;
-  if ((W & 15) == 0) {
-    *reinterpret_cast<uint4*>(cell + off) = *reinterpret_cast<const uint4*>(scratch + off);
-  } else {
-    for (int k = 0; k < 16 && c + k < W; ++k) cell[off + k] = scratch[off + k];
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// the tile kernel
-// ---------------------------------------------------------------------------------------------
 struct TileSmem {
   alignas(128) uint8_t tile[T_ROWS_MAX * T_PITCH_MAX];  // cells incl. halo, pitch = params
-  float wmat[(2 * T_MAXR + 1) * (2 * T_MAXR + 1)];      // burn kernel, row-major
   uint16_t list[T_TH * T_TW];                            // front cells of the tile: (lr << 6) | lc
-  uint8_t ignite[T_TH * T_TW];                           // 1 = ignites this sub-step
+  unsigned long long ign[T_TH];                          // cells of the tile that ignite this sub-step (bit = column)
+  uint32_t tbits[T_ROWS_MAX][4];                         // tree bit-board of tile + halo (see fbits)
+  int nlist2, n_ign, n_ext;                              // change-candidate list of the write phase, its counters
+  unsigned long long dw[T_TH + 4][3];                     // doused rows r0-2 .. r0+TH+1, words (c0 >> 6) - 1 .. + 1
+  int any_doused;
+  uint32_t fbits[T_ROWS_MAX][4];                         // fire bit-board of tile + halo: bit c of the row <-> tile column c (3 words + a zero pad)
   alignas(8) unsigned long long mbar;
   int nfront;
   int cnt_tree, cnt_fire;
+  int fire_abs;   // burning cells of the tile after the sub-step
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -179,43 +77,45 @@ __device__ __forceinline__ uint32_t dous_window_g(const unsigned long long* __re
   return v;
 }
 
+// One CA sub-step of tile (e, ty, tx) by the whole CTA (`it` = how many tiles this CTA has staged before: the parity of
+// the TMA barrier's phase).  Returns (to thread 0) the number of burning cells the tile holds afterwards.
 template <bool USE_TMA>
-__global__ void __launch_bounds__(T_THREADS)
-ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gca_state S,
-                const __grid_constant__ gca_inject J, const __grid_constant__ CUtensorMap tmap,
-                const uint8_t* __restrict__ cell_in, uint8_t* __restrict__ cell_out,
-                const uint32_t* __restrict__ sched, int32_t* __restrict__ counts, unsigned long long* stats,
-                const uint8_t* __restrict__ tile_flags, int substep, int pitch) {
-  __shared__ TileSmem sm;
-  if (!tile_active(tile_flags)) return;  // no fire within reach: nothing in this tile can change
+__device__ __forceinline__ int ca_tile_body(TileSmem& sm, const gca_params& P, const gca_state& S, const gca_inject& J,
+                                            const CUtensorMap* tmap, const uint8_t* __restrict__ cell_in,
+                                            uint8_t* __restrict__ cell_out, const uint32_t* __restrict__ sched,
+                                            int32_t* __restrict__ counts, unsigned long long* stats, int substep, int pitch,
+                                            int e, int ty, int tx, int it, int sched_env_stride, int sched_off) {
   const int H = P.H, W = P.W, R = P.R, mode = P.rng_mode;
   const int WW = (W + 63) >> 6;
-  const int e = blockIdx.z;
-  const int r0 = blockIdx.y * T_TH, c0 = blockIdx.x * T_TW;
+  const int r0 = ty * T_TH, c0 = tx * T_TW;
   const int tid = threadIdx.x, lane = tid & 31;
   const int rows = T_TH + 2 * R;
   const size_t env_off = (size_t)e * H * W;
   const int win = 2 * R + 1;
 
-  if (tid == 0) { sm.nfront = 0; sm.cnt_tree = 0; sm.cnt_fire = 0; }
-  // burn kernel weights: ring k = max(|di|, |dj|); centre shares ring 1's weight
-  for (int i = tid; i < win * win; i += T_THREADS) {
-    const int di = abs(i / win - R), dj = abs(i % win - R);
-    sm.wmat[i] = P.ring_w[max(di, dj)];
+  if (tid == 0) { sm.nfront = 0; sm.cnt_tree = 0; sm.cnt_fire = 0; sm.fire_abs = 0; sm.any_doused = 0; }
+  // doused rows within the 5x5 window's reach of the tile (requested before the tile is staged)
+  unsigned long long dword = 0ull;
+  if (tid < (T_TH + 4) * 3) {
+    const int gr = r0 - 2 + tid / 3, wc = (c0 >> 6) - 1 + tid % 3;
+    if (gr >= 0 && gr < H && wc >= 0 && wc < WW)
+      dword = reinterpret_cast<const unsigned long long*>(S.doused)[((size_t)e * H + gr) * WW + wc];
   }
   // ---- stage tile + halo -------------------------------------------------------------------------
   if (USE_TMA) {
     if (tid == 0) {
       const uint32_t bar = smem_u32(&sm.mbar);
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      if (it == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
       const uint32_t bytes = (uint32_t)(rows * pitch);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
       // box (pitch, rows, 1) at (c0 - 16, r0 - R, e); negative / beyond-edge coordinates are zero-filled.
       // The innermost start coordinate must keep the global address 16-byte aligned.
       asm volatile(
           "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-          ::"r"(smem_u32(sm.tile)), "l"(&tmap), "r"(c0 - T_HC), "r"(r0 - R), "r"(e), "r"(bar)
+          ::"r"(smem_u32(sm.tile)), "l"(tmap), "r"(c0 - T_HC), "r"(r0 - R), "r"(e), "r"(bar)
           : "memory");
     }
     __syncthreads();
@@ -226,7 +126,7 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(0u)
+            : "r"(bar), "r"((uint32_t)(it & 1))
             : "memory");
       }
     }
@@ -241,29 +141,52 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
     __syncthreads();
   }
 
-  const uint32_t* sc = sched + (size_t)e * SC_N;
+  if (tid < (T_TH + 4) * 3) {
+    sm.dw[tid / 3][tid % 3] = dword;
+    if (dword) sm.any_doused = 1;  // (benign race: every writer stores 1; read after the next barrier)
+  }
+  // fire bit-board of the staged tile (a warp ballots 32 cells of a row into one word): the heat window becomes
+  // popcounts of masked row words instead of a walk over (2R+1)^2 bytes
+  for (int wi = tid >> 5; wi < rows * 3; wi += T_THREADS / 32) {
+    const int row = wi / 3, q = wi % 3;
+    const int v = sm.tile[row * pitch + 32 * q + lane];
+    const uint32_t bf = __ballot_sync(GCA_FULL, v == 2), bt = __ballot_sync(GCA_FULL, v == 1);
+    if (lane == 0) {
+      sm.fbits[row][q] = bf;
+      sm.tbits[row][q] = bt;
+      if (q == 0) { sm.fbits[row][3] = 0u; sm.tbits[row][3] = 0u; }
+    }
+  }
+  if (tid < T_TH) sm.ign[tid] = 0ull;
+  if (tid == 0) { sm.nlist2 = 0; sm.n_ign = 0; sm.n_ext = 0; }
+  __syncthreads();
+  const uint32_t* sc = sched + (size_t)e * sched_env_stride + sched_off;
   const uint32_t tick = S.tick[e] + (uint32_t)substep;  // S.tick advances by K in the epilogue
   const uint32_t half_cell = (uint32_t)(((size_t)H * W) >> 1);
   const uint32_t half_burn = (uint32_t)((9ull * H * W) >> 1);
 
-  // ---- find the tile's front cells ---------------------------------------------------------------
-  const int lc = tid & 63, rg = tid >> 6;
-  for (int k = 0; k < T_TH / 4; ++k) {
-    const int lr = rg + 4 * k;
-    const int gr = r0 + lr, gc = c0 + lc;
-    const uint8_t* ctr = sm.tile + (lr + R) * pitch + (lc + T_HC);
-    bool front = false;
-    if (gr < H && gc < W && ctr[0] == 1) {
-      front = ctr[-pitch - 1] == 2 || ctr[-pitch] == 2 || ctr[-pitch + 1] == 2 || ctr[-1] == 2 || ctr[1] == 2 ||
-              ctr[pitch - 1] == 2 || ctr[pitch] == 2 || ctr[pitch + 1] == 2;
+  // ---- find the tile's front cells: tree cells with a burning Moore neighbour, bit-parallel (a thread per tile row:
+  //      64-bit views of the row's interior columns, the fire rows also shifted by one column either way) -------------
+  if (tid < T_TH) {
+    const int lr = tid;
+    unsigned long long fh = 0ull;  // cells of row lr with fire in columns c-1..c+1 of rows lr-1..lr+1
+#pragma unroll
+    for (int d = -1; d <= 1; ++d) {
+      const uint32_t* fr = sm.fbits[lr + R + d];
+      const unsigned long long lo = fr[0] | ((unsigned long long)fr[1] << 32), hi = fr[2] | ((unsigned long long)fr[3] << 32);
+      fh |= ((lo >> (T_HC - 1)) | (hi << (64 - (T_HC - 1)))) | ((lo >> T_HC) | (hi << (64 - T_HC))) |
+            ((lo >> (T_HC + 1)) | (hi << (64 - (T_HC + 1))));
     }
-    sm.ignite[lr * T_TW + lc] = 0;
-    const uint32_t bal = __ballot_sync(GCA_FULL, front);
-    if (bal) {
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&sm.nfront, __popc(bal));
-      base = __shfl_sync(GCA_FULL, base, 0);
-      if (front) sm.list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((lr << 6) | lc);
+    const uint32_t* tr = sm.tbits[lr + R];
+    const unsigned long long tlo = tr[0] | ((unsigned long long)tr[1] << 32), thi = tr[2] | ((unsigned long long)tr[3] << 32);
+    unsigned long long front = ((tlo >> T_HC) | (thi << (64 - T_HC))) & fh;  // (cells outside the grid are zero-filled: no trees)
+    if (front) {
+      int idx = atomicAdd(&sm.nfront, __popcll(front));
+      while (front) {
+        const int c = __ffsll((long long)front) - 1;
+        front &= front - 1;
+        sm.list[idx++] = (uint16_t)((lr << 6) | c);
+      }
     }
   }
   __syncthreads();
@@ -278,16 +201,55 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
     const int gr = r0 + lr, gc = c0 + lcc;
     const size_t gcell = (size_t)gr * W + gc;
     const uint8_t* ctr = sm.tile + (lr + R) * pitch + (lcc + T_HC);
-    // heat: any summation order is inside the enclosure
+    // the cell's hidden byte and the 8 slope factors of its directions: requested now, used after the heat sum
+    int hid = 3 | (3 << 3);
+    if (S.hidden != nullptr) hid = S.hidden[env_off + gcell];
+    float4 sl_a = make_float4(1.f, 1.f, 1.f, 1.f), sl_b = sl_a;
+    if (S.pslope != nullptr) {
+      const float4* ps = reinterpret_cast<const float4*>(S.pslope + (env_off + gcell) * 8);
+      sl_a = ps[0];
+      sl_b = ps[1];
+    }
+    // heat from the fire bit rows: H = sum_k w_k (C_k - C_{k-1}) = sum_k (w_k - w_{k+1}) C_k, C_k = burning cells within
+    // Chebyshev distance k = popcounts of the 2k+1 window rows under a (2k+1)-bit mask (the centre is a tree).  Any
+    // summation order is inside the enclosure (T_LO / T_HI leave 2048 u, this sum is off by a few dozen u at most).
+    uint32_t wr[2 * T_MAXR + 1];
+    {
+      const int start = lcc + T_HC - R;  // first tile column of the window
+      const int wq = start >> 5, sh = start & 31;
+#pragma unroll
+      for (int q = 0; q <= 2 * T_MAXR; ++q) {
+        const int di = q - T_MAXR;
+        wr[q] = 0u;
+        if (di >= -R && di <= R) {
+          const uint32_t* fr = sm.fbits[lr + R + di];
+          wr[q] = __funnelshift_r(fr[wq], fr[wq + 1], sh);  // bit b <-> column offset b - R
+        }
+      }
+    }
     float Hf = 0.0f;
-    for (int di = 0; di < win; ++di) {
-      const uint8_t* rowp = ctr + (di - R) * pitch - R;
-      const float* wrow = sm.wmat + di * win;
-      for (int dj = 0; dj < win; ++dj) Hf += (rowp[dj] == 2) ? wrow[dj] : 0.0f;
+#pragma unroll
+    for (int k = T_MAXR; k >= 1; --k) {
+      if (k <= R) {
+        const uint32_t box = ((2u << (2 * k)) - 1u) << (R - k);  // |dj| <= k
+        int Ck = 0;
+#pragma unroll
+        for (int di = -k; di <= k; ++di) Ck += __popc(wr[di + T_MAXR] & box);
+        const float dk = k < R ? __fsub_rn(P.ring_w[k], P.ring_w[k + 1]) : P.ring_w[k];
+        Hf = fmaf((float)Ck, dk, Hf);
+      }
     }
     float Dlo = 0.0f, Dhi = 0.0f;
-    uint32_t dwin = dous_window_g(reinterpret_cast<const unsigned long long*>(S.doused) + (size_t)e * H * WW, H, W,
-                                  WW, gr, gc);
+    uint32_t dwin = 0u;
+    if (sm.any_doused) {  // 5x5 doused window: bit (5 i + j) <-> (r-2+i, c-2+j); outside the grid = 0
+      const int pos = 62 + lcc, wi = pos >> 6, sh = pos & 63;  // bit offset of column c-2 in the three staged words
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const unsigned long long lo = sm.dw[lr + i][wi], hi = sm.dw[lr + i][wi + 1 < 3 ? wi + 1 : 2];
+        const unsigned long long bits = (lo >> sh) | (sh && wi + 1 < 3 ? hi << (64 - sh) : 0ull);
+        dwin |= ((uint32_t)bits & 31u) << (5 * i);
+      }
+    }
     if (dwin) {
       const int ni = __popc(dwin & ((0x0Eu << 5) | (0x0Eu << 10) | (0x0Eu << 15)));
       const int nb = __popc(dwin) - ni;
@@ -295,8 +257,6 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
       Dlo = __fmul_rn(Df, T_LO);
       Dhi = __fmul_rn(Df, T_HI);
     }
-    int hid = 3 | (3 << 3);
-    if (S.hidden != nullptr) hid = S.hidden[env_off + gcell];
     const float a = P.onep_veg[clip15(hid & 7)], b = P.onep_den[clip15((hid >> 3) & 7)];
     const float blo = __fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(Hf, T_LO), Dhi), a), b);
     const float bhi = __fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(Hf, T_HI), Dlo), a), b);
@@ -312,7 +272,9 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
       else u = bits_to_uniform(bits_at(kburn, (uint32_t)(gcell * 9 + d), half_burn, mode));
       ++n_draws;
       const float w = wind[d];
-      const float s = S.pslope ? S.pslope[(env_off + gcell) * 8 + dir_slot(d)] : 1.0f;
+      const int dsl = dir_slot(d);
+      const float4 sq = dsl < 4 ? sl_a : sl_b;
+      const float s = (dsl & 3) == 0 ? sq.x : ((dsl & 3) == 1 ? sq.y : ((dsl & 3) == 2 ? sq.z : sq.w));
       const float plo = __fmul_rn(__fmul_rn(blo, w), s), phi = __fmul_rn(__fmul_rn(bhi, w), s);
       if (u < plo) { ig = true; break; }
       if (u < phi) {
@@ -321,7 +283,7 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
           float heat = 0.0f;
           for (int di = 0; di < win; ++di)
             for (int dj = 0; dj < win; ++dj)
-              if (ctr[(di - R) * pitch + (dj - R)] == 2) heat = __fadd_rn(heat, sm.wmat[di * win + dj]);
+              if (ctr[(di - R) * pitch + (dj - R)] == 2) heat = __fadd_rn(heat, P.ring_w[max(abs(di - R), abs(dj - R))]);
           float dous = 0.0f;
           for (int q = 0; q < 25; ++q)
             if ((dwin >> q) & 1u) {
@@ -336,15 +298,93 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
         if (u < __fmul_rn(__fmul_rn(base_exact, w), s)) ig = true;
       }
     }
-    if (ig) sm.ignite[lr * T_TW + lcc] = 1;
+    if (ig) atomicOr(&sm.ign[lr], 1ull << lcc);
   }
   __syncthreads();
 
   // ---- write the new grid, burn-out ticks, counts -------------------------------------------------
   const TfKey ka1 = tf_key(sc[SC_AK10], sc[SC_AK11]), ka2 = tf_key(sc[SC_AK20], sc[SC_AK21]);
   const TfKey kg = tf_key(sc[SC_GROW0], sc[SC_GROW1]);
-  int nt = 0, nfire = 0;
+  int nt = 0, nfire = 0, nabs = 0;
   uint32_t n_ign = 0, n_ext = 0;
+  const bool dense_rule = P.p_tree > 0.0f;  // regrowth draws for every empty cell: the per-cell loop
+  const int lc = tid & 63, rg = tid >> 6;
+  if (!dense_rule) {
+    // only burning cells (burn-out) and igniting cells can change: a thread per row lists them, all threads work the
+    // list off (age draws / burn-out ticks), the changed bytes are patched in the staged tile and the tile's interior
+    // leaves as 128-bit stores
+    if (tid < T_TH) {
+      const int lr = tid;
+      const uint32_t* fr = sm.fbits[lr + R];
+      const unsigned long long lo = fr[0] | ((unsigned long long)fr[1] << 32), hi = fr[2] | ((unsigned long long)fr[3] << 32);
+      unsigned long long fire = (lo >> T_HC) | (hi << (64 - T_HC));
+      unsigned long long ig = sm.ign[lr];
+      nabs = __popcll(fire);
+      const int n = __popcll(fire) + __popcll(ig);
+      if (n) {
+        int idx = atomicAdd(&sm.nlist2, n);
+        while (fire) {
+          const int c = __ffsll((long long)fire) - 1;
+          fire &= fire - 1;
+          sm.list[idx++] = (uint16_t)((lr << 6) | c);
+        }
+        while (ig) {
+          const int c = __ffsll((long long)ig) - 1;
+          ig &= ig - 1;
+          sm.list[idx++] = (uint16_t)(0x8000 | (lr << 6) | c);
+        }
+      }
+    }
+    __syncthreads();
+    const int n2 = sm.nlist2;
+    for (int i = tid; i < n2; i += T_THREADS) {
+      const uint32_t ent = sm.list[i];
+      const int lr = (ent >> 6) & 31, lcc = ent & 63;
+      const size_t gcell = (size_t)(r0 + lr) * W + (c0 + lcc);
+      uint8_t* cellp = sm.tile + (lr + R) * pitch + (lcc + T_HC);
+      if (ent & 0x8000u) {  // tree -> fire: age draw, burn-out tick
+        int age;
+        if (J.age_new) age = J.age_new[((size_t)substep * S.N + e) * H * W + gcell];
+        else age = randint_from_bits(bits_at_ni(ka1, (uint32_t)gcell, half_cell, mode),
+                                     bits_at_ni(ka2, (uint32_t)gcell, half_cell, mode), P.age_lo, P.age_span, P.age_mult);
+        S.death[env_off + gcell] = (uint16_t)(tick + (uint32_t)age);
+        *cellp = 2;
+        ++n_ign;
+      } else if ((((uint32_t)S.death[env_off + gcell] - tick) & 0xFFFFu) == 0u) {  // fire_age <= 1 -> empty, age ends at 0
+        S.death[env_off + gcell] = 0;
+        *cellp = 0;
+        ++n_ext;
+      }
+    }
+    nt = -(int)n_ign;
+    nfire = (int)n_ign - (int)n_ext;
+    nabs += nfire;
+    __syncthreads();
+    if ((W & 15) == 0) {
+      if (tid < T_TH * 4) {
+        const int lr = tid >> 2, q = tid & 3;
+        const int gr = r0 + lr, gc = c0 + 16 * q;
+        if (gr < H && gc < W)
+          *reinterpret_cast<uint4*>(cell_out + env_off + (size_t)gr * W + gc) =
+              *reinterpret_cast<const uint4*>(sm.tile + (lr + R) * pitch + T_HC + 16 * q);
+      }
+    } else {
+      for (int k = 0; k < T_TH / 4; ++k) {
+        const int lr = rg + 4 * k, gr = r0 + lr, gc = c0 + lc;
+        if (gr < H && gc < W) cell_out[env_off + (size_t)gr * W + gc] = sm.tile[(lr + R) * pitch + (lc + T_HC)];
+      }
+    }
+  } else {
+  // the burn-out ticks of this thread's burning cells first (independent loads), then the rule
+  uint16_t dth[T_TH / 4];
+#pragma unroll
+  for (int k = 0; k < T_TH / 4; ++k) {
+    const int lr = rg + 4 * k;
+    const int gr = r0 + lr, gc = c0 + lc;
+    dth[k] = 0;
+    if (gr < H && gc < W && sm.tile[(lr + R) * pitch + (lc + T_HC)] == 2) dth[k] = S.death[env_off + (size_t)gr * W + gc];
+  }
+#pragma unroll
   for (int k = 0; k < T_TH / 4; ++k) {
     const int lr = rg + 4 * k;
     const int gr = r0 + lr, gc = c0 + lc;
@@ -352,37 +392,41 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
     const size_t gcell = (size_t)gr * W + gc;
     const int old = sm.tile[(lr + R) * pitch + (lc + T_HC)];
     int nw = old;
-    if (old == 1 && sm.ignite[lr * T_TW + lc]) {
+    if (old == 1 && ((sm.ign[lr] >> lc) & 1ull)) {
       nw = 2;
       int age;
       if (J.age_new) age = J.age_new[((size_t)substep * S.N + e) * H * W + gcell];
-      else age = randint_from_bits(bits_at(ka1, (uint32_t)gcell, half_cell, mode),
-                                   bits_at(ka2, (uint32_t)gcell, half_cell, mode), P.age_lo, P.age_span, P.age_mult);
+      else age = randint_from_bits(bits_at_ni(ka1, (uint32_t)gcell, half_cell, mode),
+                                   bits_at_ni(ka2, (uint32_t)gcell, half_cell, mode), P.age_lo, P.age_span, P.age_mult);
       S.death[env_off + gcell] = (uint16_t)(tick + (uint32_t)age);  // burns out at tick + age
       ++n_ign;
     } else if (old == 0) {
       if (P.p_tree > 0.0f) {
         float u;
         if (J.u_grow) u = J.u_grow[((size_t)substep * S.N + e) * H * W + gcell];
-        else u = bits_to_uniform(bits_at(kg, (uint32_t)gcell, half_cell, mode));
+        else u = bits_to_uniform(bits_at_ni(kg, (uint32_t)gcell, half_cell, mode));
         if (u < P.p_tree) nw = 1;
       }
     } else if (old == 2) {
-      if (((S.death[env_off + gcell] - tick) & 0xFFFFu) == 0u) {  // fire_age <= 1 -> empty, age ends at 0
+      if ((((uint32_t)dth[k] - tick) & 0xFFFFu) == 0u) {  // fire_age <= 1 -> empty, age ends at 0
         nw = 0;
         S.death[env_off + gcell] = 0;
         ++n_ext;
       }
     }
     cell_out[env_off + gcell] = (uint8_t)nw;
-    nt += (nw == 1) - (old == 1);     // change of the env's tree / fire counts (tile_flags_kernel counted
-    nfire += (nw == 2) - (old == 2);  // the grid as it was before this sub-step)
+    nabs += (nw == 2);
+    nt += (nw == 1) - (old == 1);     // change of the env's tree / fire counts
+    nfire += (nw == 2) - (old == 2);
+  }
   }
   nt = __reduce_add_sync(GCA_FULL, nt);
   nfire = __reduce_add_sync(GCA_FULL, nfire);
+  nabs = __reduce_add_sync(GCA_FULL, nabs);
   if (lane == 0) {
     if (nt) atomicAdd(&sm.cnt_tree, nt);
     if (nfire) atomicAdd(&sm.cnt_fire, nfire);
+    if (nabs) atomicAdd(&sm.fire_abs, nabs);
   }
   if (stats != nullptr) {
     const uint32_t a = __reduce_add_sync(GCA_FULL, n_draws), b = __reduce_add_sync(GCA_FULL, n_ign);
@@ -395,10 +439,253 @@ ca_tiled_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gc
     }
   }
   __syncthreads();
+  int fire_after = 0;
   if (tid == 0) {
     if (sm.cnt_tree) atomicAdd(&counts[2 * e], sm.cnt_tree);
     if (sm.cnt_fire) atomicAdd(&counts[2 * e + 1], sm.cnt_fire);
     if (stats != nullptr && nfront) atomicAdd(&stats[0], (unsigned long long)nfront);
+    fire_after = sm.fire_abs;
+  }
+  return fire_after;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile activity (see the head of the file)
+//   tile index t = (e * TY + ty) * TX + tx;  fire[t] u32;  list[] u32;  nactive[j] = entries of sub-step j's list
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tile_count_kernel(int N, int H, int W, int TX, int TY,
+                                                         const uint8_t* __restrict__ cell, uint32_t* __restrict__ fire,
+                                                         int32_t* __restrict__ counts) {
+  // a warp per tile: lane l reads 16 cells of rows (l >> 2) + 8 q, q = 0..3 -- four independent 128-bit loads in flight
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)N * TY * TX;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  // the counts of the env of the CTA's first tile are summed in shared memory first
+  __shared__ int s_cnt[2];
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const long long t_cta = (long long)blockIdx.x * (blockDim.x >> 5);
+  const int e_cta = t_cta < total ? (int)(t_cta / ((long long)TX * TY)) : N;
+  int acc_t = 0, acc_f = 0;
+  for (long long t = t_cta + (threadIdx.x >> 5); t < total; t += nwarps) {
+    const int tx = (int)(t % TX), ty = (int)((t / TX) % TY), e = (int)(t / ((long long)TX * TY));
+    const int c = tx * T_TW + (lane & 3) * 16;
+    int nt = 0, nf = 0;
+    if ((W & 15) == 0) {
+      uint4 v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = ty * T_TH + (lane >> 2) + 8 * q;
+        v[q] = make_uint4(0u, 0u, 0u, 0u);
+        if (r < H && c < W) v[q] = *reinterpret_cast<const uint4*>(cell + ((size_t)e * H + r) * W + c);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // cell codes 0 / 1 / 2: bit 0 = tree, bit 1 = fire
+          nt += __popc(w[k] & 0x01010101u);
+          nf += __popc(w[k] & 0x02020202u);
+        }
+      }
+    } else {
+      for (int q = 0; q < 4; ++q) {
+        const int r = ty * T_TH + (lane >> 2) + 8 * q;
+        if (r >= H) continue;
+        const uint8_t* src = cell + ((size_t)e * H + r) * W + c;
+        for (int k = 0; k < 16 && c + k < W; ++k) {
+          const int v = src[k];
+          nt += v == 1;
+          nf += v == 2;
+        }
+      }
+    }
+    nt = __reduce_add_sync(GCA_FULL, nt);
+    nf = __reduce_add_sync(GCA_FULL, nf);
+    if (lane == 0) {
+      fire[t] = (uint32_t)nf;
+      if (e == e_cta) { acc_t += nt; acc_f += nf; }  // (thousands of tiles of one env: no global atomic per tile)
+      else {
+        if (nt) atomicAdd(&counts[2 * e], nt);
+        if (nf) atomicAdd(&counts[2 * e + 1], nf);
+      }
+    }
+  }
+  if (lane == 0) {
+    if (acc_t) atomicAdd(&s_cnt[0], acc_t);
+    if (acc_f) atomicAdd(&s_cnt[1], acc_f);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && e_cta < N) {
+    if (s_cnt[0]) atomicAdd(&counts[2 * e_cta], s_cnt[0]);
+    if (s_cnt[1]) atomicAdd(&counts[2 * e_cta + 1], s_cnt[1]);
+  }
+}
+
+// appends tile `gid` to the list of sub-step j when it is active: its 3x3 tile neighbourhood holds fire (R <= 10 is
+// smaller than a tile) or regrowth can change any cell.  All 32 lanes of a warp call.
+__device__ __forceinline__ void list_append(long long gid, long long total, int TX, int TY, const uint32_t* __restrict__ fire,
+                                            uint32_t* __restrict__ list, int* __restrict__ nactive, int j, int all_active) {
+  bool act = false;
+  if (gid < total) {
+    act = all_active != 0;
+    if (!act) {
+      const int tx = (int)(gid % TX), ty = (int)((gid / TX) % TY);
+      const uint32_t* f = fire + (gid - (long long)ty * TX - tx);  // the env's tile (0, 0)
+      for (int dy = -1; dy <= 1 && !act; ++dy) {
+        const int y = ty + dy;
+        if (y < 0 || y >= TY) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int x = tx + dx;
+          if (x >= 0 && x < TX && f[y * TX + x] != 0u) { act = true; break; }
+        }
+      }
+    }
+  }
+  const uint32_t bal = __ballot_sync(GCA_FULL, act);
+  if (bal) {
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&nactive[j], __popc(bal));
+    base = __shfl_sync(GCA_FULL, base, 0);
+    if (act) list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)gid;
+  }
+}
+
+// Once per env step: the key schedules of ALL K sub-steps (a warp per env: the 3K split levels of the key chain are
+// sequential, a lane pair runs the two blocks of a split; then lane pair 2j derives Sburn / Sgrow / the randint keys of
+// sub-step j and pair 2j+1 its wind draws, 4 more levels) into sched[e][j][12], and the active-tile list of sub-step 0.
+__global__ void __launch_bounds__(256) tiled_sched_all_kernel(gca_params P, gca_state S, gca_inject J, uint32_t* sched,
+                                                              int TX, int TY, const uint32_t* __restrict__ fire,
+                                                              uint32_t* __restrict__ list, int* __restrict__ nactive,
+                                                              int all_active) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gwarp = gid >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gwarp < S.N) {
+    const int e = (int)gwarp, K = P.K, mode = P.rng_mode, N = S.N;
+    uint32_t* se = sched + (size_t)e * SC_N * GCA_MAX_K;
+    const int pair = lane >> 1, j = pair >> 1;
+    const uint32_t w = lane & 1;
+    const bool burn_role = (pair & 1) == 0;
+    uint32_t k0 = S.key[2 * e], k1 = S.key[2 * e + 1];
+    uint32_t c0 = 0, c1 = 0, sw0 = 0, sw1 = 0;  // burn role: S1 ; wind role: Sidx (c) and Swind (sw) of sub-step j
+    for (int q = 0; q < K; ++q) {
+      uint32_t n0, n1, s0, s1;
+      split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K1, S1
+      if (q == j && burn_role) { c0 = s0; c1 = s1; }
+      k0 = n0; k1 = n1;
+      split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K2, Swind
+      if (q == j && !burn_role) { sw0 = s0; sw1 = s1; }
+      k0 = n0; k1 = n1;
+      split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K3, Sidx
+      if (q == j && !burn_role) { c0 = s0; c1 = s1; }
+      k0 = n0; k1 = n1;
+    }
+    const uint32_t sc0 = (mode == GCA_RNG_LEGACY) ? w : 0u;  // split counters of this lane
+    const uint32_t sc1 = (mode == GCA_RNG_LEGACY) ? w + 2u : w;
+    uint32_t o0, o1, p0, p1, n0, n1, s0, s1;
+    // level 1: burn: split(S1) -> Ka, Sburn ; wind: split(Sidx) -> wk1, wk2
+    tf_exchange(c0, c1, sc0, sc1, o0, o1, p0, p1);
+    assemble_split(mode, w, o0, o1, p0, p1, n0, n1, s0, s1);
+    const uint32_t sburn0 = s0, sburn1 = s1;  // (wind role: wk2)
+    uint32_t cur0 = n0, cur1 = n1;            // burn: Ka ; wind: wk1
+    // level 2: burn: split(Ka) -> Kb, Sgrow ; wind: even lane bits(wk1, ()), odd lane bits(wk2, ())
+    tf_exchange(burn_role ? cur0 : (w ? sburn0 : cur0), burn_role ? cur1 : (w ? sburn1 : cur1), burn_role ? sc0 : 0u,
+                burn_role ? sc1 : 0u, o0, o1, p0, p1);
+    assemble_split(mode, w, o0, o1, p0, p1, n0, n1, s0, s1);
+    const uint32_t sgrow0 = s0, sgrow1 = s1;
+    const uint32_t my_bits = (mode == GCA_RNG_LEGACY) ? o0 : (o0 ^ o1);
+    const uint32_t pr_bits = (mode == GCA_RNG_LEGACY) ? p0 : (p0 ^ p1);
+    const uint32_t hb = w ? pr_bits : my_bits, lb = w ? my_bits : pr_bits;
+    cur0 = n0; cur1 = n1;  // burn: Kb
+    // level 3: burn: split(Kb) -> Kc, Sage ; wind: bits(Swind, ())
+    tf_exchange(burn_role ? cur0 : sw0, burn_role ? cur1 : sw1, burn_role ? sc0 : 0u, burn_role ? sc1 : 0u, o0, o1, p0, p1);
+    assemble_split(mode, w, o0, o1, p0, p1, n0, n1, s0, s1);
+    const uint32_t uw_bits = (mode == GCA_RNG_LEGACY) ? o0 : (o0 ^ o1);
+    // level 4: burn: split(Sage) -> ak1, ak2
+    tf_exchange(s0, s1, sc0, sc1, o0, o1, p0, p1);
+    uint32_t a10, a11, a20, a21;
+    assemble_split(mode, w, o0, o1, p0, p1, a10, a11, a20, a21);
+    if (j < K && w == 0) {
+      uint32_t* sc = se + j * SC_N;
+      if (burn_role) {
+        sc[SC_BURN0] = sburn0; sc[SC_BURN1] = sburn1; sc[SC_GROW0] = sgrow0; sc[SC_GROW1] = sgrow1;
+        sc[SC_AK10] = a10; sc[SC_AK11] = a11; sc[SC_AK20] = a20; sc[SC_AK21] = a21;
+      } else {
+        float u = bits_to_uniform(uw_bits);
+        int step = randint_from_bits(hb, lb, 1, 7u, 4u);
+        if (J.u_wind) u = J.u_wind[(size_t)j * N + e];
+        if (J.wind_step) step = J.wind_step[(size_t)j * N + e];
+        sc[9] = (u < P.p_wind_change) ? 1u : 0u;
+        sc[10] = (uint32_t)step;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {  // the wind index is threaded through the sub-steps; the chain's end is the env's new key
+      int wi = S.wind_index[e];
+      for (int q = 0; q < K; ++q) {
+        uint32_t* sc = se + q * SC_N;
+        sc[SC_WIND] = (uint32_t)wi;
+        if (sc[9]) wi = (wi + (int)sc[10]) % 8;
+      }
+      S.wind_index[e] = wi;
+      S.key[2 * e] = k0;
+      S.key[2 * e + 1] = k1;
+    }
+  }
+  list_append(gid, (long long)S.N * TY * TX, TX, TY, fire, list, nactive, 0, all_active);
+}
+
+template <bool USE_TMA>
+__global__ void __launch_bounds__(T_THREADS, 3)
+ca_tiled_list_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gca_state S,
+                     const __grid_constant__ gca_inject J, const __grid_constant__ CUtensorMap tmap,
+                     uint8_t* __restrict__ cell_out, const uint32_t* __restrict__ sched, int32_t* __restrict__ counts,
+                     unsigned long long* stats, uint32_t* __restrict__ fire, const uint32_t* __restrict__ list,
+                     const int* __restrict__ nactive, int substep, int pitch, int TX, int TY) {
+  __shared__ TileSmem sm;
+  const int n = nactive[substep];
+  const uint32_t* cur = list + (substep & 1 ? (long long)S.N * TY * TX : 0);
+  int it = 0;
+  for (int i = blockIdx.x; i < n; i += gridDim.x, ++it) {
+    const uint32_t t = cur[i];
+    const int tx = (int)(t % (uint32_t)TX), ty = (int)((t / (uint32_t)TX) % (uint32_t)TY), e = (int)(t / (uint32_t)(TX * TY));
+    const int after = ca_tile_body<USE_TMA>(sm, P, S, J, &tmap, S.cell, cell_out, sched, counts, stats, substep, pitch, e,
+                                            ty, tx, it, SC_N * GCA_MAX_K, SC_N * substep);
+    if (threadIdx.x == 0) fire[t] = (uint32_t)after;  // (only this tile's CTA writes it; the next list is built from it)
+    __syncthreads();  // the shared tile is free for the next entry
+  }
+}
+
+// copies the new cells of the listed tiles from the scratch grid back into the grid and -- every tile's new fire
+// count being final once this kernel runs -- builds the active-tile list of the NEXT sub-step (build_next)
+__global__ void __launch_bounds__(128) tile_apply_list_kernel(int N, int H, int W, int TX, int TY, uint32_t* __restrict__ list,
+                                                              int* __restrict__ nactive, int substep,
+                                                              const uint8_t* __restrict__ scratch, uint8_t* __restrict__ cell,
+                                                              const uint32_t* __restrict__ fire, int build_next, int all_active) {
+  const int n = nactive[substep];
+  const int tid = threadIdx.x;
+  const long long total = (long long)N * TY * TX;
+  // the lists of successive sub-steps alternate between the two halves of the list buffer
+  const uint32_t* cur = list + (substep & 1 ? total : 0);
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint32_t t = cur[i];
+    const int tx = (int)(t % (uint32_t)TX), ty = (int)((t / (uint32_t)TX) % (uint32_t)TY), e = (int)(t / (uint32_t)(TX * TY));
+    const int r = ty * T_TH + (tid >> 2), c = tx * T_TW + (tid & 3) * 16;
+    if (r >= H || c >= W) continue;
+    const size_t off = ((size_t)e * H + r) * W + c;
+    if ((W & 15) == 0) {
+      *reinterpret_cast<uint4*>(cell + off) = *reinterpret_cast<const uint4*>(scratch + off);
+    } else {
+      for (int k = 0; k < 16 && c + k < W; ++k) cell[off + k] = scratch[off + k];
+    }
+  }
+  if (build_next) {
+    uint32_t* nxt = list + (substep & 1 ? 0 : total);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += stride)
+      list_append(base + tid, total, TX, TY, fire, nxt, nactive, substep + 1, all_active);
   }
 }
 
@@ -470,65 +757,60 @@ static bool make_tmap(CUtensorMap* m, const uint8_t* base, int N, int H, int W, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Runs K sub-steps and the epilogue.  Per sub-step: key schedule, tile activity flags (+ cell counts in
-// the last one), the CA kernel on the active tiles (S.cell -> scratch_cell), the copy back.
-// scratch_cell: [N][H][W] u8; scratch_sched: [N][12] u32; scratch_counts: [N][2] i32;
-// tile_flags: [N][ceil(H/32)][ceil(W/64)] u8.
+// One env step: one clear, one dense count, the key schedules of all sub-steps + the first list, then 2 kernels with
+// small fixed grids per sub-step and the epilogue.  Layout of `aux` (words): nactive[16] | fire[tiles] | list[2 tiles],
+// with nactive directly behind the counts so that one clear covers both.
 static cudaError_t enqueue_tiled_env_step(const gca_params& p, const gca_state& s, const int32_t* actions,
-                                          const gca_step_out& out, const gca_inject& inj, uint32_t flags,
+                                                 const gca_step_out& out, const gca_inject& inj, uint32_t flags,
                                           uint8_t* scratch_cell, uint32_t* scratch_sched, int32_t* scratch_counts,
-                                          uint8_t* tile_flags, int use_tma, cudaStream_t st) {
+                                          uint8_t* aux8, int use_tma, cudaStream_t st) {
+  uint32_t* aux = reinterpret_cast<uint32_t*>(aux8);
   const int N = s.N, H = p.H, W = p.W, R = p.R;
   const int pitch = T_PITCH_MAX;
   const int rows = T_TH + 2 * R;
   const int TX = (W + T_TW - 1) / T_TW, TY = (H + T_TH - 1) / T_TH;
+  const long long tiles = (long long)N * TX * TY;
+  if (tiles >= (1ll << 31)) return cudaErrorInvalidValue;
+  int* nactive = reinterpret_cast<int*>(aux);
+  uint32_t* fire = aux + 16;
+  uint32_t* list = fire + tiles;
+  if (reinterpret_cast<int32_t*>(nactive) != scratch_counts + 2 * (size_t)N) return cudaErrorInvalidValue;
   cudaError_t err;
-  // regrowth (p_tree > 0) can change any empty cell: every tile is active then
-  const int all_active = p.p_tree > 0.0f ? 1 : 0;
+  const int all_active = p.p_tree > 0.0f ? 1 : 0;  // regrowth can change any empty cell
+  if ((err = cudaMemsetAsync(scratch_counts, 0, sizeof(int32_t) * (2 * (size_t)N + 16), st)) != cudaSuccess) return err;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  const int g_count = (int)((tiles + 7) / 8 < (long long)sms * 4 ? (tiles + 7) / 8 : (long long)sms * 4);  // 8 warps per CTA, a warp per tile
+  const int g_tile = (int)(tiles < (long long)sms * 4 ? tiles : (long long)sms * 4);
+  const int g_apply = (int)(tiles < (long long)sms * 8 ? tiles : (long long)sms * 8);
+  tile_count_kernel<<<g_count, 256, 0, st>>>(N, H, W, TX, TY, s.cell, fire, scratch_counts);
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  const bool tma = use_tma && make_tmap(&tm, s.cell, N, H, W, pitch, rows);
+  const long long threads = tiles > 32ll * N ? tiles : 32ll * N;
+  tiled_sched_all_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p, s, inj, scratch_sched, TX, TY, fire, list,
+                                                                          nactive, all_active);
   for (int j = 0; j < p.K; ++j) {
-    const int last = j == p.K - 1;
-    tiled_sched_kernel<<<(N + 127) / 128, 128, 0, st>>>(p, s, inj, j, scratch_sched);
-    if (last && (err = cudaMemsetAsync(scratch_counts, 0, sizeof(int32_t) * 2 * N, st)) != cudaSuccess) return err;
-    // gridDim.z holds the env: at most 65535 envs per launch
-    for (int e0 = 0; e0 < N; e0 += 65535) {
-      const int ne = min(65535, N - e0);
-      dim3 grid(TX, TY, ne);
-      gca_state sv = s;  // the slice's view of the per-env arrays the tile kernels index by blockIdx.z
-      sv.N = ne;
-      const size_t cells = (size_t)e0 * H * W;
-      sv.cell = s.cell + cells;
-      sv.death = s.death + cells;
-      sv.hidden = s.hidden ? s.hidden + cells : nullptr;
-      sv.pslope = s.pslope ? s.pslope + cells * 8 : nullptr;
-      sv.doused = s.doused + (size_t)e0 * H * ((W + 63) >> 6);
-      sv.tick = s.tick + e0;
-      gca_inject jv = inj;  // injected fields are indexed [substep][N][...]: only whole-batch launches may use them
-      if (e0 > 0 || ne < N) {
-        if (inj.u_burn || inj.u_grow || inj.age_new) return cudaErrorInvalidValue;
-      }
-      CUtensorMap tm;
-      memset(&tm, 0, sizeof(tm));
-      const bool tma = use_tma && make_tmap(&tm, sv.cell, ne, H, W, pitch, rows);
-      uint8_t* tf = tile_flags + (size_t)e0 * TX * TY;
-      tile_flags_kernel<<<grid, 128, 0, st>>>(H, W, sv.cell, tf, scratch_counts + 2 * (size_t)e0, last, all_active);
-      if (tma)
-        ca_tiled_kernel<true><<<grid, T_THREADS, 0, st>>>(p, sv, jv, tm, sv.cell, scratch_cell + cells,
-                                                          scratch_sched + (size_t)e0 * SC_N, scratch_counts + 2 * (size_t)e0,
-                                                          out.stats, tf, j, pitch);
-      else
-        ca_tiled_kernel<false><<<grid, T_THREADS, 0, st>>>(p, sv, jv, tm, sv.cell, scratch_cell + cells,
-                                                           scratch_sched + (size_t)e0 * SC_N, scratch_counts + 2 * (size_t)e0,
-                                                           out.stats, tf, j, pitch);
-      tile_apply_kernel<<<grid, 128, 0, st>>>(H, W, tf, scratch_cell + cells, sv.cell);
-    }
+    if (tma)
+      ca_tiled_list_kernel<true><<<g_tile, T_THREADS, 0, st>>>(p, s, inj, tm, scratch_cell, scratch_sched, scratch_counts,
+                                                               out.stats, fire, list, nactive, j, pitch, TX, TY);
+    else
+      ca_tiled_list_kernel<false><<<g_tile, T_THREADS, 0, st>>>(p, s, inj, tm, scratch_cell, scratch_sched, scratch_counts,
+                                                                out.stats, fire, list, nactive, j, pitch, TX, TY);
+    tile_apply_list_kernel<<<g_apply, 128, 0, st>>>(N, H, W, TX, TY, list, nactive, j, scratch_cell, s.cell, fire,
+                                                    j + 1 < p.K ? 1 : 0, all_active);
     if ((err = cudaGetLastError()) != cudaSuccess) return err;
   }
   tiled_finish_kernel<<<(N + 127) / 128, 128, 0, st>>>(p, s, actions, out, scratch_counts, flags);
   return cudaGetLastError();
 }
 
-// The 4 K + 1 launches of one env step as ONE CUDA graph launch: at 4096x4096 with a small fire nearly every tile
-// exits at once and the step is bound by launch latency (85 us for K = 1).  The graph is captured once per set of
+// The 2 K + 3 launches of one env step as ONE CUDA graph launch: at 4096x4096 with a small fire the step is bound by
+// launch latency.  The graph is captured once per set of
 // buffers (thread-local cache of one entry; a capture stream of its own: the caller's may be the legacy stream, which
 // cannot capture) and replayed with only the action pointer of the last kernel patched.  GCA_TILED_GRAPH=0 disables it.
 namespace {

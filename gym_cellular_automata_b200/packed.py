@@ -95,9 +95,10 @@ class PackedState:
         self.time_step.fill_(1)
         tiled = not (H == 64 and W == 64)
         self.scratch_cell = torch.zeros((N, H, W), dtype=torch.uint8, device=d) if tiled else None
-        # per-env key schedule + counts (14 words each), then one activity byte per 32x64 tile
+        # per env the key schedule of up to 8 sub-steps (96 words) + tree / fire counts (2), 16 list counters, then per
+        # 32x64 tile its burning-cell count and two slots of the active-tile lists (include/gca.h: scratch_u32)
         n_tiles = N * ((H + 31) // 32) * ((W + 63) // 64)
-        self.scratch_u32 = torch.zeros(N * 14 + (n_tiles + 3) // 4, dtype=torch.int32, device=d) if tiled else None
+        self.scratch_u32 = torch.zeros(N * 98 + 16 + 3 * n_tiles, dtype=torch.int32, device=d) if tiled else None
         self.work = None if tiled else torch.zeros(N, dtype=torch.int32, device=d)
         self.order = None   # set by enable_balancing()
         # tree / fire bit-boards, the grid representation the 64x64 kernel reads (kept in step with `cell`)

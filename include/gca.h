@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define GCA_VERSION 104
+#define GCA_VERSION 105
 #define GCA_MAX_R 10        /* burn kernel radius: ceil(log2(size)) - 2; 10 at 4096 */
 #define GCA_MAX_K 8         /* CA sub-steps fused into one env step */
 
@@ -129,8 +129,9 @@ typedef struct gca_state {
   float* reward_accumulated;  /* [N] */
   /* scratch of the tiled path (grids other than 64x64); may be NULL for 64x64 */
   uint8_t* scratch_cell;      /* [N][H][W] second grid buffer (tiles read one, write the other) */
-  uint32_t* scratch_u32;      /* N*14 words: per-env sub-step key schedule (12) + tree/fire counts (2), followed by
-                                 N * ceil(H/32) * ceil(W/64) bytes (rounded up to words): tile activity flags */
+  uint32_t* scratch_u32;      /* N*98 + 16 + 3*T words, T = N * ceil(H/32) * ceil(W/64) tiles: per env the key schedule
+                                 of up to GCA_MAX_K sub-steps (12 words each) + tree/fire counts (2); 16 counters of the
+                                 per-sub-step active-tile lists; per tile its number of burning cells; two list buffers */
   /* optional load balancing of the 64x64 kernel (one warp per env, so an env step costs what its
    * fire front costs): the kernel writes work[e]; gca_balance_order turns it into order[] */
   uint32_t* work;             /* [N] cost estimate of the last env step, or NULL */
