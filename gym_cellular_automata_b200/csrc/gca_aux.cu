@@ -564,14 +564,6 @@ __global__ void __launch_bounds__(1024) balance_order_kernel(int N, int wpc, int
         const int in_wave = min(BAL_WAVE, full - wave * BAL_WAVE);
         const int q = (wave & 1) ? (in_wave - 1 - pos) : pos;
         rank = wave * BAL_WAVE + q;
-#ifdef S64_FAIR
-      } else if (groups >= 2) {
-        // one CTA per SM holding `groups` interleaved lock-step groups of equal standing with the warp scheduler: the
-        // CTA's rounds are dealt to its groups like cards, every other turn in reverse, so the groups' sums are equal
-        const int g = s64_group_of(w), wg = s64_index_in_group(w);
-        const int round = wg * groups + ((wg & 1) ? (groups - 1 - g) : g);
-        rank = round * full + ((round & 1) ? (full - 1 - b) : b);
-#endif
       } else if (groups == 2) {
         // one CTA per SM holding two lock-step groups: the bin is the CTA, its two groups split the rounds like
         // the two CTAs of an SM above (skew = 0: equal sums)

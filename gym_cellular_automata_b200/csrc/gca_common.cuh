@@ -15,24 +15,6 @@
 
 namespace gca {
 
-// Which lock-step group a warp belongs to.  Blocked (warps 0 .. GE-1 = group 0, ...): the warp scheduler favours the
-// lower-numbered warps, so group 0 runs ahead of the others exactly like the first CTA of an SM runs ahead of the second.
-// S64_FAIR: the groups are interleaved so that each holds the same mix of old / young warps on every scheduler
-// (sub-partition = warp % 4): pairs of warps alternate between two groups and swap sides every quad; with four groups
-// the assignment rotates by one per quad.
-#ifdef S64_FAIR
-__host__ __device__ constexpr int s64_group_of(int w) {
-  return GCA_S64_GROUPS == 1 ? 0 : (GCA_S64_GROUPS == 2 ? (((w >> 1) + (w >> 2)) & 1) : ((w + (w >> 2)) & 3));
-}
-#else
-__host__ __device__ constexpr int s64_group_of(int w) { return w / (GCA_S64_WARPS / GCA_S64_GROUPS); }
-#endif
-__host__ __device__ constexpr int s64_index_in_group(int w) {
-  int n = 0;
-  for (int v = 0; v < w; ++v) n += s64_group_of(v) == s64_group_of(w) ? 1 : 0;
-  return n;
-}
-
 // ---------------------------------------------------------------------------------------------
 // threefry2x32-20 (Random123), the block function behind jax.random (see oracle/prng.py).
 // The key-schedule word of each injection is pre-added by the caller-side struct so that the

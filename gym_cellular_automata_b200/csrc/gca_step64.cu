@@ -47,18 +47,6 @@ constexpr int S64_CHAIN_WARPS = (S64_E + 15) / 16;  // warps that walk the key c
 // owner syncs -- a hardware wait, no polling) when there are enough barriers and no lock-step groups use them; else a
 // shared-memory flag the owner polls (measured: the polling loop was 4 % of the kernel's instructions).
 constexpr bool S64_CHAIN_BAR = S64_E <= 15 && S64_G == 1;
-// ... or, with lock-step groups / more than 15 owners, ONE named barrier per chain warp (ids S64_G + 1 ..): the chain warp
-// arrives once its (up to 16) chains are walked, the owners of those envs sync on it
-constexpr bool S64_CHAIN_BAR2 = !S64_CHAIN_BAR && S64_G + S64_CHAIN_WARPS <= 15;
-__host__ __device__ constexpr bool s64_groups_even() {
-  for (int g = 0; g < S64_G; ++g) {
-    int n = 0;
-    for (int v = 0; v < S64_E; ++v) n += s64_group_of(v) == g ? 1 : 0;
-    if (n != S64_GE) return false;
-  }
-  return true;
-}
-static_assert(S64_G != 3 && s64_groups_even(), "every lock-step group must hold S64_E / S64_G warps");
 constexpr int S64_IGN_CAP = 160;       // deferred fire-age draws buffered per env (flushed early when full)
 constexpr int S64_WP = 288;            // warp-private pair buffer: < 32 carried over + <= 256 of one chunk
 constexpr uint32_t S64_HALF_BURN = 9u * 4096u / 2u;
@@ -91,14 +79,6 @@ struct __align__(16) EnvSmem {
   int nscan;                        // rows whose burn-out ticks must be scanned in this env step: their indices are the
                                     //   first nscan BYTES of ignlist (which holds no ignitions before apply(0))
   int pad_;
-#ifdef S64_ASYNC
-  unsigned long long mbar;          // completion of the published phase: tx count = items + buffered draws outstanding
-  int q_taken;                      // ticket counter of the published phase: (phase tag << 20) | tickets handed out
-  int q_total;                      // (phase tag << 20) | work items of the phase (chunks, then scan rounds)
-  int q_nch;                        // chunks among them
-  int q_j;                          // CA sub-step of the phase (injected uniforms are addressed by it)
-  int pad2_[2];
-#endif
 };
 static_assert(S64_E >= 1 && S64_E <= 32 && 28 % S64_E == 0, "envs per CTA: a divisor of 28 (28 warps of 72 registers fill an SM)");
 static_assert(sizeof(EnvSmem) % 16 == 0 && offsetof(EnvSmem, burn) % 16 == 0 && offsetof(EnvSmem, hot) % 16 == 0, "128-bit shared accesses");
@@ -111,13 +91,6 @@ struct __align__(16) CtaSmem {
   uint16_t pidx[S64_E][S64_WP];     // (cell << 4) | direction 0..8: the pair is compared with element cell * 9 + direction of uniform(Sburn, (H,W,3,3))
   int nch[32];                      // chunks of each env in the current pass
   int next[4];                      // work-item counter of the pooled phase, per group
-  uint8_t member[4][32];            // member[g][i] = warp (= env slot) of the i-th member of lock-step group g
-#ifdef S64_ASYNC
-  uint32_t avail;                   // bit s: env slot s has a published phase with tickets left
-  int finished;                     // owners whose env step is complete (no more phases will be published)
-  int pad_[2];
-  uint32_t wstat[S64_E][2];         // per warp: draws made, threshold cells re-evaluated (statistics)
-#endif
 };
 
 // barriers of one lock-step group (named barrier 1 + group, S64_GE warps); a single group uses barrier 0
@@ -149,36 +122,6 @@ __device__ __forceinline__ int smem_ld_acquire(const int* p) {
   asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
   return v;
 }
-
-#ifdef S64_ASYNC
-// mbarrier used as a counter of outstanding work (transaction count), see the asynchronous main loop
-__device__ __forceinline__ void mbar_init(unsigned long long* b, uint32_t arrivals) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(arrivals) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* b, uint32_t tx) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(tx) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t tx) {
-  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(tx) : "memory");
-}
-__device__ __forceinline__ void mbar_complete_tx(unsigned long long* b, uint32_t tx) {
-  asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(tx) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(unsigned long long* b, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
-  return __any_sync(GCA_FULL, ok != 0u);
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* b, uint32_t parity, uint32_t ns) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(b)), "r"(parity), "r"(ns) : "memory");
-  return __any_sync(GCA_FULL, ok != 0u);
-}
-constexpr int S64_QSHIFT = 20;                      // ticket words: phase tag above, count below
-constexpr int S64_QMASK = (1 << S64_QSHIFT) - 1;
-#endif
 
 __device__ __forceinline__ void prefetch_l1(const void* p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
@@ -254,7 +197,7 @@ __device__ __noinline__ void key_chain_pooled(EnvSmem& ce, const gca_params& P, 
   }
   if (wr) {
     ce.hot.x = k0; ce.hot.y = k1;
-    if (!S64_CHAIN_BAR && !S64_CHAIN_BAR2) smem_st_release(&ce.chain_done, 1);  // the owner warp of this env polls it before key_sides
+    if (!S64_CHAIN_BAR) smem_st_release(&ce.chain_done, 1);  // the owner warp of this env polls it before key_sides
   }
 }
 __device__ __noinline__ void key_sides(EnvSmem& sm, const gca_params& P, const gca_inject& J, int N, int e,
@@ -786,190 +729,6 @@ __device__ __noinline__ void render_env64(EnvSmem& sm, uint32_t* scratch, void* 
   __syncwarp();
 }
 
-#ifdef S64_ASYNC
-// The work loop of the asynchronous kernel: this warp takes work items (32-entry chunks of a front list, burn-out scan
-// rounds) of ANY env of the CTA and draws the buffered (cell, direction) pairs, until its own published phase is complete
-// (`waiting`: mbarrier of its env, parity `own_parity`) or, for a warp whose env step is finished, until every env of
-// the CTA is.  It returns with an empty pair buffer.  Out of line on purpose: the loop gets the whole register budget
-// and the caller's state (bit-boards, counters) is saved once around the call instead of being spilled inside the loop.
-template <int MODE, int HP, bool INJ>
-__device__ __noinline__ void s64_work_loop(CtaSmem& cs, const gca_params& P, const gca_state& S, const gca_inject& J,
-                                           int warp, int lane, bool waiting, uint32_t own_parity, int n_active, int N) {
-  EnvSmem& sm = cs.env[warp];
-  uint32_t* const wp32 = cs.pairs[warp];
-  uint16_t* const wpi = cs.pidx[warp];
-  const int K = P.K, mode = MODE < 0 ? P.rng_mode : MODE;
-  const uint8_t* const hidden = HP == 0 ? nullptr : S.hidden;
-  const float* const pslope = HP == 0 ? nullptr : S.pslope;
-  if (HP == 1) { __builtin_assume(hidden != nullptr); __builtin_assume(pslope != nullptr); }
-  const float* const j_u_burn = INJ ? J.u_burn : nullptr;
-  const float lutreg = lane < 8 ? P.onep_veg[lane] : (lane < 16 ? P.onep_den[lane - 8] : 0.0f);
-  const float w1 = P.ring_w[1], w2 = P.ring_w[2], w3 = P.ring_w[3], w4 = P.ring_w[4];
-  const bool own_done = !waiting;
-  bool own_open = waiting;   // the own phase may still have tickets
-  int PT = 0;                // pairs buffered by this warp
-  uint32_t n_draws = 0, n_thresh = 0;
-        for (;;) {
-          if (PT < 32) {
-            const bool own_ready = waiting && mbar_test(&sm.mbar, own_parity);
-            if (own_ready && PT == 0) break;
-            // (own phase complete with pairs of other envs still buffered: draw them first, then leave)
-            uint32_t m = own_ready ? 0u : *reinterpret_cast<volatile uint32_t*>(&cs.avail);
-            if (own_open && !own_ready) m |= 1u << warp;   // the owner never depends on the bit for its own items
-            int es_slot = -1, item = 0;
-            while (m) {
-              const int sl_ = ((m >> warp) & 1u) ? warp : (int)__ffs(m) - 1;   // the own env first
-              int tk = 0;
-              if (lane == 0) tk = smem_add_ret(&cs.env[sl_].q_taken, 1);
-              tk = __shfl_sync(GCA_FULL, tk, 0);
-              const int tot = *reinterpret_cast<volatile int*>(&cs.env[sl_].q_total);
-              if ((tk >> S64_QSHIFT) == (tot >> S64_QSHIFT) && (tk & S64_QMASK) < (tot & S64_QMASK)) {
-                if ((tk & S64_QMASK) == (tot & S64_QMASK) - 1 && lane == 0) atomicAnd(&cs.avail, ~(1u << sl_));  // the last ticket
-                es_slot = sl_;
-                item = tk & S64_QMASK;
-                break;
-              }
-              if (sl_ == warp && (tk >> S64_QSHIFT) == (tot >> S64_QSHIFT)) own_open = false;  // own tickets are all out
-              m &= ~(1u << sl_);
-            }
-            if (es_slot >= 0) {
-              EnvSmem& es = cs.env[es_slot];
-              const int nc_env = *reinterpret_cast<volatile int*>(&es.q_nch);
-              if (item >= nc_env) {
-                scan_round(es, S, item - nc_env, K, lane);
-                __syncwarp();
-                if (lane == 0) { __threadfence_block(); mbar_complete_tx(&es.mbar, 1u); }
-                continue;
-              }
-              const int chunk = item;
-            const int t = chunk * 32 + lane;
-            const bool inrange = t < es.cnt;
-            const uint32_t cell = inrange ? es.list[t] : 0u;
-            const int r = cell >> 6, c = cell & 63;
-            // the hidden byte is requested first: its (L2) latency hides behind the window work
-            int hid = 3 | (3 << 3);
-            if (hidden != nullptr && inrange) hid = hidden[(size_t)es.hot.w * 4096 + cell];
-            uint32_t A, B, C;
-            fire_window(es, r, c, A, B, C);
-            uint32_t dirm = ((B >> 3) & 7u) | (((B >> 12) & 7u) << 3) | (((B >> 21) & 7u) << 6);
-            // still a front cell in this sub-step?  (a listed tree leaves the front by igniting -- its own
-            // fire bit is then set -- or by losing its last burning neighbour)
-            const bool valid = inrange && !(dirm & 16u) && (dirm & ~16u) != 0u;
-            dirm &= ~16u;
-            // ring populations (Chebyshev rings 1..4 around the centre)
-            const int S1 = __popc(B & 0x00E07038u);
-            const int S2 = __popc(A & (0x07Cu << 18)) + __popc(B & 0x01F0F87Cu) + __popc(C & 0x07Cu);
-            const int S3 = __popc(A & ((0x0FEu << 9) | (0x0FEu << 18))) + __popc(B & 0x03F9FCFEu) +
-                           __popc(C & (0x0FEu | (0x0FEu << 9)));
-            const int S4 = __popc(A) + __popc(B) + __popc(C);
-            const float Hf = fmaf((float)(S4 - S3), w4,
-                                  fmaf((float)(S3 - S2), w3, fmaf((float)(S2 - S1), w2, (float)S1 * w1)));
-            float Dlo = 0.0f;
-            bool near_doused = false;
-            if ((((r & 1) ? es.dous_odd : es.dous_even) >> (r >> 1)) & 1u) {
-              const uint32_t dwin = dous_window(es, r, c);
-              if (dwin) {
-                const int ni = __popc(dwin & ((0x0Eu << 5) | (0x0Eu << 10) | (0x0Eu << 15)));
-                const int nb = __popc(dwin) - ni;
-                const float Df = fmaf((float)nb, P.dous_border, (float)ni * P.dous_inner);
-                Dlo = __fmul_rn(Df, S64_LO);
-                near_doused = true;
-              }
-            }
-            const float a = __shfl_sync(GCA_FULL, lutreg, clip15(hid & 7));
-            const float b = __shfl_sync(GCA_FULL, lutreg, 8 + clip15((hid >> 3) & 7));
-            const float ph_hi = __fsub_rn(__fmul_rn(Hf, S64_HI), Dlo);
-            const float bhi = __fmul_rn(__fmul_rn(ph_hi, a), b);
-            const int nd = (valid && bhi > 0.0f) ? __popc(dirm) : 0;
-            const int incl2 = warp_incl_scan(nd, lane);
-            int off = PT + incl2 - nd;
-            const uint32_t em = nd ? dirm : 0u;
-            // one record per (cell, burning direction): the cell's bound bhi rounded UP to a multiple of 32 ulp (2^-18
-            // relative: inside the enclosure's margin) to make room for the env slot, sign bit = "dousing nearby";
-            // and (cell << 4) | direction
-            const uint32_t rec = ((__float_as_uint(bhi) + 31u) & 0x7FFFFFE0u) | (uint32_t)es_slot | (near_doused ? 0x80000000u : 0u);
-            const uint32_t c16 = cell << 4;
-#pragma unroll
-            for (uint32_t d = 0; d < 9; ++d) {
-              if (d == 4) continue;
-              if (em & (1u << d)) {
-                wp32[off] = rec;
-                wpi[off] = (uint16_t)(c16 | d);
-                ++off;
-              }
-            }
-
-              const int added = __shfl_sync(GCA_FULL, incl2, 31);
-              PT += added;
-              __syncwarp();
-              if (lane == 0) {
-                if (added) mbar_expect_tx(&es.mbar, (uint32_t)added);
-                mbar_complete_tx(&es.mbar, 1u);
-              }
-              continue;
-            }
-            if (PT == 0) {  // nothing to take, nothing buffered
-              if (waiting) { if (mbar_try_wait(&sm.mbar, own_parity, 300u)) break; }
-              else {
-                if (*reinterpret_cast<volatile int*>(&cs.finished) >= n_active) break;
-                __nanosleep(400);
-              }
-              continue;
-            }
-          }
-          // ---- draw up to 32 buffered pairs, one per lane: the record holds everything but the env's key
-          const int n = min(PT, 32);
-          PT -= n;
-          n_draws += (lane == 0) ? (uint32_t)n : 0u;
-          const bool va = lane < n;
-          const uint32_t ent = va ? wp32[PT + lane] : 0u;
-          const uint32_t pk = va ? wpi[PT + lane] : 0u;
-          EnvSmem& des = cs.env[ent & 31u];
-          const uint4 hot = des.hot;
-          const uint32_t cell = pk >> 4, d = pk & 15u;
-          const uint32_t idx = cell * 9u + d;
-          // direction's wind and slope factors: the global load's latency hides behind the threefry block
-          float sl = 1.0f;
-          if (pslope != nullptr && va) sl = pslope[((size_t)hot.w * 4096 + cell) * 8 + d - (d > 4u ? 1u : 0u)];
-          const float wd = des.wind[d];
-          float ua;
-          if (j_u_burn) {
-            const size_t inj0 = (size_t)des.q_j * N * 4096;
-            ua = va ? j_u_burn[(inj0 + (size_t)hot.w * 4096) * 9 + idx] : 1.0f;
-          } else {
-            uint32_t o0, o1;
-            TfKey key;
-            key.k0 = hot.x; key.k1 = hot.y; key.k2 = hot.z;
-            if (mode == GCA_RNG_LEGACY) {
-              const bool first = idx < S64_HALF_BURN;
-              const uint32_t c0 = first ? idx : idx - S64_HALF_BURN;
-              threefry2x32(key, c0, c0 + S64_HALF_BURN, o0, o1);
-              ua = bits_to_uniform(first ? o0 : o1);
-            } else {
-              threefry2x32(key, 0u, idx, o0, o1);
-              ua = bits_to_uniform(o0 ^ o1);
-            }
-          }
-          const float phi = __fmul_rn(__fmul_rn(__uint_as_float(ent & 0x7FFFFFE0u), wd), sl);
-          if (va && ua < phi) pair_hit(P, hidden, des, ent, cell, wd, sl, phi, ua, n_thresh);
-          __syncwarp();
-          {
-            // the pairs of this round leave their envs' outstanding counts (one lane per env)
-            const uint32_t key_ = va ? (ent & 31u) : 32u;
-            const uint32_t same = __match_any_sync(GCA_FULL, key_);
-            if (va && (int)__ffs(same) - 1 == lane) {
-              __threadfence_block();   // the ignitions or-ed into the env's accumulator above
-              mbar_complete_tx(&cs.env[key_].mbar, (uint32_t)__popc(same));
-            }
-          }
-        }
-
-  n_thresh = __reduce_add_sync(GCA_FULL, n_thresh);
-  if (lane == 0) { cs.wstat[warp][0] += n_draws; cs.wstat[warp][1] += n_thresh; }
-  __syncwarp();
-}
-#endif
-
 // S64_TRACE (diagnostic builds only): per-env phase timestamps (SM clock, relative to the warp's start) go to
 // O.stats[8 + 16 e ...]; the caller must have allocated stats with 8 + 32 N words.
 #ifdef S64_TRACE
@@ -1005,10 +764,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
 #ifdef S64_TRACE
   long long trace_t = clk0;
 #endif
-  const int group = s64_group_of(warp), gwarp = s64_index_in_group(warp);  // lock-step group of this warp, index inside it
-#ifdef S64_FAIR
-  if (lane == 0) cs.member[group][gwarp] = (uint8_t)warp;  // (read after the group's first barrier)
-#endif
+  const int group = warp / S64_GE, gwarp = warp % S64_GE;  // lock-step group of this warp, index inside it
   const int slot = blockIdx.x * S64_E + warp;
   const int N = S.N;
   const bool active = slot < N;   // a warp without an env still joins the barriers and the pooled work
@@ -1018,17 +774,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
   uint32_t* const wp32 = cs.pairs[warp];  // warp-private pair buffer (and scratch of the owner phases)
   uint16_t* const wpi = cs.pidx[warp];
   uint16_t* const wp = reinterpret_cast<uint16_t*>(wp32);
-#ifdef S64_ASYNC
-  if (lane == 0) {
-    mbar_init(&sm.mbar, 1u);
-    sm.q_taken = 0; sm.q_total = 0; sm.q_nch = 0; sm.q_j = 0;
-    cs.wstat[warp][0] = 0u; cs.wstat[warp][1] = 0u;
-    if (warp == 0) { cs.avail = 0u; cs.finished = 0; }
-  }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();  // (every warp is here within a few cycles of the launch)
-#endif
-  if (!S64_CHAIN_BAR && !S64_CHAIN_BAR2) {
+  if (!S64_CHAIN_BAR) {
     if (lane == 0) sm.chain_done = 0;
     __syncthreads();  // (every warp is here within a few cycles of the launch) the flags are clear before a chain warp can set one
   }
@@ -1110,13 +856,6 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
 #pragma unroll
       for (int w = 0; w < S64_E - 1; ++w) asm volatile("bar.arrive %0, 64;" ::"r"(w + 1) : "memory");
     }
-    if (S64_CHAIN_BAR2) {
-      // one barrier per chain warp: the owners of slots 16 c .. 16 c + 15 (all but this warp itself, should it own one
-      // of them) wait on it
-      const int c = S64_E - 1 - warp;
-      const int owners = min(16, S64_E - 16 * c) - ((warp >> 4) == c ? 1 : 0);
-      asm volatile("bar.arrive %0, %1;" ::"r"(S64_G + 1 + c), "r"(32 * (owners + 1)) : "memory");
-    }
   }
   if (active) {
     S64_STAMP(19);
@@ -1177,17 +916,10 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     S64_STAMP(18);
   }
   if (S64_CHAIN_BAR && warp < S64_E - 1) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");
-  if (S64_CHAIN_BAR2) {
-    const int c = warp >> 4;  // the chain warp that walked this owner's chain: warp S64_E - 1 - c
-    if (warp != S64_E - 1 - c) {
-      const int owners = min(16, S64_E - 16 * c) - (((S64_E - 1 - c) >> 4) == c ? 1 : 0);
-      asm volatile("bar.sync %0, %1;" ::"r"(S64_G + 1 + c), "r"(32 * (owners + 1)) : "memory");
-    }
-  }
   if (active) {
     // the env's key chain is done (the chain warp walks it while the grids stream in); no CTA-wide barrier
     S64_MARK();
-    if (!S64_CHAIN_BAR && !S64_CHAIN_BAR2) {
+    if (!S64_CHAIN_BAR) {
       while (smem_ld_acquire(&sm.chain_done) == 0) __nanosleep(40);
       __syncwarp();
     }
@@ -1220,423 +952,9 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
 #endif
   }
 
-#ifndef S64_ASYNC
   const float lutreg = lane < 8 ? P.onep_veg[lane] : (lane < 16 ? P.onep_den[lane - 8] : 0.0f);
   const float w1 = P.ring_w[1], w2 = P.ring_w[2], w3 = P.ring_w[3], w4 = P.ring_w[4];
-#endif
 
-  auto epilogue = [&]() {
-#ifdef S64_TRACE
-  const uint32_t trace_rows = __reduce_add_sync(GCA_FULL, __popc(burnrows));  // rows scanned for burn-outs
-#endif
-  // ---- sparse in-place write-back of the cells that changed --------------------------------------
-  {
-    unsigned long long ch = ch0;
-    unsigned long long tt = t0, ff = f0;
-    int row = 2 * lane;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      while (ch) {
-        const int c = __ffsll((long long)ch) - 1;
-        ch &= ch - 1;
-        const uint8_t code = ((ff >> c) & 1ull) ? 2 : (((tt >> c) & 1ull) ? 1 : 0);
-        S.cell[cell_base + row * 64 + c] = code;
-      }
-      ch = ch1;
-      tt = t1; ff = f1;
-      row = 2 * lane + 1;
-    }
-  }
-  {
-    // the bit-board copy of the grid: rows that changed
-    ulonglong2* bbp = reinterpret_cast<ulonglong2*>(S.bb + (size_t)e * 128);
-    if (ch0) bbp[2 * lane] = make_ulonglong2(t0, f0);
-    if (ch1) bbp[2 * lane + 1] = make_ulonglong2(t1, f1);
-  }
-  reinterpret_cast<uint2*>(S.row_min + (size_t)e * 64)[lane] = rm;
-  const int tcount = __reduce_add_sync(GCA_FULL, __popcll(t0) + __popcll(t1));
-  const int fcount = __reduce_add_sync(GCA_FULL, __popcll(f0) + __popcll(f1));
-
-  if (O.stats != nullptr) {
-    const uint32_t a = __reduce_add_sync(GCA_FULL, n_front), b = __reduce_add_sync(GCA_FULL, n_draws);
-    const uint32_t c = __reduce_add_sync(GCA_FULL, n_ign), d = __reduce_add_sync(GCA_FULL, n_ext);
-    const uint32_t t = __reduce_add_sync(GCA_FULL, n_thresh);
-    if (lane == 0) {
-      atomicAdd(&O.stats[0], (unsigned long long)a);
-      atomicAdd(&O.stats[1], (unsigned long long)b);
-      atomicAdd(&O.stats[2], (unsigned long long)c);
-      atomicAdd(&O.stats[3], (unsigned long long)d);
-      if (t) atomicAdd(&O.stats[4], (unsigned long long)t);
-      atomicAdd(&O.stats[5], 1ull);
-    }
-  }
-
-  // ---- per-env scalars: clock, move, douse, day/night, reward, done (key / wind were stored above) --
-  const bool ca_only = (flags & GCA_FLAG_CA_ONLY) != 0;
-  const bool done = fcount == 0;
-  if (!ca_only) {
-    asm volatile("cp.async.wait_all;" ::: "memory");   // the action words (lanes 0..2 copied them)
-    __syncwarp();
-  }
-  uint32_t rinfo = 0;  // observation inputs (lane 0): row | col << 8 | night << 16 | "add this step's dousing mark" << 17
-  if (lane == 0) {
-#ifdef S64_TRACE
-    if (O.stats) {
-      O.stats[8 + 32 * (size_t)e + 20] = work;
-      O.stats[8 + 32 * (size_t)e + 21] = 0;
-      O.stats[8 + 32 * (size_t)e + 22] = (unsigned long long)trace_rows;
-      O.stats[8 + 32 * (size_t)e + 23] = (unsigned long long)(clock64() - clk0);
-      uint32_t smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      unsigned long long gt;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-      O.stats[8 + 32 * (size_t)e + 24] = smid;
-      O.stats[8 + 32 * (size_t)e + 25] = gt;                       // end time, ns
-      O.stats[8 + 32 * (size_t)e + 26] = (unsigned long long)blockIdx.x;
-    }
-#endif
-    if (S.work != nullptr)
-      S.work[e] = (flags & GCA_FLAG_WORK_CYCLES) ? (uint32_t)(clock64() - clk0) : work;
-    S.tick[e] = tick0 + (uint32_t)K;
-    const float rew = award(tcount, fcount);
-    if (!ca_only) {
-      // all loads first (they may alias the stores below as far as the compiler knows)
-      const int a0 = __float_as_int(sm.wind[9]), a1 = __float_as_int(sm.wind[10]);
-      const float t_old = S.time[e];
-      int row = S.position[2 * e], col = S.position[2 * e + 1];
-      const int ts = S.time_step[e] + 1;
-      int night = S.is_night[e];
-      const float se = S.steps_elapsed ? S.steps_elapsed[e] : 0.0f;
-      const float ra = S.reward_accumulated ? S.reward_accumulated[e] : 0.0f;
-      const int a0c = min(max(a0, 0), 8), a1c = min(max(a1, 0), 1);
-      // clock (repeat_ca_jax.py:35-41): new = time + ((t_move + t_shoot) + t_any); keep the fraction
-      const float tt = __fadd_rn(__fadd_rn(P.t_move[a0c], P.t_shoot[a1c]), P.t_any);
-      const float nt = __fadd_rn(t_old, tt);
-      move_position(a0, 64, 64, row, col);
-      unsigned long long drow = 0ull;
-      if (a1 == 1) drow = S.doused[(size_t)e * 64 + row];
-      S.time[e] = __fsub_rn(nt, truncf(nt));
-      S.position[2 * e] = row;
-      S.position[2 * e + 1] = col;
-      if (a1 == 1) S.doused[(size_t)e * 64 + row] = drow | (1ull << col);
-      S.time_step[e] = ts;
-      if (O.obs_night) O.obs_night[e] = (uint8_t)night;
-      // the observation shows the NEW position with the PRE-step dousing marks and day/night (advanced_bulldozer.py:1120-1122)
-      rinfo = (uint32_t)row | ((uint32_t)col << 8) | ((uint32_t)night << 16);
-      if (ts % P.day_length == 0) night = 1 - night;
-      if ((flags & GCA_FLAG_AUTO_RESET) && done)
-        // ... unless the env resets now: conditional_reset redraws it from the restored grid and position with the
-        // POST-step marks and day/night (:462-487); the mark of this step sits at the position just moved to
-        rinfo = (uint32_t)row | ((uint32_t)col << 8) | ((uint32_t)night << 16) | (a1 == 1 ? 1u << 17 : 0u);
-      S.is_night[e] = night;
-      if (S.steps_elapsed) S.steps_elapsed[e] = __fadd_rn(se, 1.0f);
-      if (S.reward_accumulated) S.reward_accumulated[e] = __fadd_rn(ra, rew);
-    }
-    if (O.step_reward) O.step_reward[e] = rew;
-    if (O.terminated) O.terminated[e] = done ? 1 : 0;
-    if (O.host_terminated && !O.host_done) O.host_terminated[e] = done ? 1 : 0;
-    if (O.counts) { O.counts[2 * e] = tcount; O.counts[2 * e + 1] = fcount; }
-    if (!((flags & GCA_FLAG_AUTO_RESET) && done)) {
-      if (O.reward) O.reward[e] = rew;
-      if (O.host_reward && !O.host_done) O.host_reward[e] = rew;
-    }
-  }
-
-  // ---- observation, fused (GCA_FLAG_RENDER): MDP.grid_to_rgb (advanced_bulldozer.py:1035-1101) from the bit-boards --
-  if ((flags & GCA_FLAG_RENDER) && O.rgb != nullptr) {
-    rinfo = __shfl_sync(GCA_FULL, rinfo, 0);
-    int prow = (int)(rinfo & 255u), pcol = (int)((rinfo >> 8) & 255u);
-    const uint32_t night_obs = (rinfo >> 16) & 1u;
-    unsigned long long rt0 = t0, rt1 = t1, rf0 = f0, rf1 = f1;
-    const bool resets = (flags & GCA_FLAG_AUTO_RESET) && done;
-    if (resets) {
-      // this env resets now: the frame shows the restored grid and position (post-step marks and day/night)
-      const ulonglong2* sb = reinterpret_cast<const ulonglong2*>(SNAP.bb + (size_t)e * 128);
-      const ulonglong2 r0 = sb[2 * lane], r1 = sb[2 * lane + 1];
-      rt0 = r0.x; rf0 = r0.y; rt1 = r1.x; rf1 = r1.y;
-      if (lane == 0 && (rinfo & (1u << 17))) sm.dous64[2 + prow] |= 1ull << pcol;  // this step's mark (pre-restore position)
-      prow = SNAP.position[2 * e];
-      pcol = SNAP.position[2 * e + 1];
-      __syncwarp();
-    }
-#ifdef S64_EARLY_RENDER
-    if (!resets) {  // the prologue drew the frame from the grid the step started with: redraw the cells that changed
-      if (O.rgb_u8) render_patch64<true>(sm, wp32, O.rgb, e, t0, t1, f0, f1, ch0, ch1, prow, pcol, night_obs, lane);
-      else render_patch64<false>(sm, wp32, O.rgb, e, t0, t1, f0, f1, ch0, ch1, prow, pcol, night_obs, lane);
-    } else
-#endif
-    {
-      if (O.rgb_u8) render_env64<true>(sm, wp32, O.rgb, e, rt0, rt1, rf0, rf1, prow, pcol, night_obs, lane);
-      else render_env64<false>(sm, wp32, O.rgb, e, rt0, rt1, rf0, rf1, prow, pcol, night_obs, lane);
-    }
-  }
-
-  // ---- fused conditional_reset (advanced_bulldozer.py:422-518) ------------------------------------
-  if ((flags & GCA_FLAG_AUTO_RESET) && done) {
-    __syncwarp();
-    const uint4* sc4 = reinterpret_cast<const uint4*>(SNAP.cell + cell_base);
-    uint4* dc4 = reinterpret_cast<uint4*>(S.cell + cell_base);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dc4[i * 32 + lane] = sc4[i * 32 + lane];
-    const uint4* sd4 = reinterpret_cast<const uint4*>(SNAP.death + cell_base);
-    uint4* dd4 = reinterpret_cast<uint4*>(S.death + cell_base);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) dd4[i * 32 + lane] = sd4[i * 32 + lane];
-    reinterpret_cast<ulonglong2*>(S.doused + (size_t)e * 64)[lane] =
-        reinterpret_cast<const ulonglong2*>(SNAP.doused + (size_t)e * 64)[lane];
-    reinterpret_cast<uint2*>(S.row_min + (size_t)e * 64)[lane] =
-        reinterpret_cast<const uint2*>(SNAP.row_min + (size_t)e * 64)[lane];
-    {
-      const ulonglong2* sb = reinterpret_cast<const ulonglong2*>(SNAP.bb + (size_t)e * 128);
-      ulonglong2* db = reinterpret_cast<ulonglong2*>(S.bb + (size_t)e * 128);
-      db[2 * lane] = sb[2 * lane];
-      db[2 * lane + 1] = sb[2 * lane + 1];
-    }
-    if (lane == 0) {
-      S.key[2 * e] = SNAP.key[2 * e];
-      S.key[2 * e + 1] = SNAP.key[2 * e + 1];
-      S.wind_index[e] = SNAP.wind_index[e];
-      S.position[2 * e] = SNAP.position[2 * e];
-      S.position[2 * e + 1] = SNAP.position[2 * e + 1];
-      S.time[e] = SNAP.time[e];
-      S.tick[e] = SNAP.tick[e];
-      if (S.steps_elapsed) S.steps_elapsed[e] = 0.0f;
-      if (S.reward_accumulated) S.reward_accumulated[e] = 0.0f;
-      const float sr = snap_reward[e];
-      if (O.reward) O.reward[e] = sr;
-      if (O.host_reward && !O.host_done) O.host_reward[e] = sr;
-    }
-  }
-  // ---- completion word (gca_env_step_host): the warp whose env ends last copies the step's results -- reward and
-  //      terminated of ALL envs, from the device outputs -- to the mapped host mirrors in one burst, fences once at
-  //      system scope and stores the token the host polls.  (Every env storing its own 5 bytes to host memory and
-  //      fencing at system scope costs a PCIe round trip per warp on the kernel's tail.)
-  if (O.host_done != nullptr) {
-    uint32_t last = 0;
-    if (lane == 0) {
-      __threadfence();  // release: this env's device outputs
-      last = atomicAdd(O.done_counter, 1u) == (uint32_t)N - 1u ? 1u : 0u;
-    }
-    last = __shfl_sync(GCA_FULL, last, 0);
-    if (last) {
-      __threadfence();  // acquire: the other envs' device outputs
-      if (O.host_reward != nullptr && O.reward != nullptr)
-        burst_copy_u32(reinterpret_cast<uint32_t*>(O.host_reward), reinterpret_cast<const uint32_t*>(O.reward), N, lane);
-      if (O.host_terminated != nullptr && O.terminated != nullptr) {
-        if ((N & 3) == 0 && ((reinterpret_cast<uintptr_t>(O.host_terminated) | reinterpret_cast<uintptr_t>(O.terminated)) & 3) == 0)
-          burst_copy_u32(reinterpret_cast<uint32_t*>(O.host_terminated), reinterpret_cast<const uint32_t*>(O.terminated), N / 4, lane);
-        else
-          for (int i = lane; i < N; i += 32) O.host_terminated[i] = __ldcg(O.terminated + i);
-      }
-      __threadfence_system();
-      __syncwarp();
-      if (lane == 0) {
-        *O.done_counter = 0u;
-        *reinterpret_cast<volatile uint32_t*>(O.host_done) = O.done_token;
-      }
-    }
-  }
-  };
-
-#ifdef S64_ASYNC
-
-  // ================================ K CA sub-steps, all on-chip: ASYNCHRONOUS ======================
-  // No lock step: every owner walks its env's sub-steps at its own pace.  It publishes the work items of a sub-step
-  // (32-entry chunks of its front list, burn-out scan rounds) with a phase-tagged ticket counter and a bit in
-  // cs.avail, and waits for them on its env's mbarrier, whose transaction count holds "items + buffered draws still
-  // outstanding" (owner: arrive.expect_tx(items); a chunk: expect_tx(its pairs) then complete_tx(1); a draw round:
-  // complete_tx(pairs of that env)).  While it waits -- and after its env is finished, until every env of the CTA is --
-  // a warp takes items of ANY env.  A warp never sits on buffered draws: it draws a partial round before it waits, and
-  // before it returns to its own env's serial phase.
-  {
-    const int n_active = min(S64_E, N - (int)blockIdx.x * S64_E);
-    uint32_t own_parity = 0u;      // parity of the mbarrier phase this owner waits for next
-    int own_phase = 0;             // publish counter: tags the tickets of a phase
-    bool own_done = !active, waiting = false;
-    int j = 0, pass = 0, total = 0;
-    for (;;) {
-      if (!own_done && !waiting) {
-        if (pass == 0) {
-      const uint32_t* sc = sm.sched[j];
-      if (j > 0) {
-        unsigned long long fr0, fr1;
-        front_masks(t0, t1, f0, f1, lane, fr0, fr1);
-        n_front += (uint32_t)(__popcll(fr0) + __popcll(fr1));
-        if (!dense) {
-          const unsigned long long listed0 = sm.listed[2 * lane], listed1 = sm.listed[2 * lane + 1];
-          const unsigned long long nw0 = fr0 & ~listed0, nw1 = fr1 & ~listed1;
-          const int nn = __popcll(nw0) + __popcll(nw1);
-          const int incl_n = warp_incl_scan(nn, lane);
-          const int tot_n = __shfl_sync(GCA_FULL, incl_n, 31);
-          if (L + tot_n > S64_CAP) {
-            dense = true;
-          } else if (tot_n > 0) {
-            int idx = L + incl_n - nn;
-            unsigned long long m = nw0;
-            int rowbits = (2 * lane) << 6;
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-              while (m) {
-                const uint32_t cell = (uint32_t)(rowbits | (__ffsll((long long)m) - 1));
-                m &= m - 1;
-                sm.list[idx++] = (uint16_t)cell;
-                if (hidden != nullptr) {
-                  prefetch_l1(hidden + cell_base + cell);
-                  if (pslope != nullptr) prefetch_l1(pslope + (cell_base + cell) * 8);
-                }
-              }
-              m = nw1;
-              rowbits = (2 * lane + 1) << 6;
-            }
-            L += tot_n;
-            if (nn) {
-              sm.listed[2 * lane] = listed0 | nw0;
-              sm.listed[2 * lane + 1] = listed1 | nw1;
-            }
-          }
-        }
-        if (dense) {
-          T = build_front_list(sm, wp, fr0, fr1, lane, 0);
-          prefetch_front(sm, hidden, pslope, cell_base, 0, min(T, S64_CAP), lane);
-        }
-      }
-      if (j > 0) S64_ACC(29);
-      if (lane == 0) sm.hot = make_uint4(sc[0], sc[1], sc[0] ^ sc[1] ^ 0x1BD11BDAu, (uint32_t)e);
-      if (lane < 9) sm.wind[lane] = P.winds[(int)sc[8] * 9 + lane];
-
-          total = dense ? T : L;
-          work += (uint32_t)total;
-        } else {  // dense fires only: next slice of the list
-          unsigned long long fr0, fr1;
-          front_masks(t0, t1, f0, f1, lane, fr0, fr1);
-          build_front_list(sm, wp, fr0, fr1, lane, pass * S64_CAP);
-          prefetch_front(sm, hidden, pslope, cell_base, 0, min(S64_CAP, total - pass * S64_CAP), lane);
-        }
-        const int cnt = max(0, min(S64_CAP, total - pass * S64_CAP));
-        const int nch_own = (cnt + 31) >> 5;
-        const int nitems = nch_own + ((j == 0 && pass == 0) ? (sm.nscan + 3) >> 2 : 0);
-        if (nitems > 0) {
-          ++own_phase;
-          __syncwarp();
-          if (lane == 0) {
-            sm.cnt = cnt;
-            sm.q_nch = nch_own;
-            sm.q_j = j;
-            sm.q_total = ((own_phase & 0xFFF) << S64_QSHIFT) | nitems;
-            mbar_arrive_expect_tx(&sm.mbar, (uint32_t)nitems);
-            __threadfence_block();   // list, hot, wind, counts, the barrier's pending count: before the tickets open
-            atomicOr(&cs.avail, 1u << warp);   // (set BEFORE the tickets open: the holder of the last ticket clears it)
-            __threadfence_block();
-            *reinterpret_cast<volatile int*>(&sm.q_taken) = (own_phase & 0xFFF) << S64_QSHIFT;
-          }
-          __syncwarp();
-          waiting = true;
-        }
-      }
-      if (waiting || own_done) {
-        s64_work_loop<MODE, HP, INJ>(cs, P, S, J, warp, lane, waiting, own_parity, n_active, N);
-        if (own_done) break;
-        waiting = false;
-        own_parity ^= 1u;
-      }
-      if (total > (pass + 1) * S64_CAP) { ++pass; continue; }
-      // ---- apply: ignitions (with their fire-age draws), burn-outs, regrowth ------------------------
-      {
-      const uint32_t* sc = sm.sched[j];
-      const size_t inj_base = ((size_t)j * N + e) * 4096;
-      const unsigned long long I0 = sm.ign[2 * lane], I1 = sm.ign[2 * lane + 1];
-      const int ni_l = __popcll(I0) + __popcll(I1);
-      const int incl_i = warp_incl_scan(ni_l, lane);
-      const int NI = __shfl_sync(GCA_FULL, incl_i, 31);
-      if (NI > 0) {
-        sm.ign[2 * lane] = 0ull;
-        sm.ign[2 * lane + 1] = 0ull;
-        // remember the ignited cells with their sub-step; the age draws are deferred to flush_ages
-        int nign = sm.nign;
-        int taken = 0;
-        while (taken < NI) {
-          const int take = min(S64_IGN_CAP - nign, NI - taken);
-          int pos = nign + incl_i - ni_l - taken;  // list position of this lane's first ignition
-          unsigned long long m = I0;
-          uint32_t tag = ((uint32_t)j << 12) | ((uint32_t)(2 * lane) << 6);
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
-            while (m) {
-              const uint32_t c = (uint32_t)__ffsll((long long)m) - 1u;
-              m &= m - 1;
-              if (pos >= nign && pos < nign + take) sm.ignlist[pos] = (uint16_t)(tag | c);
-              ++pos;
-            }
-            m = I1;
-            tag += 64u;
-          }
-          nign += take;
-          taken += take;
-          if (taken < NI) {  // the list is full (hundreds of ignitions in one env step): draw what it holds
-            __syncwarp();
-            flush_ages(sm, P, S, j_age_new, mode, N, e, nign, tick0, reinterpret_cast<uint32_t*>(wp), lane);
-            rm.x = min(rm.x, reinterpret_cast<const uint32_t*>(wp)[2 * lane]);
-            rm.y = min(rm.y, reinterpret_cast<const uint32_t*>(wp)[2 * lane + 1]);
-            __syncwarp();
-            nign = 0;
-          }
-        }
-        __syncwarp();
-        if (lane == 0) sm.nign = nign;
-      }
-      S64_ACC(27);
-      if (j == 0) {  // the scan rounds of the pooled phase left the scanned rows' new minima in S.row_min
-        if (burnrows & 1u) rm.x = __ldcg(S.row_min + (size_t)e * 64 + 2 * lane);
-        if (burnrows & 2u) rm.y = __ldcg(S.row_min + (size_t)e * 64 + 2 * lane + 1);
-      }
-      unsigned long long ext0 = 0ull, ext1 = 0ull;
-      if (burnrows & 1u) {
-        const ulonglong2 a = reinterpret_cast<const ulonglong2*>(sm.burn[2 * lane])[0];
-        const ulonglong2 b = reinterpret_cast<const ulonglong2*>(sm.burn[2 * lane])[1];
-        ext0 = a.x & ((j & 1) ? a.y : ~a.y) & ((j & 2) ? b.x : ~b.x) & ((j & 4) ? b.y : ~b.y);
-      }
-      if (burnrows & 2u) {
-        const ulonglong2 a = reinterpret_cast<const ulonglong2*>(sm.burn[2 * lane + 1])[0];
-        const ulonglong2 b = reinterpret_cast<const ulonglong2*>(sm.burn[2 * lane + 1])[1];
-        ext1 = a.x & ((j & 1) ? a.y : ~a.y) & ((j & 2) ? b.x : ~b.x) & ((j & 4) ? b.y : ~b.y);
-      }
-      unsigned long long g0 = 0, g1 = 0;
-      if (P.p_tree > 0.0f) regrow_rows(P, J, tf_key(sc[2], sc[3]), inj_base, lane, ~(t0 | f0), ~(t1 | f1), g0, g1);
-      n_ign += ni_l;
-      n_ext += __popcll(ext0) + __popcll(ext1);
-      ch0 |= I0 | ext0 | g0;
-      ch1 |= I1 | ext1 | g1;
-      t0 = (t0 & ~I0) | g0;
-      t1 = (t1 & ~I1) | g1;
-      f0 = (f0 & ~ext0) | I0;
-      f1 = (f1 & ~ext1) | I1;
-      if (j + 1 < K) {
-        store_row_views(sm.fire32 + (2 * lane + 4) * 4, f0);
-        store_row_views(sm.fire32 + (2 * lane + 5) * 4, f1);
-      }
-
-        __syncwarp();
-      }
-      pass = 0;
-      if (++j == K) {
-        if (sm.nign > 0) {
-          __syncwarp();
-          flush_ages(sm, P, S, j_age_new, mode, N, e, sm.nign, tick0, reinterpret_cast<uint32_t*>(wp), lane);
-          rm.x = min(rm.x, reinterpret_cast<const uint32_t*>(wp)[2 * lane]);
-          rm.y = min(rm.y, reinterpret_cast<const uint32_t*>(wp)[2 * lane + 1]);
-        }
-        epilogue();
-        own_done = true;
-        __syncwarp();
-        if (lane == 0) atomicAdd(&cs.finished, 1);
-      }
-    }
-    if (O.stats != nullptr && lane == 0) {   // draws / threshold cells this warp worked on (of any env)
-      if (cs.wstat[warp][0]) atomicAdd(&O.stats[1], (unsigned long long)cs.wstat[warp][0]);
-      if (cs.wstat[warp][1]) atomicAdd(&O.stats[4], (unsigned long long)cs.wstat[warp][1]);
-    }
-  }
-#else
   // ================================ K CA sub-steps, all on-chip ===================================
   for (int j = 0; j < K; ++j) {
     if (active) {
@@ -1714,12 +1032,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
 
       // ---------------- pooled phase: work items = 32-entry chunks of every env's front list -------
       {
-#ifdef S64_FAIR
-        const int my_slot = lane < S64_GE ? (int)cs.member[group][lane] : 0;  // env slot of the group's lane-th member
-#else
-        const int my_slot = group * S64_GE + lane;  // blocked groups: members are consecutive warps
-#endif
-        const int my_pk = lane < S64_GE ? cs.nch[my_slot] : 0;
+        const int my_pk = lane < S64_GE ? cs.nch[group * S64_GE + lane] : 0;
         const int my_nc = my_pk & 0xFFFF;              // cell chunks of env slot `lane`
         const int my_n = my_nc + (my_pk >> 16);        // + its scan rounds
         int incl = my_n;
@@ -1752,11 +1065,7 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
 #endif
             const int gslot = __popc(__ballot_sync(GCA_FULL, lane < S64_GE && incl <= item));
             const int chunk = item - __shfl_sync(GCA_FULL, incl - my_n, gslot);
-#ifdef S64_FAIR
-            const int es_slot = __shfl_sync(GCA_FULL, my_slot, gslot);
-#else
             const int es_slot = group * S64_GE + gslot;
-#endif
             EnvSmem& es = cs.env[es_slot];
             const int nc_env = __shfl_sync(GCA_FULL, my_nc, gslot);
             if (chunk >= nc_env) {
@@ -1968,8 +1277,216 @@ env_step64_kernel(const __grid_constant__ gca_params P, const __grid_constant__ 
     return;
   }
 
-  epilogue();
+#ifdef S64_TRACE
+  const uint32_t trace_rows = __reduce_add_sync(GCA_FULL, __popc(burnrows));  // rows scanned for burn-outs
 #endif
+  // ---- sparse in-place write-back of the cells that changed --------------------------------------
+  {
+    unsigned long long ch = ch0;
+    unsigned long long tt = t0, ff = f0;
+    int row = 2 * lane;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      while (ch) {
+        const int c = __ffsll((long long)ch) - 1;
+        ch &= ch - 1;
+        const uint8_t code = ((ff >> c) & 1ull) ? 2 : (((tt >> c) & 1ull) ? 1 : 0);
+        S.cell[cell_base + row * 64 + c] = code;
+      }
+      ch = ch1;
+      tt = t1; ff = f1;
+      row = 2 * lane + 1;
+    }
+  }
+  {
+    // the bit-board copy of the grid: rows that changed
+    ulonglong2* bbp = reinterpret_cast<ulonglong2*>(S.bb + (size_t)e * 128);
+    if (ch0) bbp[2 * lane] = make_ulonglong2(t0, f0);
+    if (ch1) bbp[2 * lane + 1] = make_ulonglong2(t1, f1);
+  }
+  reinterpret_cast<uint2*>(S.row_min + (size_t)e * 64)[lane] = rm;
+  const int tcount = __reduce_add_sync(GCA_FULL, __popcll(t0) + __popcll(t1));
+  const int fcount = __reduce_add_sync(GCA_FULL, __popcll(f0) + __popcll(f1));
+
+  if (O.stats != nullptr) {
+    const uint32_t a = __reduce_add_sync(GCA_FULL, n_front), b = __reduce_add_sync(GCA_FULL, n_draws);
+    const uint32_t c = __reduce_add_sync(GCA_FULL, n_ign), d = __reduce_add_sync(GCA_FULL, n_ext);
+    const uint32_t t = __reduce_add_sync(GCA_FULL, n_thresh);
+    if (lane == 0) {
+      atomicAdd(&O.stats[0], (unsigned long long)a);
+      atomicAdd(&O.stats[1], (unsigned long long)b);
+      atomicAdd(&O.stats[2], (unsigned long long)c);
+      atomicAdd(&O.stats[3], (unsigned long long)d);
+      if (t) atomicAdd(&O.stats[4], (unsigned long long)t);
+      atomicAdd(&O.stats[5], 1ull);
+    }
+  }
+
+  // ---- per-env scalars: clock, move, douse, day/night, reward, done (key / wind were stored above) --
+  const bool ca_only = (flags & GCA_FLAG_CA_ONLY) != 0;
+  const bool done = fcount == 0;
+  if (!ca_only) {
+    asm volatile("cp.async.wait_all;" ::: "memory");   // the action words (lanes 0..2 copied them)
+    __syncwarp();
+  }
+  uint32_t rinfo = 0;  // observation inputs (lane 0): row | col << 8 | night << 16 | "add this step's dousing mark" << 17
+  if (lane == 0) {
+#ifdef S64_TRACE
+    if (O.stats) {
+      O.stats[8 + 32 * (size_t)e + 20] = work;
+      O.stats[8 + 32 * (size_t)e + 21] = 0;
+      O.stats[8 + 32 * (size_t)e + 22] = (unsigned long long)trace_rows;
+      O.stats[8 + 32 * (size_t)e + 23] = (unsigned long long)(clock64() - clk0);
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      O.stats[8 + 32 * (size_t)e + 24] = smid;
+      O.stats[8 + 32 * (size_t)e + 25] = gt;                       // end time, ns
+      O.stats[8 + 32 * (size_t)e + 26] = (unsigned long long)blockIdx.x;
+    }
+#endif
+    if (S.work != nullptr)
+      S.work[e] = (flags & GCA_FLAG_WORK_CYCLES) ? (uint32_t)(clock64() - clk0) : work;
+    S.tick[e] = tick0 + (uint32_t)K;
+    const float rew = award(tcount, fcount);
+    if (!ca_only) {
+      // all loads first (they may alias the stores below as far as the compiler knows)
+      const int a0 = __float_as_int(sm.wind[9]), a1 = __float_as_int(sm.wind[10]);
+      const float t_old = S.time[e];
+      int row = S.position[2 * e], col = S.position[2 * e + 1];
+      const int ts = S.time_step[e] + 1;
+      int night = S.is_night[e];
+      const float se = S.steps_elapsed ? S.steps_elapsed[e] : 0.0f;
+      const float ra = S.reward_accumulated ? S.reward_accumulated[e] : 0.0f;
+      const int a0c = min(max(a0, 0), 8), a1c = min(max(a1, 0), 1);
+      // clock (repeat_ca_jax.py:35-41): new = time + ((t_move + t_shoot) + t_any); keep the fraction
+      const float tt = __fadd_rn(__fadd_rn(P.t_move[a0c], P.t_shoot[a1c]), P.t_any);
+      const float nt = __fadd_rn(t_old, tt);
+      move_position(a0, 64, 64, row, col);
+      unsigned long long drow = 0ull;
+      if (a1 == 1) drow = S.doused[(size_t)e * 64 + row];
+      S.time[e] = __fsub_rn(nt, truncf(nt));
+      S.position[2 * e] = row;
+      S.position[2 * e + 1] = col;
+      if (a1 == 1) S.doused[(size_t)e * 64 + row] = drow | (1ull << col);
+      S.time_step[e] = ts;
+      if (O.obs_night) O.obs_night[e] = (uint8_t)night;
+      // the observation shows the NEW position with the PRE-step dousing marks and day/night (advanced_bulldozer.py:1120-1122)
+      rinfo = (uint32_t)row | ((uint32_t)col << 8) | ((uint32_t)night << 16);
+      if (ts % P.day_length == 0) night = 1 - night;
+      if ((flags & GCA_FLAG_AUTO_RESET) && done)
+        // ... unless the env resets now: conditional_reset redraws it from the restored grid and position with the
+        // POST-step marks and day/night (:462-487); the mark of this step sits at the position just moved to
+        rinfo = (uint32_t)row | ((uint32_t)col << 8) | ((uint32_t)night << 16) | (a1 == 1 ? 1u << 17 : 0u);
+      S.is_night[e] = night;
+      if (S.steps_elapsed) S.steps_elapsed[e] = __fadd_rn(se, 1.0f);
+      if (S.reward_accumulated) S.reward_accumulated[e] = __fadd_rn(ra, rew);
+    }
+    if (O.step_reward) O.step_reward[e] = rew;
+    if (O.terminated) O.terminated[e] = done ? 1 : 0;
+    if (O.host_terminated && !O.host_done) O.host_terminated[e] = done ? 1 : 0;
+    if (O.counts) { O.counts[2 * e] = tcount; O.counts[2 * e + 1] = fcount; }
+    if (!((flags & GCA_FLAG_AUTO_RESET) && done)) {
+      if (O.reward) O.reward[e] = rew;
+      if (O.host_reward && !O.host_done) O.host_reward[e] = rew;
+    }
+  }
+
+  // ---- observation, fused (GCA_FLAG_RENDER): MDP.grid_to_rgb (advanced_bulldozer.py:1035-1101) from the bit-boards --
+  if ((flags & GCA_FLAG_RENDER) && O.rgb != nullptr) {
+    rinfo = __shfl_sync(GCA_FULL, rinfo, 0);
+    int prow = (int)(rinfo & 255u), pcol = (int)((rinfo >> 8) & 255u);
+    const uint32_t night_obs = (rinfo >> 16) & 1u;
+    unsigned long long rt0 = t0, rt1 = t1, rf0 = f0, rf1 = f1;
+    const bool resets = (flags & GCA_FLAG_AUTO_RESET) && done;
+    if (resets) {
+      // this env resets now: the frame shows the restored grid and position (post-step marks and day/night)
+      const ulonglong2* sb = reinterpret_cast<const ulonglong2*>(SNAP.bb + (size_t)e * 128);
+      const ulonglong2 r0 = sb[2 * lane], r1 = sb[2 * lane + 1];
+      rt0 = r0.x; rf0 = r0.y; rt1 = r1.x; rf1 = r1.y;
+      if (lane == 0 && (rinfo & (1u << 17))) sm.dous64[2 + prow] |= 1ull << pcol;  // this step's mark (pre-restore position)
+      prow = SNAP.position[2 * e];
+      pcol = SNAP.position[2 * e + 1];
+      __syncwarp();
+    }
+#ifdef S64_EARLY_RENDER
+    if (!resets) {  // the prologue drew the frame from the grid the step started with: redraw the cells that changed
+      if (O.rgb_u8) render_patch64<true>(sm, wp32, O.rgb, e, t0, t1, f0, f1, ch0, ch1, prow, pcol, night_obs, lane);
+      else render_patch64<false>(sm, wp32, O.rgb, e, t0, t1, f0, f1, ch0, ch1, prow, pcol, night_obs, lane);
+    } else
+#endif
+    {
+      if (O.rgb_u8) render_env64<true>(sm, wp32, O.rgb, e, rt0, rt1, rf0, rf1, prow, pcol, night_obs, lane);
+      else render_env64<false>(sm, wp32, O.rgb, e, rt0, rt1, rf0, rf1, prow, pcol, night_obs, lane);
+    }
+  }
+
+  // ---- fused conditional_reset (advanced_bulldozer.py:422-518) ------------------------------------
+  if ((flags & GCA_FLAG_AUTO_RESET) && done) {
+    __syncwarp();
+    const uint4* sc4 = reinterpret_cast<const uint4*>(SNAP.cell + cell_base);
+    uint4* dc4 = reinterpret_cast<uint4*>(S.cell + cell_base);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dc4[i * 32 + lane] = sc4[i * 32 + lane];
+    const uint4* sd4 = reinterpret_cast<const uint4*>(SNAP.death + cell_base);
+    uint4* dd4 = reinterpret_cast<uint4*>(S.death + cell_base);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dd4[i * 32 + lane] = sd4[i * 32 + lane];
+    reinterpret_cast<ulonglong2*>(S.doused + (size_t)e * 64)[lane] =
+        reinterpret_cast<const ulonglong2*>(SNAP.doused + (size_t)e * 64)[lane];
+    reinterpret_cast<uint2*>(S.row_min + (size_t)e * 64)[lane] =
+        reinterpret_cast<const uint2*>(SNAP.row_min + (size_t)e * 64)[lane];
+    {
+      const ulonglong2* sb = reinterpret_cast<const ulonglong2*>(SNAP.bb + (size_t)e * 128);
+      ulonglong2* db = reinterpret_cast<ulonglong2*>(S.bb + (size_t)e * 128);
+      db[2 * lane] = sb[2 * lane];
+      db[2 * lane + 1] = sb[2 * lane + 1];
+    }
+    if (lane == 0) {
+      S.key[2 * e] = SNAP.key[2 * e];
+      S.key[2 * e + 1] = SNAP.key[2 * e + 1];
+      S.wind_index[e] = SNAP.wind_index[e];
+      S.position[2 * e] = SNAP.position[2 * e];
+      S.position[2 * e + 1] = SNAP.position[2 * e + 1];
+      S.time[e] = SNAP.time[e];
+      S.tick[e] = SNAP.tick[e];
+      if (S.steps_elapsed) S.steps_elapsed[e] = 0.0f;
+      if (S.reward_accumulated) S.reward_accumulated[e] = 0.0f;
+      const float sr = snap_reward[e];
+      if (O.reward) O.reward[e] = sr;
+      if (O.host_reward && !O.host_done) O.host_reward[e] = sr;
+    }
+  }
+  // ---- completion word (gca_env_step_host): the warp whose env ends last copies the step's results -- reward and
+  //      terminated of ALL envs, from the device outputs -- to the mapped host mirrors in one burst, fences once at
+  //      system scope and stores the token the host polls.  (Every env storing its own 5 bytes to host memory and
+  //      fencing at system scope costs a PCIe round trip per warp on the kernel's tail.)
+  if (O.host_done != nullptr) {
+    uint32_t last = 0;
+    if (lane == 0) {
+      __threadfence();  // release: this env's device outputs
+      last = atomicAdd(O.done_counter, 1u) == (uint32_t)N - 1u ? 1u : 0u;
+    }
+    last = __shfl_sync(GCA_FULL, last, 0);
+    if (last) {
+      __threadfence();  // acquire: the other envs' device outputs
+      if (O.host_reward != nullptr && O.reward != nullptr)
+        burst_copy_u32(reinterpret_cast<uint32_t*>(O.host_reward), reinterpret_cast<const uint32_t*>(O.reward), N, lane);
+      if (O.host_terminated != nullptr && O.terminated != nullptr) {
+        if ((N & 3) == 0 && ((reinterpret_cast<uintptr_t>(O.host_terminated) | reinterpret_cast<uintptr_t>(O.terminated)) & 3) == 0)
+          burst_copy_u32(reinterpret_cast<uint32_t*>(O.host_terminated), reinterpret_cast<const uint32_t*>(O.terminated), N / 4, lane);
+        else
+          for (int i = lane; i < N; i += 32) O.host_terminated[i] = __ldcg(O.terminated + i);
+      }
+      __threadfence_system();
+      __syncwarp();
+      if (lane == 0) {
+        *O.done_counter = 0u;
+        *reinterpret_cast<volatile uint32_t*>(O.host_done) = O.done_token;
+      }
+    }
+  }
 }
 
 template <int MODE, int HP, bool INJ>
