@@ -614,7 +614,7 @@ def run_ours(args):
                 other_config_line(torch, dev, peak, flush, 256, 1024, False, 4, 24, 40,
                                   "BASELINE config 3: 1024 envs of 256x256 (R = 6), hidden layers off"),
                 other_config_line(torch, dev, peak, flush, 4096, 1, True, 4, 16, 24,
-                                  "BASELINE config 4: one 4096x4096 grid (R = 10); generic tiled kernels (TMA-staged tiles, only tiles near fire are worked on), one CUDA graph launch per env step"),
+                                  "BASELINE config 4: one 4096x4096 grid (R = 10); generic tiled kernels (active-tile lists, TMA-staged bit-row tiles), one CUDA graph launch per env step"),
                 other_config_line(torch, dev, peak, flush, 64, 4096, True, 1, 24, 200,
                                   "config 2 at K = 1: ONE CA update per env step, the reference's own RepeatCAJax semantics (repeat_ca_jax.py:61-63)"),
                 v3_line(256, 1024, 64, 16)]
