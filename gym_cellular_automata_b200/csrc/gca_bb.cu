@@ -24,12 +24,14 @@ namespace {
 constexpr int BB_THREADS = 256;
 constexpr int BB_LIST_CAP = 4096;  // front cells the balanced list holds; larger fronts are walked word by word
 constexpr int BB_BURN_CAP = 1024;  // burn-outs of one env step the burn list holds (beyond: per-sub-step scans)
+constexpr int BB_PAIR_CAP = BB_THREADS * 8;  // (front cell, burning direction) draws of one round of BB_THREADS front cells
 #define BB_LO 0.9998779296875f     /* 1 - 2^-13: (2R+1)^2 <= 441 terms -> |err| <= 441 u |sum| */
 #define BB_HI 1.0001220703125f     /* 1 + 2^-13 */
 
 struct BbScalars {
   uint32_t sched[GCA_MAX_K][12];  // per sub-step: Sburn[2] Sgrow[2] ak1[2] ak2[2] wind change step pad
   int nfront;
+  int npairs[2];                  // draws listed in the current round of front cells (double-buffered by round parity)
   int nburn;                      // entries on the burn list (> BB_BURN_CAP: overflow, the list is not used)
   int cnt_tree, cnt_fire;
   unsigned int n_draws, n_ign, n_ext, n_thresh, n_front;
@@ -153,20 +155,22 @@ struct BbView {
   unsigned long long *tree, *fire, *dous, *ign;
   uint16_t* list;
   uint32_t* burn;   // cells that burn out during this env step: (row << 8 | col) << 3 | sub-step
+  float2* bnd;      // [BB_THREADS] enclosure (lo, hi) of the burn probability's direction-independent part, per front cell of the round
+  uint16_t* pairs;  // [BB_PAIR_CAP] draws of the round: (front cell of the round << 4) | direction 0..8
   BbScalars* sc;
 };
 
-// One front cell (r, c) of sub-step j: enclosure of the burn probability from ring populations, one draw per burning
-// direction, exact (reference-order) re-evaluation of undecided draws; an ignition sets the cell's bit in v.ign.
+// Front cell (r, c): enclosure [blo, bhi] of (heat - dousing)(1 + p_veg)(1 + p_den) from ring populations, and which of
+// its Moore neighbours burn (bit d = 3 i + j of the result; 0 when the cell cannot ignite).  `fld_out` / `dwin_out`
+// (optional): the fire rows of the window and the 5x5 doused window, for the exact re-evaluation.
 template <int R>
-__device__ __forceinline__ void bb_front_cell(const BbView& v, const gca_params& P, const gca_state& S, const gca_inject& J,
-                                              int e, int j, int r, int c, const TfKey& kburn, const float* wind,
-                                              uint32_t half_burn, uint32_t& n_draws, uint32_t& n_thresh) {
-  const int H = P.H, W = P.W, WW = W >> 6, mode = P.rng_mode;
+__device__ __forceinline__ uint32_t bb_front_bounds(const BbView& v, const gca_params& P, const gca_state& S, int e, int r,
+                                                    int c, float& blo, float& bhi, float& a, float& b, uint32_t* fld,
+                                                    uint32_t& dwin) {
+  const int H = P.H, W = P.W, WW = W >> 6;
   const size_t env_off = (size_t)e * H * W;
   const size_t gcell = (size_t)r * W + c;
   constexpr int WIN = 2 * R + 1;
-  uint32_t fld[WIN];
 #pragma unroll
   for (int di = 0; di < WIN; ++di) {
     const int rr = r - R + di;
@@ -184,7 +188,7 @@ __device__ __forceinline__ void bb_front_cell(const BbView& v, const gca_params&
     Hf = fmaf((float)(cnt - prev), P.ring_w[k], Hf);
     prev = cnt;
   }
-  uint32_t dwin = 0;
+  dwin = 0;
 #pragma unroll
   for (int i = 0; i < 5; ++i) {
     const int rr = r - 2 + i;
@@ -200,49 +204,82 @@ __device__ __forceinline__ void bb_front_cell(const BbView& v, const gca_params&
   }
   int hid = 3 | (3 << 3);
   if (S.hidden != nullptr) hid = S.hidden[env_off + gcell];
-  const float a = P.onep_veg[clip15(hid & 7)], b = P.onep_den[clip15((hid >> 3) & 7)];
-  const float blo = __fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(Hf, BB_LO), Dhi), a), b);
-  const float bhi = __fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(Hf, BB_HI), Dlo), a), b);
-  if (!(bhi > 0.0f)) return;
+  a = P.onep_veg[clip15(hid & 7)];
+  b = P.onep_den[clip15((hid >> 3) & 7)];
+  blo = __fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(Hf, BB_LO), Dhi), a), b);
+  bhi = __fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(Hf, BB_HI), Dlo), a), b);
+  if (!(bhi > 0.0f)) return 0u;
   // burning Moore neighbours: bits R-1 .. R+1 of the three middle rows
-  const uint32_t nb3[3] = {(fld[R - 1] >> (R - 1)) & 7u, (fld[R] >> (R - 1)) & 7u, (fld[R + 1] >> (R - 1)) & 7u};
+  return (((fld[R - 1] >> (R - 1)) & 7u) | (((fld[R] >> (R - 1)) & 7u) << 3) | (((fld[R + 1] >> (R - 1)) & 7u) << 6)) & ~16u;
+}
+
+// reference-order (row-major, float32, from +0) value of (heat - dousing)(1 + p_veg)(1 + p_den): threshold cells
+template <int R>
+__device__ __forceinline__ float bb_exact_from(const gca_params& P, const uint32_t* fld, uint32_t dwin, float a, float b) {
+  constexpr int WIN = 2 * R + 1;
+  float heat = 0.0f;
+#pragma unroll 1
+  for (int di = 0; di < WIN; ++di) {
+    uint32_t m = fld[di];
+    const int a_di = di < R ? R - di : di - R;
+    while (m) {
+      const int dj = __ffs((int)m) - 1;
+      m &= m - 1;
+      const int a_dj = dj < R ? R - dj : dj - R;
+      heat = __fadd_rn(heat, P.ring_w[max(a_di, a_dj)]);
+    }
+  }
+  float dous = 0.0f;
+  for (int q = 0; q < 25; ++q)
+    if ((dwin >> q) & 1u) {
+      const int qi = q / 5, qj = q % 5;
+      const bool inner = qi >= 1 && qi <= 3 && qj >= 1 && qj <= 3;
+      dous = __fadd_rn(dous, inner ? P.dous_inner : P.dous_border);
+    }
+  return __fmul_rn(__fmul_rn(__fsub_rn(heat, dous), a), b);
+}
+// ... recomputed from the bit-boards for one cell (the pooled draws keep only the bounds per cell)
+template <int R>
+__device__ __noinline__ float bb_exact_base(const BbView& v, const gca_params& P, const gca_state& S, int e, int r, int c) {
+  uint32_t fld[2 * R + 1], dwin;
+  float blo, bhi, a, b;
+  bb_front_bounds<R>(v, P, S, e, r, c, blo, bhi, a, b, fld, dwin);
+  return bb_exact_from<R>(P, fld, dwin, a, b);
+}
+
+// the uniform of draw (cell, direction d) of sub-step j
+__device__ __forceinline__ float bb_draw(const gca_params& P, const gca_state& S, const gca_inject& J, int e, int j,
+                                         size_t gcell, int d, const TfKey& kburn, uint32_t half_burn) {
+  if (J.u_burn) return J.u_burn[(((size_t)j * S.N + e) * P.H * P.W + gcell) * 9 + d];
+  return bits_to_uniform(bits_at(kburn, (uint32_t)(gcell * 9 + d), half_burn, P.rng_mode));
+}
+
+// One front cell (r, c) of sub-step j by one thread (fronts larger than the list): enclosure, one draw per burning
+// direction, exact re-evaluation of undecided draws; an ignition sets the cell's bit in v.ign.
+template <int R>
+__device__ __forceinline__ void bb_front_cell(const BbView& v, const gca_params& P, const gca_state& S, const gca_inject& J,
+                                              int e, int j, int r, int c, const TfKey& kburn, const float* wind,
+                                              uint32_t half_burn, uint32_t& n_draws, uint32_t& n_thresh) {
+  const int W = P.W, WW = W >> 6;
+  const size_t env_off = (size_t)e * P.H * W;
+  const size_t gcell = (size_t)r * W + c;
+  uint32_t fld[2 * R + 1], dwin;
+  float blo, bhi, a, b;
+  const uint32_t nb = bb_front_bounds<R>(v, P, S, e, r, c, blo, bhi, a, b, fld, dwin);
   bool ig = false, have_exact = false;
   float base_exact = 0.0f;
 #pragma unroll 1
   for (int d = 0; d < 9 && !ig; ++d) {
-    if (d == 4) continue;
-    if (!((nb3[d / 3] >> (d % 3)) & 1u)) continue;
-    float u;
-    if (J.u_burn) u = J.u_burn[(((size_t)j * S.N + e) * H * W + gcell) * 9 + d];
-    else u = bits_to_uniform(bits_at(kburn, (uint32_t)(gcell * 9 + d), half_burn, mode));
+    if (!((nb >> d) & 1u)) continue;
+    const float u = bb_draw(P, S, J, e, j, gcell, d, kburn, half_burn);
     ++n_draws;
     const float w = wind[d];
     const float s = S.pslope ? S.pslope[(env_off + gcell) * 8 + dir_slot(d)] : 1.0f;
     const float plo = __fmul_rn(__fmul_rn(blo, w), s), phi = __fmul_rn(__fmul_rn(bhi, w), s);
     if (u < plo) { ig = true; break; }
     if (u < phi) {
-      // threshold cell: reference-order (row-major, float32, from +0) sums
       if (!have_exact) {
-        float heat = 0.0f;
-#pragma unroll 1
-        for (int di = 0; di < WIN; ++di) {
-          uint32_t m = fld[di];
-          const int a_di = di < R ? R - di : di - R;
-          while (m) {
-            const int dj = __ffs((int)m) - 1;
-            m &= m - 1;
-            const int a_dj = dj < R ? R - dj : dj - R;
-            heat = __fadd_rn(heat, P.ring_w[max(a_di, a_dj)]);
-          }
-        }
-        float dous = 0.0f;
-        for (int q = 0; q < 25; ++q)
-          if ((dwin >> q) & 1u) {
-            const int qi = q / 5, qj = q % 5;
-            const bool inner = qi >= 1 && qi <= 3 && qj >= 1 && qj <= 3;
-            dous = __fadd_rn(dous, inner ? P.dous_inner : P.dous_border);
-          }
-        base_exact = __fmul_rn(__fmul_rn(__fsub_rn(heat, dous), a), b);
+        base_exact = bb_exact_from<R>(P, fld, dwin, a, b);
         have_exact = true;
         ++n_thresh;
       }
@@ -269,7 +306,9 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
   v.ign = v.dous + HW;
   v.list = reinterpret_cast<uint16_t*>(v.ign + HW);
   v.burn = reinterpret_cast<uint32_t*>(v.list + BB_LIST_CAP);
-  v.sc = reinterpret_cast<BbScalars*>(v.burn + BB_BURN_CAP);
+  v.bnd = reinterpret_cast<float2*>(v.burn + BB_BURN_CAP);
+  v.pairs = reinterpret_cast<uint16_t*>(v.bnd + BB_THREADS);
+  v.sc = reinterpret_cast<BbScalars*>(v.pairs + BB_PAIR_CAP);
   const uint32_t inv_ww = (65536u + (uint32_t)WW - 1u) / (uint32_t)WW;  // i / WW = (i * inv_ww) >> 16 for i < 1024
   BbScalars& sc = *v.sc;
   const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
@@ -279,7 +318,7 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
   const uint32_t half_burn = (uint32_t)((9ull * H * W) >> 1);
 
   if (tid == 0) {
-    sc.cnt_tree = 0; sc.cnt_fire = 0; sc.nburn = 0;
+    sc.cnt_tree = 0; sc.cnt_fire = 0; sc.nburn = 0; sc.npairs[0] = 0; sc.npairs[1] = 0;
     sc.n_draws = 0; sc.n_ign = 0; sc.n_ext = 0; sc.n_thresh = 0; sc.n_front = 0;
   }
   // ---- grid -> bit-boards (warp 0 walks the key chains meanwhile) --------------------------------------------------
@@ -354,7 +393,7 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
     const TfKey kburn = tf_key(sr[0], sr[1]);
     const float* wind = P.winds + 9 * (int)sr[8];
     const uint32_t tick = tick0 + (uint32_t)j;
-    if (tid == 0) sc.nfront = 0;
+    if (tid == 0) { sc.nfront = 0; sc.npairs[0] = 0; }  // (the rounds of a sub-step start with counter 0)
     __syncthreads();
     // ---- front = tree AND dilate(fire) ------------------------------------------------------------------------------
     constexpr int MAXW = (65536 / 64 + BB_THREADS - 1) / BB_THREADS;  // words per thread
@@ -401,9 +440,54 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
         }
       }
       __syncthreads();
-      for (int i = tid; i < nfront; i += BB_THREADS) {
-        const int cellrc = v.list[i];
-        bb_front_cell<R>(v, P, S, J, e, j, cellrc >> 8, cellrc & 255, kburn, wind, half_burn, n_draws, n_thresh);
+      // rounds of BB_THREADS front cells: a thread per cell computes the enclosure and lists the cell's burning
+      // directions; the (cell, direction) draws are then dealt one per thread -- a cell with five burning neighbours
+      // no longer makes its warp wait for five threefry blocks in a row
+      int par = 0;
+      for (int base = 0; base < nfront; base += BB_THREADS, par ^= 1) {
+        {
+          const int i = base + tid;
+          uint32_t nb = 0u;
+          float blo = 0.0f, bhi = 0.0f;
+          if (i < nfront) {
+            const int cellrc = v.list[i];
+            uint32_t fld[2 * R + 1], dwin;
+            float a, b;
+            nb = bb_front_bounds<R>(v, P, S, e, cellrc >> 8, cellrc & 255, blo, bhi, a, b, fld, dwin);
+          }
+          v.bnd[tid] = make_float2(blo, bhi);
+          if (nb) {
+            int at = atomicAdd(&sc.npairs[par], __popc(nb));
+            while (nb) {
+              const uint32_t d = (uint32_t)__ffs((int)nb) - 1u;
+              nb &= nb - 1u;
+              v.pairs[at++] = (uint16_t)(((uint32_t)tid << 4) | d);
+            }
+          }
+        }
+        __syncthreads();
+        const int npairs = sc.npairs[par];
+        if (tid == 0) sc.npairs[par ^ 1] = 0;  // the next round's counter (its last readers passed the barrier above)
+        for (int q = tid; q < npairs; q += BB_THREADS) {
+          const uint32_t rec = v.pairs[q];
+          const int t = (int)(rec >> 4), d = (int)(rec & 15u);
+          const int cellrc = v.list[base + t];
+          const int r = cellrc >> 8, c = cellrc & 255;
+          const size_t gcell = (size_t)r * W + c;
+          const float2 bd = v.bnd[t];
+          const float s = S.pslope ? S.pslope[(env_off + gcell) * 8 + dir_slot(d)] : 1.0f;
+          const float u = bb_draw(P, S, J, e, j, gcell, d, kburn, half_burn);
+          ++n_draws;
+          const float w = wind[d];
+          const float plo = __fmul_rn(__fmul_rn(bd.x, w), s), phi = __fmul_rn(__fmul_rn(bd.y, w), s);
+          bool ig = u < plo;
+          if (!ig && u < phi) {  // threshold cell: reference-order sums
+            ++n_thresh;
+            ig = u < __fmul_rn(__fmul_rn(bb_exact_base<R>(v, P, S, e, r, c), w), s);
+          }
+          if (ig) atomicOr(v.ign + r * WW + (c >> 6), 1ull << (c & 63));
+        }
+        __syncthreads();
       }
     } else {
       // a front larger than the list (dense fires): every thread walks its own words
@@ -584,7 +668,8 @@ bool bb_supported(const gca_params& p) {
 cudaError_t launch_bb_env_step(const gca_params& p, const gca_state& s, const int32_t* actions, const gca_step_out& out,
                                const gca_inject& inj, uint32_t flags, cudaStream_t st) {
   const int HW = p.H * (p.W >> 6);
-  const size_t smem = (size_t)HW * 8 * 4 + BB_LIST_CAP * sizeof(uint16_t) + BB_BURN_CAP * sizeof(uint32_t) + sizeof(BbScalars) + 16;
+  const size_t smem = (size_t)HW * 8 * 4 + BB_LIST_CAP * sizeof(uint16_t) + BB_BURN_CAP * sizeof(uint32_t) +
+                      BB_THREADS * sizeof(float2) + BB_PAIR_CAP * sizeof(uint16_t) + sizeof(BbScalars) + 16;
   switch (p.R) {
     case 4: return launch_bb_instance<4>(p, s, actions, out, inj, flags, smem, st);
     case 5: return launch_bb_instance<5>(p, s, actions, out, inj, flags, smem, st);
