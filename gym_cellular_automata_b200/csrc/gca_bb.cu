@@ -32,6 +32,7 @@ struct BbScalars {
   uint32_t sched[GCA_MAX_K][12];  // per sub-step: Sburn[2] Sgrow[2] ak1[2] ak2[2] wind change step pad
   int nfront;
   int npairs[2];                  // draws listed in the current round of front cells (double-buffered by round parity)
+  unsigned long long rowfire[4];  // bit r: row r may hold a burning cell (set when fire is seen / ignites, never cleared in a step)
   int nburn;                      // entries on the burn list (> BB_BURN_CAP: overflow, the list is not used)
   int cnt_tree, cnt_fire;
   unsigned int n_draws, n_ign, n_ext, n_thresh, n_front;
@@ -317,10 +318,12 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
   const uint32_t half_cell = (uint32_t)(((size_t)H * W) >> 1);
   const uint32_t half_burn = (uint32_t)((9ull * H * W) >> 1);
 
+  if (tid < 4) sc.rowfire[tid] = 0ull;
   if (tid == 0) {
     sc.cnt_tree = 0; sc.cnt_fire = 0; sc.nburn = 0; sc.npairs[0] = 0; sc.npairs[1] = 0;
     sc.n_draws = 0; sc.n_ign = 0; sc.n_ext = 0; sc.n_thresh = 0; sc.n_front = 0;
   }
+  __syncthreads();  // (the row flags are clear before the first word with fire sets one)
   // ---- grid -> bit-boards (warp 0 walks the key chains meanwhile) --------------------------------------------------
   if (tid < 32) bb_key_schedule(sc, P, S, J, e, lane);
   for (int i = tid; i < HW; i += BB_THREADS) {
@@ -328,6 +331,7 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
     pack64(S.cell + env_off + (size_t)i * 64, t, f);
     v.tree[i] = t;
     v.fire[i] = f;
+    if (f) atomicOr(&sc.rowfire[(((uint32_t)i * inv_ww) >> 16) >> 6], 1ull << ((((uint32_t)i * inv_ww) >> 16) & 63u));
     v.dous[i] = reinterpret_cast<const unsigned long long*>(S.doused)[(size_t)e * HW + i];
     v.ign[i] = 0ull;
   }
@@ -405,6 +409,11 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
       fr[q] = 0ull;
       if (i < HW) {
         const int r = (int)(((uint32_t)i * inv_ww) >> 16), w = i - r * WW;
+        // rows r-1 .. r+1 without a burning cell (most of a 256x256 grid): nothing to dilate
+        const int rl = r > 0 ? r - 1 : 0, rh = r + 1 < H ? r + 1 : r;
+        const unsigned long long near = ((sc.rowfire[rl >> 6] >> (rl & 63)) | (sc.rowfire[r >> 6] >> (r & 63)) |
+                                         (sc.rowfire[rh >> 6] >> (rh & 63))) & 1ull;
+        if (!near) continue;
         unsigned long long dil = 0ull;
 #pragma unroll
         for (int dr = -1; dr <= 1; ++dr) {
@@ -548,6 +557,7 @@ env_step_bb_kernel(const __grid_constant__ gca_params P, const __grid_constant__
         }
       }
       if (I) {
+        atomicOr(&sc.rowfire[r >> 6], 1ull << (r & 63));
         unsigned long long m = I;
         while (m) {
           const int b = __ffsll((long long)m) - 1;

@@ -49,6 +49,9 @@ struct TileSmem {
   unsigned long long ign[T_TH];                          // cells of the tile that ignite this sub-step (bit = column)
   uint32_t tbits[T_ROWS_MAX][4];                         // tree bit-board of tile + halo (see fbits)
   int nlist2, n_ign, n_ext;                              // change-candidate list of the write phase, its counters
+  float2 bnd[T_THREADS];                                 // per front cell of the round: enclosure (lo, hi), direction-independent part
+  uint16_t pairs[T_THREADS * 8];                         // draws of the round: (front cell of the round << 4) | direction
+  int npairs[2];                                         // their number, double-buffered by round parity
   unsigned long long dw[T_TH + 4][3];                     // doused rows r0-2 .. r0+TH+1, words (c0 >> 6) - 1 .. + 1
   int any_doused;
   uint32_t fbits[T_ROWS_MAX][4];                         // fire bit-board of tile + halo: bit c of the row <-> tile column c (3 words + a zero pad)
@@ -79,6 +82,21 @@ __device__ __forceinline__ uint32_t dous_window_g(const unsigned long long* __re
 
 // One CA sub-step of tile (e, ty, tx) by the whole CTA (`it` = how many tiles this CTA has staged before: the parity of
 // the TMA barrier's phase).  Returns (to thread 0) the number of burning cells the tile holds afterwards.
+// 5x5 doused window of tile cell (lr, lcc) from the staged rows: bit (5 i + j) <-> (r-2+i, c-2+j); outside the grid = 0
+__device__ __forceinline__ uint32_t tile_dous_window(const TileSmem& sm, int lr, int lcc) {
+  uint32_t dwin = 0u;
+  if (sm.any_doused) {
+    const int pos = 62 + lcc, wi = pos >> 6, sh = pos & 63;  // bit offset of column c-2 in the three staged words
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const unsigned long long lo = sm.dw[lr + i][wi], hi = sm.dw[lr + i][wi + 1 < 3 ? wi + 1 : 2];
+      const unsigned long long bits = (lo >> sh) | (sh && wi + 1 < 3 ? hi << (64 - sh) : 0ull);
+      dwin |= ((uint32_t)bits & 31u) << (5 * i);
+    }
+  }
+  return dwin;
+}
+
 template <bool USE_TMA>
 __device__ __forceinline__ int ca_tile_body(TileSmem& sm, const gca_params& P, const gca_state& S, const gca_inject& J,
                                             const CUtensorMap* tmap, const uint8_t* __restrict__ cell_in,
@@ -158,7 +176,7 @@ __device__ __forceinline__ int ca_tile_body(TileSmem& sm, const gca_params& P, c
     }
   }
   if (tid < T_TH) sm.ign[tid] = 0ull;
-  if (tid == 0) { sm.nlist2 = 0; sm.n_ign = 0; sm.n_ext = 0; }
+  if (tid == 0) { sm.nlist2 = 0; sm.n_ign = 0; sm.n_ext = 0; sm.npairs[0] = 0; sm.npairs[1] = 0; }
   __syncthreads();
   const uint32_t* sc = sched + (size_t)e * sched_env_stride + sched_off;
   const uint32_t tick = S.tick[e] + (uint32_t)substep;  // S.tick advances by K in the epilogue
@@ -191,116 +209,123 @@ __device__ __forceinline__ int ca_tile_body(TileSmem& sm, const gca_params& P, c
   }
   __syncthreads();
 
-  // ---- balanced pass over the front cells --------------------------------------------------------
+  // ---- the front cells, in rounds of T_THREADS: a thread per cell computes the enclosure of the burn probability's
+  //      direction-independent part and lists the cell's burning directions; the (cell, direction) draws are then dealt
+  //      one per thread (a cell with five burning neighbours does not make its warp wait for five threefry blocks) -----
   const int nfront = sm.nfront;
   const TfKey kburn = tf_key(sc[SC_BURN0], sc[SC_BURN1]);
   const float* wind = P.winds + 9 * (int)sc[SC_WIND];
   uint32_t n_draws = 0, n_thresh = 0;
-  for (int i = tid; i < nfront; i += T_THREADS) {
-    const int lr = sm.list[i] >> 6, lcc = sm.list[i] & 63;
-    const int gr = r0 + lr, gc = c0 + lcc;
-    const size_t gcell = (size_t)gr * W + gc;
-    const uint8_t* ctr = sm.tile + (lr + R) * pitch + (lcc + T_HC);
-    // the cell's hidden byte and the 8 slope factors of its directions: requested now, used after the heat sum
-    int hid = 3 | (3 << 3);
-    if (S.hidden != nullptr) hid = S.hidden[env_off + gcell];
-    float4 sl_a = make_float4(1.f, 1.f, 1.f, 1.f), sl_b = sl_a;
-    if (S.pslope != nullptr) {
-      const float4* ps = reinterpret_cast<const float4*>(S.pslope + (env_off + gcell) * 8);
-      sl_a = ps[0];
-      sl_b = ps[1];
-    }
-    // heat from the fire bit rows: H = sum_k w_k (C_k - C_{k-1}) = sum_k (w_k - w_{k+1}) C_k, C_k = burning cells within
-    // Chebyshev distance k = popcounts of the 2k+1 window rows under a (2k+1)-bit mask (the centre is a tree).  Any
-    // summation order is inside the enclosure (T_LO / T_HI leave 2048 u, this sum is off by a few dozen u at most).
-    uint32_t wr[2 * T_MAXR + 1];
+  int par = 0;
+  for (int base = 0; base < nfront; base += T_THREADS, par ^= 1) {
     {
-      const int start = lcc + T_HC - R;  // first tile column of the window
-      const int wq = start >> 5, sh = start & 31;
+      const int i = base + tid;
+      uint32_t nb = 0u;
+      float blo = 0.0f, bhi = 0.0f;
+      if (i < nfront) {
+        const int lr = sm.list[i] >> 6, lcc = sm.list[i] & 63;
+        const size_t gcell = (size_t)(r0 + lr) * W + (c0 + lcc);
+        // the cell's hidden byte: requested now, used after the heat sum
+        int hid = 3 | (3 << 3);
+        if (S.hidden != nullptr) hid = S.hidden[env_off + gcell];
+        // heat from the fire bit rows: H = sum_k w_k (C_k - C_{k-1}) = sum_k (w_k - w_{k+1}) C_k, C_k = burning cells
+        // within Chebyshev distance k = popcounts of the 2k+1 window rows under a (2k+1)-bit mask (the centre is a tree).
+        // Any summation order is inside the enclosure (T_LO / T_HI leave 2048 u, this sum is off by a few dozen u).
+        uint32_t wr[2 * T_MAXR + 1];
+        {
+          const int start = lcc + T_HC - R;  // first tile column of the window
+          const int wq = start >> 5, sh = start & 31;
 #pragma unroll
-      for (int q = 0; q <= 2 * T_MAXR; ++q) {
-        const int di = q - T_MAXR;
-        wr[q] = 0u;
-        if (di >= -R && di <= R) {
-          const uint32_t* fr = sm.fbits[lr + R + di];
-          wr[q] = __funnelshift_r(fr[wq], fr[wq + 1], sh);  // bit b <-> column offset b - R
+          for (int q = 0; q <= 2 * T_MAXR; ++q) {
+            const int di = q - T_MAXR;
+            wr[q] = 0u;
+            if (di >= -R && di <= R) {
+              const uint32_t* fr = sm.fbits[lr + R + di];
+              wr[q] = __funnelshift_r(fr[wq], fr[wq + 1], sh);  // bit b <-> column offset b - R
+            }
+          }
+        }
+        float Hf = 0.0f;
+#pragma unroll
+        for (int k = T_MAXR; k >= 1; --k) {
+          if (k <= R) {
+            const uint32_t box = ((2u << (2 * k)) - 1u) << (R - k);  // |dj| <= k
+            int Ck = 0;
+#pragma unroll
+            for (int di = -k; di <= k; ++di) Ck += __popc(wr[di + T_MAXR] & box);
+            const float dk = k < R ? __fsub_rn(P.ring_w[k], P.ring_w[k + 1]) : P.ring_w[k];
+            Hf = fmaf((float)Ck, dk, Hf);
+          }
+        }
+        float Dlo = 0.0f, Dhi = 0.0f;
+        const uint32_t dwin = tile_dous_window(sm, lr, lcc);
+        if (dwin) {
+          const int ni = __popc(dwin & ((0x0Eu << 5) | (0x0Eu << 10) | (0x0Eu << 15)));
+          const int nbd = __popc(dwin) - ni;
+          const float Df = fmaf((float)nbd, P.dous_border, (float)ni * P.dous_inner);
+          Dlo = __fmul_rn(Df, T_LO);
+          Dhi = __fmul_rn(Df, T_HI);
+        }
+        const float a = P.onep_veg[clip15(hid & 7)], b = P.onep_den[clip15((hid >> 3) & 7)];
+        blo = __fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(Hf, T_LO), Dhi), a), b);
+        bhi = __fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(Hf, T_HI), Dlo), a), b);
+        if (bhi > 0.0f)  // burning Moore neighbours: bits R-1 .. R+1 of the three middle window rows; d = 3 i + j
+          nb = ((((wr[T_MAXR - 1] >> (R - 1)) & 7u)) | (((wr[T_MAXR] >> (R - 1)) & 7u) << 3) |
+                (((wr[T_MAXR + 1] >> (R - 1)) & 7u) << 6)) & ~16u;
+      }
+      sm.bnd[tid] = make_float2(blo, bhi);
+      if (nb) {
+        int at = atomicAdd(&sm.npairs[par], __popc(nb));
+        while (nb) {
+          const uint32_t d = (uint32_t)__ffs((int)nb) - 1u;
+          nb &= nb - 1u;
+          sm.pairs[at++] = (uint16_t)(((uint32_t)tid << 4) | d);
         }
       }
     }
-    float Hf = 0.0f;
-#pragma unroll
-    for (int k = T_MAXR; k >= 1; --k) {
-      if (k <= R) {
-        const uint32_t box = ((2u << (2 * k)) - 1u) << (R - k);  // |dj| <= k
-        int Ck = 0;
-#pragma unroll
-        for (int di = -k; di <= k; ++di) Ck += __popc(wr[di + T_MAXR] & box);
-        const float dk = k < R ? __fsub_rn(P.ring_w[k], P.ring_w[k + 1]) : P.ring_w[k];
-        Hf = fmaf((float)Ck, dk, Hf);
-      }
-    }
-    float Dlo = 0.0f, Dhi = 0.0f;
-    uint32_t dwin = 0u;
-    if (sm.any_doused) {  // 5x5 doused window: bit (5 i + j) <-> (r-2+i, c-2+j); outside the grid = 0
-      const int pos = 62 + lcc, wi = pos >> 6, sh = pos & 63;  // bit offset of column c-2 in the three staged words
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const unsigned long long lo = sm.dw[lr + i][wi], hi = sm.dw[lr + i][wi + 1 < 3 ? wi + 1 : 2];
-        const unsigned long long bits = (lo >> sh) | (sh && wi + 1 < 3 ? hi << (64 - sh) : 0ull);
-        dwin |= ((uint32_t)bits & 31u) << (5 * i);
-      }
-    }
-    if (dwin) {
-      const int ni = __popc(dwin & ((0x0Eu << 5) | (0x0Eu << 10) | (0x0Eu << 15)));
-      const int nb = __popc(dwin) - ni;
-      const float Df = fmaf((float)nb, P.dous_border, (float)ni * P.dous_inner);
-      Dlo = __fmul_rn(Df, T_LO);
-      Dhi = __fmul_rn(Df, T_HI);
-    }
-    const float a = P.onep_veg[clip15(hid & 7)], b = P.onep_den[clip15((hid >> 3) & 7)];
-    const float blo = __fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(Hf, T_LO), Dhi), a), b);
-    const float bhi = __fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(Hf, T_HI), Dlo), a), b);
-    if (!(bhi > 0.0f)) continue;
-    bool ig = false;
-    float base_exact = 0.0f;
-    bool have_exact = false;
-    for (int d = 0; d < 9 && !ig; ++d) {
-      if (d == 4) continue;
-      if (ctr[(d / 3 - 1) * pitch + (d % 3 - 1)] != 2) continue;
+    __syncthreads();
+    const int npairs = sm.npairs[par];
+    if (tid == 0) sm.npairs[par ^ 1] = 0;  // the next round's counter (its last readers passed the barrier above)
+    for (int q = tid; q < npairs; q += T_THREADS) {
+      const uint32_t rec = sm.pairs[q];
+      const int t = (int)(rec >> 4), d = (int)(rec & 15u);
+      const int lr = sm.list[base + t] >> 6, lcc = sm.list[base + t] & 63;
+      const size_t gcell = (size_t)(r0 + lr) * W + (c0 + lcc);
+      const float2 bd = sm.bnd[t];
+      const float s = S.pslope ? S.pslope[(env_off + gcell) * 8 + dir_slot(d)] : 1.0f;
       float u;
       if (J.u_burn) u = J.u_burn[(((size_t)substep * S.N + e) * H * W + gcell) * 9 + d];
       else u = bits_to_uniform(bits_at(kburn, (uint32_t)(gcell * 9 + d), half_burn, mode));
       ++n_draws;
       const float w = wind[d];
-      const int dsl = dir_slot(d);
-      const float4 sq = dsl < 4 ? sl_a : sl_b;
-      const float s = (dsl & 3) == 0 ? sq.x : ((dsl & 3) == 1 ? sq.y : ((dsl & 3) == 2 ? sq.z : sq.w));
-      const float plo = __fmul_rn(__fmul_rn(blo, w), s), phi = __fmul_rn(__fmul_rn(bhi, w), s);
-      if (u < plo) { ig = true; break; }
-      if (u < phi) {
+      const float plo = __fmul_rn(__fmul_rn(bd.x, w), s), phi = __fmul_rn(__fmul_rn(bd.y, w), s);
+      bool ig = u < plo;
+      if (!ig && u < phi) {
         // threshold cell: reference-order (row-major, float32, from +0) sums
-        if (!have_exact) {
-          float heat = 0.0f;
-          for (int di = 0; di < win; ++di)
-            for (int dj = 0; dj < win; ++dj)
-              if (ctr[(di - R) * pitch + (dj - R)] == 2) heat = __fadd_rn(heat, P.ring_w[max(abs(di - R), abs(dj - R))]);
-          float dous = 0.0f;
-          for (int q = 0; q < 25; ++q)
-            if ((dwin >> q) & 1u) {
-              const int qi = q / 5, qj = q % 5;
-              const bool inner = qi >= 1 && qi <= 3 && qj >= 1 && qj <= 3;
-              dous = __fadd_rn(dous, inner ? P.dous_inner : P.dous_border);
-            }
-          base_exact = __fmul_rn(__fmul_rn(__fsub_rn(heat, dous), a), b);
-          have_exact = true;
-          ++n_thresh;
-        }
-        if (u < __fmul_rn(__fmul_rn(base_exact, w), s)) ig = true;
+        ++n_thresh;
+        const uint8_t* ctr = sm.tile + (lr + R) * pitch + (lcc + T_HC);
+        float heat = 0.0f;
+        for (int di = 0; di < win; ++di)
+          for (int dj = 0; dj < win; ++dj)
+            if (ctr[(di - R) * pitch + (dj - R)] == 2) heat = __fadd_rn(heat, P.ring_w[max(abs(di - R), abs(dj - R))]);
+        const uint32_t dwin = tile_dous_window(sm, lr, lcc);
+        float dous = 0.0f;
+        for (int qq = 0; qq < 25; ++qq)
+          if ((dwin >> qq) & 1u) {
+            const int qi = qq / 5, qj = qq % 5;
+            const bool inner = qi >= 1 && qi <= 3 && qj >= 1 && qj <= 3;
+            dous = __fadd_rn(dous, inner ? P.dous_inner : P.dous_border);
+          }
+        int hid = 3 | (3 << 3);
+        if (S.hidden != nullptr) hid = S.hidden[env_off + gcell];
+        const float a = P.onep_veg[clip15(hid & 7)], b = P.onep_den[clip15((hid >> 3) & 7)];
+        const float base_exact = __fmul_rn(__fmul_rn(__fsub_rn(heat, dous), a), b);
+        ig = u < __fmul_rn(__fmul_rn(base_exact, w), s);
       }
+      if (ig) atomicOr(&sm.ign[lr], 1ull << lcc);
     }
-    if (ig) atomicOr(&sm.ign[lr], 1ull << lcc);
+    __syncthreads();
   }
-  __syncthreads();
 
   // ---- write the new grid, burn-out ticks, counts -------------------------------------------------
   const TfKey ka1 = tf_key(sc[SC_AK10], sc[SC_AK11]), ka2 = tf_key(sc[SC_AK20], sc[SC_AK21]);
