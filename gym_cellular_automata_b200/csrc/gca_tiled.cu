@@ -82,6 +82,21 @@ __device__ __forceinline__ uint32_t dous_window_g(const unsigned long long* __re
 
 // One CA sub-step of tile (e, ty, tx) by the whole CTA (`it` = how many tiles this CTA has staged before: the parity of
 // the TMA barrier's phase).  Returns (to thread 0) the number of burning cells the tile holds afterwards.
+// copies tile (e, ty, tx) from one grid buffer to the other (first 128 threads of the CTA)
+__device__ __forceinline__ void copy_tile(int H, int W, int e, int ty, int tx, const uint8_t* __restrict__ src,
+                                          uint8_t* __restrict__ dst) {
+  const int tid = threadIdx.x;
+  if (tid >= T_TH * 4) return;
+  const int r = ty * T_TH + (tid >> 2), c = tx * T_TW + (tid & 3) * 16;
+  if (r >= H || c >= W) return;
+  const size_t off = ((size_t)e * H + r) * W + c;
+  if ((W & 15) == 0) {
+    *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(src + off);
+  } else {
+    for (int k = 0; k < 16 && c + k < W; ++k) dst[off + k] = src[off + k];
+  }
+}
+
 // 5x5 doused window of tile cell (lr, lcc) from the staged rows: bit (5 i + j) <-> (r-2+i, c-2+j); outside the grid = 0
 __device__ __forceinline__ uint32_t tile_dous_window(const TileSmem& sm, int lr, int lcc) {
   uint32_t dwin = 0u;
@@ -547,33 +562,39 @@ __global__ void __launch_bounds__(256) tile_count_kernel(int N, int H, int W, in
   }
 }
 
-// appends tile `gid` to the list of sub-step j when it is active: its 3x3 tile neighbourhood holds fire (R <= 10 is
-// smaller than a tile) or regrowth can change any cell.  All 32 lanes of a warp call.
+// The tile list of an env step (built once, from the fire counts at its start).  A burning cell moves at most one cell
+// per sub-step and a tile is 32 x 64 cells, so for K <= 32 sub-steps every tile that can become active during the step
+// -- fire in its 3x3 tile neighbourhood at that time -- lies within Chebyshev tile distance 2 of a tile that holds fire
+// NOW: those tiles are listed for computation in every sub-step.  The ring at distance 3 is listed "copy only"
+// (T_COPY_ONLY): its tiles cannot change, but their cells are the halo of the computed tiles, which read the two grid
+// buffers alternately (see ca_tiled_list_kernel).  With regrowth every tile is computed.  All 32 lanes of a warp call.
+constexpr uint32_t T_COPY_ONLY = 0x80000000u;
 __device__ __forceinline__ void list_append(long long gid, long long total, int TX, int TY, const uint32_t* __restrict__ fire,
-                                            uint32_t* __restrict__ list, int* __restrict__ nactive, int j, int all_active) {
-  bool act = false;
+                                            uint32_t* __restrict__ list, int* __restrict__ nactive, int all_active) {
+  int dist = 4;  // 4 = not listed
   if (gid < total) {
-    act = all_active != 0;
-    if (!act) {
+    if (all_active) dist = 0;
+    else {
       const int tx = (int)(gid % TX), ty = (int)((gid / TX) % TY);
       const uint32_t* f = fire + (gid - (long long)ty * TX - tx);  // the env's tile (0, 0)
-      for (int dy = -1; dy <= 1 && !act; ++dy) {
+      for (int dy = -3; dy <= 3; ++dy) {
         const int y = ty + dy;
         if (y < 0 || y >= TY) continue;
-        for (int dx = -1; dx <= 1; ++dx) {
+        for (int dx = -3; dx <= 3; ++dx) {
           const int x = tx + dx;
-          if (x >= 0 && x < TX && f[y * TX + x] != 0u) { act = true; break; }
+          if (x >= 0 && x < TX && f[y * TX + x] != 0u) dist = min(dist, max(abs(dx), abs(dy)));
         }
       }
     }
   }
+  const bool act = dist <= 3;
   const uint32_t bal = __ballot_sync(GCA_FULL, act);
   if (bal) {
     const int lane = threadIdx.x & 31;
     int base = 0;
-    if (lane == 0) base = atomicAdd(&nactive[j], __popc(bal));
+    if (lane == 0) base = atomicAdd(&nactive[0], __popc(bal));
     base = __shfl_sync(GCA_FULL, base, 0);
-    if (act) list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)gid;
+    if (act) list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)gid | (dist == 3 ? T_COPY_ONLY : 0u);
   }
 }
 
@@ -659,58 +680,53 @@ __global__ void __launch_bounds__(256) tiled_sched_all_kernel(gca_params P, gca_
       S.key[2 * e + 1] = k1;
     }
   }
-  list_append(gid, (long long)S.N * TY * TX, TX, TY, fire, list, nactive, 0, all_active);
+  list_append(gid, (long long)S.N * TY * TX, TX, TY, fire, list, nactive, all_active);
 }
 
+// One CA sub-step of every listed tile.  The grid lives in two buffers, A = S.cell and B = the scratch grid: sub-step j
+// reads tiles + halos from one (A when j is even) and writes the tiles' new cells to the other, so no copy-back pass
+// separates the sub-steps -- neighbouring tiles still read the old cells while a tile writes its new ones.  Both buffers
+// hold the current grid on the computed tiles after every sub-step (each is rewritten every other sub-step from the
+// other); the copy-only ring around them is brought into B once, in sub-step 0; nothing else is ever read from B.
 template <bool USE_TMA>
 __global__ void __launch_bounds__(T_THREADS, 3)
 ca_tiled_list_kernel(const __grid_constant__ gca_params P, const __grid_constant__ gca_state S,
-                     const __grid_constant__ gca_inject J, const __grid_constant__ CUtensorMap tmap,
-                     uint8_t* __restrict__ cell_out, const uint32_t* __restrict__ sched, int32_t* __restrict__ counts,
-                     unsigned long long* stats, uint32_t* __restrict__ fire, const uint32_t* __restrict__ list,
-                     const int* __restrict__ nactive, int substep, int pitch, int TX, int TY) {
+                     const __grid_constant__ gca_inject J, const __grid_constant__ CUtensorMap tmap_a,
+                     const __grid_constant__ CUtensorMap tmap_b, uint8_t* __restrict__ cell_b,
+                     const uint32_t* __restrict__ sched, int32_t* __restrict__ counts, unsigned long long* stats,
+                     const uint32_t* __restrict__ list, const int* __restrict__ nactive, int substep, int pitch, int TX,
+                     int TY) {
   __shared__ TileSmem sm;
-  const int n = nactive[substep];
-  const uint32_t* cur = list + (substep & 1 ? (long long)S.N * TY * TX : 0);
+  const int n = nactive[0];
+  const bool from_a = (substep & 1) == 0;
+  const uint8_t* cell_in = from_a ? S.cell : cell_b;
+  uint8_t* cell_out = from_a ? cell_b : S.cell;
+  const CUtensorMap* tmap = from_a ? &tmap_a : &tmap_b;
   int it = 0;
-  for (int i = blockIdx.x; i < n; i += gridDim.x, ++it) {
-    const uint32_t t = cur[i];
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint32_t ent = list[i], t = ent & ~T_COPY_ONLY;
     const int tx = (int)(t % (uint32_t)TX), ty = (int)((t / (uint32_t)TX) % (uint32_t)TY), e = (int)(t / (uint32_t)(TX * TY));
-    const int after = ca_tile_body<USE_TMA>(sm, P, S, J, &tmap, S.cell, cell_out, sched, counts, stats, substep, pitch, e,
-                                            ty, tx, it, SC_N * GCA_MAX_K, SC_N * substep);
-    if (threadIdx.x == 0) fire[t] = (uint32_t)after;  // (only this tile's CTA writes it; the next list is built from it)
+    if (ent & T_COPY_ONLY) {
+      if (substep == 0) copy_tile(P.H, P.W, e, ty, tx, cell_in, cell_out);
+      continue;
+    }
+    ca_tile_body<USE_TMA>(sm, P, S, J, tmap, cell_in, cell_out, sched, counts, stats, substep, pitch, e, ty, tx, it,
+                          SC_N * GCA_MAX_K, SC_N * substep);
+    ++it;
     __syncthreads();  // the shared tile is free for the next entry
   }
 }
 
-// copies the new cells of the listed tiles from the scratch grid back into the grid and -- every tile's new fire
-// count being final once this kernel runs -- builds the active-tile list of the NEXT sub-step (build_next)
-__global__ void __launch_bounds__(128) tile_apply_list_kernel(int N, int H, int W, int TX, int TY, uint32_t* __restrict__ list,
-                                                              int* __restrict__ nactive, int substep,
-                                                              const uint8_t* __restrict__ scratch, uint8_t* __restrict__ cell,
-                                                              const uint32_t* __restrict__ fire, int build_next, int all_active) {
-  const int n = nactive[substep];
-  const int tid = threadIdx.x;
-  const long long total = (long long)N * TY * TX;
-  // the lists of successive sub-steps alternate between the two halves of the list buffer
-  const uint32_t* cur = list + (substep & 1 ? total : 0);
+// K odd: the last sub-step wrote the scratch grid -- the computed tiles go back to S.cell
+__global__ void __launch_bounds__(T_THREADS) tile_copy_back_kernel(int H, int W, int TX, int TY,
+                                                                   const uint32_t* __restrict__ list,
+                                                                   const int* __restrict__ nactive,
+                                                                   const uint8_t* __restrict__ scratch, uint8_t* __restrict__ cell) {
+  const int n = nactive[0];
   for (int i = blockIdx.x; i < n; i += gridDim.x) {
-    const uint32_t t = cur[i];
-    const int tx = (int)(t % (uint32_t)TX), ty = (int)((t / (uint32_t)TX) % (uint32_t)TY), e = (int)(t / (uint32_t)(TX * TY));
-    const int r = ty * T_TH + (tid >> 2), c = tx * T_TW + (tid & 3) * 16;
-    if (r >= H || c >= W) continue;
-    const size_t off = ((size_t)e * H + r) * W + c;
-    if ((W & 15) == 0) {
-      *reinterpret_cast<uint4*>(cell + off) = *reinterpret_cast<const uint4*>(scratch + off);
-    } else {
-      for (int k = 0; k < 16 && c + k < W; ++k) cell[off + k] = scratch[off + k];
-    }
-  }
-  if (build_next) {
-    uint32_t* nxt = list + (substep & 1 ? 0 : total);
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += stride)
-      list_append(base + tid, total, TX, TY, fire, nxt, nactive, substep + 1, all_active);
+    const uint32_t ent = list[i], t = ent & ~T_COPY_ONLY;
+    if (ent & T_COPY_ONLY) continue;
+    copy_tile(H, W, (int)(t / (uint32_t)(TX * TY)), (int)((t / (uint32_t)TX) % (uint32_t)TY), (int)(t % (uint32_t)TX), scratch, cell);
   }
 }
 
@@ -782,8 +798,9 @@ static bool make_tmap(CUtensorMap* m, const uint8_t* base, int N, int H, int W, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// One env step: one clear, one dense count, the key schedules of all sub-steps + the first list, then 2 kernels with
-// small fixed grids per sub-step and the epilogue.  Layout of `aux` (words): nactive[16] | fire[tiles] | list[2 tiles],
+// One env step: one clear, one dense count, the key schedules of all sub-steps + the step's tile list, then ONE kernel
+// with a small fixed grid per sub-step (+ a copy-back when K is odd) and the epilogue.  Layout of `aux` (words):
+// nactive[16] | fire[tiles] | list[tiles] (+ tiles spare),
 // with nactive directly behind the counts so that one clear covers both.
 static cudaError_t enqueue_tiled_env_step(const gca_params& p, const gca_state& s, const int32_t* actions,
                                                  const gca_step_out& out, const gca_inject& inj, uint32_t flags,
@@ -811,30 +828,29 @@ static cudaError_t enqueue_tiled_env_step(const gca_params& p, const gca_state& 
   }
   const int g_count = (int)((tiles + 7) / 8 < (long long)sms * 4 ? (tiles + 7) / 8 : (long long)sms * 4);  // 8 warps per CTA, a warp per tile
   const int g_tile = (int)(tiles < (long long)sms * 4 ? tiles : (long long)sms * 4);
-  const int g_apply = (int)(tiles < (long long)sms * 8 ? tiles : (long long)sms * 8);
   tile_count_kernel<<<g_count, 256, 0, st>>>(N, H, W, TX, TY, s.cell, fire, scratch_counts);
-  CUtensorMap tm;
-  memset(&tm, 0, sizeof(tm));
-  const bool tma = use_tma && make_tmap(&tm, s.cell, N, H, W, pitch, rows);
+  CUtensorMap tm_a, tm_b;
+  memset(&tm_a, 0, sizeof(tm_a));
+  memset(&tm_b, 0, sizeof(tm_b));
+  const bool tma = use_tma && make_tmap(&tm_a, s.cell, N, H, W, pitch, rows) && make_tmap(&tm_b, scratch_cell, N, H, W, pitch, rows);
   const long long threads = tiles > 32ll * N ? tiles : 32ll * N;
   tiled_sched_all_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p, s, inj, scratch_sched, TX, TY, fire, list,
                                                                           nactive, all_active);
   for (int j = 0; j < p.K; ++j) {
     if (tma)
-      ca_tiled_list_kernel<true><<<g_tile, T_THREADS, 0, st>>>(p, s, inj, tm, scratch_cell, scratch_sched, scratch_counts,
-                                                               out.stats, fire, list, nactive, j, pitch, TX, TY);
+      ca_tiled_list_kernel<true><<<g_tile, T_THREADS, 0, st>>>(p, s, inj, tm_a, tm_b, scratch_cell, scratch_sched,
+                                                               scratch_counts, out.stats, list, nactive, j, pitch, TX, TY);
     else
-      ca_tiled_list_kernel<false><<<g_tile, T_THREADS, 0, st>>>(p, s, inj, tm, scratch_cell, scratch_sched, scratch_counts,
-                                                                out.stats, fire, list, nactive, j, pitch, TX, TY);
-    tile_apply_list_kernel<<<g_apply, 128, 0, st>>>(N, H, W, TX, TY, list, nactive, j, scratch_cell, s.cell, fire,
-                                                    j + 1 < p.K ? 1 : 0, all_active);
+      ca_tiled_list_kernel<false><<<g_tile, T_THREADS, 0, st>>>(p, s, inj, tm_a, tm_b, scratch_cell, scratch_sched,
+                                                                scratch_counts, out.stats, list, nactive, j, pitch, TX, TY);
     if ((err = cudaGetLastError()) != cudaSuccess) return err;
   }
+  if (p.K & 1) tile_copy_back_kernel<<<g_tile, T_THREADS, 0, st>>>(H, W, TX, TY, list, nactive, scratch_cell, s.cell);
   tiled_finish_kernel<<<(N + 127) / 128, 128, 0, st>>>(p, s, actions, out, scratch_counts, flags);
   return cudaGetLastError();
 }
 
-// The 2 K + 3 launches of one env step as ONE CUDA graph launch: at 4096x4096 with a small fire the step is bound by
+// The K + 3 launches of one env step as ONE CUDA graph launch: at 4096x4096 with a small fire the step is bound by
 // launch latency.  The graph is captured once per set of
 // buffers (thread-local cache of one entry; a capture stream of its own: the caller's may be the legacy stream, which
 // cannot capture) and replayed with only the action pointer of the last kernel patched.  GCA_TILED_GRAPH=0 disables it.

@@ -561,15 +561,15 @@ class AdvancedForestFireBulldozerEnv(CAEnv):
 
     def _kernels_per_step(self, auto_reset: bool) -> int:
         """libgca kernels one env step launches: 64x64 -- the fused kernel; whole-grid bit-board grids (W % 64 == 0, up to
-        256x256) -- one kernel (+ the reset kernel); anything else -- the dense tile count, the key schedules + first
-        active-tile list, 2 per CA sub-step (tiles, copy-back + next list) and the epilogue, replayed as one CUDA graph
-        (+ the reset kernel)."""
+        256x256) -- one kernel (+ the reset kernel); anything else -- the dense tile count, the key schedules + the
+        step's tile list, one tile kernel per CA sub-step (+ a copy-back when their number is odd) and the epilogue,
+        replayed as one CUDA graph (+ the reset kernel)."""
         if self._state.work is not None:
             return 1
         H, W, R = self.nrows, self.ncols, int(self._params.R)
         bb = (W % 64 == 0 and W <= 256 and H <= 256 and H * W <= 65536 and 4 <= R <= 6
               and not (self._flags & _lib.FLAG_GENERIC_TILES))
-        return (1 if bb else 2 * self.substeps + 3) + (1 if auto_reset else 0)
+        return (1 if bb else self.substeps + 3 + (self.substeps & 1)) + (1 if auto_reset else 0)
 
     def _can_fuse_render(self) -> bool:
         """The step kernel draws the observation itself (GCA_FLAG_RENDER): 64x64 grids without extensions."""
