@@ -3,22 +3,26 @@
 //
 // Same rule, same lazy counter-based draws and the same enclosure / exact-fallback logic as the 64x64 kernel
 // (gca_step64.cu); what differs is the decomposition:
-//   * only tiles that can change are worked on.  Tile activity is a per-tile count of burning cells: counted ONCE per
-//     env step by a dense pass (tile_count_kernel, which also counts the env's tree / fire cells for the reward) and
-//     then maintained by the tile kernel itself (a tile's own CTA knows its new count).  A tile is ACTIVE when its 3x3
-//     tile neighbourhood holds fire (R <= 10 < the tile's extent, so nothing further away can ignite it), or always
-//     when regrowth is on.  Every sub-step works on a compact LIST of the active tiles with small fixed grids whose
-//     CTAs loop over the list (one 4096x4096 grid has 8192 tiles of which a young fire touches a dozen);
+//   * only tiles that can change are worked on.  A dense pass per ENV STEP (tile_count_kernel, a warp per tile; it also
+//     counts the env's tree / fire cells for the reward) counts the burning cells of every tile; the step's tile LIST
+//     holds the tiles within two tiles of one that holds fire -- fire moves one cell per sub-step, a tile is 32 x 64
+//     cells, so nothing else can become active during the K <= 8 sub-steps -- (with regrowth: every tile), and every
+//     sub-step is ONE launch of a small fixed grid whose CTAs loop over that list (one 4096x4096 grid has 8192 tiles
+//     of which a young fire touches a few dozen);
+//   * two grid buffers, S.cell and the scratch grid, are read and written alternately (sub-step j reads the tiles +
+//     halos from one and writes the tiles' new cells to the other: neighbouring tiles still read the old cells), so no
+//     copy-back pass separates the sub-steps; the ring of tiles around the list is copied into the scratch grid once
+//     (it is only ever read as halo); after an odd number of sub-steps the listed tiles are copied back;
 //   * tile + halo of the u8 grid is staged into shared memory -- by TMA (cp.async.bulk.tensor, 3-D map (W, H, N);
 //     out-of-bounds coordinates are zero-filled, which IS the reference's jnp.pad(constant_values=0) boundary,
 //     ca_alexandridis_jax.py:26) when W % 16 == 0, by plain bounds-checked loads otherwise -- and turned into tree /
 //     fire bit rows (warp ballots): front cells are found bit-parallel (a thread per tile row), the (2R+1)^2 heat
 //     window is nested box popcounts of those rows, the doused rows in reach are staged as 64-bit words;
-//   * front cells are processed one per thread: window sum -> enclosure -> per burning direction one threefry block
-//     addressed by the GLOBAL linear index ((r W + c) 9 + d), so results do not depend on the tiling;
-//   * active tiles write their new cells to the scratch grid (neighbouring tiles still read the old ones; only burning
-//     and igniting cells are looked at unless regrowth is on) and tile_apply_list_kernel copies them back -- and builds
-//     the next sub-step's list --, so S.cell is always the current grid; burn-out ticks are updated in place;
+//   * front cells in rounds of 256: a thread per cell computes the enclosure of the burn probability, the (cell,
+//     burning direction) draws are then dealt one per thread -- one threefry block addressed by the GLOBAL linear
+//     index ((r W + c) 9 + d), so results do not depend on the tiling;
+//   * write phase: unless regrowth is on only burning cells (burn-out tick reached?) and igniting cells (age draw) are
+//     looked at; the tile's interior leaves as 128-bit stores; burn-out ticks are updated in place (own cells only);
 //   * the key schedules of all K sub-steps come from one kernel (a warp per env, lane pairs per split), the per-env
 //     scalars (clock, move, douse, reward, done) from the epilogue kernel.
 // Reference lines as in gca_step64.cu.
