@@ -23,8 +23,8 @@
 //     index ((r W + c) 9 + d), so results do not depend on the tiling;
 //   * write phase: unless regrowth is on only burning cells (burn-out tick reached?) and igniting cells (age draw) are
 //     looked at; the tile's interior leaves as 128-bit stores; burn-out ticks are updated in place (own cells only);
-//   * the key schedules of all K sub-steps come from one kernel (a warp per env, lane pairs per split), the per-env
-//     scalars (clock, move, douse, reward, done) from the epilogue kernel.
+//   * the key schedules of all K sub-steps are walked by spare warps of the count kernel (a warp per env, lane pairs
+//     per split), the per-env scalars (clock, move, douse, reward, done) come from the epilogue kernel.
 // Reference lines as in gca_step64.cu.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -493,13 +493,134 @@ __device__ __forceinline__ int ca_tile_body(TileSmem& sm, const gca_params& P, c
   return fire_after;
 }
 
+// The tile list of an env step (built once, from the fire counts at its start).  A burning cell moves at most one cell
+// per sub-step and a tile is 32 x 64 cells, so for K <= 32 sub-steps every tile that can become active during the step
+// -- fire in its 3x3 tile neighbourhood at that time -- lies within Chebyshev tile distance 2 of a tile that holds fire
+// NOW: those tiles are listed for computation in every sub-step.  The ring at distance 3 is listed "copy only"
+// (T_COPY_ONLY): its tiles cannot change, but their cells are the halo of the computed tiles, which read the two grid
+// buffers alternately (see ca_tiled_list_kernel).  With regrowth every tile is computed.  All 32 lanes of a warp call.
+constexpr uint32_t T_COPY_ONLY = 0x80000000u;
+__device__ __forceinline__ void list_append(long long gid, long long total, int TX, int TY, const uint32_t* __restrict__ fire,
+                                            uint32_t* __restrict__ list, int* __restrict__ nactive, int all_active) {
+  int dist = 4;  // 4 = not listed
+  if (gid < total) {
+    if (all_active) dist = 0;
+    else {
+      const int tx = (int)(gid % TX), ty = (int)((gid / TX) % TY);
+      const uint32_t* f = fire + (gid - (long long)ty * TX - tx);  // the env's tile (0, 0)
+      for (int dy = -3; dy <= 3; ++dy) {
+        const int y = ty + dy;
+        if (y < 0 || y >= TY) continue;
+        for (int dx = -3; dx <= 3; ++dx) {
+          const int x = tx + dx;
+          if (x >= 0 && x < TX && f[y * TX + x] != 0u) dist = min(dist, max(abs(dx), abs(dy)));
+        }
+      }
+    }
+  }
+  const bool act = dist <= 3;
+  const uint32_t bal = __ballot_sync(GCA_FULL, act);
+  if (bal) {
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&nactive[0], __popc(bal));
+    base = __shfl_sync(GCA_FULL, base, 0);
+    if (act) list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)gid | (dist == 3 ? T_COPY_ONLY : 0u);
+  }
+}
+
+// The key schedules of ALL K sub-steps of env e by one warp (the 3K split levels of the key chain are sequential, a lane
+// pair runs the two blocks of a split; then lane pair 2j derives Sburn / Sgrow / the randint keys of sub-step j and pair
+// 2j+1 its wind draws, 4 more levels) into sched[e][j][12]; the env's key and wind index advance.
+__device__ __forceinline__ void tiled_sched_warp(const gca_params& P, const gca_state& S, const gca_inject& J, uint32_t* sched,
+                                                 int e, int lane) {
+  const int K = P.K, mode = P.rng_mode, N = S.N;
+  uint32_t* se = sched + (size_t)e * SC_N * GCA_MAX_K;
+  const int pair = lane >> 1, j = pair >> 1;
+  const uint32_t w = lane & 1;
+  const bool burn_role = (pair & 1) == 0;
+  uint32_t k0 = S.key[2 * e], k1 = S.key[2 * e + 1];
+  uint32_t c0 = 0, c1 = 0, sw0 = 0, sw1 = 0;  // burn role: S1 ; wind role: Sidx (c) and Swind (sw) of sub-step j
+  for (int q = 0; q < K; ++q) {
+    uint32_t n0, n1, s0, s1;
+    split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K1, S1
+    if (q == j && burn_role) { c0 = s0; c1 = s1; }
+    k0 = n0; k1 = n1;
+    split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K2, Swind
+    if (q == j && !burn_role) { sw0 = s0; sw1 = s1; }
+    k0 = n0; k1 = n1;
+    split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K3, Sidx
+    if (q == j && !burn_role) { c0 = s0; c1 = s1; }
+    k0 = n0; k1 = n1;
+  }
+  const uint32_t sc0 = (mode == GCA_RNG_LEGACY) ? w : 0u;  // split counters of this lane
+  const uint32_t sc1 = (mode == GCA_RNG_LEGACY) ? w + 2u : w;
+  uint32_t o0, o1, p0, p1, n0, n1, s0, s1;
+  // level 1: burn: split(S1) -> Ka, Sburn ; wind: split(Sidx) -> wk1, wk2
+  tf_exchange(c0, c1, sc0, sc1, o0, o1, p0, p1);
+  assemble_split(mode, w, o0, o1, p0, p1, n0, n1, s0, s1);
+  const uint32_t sburn0 = s0, sburn1 = s1;  // (wind role: wk2)
+  uint32_t cur0 = n0, cur1 = n1;            // burn: Ka ; wind: wk1
+  // level 2: burn: split(Ka) -> Kb, Sgrow ; wind: even lane bits(wk1, ()), odd lane bits(wk2, ())
+  tf_exchange(burn_role ? cur0 : (w ? sburn0 : cur0), burn_role ? cur1 : (w ? sburn1 : cur1), burn_role ? sc0 : 0u,
+              burn_role ? sc1 : 0u, o0, o1, p0, p1);
+  assemble_split(mode, w, o0, o1, p0, p1, n0, n1, s0, s1);
+  const uint32_t sgrow0 = s0, sgrow1 = s1;
+  const uint32_t my_bits = (mode == GCA_RNG_LEGACY) ? o0 : (o0 ^ o1);
+  const uint32_t pr_bits = (mode == GCA_RNG_LEGACY) ? p0 : (p0 ^ p1);
+  const uint32_t hb = w ? pr_bits : my_bits, lb = w ? my_bits : pr_bits;
+  cur0 = n0; cur1 = n1;  // burn: Kb
+  // level 3: burn: split(Kb) -> Kc, Sage ; wind: bits(Swind, ())
+  tf_exchange(burn_role ? cur0 : sw0, burn_role ? cur1 : sw1, burn_role ? sc0 : 0u, burn_role ? sc1 : 0u, o0, o1, p0, p1);
+  assemble_split(mode, w, o0, o1, p0, p1, n0, n1, s0, s1);
+  const uint32_t uw_bits = (mode == GCA_RNG_LEGACY) ? o0 : (o0 ^ o1);
+  // level 4: burn: split(Sage) -> ak1, ak2
+  tf_exchange(s0, s1, sc0, sc1, o0, o1, p0, p1);
+  uint32_t a10, a11, a20, a21;
+  assemble_split(mode, w, o0, o1, p0, p1, a10, a11, a20, a21);
+  if (j < K && w == 0) {
+    uint32_t* sc = se + j * SC_N;
+    if (burn_role) {
+      sc[SC_BURN0] = sburn0; sc[SC_BURN1] = sburn1; sc[SC_GROW0] = sgrow0; sc[SC_GROW1] = sgrow1;
+      sc[SC_AK10] = a10; sc[SC_AK11] = a11; sc[SC_AK20] = a20; sc[SC_AK21] = a21;
+    } else {
+      float u = bits_to_uniform(uw_bits);
+      int step = randint_from_bits(hb, lb, 1, 7u, 4u);
+      if (J.u_wind) u = J.u_wind[(size_t)j * N + e];
+      if (J.wind_step) step = J.wind_step[(size_t)j * N + e];
+      sc[9] = (u < P.p_wind_change) ? 1u : 0u;
+      sc[10] = (uint32_t)step;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {  // the wind index is threaded through the sub-steps; the chain's end is the env's new key
+    int wi = S.wind_index[e];
+    for (int q = 0; q < K; ++q) {
+      uint32_t* sc = se + q * SC_N;
+      sc[SC_WIND] = (uint32_t)wi;
+      if (sc[9]) wi = (wi + (int)sc[10]) % 8;
+    }
+    S.wind_index[e] = wi;
+    S.key[2 * e] = k0;
+    S.key[2 * e + 1] = k1;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // tile activity (see the head of the file)
 //   tile index t = (e * TY + ty) * TX + tx;  fire[t] u32;  list[] u32;  nactive[j] = entries of sub-step j's list
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tile_count_kernel(int N, int H, int W, int TX, int TY,
-                                                         const uint8_t* __restrict__ cell, uint32_t* __restrict__ fire,
-                                                         int32_t* __restrict__ counts) {
+__global__ void __launch_bounds__(256) tile_count_kernel(gca_params P, gca_state S, gca_inject J, uint32_t* sched, int TX,
+                                                         int TY, uint32_t* __restrict__ fire, int32_t* __restrict__ counts) {
+  const int N = S.N, H = P.H, W = P.W;
+  const uint8_t* __restrict__ cell = S.cell;
+  {
+    // the envs' key schedules ride along: the LAST N warps of the grid walk them first (16 dependent threefry levels,
+    // hidden behind the other warps' counting), so the step needs no schedule kernel
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (long long e = nw - 1 - gw; e < N; e += nw) tiled_sched_warp(P, S, J, sched, (int)e, threadIdx.x & 31);
+  }
   // a warp per tile: lane l reads 16 cells of rows (l >> 2) + 8 q, q = 0..3 -- four independent 128-bit loads in flight
   const int lane = threadIdx.x & 31;
   const long long total = (long long)N * TY * TX;
@@ -566,126 +687,13 @@ __global__ void __launch_bounds__(256) tile_count_kernel(int N, int H, int W, in
   }
 }
 
-// The tile list of an env step (built once, from the fire counts at its start).  A burning cell moves at most one cell
-// per sub-step and a tile is 32 x 64 cells, so for K <= 32 sub-steps every tile that can become active during the step
-// -- fire in its 3x3 tile neighbourhood at that time -- lies within Chebyshev tile distance 2 of a tile that holds fire
-// NOW: those tiles are listed for computation in every sub-step.  The ring at distance 3 is listed "copy only"
-// (T_COPY_ONLY): its tiles cannot change, but their cells are the halo of the computed tiles, which read the two grid
-// buffers alternately (see ca_tiled_list_kernel).  With regrowth every tile is computed.  All 32 lanes of a warp call.
-constexpr uint32_t T_COPY_ONLY = 0x80000000u;
-__device__ __forceinline__ void list_append(long long gid, long long total, int TX, int TY, const uint32_t* __restrict__ fire,
-                                            uint32_t* __restrict__ list, int* __restrict__ nactive, int all_active) {
-  int dist = 4;  // 4 = not listed
-  if (gid < total) {
-    if (all_active) dist = 0;
-    else {
-      const int tx = (int)(gid % TX), ty = (int)((gid / TX) % TY);
-      const uint32_t* f = fire + (gid - (long long)ty * TX - tx);  // the env's tile (0, 0)
-      for (int dy = -3; dy <= 3; ++dy) {
-        const int y = ty + dy;
-        if (y < 0 || y >= TY) continue;
-        for (int dx = -3; dx <= 3; ++dx) {
-          const int x = tx + dx;
-          if (x >= 0 && x < TX && f[y * TX + x] != 0u) dist = min(dist, max(abs(dx), abs(dy)));
-        }
-      }
-    }
-  }
-  const bool act = dist <= 3;
-  const uint32_t bal = __ballot_sync(GCA_FULL, act);
-  if (bal) {
-    const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&nactive[0], __popc(bal));
-    base = __shfl_sync(GCA_FULL, base, 0);
-    if (act) list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)gid | (dist == 3 ? T_COPY_ONLY : 0u);
-  }
+// the step's tile list (thread per tile), once the counts of tile_count_kernel are complete
+__global__ void __launch_bounds__(256) tile_list_kernel(int N, int TX, int TY, const uint32_t* __restrict__ fire,
+                                                        uint32_t* __restrict__ list, int* __restrict__ nactive, int all_active) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  list_append(gid, (long long)N * TY * TX, TX, TY, fire, list, nactive, all_active);
 }
 
-// Once per env step: the key schedules of ALL K sub-steps (a warp per env: the 3K split levels of the key chain are
-// sequential, a lane pair runs the two blocks of a split; then lane pair 2j derives Sburn / Sgrow / the randint keys of
-// sub-step j and pair 2j+1 its wind draws, 4 more levels) into sched[e][j][12], and the active-tile list of sub-step 0.
-__global__ void __launch_bounds__(256) tiled_sched_all_kernel(gca_params P, gca_state S, gca_inject J, uint32_t* sched,
-                                                              int TX, int TY, const uint32_t* __restrict__ fire,
-                                                              uint32_t* __restrict__ list, int* __restrict__ nactive,
-                                                              int all_active) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long gwarp = gid >> 5;
-  const int lane = threadIdx.x & 31;
-  if (gwarp < S.N) {
-    const int e = (int)gwarp, K = P.K, mode = P.rng_mode, N = S.N;
-    uint32_t* se = sched + (size_t)e * SC_N * GCA_MAX_K;
-    const int pair = lane >> 1, j = pair >> 1;
-    const uint32_t w = lane & 1;
-    const bool burn_role = (pair & 1) == 0;
-    uint32_t k0 = S.key[2 * e], k1 = S.key[2 * e + 1];
-    uint32_t c0 = 0, c1 = 0, sw0 = 0, sw1 = 0;  // burn role: S1 ; wind role: Sidx (c) and Swind (sw) of sub-step j
-    for (int q = 0; q < K; ++q) {
-      uint32_t n0, n1, s0, s1;
-      split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K1, S1
-      if (q == j && burn_role) { c0 = s0; c1 = s1; }
-      k0 = n0; k1 = n1;
-      split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K2, Swind
-      if (q == j && !burn_role) { sw0 = s0; sw1 = s1; }
-      k0 = n0; k1 = n1;
-      split_pair(k0, k1, mode, lane, n0, n1, s0, s1);  // K3, Sidx
-      if (q == j && !burn_role) { c0 = s0; c1 = s1; }
-      k0 = n0; k1 = n1;
-    }
-    const uint32_t sc0 = (mode == GCA_RNG_LEGACY) ? w : 0u;  // split counters of this lane
-    const uint32_t sc1 = (mode == GCA_RNG_LEGACY) ? w + 2u : w;
-    uint32_t o0, o1, p0, p1, n0, n1, s0, s1;
-    // level 1: burn: split(S1) -> Ka, Sburn ; wind: split(Sidx) -> wk1, wk2
-    tf_exchange(c0, c1, sc0, sc1, o0, o1, p0, p1);
-    assemble_split(mode, w, o0, o1, p0, p1, n0, n1, s0, s1);
-    const uint32_t sburn0 = s0, sburn1 = s1;  // (wind role: wk2)
-    uint32_t cur0 = n0, cur1 = n1;            // burn: Ka ; wind: wk1
-    // level 2: burn: split(Ka) -> Kb, Sgrow ; wind: even lane bits(wk1, ()), odd lane bits(wk2, ())
-    tf_exchange(burn_role ? cur0 : (w ? sburn0 : cur0), burn_role ? cur1 : (w ? sburn1 : cur1), burn_role ? sc0 : 0u,
-                burn_role ? sc1 : 0u, o0, o1, p0, p1);
-    assemble_split(mode, w, o0, o1, p0, p1, n0, n1, s0, s1);
-    const uint32_t sgrow0 = s0, sgrow1 = s1;
-    const uint32_t my_bits = (mode == GCA_RNG_LEGACY) ? o0 : (o0 ^ o1);
-    const uint32_t pr_bits = (mode == GCA_RNG_LEGACY) ? p0 : (p0 ^ p1);
-    const uint32_t hb = w ? pr_bits : my_bits, lb = w ? my_bits : pr_bits;
-    cur0 = n0; cur1 = n1;  // burn: Kb
-    // level 3: burn: split(Kb) -> Kc, Sage ; wind: bits(Swind, ())
-    tf_exchange(burn_role ? cur0 : sw0, burn_role ? cur1 : sw1, burn_role ? sc0 : 0u, burn_role ? sc1 : 0u, o0, o1, p0, p1);
-    assemble_split(mode, w, o0, o1, p0, p1, n0, n1, s0, s1);
-    const uint32_t uw_bits = (mode == GCA_RNG_LEGACY) ? o0 : (o0 ^ o1);
-    // level 4: burn: split(Sage) -> ak1, ak2
-    tf_exchange(s0, s1, sc0, sc1, o0, o1, p0, p1);
-    uint32_t a10, a11, a20, a21;
-    assemble_split(mode, w, o0, o1, p0, p1, a10, a11, a20, a21);
-    if (j < K && w == 0) {
-      uint32_t* sc = se + j * SC_N;
-      if (burn_role) {
-        sc[SC_BURN0] = sburn0; sc[SC_BURN1] = sburn1; sc[SC_GROW0] = sgrow0; sc[SC_GROW1] = sgrow1;
-        sc[SC_AK10] = a10; sc[SC_AK11] = a11; sc[SC_AK20] = a20; sc[SC_AK21] = a21;
-      } else {
-        float u = bits_to_uniform(uw_bits);
-        int step = randint_from_bits(hb, lb, 1, 7u, 4u);
-        if (J.u_wind) u = J.u_wind[(size_t)j * N + e];
-        if (J.wind_step) step = J.wind_step[(size_t)j * N + e];
-        sc[9] = (u < P.p_wind_change) ? 1u : 0u;
-        sc[10] = (uint32_t)step;
-      }
-    }
-    __syncwarp();
-    if (lane == 0) {  // the wind index is threaded through the sub-steps; the chain's end is the env's new key
-      int wi = S.wind_index[e];
-      for (int q = 0; q < K; ++q) {
-        uint32_t* sc = se + q * SC_N;
-        sc[SC_WIND] = (uint32_t)wi;
-        if (sc[9]) wi = (wi + (int)sc[10]) % 8;
-      }
-      S.wind_index[e] = wi;
-      S.key[2 * e] = k0;
-      S.key[2 * e + 1] = k1;
-    }
-  }
-  list_append(gid, (long long)S.N * TY * TX, TX, TY, fire, list, nactive, all_active);
-}
 
 // One CA sub-step of every listed tile.  The grid lives in two buffers, A = S.cell and B = the scratch grid: sub-step j
 // reads tiles + halos from one (A when j is even) and writes the tiles' new cells to the other, so no copy-back pass
@@ -832,14 +840,12 @@ static cudaError_t enqueue_tiled_env_step(const gca_params& p, const gca_state& 
   }
   const int g_count = (int)((tiles + 7) / 8 < (long long)sms * 4 ? (tiles + 7) / 8 : (long long)sms * 4);  // 8 warps per CTA, a warp per tile
   const int g_tile = (int)(tiles < (long long)sms * 4 ? tiles : (long long)sms * 4);
-  tile_count_kernel<<<g_count, 256, 0, st>>>(N, H, W, TX, TY, s.cell, fire, scratch_counts);
+  tile_count_kernel<<<g_count, 256, 0, st>>>(p, s, inj, scratch_sched, TX, TY, fire, scratch_counts);
   CUtensorMap tm_a, tm_b;
   memset(&tm_a, 0, sizeof(tm_a));
   memset(&tm_b, 0, sizeof(tm_b));
   const bool tma = use_tma && make_tmap(&tm_a, s.cell, N, H, W, pitch, rows) && make_tmap(&tm_b, scratch_cell, N, H, W, pitch, rows);
-  const long long threads = tiles > 32ll * N ? tiles : 32ll * N;
-  tiled_sched_all_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p, s, inj, scratch_sched, TX, TY, fire, list,
-                                                                          nactive, all_active);
+  tile_list_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(N, TX, TY, fire, list, nactive, all_active);
   for (int j = 0; j < p.K; ++j) {
     if (tma)
       ca_tiled_list_kernel<true><<<g_tile, T_THREADS, 0, st>>>(p, s, inj, tm_a, tm_b, scratch_cell, scratch_sched,

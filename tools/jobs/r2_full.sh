@@ -10,7 +10,7 @@ d=json.load(open("gpurun_out/r2_bench_e.json"))
 print("bench: us/step %.2f value %.3e frac %.3f e2e %.3e (%.1f us) warm %.3e window/longrun %.3f launches %d" % (d["ms_per_step"]*1e3, d["value"], d["roofline"]["frac"], d["e2e"]["value"], d["e2e"]["us_per_step"], d["value_l2_warm"], d["workload_stats"]["long_run"]["timed_window_over_long_run"], d["gpu_launches"]))
 print(d["step_us"]["series"])
 print({k: round(v["us_per_step"],1) for k,v in d["with_observation"].items()})
-for o in d.get("other_configs", []): print(o["workload"][:40], "us/step %.1f value %.3e frac %.3f launches/step %.1f" % (o["us_per_step"], o["value"], o["roofline"]["frac"], o["launches_per_step"]))
+for o in [x for x in d.get("other_configs", []) if "roofline" in x]: print(o["workload"][:40], "us/step %.1f value %.3e frac %.3f launches/step %.1f" % (o["us_per_step"], o["value"], o["roofline"]["frac"], o["launches_per_step"]))
 print(d.get("cpu_baseline"))
 r=json.load(open("gpurun_out/r2_ref_e.json")); print("reference arm:", r["value"], r["config"].get("cpu_sample_envs_per_step"))
 PY
