@@ -500,21 +500,27 @@ __device__ __forceinline__ int ca_tile_body(TileSmem& sm, const gca_params& P, c
 // (T_COPY_ONLY): its tiles cannot change, but their cells are the halo of the computed tiles, which read the two grid
 // buffers alternately (see ca_tiled_list_kernel).  With regrowth every tile is computed.  All 32 lanes of a warp call.
 constexpr uint32_t T_COPY_ONLY = 0x80000000u;
-__device__ __forceinline__ void list_append(long long gid, long long total, int TX, int TY, const uint32_t* __restrict__ fire,
+__device__ __forceinline__ void list_append(long long gid, long long total, int TX, int TY, const uint32_t* __restrict__ hasfire,
                                             uint32_t* __restrict__ list, int* __restrict__ nactive, int all_active) {
   int dist = 4;  // 4 = not listed
   if (gid < total) {
     if (all_active) dist = 0;
     else {
+      // `hasfire`: one bit per tile (set by tile_count_kernel), tile t = bit t & 31 of word t >> 5; the 7 x 7 tile
+      // neighbourhood is 7 bit fields of up to 7 bits
       const int tx = (int)(gid % TX), ty = (int)((gid / TX) % TY);
-      const uint32_t* f = fire + (gid - (long long)ty * TX - tx);  // the env's tile (0, 0)
+      const long long env0 = gid - (long long)ty * TX - tx;  // the env's tile (0, 0)
+      const int x0 = max(tx - 3, 0), x1 = min(tx + 3, TX - 1), n = x1 - x0 + 1;
       for (int dy = -3; dy <= 3; ++dy) {
         const int y = ty + dy;
         if (y < 0 || y >= TY) continue;
-        for (int dx = -3; dx <= 3; ++dx) {
-          const int x = tx + dx;
-          if (x >= 0 && x < TX && f[y * TX + x] != 0u) dist = min(dist, max(abs(dx), abs(dy)));
-        }
+        const long long p = env0 + (long long)y * TX + x0;
+        const int sh = (int)(p & 31);
+        const uint32_t lo = hasfire[p >> 5], hi = sh + n > 32 ? hasfire[(p >> 5) + 1] : 0u;
+        const uint32_t bits = (__funnelshift_r(lo, hi, sh) & ((1u << n) - 1u)) << (x0 - (tx - 3));  // bit k <-> dx = k - 3
+        if (!bits) continue;
+        const int mdx = (bits & 0x08u) ? 0 : ((bits & 0x14u) ? 1 : ((bits & 0x22u) ? 2 : 3));
+        dist = min(dist, max(mdx, abs(dy)));
       }
     }
   }
@@ -611,7 +617,7 @@ __device__ __forceinline__ void tiled_sched_warp(const gca_params& P, const gca_
 //   tile index t = (e * TY + ty) * TX + tx;  fire[t] u32;  list[] u32;  nactive[j] = entries of sub-step j's list
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tile_count_kernel(gca_params P, gca_state S, gca_inject J, uint32_t* sched, int TX,
-                                                         int TY, uint32_t* __restrict__ fire, int32_t* __restrict__ counts) {
+                                                         int TY, uint32_t* __restrict__ hasfire, int32_t* __restrict__ counts) {
   const int N = S.N, H = P.H, W = P.W;
   const uint8_t* __restrict__ cell = S.cell;
   {
@@ -668,7 +674,7 @@ __global__ void __launch_bounds__(256) tile_count_kernel(gca_params P, gca_state
     nt = __reduce_add_sync(GCA_FULL, nt);
     nf = __reduce_add_sync(GCA_FULL, nf);
     if (lane == 0) {
-      fire[t] = (uint32_t)nf;
+      if (nf) atomicOr(&hasfire[t >> 5], 1u << (t & 31));
       if (e == e_cta) { acc_t += nt; acc_f += nf; }  // (thousands of tiles of one env: no global atomic per tile)
       else {
         if (nt) atomicAdd(&counts[2 * e], nt);
@@ -688,10 +694,10 @@ __global__ void __launch_bounds__(256) tile_count_kernel(gca_params P, gca_state
 }
 
 // the step's tile list (thread per tile), once the counts of tile_count_kernel are complete
-__global__ void __launch_bounds__(256) tile_list_kernel(int N, int TX, int TY, const uint32_t* __restrict__ fire,
+__global__ void __launch_bounds__(256) tile_list_kernel(int N, int TX, int TY, const uint32_t* __restrict__ hasfire,
                                                         uint32_t* __restrict__ list, int* __restrict__ nactive, int all_active) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  list_append(gid, (long long)N * TY * TX, TX, TY, fire, list, nactive, all_active);
+  list_append(gid, (long long)N * TY * TX, TX, TY, hasfire, list, nactive, all_active);
 }
 
 
@@ -751,29 +757,42 @@ __global__ void tiled_finish_kernel(gca_params P, gca_state S, const int32_t* __
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= S.N) return;
   const int WW = (P.W + 63) >> 6;
-  S.tick[e] += (uint32_t)P.K;
+  const bool full = !(flags & GCA_FLAG_CA_ONLY);
+  // every load first (independent, one DRAM round trip), the stores after: as written in program order the compiler must
+  // keep each load behind the preceding store (they may alias), which makes the kernel a chain of cold misses
+  const uint32_t tick = S.tick[e];
   const int t = counts[2 * e], f = counts[2 * e + 1];
+  int a0 = 4, a1 = 0, row = 0, col = 0, ts = 0, night = 0;
+  float tm = 0.0f, se = 0.0f, ra = 0.0f;
+  if (full) {
+    a0 = actions[3 * e]; a1 = actions[3 * e + 1];
+    tm = S.time[e];
+    row = S.position[2 * e]; col = S.position[2 * e + 1];
+    ts = S.time_step[e];
+    night = S.is_night[e];
+    if (S.steps_elapsed) se = S.steps_elapsed[e];
+    if (S.reward_accumulated) ra = S.reward_accumulated[e];
+  }
+  S.tick[e] = tick + (uint32_t)P.K;
   const float rew = award(t, f);
   const bool done = f == 0;
-  if (!(flags & GCA_FLAG_CA_ONLY)) {
-    const int a0 = actions[3 * e], a1 = actions[3 * e + 1];
+  if (full) {
     const int a0c = min(max(a0, 0), 8), a1c = min(max(a1, 0), 1);
     const float tt = __fadd_rn(__fadd_rn(P.t_move[a0c], P.t_shoot[a1c]), P.t_any);
-    const float ntm = __fadd_rn(S.time[e], tt);
+    const float ntm = __fadd_rn(tm, tt);
     S.time[e] = __fsub_rn(ntm, truncf(ntm));
-    int row = S.position[2 * e], col = S.position[2 * e + 1];
     move_position(a0, P.H, P.W, row, col);
     S.position[2 * e] = row;
     S.position[2 * e + 1] = col;
-    if (a1 == 1) S.doused[((size_t)e * P.H + row) * WW + (col >> 6)] |= 1ull << (col & 63);
-    const int ts = S.time_step[e] + 1;
+    if (a1 == 1)
+      atomicOr(reinterpret_cast<unsigned long long*>(S.doused) + ((size_t)e * P.H + row) * WW + (col >> 6), 1ull << (col & 63));
+    ts += 1;
     S.time_step[e] = ts;
-    int night = S.is_night[e];
     if (O.obs_night) O.obs_night[e] = (uint8_t)night;
     if (ts % P.day_length == 0) night = 1 - night;
     S.is_night[e] = night;
-    if (S.steps_elapsed) S.steps_elapsed[e] = __fadd_rn(S.steps_elapsed[e], 1.0f);
-    if (S.reward_accumulated) S.reward_accumulated[e] = __fadd_rn(S.reward_accumulated[e], rew);
+    if (S.steps_elapsed) S.steps_elapsed[e] = __fadd_rn(se, 1.0f);
+    if (S.reward_accumulated) S.reward_accumulated[e] = __fadd_rn(ra, rew);
   }
   if (O.step_reward) O.step_reward[e] = rew;
   if (O.reward) O.reward[e] = rew;
@@ -812,7 +831,7 @@ static bool make_tmap(CUtensorMap* m, const uint8_t* base, int N, int H, int W, 
 
 // One env step: one clear, one dense count, the key schedules of all sub-steps + the step's tile list, then ONE kernel
 // with a small fixed grid per sub-step (+ a copy-back when K is odd) and the epilogue.  Layout of `aux` (words):
-// nactive[16] | fire[tiles] | list[tiles] (+ tiles spare),
+// nactive[16] | hasfire[tiles / 32 + 1] (one bit per tile) | list[tiles],
 // with nactive directly behind the counts so that one clear covers both.
 static cudaError_t enqueue_tiled_env_step(const gca_params& p, const gca_state& s, const int32_t* actions,
                                                  const gca_step_out& out, const gca_inject& inj, uint32_t flags,
@@ -826,12 +845,13 @@ static cudaError_t enqueue_tiled_env_step(const gca_params& p, const gca_state& 
   const long long tiles = (long long)N * TX * TY;
   if (tiles >= (1ll << 31)) return cudaErrorInvalidValue;
   int* nactive = reinterpret_cast<int*>(aux);
-  uint32_t* fire = aux + 16;
-  uint32_t* list = fire + tiles;
+  const long long bw = (tiles + 31) / 32 + 1;   // words of the one-bit-per-tile "holds fire" map
+  uint32_t* hasfire = aux + 16;
+  uint32_t* list = hasfire + bw;
   if (reinterpret_cast<int32_t*>(nactive) != scratch_counts + 2 * (size_t)N) return cudaErrorInvalidValue;
   cudaError_t err;
   const int all_active = p.p_tree > 0.0f ? 1 : 0;  // regrowth can change any empty cell
-  if ((err = cudaMemsetAsync(scratch_counts, 0, sizeof(int32_t) * (2 * (size_t)N + 16), st)) != cudaSuccess) return err;
+  if ((err = cudaMemsetAsync(scratch_counts, 0, sizeof(int32_t) * (2 * (size_t)N + 16 + (size_t)bw), st)) != cudaSuccess) return err;
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -840,12 +860,12 @@ static cudaError_t enqueue_tiled_env_step(const gca_params& p, const gca_state& 
   }
   const int g_count = (int)((tiles + 7) / 8 < (long long)sms * 4 ? (tiles + 7) / 8 : (long long)sms * 4);  // 8 warps per CTA, a warp per tile
   const int g_tile = (int)(tiles < (long long)sms * 4 ? tiles : (long long)sms * 4);
-  tile_count_kernel<<<g_count, 256, 0, st>>>(p, s, inj, scratch_sched, TX, TY, fire, scratch_counts);
+  tile_count_kernel<<<g_count, 256, 0, st>>>(p, s, inj, scratch_sched, TX, TY, hasfire, scratch_counts);
   CUtensorMap tm_a, tm_b;
   memset(&tm_a, 0, sizeof(tm_a));
   memset(&tm_b, 0, sizeof(tm_b));
   const bool tma = use_tma && make_tmap(&tm_a, s.cell, N, H, W, pitch, rows) && make_tmap(&tm_b, scratch_cell, N, H, W, pitch, rows);
-  tile_list_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(N, TX, TY, fire, list, nactive, all_active);
+  tile_list_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(N, TX, TY, hasfire, list, nactive, all_active);
   for (int j = 0; j < p.K; ++j) {
     if (tma)
       ca_tiled_list_kernel<true><<<g_tile, T_THREADS, 0, st>>>(p, s, inj, tm_a, tm_b, scratch_cell, scratch_sched,
