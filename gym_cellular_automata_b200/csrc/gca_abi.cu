@@ -33,7 +33,8 @@ cudaError_t launch_windy_pack(int, int, int, const uint8_t*, unsigned long long*
 cudaError_t launch_windy_unpack(int, int, int, const unsigned long long*, const unsigned long long*, uint8_t*,
                                 cudaStream_t);
 cudaError_t launch_tiled_env_step(const gca_params&, const gca_state&, const int32_t*, const gca_step_out&,
-                                  const gca_inject&, uint32_t, uint8_t*, uint32_t*, int32_t*, uint8_t*, int, cudaStream_t);
+                                  const gca_inject&, uint32_t, uint8_t*, uint32_t*, int32_t*, uint8_t*, int, const gca_state*,
+                                  const float*, cudaStream_t);
 cudaError_t launch_auto_reset(const gca_params&, const gca_state&, const gca_state&, const float*, float*,
                               const uint8_t*, cudaStream_t);
 bool bb_supported(const gca_params&);
@@ -198,15 +199,19 @@ static int env_step_impl(const gca_params* p, const gca_state* s, const int32_t*
     // grids of whole 64-bit words up to 256x256: one launch per env step, the grid as bit-boards in shared memory
     rc = check_cuda(gca::launch_bb_env_step(*p, st, actions, o, j, flags, (cudaStream_t)stream), "env_step_bb");
   } else {
-    // any other grid: generic tiled kernels (active-tile lists), 2 per CA sub-step + 3, replayed as one CUDA graph
+    // any other grid: generic tiled kernels (a tile list per env step), one per CA sub-step + 3, replayed as one CUDA
+    // graph -- the fused conditional_reset included
     if (((long long)p->H * p->W) & 1) return fail(GCA_ERR_UNSUPPORTED, "gca_env_step: H*W must be even");
     if (!s->scratch_cell || !s->scratch_u32)
       return fail(GCA_ERR_ARG, "gca_env_step: grids other than 64x64 need scratch_cell and scratch_u32");
-    rc = check_cuda(gca::launch_tiled_env_step(*p, st, actions, o, j, flags, s->scratch_cell, s->scratch_u32,
-                                               reinterpret_cast<int32_t*>(s->scratch_u32) + 12 * GCA_MAX_K * (size_t)s->N,
-                                               reinterpret_cast<uint8_t*>(s->scratch_u32 + (12 * GCA_MAX_K + 2) * (size_t)s->N),
-                                               (flags & GCA_FLAG_NO_TMA) ? 0 : 1, (cudaStream_t)stream),
-                    "env_step_tiled");
+    const bool reset = (flags & GCA_FLAG_AUTO_RESET) != 0;
+    if (reset && !o.terminated) return fail(GCA_ERR_ARG, "gca_env_step: auto-reset on the tiled path needs out->terminated");
+    return check_cuda(gca::launch_tiled_env_step(*p, st, actions, o, j, flags, s->scratch_cell, s->scratch_u32,
+                                                 reinterpret_cast<int32_t*>(s->scratch_u32) + 12 * GCA_MAX_K * (size_t)s->N,
+                                                 reinterpret_cast<uint8_t*>(s->scratch_u32 + (12 * GCA_MAX_K + 2) * (size_t)s->N),
+                                                 (flags & GCA_FLAG_NO_TMA) ? 0 : 1, reset ? &sn : nullptr, snapshot_reward,
+                                                 (cudaStream_t)stream),
+                      "env_step_tiled");
   }
   if (rc) return rc;
   if (flags & GCA_FLAG_AUTO_RESET) {

@@ -35,6 +35,9 @@
 
 namespace gca {
 
+cudaError_t launch_auto_reset(const gca_params&, const gca_state&, const gca_state&, const float*, float*, const uint8_t*,
+                              cudaStream_t);  // gca_aux.cu
+
 constexpr int T_TH = 32, T_TW = 64, T_THREADS = 256;
 constexpr int T_MAXR = GCA_MAX_R;
 constexpr int T_HC = 16;                              // column halo: TMA needs the box start 16-byte aligned,
@@ -836,7 +839,8 @@ static bool make_tmap(CUtensorMap* m, const uint8_t* base, int N, int H, int W, 
 static cudaError_t enqueue_tiled_env_step(const gca_params& p, const gca_state& s, const int32_t* actions,
                                                  const gca_step_out& out, const gca_inject& inj, uint32_t flags,
                                           uint8_t* scratch_cell, uint32_t* scratch_sched, int32_t* scratch_counts,
-                                          uint8_t* aux8, int use_tma, cudaStream_t st) {
+                                          uint8_t* aux8, int use_tma, const gca_state* snap, const float* snap_reward,
+                                          cudaStream_t st) {
   uint32_t* aux = reinterpret_cast<uint32_t*>(aux8);
   const int N = s.N, H = p.H, W = p.W, R = p.R;
   const int pitch = T_PITCH_MAX;
@@ -877,7 +881,10 @@ static cudaError_t enqueue_tiled_env_step(const gca_params& p, const gca_state& 
   }
   if (p.K & 1) tile_copy_back_kernel<<<g_tile, T_THREADS, 0, st>>>(H, W, TX, TY, list, nactive, scratch_cell, s.cell);
   tiled_finish_kernel<<<(N + 127) / 128, 128, 0, st>>>(p, s, actions, out, scratch_counts, flags);
-  return cudaGetLastError();
+  if ((err = cudaGetLastError()) != cudaSuccess) return err;
+  // the fused conditional_reset rides in the same graph
+  if (snap != nullptr) return launch_auto_reset(p, s, *snap, snap_reward, out.reward, out.terminated, st);
+  return cudaSuccess;
 }
 
 // The K + 3 launches of one env step as ONE CUDA graph launch: at 4096x4096 with a small fire the step is bound by
@@ -887,6 +894,7 @@ static cudaError_t enqueue_tiled_env_step(const gca_params& p, const gca_state& 
 namespace {
 struct TiledGraphKey {
   gca_params p; gca_state s; gca_step_out out; uint32_t flags; const void *a, *b, *c, *d; int use_tma;
+  gca_state snap; const void* snap_reward; int has_snap;
 };
 struct TiledGraphCache {
   bool valid = false, broken = false;
@@ -902,24 +910,25 @@ thread_local TiledGraphCache g_tiled_graph;
 cudaError_t launch_tiled_env_step(const gca_params& p, const gca_state& s, const int32_t* actions,
                                   const gca_step_out& out, const gca_inject& inj, uint32_t flags, uint8_t* scratch_cell,
                                   uint32_t* scratch_sched, int32_t* scratch_counts, uint8_t* tile_flags, int use_tma,
-                                  cudaStream_t st) {
+                                  const gca_state* snap, const float* snap_reward, cudaStream_t st) {
   static const bool enabled = [] { const char* v = getenv("GCA_TILED_GRAPH"); return !(v && v[0] == '0'); }();
   TiledGraphCache& G = g_tiled_graph;
   const bool injected = inj.u_burn || inj.u_grow || inj.age_new || inj.u_wind || inj.wind_step;
   if (!enabled || G.broken || injected)
     return enqueue_tiled_env_step(p, s, actions, out, inj, flags, scratch_cell, scratch_sched, scratch_counts, tile_flags,
-                                  use_tma, st);
+                                  use_tma, snap, snap_reward, st);
   TiledGraphKey key;
   memset(&key, 0, sizeof(key));
   key.p = p; key.s = s; key.out = out; key.flags = flags;
   key.out.done_token = 0; key.out.rgb = nullptr; key.out.rgb_u8 = 0;  // per-step values no tiled kernel reads
   key.out.host_done = nullptr; key.out.done_counter = nullptr;
   key.a = scratch_cell; key.b = scratch_sched; key.c = scratch_counts; key.d = tile_flags; key.use_tma = use_tma;
+  if (snap != nullptr) { key.snap = *snap; key.snap_reward = snap_reward; key.has_snap = 1; }
   auto fallback = [&]() {
     G.broken = true;
     cudaGetLastError();
     return enqueue_tiled_env_step(p, s, actions, out, inj, flags, scratch_cell, scratch_sched, scratch_counts, tile_flags,
-                                  use_tma, st);
+                                  use_tma, snap, snap_reward, st);
   };
   if (!G.valid || memcmp(&G.key, &key, sizeof(key)) != 0) {
     if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
@@ -928,7 +937,7 @@ cudaError_t launch_tiled_env_step(const gca_params& p, const gca_state& s, const
     if (!G.cap && cudaStreamCreateWithFlags(&G.cap, cudaStreamNonBlocking) != cudaSuccess) return fallback();
     if (cudaStreamBeginCapture(G.cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return fallback();
     const cudaError_t e1 = enqueue_tiled_env_step(p, s, actions, out, inj, flags, scratch_cell, scratch_sched, scratch_counts,
-                                                  tile_flags, use_tma, G.cap);
+                                                  tile_flags, use_tma, snap, snap_reward, G.cap);
     const cudaError_t e2 = cudaStreamEndCapture(G.cap, &G.graph);
     if (e1 != cudaSuccess || e2 != cudaSuccess || !G.graph) return fallback();
     size_t nn = 0;
