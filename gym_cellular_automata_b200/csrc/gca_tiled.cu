@@ -47,7 +47,7 @@ constexpr int T_ROWS_MAX = T_TH + 2 * T_MAXR;         // 52
 #define T_LO 0.9998779296875f  /* 1 - 2^-13: (2R+1)^2 <= 441 terms -> |err| <= 441 u |sum| */
 #define T_HI 1.0001220703125f  /* 1 + 2^-13 */
 
-// sched[e][*] written by tiled_sched_kernel for the current sub-step
+// sched[e][j][*] of env e, sub-step j (written by tiled_sched_warp)
 enum { SC_BURN0 = 0, SC_BURN1, SC_GROW0, SC_GROW1, SC_AK10, SC_AK11, SC_AK20, SC_AK21, SC_WIND, SC_N = 12 };
 
 struct TileSmem {
@@ -55,7 +55,7 @@ struct TileSmem {
   uint16_t list[T_TH * T_TW];                            // front cells of the tile: (lr << 6) | lc
   unsigned long long ign[T_TH];                          // cells of the tile that ignite this sub-step (bit = column)
   uint32_t tbits[T_ROWS_MAX][4];                         // tree bit-board of tile + halo (see fbits)
-  int nlist2, n_ign, n_ext;                              // change-candidate list of the write phase, its counters
+  int nlist2;                                            // entries of the write phase's change-candidate list
   float2 bnd[T_THREADS];                                 // per front cell of the round: enclosure (lo, hi), direction-independent part
   uint16_t pairs[T_THREADS * 8];                         // draws of the round: (front cell of the round << 4) | direction
   int npairs[2];                                         // their number, double-buffered by round parity
@@ -65,30 +65,10 @@ struct TileSmem {
   alignas(8) unsigned long long mbar;
   int nfront;
   int cnt_tree, cnt_fire;
-  int fire_abs;   // burning cells of the tile after the sub-step
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// 5x5 dousing window of (r, c) from the global bit-board: bit (5 i + j) <-> (r-2+i, c-2+j)
-__device__ __forceinline__ uint32_t dous_window_g(const unsigned long long* __restrict__ db, int H, int W, int WW,
-                                                  int r, int c) {
-  uint32_t v = 0;
-  for (int i = 0; i < 5; ++i) {
-    const int rr = r - 2 + i;
-    if (rr < 0 || rr >= H) continue;
-    const unsigned long long* row = db + (size_t)rr * WW;
-    for (int j = 0; j < 5; ++j) {
-      const int cc = c - 2 + j;
-      if (cc < 0 || cc >= W) continue;
-      v |= (uint32_t)((row[cc >> 6] >> (cc & 63)) & 1ull) << (5 * i + j);
-    }
-  }
-  return v;
-}
-
-// One CA sub-step of tile (e, ty, tx) by the whole CTA (`it` = how many tiles this CTA has staged before: the parity of
-// the TMA barrier's phase).  Returns (to thread 0) the number of burning cells the tile holds afterwards.
 // copies tile (e, ty, tx) from one grid buffer to the other (first 128 threads of the CTA)
 __device__ __forceinline__ void copy_tile(int H, int W, int e, int ty, int tx, const uint8_t* __restrict__ src,
                                           uint8_t* __restrict__ dst) {
@@ -119,8 +99,10 @@ __device__ __forceinline__ uint32_t tile_dous_window(const TileSmem& sm, int lr,
   return dwin;
 }
 
+// One CA sub-step of tile (e, ty, tx) by the whole CTA: staged from `cell_in` (TMA map `tmap`), new cells to `cell_out`
+// (`it` = how many tiles this CTA has staged before: the parity of the TMA barrier's phase).
 template <bool USE_TMA>
-__device__ __forceinline__ int ca_tile_body(TileSmem& sm, const gca_params& P, const gca_state& S, const gca_inject& J,
+__device__ __forceinline__ void ca_tile_body(TileSmem& sm, const gca_params& P, const gca_state& S, const gca_inject& J,
                                             const CUtensorMap* tmap, const uint8_t* __restrict__ cell_in,
                                             uint8_t* __restrict__ cell_out, const uint32_t* __restrict__ sched,
                                             int32_t* __restrict__ counts, unsigned long long* stats, int substep, int pitch,
@@ -133,7 +115,7 @@ __device__ __forceinline__ int ca_tile_body(TileSmem& sm, const gca_params& P, c
   const size_t env_off = (size_t)e * H * W;
   const int win = 2 * R + 1;
 
-  if (tid == 0) { sm.nfront = 0; sm.cnt_tree = 0; sm.cnt_fire = 0; sm.fire_abs = 0; sm.any_doused = 0; }
+  if (tid == 0) { sm.nfront = 0; sm.cnt_tree = 0; sm.cnt_fire = 0; sm.any_doused = 0; }
   // doused rows within the 5x5 window's reach of the tile (requested before the tile is staged)
   unsigned long long dword = 0ull;
   if (tid < (T_TH + 4) * 3) {
@@ -198,7 +180,7 @@ __device__ __forceinline__ int ca_tile_body(TileSmem& sm, const gca_params& P, c
     }
   }
   if (tid < T_TH) sm.ign[tid] = 0ull;
-  if (tid == 0) { sm.nlist2 = 0; sm.n_ign = 0; sm.n_ext = 0; sm.npairs[0] = 0; sm.npairs[1] = 0; }
+  if (tid == 0) { sm.nlist2 = 0; sm.npairs[0] = 0; sm.npairs[1] = 0; }
   __syncthreads();
   const uint32_t* sc = sched + (size_t)e * sched_env_stride + sched_off;
   const uint32_t tick = S.tick[e] + (uint32_t)substep;  // S.tick advances by K in the epilogue
@@ -352,7 +334,7 @@ __device__ __forceinline__ int ca_tile_body(TileSmem& sm, const gca_params& P, c
   // ---- write the new grid, burn-out ticks, counts -------------------------------------------------
   const TfKey ka1 = tf_key(sc[SC_AK10], sc[SC_AK11]), ka2 = tf_key(sc[SC_AK20], sc[SC_AK21]);
   const TfKey kg = tf_key(sc[SC_GROW0], sc[SC_GROW1]);
-  int nt = 0, nfire = 0, nabs = 0;
+  int nt = 0, nfire = 0;
   uint32_t n_ign = 0, n_ext = 0;
   const bool dense_rule = P.p_tree > 0.0f;  // regrowth draws for every empty cell: the per-cell loop
   const int lc = tid & 63, rg = tid >> 6;
@@ -366,7 +348,6 @@ __device__ __forceinline__ int ca_tile_body(TileSmem& sm, const gca_params& P, c
       const unsigned long long lo = fr[0] | ((unsigned long long)fr[1] << 32), hi = fr[2] | ((unsigned long long)fr[3] << 32);
       unsigned long long fire = (lo >> T_HC) | (hi << (64 - T_HC));
       unsigned long long ig = sm.ign[lr];
-      nabs = __popcll(fire);
       const int n = __popcll(fire) + __popcll(ig);
       if (n) {
         int idx = atomicAdd(&sm.nlist2, n);
@@ -405,7 +386,6 @@ __device__ __forceinline__ int ca_tile_body(TileSmem& sm, const gca_params& P, c
     }
     nt = -(int)n_ign;
     nfire = (int)n_ign - (int)n_ext;
-    nabs += nfire;
     __syncthreads();
     if ((W & 15) == 0) {
       if (tid < T_TH * 4) {
@@ -462,18 +442,15 @@ __device__ __forceinline__ int ca_tile_body(TileSmem& sm, const gca_params& P, c
       }
     }
     cell_out[env_off + gcell] = (uint8_t)nw;
-    nabs += (nw == 2);
     nt += (nw == 1) - (old == 1);     // change of the env's tree / fire counts
     nfire += (nw == 2) - (old == 2);
   }
   }
   nt = __reduce_add_sync(GCA_FULL, nt);
   nfire = __reduce_add_sync(GCA_FULL, nfire);
-  nabs = __reduce_add_sync(GCA_FULL, nabs);
   if (lane == 0) {
     if (nt) atomicAdd(&sm.cnt_tree, nt);
     if (nfire) atomicAdd(&sm.cnt_fire, nfire);
-    if (nabs) atomicAdd(&sm.fire_abs, nabs);
   }
   if (stats != nullptr) {
     const uint32_t a = __reduce_add_sync(GCA_FULL, n_draws), b = __reduce_add_sync(GCA_FULL, n_ign);
@@ -486,14 +463,11 @@ __device__ __forceinline__ int ca_tile_body(TileSmem& sm, const gca_params& P, c
     }
   }
   __syncthreads();
-  int fire_after = 0;
   if (tid == 0) {
     if (sm.cnt_tree) atomicAdd(&counts[2 * e], sm.cnt_tree);
     if (sm.cnt_fire) atomicAdd(&counts[2 * e + 1], sm.cnt_fire);
     if (stats != nullptr && nfront) atomicAdd(&stats[0], (unsigned long long)nfront);
-    fire_after = sm.fire_abs;
   }
-  return fire_after;
 }
 
 // The tile list of an env step (built once, from the fire counts at its start).  A burning cell moves at most one cell

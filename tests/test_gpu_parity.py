@@ -1126,3 +1126,35 @@ def test_reset_frame_reference_mode(cuda_device, tag, mode):
     want = rgb.astype(np.uint8) if mode == "rgb_u8" else rgb
     assert frames["reference"].dtype == want.dtype and np.array_equal(frames["reference"], want)
     assert not np.array_equal(frames["true_grid"], want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [3, 4])
+def test_tiled_fused_auto_reset_matches_two_call_path(cuda_device, K):
+    """The tiled path (a 96 x 80 grid: 3 x 2 tiles, the last ones partial; odd K ends in the scratch grid and is copied
+    back) with the fused conditional_reset as a node of the step's CUDA graph == stateless_step followed by
+    conditional_reset, state by state, while envs terminate and restart."""
+    from parity_util import make_pair, random_actions, sync, read_cuda_state
+    N = 5
+    envs = []
+    for fused in (False, True):
+        env, co, E, state, info = make_pair(N=N, size=96, ncols=80, K=K, mode="legacy", use_hidden=True, seed=21,
+                                            fast_slope=True)
+        ctx = state["per_env_context"]
+        ctx["fire_age"][ctx["true_grid"] == 2] = np.float32(3)
+        sync(env, state, as_snapshot=True)
+        envs.append(env)
+    rng = np.random.default_rng(6)
+    seen_done = 0
+    for step in range(10):
+        act = random_actions(rng, N)
+        a = torch.as_tensor(act, device="cuda")
+        tup = envs[0].stateless_step(act)
+        seen_done += int(tup[2].sum())
+        tup = envs[0].conditional_reset(tup, act)
+        out = envs[1].step_device(a, auto_reset=True)
+        s0, s1 = read_cuda_state(envs[0]), read_cuda_state(envs[1])
+        for k in s0:
+            assert np.array_equal(s0[k], s1[k]), (step, k)
+        assert np.array_equal(tup[1].cpu().numpy(), out.reward.cpu().numpy())
+    assert seen_done > 0

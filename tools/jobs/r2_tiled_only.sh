@@ -1,6 +1,6 @@
 #!/bin/bash
 export GCA_SKIP_VERSION_CHECK=1 GCA_LIB_PATH=build/variants/cur.so
-timeout 900 python -m pytest tests -x -q -m gpu -k "tiled_parity or large_single or injected_uniforms_128 or other_widths or many_envs or partitionable_hidden_off" 2>&1 | tail -3
+timeout 900 python -m pytest tests -x -q -m gpu -k "tiled or large_single or injected_uniforms_128 or other_widths or many_envs or conditional_reset or env_api_surface" 2>&1 | tail -4
 timeout 300 python bench.py --size 4096 --envs-per-gpu 1 --hidden device --steps 24 --warmup 24 --preroll 0 --no-cpu-baseline --no-obs-leg --no-other-configs --long-run 0 > gpurun_out/t4096_1.json 2> gpurun_out/t4096_1.err
 python - <<PY
 import json
