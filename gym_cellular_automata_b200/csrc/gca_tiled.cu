@@ -591,7 +591,8 @@ __device__ __forceinline__ void tiled_sched_warp(const gca_params& P, const gca_
 
 // ---------------------------------------------------------------------------------------------
 // tile activity (see the head of the file)
-//   tile index t = (e * TY + ty) * TX + tx;  fire[t] u32;  list[] u32;  nactive[j] = entries of sub-step j's list
+//   tile index t = (e * TY + ty) * TX + tx;  hasfire: bit t & 31 of word t >> 5;  list[] u32 (| T_COPY_ONLY);
+//   nactive[0] = entries of the step's list
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tile_count_kernel(gca_params P, gca_state S, gca_inject J, uint32_t* sched, int TX,
                                                          int TY, uint32_t* __restrict__ hasfire, int32_t* __restrict__ counts) {
