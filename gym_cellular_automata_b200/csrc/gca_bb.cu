@@ -9,11 +9,13 @@
 // advanced_bulldozer.py:332-399,1103-1133).  What differs from the tiled kernel:
 //   * tree / fire / doused masks are 64-bit words per 64 cells of a row (H * W / 8 bytes per mask: 8 KB at 256x256),
 //     built from the u8 grid with 128-bit loads at the start of the step and written back as bytes at its end;
-//   * the front (tree with a burning Moore neighbour) is three shifted ORs per word; front cells are compacted into a
-//     CTA-wide list and processed one per thread: the (2R+1)^2 heat window is cut out of the fire rows as 2R+1 bit
-//     fields, ring populations by popc -- ~250 instructions where the byte version walks 169 cells;
-//   * burn-outs: once per sub-step the burn-out ticks of the words that hold fire are checked 64 cells at a time
-//     (eight 128-bit loads);
+//   * the front (tree with a burning Moore neighbour) is three shifted ORs per word -- skipped for words whose three
+//     rows hold no fire (per-row flags) --; front cells are compacted into a CTA-wide list and worked on in rounds of
+//     256: a thread per cell cuts the (2R+1)^2 heat window out of the fire rows as 2R+1 bit fields (ring populations by
+//     popc, ~250 instructions where the byte version walks 169 cells) and lists the cell's burning directions, then the
+//     (cell, direction) draws are dealt one per thread over the CTA;
+//   * burn-outs: once per ENV STEP the burn-out ticks of the words that hold fire are checked 64 cells at a time
+//     (eight 128-bit loads); cells due inside the step go on a burn list with their sub-step;
 //   * key schedule (jax.random.split chain of the K sub-steps), clock, move, douse, day/night, reward, done and the
 //     info counters are part of the same launch.
 #include "gca_common.cuh"
